@@ -1,0 +1,196 @@
+/* ivx.h — C ABI of libivx.so, the B200 (sm_100a) implementation of IV_INTERPOLATION's hot path.
+ *
+ * The reference (liu-wei2021/IV_INTERPOLATION) is pure Python and has no FFI; the seam this
+ * library sits behind is the pair of classes the reference's batch drivers construct
+ * (reference src/interpolation/batch_processor.py:21-24,97 and
+ * src/candle_reconstruction/core.py:180,229-248).  Each entry point names the reference code
+ * it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative IVX_ERR_* code; nothing throws;
+ *     ivx_last_error_string() describes the last failure on the calling thread;
+ *   - all array arguments are DEVICE pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()); the library allocates nothing and synchronises nothing: work is enqueued
+ *     on `stream` (a cudaStream_t, may be NULL for the legacy default stream);
+ *   - scratch memory is passed in explicitly (`workspace`), sized by the *_workspace_bytes call;
+ *   - timestamps are int64 ticks in the caller's datetime64 unit; NaT is INT64_MIN and is ignored;
+ *   - rows of one symbol are contiguous (CSR offsets, int64) and sorted by timestamp ascending.
+ */
+#ifndef IVX_H_
+#define IVX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVX_VERSION 100
+
+/* error codes */
+#define IVX_OK 0
+#define IVX_ERR_INVALID_ARG (-1)
+#define IVX_ERR_CUDA (-2)
+#define IVX_ERR_TOO_LARGE (-3)
+#define IVX_ERR_UNSUPPORTED (-4)
+
+/* per-symbol status (uint8): why the reference would have returned None */
+#define IVX_SYM_OK 0
+#define IVX_SYM_TOO_FEW 1    /* interpolation/core.py:26-28, candle_reconstruction/core.py:47-49,64-66 */
+#define IVX_SYM_SPAN 2       /* interpolation/core.py:36-39: max-min > 30 days */
+#define IVX_SYM_TOO_LONG 3   /* interpolation/core.py:49-51: > 100000 grid points */
+#define IVX_SYM_EMPTY_OUT 4  /* interpolation/core.py:76-78: nothing left after dropna */
+#define IVX_SYM_NO_DATES 5   /* every date is NaT: date_range raises -> core.py:83-85 */
+
+/* per-symbol flag bits (uint32) */
+#define IVX_FLAG_IN_BAD_OHLC 1u     /* candle core.py:115-124 on the input rows */
+#define IVX_FLAG_IN_NEG_VOLUME 2u   /* candle core.py:127-130 */
+#define IVX_FLAG_IN_NAN 4u          /* candle core.py:133-137 */
+#define IVX_FLAG_OUT_BAD_OHLC 8u    /* same three checks on the emitted candles (core.py:239) */
+#define IVX_FLAG_OUT_NEG_VOLUME 16u
+#define IVX_FLAG_OUT_NAN 32u
+#define IVX_FLAG_UNSORTED 64u       /* timestamps decrease inside the symbol: result undefined */
+#define IVX_FLAG_NONFINITE 128u     /* +-inf among the interpolated columns: dropna may cut interior rows */
+
+#define IVX_MAX_FILL_COLS 8
+#define IVX_MAX_IDX_COLS 4
+
+typedef void* ivx_stream_t; /* cudaStream_t */
+
+int ivx_version(void);
+const char* ivx_last_error_string(void);
+/* name of every exported kernel family compiled into the library, comma separated */
+const char* ivx_build_info(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel B — OHLCV bucket reduction.
+ * Replaces CandleReconstructor.reconstruct_symbol_candles (candle_reconstruction/core.py:59-89)
+ * and CompleteOptimizedPipeline._aggregate_to_5min (complete_pipeline.py:685-710), for a whole
+ * CSR batch of symbols in one launch, plus validate_candle_data (core.py:108-144) as flag bits.
+ *
+ *   bucket      = floor(ts / bucket_ticks)                      (epoch anchored, core.py:70)
+ *   open/close  = first/last non-NaN in row order; high/low = NaN-skipping max/min
+ *   volume      = Kahan-compensated sum in row order, NaN skipped, all-NaN -> 0.0 (pandas group_sum)
+ *   a bucket is emitted iff its raw row count >= min_count       (core.py:87-89)
+ *   check_len != 0: a symbol with fewer than min_count rows emits nothing and gets
+ *                   IVX_SYM_TOO_FEW (core.py:64-66); empty symbols always do (core.py:47-49).
+ *
+ * Outputs are compacted, symbol-major, time order.  capacity = length of the o_* arrays;
+ * n_rows is an upper bound on the candle count.  o_sym_row / o_group / sym_group_off /
+ * sym_flags / sym_valid may be NULL.
+ *   out_off[n_sym+1]    CSR offsets of the emitted candles
+ *   o_sym_row[i]        global row index of the first row with a non-null symbol in the bucket
+ *                       (-1 if none) — the 'symbol':'first' aggregate, core.py:79
+ *   o_group[i]          rank of the bucket among ALL buckets of the batch; minus
+ *                       sym_group_off[s] it is the (not reset) index pandas returns
+ *   total[0]            number of candles written (device int64)
+ * ------------------------------------------------------------------------------------------- */
+int64_t ivx_ohlcv_workspace_bytes(int64_t n_sym, int64_t n_rows);
+int ivx_ohlcv_reduce(int64_t n_sym, const int64_t* in_off, int64_t n_rows, const int64_t* ts,
+                     const double* open, const double* high, const double* low, const double* close,
+                     const double* volume, const uint8_t* sym_valid, int64_t bucket_ticks,
+                     int32_t min_count, int32_t check_len, int64_t capacity, int64_t* out_off,
+                     int64_t* o_ts, double* o_open, double* o_high, double* o_low, double* o_close,
+                     double* o_volume, int32_t* o_count, int64_t* o_sym_row, int64_t* o_group,
+                     int64_t* sym_group_off, uint8_t* sym_status, uint32_t* sym_flags,
+                     int64_t* total, void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+
+/* Time-major variant for the surface pipeline: x[t*n_series + s], all series share the stamp
+ * ts[t]; one candle per (bucket, series).  Same aggregation rules with value=open=high=low=close
+ * source (the interpolated IV) and no volume: o_*[b*n_series + s].  bucket_of_t[t] (int32,
+ * non-decreasing, dense from 0) and n_buckets come from ivx_time_buckets.  Buckets with fewer
+ * than min_count stamps are written as NaN with o_count = their count. */
+int ivx_time_buckets(int64_t n_t, const int64_t* ts, int64_t bucket_ticks, int32_t* bucket_of_t,
+                     int64_t* bucket_ts, int32_t* bucket_start, int64_t* n_buckets, ivx_stream_t stream);
+int ivx_ohlc_time_major(int64_t n_t, int64_t n_series, const double* x, int64_t n_buckets,
+                        const int32_t* bucket_start, int32_t min_count, double* o_open, double* o_high,
+                        double* o_low, double* o_close, int32_t* o_count, ivx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel A — per-contract time-linear interpolation + forward fill.
+ * Replaces IVInterpolator.interpolate_symbol (interpolation/core.py:26-81) for a CSR batch.
+ *
+ * Step 1, ivx_interp_plan: guards (core.py:26-28,36-39,49-51), the minute grid anchored at
+ *   min(date) (core.py:42-46), the left join (core.py:54-55; off-grid rows vanish, duplicate
+ *   stamps widen the position axis), per-column bracketing knots and forward-fill sources,
+ *   and the dropna cut (core.py:74).  Writes sym_status, sym_flags and out_count[n_sym]
+ *   (rows each contract will emit) and out_off[n_sym+1] (their exclusive scan; out_off[n_sym]
+ *   is the total, a device int64 the caller reads to size the outputs).
+ * Step 2, ivx_interp_exec: writes the output rows, contract-major:
+ *   o_ts       int64   grid stamp
+ *   o_interp   3 x f64 iv, underlying_price, time_to_maturity:  y = slope*(p-p0) + y0 evaluated
+ *              as a separate multiply and add, with np.interp's NaN fallbacks (bit-equal to pandas)
+ *   o_fill     n_fill x f64: last non-NaN observation carried forward, column by column
+ *   o_idx      n_idx x i32: global source-row index carried forward for string columns whose
+ *              non-null mask is idx_valid[k] (NULL mask = all valid); -1 = none yet
+ *   o_src_row  i32: global source row sitting exactly on this grid point, else -1
+ *   o_pos      i32: position on the contract's merged axis (the index pandas leaves after dropna)
+ *   o_keep     u8 : 1 where dropna keeps the row (all 1 unless IVX_FLAG_NONFINITE)
+ *   Any of o_fill/o_idx/o_src_row/o_pos/o_keep/o_is_interpolated may be NULL.
+ *   o_is_interpolated (u8) is written as 0: core.py:71 tests `symbol` after the forward fill.
+ * idx_valid[0] is the `symbol` column's mask and takes part in dropna (core.py:74).
+ * ------------------------------------------------------------------------------------------- */
+int64_t ivx_interp_workspace_bytes(int64_t n_sym, int64_t n_src, int32_t n_fill, int32_t n_idx);
+int ivx_interp_plan(int64_t n_sym, const int64_t* src_off, int64_t n_src, const int64_t* src_ts,
+                    const double* const* interp_cols /*3, host array of device ptrs*/,
+                    int32_t n_fill, const double* const* fill_cols,
+                    int32_t n_idx, const uint8_t* const* idx_valid,
+                    int64_t step_ticks, int64_t max_span_ticks, int64_t max_grid_points,
+                    int32_t min_points, int64_t* out_count, int64_t* out_off, uint8_t* sym_status,
+                    uint32_t* sym_flags, void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+int ivx_interp_exec(int64_t n_sym, const int64_t* src_off, int64_t n_src, const int64_t* out_off,
+                    int64_t n_out, int64_t step_ticks, int32_t n_fill, int32_t n_idx,
+                    int64_t* o_ts, double* const* o_interp /*3*/, double* const* o_fill,
+                    int32_t* const* o_idx, int32_t* o_src_row, int32_t* o_pos, uint8_t* o_keep,
+                    uint8_t* o_is_interpolated, const void* workspace, int64_t workspace_bytes,
+                    ivx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel C — Black-Scholes implied volatility, one thread per quote (north_star kernel 1; the
+ * reference has no solver, its conventions come from interpolation/greeks.py:21-22: continuous
+ * rate r, no dividend, T in years).  sigma[i] = NaN outside the invertible domain
+ * (non-finite/non-positive inputs, or price not strictly inside the no-arbitrage bounds).
+ * iters may be NULL.  ivx_bs_price is the forward pricer (used to build synthetic tapes),
+ * ivx_bs_greeks the Greeks of greeks.py:24-35 (put rho keeps the reference's sign when
+ * reference_put_rho_sign != 0).
+ * ------------------------------------------------------------------------------------------- */
+int ivx_bs_implied_vol(int64_t n, const double* price, const double* S, const double* K,
+                       const double* T, const double* r, const uint8_t* is_call, double* sigma,
+                       int32_t* iters, ivx_stream_t stream);
+int ivx_bs_price(int64_t n, const double* S, const double* K, const double* T, const double* r,
+                 const double* sigma, const uint8_t* is_call, double* price, ivx_stream_t stream);
+int ivx_bs_greeks(int64_t n, const double* S, const double* K, const double* T, const double* r,
+                  const double* sigma, const uint8_t* is_call, int32_t reference_put_rho_sign,
+                  double* delta, double* gamma, double* theta, double* vega, double* rho,
+                  ivx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel D — batched natural cubic spline fit + evaluation (north_star kernel 2; no reference
+ * code).  Slice i has knots x/y[knot_off[i]:knot_off[i+1]] (x strictly increasing; knots whose
+ * x or y is not finite are skipped) and is evaluated at the n_q shared abscissae xq (ascending):
+ * yq[i*n_q + j].  extrap: 0 NaN outside the knots, 1 continue the end cubic, 2 clamp flat.
+ * Fewer than 2 usable knots -> NaN row; exactly 2 -> the straight line.
+ * ivx_spline_strided solves many small systems laid out [knot][system] (system index
+ * contiguous): used for the maturity direction of the surface.
+ * ------------------------------------------------------------------------------------------- */
+int64_t ivx_spline_workspace_bytes(int64_t n_slices, int64_t n_knots_total);
+int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots,
+                        const double* x, const double* y, int64_t n_q, const double* xq,
+                        int32_t extrap, double* yq, void* workspace, int64_t workspace_bytes,
+                        ivx_stream_t stream);
+int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
+                       const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
+                       int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Utilities: exclusive scan of int64, stream-copy and fp64-FMA microbenchmarks that give the
+ * roofline denominators measured in the same run (bench.py).
+ * ------------------------------------------------------------------------------------------- */
+int ivx_exclusive_scan_i64(int64_t n, const int64_t* in, int64_t* out /*n+1*/, ivx_stream_t stream);
+int ivx_probe_copy(int64_t n_f64, const double* src, double* dst, ivx_stream_t stream);
+int ivx_probe_fp64_fma(int64_t n_threads, int32_t iters, double* sink, ivx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVX_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of libivx.so (the C ABI declared in include/ivx.h).
+
+There is NO fallback: if the shared library is missing this module raises, and every compute
+entry point of the package goes through it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libivx.so")
+
+# error / status codes (include/ivx.h)
+IVX_OK = 0
+SYM_OK, SYM_TOO_FEW, SYM_SPAN, SYM_TOO_LONG, SYM_EMPTY_OUT, SYM_NO_DATES = 0, 1, 2, 3, 4, 5
+FLAG_IN_BAD_OHLC, FLAG_IN_NEG_VOLUME, FLAG_IN_NAN = 1, 2, 4
+FLAG_OUT_BAD_OHLC, FLAG_OUT_NEG_VOLUME, FLAG_OUT_NAN = 8, 16, 32
+FLAG_UNSORTED, FLAG_NONFINITE = 64, 128
+MAX_FILL_COLS, MAX_IDX_COLS = 8, 4
+
+
+class IvxError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+_i64, _i32, _p = C.c_int64, C.c_int32, C.c_void_p
+_pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/ivx.h one to one
+SIGNATURES = {
+    "ivx_version": (C.c_int, []),
+    "ivx_last_error_string": (C.c_char_p, []),
+    "ivx_build_info": (C.c_char_p, []),
+    "ivx_ohlcv_workspace_bytes": (_i64, [_i64, _i64]),
+    "ivx_ohlcv_reduce": (C.c_int, [_i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i64, _p,
+                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "ivx_time_buckets": (C.c_int, [_i64, _p, _i64, _p, _p, _p, _p, _p]),
+    "ivx_ohlc_time_major": (C.c_int, [_i64, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "ivx_interp_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),
+    "ivx_interp_plan": (C.c_int, [_i64, _p, _i64, _p, _pp, _i32, _pp, _i32, _pp, _i64, _i64, _i64, _i32,
+                                  _p, _p, _p, _p, _p, _i64, _p]),
+    "ivx_interp_exec": (C.c_int, [_i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _pp, _pp, _pp, _p, _p, _p,
+                                  _p, _p, _i64, _p]),
+    "ivx_bs_implied_vol": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ivx_bs_price": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ivx_bs_greeks": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "ivx_spline_workspace_bytes": (_i64, [_i64, _i64]),
+    "ivx_spline_fit_eval": (C.c_int, [_i64, _p, _i64, _p, _p, _i64, _p, _i32, _p, _p, _i64, _p]),
+    "ivx_spline_strided": (C.c_int, [_i64, _i32, _p, _p, _i32, _p, _i32, _p, _p]),
+    "ivx_exclusive_scan_i64": (C.c_int, [_i64, _p, _p, _p]),
+    "ivx_probe_copy": (C.c_int, [_i64, _p, _p, _p]),
+    "ivx_probe_fp64_fma": (C.c_int, [_i64, _i32, _p, _p]),
+    "ivx_host_floor_div": (_i64, [_i64, _i64]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libivx.so once.  Raises IvxError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise IvxError(
+                f"{LIB_PATH} is missing: build it with `make -C iv_interpolation_b200/csrc` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().ivx_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != IVX_OK:
+        raise IvxError(f"{what or 'libivx'} failed with code {rc}: {last_error()}")
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers (``const double* const*`` arguments)."""
+    arr = (C.c_void_p * max(1, len(ptrs)))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr

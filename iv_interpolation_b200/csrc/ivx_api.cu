@@ -1,0 +1,50 @@
+// ivx_api.cu — error plumbing and library identification for libivx.so.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ivx_common.cuh"
+
+namespace ivx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return IVX_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;  // B200
+  }
+  return cached;
+}
+
+}  // namespace ivx
+
+extern "C" int ivx_version(void) { return IVX_VERSION; }
+extern "C" const char* ivx_last_error_string(void) { return ivx::g_err; }
+extern "C" const char* ivx_build_info(void) {
+  return "libivx sm_100a: k_interp_plan,k_interp_exec,k_scan_i64,k_ohlcv_reduce,k_ohlcv_finalize,k_time_buckets,"
+         "k_ohlc_time_major,k_bs_implied_vol,k_bs_price,k_bs_greeks,k_spline_fit_eval,k_spline_strided,"
+         "k_probe_copy,k_probe_fp64";
+}
+
+// host-side check of the multiply-high floor division used by the bucket kernels (tests call this)
+extern "C" int64_t ivx_host_floor_div(int64_t t, int64_t d) {
+  if (d < 1) return 0;
+  ivx::FloorDiv f = ivx::make_floor_div(d);
+  return ivx::floor_div(t, f);
+}

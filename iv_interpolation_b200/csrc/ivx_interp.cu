@@ -1,0 +1,499 @@
+// ivx_interp.cu — kernel A: per-contract time-linear interpolation + forward fill.
+//
+// Replaces reference src/interpolation/core.py:26-81 for a CSR batch of contracts.
+//   plan  (one warp per contract, reads only the SOURCE rows — ~60x fewer than the output):
+//         guards, minute grid anchored at min(date), left-join positions (off-grid rows vanish,
+//         duplicate stamps widen the axis), and for every on-grid source row the parameters of
+//         the interval that starts there: per interpolated column the bracketing valid knots
+//         (x0,y0,x1,y1,slope), per fill column the carried value / row index.
+//   exec  (tiles of TA_ROWS output rows): each output row finds its interval and evaluates
+//         y = slope*(p-x0) + y0 with a separate multiply and add plus np.interp's NaN fallbacks —
+//         bit-equal to pandas' Series.interpolate('linear') — and streams the row out.
+// HBM traffic: ~81 B written per output row + the (small) interval table read through L1/L2.
+#include "ivx_common.cuh"
+
+namespace ivx {
+namespace {
+
+constexpr int TA_THREADS = 256;
+constexpr int TA_ROWS = 1024;
+constexpr int PLAN_WARPS = 8;
+
+struct InterpWs {
+  // per compacted on-grid source row
+  int32_t* gpos;
+  int64_t* gts;
+  int32_t* grow;
+  double* y0[3];
+  double* y1[3];
+  double* slope[3];
+  int32_t* x0[3];
+  int32_t* x1[3];
+  double* fval[IVX_MAX_FILL_COLS];
+  int32_t* fidx[IVX_MAX_IDX_COLS];
+  // per contract
+  int32_t* n_on;
+  int32_t* p0;
+  int64_t* tile_count;
+  int64_t* tile_off;  // n_sym + 1
+};
+
+InterpWs carve(void* ws, int64_t bytes, int64_t n_sym, int64_t n_src, int n_fill, int n_idx, bool* ok) {
+  Carver cv(ws, bytes);
+  InterpWs W;
+  W.gpos = cv.take<int32_t>(n_src);
+  W.gts = cv.take<int64_t>(n_src);
+  W.grow = cv.take<int32_t>(n_src);
+  for (int c = 0; c < 3; ++c) {
+    W.y0[c] = cv.take<double>(n_src);
+    W.y1[c] = cv.take<double>(n_src);
+    W.slope[c] = cv.take<double>(n_src);
+    W.x0[c] = cv.take<int32_t>(n_src);
+    W.x1[c] = cv.take<int32_t>(n_src);
+  }
+  for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) W.fval[k] = k < n_fill ? cv.take<double>(n_src) : nullptr;
+  for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) W.fidx[k] = k < n_idx ? cv.take<int32_t>(n_src) : nullptr;
+  W.n_on = cv.take<int32_t>(n_sym);
+  W.p0 = cv.take<int32_t>(n_sym);
+  W.tile_count = cv.take<int64_t>(n_sym + 1);
+  W.tile_off = cv.take<int64_t>(n_sym + 2);
+  *ok = cv.ok();
+  return W;
+}
+
+struct PlanParams {
+  int64_t n_sym;
+  const int64_t* src_off;
+  const int64_t* ts;
+  const double* icol[3];
+  const double* fcol[IVX_MAX_FILL_COLS];
+  const uint8_t* ivalid[IVX_MAX_IDX_COLS];
+  int32_t n_fill, n_idx;
+  int64_t step, max_span, max_pts;
+  int32_t min_pts;
+  int64_t* out_count;
+  uint8_t* sym_status;
+  uint32_t* sym_flags;
+  InterpWs W;
+};
+
+__device__ __forceinline__ int highest_bit_le(uint32_t m, int lane) {  // highest set bit at or below lane, -1 if none
+  uint32_t mm = m & (0xffffffffu >> (31 - lane));
+  return mm ? 31 - __clz(mm) : -1;
+}
+__device__ __forceinline__ int lowest_bit_gt(uint32_t m, int lane) {   // lowest set bit strictly above lane, -1 if none
+  uint32_t mm = (lane == 31) ? 0u : (m & (0xffffffffu << (lane + 1)));
+  return mm ? __ffs(mm) - 1 : -1;
+}
+
+__global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = blockIdx.x * (int64_t)PLAN_WARPS + (threadIdx.x >> 5);
+  if (s >= P.n_sym) return;
+  const int64_t a = P.src_off[s], b = P.src_off[s + 1];
+  const int64_t n = b - a;
+  const InterpWs& W = P.W;
+
+  auto finish = [&](uint8_t status, int64_t count, int32_t n_on, int32_t p0, uint32_t flags) {
+    if (lane == 0) {
+      P.sym_status[s] = status;
+      P.out_count[s] = count;
+      W.n_on[s] = n_on;
+      W.p0[s] = p0;
+      W.tile_count[s] = (count + TA_ROWS - 1) / TA_ROWS;
+      if (P.sym_flags) P.sym_flags[s] = flags;
+    }
+  };
+
+  if (n < P.min_pts) { finish(IVX_SYM_TOO_FEW, 0, 0, 0, 0); return; }        // core.py:26-28
+
+  // ---- span (NaT ignored, like Series.min/max) ----------------------------------------------------
+  int64_t tmin = INT64_MAX, tmax = INT64_MIN;
+  uint32_t flags = 0;
+  int64_t prev_last = IVX_NAT;
+  for (int64_t base = a; base < b; base += 32) {
+    int64_t r = base + lane;
+    int64_t t = (r < b) ? P.ts[r] : IVX_NAT;
+    if (t != IVX_NAT) { tmin = min(tmin, t); tmax = max(tmax, t); }
+    int64_t tp = __shfl_up_sync(IVX_FULL_MASK, t, 1);
+    if (lane == 0) tp = prev_last;
+    if (t != IVX_NAT && tp != IVX_NAT && t < tp) flags |= IVX_FLAG_UNSORTED;
+    prev_last = __shfl_sync(IVX_FULL_MASK, t, 31);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    tmin = min(tmin, __shfl_xor_sync(IVX_FULL_MASK, tmin, d));
+    tmax = max(tmax, __shfl_xor_sync(IVX_FULL_MASK, tmax, d));
+    flags |= __shfl_xor_sync(IVX_FULL_MASK, flags, d);
+  }
+  if (tmax == INT64_MIN) { finish(IVX_SYM_NO_DATES, 0, 0, 0, flags); return; }
+  const int64_t span = tmax - tmin;
+  if (span > P.max_span) { finish(IVX_SYM_SPAN, 0, 0, 0, flags); return; }     // core.py:36-39
+  const int64_t n_grid = span / P.step + 1;                                     // core.py:42-46
+  if (n_grid > P.max_pts) { finish(IVX_SYM_TOO_LONG, 0, 0, 0, flags); return; } // core.py:49-51
+
+  // ---- forward sweep: positions and carried-forward state ------------------------------------------
+  int32_t carry_on = 0, carry_dups = 0;
+  int64_t carry_k = -1;
+  int32_t cpos[3] = {-1, -1, -1};
+  double cval[3] = {0, 0, 0};
+  int32_t first_pos[3] = {INT32_MAX, INT32_MAX, INT32_MAX};
+  double cfill[IVX_MAX_FILL_COLS];
+  int32_t cidx[IVX_MAX_IDX_COLS];
+  int32_t first_sym_pos = INT32_MAX;
+#pragma unroll
+  for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) cfill[k] = qnan();
+#pragma unroll
+  for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) cidx[k] = -1;
+
+  for (int64_t base = a; base < b; base += 32) {
+    const int64_t r = base + lane;
+    const bool inr = r < b;
+    const int64_t t = inr ? P.ts[r] : IVX_NAT;
+    int64_t k = -2;
+    bool on = false;
+    if (t != IVX_NAT) {
+      int64_t off = t - tmin;
+      int64_t q = off / P.step;
+      on = (q * P.step == off);                                   // core.py:54-55 left join on equality
+      k = q;
+    }
+    const uint32_t m_on = __ballot_sync(IVX_FULL_MASK, on);
+    // k of the previous on-grid row
+    int src = highest_bit_le(m_on & ~(1u << lane), lane);
+    int64_t kprev = __shfl_sync(IVX_FULL_MASK, k, src < 0 ? 0 : src);
+    if (src < 0) kprev = carry_k;
+    const bool dup = on && (k == kprev);
+    const uint32_t m_dup = __ballot_sync(IVX_FULL_MASK, dup);
+    const uint32_t le = 0xffffffffu >> (31 - lane);
+    const int32_t pos = (int32_t)k + carry_dups + __popc(m_dup & le);
+    const int64_t g = a + carry_on + __popc(m_on & (le >> 1));
+    if (on) { W.gpos[g] = pos; W.gts[g] = t; W.grow[g] = (int32_t)r; }
+
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double v = inr ? P.icol[c][r] : qnan();
+      const bool valid = on && !isnan(v);
+      if (valid && isinf(v)) flags |= IVX_FLAG_NONFINITE;
+      const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
+      const int sl = highest_bit_le(m_v, lane);
+      int32_t ppos = __shfl_sync(IVX_FULL_MASK, pos, sl < 0 ? 0 : sl);
+      double pval = __shfl_sync(IVX_FULL_MASK, v, sl < 0 ? 0 : sl);
+      if (sl < 0) { ppos = cpos[c]; pval = cval[c]; }
+      if (on) { W.x0[c][g] = ppos; W.y0[c][g] = pval; }
+      if (m_v) {
+        const int last = 31 - __clz(m_v);
+        if (first_pos[c] == INT32_MAX) first_pos[c] = __shfl_sync(IVX_FULL_MASK, pos, __ffs(m_v) - 1);
+        cpos[c] = __shfl_sync(IVX_FULL_MASK, pos, last);
+        cval[c] = __shfl_sync(IVX_FULL_MASK, v, last);
+      }
+    }
+#pragma unroll
+    for (int kf = 0; kf < IVX_MAX_FILL_COLS; ++kf) {
+      if (kf < P.n_fill) {
+        const double v = inr ? P.fcol[kf][r] : qnan();
+        const bool valid = on && !isnan(v);
+        const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
+        const int sl = highest_bit_le(m_v, lane);
+        double pval = __shfl_sync(IVX_FULL_MASK, v, sl < 0 ? 0 : sl);
+        if (sl < 0) pval = cfill[kf];
+        if (on) W.fval[kf][g] = pval;
+        if (m_v) cfill[kf] = __shfl_sync(IVX_FULL_MASK, v, 31 - __clz(m_v));
+      }
+    }
+#pragma unroll
+    for (int ki = 0; ki < IVX_MAX_IDX_COLS; ++ki) {
+      if (ki < P.n_idx) {
+        const bool valid = on && (P.ivalid[ki] ? (P.ivalid[ki][r] != 0) : true);
+        const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
+        const int sl = highest_bit_le(m_v, lane);
+        int32_t pidx = __shfl_sync(IVX_FULL_MASK, (int32_t)r, sl < 0 ? 0 : sl);
+        if (sl < 0) pidx = cidx[ki];
+        if (on) W.fidx[ki][g] = pidx;
+        if (m_v) {
+          if (ki == 0 && first_sym_pos == INT32_MAX) first_sym_pos = __shfl_sync(IVX_FULL_MASK, pos, __ffs(m_v) - 1);
+          cidx[ki] = __shfl_sync(IVX_FULL_MASK, (int32_t)r, 31 - __clz(m_v));
+        }
+      }
+    }
+    if (m_on) carry_k = __shfl_sync(IVX_FULL_MASK, k, 31 - __clz(m_on));
+    carry_on += __popc(m_on);
+    carry_dups += __popc(m_dup);
+  }
+  const int32_t n_on = carry_on;
+  const int64_t n_pos = n_grid + carry_dups;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) flags |= __shfl_xor_sync(IVX_FULL_MASK, flags, d);
+
+  // ---- backward sweep: next valid knot of each interpolated column, slopes ----------------------------
+  int32_t npos[3] = {-1, -1, -1};
+  double nval[3] = {0, 0, 0};
+  for (int64_t hi = a + n_on; hi > a; hi -= 32) {
+    const int64_t g = hi - 32 + lane;              // chunk [hi-32, hi), may start before a
+    const bool ing = g >= a;
+    const int32_t pos = ing ? W.gpos[g] : -1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int32_t x0 = ing ? W.x0[c][g] : -1;
+      const double y0 = ing ? W.y0[c][g] : 0.0;
+      const bool valid = ing && (x0 == pos);       // the row's own value is a knot
+      const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
+      const int sl = lowest_bit_gt(m_v, lane);
+      int32_t x1 = __shfl_sync(IVX_FULL_MASK, pos, sl < 0 ? 0 : sl);
+      double y1 = __shfl_sync(IVX_FULL_MASK, y0, sl < 0 ? 0 : sl);
+      if (sl < 0) { x1 = npos[c]; y1 = nval[c]; }
+      if (ing) {
+        W.x1[c][g] = x1;
+        W.y1[c][g] = y1;
+        double slope = 0.0;
+        if (x0 >= 0 && x1 >= 0) slope = __ddiv_rn(__dsub_rn(y1, y0), (double)(x1 - x0));   // np.interp slope
+        W.slope[c][g] = slope;
+      }
+      if (m_v) {
+        const int first = __ffs(m_v) - 1;
+        npos[c] = __shfl_sync(IVX_FULL_MASK, pos, first);
+        nval[c] = __shfl_sync(IVX_FULL_MASK, y0, first);
+      }
+    }
+  }
+
+  // ---- dropna (core.py:74): rows before the first valid value of any key column go ------------------------
+  int32_t p0 = 0;
+  bool empty = false;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (first_pos[c] == INT32_MAX) empty = true; else p0 = max(p0, first_pos[c]);
+  }
+  if (P.n_idx > 0) {
+    if (first_sym_pos == INT32_MAX) empty = true; else p0 = max(p0, first_sym_pos);
+  }
+  if (empty) { finish(IVX_SYM_EMPTY_OUT, 0, n_on, 0, flags); return; }             // core.py:76-78
+  finish(IVX_SYM_OK, n_pos - p0, n_on, p0, flags);
+}
+
+// single-block exclusive scan (n is a symbol count: at most a few million)
+__global__ void __launch_bounds__(1024) k_scan_i64(int64_t n, const int64_t* __restrict__ in, int64_t* __restrict__ out) {
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    int64_t v = i < n ? in[i] : 0;
+    int64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t u = __shfl_up_sync(IVX_FULL_MASK, incl, d);
+      if (lane >= d) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = s_warp[lane];
+      int64_t wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int64_t u = __shfl_up_sync(IVX_FULL_MASK, wi, d);
+        if (lane >= d) wi += u;
+      }
+      s_warp[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const int64_t carry = s_carry;
+    if (i < n) out[i] = carry + s_warp[warp] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+struct ExecParams {
+  int64_t n_sym;
+  const int64_t* src_off;
+  const int64_t* out_off;
+  int64_t step;
+  int32_t n_fill, n_idx;
+  int64_t* o_ts;
+  double* o_interp[3];
+  double* o_fill[IVX_MAX_FILL_COLS];
+  int32_t* o_idx[IVX_MAX_IDX_COLS];
+  int32_t* o_src_row;
+  int32_t* o_pos;
+  uint8_t* o_keep;
+  uint8_t* o_isint;
+  InterpWs W;
+};
+
+__global__ void __launch_bounds__(TA_THREADS) k_interp_exec(const ExecParams P) {
+  __shared__ int64_t s_sym;
+  const InterpWs& W = P.W;
+  const int64_t tile = blockIdx.x;
+  if (tile >= W.tile_off[P.n_sym]) return;
+  if (threadIdx.x == 0) {
+    int64_t lo = 0, hi = P.n_sym;   // largest s with tile_off[s] <= tile
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (W.tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
+    s_sym = lo;
+  }
+  __syncthreads();
+  const int64_t s = s_sym;
+  const int64_t a = P.src_off[s];
+  const int32_t n_on = W.n_on[s];
+  const int32_t p0 = W.p0[s];
+  const int64_t obase = P.out_off[s];
+  const int64_t count = P.out_off[s + 1] - obase;
+  const int64_t q0 = (tile - W.tile_off[s]) * TA_ROWS;
+  const int32_t* __restrict__ gpos = W.gpos + a;
+
+#pragma unroll 1
+  for (int it = 0; it < TA_ROWS / TA_THREADS; ++it) {
+    const int64_t q = q0 + it * TA_THREADS + threadIdx.x;
+    const bool act = q < count;
+    const int32_t p = p0 + (int32_t)(act ? q : (count - 1));
+    // warp-uniform coarse search for the warp's first position, then a short per-lane search
+    const int32_t pw = __shfl_sync(IVX_FULL_MASK, p, 0);
+    int32_t lo = 0, hi = n_on;      // last g with gpos[g] <= pw ; gpos[0] == 0 <= pw always
+    while (hi - lo > 1) {
+      int32_t mid = (lo + hi) >> 1;
+      if (__ldg(gpos + mid) <= pw) lo = mid; else hi = mid;
+    }
+    int32_t l2 = lo, h2 = min(n_on, lo + 33);
+    while (h2 - l2 > 1) {
+      int32_t mid = (l2 + h2) >> 1;
+      if (__ldg(gpos + mid) <= p) l2 = mid; else h2 = mid;
+    }
+    if (!act) continue;
+    const int64_t g = a + l2;
+    const int32_t gp = __ldg(W.gpos + g);
+    const int64_t o = obase + q;
+    st_stream(P.o_ts + o, __ldg(W.gts + g) + (int64_t)(p - gp) * P.step);
+    bool keep = true;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int32_t x0 = __ldg(W.x0[c] + g);
+      double v;
+      if (x0 < 0) {
+        v = qnan();                                              // leading NaNs are preserved
+      } else {
+        const double y0 = __ldg(W.y0[c] + g);
+        const int32_t x1 = __ldg(W.x1[c] + g);
+        if (x1 < 0 || p == x0) {
+          v = y0;                                                // a knot itself / flat tail
+        } else {
+          const double sl = __ldg(W.slope[c] + g);
+          v = __dadd_rn(__dmul_rn(sl, (double)(p - x0)), y0);    // np.interp: slope*(x-x0)+y0, no FMA
+          if (isnan(v)) {
+            const double y1 = __ldg(W.y1[c] + g);
+            v = __dadd_rn(__dmul_rn(sl, (double)(p - x1)), y1);
+            if (isnan(v) && y0 == y1) v = y0;
+          }
+        }
+      }
+      keep = keep && !isnan(v);
+      st_stream(P.o_interp[c] + o, v);
+    }
+#pragma unroll
+    for (int k = 0; k < IVX_MAX_FILL_COLS; ++k)
+      if (k < P.n_fill && P.o_fill[k]) st_stream(P.o_fill[k] + o, __ldg(W.fval[k] + g));
+#pragma unroll
+    for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) {
+      if (k < P.n_idx) {
+        const int32_t ix = __ldg(W.fidx[k] + g);
+        if (k == 0) keep = keep && ix >= 0;
+        if (P.o_idx[k]) st_stream(P.o_idx[k] + o, ix);
+      }
+    }
+    if (P.o_src_row) st_stream(P.o_src_row + o, p == gp ? __ldg(W.grow + g) : -1);
+    if (P.o_pos) st_stream(P.o_pos + o, p);
+    if (P.o_keep) P.o_keep[o] = keep ? 1 : 0;
+    if (P.o_isint) P.o_isint[o] = 0;                             // core.py:71, always False
+  }
+}
+
+}  // namespace
+}  // namespace ivx
+
+using namespace ivx;
+
+extern "C" int64_t ivx_interp_workspace_bytes(int64_t n_sym, int64_t n_src, int32_t n_fill, int32_t n_idx) {
+  if (n_sym < 0 || n_src < 0 || n_fill < 0 || n_idx < 0) return -1;
+  int64_t per_row = 4 + 8 + 4 + 3 * (8 + 8 + 8 + 4 + 4) + 8 * (int64_t)n_fill + 4 * (int64_t)n_idx;
+  int64_t arrays = 3 + 15 + n_fill + n_idx + 4;
+  return per_row * n_src + (4 + 4 + 8 + 8) * (n_sym + 2) + 256 * (arrays + 2);
+}
+
+extern "C" int ivx_exclusive_scan_i64(int64_t n, const int64_t* in, int64_t* out, ivx_stream_t stream_) {
+  IVX_REQUIRE(n >= 0 && out && (n == 0 || in), IVX_ERR_INVALID_ARG, "ivx_exclusive_scan_i64: bad arguments");
+  k_scan_i64<<<1, 1024, 0, (cudaStream_t)stream_>>>(n, in, out);
+  IVX_LAUNCH_CHECK("k_scan_i64");
+  return IVX_OK;
+}
+
+extern "C" int ivx_interp_plan(int64_t n_sym, const int64_t* src_off, int64_t n_src, const int64_t* src_ts,
+                               const double* const* interp_cols, int32_t n_fill, const double* const* fill_cols,
+                               int32_t n_idx, const uint8_t* const* idx_valid, int64_t step_ticks,
+                               int64_t max_span_ticks, int64_t max_grid_points, int32_t min_points,
+                               int64_t* out_count, int64_t* out_off, uint8_t* sym_status, uint32_t* sym_flags,
+                               void* workspace, int64_t workspace_bytes, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_sym >= 0 && n_src >= 0, IVX_ERR_INVALID_ARG, "ivx_interp_plan: negative size");
+  IVX_REQUIRE(n_src < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_interp_plan: n_src %lld exceeds 2^31 per call; split the batch", (long long)n_src);
+  IVX_REQUIRE(n_fill >= 0 && n_fill <= IVX_MAX_FILL_COLS && n_idx >= 0 && n_idx <= IVX_MAX_IDX_COLS, IVX_ERR_INVALID_ARG, "ivx_interp_plan: n_fill/n_idx out of range");
+  IVX_REQUIRE(step_ticks >= 1 && max_grid_points >= 1 && max_grid_points < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_interp_plan: bad step/max_grid_points");
+  IVX_REQUIRE(src_off && out_count && out_off && sym_status && workspace && interp_cols, IVX_ERR_INVALID_ARG, "ivx_interp_plan: null pointer");
+  IVX_REQUIRE(n_src == 0 || (src_ts && interp_cols[0] && interp_cols[1] && interp_cols[2]), IVX_ERR_INVALID_ARG, "ivx_interp_plan: null input column");
+  IVX_REQUIRE(workspace_bytes >= ivx_interp_workspace_bytes(n_sym, n_src, n_fill, n_idx), IVX_ERR_INVALID_ARG, "ivx_interp_plan: workspace too small");
+  bool ok;
+  PlanParams P;
+  P.W = carve(workspace, workspace_bytes, n_sym, n_src, n_fill, n_idx, &ok);
+  IVX_REQUIRE(ok, IVX_ERR_INVALID_ARG, "ivx_interp_plan: workspace carve overflow");
+  P.n_sym = n_sym; P.src_off = src_off; P.ts = src_ts;
+  for (int c = 0; c < 3; ++c) P.icol[c] = interp_cols[c];
+  for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) P.fcol[k] = k < n_fill ? fill_cols[k] : nullptr;
+  for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) P.ivalid[k] = k < n_idx ? idx_valid[k] : nullptr;
+  for (int k = 0; k < n_fill; ++k) IVX_REQUIRE(n_src == 0 || P.fcol[k], IVX_ERR_INVALID_ARG, "ivx_interp_plan: null fill column %d", k);
+  P.n_fill = n_fill; P.n_idx = n_idx;
+  P.step = step_ticks; P.max_span = max_span_ticks; P.max_pts = max_grid_points; P.min_pts = min_points;
+  P.out_count = out_count; P.sym_status = sym_status; P.sym_flags = sym_flags;
+  if (n_sym > 0) {
+    k_interp_plan<<<(unsigned)((n_sym + PLAN_WARPS - 1) / PLAN_WARPS), PLAN_WARPS * 32, 0, stream>>>(P);
+    IVX_LAUNCH_CHECK("k_interp_plan");
+  }
+  k_scan_i64<<<1, 1024, 0, stream>>>(n_sym, out_count, out_off);
+  IVX_LAUNCH_CHECK("k_scan_i64(out_off)");
+  k_scan_i64<<<1, 1024, 0, stream>>>(n_sym, P.W.tile_count, P.W.tile_off);
+  IVX_LAUNCH_CHECK("k_scan_i64(tile_off)");
+  return IVX_OK;
+}
+
+extern "C" int ivx_interp_exec(int64_t n_sym, const int64_t* src_off, int64_t n_src, const int64_t* out_off,
+                               int64_t n_out, int64_t step_ticks, int32_t n_fill, int32_t n_idx, int64_t* o_ts,
+                               double* const* o_interp, double* const* o_fill, int32_t* const* o_idx,
+                               int32_t* o_src_row, int32_t* o_pos, uint8_t* o_keep, uint8_t* o_is_interpolated,
+                               const void* workspace, int64_t workspace_bytes, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_sym >= 0 && n_src >= 0 && n_out >= 0, IVX_ERR_INVALID_ARG, "ivx_interp_exec: negative size");
+  IVX_REQUIRE(n_fill >= 0 && n_fill <= IVX_MAX_FILL_COLS && n_idx >= 0 && n_idx <= IVX_MAX_IDX_COLS, IVX_ERR_INVALID_ARG, "ivx_interp_exec: n_fill/n_idx out of range");
+  if (n_out == 0 || n_sym == 0) return IVX_OK;
+  IVX_REQUIRE(src_off && out_off && workspace && o_ts && o_interp && o_interp[0] && o_interp[1] && o_interp[2], IVX_ERR_INVALID_ARG, "ivx_interp_exec: null pointer");
+  IVX_REQUIRE(workspace_bytes >= ivx_interp_workspace_bytes(n_sym, n_src, n_fill, n_idx), IVX_ERR_INVALID_ARG, "ivx_interp_exec: workspace too small");
+  bool ok;
+  ExecParams P;
+  P.W = carve(const_cast<void*>(workspace), workspace_bytes, n_sym, n_src, n_fill, n_idx, &ok);
+  P.n_sym = n_sym; P.src_off = src_off; P.out_off = out_off; P.step = step_ticks;
+  P.n_fill = n_fill; P.n_idx = n_idx; P.o_ts = o_ts;
+  for (int c = 0; c < 3; ++c) P.o_interp[c] = o_interp[c];
+  for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) P.o_fill[k] = (k < n_fill && o_fill) ? o_fill[k] : nullptr;
+  for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) P.o_idx[k] = (k < n_idx && o_idx) ? o_idx[k] : nullptr;
+  P.o_src_row = o_src_row; P.o_pos = o_pos; P.o_keep = o_keep; P.o_isint = o_is_interpolated;
+  // upper bound on the tile count known without a device read: ceil per contract <= n_out/TA_ROWS + n_sym
+  const int64_t max_tiles = n_out / TA_ROWS + n_sym + 1;
+  IVX_REQUIRE(max_tiles < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_interp_exec: too many tiles; split the batch");
+  k_interp_exec<<<(unsigned)max_tiles, TA_THREADS, 0, stream>>>(P);
+  IVX_LAUNCH_CHECK("k_interp_exec");
+  return IVX_OK;
+}

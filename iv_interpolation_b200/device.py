@@ -1,0 +1,328 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out, all compute in libivx.so.
+
+PyTorch is plumbing here (device memory, streams); every kernel is a hand-written sm_100a kernel
+reached through the C ABI of include/ivx.h.  Nothing in this module computes on the CPU, and
+nothing falls back: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr_array
+
+_LAUNCHES = 0     # kernels of ours enqueued since the last reset (bench.py reports it)
+
+# kernels each entry point enqueues (memsets are not kernels of ours and are not counted)
+_KERNELS_PER_CALL = {
+    "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
+    "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
+    "scan": 1, "probe": 1,
+}
+
+
+def reset_launch_count() -> None:
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _count(name: str) -> None:
+    global _LAUNCHES
+    _LAUNCHES += _KERNELS_PER_CALL[name]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.IvxError("libivx operators take CUDA tensors (no CPU path exists)")
+    if not t.is_contiguous():
+        raise _lib.IvxError("libivx operators take contiguous tensors")
+    return t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if t.dtype != dtype:
+        raise _lib.IvxError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+def _empty(n: int, dtype: torch.dtype, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(int(n), dtype=dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# Kernel B
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class CandleBatch:
+    out_off: torch.Tensor          # int64[n_sym+1]
+    ts: torch.Tensor               # int64[m] bucket start
+    open: torch.Tensor
+    high: torch.Tensor
+    low: torch.Tensor
+    close: torch.Tensor
+    volume: torch.Tensor
+    count: torch.Tensor            # int32[m] raw rows per candle
+    sym_status: torch.Tensor       # uint8[n_sym]
+    sym_flags: torch.Tensor        # int32[n_sym] (bit flags)
+    sym_row: Optional[torch.Tensor] = None     # int64[m]
+    group: Optional[torch.Tensor] = None       # int64[m]
+    sym_group_off: Optional[torch.Tensor] = None
+    total: int = 0
+
+
+def ohlcv_reduce(in_off: torch.Tensor, ts: torch.Tensor, o: torch.Tensor, h: torch.Tensor, l: torch.Tensor,
+                 c: torch.Tensor, v: torch.Tensor, *, bucket_ticks: int, min_count: int, check_len: bool = True,
+                 sym_valid: Optional[torch.Tensor] = None, want_index: bool = False,
+                 capacity: Optional[int] = None, trim: bool = True) -> CandleBatch:
+    """CSR batch of symbols -> compacted candles (reference candle_reconstruction/core.py:59-89).
+
+    ``trim`` reads the candle count back (one 8-byte D2H sync) and slices the outputs to it.
+    """
+    n_sym = in_off.numel() - 1
+    n_rows = ts.numel()
+    _req(in_off, torch.int64, "in_off"); _req(ts, torch.int64, "ts")
+    for name, t in (("open", o), ("high", h), ("low", l), ("close", c), ("volume", v)):
+        _req(t, torch.float64, name)
+        if t.numel() != n_rows:
+            raise _lib.IvxError(f"{name}: length {t.numel()} != {n_rows}")
+    if min_count < 0 or bucket_ticks < 1:
+        raise _lib.IvxError("bucket_ticks must be >= 1 and min_count >= 0")
+    if capacity is None:
+        capacity = n_rows // max(1, min_count) if min_count >= 1 else n_rows
+    L = lib()
+    ws_bytes = L.ivx_ohlcv_workspace_bytes(n_sym, n_rows)
+    ws = _empty(ws_bytes, torch.uint8, ts)
+    out_off = _empty(n_sym + 1, torch.int64, ts)
+    o_ts = _empty(capacity, torch.int64, ts)
+    oo, oh, ol, oc, ov = (_empty(capacity, torch.float64, ts) for _ in range(5))
+    o_count = _empty(capacity, torch.int32, ts)
+    o_sym_row = _empty(capacity, torch.int64, ts) if want_index else None
+    o_group = _empty(capacity, torch.int64, ts) if want_index else None
+    sym_group_off = _empty(n_sym + 1, torch.int64, ts) if want_index else None
+    sym_status = _empty(n_sym, torch.uint8, ts)
+    sym_flags = _empty(n_sym, torch.int32, ts)
+    total = _empty(1, torch.int64, ts)
+    check(L.ivx_ohlcv_reduce(
+        n_sym, _ptr(in_off), n_rows, _ptr(ts), _ptr(o), _ptr(h), _ptr(l), _ptr(c), _ptr(v), _ptr(sym_valid),
+        int(bucket_ticks), int(min_count), int(bool(check_len)), int(capacity), _ptr(out_off),
+        _ptr(o_ts), _ptr(oo), _ptr(oh), _ptr(ol), _ptr(oc), _ptr(ov), _ptr(o_count), _ptr(o_sym_row), _ptr(o_group),
+        _ptr(sym_group_off), _ptr(sym_status), _ptr(sym_flags), _ptr(total), _ptr(ws), ws_bytes, _stream()),
+        "ivx_ohlcv_reduce")
+    _count("ohlcv_reduce")
+    res = CandleBatch(out_off, o_ts, oo, oh, ol, oc, ov, o_count, sym_status, sym_flags, o_sym_row, o_group,
+                      sym_group_off)
+    res._total_dev = total
+    if trim:
+        m = int(total.item())
+        if m > capacity:
+            raise _lib.IvxError(f"ohlcv_reduce: {m} candles exceed the capacity {capacity}")
+        res.total = m
+        for name in ("ts", "open", "high", "low", "close", "volume", "count", "sym_row", "group"):
+            t = getattr(res, name)
+            if t is not None:
+                setattr(res, name, t[:m])
+    return res
+
+
+def time_buckets(ts: torch.Tensor, bucket_ticks: int):
+    """Stamps of one step -> (bucket_of_t int32[n_t], bucket_ts int64[nb], bucket_start int32[nb+1], nb)."""
+    n_t = ts.numel()
+    bucket_of_t = _empty(n_t, torch.int32, ts)
+    bucket_ts = _empty(n_t, torch.int64, ts)
+    bucket_start = _empty(n_t + 1, torch.int32, ts)
+    nb = _empty(1, torch.int64, ts)
+    check(lib().ivx_time_buckets(n_t, _ptr(_req(ts, torch.int64, "ts")), int(bucket_ticks), _ptr(bucket_of_t),
+                                 _ptr(bucket_ts), _ptr(bucket_start), _ptr(nb), _stream()), "ivx_time_buckets")
+    _count("time_buckets")
+    n = int(nb.item())
+    return bucket_of_t, bucket_ts[:n], bucket_start[:n + 1], n
+
+
+def ohlc_time_major(x: torch.Tensor, n_series: int, bucket_start: torch.Tensor, n_buckets: int, min_count: int):
+    """x[t*n_series+s] -> four [n_buckets*n_series] candle arrays + int32 counts per bucket."""
+    n_t = x.numel() // max(1, n_series)
+    outs = [_empty(n_buckets * n_series, torch.float64, x) for _ in range(4)]
+    cnt = _empty(n_buckets, torch.int32, x)
+    check(lib().ivx_ohlc_time_major(n_t, n_series, _ptr(_req(x, torch.float64, "x")), n_buckets,
+                                    _ptr(_req(bucket_start, torch.int32, "bucket_start")), int(min_count),
+                                    _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(cnt), _stream()),
+          "ivx_ohlc_time_major")
+    _count("ohlc_time_major")
+    return outs[0], outs[1], outs[2], outs[3], cnt
+
+
+# ------------------------------------------------------------------------------------------------
+# Kernel A
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class InterpBatch:
+    out_off: torch.Tensor                   # int64[n_sym+1]
+    sym_status: torch.Tensor                # uint8[n_sym]
+    sym_flags: torch.Tensor                 # int32[n_sym]
+    ts: torch.Tensor                        # int64[m]
+    interp: List[torch.Tensor]              # 3 x float64[m]
+    fill: List[torch.Tensor]                # n_fill x float64[m]
+    idx: List[torch.Tensor]                 # n_idx x int32[m]
+    src_row: Optional[torch.Tensor]
+    pos: Optional[torch.Tensor]
+    keep: Optional[torch.Tensor]
+    is_interpolated: Optional[torch.Tensor]
+    total: int = 0
+
+
+def interp_linear_ffill(src_off: torch.Tensor, ts: torch.Tensor, interp_cols: Sequence[torch.Tensor],
+                        fill_cols: Sequence[torch.Tensor] = (), idx_valid: Sequence[Optional[torch.Tensor]] = (),
+                        *, step: int, max_span: int, max_points: int = 100_000, min_points: int = 10,
+                        want_src_row: bool = False, want_pos: bool = False, want_keep: bool = False,
+                        want_is_interpolated: bool = True) -> InterpBatch:
+    """CSR batch of contracts -> minute rows (reference interpolation/core.py:26-81).
+
+    ``idx_valid[0]`` is the ``symbol`` column's non-null mask (uint8 tensor, or None = all valid).
+    One 8-byte D2H sync (the total row count) sits between plan and exec.
+    """
+    n_sym = src_off.numel() - 1
+    n_src = ts.numel()
+    _req(src_off, torch.int64, "src_off"); _req(ts, torch.int64, "ts")
+    if len(interp_cols) != 3:
+        raise _lib.IvxError("interp_cols must be (iv, underlying_price, time_to_maturity)")
+    n_fill, n_idx = len(fill_cols), len(idx_valid)
+    if n_fill > _lib.MAX_FILL_COLS or n_idx > _lib.MAX_IDX_COLS:
+        raise _lib.IvxError(f"at most {_lib.MAX_FILL_COLS} fill and {_lib.MAX_IDX_COLS} index columns per call")
+    for t in list(interp_cols) + list(fill_cols):
+        _req(t, torch.float64, "column")
+        if t.numel() != n_src:
+            raise _lib.IvxError("column length mismatch")
+    L = lib()
+    ws_bytes = L.ivx_interp_workspace_bytes(n_sym, n_src, n_fill, n_idx)
+    ws = _empty(ws_bytes, torch.uint8, ts)
+    out_count = _empty(n_sym, torch.int64, ts)
+    out_off = _empty(n_sym + 1, torch.int64, ts)
+    sym_status = _empty(n_sym, torch.uint8, ts)
+    sym_flags = _empty(n_sym, torch.int32, ts)
+    check(L.ivx_interp_plan(
+        n_sym, _ptr(src_off), n_src, _ptr(ts), ptr_array([_ptr(t) for t in interp_cols]),
+        n_fill, ptr_array([_ptr(t) for t in fill_cols]), n_idx,
+        ptr_array([None if t is None else _ptr(_req(t, torch.uint8, "idx_valid")) for t in idx_valid]),
+        int(step), int(max_span), int(max_points), int(min_points), _ptr(out_count), _ptr(out_off),
+        _ptr(sym_status), _ptr(sym_flags), _ptr(ws), ws_bytes, _stream()), "ivx_interp_plan")
+    _count("interp_plan")
+    m = int(out_off[n_sym].item())                     # sizes the outputs
+    o_ts = _empty(m, torch.int64, ts)
+    o_interp = [_empty(m, torch.float64, ts) for _ in range(3)]
+    o_fill = [_empty(m, torch.float64, ts) for _ in range(n_fill)]
+    o_idx = [_empty(m, torch.int32, ts) for _ in range(n_idx)]
+    o_src = _empty(m, torch.int32, ts) if want_src_row else None
+    o_pos = _empty(m, torch.int32, ts) if want_pos else None
+    o_keep = _empty(m, torch.uint8, ts) if want_keep else None
+    o_isint = _empty(m, torch.uint8, ts) if want_is_interpolated else None
+    check(L.ivx_interp_exec(
+        n_sym, _ptr(src_off), n_src, _ptr(out_off), m, int(step), n_fill, n_idx, _ptr(o_ts),
+        ptr_array([_ptr(t) for t in o_interp]), ptr_array([_ptr(t) for t in o_fill]),
+        ptr_array([_ptr(t) for t in o_idx]), _ptr(o_src), _ptr(o_pos), _ptr(o_keep), _ptr(o_isint),
+        _ptr(ws), ws_bytes, _stream()), "ivx_interp_exec")
+    _count("interp_exec")
+    return InterpBatch(out_off, sym_status, sym_flags, o_ts, o_interp, o_fill, o_idx, o_src, o_pos, o_keep,
+                       o_isint, m)
+
+
+# ------------------------------------------------------------------------------------------------
+# Kernel C
+# ------------------------------------------------------------------------------------------------
+def bs_implied_vol(price, S, K, T, r, is_call, *, want_iters: bool = False, out: Optional[torch.Tensor] = None):
+    n = price.numel()
+    for t in (price, S, K, T, r):
+        _req(t, torch.float64, "quote column")
+        if t.numel() != n:
+            raise _lib.IvxError("quote column length mismatch")
+    _req(is_call, torch.uint8, "is_call")
+    sigma = out if out is not None else _empty(n, torch.float64, price)
+    iters = _empty(n, torch.int32, price) if want_iters else None
+    check(lib().ivx_bs_implied_vol(n, _ptr(price), _ptr(S), _ptr(K), _ptr(T), _ptr(r), _ptr(is_call), _ptr(sigma),
+                                   _ptr(iters), _stream()), "ivx_bs_implied_vol")
+    _count("bs_implied_vol")
+    return (sigma, iters) if want_iters else sigma
+
+
+def bs_price(S, K, T, r, sigma, is_call):
+    n = S.numel()
+    price = _empty(n, torch.float64, S)
+    check(lib().ivx_bs_price(n, _ptr(S), _ptr(K), _ptr(T), _ptr(r), _ptr(sigma), _ptr(_req(is_call, torch.uint8, "is_call")),
+                             _ptr(price), _stream()), "ivx_bs_price")
+    _count("bs_price")
+    return price
+
+
+def bs_greeks(S, K, T, r, sigma, is_call, reference_put_rho_sign: bool = True) -> Dict[str, torch.Tensor]:
+    n = S.numel()
+    out = {k: _empty(n, torch.float64, S) for k in ("delta", "gamma", "theta", "vega", "rho")}
+    check(lib().ivx_bs_greeks(n, _ptr(S), _ptr(K), _ptr(T), _ptr(r), _ptr(sigma), _ptr(_req(is_call, torch.uint8, "is_call")),
+                              int(reference_put_rho_sign), _ptr(out["delta"]), _ptr(out["gamma"]), _ptr(out["theta"]),
+                              _ptr(out["vega"]), _ptr(out["rho"]), _stream()), "ivx_bs_greeks")
+    _count("bs_greeks")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Kernel D
+# ------------------------------------------------------------------------------------------------
+def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, *,
+                    max_knots: int, extrap: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n_slices = knot_off.numel() - 1
+    n_q = xq.numel()
+    _req(knot_off, torch.int64, "knot_off")
+    for t in (x, y, xq):
+        _req(t, torch.float64, "spline column")
+    yq = out if out is not None else _empty(n_slices * n_q, torch.float64, x)
+    ws = _empty(256, torch.uint8, x)
+    check(lib().ivx_spline_fit_eval(n_slices, _ptr(knot_off), int(max_knots), _ptr(x), _ptr(y), n_q, _ptr(xq),
+                                    int(extrap), _ptr(yq), _ptr(ws), 256, _stream()), "ivx_spline_fit_eval")
+    _count("spline_fit_eval")
+    return yq
+
+
+def spline_strided(x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, n_systems: int, *, extrap: int = 1,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n_knots, n_q = x.numel(), xq.numel()
+    for t in (x, y, xq):
+        _req(t, torch.float64, "spline column")
+    if y.numel() != n_knots * n_systems:
+        raise _lib.IvxError("y must be [n_knots][n_systems]")
+    yq = out if out is not None else _empty(n_q * n_systems, torch.float64, x)
+    check(lib().ivx_spline_strided(n_systems, n_knots, _ptr(x), _ptr(y), n_q, _ptr(xq), int(extrap), _ptr(yq),
+                                   _stream()), "ivx_spline_strided")
+    _count("spline_strided")
+    return yq
+
+
+# ------------------------------------------------------------------------------------------------
+# Utilities
+# ------------------------------------------------------------------------------------------------
+def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
+    out = _empty(x.numel() + 1, torch.int64, x)
+    check(lib().ivx_exclusive_scan_i64(x.numel(), _ptr(_req(x, torch.int64, "x")), _ptr(out), _stream()), "ivx_exclusive_scan_i64")
+    _count("scan")
+    return out
+
+
+def probe_copy(src: torch.Tensor, dst: torch.Tensor) -> None:
+    check(lib().ivx_probe_copy(src.numel(), _ptr(src), _ptr(dst), _stream()), "ivx_probe_copy")
+    _count("probe")
+
+
+def probe_fp64_fma(n_threads: int, iters: int, sink: torch.Tensor) -> None:
+    check(lib().ivx_probe_fp64_fma(n_threads, iters, _ptr(sink), _stream()), "ivx_probe_fp64_fma")
+    _count("probe")

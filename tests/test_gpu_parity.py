@@ -1,0 +1,313 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference-generated golden
+vectors and against the numpy oracle on seeded tapes.  Integer/selection results bit-exact;
+fp64 values bit-exact for kernels A and B, |d| <= 1e-8 (BASELINE.json north_star) for C and D."""
+import json
+import logging
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from iv_interpolation_b200 import tapes  # noqa: E402
+from oracle import golden_io, np_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from iv_interpolation_b200 import _lib
+    _lib.lib()
+    logging.disable(logging.CRITICAL)
+    return torch.device("cuda")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype.kind == "f":
+        return bool(((a == b) | (np.isnan(a) & np.isnan(b))).all()) and a.shape == b.shape
+    return a.shape == b.shape and bool((a == b).all())
+
+
+# ---------------------------------------------------------------------------------------------
+# DataFrame face against the reference's own outputs
+# ---------------------------------------------------------------------------------------------
+def test_interpolator_matches_reference_golden(dev, golden_interp):
+    from iv_interpolation_b200.interpolation.core import IVInterpolator
+    names = json.loads(str(golden_interp["names"]))
+    for name in names:
+        frame = golden_io.dict_to_frame(f"{name}/in", golden_interp)
+        want = golden_io.dict_to_frame(f"{name}/out", golden_interp)
+        kw = json.loads(str(golden_interp[f"{name}/kwargs"]))
+        got = IVInterpolator(**kw).interpolate_symbol(frame)
+        try:
+            golden_io.assert_frames_match(want, got)
+        except AssertionError as e:
+            raise AssertionError(f"case {name}: {e}") from None
+
+
+def test_interpolator_batch_equals_single_calls(dev, golden_interp):
+    from iv_interpolation_b200.interpolation.core import IVInterpolator
+    names = [n for n in json.loads(str(golden_interp["names"])) if n.startswith("tape_cfg1")]
+    frames = [golden_io.dict_to_frame(f"{n}/in", golden_interp) for n in names]
+    outs = IVInterpolator().interpolate_batch(frames)
+    for n, got in zip(names, outs):
+        golden_io.assert_frames_match(golden_io.dict_to_frame(f"{n}/out", golden_interp), got)
+
+
+def test_reconstructor_matches_reference_golden(dev, golden_candles):
+    from iv_interpolation_b200.candle_reconstruction.core import CandleReconstructor
+    names = json.loads(str(golden_candles["names"]))
+    for name in names:
+        frame = golden_io.dict_to_frame(f"{name}/in", golden_candles)
+        want = golden_io.dict_to_frame(f"{name}/out", golden_candles)
+        freq = str(golden_candles[f"{name}/freq"])
+        rec = CandleReconstructor(freq)
+        got = rec.reconstruct_symbol_candles(frame)
+        try:
+            golden_io.assert_frames_match(want, got)
+            if all(c in frame.columns for c in ("open", "high", "low", "close", "volume")):
+                assert rec.validate_candle_data(frame) == bool(golden_candles[f"{name}/valid_in"]), "validate(input)"
+            if want is not None:
+                assert rec.validate_candle_data(want) == bool(golden_candles[f"{name}/valid_out"]), "validate(output)"
+        except AssertionError as e:
+            raise AssertionError(f"case {name}: {e}") from None
+
+
+def test_aggregate_to_5min_entry(dev, golden_candles):
+    """complete_pipeline.py:685-710 gives the same OHLCV as the class method on sorted unique input."""
+    from iv_interpolation_b200.candle_reconstruction.core import CandleReconstructor
+    frame = golden_io.dict_to_frame("tape_seed1_0_5min/in", golden_candles)
+    want = golden_io.dict_to_frame("tape_seed1_0_5min/out", golden_candles)
+    got = CandleReconstructor("5min").aggregate_to_5min(frame)
+    assert list(got.columns) == ["timestamp", "open", "high", "low", "close", "volume", "symbol"]
+    for c in ("open", "high", "low", "close", "volume"):
+        assert _eq(want[c].to_numpy(), got[c].to_numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# batched CSR operators against the numpy oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,n_sym,rows,freq_min,spacing", [
+    (11, 120, 1441, 5, tapes.MINUTE_US), (12, 60, 700, 7, tapes.MINUTE_US), (13, 40, 3000, 1, tapes.US),
+    (14, 300, 23, 5, tapes.MINUTE_US), (15, 3, 20000, 60, tapes.MINUTE_US), (16, 50, 1030, 15, tapes.MINUTE_US)])
+def test_ohlcv_batch_vs_oracle(dev, seed, n_sym, rows, freq_min, spacing):
+    from iv_interpolation_b200 import device as D
+    ct = tapes.make_candle_tape(seed, n_sym, rows_per_symbol=rows, spacing_us=spacing, gap_frac=0.03, nan_frac=0.02)
+    ticks = freq_min * tapes.MINUTE_US
+    res = D.ohlcv_reduce(_t(ct.off, dev), _t(ct.ts, dev), _t(ct.o, dev), _t(ct.h, dev), _t(ct.l, dev), _t(ct.c, dev),
+                         _t(ct.v, dev), bucket_ticks=ticks, min_count=freq_min, want_index=True)
+    out_off = res.out_off.cpu().numpy()
+    got = {k: getattr(res, k).cpu().numpy() for k in ("ts", "open", "high", "low", "close", "volume", "count", "group")}
+    goff = res.sym_group_off.cpu().numpy()
+    status = res.sym_status.cpu().numpy()
+    flags = res.sym_flags.cpu().numpy()
+    total = 0
+    for i in range(ct.n_sym):
+        a, b = int(ct.off[i]), int(ct.off[i + 1])
+        w = O.ohlcv_reduce(ct.ts[a:b], ct.o[a:b], ct.h[a:b], ct.l[a:b], ct.c[a:b], ct.v[a:b],
+                           bucket_ticks=ticks, min_count=freq_min)
+        assert status[i] == w["status"], f"symbol {i}: status"
+        ga, gb = int(out_off[i]), int(out_off[i + 1])
+        if w["status"] != 0:
+            assert ga == gb
+            continue
+        for k in ("ts", "open", "high", "low", "close", "volume", "count"):
+            assert _eq(got[k][ga:gb], w[k]), f"symbol {i}: {k}"
+        assert _eq(got["group"][ga:gb] - goff[i], w["group_index"]), f"symbol {i}: group index"
+        want_flags = O.validate_flags(ct.o[a:b], ct.h[a:b], ct.l[a:b], ct.c[a:b], ct.v[a:b])
+        if gb > ga:
+            want_flags |= O.validate_flags(w["open"], w["high"], w["low"], w["close"], w["volume"]) << 3
+        assert int(flags[i]) == want_flags, f"symbol {i}: flags {int(flags[i])} != {want_flags}"
+        total += gb - ga
+    assert total == res.total == int(out_off[-1])
+
+
+def test_ohlcv_edge_batches(dev):
+    """Empty batch, empty symbols between non-empty ones, a bucket longer than a tile, one-row symbols."""
+    from iv_interpolation_b200 import device as D
+    z = lambda dt: torch.zeros(0, dtype=dt, device=dev)
+    res = D.ohlcv_reduce(torch.zeros(1, dtype=torch.int64, device=dev), z(torch.int64), *(z(torch.float64) for _ in range(5)),
+                         bucket_ticks=300, min_count=5)
+    assert res.total == 0 and res.out_off.cpu().tolist() == [0]
+    rng = np.random.default_rng(3)
+    lens = np.array([0, 7, 0, 0, 2500, 1, 0, 64, 1, 1, 0])
+    off = np.r_[0, np.cumsum(lens)].astype(np.int64)
+    n = int(off[-1])
+    ts = np.concatenate([np.arange(m, dtype=np.int64) * 60 for m in lens])      # unit: seconds
+    cols = [rng.normal(100, 5, n) for _ in range(5)]
+    for N, ticks in ((5, 300), (1, 60), (3000, 3000 * 60), (2, 120)):
+        res = D.ohlcv_reduce(_t(off, dev), _t(ts, dev), *(_t(c, dev) for c in cols), bucket_ticks=ticks, min_count=N)
+        out_off = res.out_off.cpu().numpy()
+        for i in range(len(lens)):
+            a, b = int(off[i]), int(off[i + 1])
+            w = O.ohlcv_reduce(ts[a:b], *(c[a:b] for c in cols), bucket_ticks=ticks, min_count=N)
+            ga, gb = int(out_off[i]), int(out_off[i + 1])
+            if w["status"] != 0:
+                assert ga == gb and res.sym_status.cpu().numpy()[i] == w["status"]
+                continue
+            for k, g in (("ts", res.ts), ("open", res.open), ("high", res.high), ("low", res.low),
+                         ("close", res.close), ("volume", res.volume), ("count", res.count)):
+                assert _eq(g.cpu().numpy()[ga:gb], w[k]), (N, i, k)
+
+
+@pytest.mark.parametrize("seed,n_contracts,rows,spacing,kw", [
+    (21, 200, 25, tapes.HOUR_US, {}), (22, 64, 73, 20 * tapes.MINUTE_US, dict(nan_frac=0.3, missing_frac=0.1)),
+    (23, 30, 481, tapes.HOUR_US, {}), (24, 40, 300, tapes.MINUTE_US, dict(nan_frac=0.2, offgrid_frac=0.1))])
+def test_interp_batch_vs_oracle(dev, seed, n_contracts, rows, spacing, kw):
+    from iv_interpolation_b200 import device as D
+    tp = tapes.make_contract_tape(seed, n_contracts, rows_per_contract=rows, spacing_us=spacing, **kw)
+    icols = [tp.cols[c] for c in tapes.INTERP_COLS]
+    fcols = [tp.cols[c] for c in tapes.FILL_NUM_COLS]
+    res = D.interp_linear_ffill(_t(tp.off, dev), _t(tp.date, dev), [_t(c, dev) for c in icols], [_t(c, dev) for c in fcols],
+                                [None], step=tapes.MINUTE_US, max_span=30 * tapes.DAY_US, min_points=10,
+                                want_src_row=True, want_pos=True, want_keep=True)
+    out_off = res.out_off.cpu().numpy()
+    status = res.sym_status.cpu().numpy()
+    g_ts = res.ts.cpu().numpy()
+    g_i = [t.cpu().numpy() for t in res.interp]
+    g_f = [t.cpu().numpy() for t in res.fill]
+    g_idx = res.idx[0].cpu().numpy()
+    g_src = res.src_row.cpu().numpy()
+    g_pos = res.pos.cpu().numpy()
+    assert res.keep.cpu().numpy().all() and not res.is_interpolated.cpu().numpy().any()
+    n_rows = 0
+    for i in range(tp.n_sym):
+        a, b = int(tp.off[i]), int(tp.off[i + 1])
+        w = O.interp_linear_ffill(tp.date[a:b], [c[a:b] for c in icols], [c[a:b] for c in fcols], [np.ones(b - a, bool)],
+                                  step=tapes.MINUTE_US, max_span=30 * tapes.DAY_US, min_points=10)
+        assert status[i] == w["status"], f"contract {i}: status {status[i]} != {w['status']}"
+        ga, gb = int(out_off[i]), int(out_off[i + 1])
+        if w["status"] != 0:
+            assert ga == gb
+            continue
+        assert gb - ga == len(w["date"]), f"contract {i}: row count"
+        assert _eq(g_ts[ga:gb], w["date"]), f"contract {i}: date"
+        for k in range(3):
+            assert _eq(g_i[k][ga:gb], w["interp"][k]), f"contract {i}: {tapes.INTERP_COLS[k]}"
+        for k in range(len(fcols)):
+            assert _eq(g_f[k][ga:gb], w["fill"][k]), f"contract {i}: {tapes.FILL_NUM_COLS[k]}"
+        assert _eq(np.where(g_idx[ga:gb] >= 0, g_idx[ga:gb] - a, -1), w["str_src"][0]), f"contract {i}: symbol source row"
+        assert _eq(np.where(g_src[ga:gb] >= 0, g_src[ga:gb] - a, -1), w["src_row"]), f"contract {i}: src_row"
+        assert _eq(g_pos[ga:gb], w["index"]), f"contract {i}: positions"
+        n_rows += gb - ga
+    assert n_rows == res.total
+
+
+# ---------------------------------------------------------------------------------------------
+# north_star kernels without reference code: scipy oracles, 1e-8 absolute
+# ---------------------------------------------------------------------------------------------
+def test_bs_price_and_greeks_vs_oracle(dev, golden_kats):
+    from iv_interpolation_b200 import device as D
+    q = tapes.make_quote_tape(5, 20000)
+    d = [_t(a, dev) for a in (q.S, q.K, q.T, q.r, q.sigma_true)] + [_t(q.is_call, dev)]
+    price = D.bs_price(*d).cpu().numpy()
+    want = O.bs_price(q.S, q.K, q.T, q.r, q.sigma_true, q.is_call)
+    assert np.all(np.abs(price - want) <= 1e-12 * np.maximum(1.0, np.abs(want)) + 1e-10)
+    for case in golden_kats["greeks"]:
+        c = dict(case["in"])
+        call = np.array([1 if c.pop("option_type") == "call" else 0], np.uint8)
+        arrs = [_t(np.array([c[k]]), dev) for k in ("S", "K", "T", "r", "sigma")]
+        got = D.bs_greeks(*arrs, _t(call, dev))
+        for k, v in case["out"].items():
+            assert abs(float(got[k].cpu()[0]) - v) <= 1e-12 * max(1.0, abs(v)), (k, float(got[k].cpu()[0]), v)
+
+
+def test_implied_vol_vs_oracle(dev):
+    from iv_interpolation_b200 import device as D
+    n = 12000
+    q = tapes.make_quote_tape(6, n, pricer=O.bs_price)
+    # add hand-made edge quotes: outside the no-arbitrage bounds, non-finite, zero/negative inputs
+    price = q.price.copy()
+    price[:8] = [np.nan, -1.0, 0.0, np.inf, 1e9, q.S[5] * 2, 0.0, np.nan]
+    S, K, T, r = q.S.copy(), q.K.copy(), q.T.copy(), q.r.copy()
+    S[8], K[9], T[10], T[11] = -1.0, 0.0, 0.0, np.nan
+    sig, iters = D.bs_implied_vol(*(_t(a, dev) for a in (price, S, K, T, r)), _t(q.is_call, dev), want_iters=True)
+    sig, iters = sig.cpu().numpy(), iters.cpu().numpy()
+    want = O.implied_vol(price, S, K, T, r, q.is_call)
+    dom = O.implied_vol_domain(price, S, K, T, r, q.is_call)
+    assert np.isnan(sig[~dom]).all(), "quotes outside the invertible domain must come back NaN"
+    both = ~np.isnan(want) & ~np.isnan(sig)
+    # NaN masks agree except where the time value is at rounding level (target price ~ 0)
+    mism = np.isnan(want) != np.isnan(sig)
+    assert mism.sum() <= 2e-3 * n, f"NaN mask differs on {mism.sum()} quotes"
+    err = np.abs(sig[both] - want[both])
+    fwd_ok = err <= 1e-8                                   # north_star tolerance
+    # where the price does not determine sigma to 1e-8 (vega * 1e-8 below a few ulps of the price),
+    # require instead that the solution reprices the quote to rounding (backward error)
+    rep = O.bs_price(S[both], K[both], T[both], r[both], sig[both], q.is_call[both])
+    back_ok = np.abs(rep - price[both]) <= 64 * np.spacing(np.maximum(np.abs(price[both]), S[both]))
+    assert (fwd_ok | back_ok).all(), f"{(~(fwd_ok | back_ok)).sum()} quotes fail both forward and backward error"
+    assert fwd_ok.mean() >= 0.90, f"only {fwd_ok.mean():.3f} of finite IVs within 1e-8"
+    assert iters[both].max() <= 64 and iters[both].mean() < 12
+    # round trip on the well-conditioned core: sigma -> price -> sigma
+    core = both & (np.abs(np.log(S / K)) < 0.25) & (T > 0.05)
+    assert np.abs(sig[core] - q.sigma_true[core]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("extrap", [0, 1, 2])
+def test_spline_fit_eval_vs_scipy(dev, extrap):
+    from iv_interpolation_b200 import device as D
+    off, x, y, xq = tapes.make_smile_slices(7, 300, 2, 2000, 512, nan_frac=0.03)
+    # force the tiny-slice cases
+    for i, nk in enumerate((2, 3, 4)):
+        y[off[i] + nk: off[i + 1]] = np.nan
+    y[off[3]: off[4]] = np.nan
+    y[off[4] + 1: off[5]] = np.nan
+    got = D.spline_fit_eval(_t(off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=int(np.diff(off).max()),
+                            extrap=extrap).cpu().numpy().reshape(len(off) - 1, -1)
+    for i in range(len(off) - 1):
+        want = O.natural_spline_eval(x[off[i]:off[i + 1]], y[off[i]:off[i + 1]], xq, extrap)
+        assert _eq(np.isnan(got[i]), np.isnan(want)), f"slice {i}: NaN mask"
+        ok = ~np.isnan(want)
+        assert np.abs(got[i][ok] - want[ok]).max(initial=0.0) <= 1e-8, f"slice {i}: {np.abs(got[i][ok] - want[ok]).max()}"
+
+
+@pytest.mark.parametrize("extrap", [1, 2])
+def test_spline_strided_vs_scipy(dev, extrap):
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(8)
+    nk, nsys, nq = 30, 700, 64
+    x = np.sort(rng.uniform(0.01, 2.0, nk))
+    y = 0.2 + 0.1 * np.sqrt(x)[:, None] + 0.01 * rng.standard_normal((nk, nsys))
+    y[rng.random((nk, nsys)) < 0.02] = np.nan
+    y[:, 5] = np.nan
+    y[1:, 6] = np.nan
+    xq = np.linspace(0.0, 2.1, nq)
+    got = D.spline_strided(_t(x, dev), _t(y.reshape(-1), dev), _t(xq, dev), nsys, extrap=extrap).cpu().numpy().reshape(nq, nsys)
+    for s in range(nsys):
+        want = O.natural_spline_eval(x, y[:, s], xq, extrap)
+        assert _eq(np.isnan(got[:, s]), np.isnan(want)), f"system {s}: NaN mask"
+        ok = ~np.isnan(want)
+        assert np.abs(got[:, s][ok] - want[ok]).max(initial=0.0) <= 1e-8, f"system {s}"
+
+
+def test_time_major_candles_vs_oracle(dev):
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(9)
+    n_t, n_series = 500, 777
+    ts = (tapes.T0_US + 34_200 * tapes.US + np.sort(rng.choice(900, n_t, replace=False)).astype(np.int64) * tapes.US)
+    x = rng.normal(0.3, 0.05, (n_t, n_series))
+    x[rng.random((n_t, n_series)) < 0.05] = np.nan
+    bucket_of_t, bucket_ts, bucket_start, nb = D.time_buckets(_t(ts, dev), tapes.MINUTE_US)
+    want_b = ts // tapes.MINUTE_US
+    uniq, start = np.unique(want_b, return_index=True)
+    assert nb == len(uniq) and _eq(bucket_ts.cpu().numpy(), uniq * tapes.MINUTE_US)
+    assert _eq(bucket_start.cpu().numpy(), np.r_[start, n_t]) and _eq(bucket_of_t.cpu().numpy(), np.searchsorted(uniq, want_b))
+    min_count = 30
+    o, h, l, c, cnt = D.ohlc_time_major(_t(x.reshape(-1), dev), n_series, bucket_start, nb, min_count)
+    o, h, l, c = (a.cpu().numpy().reshape(nb, n_series) for a in (o, h, l, c))
+    for s in (0, 1, 300, 776):
+        w = O.ohlcv_reduce(ts, x[:, s], x[:, s], x[:, s], x[:, s], np.zeros(n_t), bucket_ticks=tapes.MINUTE_US, min_count=1)
+        full = np.diff(np.r_[start, n_t]) >= min_count
+        for got, key in ((o, "open"), (h, "high"), (l, "low"), (c, "close")):
+            assert _eq(got[:, s][full], w[key][full]), key
+            assert np.isnan(got[:, s][~full]).all()
+    assert _eq(cnt.cpu().numpy(), np.diff(np.r_[start, n_t]))
