@@ -181,6 +181,13 @@ int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_k
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);
+/* n_batches independent planes (one per timestamp): batch b reads its abscissae at
+ * x[b*x_batch_stride + i*x_knot_stride] (so they can be read in place from a per-quote column),
+ * its knots at y[b][knot][system] and writes yq[b][query][system]. */
+int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, int32_t n_knots, const double* x,
+                               int64_t x_batch_stride, int64_t x_knot_stride, const double* y,
+                               int32_t n_q, const double* xq, int32_t extrap, double* yq,
+                               ivx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Utilities: exclusive scan of int64, stream-copy and fp64-FMA microbenchmarks that give the

@@ -138,16 +138,22 @@ __global__ void __launch_bounds__(SPL_MAX_WARPS * 32) k_spline_fit_eval(int64_t 
 }
 
 // ---- many small systems, [knot][system] layout ----------------------------------------------------------
+// blockIdx.y = batch: batch b has its own abscissae x[b*x_batch_stride + i*x_knot_stride] and its own
+// [knot][system] / [query][system] planes of y / yq
 __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, const double* __restrict__ x,
+                                                        int64_t x_batch_stride, int64_t x_knot_stride,
                                                         const double* __restrict__ y, int n_q,
                                                         const double* __restrict__ xq, int extrap,
                                                         double* __restrict__ yq) {
   __shared__ double s_x[STRIDED_MAXK], s_cp[STRIDED_MAXK], s_inv[STRIDED_MAXK];
   __shared__ int s_x_ok;
+  x += (int64_t)blockIdx.y * x_batch_stride;
+  y += (int64_t)blockIdx.y * nk * n_sys;
+  yq += (int64_t)blockIdx.y * n_q * n_sys;
   // LU factors of the shared abscissae (valid when a system has every knot)
   if (threadIdx.x == 0) {
     bool okx = true;
-    for (int i = 0; i < nk; ++i) { s_x[i] = x[i]; okx = okx && isfinite(x[i]); }
+    for (int i = 0; i < nk; ++i) { s_x[i] = x[i * x_knot_stride]; okx = okx && isfinite(s_x[i]); }
     s_x_ok = okx;
     double c_prev = 0.0;
     for (int i = 1; i + 1 < nk; ++i) {
@@ -274,7 +280,28 @@ extern "C" int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const doub
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_strided: extrap must be 0, 1 or 2");
   if (n_systems == 0 || n_q == 0) return IVX_OK;
   IVX_REQUIRE(x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_strided: null pointer");
-  k_spline_strided<<<(unsigned)((n_systems + 127) / 128), 128, 0, stream>>>(n_systems, n_knots, x, y, n_q, xq, extrap, yq);
+  k_spline_strided<<<(unsigned)((n_systems + 127) / 128), 128, 0, stream>>>(n_systems, n_knots, x, 0, 1, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_strided");
+  return IVX_OK;
+}
+
+extern "C" int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, int32_t n_knots, const double* x,
+                                          int64_t x_batch_stride, int64_t x_knot_stride, const double* y, int32_t n_q,
+                                          const double* xq, int32_t extrap, double* yq, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_batches >= 0 && n_systems >= 0 && n_knots >= 0 && n_q >= 0, IVX_ERR_INVALID_ARG, "ivx_spline_strided_batched: bad sizes");
+  IVX_REQUIRE(n_knots <= STRIDED_MAXK, IVX_ERR_UNSUPPORTED, "ivx_spline_strided_batched: at most %d knots per system (got %d)", STRIDED_MAXK, n_knots);
+  IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_strided_batched: extrap must be 0, 1 or 2");
+  IVX_REQUIRE(x_batch_stride >= 0 && x_knot_stride >= 1, IVX_ERR_INVALID_ARG, "ivx_spline_strided_batched: bad abscissa strides");
+  if (n_batches == 0 || n_systems == 0 || n_q == 0) return IVX_OK;
+  IVX_REQUIRE(x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_strided_batched: null pointer");
+  const int64_t gx = (n_systems + 127) / 128;
+  for (int64_t b0 = 0; b0 < n_batches; b0 += 65535) {   // gridDim.y limit
+    const int64_t nb = n_batches - b0 < 65535 ? n_batches - b0 : 65535;
+    dim3 grid((unsigned)gx, (unsigned)nb);
+    k_spline_strided<<<grid, 128, 0, stream>>>(n_systems, n_knots, x + b0 * x_batch_stride, x_batch_stride, x_knot_stride,
+                                               y + b0 * n_knots * n_systems, n_q, xq, extrap, yq + b0 * n_q * n_systems);
+    IVX_LAUNCH_CHECK("k_spline_strided(batched)");
+  }
   return IVX_OK;
 }

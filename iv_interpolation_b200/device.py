@@ -21,7 +21,7 @@ _LAUNCHES = 0     # kernels of ours enqueued since the last reset (bench.py repo
 _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
-    "scan": 1, "probe": 1,
+    "spline_strided_batched": 1, "scan": 1, "probe": 1,
 }
 
 
@@ -152,11 +152,30 @@ def time_buckets(ts: torch.Tensor, bucket_ticks: int):
     return bucket_of_t, bucket_ts[:n], bucket_start[:n + 1], n
 
 
-def ohlc_time_major(x: torch.Tensor, n_series: int, bucket_start: torch.Tensor, n_buckets: int, min_count: int):
+def time_buckets_into(ts: torch.Tensor, bucket_ticks: int, bucket_of_t: torch.Tensor, bucket_ts: torch.Tensor,
+                      bucket_start: torch.Tensor, n_buckets: torch.Tensor) -> None:
+    """``time_buckets`` into caller-owned buffers, without the read-back of the bucket count."""
+    n_t = ts.numel()
+    if bucket_of_t.numel() < n_t or bucket_ts.numel() < n_t or bucket_start.numel() < n_t + 1 or n_buckets.numel() < 1:
+        raise _lib.IvxError("time_buckets_into: output buffers too small")
+    _req(bucket_of_t, torch.int32, "bucket_of_t"); _req(bucket_ts, torch.int64, "bucket_ts")
+    _req(bucket_start, torch.int32, "bucket_start"); _req(n_buckets, torch.int64, "n_buckets")
+    check(lib().ivx_time_buckets(n_t, _ptr(_req(ts, torch.int64, "ts")), int(bucket_ticks), _ptr(bucket_of_t),
+                                 _ptr(bucket_ts), _ptr(bucket_start), _ptr(n_buckets), _stream()), "ivx_time_buckets")
+    _count("time_buckets")
+
+
+def ohlc_time_major(x: torch.Tensor, n_series: int, bucket_start: torch.Tensor, n_buckets: int, min_count: int,
+                    outs: Optional[Sequence[torch.Tensor]] = None, count: Optional[torch.Tensor] = None):
     """x[t*n_series+s] -> four [n_buckets*n_series] candle arrays + int32 counts per bucket."""
     n_t = x.numel() // max(1, n_series)
-    outs = [_empty(n_buckets * n_series, torch.float64, x) for _ in range(4)]
-    cnt = _empty(n_buckets, torch.int32, x)
+    if outs is None:
+        outs = [_empty(n_buckets * n_series, torch.float64, x) for _ in range(4)]
+    elif len(outs) != 4 or any(o.numel() < n_buckets * n_series or o.dtype != torch.float64 for o in outs):
+        raise _lib.IvxError("outs must be four float64 tensors of at least n_buckets*n_series elements")
+    cnt = count if count is not None else _empty(n_buckets, torch.int32, x)
+    if cnt.dtype != torch.int32 or cnt.numel() < n_buckets:
+        raise _lib.IvxError("count must be int32[n_buckets]")
     check(lib().ivx_ohlc_time_major(n_t, n_series, _ptr(_req(x, torch.float64, "x")), n_buckets,
                                     _ptr(_req(bucket_start, torch.int32, "bucket_start")), int(min_count),
                                     _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(cnt), _stream()),
@@ -280,14 +299,19 @@ def bs_greeks(S, K, T, r, sigma, is_call, reference_put_rho_sign: bool = True) -
 # Kernel D
 # ------------------------------------------------------------------------------------------------
 def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, *,
-                    max_knots: int, extrap: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    max_knots: int, extrap: int = 1, out: Optional[torch.Tensor] = None,
+                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     n_slices = knot_off.numel() - 1
     n_q = xq.numel()
     _req(knot_off, torch.int64, "knot_off")
     for t in (x, y, xq):
         _req(t, torch.float64, "spline column")
     yq = out if out is not None else _empty(n_slices * n_q, torch.float64, x)
-    ws = _empty(256, torch.uint8, x)
+    ws = workspace if workspace is not None else _empty(256, torch.uint8, x)
+    if ws.numel() < 256:
+        raise _lib.IvxError("spline workspace must hold 256 bytes")
+    if yq.numel() < n_slices * n_q or x.numel() != y.numel():
+        raise _lib.IvxError("spline_fit_eval: output too small or x/y length mismatch")
     check(lib().ivx_spline_fit_eval(n_slices, _ptr(knot_off), int(max_knots), _ptr(x), _ptr(y), n_q, _ptr(xq),
                                     int(extrap), _ptr(yq), _ptr(ws), 256, _stream()), "ivx_spline_fit_eval")
     _count("spline_fit_eval")
@@ -305,6 +329,28 @@ def spline_strided(x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, n_systems
     check(lib().ivx_spline_strided(n_systems, n_knots, _ptr(x), _ptr(y), n_q, _ptr(xq), int(extrap), _ptr(yq),
                                    _stream()), "ivx_spline_strided")
     _count("spline_strided")
+    return yq
+
+
+def spline_strided_batched(x: torch.Tensor, x_batch_stride: int, x_knot_stride: int, y: torch.Tensor, xq: torch.Tensor,
+                           n_batches: int, n_systems: int, n_knots: int, *, extrap: int = 1,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``n_batches`` planes of ``n_systems`` splines: y[b][knot][system] -> yq[b][query][system]; the abscissae of
+    plane b are read in place at ``x[b*x_batch_stride + i*x_knot_stride]``."""
+    n_q = xq.numel()
+    for t in (x, y, xq):
+        _req(t, torch.float64, "spline column")
+    if y.numel() != n_batches * n_knots * n_systems:
+        raise _lib.IvxError("y must be [n_batches][n_knots][n_systems]")
+    if n_batches and x.numel() <= (n_batches - 1) * x_batch_stride + (n_knots - 1) * x_knot_stride:
+        raise _lib.IvxError("x is too short for the given strides")
+    yq = out if out is not None else _empty(n_batches * n_q * n_systems, torch.float64, y)
+    check(lib().ivx_spline_strided_batched(n_batches, n_systems, n_knots, _ptr(x), int(x_batch_stride), int(x_knot_stride),
+                                           _ptr(y), n_q, _ptr(xq), int(extrap), _ptr(yq), _stream()),
+          "ivx_spline_strided_batched")
+    _LAUNCH_EXTRA = (n_batches + 65534) // 65535
+    global _LAUNCHES
+    _LAUNCHES += max(1, _LAUNCH_EXTRA)
     return yq
 
 

@@ -1,0 +1,266 @@
+"""The north_star pipeline for one option chain (one underlying, one trading day):
+
+    quotes --(kernel C: Black-Scholes implied vol, one thread per quote)--> iv[t][expiry][strike]
+           --(kernel D: natural cubic spline across strike, per (timestamp, expiry) slice)--> smile[t][expiry][grid_k]
+           --(kernel D': natural cubic spline across maturity, per (timestamp, grid strike))--> surface[t][grid_m][grid_k]
+           --(kernel B': OHLC over epoch-anchored time buckets, per surface point)--> candles[bucket][grid_m][grid_k]
+
+The reference has no such code: its conventions come from reference
+src/interpolation/greeks.py:21-22 (pricing) and src/candle_reconstruction/core.py:68-89 (bucketing and the
+first/max/min/last aggregation, complete-bucket rule).  All compute is in libivx.so; torch supplies memory
+and streams.  Quotes are laid out time-major, ``q = (t * n_exp + e) * n_strike + k``, so each
+(timestamp, expiry) smile is one contiguous slice of the quote columns and no reshuffle is needed
+between the stages.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import device as D
+from ._lib import IvxError
+
+QUOTE_F64 = ("price", "S", "K", "T", "r")
+
+
+@dataclass
+class ChainSpec:
+    n_t: int                      # timestamps (ticks) of the day
+    n_exp: int                    # expiries
+    n_strike: int                 # quoted strikes per expiry
+    n_grid_k: int = 512           # output strike grid
+    n_grid_m: int = 64            # output maturity grid
+    bucket_ticks: int = 60_000_000   # candle width in ts ticks (1 min at datetime64[us])
+    min_count: int = 1            # a bucket is kept iff it holds at least this many stamps (candle core.py:87-89)
+    extrap: int = 2               # outside the quoted strikes/maturities: clamp flat
+
+    @property
+    def n_quotes(self) -> int:
+        return self.n_t * self.n_exp * self.n_strike
+
+    @property
+    def n_series(self) -> int:
+        return self.n_grid_m * self.n_grid_k
+
+
+@dataclass
+class QuoteChain:
+    """Device-resident quotes of one chain, structure of arrays (49 B per quote with the IV output)."""
+    spec: ChainSpec
+    ts: torch.Tensor              # int64[n_t]
+    price: torch.Tensor           # float64[n_quotes]
+    S: torch.Tensor
+    K: torch.Tensor
+    T: torch.Tensor
+    r: torch.Tensor
+    is_call: torch.Tensor         # uint8[n_quotes]
+    grid_k: torch.Tensor          # float64[n_grid_k] strikes of the output grid, ascending
+    grid_m: torch.Tensor          # float64[n_grid_m] maturities (years) of the output grid, ascending
+
+    def check(self) -> None:
+        n = self.spec.n_quotes
+        for name in QUOTE_F64:
+            t = getattr(self, name)
+            if t.dtype != torch.float64 or t.numel() != n:
+                raise IvxError(f"QuoteChain.{name}: expected float64[{n}]")
+        if self.is_call.dtype != torch.uint8 or self.is_call.numel() != n:
+            raise IvxError(f"QuoteChain.is_call: expected uint8[{n}]")
+        if self.ts.dtype != torch.int64 or self.ts.numel() != self.spec.n_t:
+            raise IvxError("QuoteChain.ts: expected int64[n_t]")
+        if self.grid_k.numel() != self.spec.n_grid_k or self.grid_m.numel() != self.spec.n_grid_m:
+            raise IvxError("QuoteChain grids do not match the spec")
+
+
+@dataclass
+class SurfaceResult:
+    iv: torch.Tensor              # float64[n_quotes]
+    smile: torch.Tensor           # float64[n_t * n_exp * n_grid_k]
+    surface: torch.Tensor         # float64[n_t * n_grid_m * n_grid_k]
+    bucket_ts: torch.Tensor       # int64[n_buckets]
+    count: torch.Tensor           # int32[n_buckets] stamps per bucket
+    open: torch.Tensor            # float64[n_buckets * n_series]; NaN rows where count < min_count
+    high: torch.Tensor
+    low: torch.Tensor
+    close: torch.Tensor
+    n_buckets: int
+
+
+class SurfacePipeline:
+    """Owns the intermediate buffers of one chain shape so that a step allocates nothing."""
+
+    STAGES = ("implied_vol", "spline_strike", "spline_maturity", "candles")
+
+    def __init__(self, spec: ChainSpec, device: torch.device, max_buckets: Optional[int] = None):
+        if device.type != "cuda":
+            raise IvxError("SurfacePipeline needs a CUDA device (no CPU path exists)")
+        self.spec = spec
+        self.device = device
+        f64 = dict(dtype=torch.float64, device=device)
+        self.iv = torch.empty(spec.n_quotes, **f64)
+        self.smile = torch.empty(spec.n_t * spec.n_exp * spec.n_grid_k, **f64)
+        self.surface = torch.empty(spec.n_t * spec.n_series, **f64)
+        self.knot_off = torch.arange(spec.n_t * spec.n_exp + 1, dtype=torch.int64, device=device) * spec.n_strike
+        self.max_buckets = max_buckets if max_buckets is not None else spec.n_t
+        self.candles = [torch.empty(self.max_buckets * spec.n_series, **f64) for _ in range(4)]
+        self.count = torch.empty(self.max_buckets, dtype=torch.int32, device=device)
+        self._ws = torch.empty(256, dtype=torch.uint8, device=device)
+        self._buckets = None       # (ts tensor identity, bucket_ts, bucket_start, n_buckets)
+
+    def plan_buckets(self, ts: torch.Tensor):
+        """Bucket boundaries of the day's stamps (one tiny kernel + an 8-byte read-back, done once per tape)."""
+        _, bucket_ts, bucket_start, nb = D.time_buckets(ts, self.spec.bucket_ticks)
+        if nb > self.max_buckets:
+            raise IvxError(f"{nb} buckets exceed the planned {self.max_buckets}")
+        self._buckets = (ts.data_ptr(), bucket_ts, bucket_start, nb)
+        return self._buckets
+
+    def run(self, q: QuoteChain, events: Optional[Dict[str, List[torch.cuda.Event]]] = None) -> SurfaceResult:
+        """One pass of the hot path.  ``events`` (stage -> [start, end]) are recorded on the current stream."""
+        sp = self.spec
+        if self._buckets is None or self._buckets[0] != q.ts.data_ptr():
+            self.plan_buckets(q.ts)
+        _, bucket_ts, bucket_start, nb = self._buckets
+
+        def mark(stage, k):
+            if events is not None:
+                events[stage][k].record()
+
+        mark("implied_vol", 0)
+        D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv)
+        mark("implied_vol", 1)
+        mark("spline_strike", 0)
+        # knots of slice (t, e): x = the quoted strikes, read in place from the K column
+        D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
+                          out=self.smile, workspace=self._ws)
+        mark("spline_strike", 1)
+        mark("spline_maturity", 0)
+        # plane t: n_grid_k systems with n_exp knots at x = T[t][e][0], read in place from the T column
+        D.spline_strided_batched(q.T, sp.n_exp * sp.n_strike, sp.n_strike, self.smile, q.grid_m,
+                                 sp.n_t, sp.n_grid_k, sp.n_exp, extrap=sp.extrap, out=self.surface)
+        mark("spline_maturity", 1)
+        mark("candles", 0)
+        D.ohlc_time_major(self.surface, sp.n_series, bucket_start, nb, sp.min_count, outs=self.candles, count=self.count)
+        mark("candles", 1)
+        m = nb * sp.n_series
+        return SurfaceResult(self.iv, self.smile, self.surface, bucket_ts, self.count[:nb],
+                             self.candles[0][:m], self.candles[1][:m], self.candles[2][:m], self.candles[3][:m], nb)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Host-facing entry: quotes in (pinned) host memory -> candles in host memory
+# ------------------------------------------------------------------------------------------------------
+@dataclass
+class HostQuoteChunk:
+    """A run of whole time buckets of one chain in host memory (pinned for full PCIe speed): ``ts`` int64[n_t],
+    the five float64 quote columns and ``is_call`` uint8, each n_t*n_exp*n_strike long, time-major."""
+    ts: torch.Tensor
+    price: torch.Tensor
+    S: torch.Tensor
+    K: torch.Tensor
+    T: torch.Tensor
+    r: torch.Tensor
+    is_call: torch.Tensor
+
+    @property
+    def n_t(self) -> int:
+        return self.ts.numel()
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.ts, self.price, self.S, self.K, self.T, self.r, self.is_call))
+
+
+class HostSurfaceStream:
+    """Streams a day of quotes from host memory through the pipeline, chunk by chunk, double-buffered:
+    while chunk i is being solved on the compute stream, chunk i+1 is on its way over PCIe on the copy
+    stream, and the candles of chunk i-1 are on their way back.  A chunk must hold whole time buckets
+    (the caller cuts the tape at bucket boundaries); every chunk has at most ``chunk_spec.n_t`` stamps.
+    """
+
+    def __init__(self, chunk_spec: ChainSpec, device: torch.device, grid_k: torch.Tensor, grid_m: torch.Tensor,
+                 max_buckets_per_chunk: int):
+        self.spec = chunk_spec
+        self.device = device
+        self.grid_k = grid_k.to(device)
+        self.grid_m = grid_m.to(device)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.out_stream = torch.cuda.Stream(device=device)
+        self.max_buckets = max_buckets_per_chunk
+        n = chunk_spec.n_quotes
+        self.slots = []
+        for _ in range(2):
+            cols = {name: torch.empty(n, dtype=torch.float64, device=device) for name in QUOTE_F64}
+            cols["is_call"] = torch.empty(n, dtype=torch.uint8, device=device)
+            cols["ts"] = torch.empty(chunk_spec.n_t, dtype=torch.int64, device=device)
+            self.slots.append(dict(cols=cols, pipe=SurfacePipeline(chunk_spec, device, max_buckets=max_buckets_per_chunk),
+                                   loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event()))
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _full_chunk(self, ch: HostQuoteChunk) -> None:
+        if ch.n_t != self.spec.n_t:
+            raise IvxError(f"chunk has {ch.n_t} stamps, the stream was planned for {self.spec.n_t} "
+                           "(build a second stream for the ragged tail)")
+
+    def run(self, chunks: List[HostQuoteChunk], out_ohlc: List[torch.Tensor], out_bucket_ts: torch.Tensor,
+            out_count: torch.Tensor) -> int:
+        """Process ``chunks`` in order; candles land in the (pinned) host tensors ``out_ohlc`` (4 x
+        float64[total_buckets * n_series]), bucket stamps/counts in ``out_bucket_ts``/``out_count``.
+        Returns the number of buckets written.  Synchronises once, at the end."""
+        sp = self.spec
+        compute = torch.cuda.current_stream(self.device)
+        n_series = sp.n_series
+        row = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+        for slot in self.slots:
+            slot["drained"].record(compute)
+        pending = []
+        for i, ch in enumerate(chunks):
+            self._full_chunk(ch)
+            slot = self.slots[i & 1]
+            # bucket layout of the chunk is host knowledge: stamps are host data
+            b = ch.ts // sp.bucket_ticks if ch.ts.dtype == torch.int64 else None
+            nb = int(torch.unique_consecutive(b).numel())
+            if nb > self.max_buckets:
+                raise IvxError(f"chunk {i} spans {nb} buckets (> {self.max_buckets})")
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(slot["drained"])          # the slot's previous results have left
+                for name in QUOTE_F64 + ("is_call", "ts"):
+                    slot["cols"][name].copy_(getattr(ch, name), non_blocking=True)
+                slot["loaded"].record(self.copy_stream)
+            self.h2d_bytes += ch.nbytes()
+            compute.wait_event(slot["loaded"])
+            c = slot["cols"]
+            q = QuoteChain(sp, c["ts"], c["price"], c["S"], c["K"], c["T"], c["r"], c["is_call"], self.grid_k, self.grid_m)
+            pipe = slot["pipe"]
+            pipe._buckets = None
+            # time_buckets reads its count back (8 bytes): the host already knows nb, so plan without the sync
+            _, bucket_ts, bucket_start, _ = _plan_buckets_nosync(pipe, c["ts"], nb)
+            res = pipe.run(q)
+            slot["computed"].record(compute)
+            with torch.cuda.stream(self.out_stream):
+                self.out_stream.wait_event(slot["computed"])
+                m = nb * n_series
+                for k, src in enumerate((res.open, res.high, res.low, res.close)):
+                    out_ohlc[k][row * n_series: row * n_series + m].copy_(src[:m], non_blocking=True)
+                out_bucket_ts[row: row + nb].copy_(bucket_ts[:nb], non_blocking=True)
+                out_count[row: row + nb].copy_(pipe.count[:nb], non_blocking=True)
+                slot["drained"].record(self.out_stream)
+            self.d2h_bytes += 4 * m * 8 + nb * 12
+            row += nb
+        compute.wait_stream(self.out_stream)
+        compute.synchronize()
+        return row
+
+
+def _plan_buckets_nosync(pipe: SurfacePipeline, ts: torch.Tensor, nb: int):
+    n_t = ts.numel()
+    if not hasattr(pipe, "_bk"):
+        dev = ts.device
+        pipe._bk = (torch.empty(n_t, dtype=torch.int32, device=dev), torch.empty(n_t, dtype=torch.int64, device=dev),
+                    torch.empty(n_t + 1, dtype=torch.int32, device=dev), torch.empty(1, dtype=torch.int64, device=dev))
+    bucket_of_t, bucket_ts, bucket_start, nbuf = pipe._bk
+    D.time_buckets_into(ts, pipe.spec.bucket_ticks, bucket_of_t, bucket_ts, bucket_start, nbuf)
+    pipe._buckets = (ts.data_ptr(), bucket_ts, bucket_start, nb)
+    return pipe._buckets

@@ -261,3 +261,91 @@ def make_smile_slices(seed: int, n_slices: int, n_knots_lo: int = 50, n_knots_hi
         y[rng.random(len(y)) < nan_frac] = np.nan
     xq = np.linspace(0.45, 1.55, n_query)
     return off, x, y, xq
+
+
+def make_quote_chain(seed: int, spec, device, s0: float = 4500.0, t0: int = T0_US + 34_200 * US, tick_us: int = US,
+                     chunk_t: int = 128, drop_frac: float = 0.0):
+    """Config 2: one SPX-like chain, ``spec.n_t`` ticks x ``spec.n_exp`` expiries x
+    ``spec.n_strike`` strikes, generated on ``device`` with torch's seeded generator, time-major.
+
+    spot: geometric random walk; strikes: a fixed ladder over [0.5, 1.5] s0; T_e(t) = (7 + 12 e) days - t;
+    sigma: a skewed smile in ln(K/S)/sqrt(T) clipped to [0.05, 1.5] plus 0.3 vol-point noise; 90 % of the
+    quotes are out-of-the-money options, 10 % their in-the-money twins; r = 0.05.  Prices come from the
+    library's own forward pricer (ivx_bs_price).  ``drop_frac`` of the prices are set to NaN (missing quotes).
+    Returns a surface.QuoteChain.
+    """
+    import torch
+
+    from . import device as D
+    from .surface import QuoteChain
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    f64 = dict(dtype=torch.float64, device=device)
+    n_t, n_e, n_k = spec.n_t, spec.n_exp, spec.n_strike
+    n = spec.n_quotes
+    ts = t0 + torch.arange(n_t, dtype=torch.int64, device=device) * tick_us
+    spot = s0 * torch.exp(torch.cumsum(torch.randn(n_t, generator=g, **f64) * 1e-4, 0))
+    ladder = s0 * torch.linspace(0.5, 1.5, n_k, **f64)
+    T0 = (7.0 + 12.0 * torch.arange(n_e, **f64)) / 365.0
+    level = 0.2 + 0.02 * torch.sin(torch.arange(n_t, **f64) * (6.283185307179586 / max(1, n_t)))
+    S = torch.empty(n, **f64); K = torch.empty(n, **f64); T = torch.empty(n, **f64)
+    sigma = torch.empty(n, **f64)
+    is_call = torch.empty(n, dtype=torch.uint8, device=device)
+    per_t = n_e * n_k
+    ke = (torch.arange(n_e, device=device)[:, None] * 3 + torch.arange(n_k, device=device)[None, :] * 7)
+    for a in range(0, n_t, chunk_t):
+        b = min(n_t, a + chunk_t)
+        sl = slice(a * per_t, b * per_t)
+        s_ = spot[a:b, None, None].expand(b - a, n_e, n_k)
+        k_ = ladder[None, None, :].expand(b - a, n_e, n_k)
+        t_ = (T0[None, :, None] - (ts[a:b, None, None] - t0).to(torch.float64) / (365.0 * DAY_US)).expand(b - a, n_e, n_k)
+        m = torch.log(k_ / s_) / torch.sqrt(t_)
+        sg = level[a:b, None, None] + 0.35 * m * m - 0.08 * m + 0.003 * torch.randn(b - a, n_e, n_k, generator=g, **f64)
+        S[sl] = s_.reshape(-1); K[sl] = k_.reshape(-1); T[sl] = t_.reshape(-1)
+        sigma[sl] = sg.clamp_(0.05, 1.5).reshape(-1)
+        otm_call = k_ >= s_
+        flip = ((ke[None] + torch.arange(a, b, device=device)[:, None, None]) % 10) == 0
+        is_call[sl] = (otm_call ^ flip).to(torch.uint8).reshape(-1)
+        del s_, k_, t_, m, sg, otm_call, flip
+    r = torch.full((n,), 0.05, **f64)
+    price = D.bs_price(S, K, T, r, sigma, is_call)
+    if drop_frac > 0:
+        for a in range(0, n, 1 << 26):
+            b = min(n, a + (1 << 26))
+            price[a:b][torch.rand(b - a, generator=g, device=device) < drop_frac] = float("nan")
+    grid_k = s0 * torch.linspace(0.55, 1.45, spec.n_grid_k, **f64)
+    grid_m = torch.linspace(10.0 / 365.0, 340.0 / 365.0, spec.n_grid_m, **f64)
+    chain = QuoteChain(spec, ts, price, S, K, T, r, is_call, grid_k, grid_m)
+    chain.sigma_true = sigma
+    return chain
+
+
+def make_quote_chain_np(seed: int, n_t: int, n_exp: int, n_strike: int, pricer, n_grid_k: int = 512, n_grid_m: int = 64,
+                        s0: float = 4500.0, t0: int = T0_US + 34_200 * US, tick_us: int = US, drop_frac: float = 0.0):
+    """Host (numpy) twin of ``make_quote_chain`` — same shapes and distributions, numpy's generator — for the CPU
+    baseline and the small parity cases.  ``pricer(S,K,T,r,sigma,is_call)`` supplies the prices.
+    Returns a dict of arrays: ts, price, S, K, T, r, is_call, sigma_true, grid_k, grid_m."""
+    rng = np.random.default_rng(seed)
+    ts = t0 + np.arange(n_t, dtype=np.int64) * tick_us
+    spot = s0 * np.exp(np.cumsum(rng.standard_normal(n_t) * 1e-4))
+    ladder = s0 * np.linspace(0.5, 1.5, n_strike)
+    T0 = (7.0 + 12.0 * np.arange(n_exp)) / 365.0
+    level = 0.2 + 0.02 * np.sin(np.arange(n_t) * (2 * np.pi / max(1, n_t)))
+    shape = (n_t, n_exp, n_strike)
+    S = np.broadcast_to(spot[:, None, None], shape)
+    K = np.broadcast_to(ladder[None, None, :], shape)
+    T = np.broadcast_to(T0[None, :, None] - ((ts - t0) / (365.0 * DAY_US))[:, None, None], shape)
+    m = np.log(K / S) / np.sqrt(T)
+    sigma = np.clip(level[:, None, None] + 0.35 * m * m - 0.08 * m + 0.003 * rng.standard_normal(shape), 0.05, 1.5)
+    ke = np.arange(n_exp)[:, None] * 3 + np.arange(n_strike)[None, :] * 7
+    flip = ((ke[None] + np.arange(n_t)[:, None, None]) % 10) == 0
+    is_call = ((K >= S) ^ flip).astype(np.uint8)
+    flat = lambda a: np.ascontiguousarray(a).reshape(-1)
+    S, K, T, sigma, is_call = flat(S), flat(K), flat(T), flat(sigma), flat(is_call)
+    r = np.full(S.shape, 0.05)
+    price = np.asarray(pricer(S, K, T, r, sigma, is_call), dtype=np.float64)
+    if drop_frac > 0:
+        price[rng.random(price.shape) < drop_frac] = np.nan
+    return dict(ts=ts, price=price, S=S, K=K, T=T, r=r, is_call=is_call, sigma_true=sigma,
+                grid_k=s0 * np.linspace(0.55, 1.45, n_grid_k), grid_m=np.linspace(10.0 / 365.0, 340.0 / 365.0, n_grid_m))

@@ -233,7 +233,17 @@ def test_implied_vol_vs_oracle(dev):
     sig, iters = sig.cpu().numpy(), iters.cpu().numpy()
     want = O.implied_vol(price, S, K, T, r, q.is_call)
     dom = O.implied_vol_domain(price, S, K, T, r, q.is_call)
-    assert np.isnan(sig[~dom]).all(), "quotes outside the invertible domain must come back NaN"
+    # exp(-rT) differs by an ulp between libm and CUDA, so quotes sitting ON a no-arbitrage bound
+    # (deep in-the-money prices equal to intrinsic value in fp64) may fall on either side of it
+    with np.errstate(all="ignore"):
+        kd = K * np.exp(-r * T)
+        lower = np.maximum(np.where(q.is_call != 0, S - kd, kd - S), 0.0)
+        upper = np.where(q.is_call != 0, S, kd)
+        ulp = np.spacing(np.maximum(np.abs(S), np.abs(K)))
+        on_bound = (np.abs(price - lower) <= 8 * ulp) | (np.abs(price - upper) <= 8 * ulp)
+    clear_out = ~dom & ~(on_bound & np.isfinite(price))
+    bad = np.flatnonzero(clear_out & ~np.isnan(sig))
+    assert len(bad) == 0, f"quotes outside the invertible domain must come back NaN: {bad[:5]}, price {price[bad[:5]]}, S {S[bad[:5]]}, K {K[bad[:5]]}, T {T[bad[:5]]}, sigma {sig[bad[:5]]}"
     both = ~np.isnan(want) & ~np.isnan(sig)
     # NaN masks agree except where the time value is at rounding level (target price ~ 0)
     mism = np.isnan(want) != np.isnan(sig)
@@ -248,8 +258,13 @@ def test_implied_vol_vs_oracle(dev):
     assert fwd_ok.mean() >= 0.90, f"only {fwd_ok.mean():.3f} of finite IVs within 1e-8"
     assert iters[both].max() <= 64 and iters[both].mean() < 12
     # round trip on the well-conditioned core: sigma -> price -> sigma
-    core = both & (np.abs(np.log(S / K)) < 0.25) & (T > 0.05)
-    assert np.abs(sig[core] - q.sigma_true[core]).max() <= 1e-8
+    with np.errstate(all="ignore"):
+        core = both & (np.abs(np.log(S / K)) < 0.25) & (T > 0.05) & (price - lower > 1e-6 * S)
+    rt = np.abs(sig - q.sigma_true)
+    worst = int(np.argmax(np.where(core, rt, 0.0)))
+    assert core.sum() > 3000 and rt[worst] <= 1e-8, (
+        f"round trip worst {rt[worst]:.3e} at S={S[worst]!r} K={K[worst]!r} T={T[worst]!r} price={price[worst]!r} "
+        f"call={q.is_call[worst]} sigma_true={q.sigma_true[worst]!r} got={sig[worst]!r} oracle={want[worst]!r}")
 
 
 @pytest.mark.parametrize("extrap", [0, 1, 2])
