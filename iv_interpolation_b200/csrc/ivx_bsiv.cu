@@ -10,11 +10,18 @@
 // moved across put-call parity).  b is increasing in s with its inflection at s_c = sqrt(2|x|):
 //   * beta <  b(s_c): root in the convex branch — solve ln b(s) = ln beta, evaluated through
 //     erfcx so that deep-wing prices never underflow: b = E/2 [erfcx(q1) - erfcx(q2)],
-//     E = exp(-(h^2+t^2)/2), h = x/s, t = s/2, q1,2 = (|h| -+ t)/sqrt2, b' = E/sqrt(2 pi);
+//     E = exp(-(h^2+t^2)/2), h = |x|/s, t = s/2, q1,2 = (h -+ t)/sqrt2, b' = E/sqrt(2 pi);
 //   * beta >= b(s_c): root in the concave branch — solve b(s) = beta directly.
-// Both branches run bracketed Halley iterations (third order) and fall back to bisection of the
-// bracket when a step leaves it ("Newton/Brent" safeguarding); a warp leaves the loop when every
-// lane has converged (warp vote).  Loads are structure-of-arrays, one coalesced stream per column.
+// The fp64 pipe is this kernel's roofline (ncu: profiles/), so the solver is split in two phases:
+//   1. an fp32 PRE-SOLVE (FP32 pipe + MUFU, runs in the shadow of other warps' fp64 work): the
+//      closed-form guess at the inflection point followed by four bracketed Halley iterations
+//      in single precision — leaves s to ~1e-7 relative on all but a few 1e-4 of the quotes;
+//   2. an fp64 POLISH: bracketed Halley iterations (third order; two divisions, two erfcx|erfc
+//      and one log|exp each) until a step is below 1e-4 s — after such a step the remaining
+//      error is ~1e-13 s — with bisection of the bracket whenever a step leaves it
+//      ("Newton/Brent" safeguarding).  Nearly every warp leaves after ONE fp64 evaluation; a
+//      warp leaves the loop when all its lanes have converged (warp vote).
+// Loads are structure-of-arrays, one coalesced stream per column.
 #include "ivx_common.cuh"
 
 namespace ivx {
@@ -26,74 +33,83 @@ constexpr double SQRT_2PI = 2.5066282746310002;
 constexpr double INV_SQRT_2PI = 0.3989422804014327;
 constexpr double S_MAX = 40.0;   // sigma*sqrt(T) bracket; fp64 prices cannot encode more than ~17
 constexpr int MAX_ITERS = 64;
+constexpr int PRE_ITERS = 4;
+constexpr double ACCEPT_STEP = 1e-4;   // relative size of a Halley step after which s is converged (cubic)
 
 __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * INV_SQRT2); }
 __device__ __forceinline__ double norm_pdf(double z) { return INV_SQRT_2PI * exp(-0.5 * z * z); }
 
-// normalised OTM price in the concave branch (s >= s_c, so h + t >= 0)
-__device__ __forceinline__ void eval_upper(double x, double ex2, double iex2, double s, double& b, double& db,
-                                           double& d2ratio) {
-  const double h = x / s, t = 0.5 * s;
-  b = ex2 * norm_cdf(h + t) - iex2 * norm_cdf(h - t);
-  db = INV_SQRT_2PI * exp(-0.5 * (h * h + t * t));
-  d2ratio = h * h / s - 0.25 * s;    // b''/b'
-}
-
-// ln b, (ln b)', via scaled complementary error functions (s <= ~s_c, so q1 >= 0 up to overshoot)
-__device__ __forceinline__ void eval_lower(double x, double s, double& lnb, double& dlnb, double& d2ratio_b) {
-  const double h = -x / s /* = |h| */, t = 0.5 * s;
-  const double D = erfcx((h - t) * INV_SQRT2) - erfcx((h + t) * INV_SQRT2);
-  lnb = -0.5 * (h * h + t * t) + log(0.5 * D);
-  dlnb = 2.0 * INV_SQRT_2PI / D;      // b'/b = (E/sqrt(2pi)) / (E D / 2)
-  d2ratio_b = h * h / s - 0.25 * s;   // b''/b'
-}
-
-__device__ __forceinline__ double solve_total_vol(double x, double beta, int& iters) {
-  // x <= 0, 0 < beta < e^{x/2}
-  const double ex2 = exp(0.5 * x), iex2 = 1.0 / ex2;
-  const double s_c = sqrt(-2.0 * x);
-  const double b_c = 0.5 * ex2 - iex2 * 0.5 * erfc(s_c * INV_SQRT2);
-  const bool lower = beta < b_c;
-  double lo, hi, s;
-  double lnbeta = 0.0;
+// ---- phase 1: single precision -------------------------------------------------------------------------
+// x <= 0, 0 < beta < e^{x/2}; lnbeta only used (and only valid) when `lower`.  Returns the guess for s.
+__device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta, float ex2, float iex2, float s_c,
+                                              float b_c, bool lower) {
+  const float kInvSqrt2 = 0.70710678f, kSqrt2Pi = 2.50662827f;
+  float lo, hi, s;
   if (lower) {
-    lnbeta = log(beta);
-    lo = 0.0; hi = s_c;
+    lo = 0.0f; hi = s_c;
     // match ln b ~ C - x^2/(2 s^2) at s_c  ->  s0 = |x| / sqrt(2 (ln b_c - ln beta) + |x|/2)
-    s = -x / sqrt(2.0 * (log(b_c) - lnbeta) - 0.5 * x);
+    s = -x * rsqrtf(2.0f * (__logf(b_c) - lnbeta) - 0.5f * x);
   } else {
-    lo = s_c; hi = S_MAX;
-    s = s_c + (beta - b_c) * SQRT_2PI * iex2;   // Newton step from the inflection point (stays left of the root)
+    lo = s_c; hi = (float)S_MAX;
+    s = s_c + (beta - b_c) * kSqrt2Pi * iex2;        // Newton step from the inflection point
   }
-  if (!(s > lo && s < hi)) s = 0.5 * (lo + hi);
+  if (!(s > lo && s < hi)) s = 0.5f * (lo + hi);
+#pragma unroll
+  for (int it = 0; it < PRE_ITERS; ++it) {
+    const float inv_s = __fdividef(1.0f, s);
+    const float h = -x * inv_s, t = 0.5f * s;        // h >= 0
+    const float r2 = h * h * inv_s - 0.25f * s;      // b''/b'
+    float g, newton, den;
+    if (lower) {
+      const float D = erfcxf((h - t) * kInvSqrt2) - erfcxf((h + t) * kInvSqrt2);
+      g = -0.5f * (h * h + t * t) + __logf(0.5f * D) - lnbeta;
+      newton = -g * D * (0.5f * kSqrt2Pi);           // -g / (ln b)',  (ln b)' = 2 / (sqrt(2 pi) D)
+      den = 1.0f + 0.5f * newton * r2 + 0.5f * g;    // 1 + newton/2 * ((ln b)''/(ln b)'),  newton (ln b)' = -g
+    } else {
+      const float b = 0.5f * (ex2 * erfcf((h - t) * kInvSqrt2) - iex2 * erfcf((h + t) * kInvSqrt2));
+      g = b - beta;
+      newton = -g * kSqrt2Pi * __expf(0.5f * (h * h + t * t));
+      den = 1.0f + 0.5f * newton * r2;
+    }
+    if (g > 0.0f) hi = s; else lo = s;
+    float sn = s + ((den > 0.5f && den < 2.0f) ? __fdividef(newton, den) : newton);
+    if (!(sn >= lo && sn <= hi && sn > 0.0f)) sn = 0.5f * (lo + hi);   // also catches NaN
+    s = sn;
+  }
+  return s;
+}
+
+// ---- phase 2: double precision ---------------------------------------------------------------------------
+__device__ __forceinline__ double polish_f64(double x, double beta, double lnbeta, double ex2, double iex2, bool lower,
+                                             double s, int& iters) {
+  double lo = 0.0, hi = S_MAX;
   bool done = false;
   int it = 0;
   while (true) {
     if (!done) {
-      double g, dg, ratio;   // objective, its derivative, g''/g'
+      const double inv_s = 1.0 / s;
+      const double h = -x * inv_s, t = 0.5 * s;      // h >= 0
+      const double r2 = h * h * inv_s - 0.25 * s;
+      const double e = 0.5 * (h * h + t * t);
+      double g, newton, den;
       if (lower) {
-        double lnb, dlnb, r2;
-        eval_lower(x, s, lnb, dlnb, r2);
-        g = lnb - lnbeta;
-        dg = dlnb;
-        ratio = r2 - dlnb;                 // (ln b)''/(ln b)' = b''/b' - b'/b
+        const double D = erfcx((h - t) * INV_SQRT2) - erfcx((h + t) * INV_SQRT2);
+        g = log(0.5 * D) - e - lnbeta;
+        newton = -g * D * (0.5 * SQRT_2PI);
+        den = 1.0 + 0.5 * newton * r2 + 0.5 * g;
       } else {
-        double b, db, r2;
-        eval_upper(x, ex2, iex2, s, b, db, r2);
+        const double b = 0.5 * (ex2 * erfc((h - t) * INV_SQRT2) - iex2 * erfc((h + t) * INV_SQRT2));
         g = b - beta;
-        dg = db;
-        ratio = r2;
+        newton = -g * SQRT_2PI * exp(e);
+        den = 1.0 + 0.5 * newton * r2;
       }
       ++it;
       if (g > 0.0) hi = s; else lo = s;
-      const double newton = -g / dg;
-      const double den = 1.0 + 0.5 * newton * ratio;            // Halley: dn / (1 + dn g''/(2 g'))
       double step = (den > 0.5 && den < 2.0) ? newton / den : newton;
       double sn = s + step;
-      bool safe = (sn > lo) && (sn < hi);
+      const bool safe = (sn >= lo) && (sn <= hi) && (sn > 0.0);          // false for NaN
       if (!safe) { sn = 0.5 * (lo + hi); step = sn - s; }
-      // cubic convergence: a step below 1e-6 s leaves an error far below one ulp
-      if ((safe && fabs(step) <= 1e-6 * sn) || !(hi - lo > 4.0e-16 * hi) || it >= MAX_ITERS) done = true;
+      if ((safe && fabs(step) <= ACCEPT_STEP * sn) || !(hi - lo > 4.0e-16 * hi) || it >= MAX_ITERS) done = true;
       s = sn;
     }
     if (__all_sync(__activemask(), done)) break;
@@ -118,28 +134,36 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol(int64_t n, const double*
   }
   const double kd = k_ * exp(-r_ * t_);
   const double intrinsic = call ? (s_ - kd) : (kd - s_);
-  const double lower = fmax(intrinsic, 0.0);
-  const double upper = call ? s_ : kd;
+  const double lower_bound = fmax(intrinsic, 0.0);
+  const double upper_bound = call ? s_ : kd;
   bool ok = inr && isfinite(p) && isfinite(s_) && isfinite(k_) && isfinite(t_) && isfinite(r_) &&
-            (s_ > 0.0) && (k_ > 0.0) && (t_ > 0.0) && (p > lower) && (p < upper);
+            (s_ > 0.0) && (k_ > 0.0) && (t_ > 0.0) && (p > lower_bound) && (p < upper_bound);
   const double target = intrinsic > 0.0 ? p - intrinsic : p;    // the out-of-the-money twin
   ok = ok && (target > 0.0);
-  double out = qnan();
+  // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}
+  const double mx = fmax(s_, kd), mn = fmin(s_, kd);
+  const double ratio = ok ? mn / mx : 0.9;
+  double x = log(ratio);
+  double ex2 = sqrt(ratio);
+  double beta = ok ? target / (mx * ex2) : 0.05;
+  if (ok && !(beta < ex2)) ok = false;                           // rounding pushed it onto the bound
+  if (!ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9: solved alongside, result dropped
+  const double iex2 = 1.0 / ex2;
+
+  const float xf = (float)x;
+  const float ex2f = (float)ex2, iex2f = (float)iex2;
+  const float s_cf = sqrtf(-2.0f * xf);
+  const float b_cf = 0.5f * (ex2f - iex2f * erfcf(s_cf * 0.70710678f));
+  const bool lower = beta < (double)b_cf;
+  const double lnbeta = lower ? log(beta) : 0.0;
+  float s0 = presolve_f32(xf, (float)beta, (float)lnbeta, ex2f, iex2f, s_cf, b_cf, lower);
+  double s = (double)s0;
+  if (!(s > 0.0 && s < S_MAX)) s = fmax(sqrt(-2.0 * x), 0.1);  // fp32 range exhausted: start at the inflection point
   int it = 0;
-  // warp-uniform entry keeps the vote inside solve_total_vol well defined
-  const unsigned live = __ballot_sync(IVX_FULL_MASK, ok);
-  if (live) {
-    double x = ok ? -fabs(log(s_ / kd)) : -0.1;
-    double beta = ok ? target / sqrt(s_ * kd) : 0.05;
-    const double bmax = exp(0.5 * x);
-    if (ok && !(beta < bmax)) { ok = false; x = -0.1; beta = 0.05; }   // rounding pushed it onto the bound
-    int its;
-    double s = solve_total_vol(x, beta, its);
-    if (ok) { out = s / sqrt(t_); it = its; }
-  }
+  s = polish_f64(x, beta, lnbeta, ex2, iex2, lower, s, it);
   if (inr) {
-    st_stream(sigma + i, out);
-    if (iters) st_stream(iters + i, it);
+    st_stream(sigma + i, ok ? s / sqrt(t_) : qnan());
+    if (iters) st_stream(iters + i, ok ? it : 0);
   }
 }
 
