@@ -4,16 +4,24 @@
 // slice, fit the natural cubic spline through the quoted (strike, IV) knots and evaluate it on a
 // shared strike grid; then the same across maturities for every grid strike.
 //
-// ivx_spline_fit_eval — one WARP per slice, slice staged in shared memory (x, y, c', d'/M: 32 B per
-//   knot, so a 2000-knot slice is 64 KB and three slices are resident per SM).  The second
-//   derivatives M solve the tridiagonal system  h[i-1] M[i-1] + 2(h[i-1]+h[i]) M[i] + h[i] M[i+1] =
-//   6 (dy[i]/h[i] - dy[i-1]/h[i-1]),  M[0] = M[n-1] = 0.  The system is strictly diagonally
-//   dominant, so both Thomas recurrences forget their start geometrically (c' contracts by
-//   <= 0.083 per row, the right-hand-side recurrence by a_i/den_i, 0.27 on a uniform grid).  Each
-//   lane therefore owns a contiguous chunk of rows and warms its recurrences up over a HALO of rows
-//   before (forward) / after (backward) the chunk: 32-way parallel with O(n) work per slice —
-//   a cyclic-reduction solve would need 2 fp64 divisions per row per level, ~10x the flops, and
-//   this kernel is fp64-pipe bound, not HBM bound, at 2000 knots.
+// ivx_spline_fit_eval — a GROUP of G threads per slice (G = 32 ... 1024 chosen from max_knots; 256 for
+//   the 2000-strike chains), 8 consecutive rows per thread held in REGISTERS; the slice is staged once
+//   into (padded, conflict-free) shared memory with coalesced loads, which is also where non-finite
+//   knots are squeezed out.  The second derivatives M solve the tridiagonal system
+//       h[i-1] M[i-1] + 2(h[i-1]+h[i]) M[i] + h[i] M[i+1] = 6 (dy[i]/h[i] - dy[i-1]/h[i-1]),  M[0] = M[n-1] = 0.
+//   Thomas elimination is a chain of 2n dependent divisions; written in homogeneous form it is LINEAR:
+//       q[i] = b[i] q[i-1] - h[i-1]^2 q[i-2]   (q = leading principal minors, c'[i] = h[i] q[i-1]/q[i])
+//       D[i] = r[i] q[i-1] - h[i-1] D[i-1]     (d'[i] = D[i]/q[i])
+//   so the state (q[i], q[i-1], D[i]) advances by a 3x3 matrix per row.  Each thread multiplies out its
+//   8 rows (no division), the group runs a parallel prefix over those matrices (warp shuffles, then
+//   one shared-memory hop between warps), and every thread re-walks its rows from the exact incoming
+//   state — the divisions that are left (one per row, for 1/q[i]) are independent of each other.
+//   Back-substitution M[i] = d'[i] - c'[i] M[i+1] is an affine map per row: same pattern, suffix scan
+//   of 2-vectors.  The whole solve is exact (no truncated halo), O(n) work, depth 8 + log2(G); prefix
+//   products are renormalised by powers of two (the recurrences are homogeneous), so no range limit.
+//   Each thread then evaluates the grid points that fall inside its own 8 segments (the grid is sorted:
+//   two binary searches give its range) straight from registers.
+//   HBM traffic: 16 B per knot read once, 8 B per grid point written once.
 // ivx_spline_strided — one THREAD per system for the many tiny systems of the maturity direction,
 //   data laid out [knot][system] so every load/store is coalesced; when no knot is missing the LU
 //   factors depend only on the shared abscissae and are computed once per CTA in shared memory.
@@ -22,8 +30,7 @@
 namespace ivx {
 namespace {
 
-constexpr int HALO = 64;
-constexpr int SPL_MAX_WARPS = 8;
+constexpr int SPL_R = 8;          // rows per thread
 constexpr int STRIDED_MAXK = 64;
 
 __device__ __forceinline__ double spline_eval(double xl, double xr, double yl, double yr, double Ml, double Mr, double xq) {
@@ -41,99 +48,266 @@ __device__ __forceinline__ double apply_extrap(double v, double xq, double xlo, 
   return v;
 }
 
-__global__ void __launch_bounds__(SPL_MAX_WARPS * 32) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
+// state transition of the homogeneous elimination: [[A,B,0],[C,E,0],[F,G,H]]
+struct Mat3 {
+  double A, B, C, E, F, G, H;
+};
+__device__ __forceinline__ Mat3 mat_identity() { return Mat3{1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0}; }
+// L * R (R is applied first)
+__device__ __forceinline__ Mat3 mat_mul(const Mat3& L, const Mat3& R) {
+  Mat3 o;
+  o.A = L.A * R.A + L.B * R.C;
+  o.B = L.A * R.B + L.B * R.E;
+  o.C = L.C * R.A + L.E * R.C;
+  o.E = L.C * R.B + L.E * R.E;
+  o.F = L.F * R.A + L.G * R.C + L.H * R.F;
+  o.G = L.F * R.B + L.G * R.E + L.H * R.G;
+  o.H = L.H * R.H;
+  return o;
+}
+// 2^-e for a finite positive m = 1.f x 2^e (1.0 for zero, subnormal, inf, NaN)
+__device__ __forceinline__ double pow2_inv(double m) {
+  const int e = (__double2hiint(m) >> 20) & 0x7ff;
+  return (e == 0 || e == 0x7ff) ? 1.0 : __hiloint2double((2046 - e) << 20, 0);
+}
+__device__ __forceinline__ void mat_normalize(Mat3& P) {
+  const double m = fmax(fmax(fmax(fabs(P.A), fabs(P.B)), fmax(fabs(P.C), fabs(P.E))),
+                        fmax(fmax(fabs(P.F), fabs(P.G)), fabs(P.H)));
+  const double sc = pow2_inv(m);
+  P.A *= sc; P.B *= sc; P.C *= sc; P.E *= sc; P.F *= sc; P.G *= sc; P.H *= sc;
+}
+__device__ __forceinline__ Mat3 mat_shfl_up(const Mat3& P, int d) {
+  Mat3 o;
+  o.A = __shfl_up_sync(IVX_FULL_MASK, P.A, d); o.B = __shfl_up_sync(IVX_FULL_MASK, P.B, d);
+  o.C = __shfl_up_sync(IVX_FULL_MASK, P.C, d); o.E = __shfl_up_sync(IVX_FULL_MASK, P.E, d);
+  o.F = __shfl_up_sync(IVX_FULL_MASK, P.F, d); o.G = __shfl_up_sync(IVX_FULL_MASK, P.G, d);
+  o.H = __shfl_up_sync(IVX_FULL_MASK, P.H, d);
+  return o;
+}
+
+__device__ __forceinline__ int spl_pad(int i) { return i + (i >> 3); }   // 1 pad per 8 doubles: chunk reads are conflict-free
+
+template <int G>
+__device__ __forceinline__ void group_sync(int grp) {
+  if (G == 32) __syncwarp();
+  else if (G >= 256) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G) : "memory");
+}
+
+// first q in [0, n_q) with xq[q] >= v (n_q if none)
+__device__ __forceinline__ int lower_bound_q(const double* __restrict__ xq, int n_q, double v) {
+  int lo = 0, hi = n_q;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(xq + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int G>
+struct SplLayout {
+  static constexpr int BT = G < 256 ? 256 : G;
+  static constexpr int SPB = BT / G;
+  static constexpr int NW = G / 32;
+  static constexpr int CAP = G * SPL_R;
+  static constexpr int PADCAP = CAP + CAP / 8 + 8;                 // rows CAP, CAP+1 exist (read as neighbours)
+  static constexpr int PER_SLICE = 2 * PADCAP + NW * 7 + NW * 2 + NW;   // doubles (the last NW hold int counts)
+  static constexpr size_t SMEM = (size_t)SPB * PER_SLICE * sizeof(double);
+};
+
+template <int G>
+__global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
                                                                        const double* __restrict__ x, const double* __restrict__ y,
                                                                        int n_q, const double* __restrict__ xq, int extrap,
-                                                                       double* __restrict__ yq, int mk,
-                                                                       unsigned long long* counter) {
+                                                                       double* __restrict__ yq) {
+  using L = SplLayout<G>;
   extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* xs = smem + (size_t)warp * 4 * mk;
-  double* ys = xs + mk;
-  double* cp = ys + mk;
-  double* dp = cp + mk;
+  const int grp = threadIdx.x / G, g = threadIdx.x % G;
+  const int lane = threadIdx.x & 31, w = g >> 5;
+  double* xs = smem + (size_t)grp * L::PER_SLICE;
+  double* ys = xs + L::PADCAP;
+  double* wm = ys + L::PADCAP;          // [NW][7] warp totals of the forward scan
+  double* wa = wm + L::NW * 7;          // [NW][2] warp totals of the backward scan
+  int* wc = reinterpret_cast<int*>(wa + L::NW * 2);   // [NW] valid-knot counts
+  const int64_t sl = (int64_t)blockIdx.x * L::SPB + grp;
+  if (sl >= n_slices) return;           // a whole group leaves together (named barriers / warp sync below)
+  const int64_t k0 = knot_off[sl];
+  int m = (int)min((int64_t)L::CAP + 1, knot_off[sl + 1] - k0);
+  if (m > L::CAP) m = 0;                // more knots than the launch was sized for: NaN row (host checks max_knots)
+  double* out = yq + sl * (int64_t)n_q;
 
-  while (true) {
-    unsigned long long sl = 0;
-    if (lane == 0) sl = atomicAdd(counter, 1ull);
-    sl = __shfl_sync(IVX_FULL_MASK, sl, 0);
-    if ((int64_t)sl >= n_slices) break;
-    const int64_t k0 = knot_off[sl], k1 = knot_off[sl + 1];
-    double* out = yq + (int64_t)sl * n_q;
-
-    // ---- stage + compact the usable knots ---------------------------------------------------------
-    int n = 0;
-    for (int64_t base = k0; base < k1; base += 32) {
-      const int64_t i = base + lane;
+  // ---- stage the slice (coalesced), NaN beyond its end ------------------------------------------------
+#pragma unroll
+  for (int r = 0; r < SPL_R + 1; ++r) {
+    const int j = r * G + g;
+    if (j < L::CAP + 2) {
       double xv = qnan(), yv = qnan();
-      if (i < k1) { xv = ld_stream(x + i); yv = ld_stream(y + i); }
-      const bool ok = isfinite(xv) && isfinite(yv);
-      const uint32_t m = __ballot_sync(IVX_FULL_MASK, ok);
-      if (ok) {
-        const int j = n + __popc(m & ((1u << lane) - 1u));
-        xs[j] = xv; ys[j] = yv;
-      }
-      n += __popc(m);
+      if (j < m) { xv = ld_stream(x + k0 + j); yv = ld_stream(y + k0 + j); }
+      xs[spl_pad(j)] = xv; ys[spl_pad(j)] = yv;
     }
-    __syncwarp();
+  }
+  group_sync<G>(grp);
 
-    if (n < 2) {
-      for (int q = lane; q < n_q; q += 32) st_stream(out + q, qnan());
-      __syncwarp();
-      continue;
+  // ---- own rows; squeeze out unusable knots if there are any -----------------------------------------------
+  const int i0 = g * SPL_R;
+  double xv[SPL_R], yv[SPL_R];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < SPL_R; ++j) {
+    xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)];
+    cnt += (isfinite(xv[j]) && isfinite(yv[j])) ? 1 : 0;
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(IVX_FULL_MASK, incl, d);
+    if (lane >= d) incl += u;
+  }
+  int before = incl - cnt, n = __shfl_sync(IVX_FULL_MASK, incl, 31);
+  if (L::NW > 1) {
+    if (lane == 31) wc[w] = incl;
+    group_sync<G>(grp);
+    n = 0;
+#pragma unroll
+    for (int ww = 0; ww < L::NW; ++ww) {
+      const int c = wc[ww];
+      if (ww < w) before += c;
+      n += c;
     }
-    const double xlo = xs[0], xhi = xs[n - 1], ylo = ys[0], yhi = ys[n - 1];
+  }
+  if (n != m) {                          // group-uniform
+    group_sync<G>(grp);                  // every thread holds its rows in registers by now
+    int o = before;
+#pragma unroll
+    for (int j = 0; j < SPL_R; ++j) {
+      if (isfinite(xv[j]) && isfinite(yv[j])) { xs[spl_pad(o)] = xv[j]; ys[spl_pad(o)] = yv[j]; ++o; }
+    }
+#pragma unroll
+    for (int r = 0; r < SPL_R; ++r) {
+      const int j = r * G + g;
+      if (j >= n && j < m) { xs[spl_pad(j)] = qnan(); ys[spl_pad(j)] = qnan(); }
+    }
+    group_sync<G>(grp);
+#pragma unroll
+    for (int j = 0; j < SPL_R; ++j) { xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)]; }
+  }
+  if (n < 2) {
+    for (int q = g; q < n_q; q += G) st_stream(out + q, qnan());
+    return;
+  }
 
-    if (n > 2) {
-      // rows 1..n-2, split in contiguous chunks over the lanes
-      const int m = n - 2;
-      const int chunk = (m + 31) / 32;
-      const int first = 1 + lane * chunk;
-      const int last = min(first + chunk - 1, n - 2);   // inclusive; empty when first > n-2
-      if (first <= n - 2) {
-        int i = max(1, first - HALO);
-        double c_prev = 0.0, d_prev = 0.0;
-        double xm = xs[i - 1], x0 = xs[i], ym = ys[i - 1], y0 = ys[i];
-        double hm = x0 - xm, sm = (y0 - ym) / hm;
-        for (; i <= last; ++i) {
-          const double xp = xs[i + 1], yp = ys[i + 1];
-          const double hp = xp - x0;
-          const double sp = (yp - y0) / hp;
-          const double inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
-          c_prev = hp * inv;
-          d_prev = (6.0 * (sp - sm) - hm * d_prev) * inv;
-          if (i >= first) { cp[i] = c_prev; dp[i] = d_prev; }
-          x0 = xp; y0 = yp; hm = hp; sm = sp;
-        }
-      }
-      __syncwarp();
-      // backward: warm up over the rows after the chunk (owned by higher lanes), then own rows in place
-      double M = 0.0;
-      if (first <= n - 2) {
-        for (int i = min(n - 2, last + HALO); i > last; --i) M = dp[i] - cp[i] * M;
-      }
-      __syncwarp();
-      if (first <= n - 2) {
-        for (int i = last; i >= first; --i) { M = dp[i] - cp[i] * M; dp[i] = M; }
-      }
-      if (lane == 0) { dp[0] = 0.0; dp[n - 1] = 0.0; }
-    } else {
-      if (lane == 0) { dp[0] = 0.0; dp[1] = 0.0; }     // two knots: the straight line
-    }
-    __syncwarp();
+  // ---- row coefficients: hh[k] = x[i0+k] - x[i0+k-1], slopes likewise, k = 0..8 -------------------------
+  double hh[SPL_R + 1], rr[SPL_R];
+  {
+    const double xp = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yp = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
+    const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
+    double ss[SPL_R + 1];
+    hh[0] = xv[0] - xp; ss[0] = (yv[0] - yp) / hh[0];
+#pragma unroll
+    for (int k = 1; k < SPL_R; ++k) { hh[k] = xv[k] - xv[k - 1]; ss[k] = (yv[k] - yv[k - 1]) / hh[k]; }
+    hh[SPL_R] = xn - xv[SPL_R - 1]; ss[SPL_R] = (yn - yv[SPL_R - 1]) / hh[SPL_R];
+#pragma unroll
+    for (int j = 0; j < SPL_R; ++j) rr[j] = 6.0 * (ss[j + 1] - ss[j]);
+  }
+  // row i0+j is an equation of the system iff 1 <= i0+j <= n-2
+  auto interior = [&](int j) { const int i = i0 + j; return i >= 1 && i <= n - 2; };
 
-    // ---- evaluate on the shared grid ---------------------------------------------------------------
-    for (int q = lane; q < n_q; q += 32) {
-      const double xv = __ldg(xq + q);
-      int lo = 0, hi = n - 1;                            // last i in [0, n-2] with xs[i] <= xv
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (xs[mid] <= xv) lo = mid; else hi = mid;
-      }
-      const double v = spline_eval(xs[lo], xs[lo + 1], ys[lo], ys[lo + 1], dp[lo], dp[lo + 1], xv);
-      st_stream(out + q, apply_extrap(v, xv, xlo, xhi, ylo, yhi, extrap));
+  // ---- forward: chunk transition matrix, prefix over the group ----------------------------------------------
+  Mat3 P = mat_identity();
+#pragma unroll
+  for (int j = 0; j < SPL_R; ++j) {
+    if (interior(j)) {
+      const double a = hh[j], b = 2.0 * (hh[j] + hh[j + 1]), ag = a * a, r = rr[j];
+      const double nA = b * P.A - ag * P.C, nB = b * P.B - ag * P.E;
+      const double nF = r * P.A - a * P.F, nG = r * P.B - a * P.G;
+      P.C = P.A; P.E = P.B; P.A = nA; P.B = nB; P.F = nF; P.G = nG; P.H = -a * P.H;
     }
-    __syncwarp();
+  }
+  mat_normalize(P);
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const Mat3 Q = mat_shfl_up(P, d);
+    if (lane >= d) { P = mat_mul(P, Q); mat_normalize(P); }
+  }
+  Mat3 X = mat_shfl_up(P, 1);            // exclusive prefix inside the warp
+  if (lane == 0) X = mat_identity();
+  double q = 1.0, qp = 0.0, D = 0.0;     // state before row 1: q[0] = 1, q[-1] = 0, D[0] = 0
+  if (L::NW > 1) {
+    if (lane == 31) {
+      double* t = wm + w * 7;
+      t[0] = P.A; t[1] = P.B; t[2] = P.C; t[3] = P.E; t[4] = P.F; t[5] = P.G; t[6] = P.H;
+    }
+    group_sync<G>(grp);
+    for (int ww = 0; ww < w; ++ww) {
+      const double* t = wm + ww * 7;
+      const double nq = t[0] * q + t[1] * qp, nqp = t[2] * q + t[3] * qp, nD = t[4] * q + t[5] * qp + t[6] * D;
+      const double sc = pow2_inv(fmax(fmax(fabs(nq), fabs(nqp)), fabs(nD)));
+      q = nq * sc; qp = nqp * sc; D = nD * sc;
+    }
+  }
+  {
+    const double nq = X.A * q + X.B * qp, nqp = X.C * q + X.E * qp, nD = X.F * q + X.G * qp + X.H * D;
+    const double sc = pow2_inv(fmax(fmax(fabs(nq), fabs(nqp)), fabs(nD)));
+    q = nq * sc; qp = nqp * sc; D = nD * sc;
+  }
+  // ---- re-walk the rows from the exact incoming state: Thomas' c', d' ---------------------------------------
+  double cv[SPL_R], dv[SPL_R];
+#pragma unroll
+  for (int j = 0; j < SPL_R; ++j) {
+    cv[j] = 0.0; dv[j] = 0.0;
+    if (interior(j)) {
+      const double a = hh[j], b = 2.0 * (hh[j] + hh[j + 1]);
+      const double qn = b * q - a * a * qp, Dn = rr[j] * q - a * D;
+      const double inv = 1.0 / qn;
+      cv[j] = hh[j + 1] * q * inv;
+      dv[j] = Dn * inv;
+      qp = q; q = qn; D = Dn;
+    }
+  }
+  // ---- backward: M[i] = d'[i] - c'[i] M[i+1] as affine maps, suffix scan ---------------------------------------
+  double al = 0.0, be = 1.0;             // M[first row of the chunk] = al + be * M[first row of the next chunk]
+#pragma unroll
+  for (int j = SPL_R - 1; j >= 0; --j) { al = dv[j] - cv[j] * al; be = -cv[j] * be; }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double al2 = __shfl_down_sync(IVX_FULL_MASK, al, d), be2 = __shfl_down_sync(IVX_FULL_MASK, be, d);
+    if (lane + d < 32) { al = al + be * al2; be = be * be2; }
+  }
+  double z = 0.0;                        // M at the first row of the next warp
+  if (L::NW > 1) {
+    if (lane == 0) { wa[w * 2] = al; wa[w * 2 + 1] = be; }
+    group_sync<G>(grp);
+    for (int ww = L::NW - 1; ww > w; --ww) z = wa[ww * 2] + wa[ww * 2 + 1] * z;
+  }
+  const double m_first = al + be * z;
+  double Mn = __shfl_down_sync(IVX_FULL_MASK, m_first, 1);
+  if (lane == 31) Mn = z;
+#pragma unroll
+  for (int j = SPL_R - 1; j >= 0; --j) { dv[j] = dv[j] - cv[j] * (j == SPL_R - 1 ? Mn : dv[j + 1]); }   // dv = M now
+
+  // ---- evaluate the grid points inside my segments ------------------------------------------------------------
+  if (i0 > n - 2) return;
+  const double xlo = xs[spl_pad(0)], xhi = xs[spl_pad(n - 1)], ylo = ys[spl_pad(0)], yhi = ys[spl_pad(n - 1)];
+  const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
+  const bool owns_last = (n - 2) <= i0 + SPL_R - 1;
+  int qi = g == 0 ? 0 : lower_bound_q(xq, n_q, xv[0]);
+  const int qhi = owns_last ? n_q : lower_bound_q(xq, n_q, xn);
+#pragma unroll
+  for (int j = 0; j < SPL_R; ++j) {
+    const int i = i0 + j;
+    if (i <= n - 2) {
+      const bool lastseg = (i == n - 2);
+      const double xr_ = j < SPL_R - 1 ? xv[j + 1 < SPL_R ? j + 1 : j] : xn;
+      const double yr_ = j < SPL_R - 1 ? yv[j + 1 < SPL_R ? j + 1 : j] : yn;
+      const double Mr_ = j < SPL_R - 1 ? dv[j + 1 < SPL_R ? j + 1 : j] : Mn;
+      while (qi < qhi) {
+        const double xv_q = __ldg(xq + qi);
+        if (!(lastseg || xv_q < xr_)) break;
+        const double v = spline_eval(xv[j], xr_, yv[j], yr_, dv[j], Mr_, xv_q);
+        st_stream(out + qi, apply_extrap(v, xv_q, xlo, xhi, ylo, yhi, extrap));
+        ++qi;
+      }
+    }
   }
 }
 
@@ -243,33 +417,39 @@ using namespace ivx;
 
 extern "C" int64_t ivx_spline_workspace_bytes(int64_t, int64_t) { return 256; }
 
+template <int G>
+static int launch_spline(int64_t n_slices, const int64_t* knot_off, const double* x, const double* y, int n_q,
+                         const double* xq, int extrap, double* yq, cudaStream_t stream) {
+  using L = SplLayout<G>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    attr_set = true;
+  }
+  const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
+  IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
+  k_spline_fit_eval<G><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x, y, n_q, xq, extrap, yq);
+  IVX_LAUNCH_CHECK("k_spline_fit_eval");
+  return IVX_OK;
+}
+
 extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots, const double* x,
                                    const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq,
                                    void* workspace, int64_t workspace_bytes, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  (void)workspace; (void)workspace_bytes;   // kept in the ABI; this version needs no scratch
   IVX_REQUIRE(n_slices >= 0 && max_knots >= 0 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: extrap must be 0, 1 or 2");
   if (n_slices == 0 || n_q == 0) return IVX_OK;
-  IVX_REQUIRE(knot_off && x && y && xq && yq && workspace && workspace_bytes >= 256, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: null pointer or workspace < 256 B");
-  int mk = (int)((max_knots + 3) / 2 * 2);   // room for row n+1 reads, even for 16-byte alignment
-  if (mk < 4) mk = 4;
-  const size_t per_warp = (size_t)mk * 4 * sizeof(double);
-  IVX_REQUIRE(per_warp <= 227 * 1024, IVX_ERR_UNSUPPORTED, "ivx_spline_fit_eval: max_knots %lld needs %zu B of shared memory per slice (limit 227 KB)", (long long)max_knots, per_warp);
-  int warps = (int)((227 * 1024) / per_warp);
-  if (warps > SPL_MAX_WARPS) warps = SPL_MAX_WARPS;
-  const size_t smem = per_warp * warps;
-  IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm * warps > 48) ctas_per_sm = 48 / warps;
-  int64_t grid = (int64_t)sm_count() * ctas_per_sm;
-  const int64_t need = (n_slices + warps - 1) / warps;
-  if (grid > need) grid = need;
-  unsigned long long* counter = (unsigned long long*)workspace;
-  IVX_CUDA(cudaMemsetAsync(counter, 0, 8, stream));
-  k_spline_fit_eval<<<(unsigned)grid, warps * 32, smem, stream>>>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, mk, counter);
-  IVX_LAUNCH_CHECK("k_spline_fit_eval");
-  return IVX_OK;
+  IVX_REQUIRE(knot_off && x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: null pointer");
+  IVX_REQUIRE(max_knots <= 1024 * SPL_R, IVX_ERR_UNSUPPORTED, "ivx_spline_fit_eval: at most %d knots per slice (got max_knots %lld)", 1024 * SPL_R, (long long)max_knots);
+  // slices longer than max_knots come back as NaN rows
+  if (max_knots <= 32 * SPL_R) return launch_spline<32>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
+  if (max_knots <= 64 * SPL_R) return launch_spline<64>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
+  if (max_knots <= 128 * SPL_R) return launch_spline<128>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
+  if (max_knots <= 256 * SPL_R) return launch_spline<256>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
+  if (max_knots <= 512 * SPL_R) return launch_spline<512>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
+  return launch_spline<1024>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
 }
 
 extern "C" int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x, const double* y, int32_t n_q,

@@ -285,6 +285,28 @@ def test_spline_fit_eval_vs_scipy(dev, extrap):
         assert np.abs(got[i][ok] - want[ok]).max(initial=0.0) <= 1e-8, f"slice {i}: {np.abs(got[i][ok] - want[ok]).max()}"
 
 
+@pytest.mark.parametrize("lo,hi,n_slices,nq", [(2, 40, 300, 33), (200, 256, 64, 100), (257, 500, 40, 512), (700, 1024, 24, 64),
+                                               (1500, 2048, 12, 700), (2500, 4096, 6, 512), (5000, 8192, 3, 512)])
+def test_spline_fit_eval_every_group_width(dev, lo, hi, n_slices, nq):
+    """Each slice width class runs a different instantiation (32 ... 1024 threads per slice)."""
+    from iv_interpolation_b200 import device as D
+    off, x, y, xq = tapes.make_smile_slices(lo + hi, n_slices, lo, hi, nq, nan_frac=0.02)
+    x = x * 4500.0                                   # strikes in index points, like the chain tapes
+    xq = xq * 4500.0
+    got = D.spline_fit_eval(_t(off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=hi, extrap=1).cpu().numpy()
+    got = got.reshape(n_slices, -1)
+    for i in range(n_slices):
+        want = O.natural_spline_eval(x[off[i]:off[i + 1]], y[off[i]:off[i + 1]], xq, 1)
+        assert _eq(np.isnan(got[i]), np.isnan(want)), f"slice {i}: NaN mask"
+        ok = ~np.isnan(want)
+        assert np.abs(got[i] - want)[ok].max(initial=0.0) <= 1e-8, f"slice {i}: {np.abs(got[i] - want)[ok].max()}"
+    # a slice longer than the launch was sized for comes back as a NaN row, its neighbours untouched
+    if hi >= 64:
+        short = D.spline_fit_eval(_t(off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=lo - 1 if lo > 40 else 8,
+                                  extrap=1).cpu().numpy().reshape(n_slices, -1)
+        assert np.isnan(short).all()
+
+
 @pytest.mark.parametrize("extrap", [1, 2])
 def test_spline_strided_vs_scipy(dev, extrap):
     from iv_interpolation_b200 import device as D
