@@ -39,6 +39,23 @@ constexpr double ACCEPT_STEP = 1e-4;   // relative size of a Halley step after w
 __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * INV_SQRT2); }
 __device__ __forceinline__ double norm_pdf(double z) { return INV_SQRT_2PI * exp(-0.5 * z * z); }
 
+// erfcx(x) for x >= 0 in single precision: (1 + 2x) erfcx(x) is smooth in t = (x-2)/(x+2) on [-1, 1);
+// degree-9 fit, 5e-7 relative (own Chebyshev fit against scipy.special.erfcx) — 16 instructions.
+__device__ __forceinline__ float erfcx_pos_f(float x) {
+  const float t = __fdividef(x - 2.0f, x + 2.0f);
+  float p = -1.836544373e-04f;
+  p = fmaf(p, t, -9.936979918e-04f);
+  p = fmaf(p, t, 1.043144582e-03f);
+  p = fmaf(p, t, 8.337401823e-03f);
+  p = fmaf(p, t, -7.942721699e-03f);
+  p = fmaf(p, t, -5.408633070e-02f);
+  p = fmaf(p, t, 1.640358396e-01f);
+  p = fmaf(p, t, -1.660467991e-01f);
+  p = fmaf(p, t, -9.276308205e-02f);
+  p = fmaf(p, t, 1.276978705e+00f);
+  return __fdividef(p, fmaf(2.0f, x, 1.0f));
+}
+
 // ---- phase 1: single precision -------------------------------------------------------------------------
 // x <= 0, 0 < beta < e^{x/2}; lnbeta only used (and only valid) when `lower`.  Returns the guess for s.
 __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta, float ex2, float iex2, float s_c,
@@ -61,7 +78,8 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
     const float r2 = h * h * inv_s - 0.25f * s;      // b''/b'
     float g, newton, den;
     if (lower) {
-      const float D = erfcxf((h - t) * kInvSqrt2) - erfcxf((h + t) * kInvSqrt2);
+      const float q1 = (h - t) * kInvSqrt2;           // < 0 only if s overshot the inflection point
+      const float D = (q1 >= 0.0f ? erfcx_pos_f(q1) : erfcxf(q1)) - erfcx_pos_f((h + t) * kInvSqrt2);
       g = -0.5f * (h * h + t * t) + __logf(0.5f * D) - lnbeta;
       newton = -g * D * (0.5f * kSqrt2Pi);           // -g / (ln b)',  (ln b)' = 2 / (sqrt(2 pi) D)
       den = 1.0f + 0.5f * newton * r2 + 0.5f * g;    // 1 + newton/2 * ((ln b)''/(ln b)'),  newton (ln b)' = -g
@@ -80,8 +98,10 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
 }
 
 // ---- phase 2: double precision ---------------------------------------------------------------------------
-__device__ __forceinline__ double polish_f64(double x, double beta, double lnbeta, double ex2, double iex2, bool lower,
-                                             double s, int& iters) {
+// lower: g = ln b - ln beta = ln(b / beta), one logarithm per evaluation: inv_beta = 1/beta, lnbeta_off = 0
+// (for beta below 1e-290, where 1/beta is not finite, inv_beta = 1 and lnbeta_off = ln beta)
+__device__ __forceinline__ double polish_f64(double x, double beta, double inv_beta, double lnbeta_off, double ex2, double iex2,
+                                             bool lower, double s, int& iters) {
   double lo = 0.0, hi = S_MAX;
   bool done = false;
   int it = 0;
@@ -94,7 +114,7 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double lnbet
       double g, newton, den;
       if (lower) {
         const double D = erfcx((h - t) * INV_SQRT2) - erfcx((h + t) * INV_SQRT2);
-        g = log(0.5 * D) - e - lnbeta;
+        g = log(0.5 * D * inv_beta) - e - lnbeta_off;
         newton = -g * D * (0.5 * SQRT_2PI);
         den = 1.0 + 0.5 * newton * r2 + 0.5 * g;
       } else {
@@ -155,14 +175,23 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol(int64_t n, const double*
   const float s_cf = sqrtf(-2.0f * xf);
   const float b_cf = 0.5f * (ex2f - iex2f * erfcf(s_cf * 0.70710678f));
   const bool lower = beta < (double)b_cf;
-  const double lnbeta = lower ? log(beta) : 0.0;
-  float s0 = presolve_f32(xf, (float)beta, (float)lnbeta, ex2f, iex2f, s_cf, b_cf, lower);
+  // ln beta to single precision from the exponent and the leading mantissa bits (beta may be far below FLT_MIN)
+  const int bhi = __double2hiint(beta);
+  const float lnbeta_f = fmaf((float)(((bhi >> 20) & 0x7ff) - 1023), 0.69314718f,
+                              __logf((float)__hiloint2double((bhi & 0x000fffff) | 0x3ff00000, __double2loint(beta))));
+  float s0 = presolve_f32(xf, (float)beta, lnbeta_f, ex2f, iex2f, s_cf, b_cf, lower);
   double s = (double)s0;
-  if (!(s > 0.0 && s < S_MAX)) s = fmax(sqrt(-2.0 * x), 0.1);  // fp32 range exhausted: start at the inflection point
+  if (!(s > 0.0 && s < S_MAX)) {   // fp32 range exhausted: start at the inflection point
+    s = fmax(sqrt(-2.0 * x), 0.1);
+  }
+  double inv_beta = 1.0, lnbeta_off = 0.0;
+  if (lower) {
+    if (beta < 1e-290) lnbeta_off = log(beta); else inv_beta = 1.0 / beta;
+  }
   int it = 0;
-  s = polish_f64(x, beta, lnbeta, ex2, iex2, lower, s, it);
+  s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, iex2, lower, s, it);
   if (inr) {
-    st_stream(sigma + i, ok ? s / sqrt(t_) : qnan());
+    st_stream(sigma + i, ok ? s * rsqrt(t_) : qnan());
     if (iters) st_stream(iters + i, ok ? it : 0);
   }
 }

@@ -111,7 +111,7 @@ struct SplLayout {
   static constexpr int NW = G / 32;
   static constexpr int CAP = G * SPL_R;
   static constexpr int PADCAP = CAP + CAP / 8 + 8;                 // rows CAP, CAP+1 exist (read as neighbours)
-  static constexpr int PER_SLICE = 2 * PADCAP + NW * 7 + NW * 2 + NW;   // doubles (the last NW hold int counts)
+  static constexpr int PER_SLICE = 2 * PADCAP + NW * 7 + NW * 2 + NW + (G + 2) / 2;   // doubles (the tail holds NW + G+1 ints)
   static constexpr size_t SMEM = (size_t)SPB * PER_SLICE * sizeof(double);
 };
 
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
   double* wm = ys + L::PADCAP;          // [NW][7] warp totals of the forward scan
   double* wa = wm + L::NW * 7;          // [NW][2] warp totals of the backward scan
   int* wc = reinterpret_cast<int*>(wa + L::NW * 2);   // [NW] valid-knot counts
+  int* qs = reinterpret_cast<int*>(wa + L::NW * 3);   // [G+1] first grid point of every thread
   const int64_t sl = (int64_t)blockIdx.x * L::SPB + grp;
   if (sl >= n_slices) return;           // a whole group leaves together (named barriers / warp sync below)
   const int64_t k0 = knot_off[sl];
@@ -196,20 +197,21 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
     return;
   }
 
-  // ---- row coefficients: hh[k] = x[i0+k] - x[i0+k-1], slopes likewise, k = 0..8 -------------------------
-  double hh[SPL_R + 1], rr[SPL_R];
+  // ---- row coefficients.  Row i (1 <= i <= n-2) is multiplied by h[i-1] h[i], which clears both slope
+  //      divisions:  a = hm^2 hp,  b = 2 (hm+hp) hm hp,  c = hm hp^2,  r = 6 (dy[i] hm - dy[i-1] hp);
+  //      the q recurrence needs a[i] c[i-1] = h[i-2] hm^4 hp.  hh[k] = x[i0+k-1] - x[i0+k-2], k = 0..9 ---------
+  double hh[SPL_R + 2], dy[SPL_R + 1];
   {
     const double xp = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yp = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
+    const double xpp = g > 0 ? xs[spl_pad(i0 - 2)] : qnan();
     const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
-    double ss[SPL_R + 1];
-    hh[0] = xv[0] - xp; ss[0] = (yv[0] - yp) / hh[0];
+    hh[0] = xp - xpp;
+    hh[1] = xv[0] - xp; dy[0] = yv[0] - yp;
 #pragma unroll
-    for (int k = 1; k < SPL_R; ++k) { hh[k] = xv[k] - xv[k - 1]; ss[k] = (yv[k] - yv[k - 1]) / hh[k]; }
-    hh[SPL_R] = xn - xv[SPL_R - 1]; ss[SPL_R] = (yn - yv[SPL_R - 1]) / hh[SPL_R];
-#pragma unroll
-    for (int j = 0; j < SPL_R; ++j) rr[j] = 6.0 * (ss[j + 1] - ss[j]);
+    for (int k = 1; k < SPL_R; ++k) { hh[k + 1] = xv[k] - xv[k - 1]; dy[k] = yv[k] - yv[k - 1]; }
+    hh[SPL_R + 1] = xn - xv[SPL_R - 1]; dy[SPL_R] = yn - yv[SPL_R - 1];
   }
-  // row i0+j is an equation of the system iff 1 <= i0+j <= n-2
+  // row i0+j is an equation of the system iff 1 <= i0+j <= n-2; its hm = hh[j+1], hp = hh[j+2], h[i-2] = hh[j]
   auto interior = [&](int j) { const int i = i0 + j; return i >= 1 && i <= n - 2; };
 
   // ---- forward: chunk transition matrix, prefix over the group ----------------------------------------------
@@ -217,7 +219,9 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
 #pragma unroll
   for (int j = 0; j < SPL_R; ++j) {
     if (interior(j)) {
-      const double a = hh[j], b = 2.0 * (hh[j] + hh[j + 1]), ag = a * a, r = rr[j];
+      const double hm = hh[j + 1], hp = hh[j + 2], hmp = hm * hp;
+      const double a = hm * hmp, b = 2.0 * (hm + hp) * hmp, r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
+      const double ag = (i0 + j == 1) ? 0.0 : hh[j] * hm * hm * a;     // multiplies q[-1] = 0 in row 1
       const double nA = b * P.A - ag * P.C, nB = b * P.B - ag * P.E;
       const double nF = r * P.A - a * P.F, nG = r * P.B - a * P.G;
       P.C = P.A; P.E = P.B; P.A = nA; P.B = nB; P.F = nF; P.G = nG; P.H = -a * P.H;
@@ -225,10 +229,11 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
   }
   mat_normalize(P);
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
+  for (int d = 1; d < 32; d <<= 1) {       // products of normalised matrices grow by at most 3x per level: no rescaling inside
     const Mat3 Q = mat_shfl_up(P, d);
-    if (lane >= d) { P = mat_mul(P, Q); mat_normalize(P); }
+    if (lane >= d) P = mat_mul(P, Q);
   }
+  mat_normalize(P);
   Mat3 X = mat_shfl_up(P, 1);            // exclusive prefix inside the warp
   if (lane == 0) X = mat_identity();
   double q = 1.0, qp = 0.0, D = 0.0;     // state before row 1: q[0] = 1, q[-1] = 0, D[0] = 0
@@ -256,10 +261,12 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
   for (int j = 0; j < SPL_R; ++j) {
     cv[j] = 0.0; dv[j] = 0.0;
     if (interior(j)) {
-      const double a = hh[j], b = 2.0 * (hh[j] + hh[j + 1]);
-      const double qn = b * q - a * a * qp, Dn = rr[j] * q - a * D;
+      const double hm = hh[j + 1], hp = hh[j + 2], hmp = hm * hp;
+      const double a = hm * hmp, b = 2.0 * (hm + hp) * hmp, r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
+      const double ag = (i0 + j == 1) ? 0.0 : hh[j] * hm * hm * a;
+      const double qn = b * q - ag * qp, Dn = r * q - a * D;
       const double inv = 1.0 / qn;
-      cv[j] = hh[j + 1] * q * inv;
+      cv[j] = hmp * hp * q * inv;
       dv[j] = Dn * inv;
       qp = q; q = qn; D = Dn;
     }
@@ -286,12 +293,16 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
   for (int j = SPL_R - 1; j >= 0; --j) { dv[j] = dv[j] - cv[j] * (j == SPL_R - 1 ? Mn : dv[j + 1]); }   // dv = M now
 
   // ---- evaluate the grid points inside my segments ------------------------------------------------------------
+  // the grid is sorted: thread g's points start at the first one >= x[i0] and end where thread g+1's start
+  qs[g] = (g == 0) ? 0 : ((i0 <= n - 2) ? lower_bound_q(xq, n_q, xv[0]) : n_q);
+  if (g == 0) qs[G] = n_q;
+  group_sync<G>(grp);
   if (i0 > n - 2) return;
   const double xlo = xs[spl_pad(0)], xhi = xs[spl_pad(n - 1)], ylo = ys[spl_pad(0)], yhi = ys[spl_pad(n - 1)];
   const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
   const bool owns_last = (n - 2) <= i0 + SPL_R - 1;
-  int qi = g == 0 ? 0 : lower_bound_q(xq, n_q, xv[0]);
-  const int qhi = owns_last ? n_q : lower_bound_q(xq, n_q, xn);
+  int qi = qs[g];
+  const int qhi = owns_last ? n_q : qs[g + 1];
 #pragma unroll
   for (int j = 0; j < SPL_R; ++j) {
     const int i = i0 + j;
