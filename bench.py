@@ -291,11 +291,12 @@ def run_gpu(args):
     if not args.skip_e2e:
         e2e = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks)
 
-    # ---- reference-pinned kernels A and B on a config-3-shaped tape (rank 0's GPU only adds them) --------
+    # ---- reference-pinned kernels A and B on a config-3-shaped tape, every rank its own contracts --------
     del pipe, res
     torch.cuda.empty_cache()
-    if rank == 0 and not args.skip_kernels:
-        kernels.update(_bench_ab(args, torch, D, tapes, dev, peak))
+    if not args.skip_kernels:
+        ab = _bench_ab(args, torch, D, tapes, dev, peak, rank, world, barrier, max_over_ranks)
+        kernels.update(ab)
 
     cb = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -370,50 +371,56 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
             "pcie_gbs": stream.h2d_bytes / (ms / 1e3) / 1e9}
 
 
-def _bench_ab(args, torch, D, tapes, dev, peak):
+def _bench_ab(args, torch, D, tapes, dev, peak, rank, world, barrier, max_over_ranks):
     """Kernel A (reference src/interpolation/core.py:26-81) and kernel B (src/candle_reconstruction/core.py:59-89)
-    on a config-3-shaped tape: contracts with 481 hourly rows (20 days) -> 28 801 minute rows each."""
+    on a config-3-shaped tape: every rank owns `--ab-contracts` contracts with 481 hourly rows (20 days) ->
+    28 801 minute rows each.  Timed per launch with CUDA events, outputs preallocated (steady state of a pipeline);
+    the plan step (reads the source rows only, then one 8-byte read-back) is reported separately."""
     import numpy as np
     n_contracts = args.ab_contracts
-    tp = tapes.make_contract_tape(3, n_contracts, rows_per_contract=481)
+    tp = tapes.make_contract_tape(3 + rank, n_contracts, rows_per_contract=481)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     off, date = t(tp.off), t(tp.date)
     icols = [t(tp.cols[c]) for c in tapes.INTERP_COLS]
     fcols = [t(tp.cols[c]) for c in tapes.FILL_NUM_COLS]
     kw = dict(step=tapes.MINUTE_US, max_span=30 * tapes.DAY_US)
-    out = {}
-    ms = []
-    for it in range(args.warmup + args.steps):
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        res = D.interp_linear_ffill(off, date, icols, fcols, [None], **kw)
-        a1.record(); torch.cuda.synchronize()
-        if it >= args.warmup:
-            ms.append(a0.elapsed_time(a1))
-        if it < args.warmup + args.steps - 1:
-            del res
-    m = sum(ms) / len(ms)
+    n_it = args.warmup + args.steps
+
+    def timed(fn):
+        ms = []
+        for it in range(n_it):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a0.record(); r = fn(); a1.record(); torch.cuda.synchronize()
+            if it >= args.warmup:
+                ms.append(a0.elapsed_time(a1))
+        return max_over_ranks(sum(ms) / len(ms)), r
+
+    plan_ms, plan = timed(lambda: D.interp_plan(off, date, icols, fcols, [None], **kw))
+    res = D.interp_exec(plan)
+    exec_ms, res = timed(lambda: D.interp_exec(plan, out=res))
     rows = res.total
-    # written: date 8 + 3 interp x 8 + 6 fill x 8 + symbol source index 4 + is_interpolated 1 = 85 B/row; read: 80 B/source row
-    bytes_a = rows * (8 + 24 + 48 + 4 + 1) + tp.n_rows * 80
-    out["interp_linear_ffill"] = {"ms": round(m, 4), "rate": rows / (m / 1e3), "rate_unit": "minute-rows/s", "algorithmic_bytes": bytes_a,
-                                  "gbs": round(bytes_a / (m / 1e3) / 1e9, 1), "frac_hbm": round(bytes_a / (m / 1e3) / 1e9 / peak, 4),
-                                  "note": f"{n_contracts} contracts x 481 hourly rows -> {rows} rows; plan + 8-byte read-back + exec, allocation included"}
-    S = res.interp[1]
-    vol = res.fill[4]
-    ms = []
-    for it in range(args.warmup + args.steps):
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        cb = D.ohlcv_reduce(res.out_off, res.ts, S, S, S, S, vol, bucket_ticks=5 * tapes.MINUTE_US, min_count=5)
-        b1.record(); torch.cuda.synchronize()
-        if it >= args.warmup:
-            ms.append(b0.elapsed_time(b1))
-    m = sum(ms) / len(ms)
-    bytes_b = rows * 48 + cb.total * 52
-    out["ohlcv_reduce"] = {"ms": round(m, 4), "rate": rows / (m / 1e3), "rate_unit": "minute-rows/s", "algorithmic_bytes": bytes_b,
-                           "gbs": round(bytes_b / (m / 1e3) / 1e9, 1), "frac_hbm": round(bytes_b / (m / 1e3) / 1e9 / peak, 4),
-                           "note": f"{rows} minute rows -> {cb.total} 5-min candles; memsets, reduce, finalize and the 8-byte count read-back included"}
+    # exec writes per row: date 8 + 3 interp x 8 + 6 fill x 8 + symbol source index 4 + is_interpolated 1 = 85 B;
+    # the source side (80 B per source row, 60x fewer rows) is read by the plan step
+    bytes_exec = rows * (8 + 24 + 48 + 4 + 1)
+    out = {}
+
+    def entry(ms, nbytes, nrows, note):
+        gbs = nbytes / (ms / 1e3) / 1e9
+        return {"ms": round(ms, 4), "rate": world * nrows / (ms / 1e3), "rate_unit": "minute-rows/s", "algorithmic_bytes": nbytes,
+                "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4), "note": note}
+
+    out["interp_linear_ffill"] = entry(exec_ms, bytes_exec, rows,
+                                       f"k_interp_exec: {n_contracts} contracts x 481 hourly rows -> {rows} minute rows per GPU, 85 B written per row")
+    out["interp_plan"] = entry(plan_ms, tp.n_rows * 80, rows,
+                               f"k_interp_plan + 2 scans over {tp.n_rows} source rows (80 B each); rate is quoted in output rows planned")
+    S, vol = res.interp[1], res.fill[4]
+    b_ms, cb = timed(lambda: D.ohlcv_reduce(res.out_off, res.ts, S, S, S, S, vol, bucket_ticks=5 * tapes.MINUTE_US, min_count=5, trim=False))
+    n_candles = int(cb._total_dev.item())
+    bytes_b = rows * 48 + n_candles * 52
+    out["ohlcv_reduce"] = entry(b_ms, bytes_b, rows,
+                                f"{rows} minute rows -> {n_candles} 5-min candles per GPU: memsets + k_ohlcv_reduce + k_ohlcv_finalize, "
+                                "48 B read per row + 52 B written per candle")
     return out
 
 

@@ -203,16 +203,33 @@ class InterpBatch:
     total: int = 0
 
 
-def interp_linear_ffill(src_off: torch.Tensor, ts: torch.Tensor, interp_cols: Sequence[torch.Tensor],
-                        fill_cols: Sequence[torch.Tensor] = (), idx_valid: Sequence[Optional[torch.Tensor]] = (),
-                        *, step: int, max_span: int, max_points: int = 100_000, min_points: int = 10,
-                        want_src_row: bool = False, want_pos: bool = False, want_keep: bool = False,
-                        want_is_interpolated: bool = True) -> InterpBatch:
-    """CSR batch of contracts -> minute rows (reference interpolation/core.py:26-81).
+@dataclass
+class InterpPlan:
+    """Result of ivx_interp_plan: guards, grid and interval tables (in ``ws``), output sizes."""
+    src_off: torch.Tensor
+    n_src: int
+    n_fill: int
+    n_idx: int
+    step: int
+    ws: torch.Tensor
+    ws_bytes: int
+    out_off: torch.Tensor                   # int64[n_sym+1]
+    sym_status: torch.Tensor
+    sym_flags: torch.Tensor
+    _total: Optional[int] = None
 
-    ``idx_valid[0]`` is the ``symbol`` column's non-null mask (uint8 tensor, or None = all valid).
-    One 8-byte D2H sync (the total row count) sits between plan and exec.
-    """
+    @property
+    def total(self) -> int:
+        """Rows the batch will emit (reads 8 bytes back from the device the first time)."""
+        if self._total is None:
+            self._total = int(self.out_off[-1].item())
+        return self._total
+
+
+def interp_plan(src_off: torch.Tensor, ts: torch.Tensor, interp_cols: Sequence[torch.Tensor],
+                fill_cols: Sequence[torch.Tensor] = (), idx_valid: Sequence[Optional[torch.Tensor]] = (),
+                *, step: int, max_span: int, max_points: int = 100_000, min_points: int = 10) -> InterpPlan:
+    """Step 1 of kernel A (reference interpolation/core.py:26-55,74): reads only the source rows."""
     n_sym = src_off.numel() - 1
     n_src = ts.numel()
     _req(src_off, torch.int64, "src_off"); _req(ts, torch.int64, "ts")
@@ -239,23 +256,55 @@ def interp_linear_ffill(src_off: torch.Tensor, ts: torch.Tensor, interp_cols: Se
         int(step), int(max_span), int(max_points), int(min_points), _ptr(out_count), _ptr(out_off),
         _ptr(sym_status), _ptr(sym_flags), _ptr(ws), ws_bytes, _stream()), "ivx_interp_plan")
     _count("interp_plan")
-    m = int(out_off[n_sym].item())                     # sizes the outputs
-    o_ts = _empty(m, torch.int64, ts)
-    o_interp = [_empty(m, torch.float64, ts) for _ in range(3)]
-    o_fill = [_empty(m, torch.float64, ts) for _ in range(n_fill)]
-    o_idx = [_empty(m, torch.int32, ts) for _ in range(n_idx)]
-    o_src = _empty(m, torch.int32, ts) if want_src_row else None
-    o_pos = _empty(m, torch.int32, ts) if want_pos else None
-    o_keep = _empty(m, torch.uint8, ts) if want_keep else None
-    o_isint = _empty(m, torch.uint8, ts) if want_is_interpolated else None
-    check(L.ivx_interp_exec(
-        n_sym, _ptr(src_off), n_src, _ptr(out_off), m, int(step), n_fill, n_idx, _ptr(o_ts),
-        ptr_array([_ptr(t) for t in o_interp]), ptr_array([_ptr(t) for t in o_fill]),
-        ptr_array([_ptr(t) for t in o_idx]), _ptr(o_src), _ptr(o_pos), _ptr(o_keep), _ptr(o_isint),
-        _ptr(ws), ws_bytes, _stream()), "ivx_interp_exec")
+    return InterpPlan(src_off, n_src, n_fill, n_idx, int(step), ws, ws_bytes, out_off, sym_status, sym_flags)
+
+
+def interp_exec(plan: InterpPlan, *, want_src_row: bool = False, want_pos: bool = False, want_keep: bool = False,
+                want_is_interpolated: bool = True, want_fill: bool = True, want_idx: bool = True,
+                out: Optional["InterpBatch"] = None) -> "InterpBatch":
+    """Step 2 of kernel A: writes the output rows.  ``out`` reuses the buffers of an earlier result of the same
+    shape (no allocation inside a timed loop)."""
+    n_sym = plan.src_off.numel() - 1
+    m = plan.total
+    like = plan.out_off
+    if out is not None and out.ts.numel() == m:
+        o_ts, o_interp, o_fill, o_idx = out.ts, out.interp, out.fill, out.idx
+        o_src, o_pos, o_keep, o_isint = out.src_row, out.pos, out.keep, out.is_interpolated
+    else:
+        o_ts = _empty(m, torch.int64, like)
+        o_interp = [_empty(m, torch.float64, like) for _ in range(3)]
+        o_fill = [_empty(m, torch.float64, like) for _ in range(plan.n_fill)] if want_fill else []
+        o_idx = [_empty(m, torch.int32, like) for _ in range(plan.n_idx)] if want_idx else []
+        o_src = _empty(m, torch.int32, like) if want_src_row else None
+        o_pos = _empty(m, torch.int32, like) if want_pos else None
+        o_keep = _empty(m, torch.uint8, like) if want_keep else None
+        o_isint = _empty(m, torch.uint8, like) if want_is_interpolated else None
+    check(lib().ivx_interp_exec(
+        n_sym, _ptr(plan.src_off), plan.n_src, _ptr(plan.out_off), m, plan.step, plan.n_fill, plan.n_idx, _ptr(o_ts),
+        ptr_array([_ptr(t) for t in o_interp]),
+        ptr_array([_ptr(t) for t in o_fill]) if o_fill else None,
+        ptr_array([_ptr(t) for t in o_idx]) if o_idx else None,
+        _ptr(o_src), _ptr(o_pos), _ptr(o_keep), _ptr(o_isint),
+        _ptr(plan.ws), plan.ws_bytes, _stream()), "ivx_interp_exec")
     _count("interp_exec")
-    return InterpBatch(out_off, sym_status, sym_flags, o_ts, o_interp, o_fill, o_idx, o_src, o_pos, o_keep,
+    return InterpBatch(plan.out_off, plan.sym_status, plan.sym_flags, o_ts, o_interp, o_fill, o_idx, o_src, o_pos, o_keep,
                        o_isint, m)
+
+
+def interp_linear_ffill(src_off: torch.Tensor, ts: torch.Tensor, interp_cols: Sequence[torch.Tensor],
+                        fill_cols: Sequence[torch.Tensor] = (), idx_valid: Sequence[Optional[torch.Tensor]] = (),
+                        *, step: int, max_span: int, max_points: int = 100_000, min_points: int = 10,
+                        want_src_row: bool = False, want_pos: bool = False, want_keep: bool = False,
+                        want_is_interpolated: bool = True) -> InterpBatch:
+    """CSR batch of contracts -> minute rows (reference interpolation/core.py:26-81): plan + exec.
+
+    ``idx_valid[0]`` is the ``symbol`` column's non-null mask (uint8 tensor, or None = all valid).
+    One 8-byte D2H sync (the total row count) sits between plan and exec.
+    """
+    plan = interp_plan(src_off, ts, interp_cols, fill_cols, idx_valid, step=step, max_span=max_span,
+                       max_points=max_points, min_points=min_points)
+    return interp_exec(plan, want_src_row=want_src_row, want_pos=want_pos, want_keep=want_keep,
+                       want_is_interpolated=want_is_interpolated)
 
 
 # ------------------------------------------------------------------------------------------------
