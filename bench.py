@@ -415,7 +415,9 @@ def _bench_ab(args, torch, D, tapes, dev, peak, rank, world, barrier, max_over_r
     out["interp_plan"] = entry(plan_ms, tp.n_rows * 80, rows,
                                f"k_interp_plan + 2 scans over {tp.n_rows} source rows (80 B each); rate is quoted in output rows planned")
     S, vol = res.interp[1], res.fill[4]
-    b_ms, cb = timed(lambda: D.ohlcv_reduce(res.out_off, res.ts, S, S, S, S, vol, bucket_ticks=5 * tapes.MINUTE_US, min_count=5, trim=False))
+    # five DISTINCT input columns (the same array passed four times would be served from L2)
+    hi_, lo_, cl_ = S + 3.0, S - 3.0, S + 0.5
+    b_ms, cb = timed(lambda: D.ohlcv_reduce(res.out_off, res.ts, S, hi_, lo_, cl_, vol, bucket_ticks=5 * tapes.MINUTE_US, min_count=5, trim=False))
     n_candles = int(cb._total_dev.item())
     bytes_b = rows * 48 + n_candles * 52
     out["ohlcv_reduce"] = entry(b_ms, bytes_b, rows,

@@ -326,18 +326,34 @@ struct ExecParams {
   InterpWs W;
 };
 
+// last index i in [lo, hi) with key[i] <= v, given key[lo] <= v: 32-ary search by one warp (one round per 5 bits)
+template <typename T>
+__device__ __forceinline__ int64_t warp_upper_le(const T* __restrict__ key, int64_t lo, int64_t hi, T v, int lane) {
+  while (hi - lo > 1) {
+    const int64_t stepw = (hi - lo + 31) >> 5;
+    const int64_t idx = lo + lane * stepw;
+    const bool le = idx < hi && __ldg(key + idx) <= v;
+    const uint32_t m = __ballot_sync(IVX_FULL_MASK, le) | 1u;
+    const int last = 31 - __clz(m);
+    lo += last * stepw;
+    hi = min(hi, lo + stepw);
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(TA_THREADS) k_interp_exec(const ExecParams P) {
   __shared__ int64_t s_sym;
+  __shared__ int32_t s_g0;
+  __shared__ uint32_t s_bits[TA_ROWS / 32];    // bit r set: a source knot sits on row r of the tile
+  __shared__ int32_t s_pref[TA_ROWS / 32];     // knots before each 32-row group
   const InterpWs& W = P.W;
   const int64_t tile = blockIdx.x;
   if (tile >= W.tile_off[P.n_sym]) return;
-  if (threadIdx.x == 0) {
-    int64_t lo = 0, hi = P.n_sym;   // largest s with tile_off[s] <= tile
-    while (hi - lo > 1) {
-      int64_t mid = (lo + hi) >> 1;
-      if (W.tile_off[mid] <= tile) lo = mid; else hi = mid;
-    }
-    s_sym = lo;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    s_bits[threadIdx.x] = 0;
+    const int64_t lo = warp_upper_le<int64_t>(W.tile_off, 0, P.n_sym, tile, lane);   // largest s with tile_off[s] <= tile
+    if (lane == 0) s_sym = lo;
   }
   __syncthreads();
   const int64_t s = s_sym;
@@ -348,24 +364,41 @@ __global__ void __launch_bounds__(TA_THREADS) k_interp_exec(const ExecParams P) 
   const int64_t count = P.out_off[s + 1] - obase;
   const int64_t q0 = (tile - W.tile_off[s]) * TA_ROWS;
   const int32_t* __restrict__ gpos = W.gpos + a;
+  const int32_t P0 = p0 + (int32_t)q0;         // position of the tile's first row on the contract's axis
+
+  // interval of the first row (gpos[0] == 0 <= P0), then one bit per knot inside the tile: a row's interval is
+  // g0 + (number of knots at or before it), i.e. a prefix popcount instead of a binary search per row
+  if (threadIdx.x < 32) {
+    const int32_t g0 = (int32_t)warp_upper_le<int32_t>(gpos, 0, n_on, P0, lane);
+    if (lane == 0) s_g0 = g0;
+  }
+  __syncthreads();
+  const int32_t g0 = s_g0;
+  for (int32_t k = g0 + 1 + (int32_t)threadIdx.x; k < n_on; k += TA_THREADS) {
+    const int32_t d = __ldg(gpos + k) - P0;
+    if (d >= TA_ROWS) break;
+    atomicOr(&s_bits[d >> 5], 1u << (d & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int c = __popc(s_bits[threadIdx.x]);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(IVX_FULL_MASK, incl, d);
+      if (lane >= d) incl += u;
+    }
+    s_pref[threadIdx.x] = incl - c;
+  }
+  __syncthreads();
 
 #pragma unroll 1
   for (int it = 0; it < TA_ROWS / TA_THREADS; ++it) {
-    const int64_t q = q0 + it * TA_THREADS + threadIdx.x;
+    const int r = it * TA_THREADS + threadIdx.x;
+    const int64_t q = q0 + r;
     const bool act = q < count;
-    const int32_t p = p0 + (int32_t)(act ? q : (count - 1));
-    // warp-uniform coarse search for the warp's first position, then a short per-lane search
-    const int32_t pw = __shfl_sync(IVX_FULL_MASK, p, 0);
-    int32_t lo = 0, hi = n_on;      // last g with gpos[g] <= pw ; gpos[0] == 0 <= pw always
-    while (hi - lo > 1) {
-      int32_t mid = (lo + hi) >> 1;
-      if (__ldg(gpos + mid) <= pw) lo = mid; else hi = mid;
-    }
-    int32_t l2 = lo, h2 = min(n_on, lo + 33);
-    while (h2 - l2 > 1) {
-      int32_t mid = (l2 + h2) >> 1;
-      if (__ldg(gpos + mid) <= p) l2 = mid; else h2 = mid;
-    }
+    const int32_t p = P0 + r;
+    const int32_t l2 = g0 + s_pref[r >> 5] + __popc(s_bits[r >> 5] & (0xffffffffu >> (31 - (r & 31))));
     if (!act) continue;
     const int64_t g = a + l2;
     const int32_t gp = __ldg(W.gpos + g);

@@ -7,8 +7,9 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kern}"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
-fname, hdr, items = None, None, []
+fname, hdr, items, seen = None, None, [], set()      # several launches of the kernel in a report: keep the first
 for r in rows:
+
     if not r:
         continue
     if r[0] == "File Path":
@@ -19,6 +20,10 @@ for r in rows:
         d = {}
         for k, v in zip(hdr, r):
             d.setdefault(k, v)
+        key = (fname, d["Line No"])
+        if key in seen:
+            continue
+        seen.add(key)
         try:
             items.append((int(d["Instructions Executed"]), int(d["# Samples"] or 0), fname, d["Line No"], r[1].strip()[:100],
                           float(d["Avg. Threads Executed"] or 0)))
