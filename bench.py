@@ -287,9 +287,10 @@ def run_gpu(args):
     roofline["fp64_fma_peak_tflops_measured"] = round(fp64_tflops, 2)
 
     # ---- e2e: the same day streamed from pinned host memory ---------------------------------------------
-    e2e = None
+    e2e = e2e_q = None
     if not args.skip_e2e:
-        e2e = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks)
+        e2e = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, "chain")
+        e2e_q = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, "quotes")
 
     # ---- reference-pinned kernels A and B on a config-3-shaped tape, every rank its own contracts --------
     del pipe, res
@@ -321,7 +322,7 @@ def run_gpu(args):
                            "full_day": n_t == N_T_DAY},
                 "surface_points_per_sec": world * n_t * N_GRID_M * N_GRID_K / (ms_step / 1e3),
                 "candles_per_step": world * n_buckets * N_GRID_M * N_GRID_K,
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches * world,
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
                 "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -329,35 +330,46 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks):
+def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, layout):
     """Through the host-facing entry (surface.HostSurfaceStream): every step copies the whole day's quotes
     H2D from pinned memory, chunk by chunk, and the candles D2H.  The host tape holds RING distinct chunks
-    (pinned) that are re-sent cyclically until the day's stamps are covered — every byte crosses PCIe."""
+    (pinned) that are re-sent cyclically until the day's stamps are covered — every byte crosses PCIe.
+    layout "chain": S per stamp, K per contract (sent once), T per (stamp, expiry) — 9 B per quote;
+    layout "quotes": every column per quote — 41 B per quote."""
     ring = 8
     n_chunks = max(1, n_t // CHUNK_T)
     ring = min(ring, n_chunks)
     cspec = SF.ChainSpec(CHUNK_T, N_EXP, N_STRIKE, N_GRID_K, N_GRID_M, bucket_ticks=60 * tapes.US, min_count=1)
     per = cspec.n_quotes
+    pin = lambda t: t.cpu().pin_memory()
     host = []
+    sc = SF.StructuredChain.from_quotes(chain) if layout == "chain" else None
     for i in range(ring):
-        sl = slice(i * per, (i + 1) * per)
-        cols = {name: getattr(chain, name)[sl].cpu().pin_memory() for name in SF.QUOTE_F64 + ("is_call",)}
-        host.append(SF.HostQuoteChunk(ts=chain.ts[i * CHUNK_T:(i + 1) * CHUNK_T].cpu().pin_memory(), **cols))
+        sl, tl = slice(i * per, (i + 1) * per), slice(i * CHUNK_T, (i + 1) * CHUNK_T)
+        if layout == "chain":
+            host.append(SF.HostChainChunk(ts=pin(sc.ts[tl]), price=pin(sc.price[sl]), is_call=pin(sc.is_call[sl]), S_t=pin(sc.S_t[tl]),
+                                          T_te=pin(sc.T_te[i * CHUNK_T * N_EXP:(i + 1) * CHUNK_T * N_EXP]), r_t=pin(sc.r_t[tl])))
+        else:
+            cols = {name: pin(getattr(chain, name)[sl]) for name in SF.QUOTE_F64 + ("is_call",)}
+            host.append(SF.HostQuoteChunk(ts=pin(chain.ts[tl]), **cols))
     chunks = [host[i % ring] for i in range(n_chunks)]
-    stream = SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=CHUNK_T // 60 + 1)
-    nb_total = n_chunks * (CHUNK_T // 60 + 1)
+    nb_chunk = CHUNK_T // 60
+    stream = SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=nb_chunk + 1,
+                                  K_ek=sc.K_ek if sc is not None else None)
+    nb_total = n_chunks * (nb_chunk + 1)
     out = [torch.empty(nb_total * cspec.n_series, dtype=torch.float64).pin_memory() for _ in range(4)]
     out_ts = torch.empty(nb_total, dtype=torch.int64).pin_memory()
     out_cnt = torch.empty(nb_total, dtype=torch.int32).pin_memory()
+    counts = [nb_chunk] * n_chunks                 # 1-s stamps starting on a minute: the host knows its bucket layout
     for _ in range(min(2, args.warmup)):
-        stream.run(chunks[: min(8, n_chunks)], out, out_ts, out_cnt)
+        stream.run(chunks[: min(8, n_chunks)], out, out_ts, out_cnt, bucket_counts=counts)
     steps = max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        rows = stream.run(chunks, out, out_ts, out_cnt)
+        rows = stream.run(chunks, out, out_ts, out_cnt, bucket_counts=counts)
     e1.record()
     barrier()
     wall = (time.perf_counter() - t0) / steps
@@ -365,6 +377,7 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
     nq = n_chunks * per
     return {"value": world * nq / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": stream.h2d_bytes, "d2h_bytes_per_step": stream.d2h_bytes,
             "ms_per_step": ms, "wall_ms_per_step": wall * 1e3, "steps": steps, "quotes_per_step_per_gpu": nq, "buckets": rows,
+            "layout": layout, "h2d_bytes_per_quote": round(stream.h2d_bytes / nq, 2),
             "api": "iv_interpolation_b200.surface.HostSurfaceStream.run (pinned host columns in, pinned host candles out)",
             "host_tape": f"{ring} distinct pinned chunks of {CHUNK_T} stamps ({host[0].nbytes() >> 20} MiB each) re-sent cyclically, "
                          f"{n_chunks} chunks per step; per-quote IVs stay on the device (candles are the result)",

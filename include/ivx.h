@@ -157,6 +157,15 @@ int ivx_interp_exec(int64_t n_sym, const int64_t* src_off, int64_t n_src, const 
 int ivx_bs_implied_vol(int64_t n, const double* price, const double* S, const double* K,
                        const double* T, const double* r, const uint8_t* is_call, double* sigma,
                        int32_t* iters, ivx_stream_t stream);
+/* Chain layout (one underlying, one day): quote (t, e, k) sits at price[(t*n_exp + e)*n_strike + k]; the
+ * underlying S_t[n_t] and rate r_t[n_t] are per stamp, the strike K_ek[n_exp*n_strike] per contract, the time to
+ * expiry T_te[n_t*n_exp] per (stamp, expiry): 9 B/quote in, 8 B out instead of 41 + 8.  ln S, ln K, rT and
+ * e^{-rT} are formed once per stamp / contract / (stamp, expiry) in `workspace`. */
+int64_t ivx_bs_chain_workspace_bytes(int64_t n_t, int64_t n_exp, int64_t n_strike);
+int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
+                             const uint8_t* is_call, const double* S_t, const double* K_ek,
+                             const double* T_te, const double* r_t, double* sigma, int32_t* iters,
+                             void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
 int ivx_bs_price(int64_t n, const double* S, const double* K, const double* T, const double* r,
                  const double* sigma, const uint8_t* is_call, double* price, ivx_stream_t stream);
 int ivx_bs_greeks(int64_t n, const double* S, const double* K, const double* T, const double* r,
@@ -178,6 +187,11 @@ int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_k
                         const double* x, const double* y, int64_t n_q, const double* xq,
                         int32_t extrap, double* yq, void* workspace, int64_t workspace_bytes,
                         ivx_stream_t stream);
+/* Same, with the abscissae of slice i at x[x_off[i] + j] (x_off NULL = knot_off): many slices may share one
+ * strike ladder.  Needs no workspace. */
+int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
+                             const double* x, const double* y, int64_t n_q, const double* xq,
+                             int32_t extrap, double* yq, ivx_stream_t stream);
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);

@@ -138,32 +138,22 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double inv_b
   return s;
 }
 
-__global__ void __launch_bounds__(256) k_bs_implied_vol(int64_t n, const double* __restrict__ price,
-                                                        const double* __restrict__ S, const double* __restrict__ K,
-                                                        const double* __restrict__ T, const double* __restrict__ r,
-                                                        const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
-                                                        int32_t* __restrict__ iters) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  // every lane takes part in the convergence vote; lanes past the end carry an already-solved dummy
-  const bool inr = i < n;
-  double p = 0, s_ = 1, k_ = 1, t_ = 1, r_ = 0;
-  bool call = true;
-  if (inr) {
-    p = ld_stream(price + i); s_ = ld_stream(S + i); k_ = ld_stream(K + i);
-    t_ = ld_stream(T + i); r_ = ld_stream(r + i); call = is_call[i] != 0;
-  }
-  const double kd = k_ * exp(-r_ * t_);
+// One quote, given Kd = K e^{-rT}.  `ok` says the inputs are finite and positive; every lane of the warp must call
+// (the polish loop votes), lanes that are not ok solve a dummy alongside.  PRE_X: x_pre = ln(S/Kd) was formed
+// from precomputed logarithms (chain layout) and the fp64 log is skipped.
+template <bool PRE_X>
+__device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double kd, double t_, bool call, double x_pre,
+                                            double& sigma_out, int& iters_out) {
   const double intrinsic = call ? (s_ - kd) : (kd - s_);
   const double lower_bound = fmax(intrinsic, 0.0);
   const double upper_bound = call ? s_ : kd;
-  bool ok = inr && isfinite(p) && isfinite(s_) && isfinite(k_) && isfinite(t_) && isfinite(r_) &&
-            (s_ > 0.0) && (k_ > 0.0) && (t_ > 0.0) && (p > lower_bound) && (p < upper_bound);
+  ok = ok && (p > lower_bound) && (p < upper_bound);
   const double target = intrinsic > 0.0 ? p - intrinsic : p;    // the out-of-the-money twin
   ok = ok && (target > 0.0);
   // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}
   const double mx = fmax(s_, kd), mn = fmin(s_, kd);
   const double ratio = ok ? mn / mx : 0.9;
-  double x = log(ratio);
+  double x = PRE_X ? -fabs(x_pre) : log(ratio);
   double ex2 = sqrt(ratio);
   double beta = ok ? target / (mx * ex2) : 0.05;
   if (ok && !(beta < ex2)) ok = false;                           // rounding pushed it onto the bound
@@ -190,9 +180,90 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol(int64_t n, const double*
   }
   int it = 0;
   s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, iex2, lower, s, it);
+  sigma_out = ok ? s * rsqrt(t_) : qnan();
+  iters_out = ok ? it : 0;
+}
+
+__global__ void __launch_bounds__(256) k_bs_implied_vol(int64_t n, const double* __restrict__ price,
+                                                        const double* __restrict__ S, const double* __restrict__ K,
+                                                        const double* __restrict__ T, const double* __restrict__ r,
+                                                        const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
+                                                        int32_t* __restrict__ iters) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // every lane takes part in the convergence vote; lanes past the end carry an already-solved dummy
+  const bool inr = i < n;
+  double p = 0, s_ = 1, k_ = 1, t_ = 1, r_ = 0;
+  bool call = true;
   if (inr) {
-    st_stream(sigma + i, ok ? s * rsqrt(t_) : qnan());
-    if (iters) st_stream(iters + i, ok ? it : 0);
+    p = ld_stream(price + i); s_ = ld_stream(S + i); k_ = ld_stream(K + i);
+    t_ = ld_stream(T + i); r_ = ld_stream(r + i); call = is_call[i] != 0;
+  }
+  const double kd = k_ * exp(-r_ * t_);
+  const bool ok = inr && isfinite(p) && isfinite(s_) && isfinite(k_) && isfinite(t_) && isfinite(r_) &&
+                  (s_ > 0.0) && (k_ > 0.0) && (t_ > 0.0);
+  double out;
+  int it;
+  solve_quote<false>(ok, p, s_, kd, t_, call, 0.0, out, it);
+  if (inr) {
+    st_stream(sigma + i, out);
+    if (iters) st_stream(iters + i, it);
+  }
+}
+
+// ---- chain layout: quote (t, e, k) = price[(t n_exp + e) n_strike + k]; S per stamp, K per contract, T per (stamp, expiry)
+// terms[0 .. n_t)            ln S[t]
+// terms[n_t .. +n_ek)        ln K[e][k]
+// terms[.. +n_te)            r[t] T[t][e]
+// terms[.. +n_te)            e^{-r T}
+__global__ void __launch_bounds__(256) k_chain_terms(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* __restrict__ S_t,
+                                                     const double* __restrict__ K_ek, const double* __restrict__ T_te,
+                                                     const double* __restrict__ r_t, double* __restrict__ terms) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t n_ek = n_exp * n_strike, n_te = n_t * n_exp;
+  if (i < n_t) { terms[i] = log(S_t[i]); return; }
+  int64_t j = i - n_t;
+  if (j < n_ek) { terms[n_t + j] = log(K_ek[j]); return; }
+  j -= n_ek;
+  if (j < n_te) {
+    const double rt = r_t[j / n_exp] * T_te[j];
+    terms[n_t + n_ek + j] = rt;
+    terms[n_t + n_ek + n_te + j] = exp(-rt);
+  }
+}
+
+// grid: x over the n_exp*n_strike contracts of one stamp, y over stamps
+__global__ void __launch_bounds__(256) k_bs_implied_vol_chain(int64_t t0, int32_t n_exp, int32_t n_strike, int64_t n_t,
+                                                              const double* __restrict__ price, const uint8_t* __restrict__ is_call,
+                                                              const double* __restrict__ S_t, const double* __restrict__ K_ek,
+                                                              const double* __restrict__ T_te, const double* __restrict__ terms,
+                                                              double* __restrict__ sigma, int32_t* __restrict__ iters) {
+  const int32_t n_ek = n_exp * n_strike;
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;        // contract (e, k)
+  const int64_t t = t0 + blockIdx.y;
+  const bool inr = j < n_ek;
+  const int64_t i = t * n_ek + j;
+  double p = 0, s_ = 1, k_ = 1, t_ = 1, disc = 1, xi = 0;
+  bool call = true;
+  if (inr) {
+    const int32_t e = j / n_strike;
+    const int64_t te = t * n_exp + e;
+    const int64_t n_te = n_t * (int64_t)n_exp;
+    p = ld_stream(price + i); call = is_call[i] != 0;
+    s_ = __ldg(S_t + t); k_ = __ldg(K_ek + j); t_ = __ldg(T_te + te);
+    const double lnS = __ldg(terms + t), lnK = __ldg(terms + n_t + j);
+    const double rt = __ldg(terms + n_t + n_ek + te);
+    disc = __ldg(terms + n_t + n_ek + n_te + te);
+    xi = (lnS - lnK) + rt;                                         // ln(S / (K e^{-rT}))
+  }
+  const double kd = k_ * disc;
+  const bool ok = inr && isfinite(p) && isfinite(s_) && isfinite(k_) && isfinite(t_) && isfinite(disc) &&
+                  (s_ > 0.0) && (k_ > 0.0) && (t_ > 0.0) && isfinite(xi);
+  double out;
+  int it;
+  solve_quote<true>(ok, p, s_, kd, t_, call, xi, out, it);
+  if (inr) {
+    st_stream(sigma + i, out);
+    if (iters) st_stream(iters + i, it);
   }
 }
 
@@ -267,6 +338,35 @@ extern "C" int ivx_bs_implied_vol(int64_t n, const double* price, const double* 
   IVX_REQUIRE(price && S && K && T && r && is_call && sigma, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol: null pointer");
   k_bs_implied_vol<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, price, S, K, T, r, is_call, sigma, iters);
   IVX_LAUNCH_CHECK("k_bs_implied_vol");
+  return IVX_OK;
+}
+
+extern "C" int64_t ivx_bs_chain_workspace_bytes(int64_t n_t, int64_t n_exp, int64_t n_strike) {
+  if (n_t < 0 || n_exp < 0 || n_strike < 0) return -1;
+  return 8 * (n_t + n_exp * n_strike + 2 * n_t * n_exp) + 256;
+}
+
+extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
+                                        const uint8_t* is_call, const double* S_t, const double* K_ek, const double* T_te,
+                                        const double* r_t, double* sigma, int32_t* iters, void* workspace,
+                                        int64_t workspace_bytes, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_t >= 0 && n_exp >= 0 && n_strike >= 0, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_chain: negative size");
+  if (n_t == 0 || n_exp == 0 || n_strike == 0) return IVX_OK;
+  IVX_REQUIRE(n_exp * n_strike < ((int64_t)1 << 30), IVX_ERR_TOO_LARGE, "ivx_bs_implied_vol_chain: more than 2^30 contracts per stamp");
+  IVX_REQUIRE(price && is_call && S_t && K_ek && T_te && r_t && sigma && workspace, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_chain: null pointer");
+  IVX_REQUIRE(workspace_bytes >= ivx_bs_chain_workspace_bytes(n_t, n_exp, n_strike), IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_chain: workspace too small");
+  double* terms = (double*)workspace;
+  const int64_t n_terms = n_t + n_exp * n_strike + n_t * n_exp;
+  k_chain_terms<<<(unsigned)((n_terms + 255) / 256), 256, 0, stream>>>(n_t, n_exp, n_strike, S_t, K_ek, T_te, r_t, terms);
+  IVX_LAUNCH_CHECK("k_chain_terms");
+  const unsigned gx = (unsigned)((n_exp * n_strike + 255) / 256);
+  for (int64_t t0 = 0; t0 < n_t; t0 += 65535) {
+    const unsigned gy = (unsigned)(n_t - t0 < 65535 ? n_t - t0 : 65535);
+    k_bs_implied_vol_chain<<<dim3(gx, gy), 256, 0, stream>>>(t0, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, S_t, K_ek,
+                                                             T_te, terms, sigma, iters);
+    IVX_LAUNCH_CHECK("k_bs_implied_vol_chain");
+  }
   return IVX_OK;
 }
 

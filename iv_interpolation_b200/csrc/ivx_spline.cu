@@ -117,6 +117,7 @@ struct SplLayout {
 
 template <int G>
 __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
+                                                                       const int64_t* __restrict__ x_off,
                                                                        const double* __restrict__ x, const double* __restrict__ y,
                                                                        int n_q, const double* __restrict__ xq, int extrap,
                                                                        double* __restrict__ yq) {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
   const int64_t sl = (int64_t)blockIdx.x * L::SPB + grp;
   if (sl >= n_slices) return;           // a whole group leaves together (named barriers / warp sync below)
   const int64_t k0 = knot_off[sl];
+  const int64_t xk0 = x_off ? x_off[sl] : k0;      // abscissae may live elsewhere (a strike ladder shared by many slices)
   int m = (int)min((int64_t)L::CAP + 1, knot_off[sl + 1] - k0);
   if (m > L::CAP) m = 0;                // more knots than the launch was sized for: NaN row (host checks max_knots)
   double* out = yq + sl * (int64_t)n_q;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_
     const int j = r * G + g;
     if (j < L::CAP + 2) {
       double xv = qnan(), yv = qnan();
-      if (j < m) { xv = ld_stream(x + k0 + j); yv = ld_stream(y + k0 + j); }
+      if (j < m) { xv = x_off ? __ldg(x + xk0 + j) : ld_stream(x + xk0 + j); yv = ld_stream(y + k0 + j); }
       xs[spl_pad(j)] = xv; ys[spl_pad(j)] = yv;
     }
   }
@@ -429,7 +431,7 @@ using namespace ivx;
 extern "C" int64_t ivx_spline_workspace_bytes(int64_t, int64_t) { return 256; }
 
 template <int G>
-static int launch_spline(int64_t n_slices, const int64_t* knot_off, const double* x, const double* y, int n_q,
+static int launch_spline(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const double* x, const double* y, int n_q,
                          const double* xq, int extrap, double* yq, cudaStream_t stream) {
   using L = SplLayout<G>;
   static bool attr_set = false;
@@ -439,28 +441,35 @@ static int launch_spline(int64_t n_slices, const int64_t* knot_off, const double
   }
   const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
   IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
-  k_spline_fit_eval<G><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x, y, n_q, xq, extrap, yq);
+  k_spline_fit_eval<G><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_fit_eval");
   return IVX_OK;
 }
 
-extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots, const double* x,
-                                   const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq,
-                                   void* workspace, int64_t workspace_bytes, ivx_stream_t stream_) {
+extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
+                                        const double* x, const double* y, int64_t n_q, const double* xq, int32_t extrap,
+                                        double* yq, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  (void)workspace; (void)workspace_bytes;   // kept in the ABI; this version needs no scratch
   IVX_REQUIRE(n_slices >= 0 && max_knots >= 0 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: extrap must be 0, 1 or 2");
   if (n_slices == 0 || n_q == 0) return IVX_OK;
   IVX_REQUIRE(knot_off && x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: null pointer");
   IVX_REQUIRE(max_knots <= 1024 * SPL_R, IVX_ERR_UNSUPPORTED, "ivx_spline_fit_eval: at most %d knots per slice (got max_knots %lld)", 1024 * SPL_R, (long long)max_knots);
-  // slices longer than max_knots come back as NaN rows
-  if (max_knots <= 32 * SPL_R) return launch_spline<32>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
-  if (max_knots <= 64 * SPL_R) return launch_spline<64>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
-  if (max_knots <= 128 * SPL_R) return launch_spline<128>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
-  if (max_knots <= 256 * SPL_R) return launch_spline<256>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
-  if (max_knots <= 512 * SPL_R) return launch_spline<512>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
-  return launch_spline<1024>(n_slices, knot_off, x, y, (int)n_q, xq, extrap, yq, stream);
+  // slices longer than the capacity the launch is sized for come back as NaN rows
+  const int nq = (int)n_q;
+  if (max_knots <= 32 * SPL_R) return launch_spline<32>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
+  if (max_knots <= 64 * SPL_R) return launch_spline<64>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
+  if (max_knots <= 128 * SPL_R) return launch_spline<128>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
+  if (max_knots <= 256 * SPL_R) return launch_spline<256>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
+  if (max_knots <= 512 * SPL_R) return launch_spline<512>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
+  return launch_spline<1024>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
+}
+
+extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots, const double* x,
+                                   const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq,
+                                   void* workspace, int64_t workspace_bytes, ivx_stream_t stream_) {
+  (void)workspace; (void)workspace_bytes;   // kept in the ABI; this version needs no scratch
+  return ivx_spline_fit_eval_xoff(n_slices, knot_off, nullptr, max_knots, x, y, n_q, xq, extrap, yq, stream_);
 }
 
 extern "C" int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x, const double* y, int32_t n_q,

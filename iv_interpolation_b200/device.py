@@ -21,7 +21,7 @@ _LAUNCHES = 0     # kernels of ours enqueued since the last reset (bench.py repo
 _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
-    "spline_strided_batched": 1, "scan": 1, "probe": 1,
+    "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2,
 }
 
 
@@ -325,6 +325,31 @@ def bs_implied_vol(price, S, K, T, r, is_call, *, want_iters: bool = False, out:
     return (sigma, iters) if want_iters else sigma
 
 
+def bs_implied_vol_chain(price, is_call, S_t, K_ek, T_te, r_t, *, n_t: int, n_exp: int, n_strike: int,
+                         out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                         want_iters: bool = False):
+    """Chain layout: ``price``/``is_call`` per quote [t][e][k]; ``S_t``, ``r_t`` per stamp, ``K_ek`` per contract,
+    ``T_te`` per (stamp, expiry).  9 B/quote read instead of 41."""
+    n = n_t * n_exp * n_strike
+    _req(price, torch.float64, "price"); _req(is_call, torch.uint8, "is_call")
+    for t, m, name in ((price, n, "price"), (is_call, n, "is_call"), (S_t, n_t, "S_t"), (r_t, n_t, "r_t"),
+                       (K_ek, n_exp * n_strike, "K_ek"), (T_te, n_t * n_exp, "T_te")):
+        if t.numel() != m:
+            raise _lib.IvxError(f"{name}: expected {m} elements, got {t.numel()}")
+    for t in (S_t, K_ek, T_te, r_t):
+        _req(t, torch.float64, "chain column")
+    L = lib()
+    wsb = L.ivx_bs_chain_workspace_bytes(n_t, n_exp, n_strike)
+    ws = workspace if workspace is not None and workspace.numel() >= wsb else _empty(wsb, torch.uint8, price)
+    sigma = out if out is not None else _empty(n, torch.float64, price)
+    iters = _empty(n, torch.int32, price) if want_iters else None
+    check(L.ivx_bs_implied_vol_chain(n_t, n_exp, n_strike, _ptr(price), _ptr(is_call), _ptr(S_t), _ptr(K_ek), _ptr(T_te),
+                                     _ptr(r_t), _ptr(sigma), _ptr(iters), _ptr(ws), ws.numel(), _stream()),
+          "ivx_bs_implied_vol_chain")
+    _count("bs_implied_vol_chain")
+    return (sigma, iters) if want_iters else sigma
+
+
 def bs_price(S, K, T, r, sigma, is_call):
     n = S.numel()
     price = _empty(n, torch.float64, S)
@@ -349,20 +374,24 @@ def bs_greeks(S, K, T, r, sigma, is_call, reference_put_rho_sign: bool = True) -
 # ------------------------------------------------------------------------------------------------
 def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, *,
                     max_knots: int, extrap: int = 1, out: Optional[torch.Tensor] = None,
-                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    workspace: Optional[torch.Tensor] = None, x_off: Optional[torch.Tensor] = None) -> torch.Tensor:
     n_slices = knot_off.numel() - 1
     n_q = xq.numel()
     _req(knot_off, torch.int64, "knot_off")
     for t in (x, y, xq):
         _req(t, torch.float64, "spline column")
     yq = out if out is not None else _empty(n_slices * n_q, torch.float64, x)
-    ws = workspace if workspace is not None else _empty(256, torch.uint8, x)
-    if ws.numel() < 256:
-        raise _lib.IvxError("spline workspace must hold 256 bytes")
-    if yq.numel() < n_slices * n_q or x.numel() != y.numel():
-        raise _lib.IvxError("spline_fit_eval: output too small or x/y length mismatch")
-    check(lib().ivx_spline_fit_eval(n_slices, _ptr(knot_off), int(max_knots), _ptr(x), _ptr(y), n_q, _ptr(xq),
-                                    int(extrap), _ptr(yq), _ptr(ws), 256, _stream()), "ivx_spline_fit_eval")
+    if yq.numel() < n_slices * n_q:
+        raise _lib.IvxError("spline_fit_eval: output too small")
+    if x_off is None:
+        if x.numel() != y.numel():
+            raise _lib.IvxError("spline_fit_eval: x/y length mismatch")
+    else:
+        _req(x_off, torch.int64, "x_off")
+        if x_off.numel() < n_slices:
+            raise _lib.IvxError("spline_fit_eval: x_off must have one entry per slice")
+    check(lib().ivx_spline_fit_eval_xoff(n_slices, _ptr(knot_off), _ptr(x_off), int(max_knots), _ptr(x), _ptr(y), n_q,
+                                         _ptr(xq), int(extrap), _ptr(yq), _stream()), "ivx_spline_fit_eval_xoff")
     _count("spline_fit_eval")
     return yq
 

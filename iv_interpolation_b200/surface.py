@@ -74,6 +74,30 @@ class QuoteChain:
 
 
 @dataclass
+class StructuredChain:
+    """The same chain with its structure spelled out instead of repeated per quote: the underlying and the rate
+    are per stamp, the strike per contract, the time to expiry per (stamp, expiry).  9 B per quote instead of 41."""
+    spec: ChainSpec
+    ts: torch.Tensor              # int64[n_t]
+    price: torch.Tensor           # float64[n_quotes], [t][e][k]
+    is_call: torch.Tensor         # uint8[n_quotes]
+    S_t: torch.Tensor             # float64[n_t]
+    K_ek: torch.Tensor            # float64[n_exp * n_strike], ascending inside an expiry
+    T_te: torch.Tensor            # float64[n_t * n_exp], ascending inside a stamp
+    r_t: torch.Tensor             # float64[n_t]
+    grid_k: torch.Tensor
+    grid_m: torch.Tensor
+
+    @staticmethod
+    def from_quotes(q: "QuoteChain") -> "StructuredChain":
+        """Strip the redundancy of a per-quote chain (tests and benches; assumes the chain IS structured)."""
+        sp = q.spec
+        v = lambda t: t.view(sp.n_t, sp.n_exp, sp.n_strike)
+        return StructuredChain(sp, q.ts, q.price, q.is_call, v(q.S)[:, 0, 0].contiguous(), v(q.K)[0].reshape(-1).contiguous(),
+                               v(q.T)[:, :, 0].reshape(-1).contiguous(), v(q.r)[:, 0, 0].contiguous(), q.grid_k, q.grid_m)
+
+
+@dataclass
 class SurfaceResult:
     iv: torch.Tensor              # float64[n_quotes]
     smile: torch.Tensor           # float64[n_t * n_exp * n_grid_k]
@@ -107,6 +131,9 @@ class SurfacePipeline:
         self.count = torch.empty(self.max_buckets, dtype=torch.int32, device=device)
         self._ws = torch.empty(256, dtype=torch.uint8, device=device)
         self._buckets = None       # (ts tensor identity, bucket_ts, bucket_start, n_buckets)
+        # chain layout: every slice (t, e) reads its abscissae from the shared ladder of expiry e
+        self._x_off = None
+        self._chain_ws = None
 
     def plan_buckets(self, ts: torch.Tensor):
         """Bucket boundaries of the day's stamps (one tiny kernel + an 8-byte read-back, done once per tape)."""
@@ -127,18 +154,35 @@ class SurfacePipeline:
             if events is not None:
                 events[stage][k].record()
 
+        structured = isinstance(q, StructuredChain)
         mark("implied_vol", 0)
-        D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv)
+        if structured:
+            if self._chain_ws is None:
+                from ._lib import lib
+                self._chain_ws = torch.empty(lib().ivx_bs_chain_workspace_bytes(sp.n_t, sp.n_exp, sp.n_strike), dtype=torch.uint8,
+                                             device=self.device)
+                self._x_off = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp) * sp.n_strike
+            D.bs_implied_vol_chain(q.price, q.is_call, q.S_t, q.K_ek, q.T_te, q.r_t, n_t=sp.n_t, n_exp=sp.n_exp,
+                                   n_strike=sp.n_strike, out=self.iv, workspace=self._chain_ws)
+        else:
+            D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv)
         mark("implied_vol", 1)
         mark("spline_strike", 0)
-        # knots of slice (t, e): x = the quoted strikes, read in place from the K column
-        D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
-                          out=self.smile, workspace=self._ws)
+        # knots of slice (t, e): x = the quoted strikes, read in place from the K column / the expiry's ladder
+        if structured:
+            D.spline_fit_eval(self.knot_off, q.K_ek, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
+                              out=self.smile, x_off=self._x_off)
+        else:
+            D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile)
         mark("spline_strike", 1)
         mark("spline_maturity", 0)
-        # plane t: n_grid_k systems with n_exp knots at x = T[t][e][0], read in place from the T column
-        D.spline_strided_batched(q.T, sp.n_exp * sp.n_strike, sp.n_strike, self.smile, q.grid_m,
-                                 sp.n_t, sp.n_grid_k, sp.n_exp, extrap=sp.extrap, out=self.surface)
+        # plane t: n_grid_k systems with n_exp knots at x = T[t][e], read in place
+        if structured:
+            D.spline_strided_batched(q.T_te, sp.n_exp, 1, self.smile, q.grid_m, sp.n_t, sp.n_grid_k, sp.n_exp,
+                                     extrap=sp.extrap, out=self.surface)
+        else:
+            D.spline_strided_batched(q.T, sp.n_exp * sp.n_strike, sp.n_strike, self.smile, q.grid_m,
+                                     sp.n_t, sp.n_grid_k, sp.n_exp, extrap=sp.extrap, out=self.surface)
         mark("spline_maturity", 1)
         mark("candles", 0)
         D.ohlc_time_major(self.surface, sp.n_series, bucket_start, nb, sp.min_count, outs=self.candles, count=self.count)
@@ -153,8 +197,8 @@ class SurfacePipeline:
 # ------------------------------------------------------------------------------------------------------
 @dataclass
 class HostQuoteChunk:
-    """A run of whole time buckets of one chain in host memory (pinned for full PCIe speed): ``ts`` int64[n_t],
-    the five float64 quote columns and ``is_call`` uint8, each n_t*n_exp*n_strike long, time-major."""
+    """A run of whole time buckets of one chain in host memory (pinned for full PCIe speed), per-quote layout:
+    ``ts`` int64[n_t], the five float64 quote columns and ``is_call`` uint8, each n_t*n_exp*n_strike long."""
     ts: torch.Tensor
     price: torch.Tensor
     S: torch.Tensor
@@ -162,51 +206,73 @@ class HostQuoteChunk:
     T: torch.Tensor
     r: torch.Tensor
     is_call: torch.Tensor
+    FIELDS = ("ts", "price", "S", "K", "T", "r", "is_call")
 
     @property
     def n_t(self) -> int:
         return self.ts.numel()
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.ts, self.price, self.S, self.K, self.T, self.r, self.is_call))
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
+
+
+@dataclass
+class HostChainChunk:
+    """The same run in the chain layout: per-quote ``price`` and ``is_call``; ``S_t``, ``r_t`` float64[n_t];
+    ``T_te`` float64[n_t*n_exp].  The strike ladder ``K_ek`` belongs to the stream (contracts do not change intraday)."""
+    ts: torch.Tensor
+    price: torch.Tensor
+    is_call: torch.Tensor
+    S_t: torch.Tensor
+    T_te: torch.Tensor
+    r_t: torch.Tensor
+    FIELDS = ("ts", "price", "is_call", "S_t", "T_te", "r_t")
+
+    @property
+    def n_t(self) -> int:
+        return self.ts.numel()
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
 
 
 class HostSurfaceStream:
     """Streams a day of quotes from host memory through the pipeline, chunk by chunk, double-buffered:
     while chunk i is being solved on the compute stream, chunk i+1 is on its way over PCIe on the copy
     stream, and the candles of chunk i-1 are on their way back.  A chunk must hold whole time buckets
-    (the caller cuts the tape at bucket boundaries); every chunk has at most ``chunk_spec.n_t`` stamps.
+    (the caller cuts the tape at bucket boundaries) and exactly ``chunk_spec.n_t`` stamps.  ``K_ek`` selects
+    the chain layout (HostChainChunk); without it chunks are per-quote (HostQuoteChunk).
     """
 
     def __init__(self, chunk_spec: ChainSpec, device: torch.device, grid_k: torch.Tensor, grid_m: torch.Tensor,
-                 max_buckets_per_chunk: int):
+                 max_buckets_per_chunk: int, K_ek: Optional[torch.Tensor] = None):
         self.spec = chunk_spec
         self.device = device
         self.grid_k = grid_k.to(device)
         self.grid_m = grid_m.to(device)
+        self.K_ek = None if K_ek is None else K_ek.to(device)
+        self.chunk_type = HostQuoteChunk if K_ek is None else HostChainChunk
         self.copy_stream = torch.cuda.Stream(device=device)
         self.out_stream = torch.cuda.Stream(device=device)
         self.max_buckets = max_buckets_per_chunk
-        n = chunk_spec.n_quotes
+        sp = chunk_spec
+        sizes = {"ts": (sp.n_t, torch.int64), "price": (sp.n_quotes, torch.float64), "is_call": (sp.n_quotes, torch.uint8),
+                 "S": (sp.n_quotes, torch.float64), "K": (sp.n_quotes, torch.float64), "T": (sp.n_quotes, torch.float64),
+                 "r": (sp.n_quotes, torch.float64), "S_t": (sp.n_t, torch.float64), "r_t": (sp.n_t, torch.float64),
+                 "T_te": (sp.n_t * sp.n_exp, torch.float64)}
         self.slots = []
         for _ in range(2):
-            cols = {name: torch.empty(n, dtype=torch.float64, device=device) for name in QUOTE_F64}
-            cols["is_call"] = torch.empty(n, dtype=torch.uint8, device=device)
-            cols["ts"] = torch.empty(chunk_spec.n_t, dtype=torch.int64, device=device)
+            cols = {f: torch.empty(sizes[f][0], dtype=sizes[f][1], device=device) for f in self.chunk_type.FIELDS}
             self.slots.append(dict(cols=cols, pipe=SurfacePipeline(chunk_spec, device, max_buckets=max_buckets_per_chunk),
                                    loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event()))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _full_chunk(self, ch: HostQuoteChunk) -> None:
-        if ch.n_t != self.spec.n_t:
-            raise IvxError(f"chunk has {ch.n_t} stamps, the stream was planned for {self.spec.n_t} "
-                           "(build a second stream for the ragged tail)")
-
-    def run(self, chunks: List[HostQuoteChunk], out_ohlc: List[torch.Tensor], out_bucket_ts: torch.Tensor,
-            out_count: torch.Tensor) -> int:
+    def run(self, chunks: List, out_ohlc: List[torch.Tensor], out_bucket_ts: torch.Tensor, out_count: torch.Tensor,
+            bucket_counts: Optional[List[int]] = None) -> int:
         """Process ``chunks`` in order; candles land in the (pinned) host tensors ``out_ohlc`` (4 x
         float64[total_buckets * n_series]), bucket stamps/counts in ``out_bucket_ts``/``out_count``.
+        ``bucket_counts[i]`` = number of time buckets in chunk i (computed from the host stamps when omitted).
         Returns the number of buckets written.  Synchronises once, at the end."""
         sp = self.spec
         compute = torch.cuda.current_stream(self.device)
@@ -215,28 +281,33 @@ class HostSurfaceStream:
         self.h2d_bytes = self.d2h_bytes = 0
         for slot in self.slots:
             slot["drained"].record(compute)
-        pending = []
         for i, ch in enumerate(chunks):
-            self._full_chunk(ch)
+            if not isinstance(ch, self.chunk_type):
+                raise IvxError(f"chunk {i} is a {type(ch).__name__}, this stream takes {self.chunk_type.__name__}")
+            if ch.n_t != sp.n_t:
+                raise IvxError(f"chunk {i} has {ch.n_t} stamps, the stream was planned for {sp.n_t} "
+                               "(build a second stream for the ragged tail)")
             slot = self.slots[i & 1]
-            # bucket layout of the chunk is host knowledge: stamps are host data
-            b = ch.ts // sp.bucket_ticks if ch.ts.dtype == torch.int64 else None
-            nb = int(torch.unique_consecutive(b).numel())
+            # the bucket layout of a chunk is host knowledge: the stamps are host data
+            nb = bucket_counts[i] if bucket_counts is not None else int(torch.unique_consecutive(ch.ts // sp.bucket_ticks).numel())
             if nb > self.max_buckets:
                 raise IvxError(f"chunk {i} spans {nb} buckets (> {self.max_buckets})")
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(slot["drained"])          # the slot's previous results have left
-                for name in QUOTE_F64 + ("is_call", "ts"):
+                for name in ch.FIELDS:
                     slot["cols"][name].copy_(getattr(ch, name), non_blocking=True)
                 slot["loaded"].record(self.copy_stream)
             self.h2d_bytes += ch.nbytes()
             compute.wait_event(slot["loaded"])
             c = slot["cols"]
-            q = QuoteChain(sp, c["ts"], c["price"], c["S"], c["K"], c["T"], c["r"], c["is_call"], self.grid_k, self.grid_m)
+            if self.K_ek is None:
+                q = QuoteChain(sp, c["ts"], c["price"], c["S"], c["K"], c["T"], c["r"], c["is_call"], self.grid_k, self.grid_m)
+            else:
+                q = StructuredChain(sp, c["ts"], c["price"], c["is_call"], c["S_t"], self.K_ek, c["T_te"], c["r_t"],
+                                    self.grid_k, self.grid_m)
             pipe = slot["pipe"]
-            pipe._buckets = None
             # time_buckets reads its count back (8 bytes): the host already knows nb, so plan without the sync
-            _, bucket_ts, bucket_start, _ = _plan_buckets_nosync(pipe, c["ts"], nb)
+            _, bucket_ts, _, _ = _plan_buckets_nosync(pipe, c["ts"], nb)
             res = pipe.run(q)
             slot["computed"].record(compute)
             with torch.cuda.stream(self.out_stream):
