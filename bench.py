@@ -193,6 +193,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("IVX_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line
         dist.init_process_group("nccl", device_id=dev)
     if args.gpus != world:
         if rank == 0:
