@@ -30,7 +30,7 @@
 namespace ivx {
 namespace {
 
-constexpr int SPL_R = 8;          // rows per thread
+constexpr int SPL_RMAX = 8;       // rows per thread
 constexpr int STRIDED_MAXK = 64;
 
 __device__ __forceinline__ double spline_eval(double xl, double xr, double yl, double yr, double Ml, double Mr, double xq) {
@@ -85,7 +85,9 @@ __device__ __forceinline__ Mat3 mat_shfl_up(const Mat3& P, int d) {
   return o;
 }
 
-__device__ __forceinline__ int spl_pad(int i) { return i + (i >> 3); }   // 1 pad per 8 doubles: chunk reads are conflict-free
+// one pad double per R rows: thread g reads doubles (R+1) g + j, and R+1 is odd -> conflict-free chunk reads
+template <int R>
+__device__ __forceinline__ int spl_pad_t(int i) { return i + i / R; }
 
 template <int G>
 __device__ __forceinline__ void group_sync(int grp) {
@@ -104,24 +106,25 @@ __device__ __forceinline__ int lower_bound_q(const double* __restrict__ xq, int 
   return lo;
 }
 
-template <int G>
+template <int G, int SPL_R>
 struct SplLayout {
   static constexpr int BT = G < 256 ? 256 : G;
   static constexpr int SPB = BT / G;
   static constexpr int NW = G / 32;
   static constexpr int CAP = G * SPL_R;
-  static constexpr int PADCAP = CAP + CAP / 8 + 8;                 // rows CAP, CAP+1 exist (read as neighbours)
+  static constexpr int PADCAP = CAP + CAP / SPL_R + 8;                 // rows CAP, CAP+1 exist (read as neighbours)
   static constexpr int PER_SLICE = 2 * PADCAP + NW * 7 + NW * 2 + NW + (G + 2) / 2;   // doubles (the tail holds NW + G+1 ints)
   static constexpr size_t SMEM = (size_t)SPB * PER_SLICE * sizeof(double);
 };
 
-template <int G>
-__global__ void __launch_bounds__(SplLayout<G>::BT) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
+template <int G, int SPL_R>
+__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
                                                                        const int64_t* __restrict__ x_off,
                                                                        const double* __restrict__ x, const double* __restrict__ y,
                                                                        int n_q, const double* __restrict__ xq, int extrap,
                                                                        double* __restrict__ yq) {
-  using L = SplLayout<G>;
+  using L = SplLayout<G, SPL_R>;
+  auto spl_pad = [](int i) { return spl_pad_t<SPL_R>(i); };
   extern __shared__ __align__(16) double smem[];
   const int grp = threadIdx.x / G, g = threadIdx.x % G;
   const int lane = threadIdx.x & 31, w = g >> 5;
@@ -430,18 +433,18 @@ using namespace ivx;
 
 extern "C" int64_t ivx_spline_workspace_bytes(int64_t, int64_t) { return 256; }
 
-template <int G>
+template <int G, int SPL_R>
 static int launch_spline(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const double* x, const double* y, int n_q,
                          const double* xq, int extrap, double* yq, cudaStream_t stream) {
-  using L = SplLayout<G>;
+  using L = SplLayout<G, SPL_R>;
   static bool attr_set = false;
   if (!attr_set) {
-    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     attr_set = true;
   }
   const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
   IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
-  k_spline_fit_eval<G><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, y, n_q, xq, extrap, yq);
+  k_spline_fit_eval<G, SPL_R><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_fit_eval");
   return IVX_OK;
 }
@@ -454,15 +457,17 @@ extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_of
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: extrap must be 0, 1 or 2");
   if (n_slices == 0 || n_q == 0) return IVX_OK;
   IVX_REQUIRE(knot_off && x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: null pointer");
-  IVX_REQUIRE(max_knots <= 1024 * SPL_R, IVX_ERR_UNSUPPORTED, "ivx_spline_fit_eval: at most %d knots per slice (got max_knots %lld)", 1024 * SPL_R, (long long)max_knots);
+  IVX_REQUIRE(max_knots <= 1024 * SPL_RMAX, IVX_ERR_UNSUPPORTED, "ivx_spline_fit_eval: at most %d knots per slice (got max_knots %lld)", 1024 * SPL_RMAX, (long long)max_knots);
   // slices longer than the capacity the launch is sized for come back as NaN rows
   const int nq = (int)n_q;
-  if (max_knots <= 32 * SPL_R) return launch_spline<32>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
-  if (max_knots <= 64 * SPL_R) return launch_spline<64>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
-  if (max_knots <= 128 * SPL_R) return launch_spline<128>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
-  if (max_knots <= 256 * SPL_R) return launch_spline<256>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
-  if (max_knots <= 512 * SPL_R) return launch_spline<512>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
-  return launch_spline<1024>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream);
+#define IVX_SPL(G, R) return launch_spline<G, R>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream)
+  if (max_knots <= 32 * 8) IVX_SPL(32, 8);
+  if (max_knots <= 64 * 8) IVX_SPL(64, 8);
+  if (max_knots <= 128 * 8) IVX_SPL(128, 8);
+  if (max_knots <= 256 * 8) IVX_SPL(256, 8);     // measured on B200: 8 rows x 256 threads beats 4 rows x 512 threads (24 vs 30 ms per day)
+  if (max_knots <= 512 * 8) IVX_SPL(512, 8);
+  IVX_SPL(1024, 8);
+#undef IVX_SPL
 }
 
 extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots, const double* x,
