@@ -127,6 +127,21 @@ __device__ __forceinline__ void st_stream(int32_t* p, int32_t v) { __stcs(p, v);
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// last index i in [lo, hi) with key[i] <= v, given key[lo] <= v: 32-ary search by one warp (one round per 5 bits)
+template <typename T>
+__device__ __forceinline__ int64_t warp_upper_le(const T* __restrict__ key, int64_t lo, int64_t hi, T v, int lane) {
+  while (hi - lo > 1) {
+    const int64_t stepw = (hi - lo + 31) >> 5;
+    const int64_t idx = lo + lane * stepw;
+    const bool le = idx < hi && __ldg(key + idx) <= v;
+    const uint32_t m = __ballot_sync(IVX_FULL_MASK, le) | 1u;
+    const int last = 31 - __clz(m);
+    lo += last * stepw;
+    hi = min(hi, lo + stepw);
+  }
+  return lo;
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -326,21 +326,6 @@ struct ExecParams {
   InterpWs W;
 };
 
-// last index i in [lo, hi) with key[i] <= v, given key[lo] <= v: 32-ary search by one warp (one round per 5 bits)
-template <typename T>
-__device__ __forceinline__ int64_t warp_upper_le(const T* __restrict__ key, int64_t lo, int64_t hi, T v, int lane) {
-  while (hi - lo > 1) {
-    const int64_t stepw = (hi - lo + 31) >> 5;
-    const int64_t idx = lo + lane * stepw;
-    const bool le = idx < hi && __ldg(key + idx) <= v;
-    const uint32_t m = __ballot_sync(IVX_FULL_MASK, le) | 1u;
-    const int last = 31 - __clz(m);
-    lo += last * stepw;
-    hi = min(hi, lo + stepw);
-  }
-  return lo;
-}
-
 __global__ void __launch_bounds__(TA_THREADS) k_interp_exec(const ExecParams P) {
   __shared__ int64_t s_sym;
   __shared__ int32_t s_g0;

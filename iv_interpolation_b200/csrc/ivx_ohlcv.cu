@@ -60,6 +60,7 @@ struct TileSmem {
   int32_t head_base[TB_GROUPS + 1];
   int32_t kept_base[TB_GROUPS + 1];
   uint16_t bstart[TB_ROWS + 1];
+  int64_t symrow[TB_ROWS];   // per candle (at its first row): global row of the first non-null symbol
   int32_t last_count_ext;    // rows of the tile's last bucket that live beyond the tile
   int64_t tile_sym_end;      // end row of the symbol owning the tile's last row
   uint32_t excl_kept, excl_heads;
@@ -153,16 +154,12 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
   if (P.sym_valid) {
     for (int i = tid; i < rows; i += TB_THREADS) S.valid[i] = P.sym_valid[r0 + i];
   }
-  // symbol starts inside the tile (overlapped with the copy)
-  if (tid == 0) {
-    // first symbol whose start is >= r0
-    int64_t lo = 0, hi = P.n_sym;  // find smallest s in [0, n_sym] with in_off[s] >= r0
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if (__ldg(P.in_off + mid) >= r0) hi = mid; else lo = mid + 1;
-    }
-    S.s_lo = (int32_t)lo;
-    S.tile_sym_end = __ldg(P.in_off + symbol_of_row(P.in_off, P.n_sym, r0 + rows - 1) + 1);
+  // symbol starts inside the tile (overlapped with the copy): 32-ary searches by warp 1
+  if (warp == 1) {
+    // first symbol whose start is >= r0  =  1 + last s in [0, n_sym] with in_off[s] <= r0 - 1   (in_off[0] = 0)
+    const int64_t s_lo = r0 == 0 ? 0 : warp_upper_le<int64_t>(P.in_off, 0, P.n_sym + 1, r0 - 1, lane) + 1;
+    const int64_t s_last = warp_upper_le<int64_t>(P.in_off, 0, P.n_sym, r0 + rows - 1, lane);   // symbol of the tile's last row
+    if (lane == 0) { S.s_lo = (int32_t)s_lo; S.tile_sym_end = __ldg(P.in_off + s_last + 1); }
   }
   __syncthreads();
   for (int64_t s = (int64_t)S.s_lo + tid; s < P.n_sym; s += TB_THREADS) {
@@ -259,6 +256,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
   }
   __syncthreads();
   if (warp == 0) {
+    // ---- warp 0: kept ranks, then the decoupled look-back over earlier tiles — the other warps reduce meanwhile --
     int c = __popc(S.kept_mask[lane]);
     int incl = c;
 #pragma unroll
@@ -270,8 +268,6 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
     if (lane == 31) S.kept_base[TB_GROUPS] = incl;
     const uint32_t agg_kept = (uint32_t)__shfl_sync(IVX_FULL_MASK, incl, 31);
     const uint32_t agg_heads = (uint32_t)n_heads;
-
-    // ---- decoupled look-back over earlier tiles --------------------------------------------------
     volatile unsigned long long* st = P.tile_state;
     uint32_t ex_k = 0, ex_h = 0;
     if (tile == 0) {
@@ -305,53 +301,53 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
       S.excl_kept = ex_k; S.excl_heads = ex_h;
       if (tile == P.n_tiles - 1 && P.total) *P.total = (int64_t)ex_k + agg_kept;
     }
+  } else {
+    // ---- warps 1..7: one thread per bucket, rows in order; the candle is parked in the tile at its first row -----
+    for (int j = tid - 32; j < n_heads; j += TB_THREADS - 32) {
+      const int b0 = S.bstart[j], b1 = S.bstart[j + 1];
+      const bool kept = (S.kept_mask[j >> 5] >> (j & 31)) & 1u;
+      Candle cd;
+      cd.init();
+      for (int i = b0; i < b1; ++i)
+        cd.feed(S.col[0][i], S.col[1][i], S.col[2][i], S.col[3][i], S.col[4][i],
+                P.sym_valid ? (S.valid[i] != 0) : true, r0 + i);
+      if (j == n_heads - 1 && S.last_count_ext > 0) {
+        for (int64_t r = r0 + rows; r < r0 + rows + S.last_count_ext; ++r)
+          cd.feed(__ldg(P.col[0] + r), __ldg(P.col[1] + r), __ldg(P.col[2] + r), __ldg(P.col[3] + r),
+                  __ldg(P.col[4] + r), P.sym_valid ? (P.sym_valid[r] != 0) : true, r);
+      }
+      uint32_t flags = cd.flags;
+      if (kept) flags |= row_flags(cd.open, cd.high, cd.low, cd.close, cd.sum) << 3;  // IVX_FLAG_OUT_*
+      S.col[0][b0] = cd.open; S.col[1][b0] = cd.high; S.col[2][b0] = cd.low; S.col[3][b0] = cd.close; S.col[4][b0] = cd.sum;
+      S.symrow[b0] = cd.sym_row;
+      if (flags && P.sym_flags) atomicOr(P.sym_flags + symbol_of_row(P.in_off, P.n_sym, r0 + b0), flags);
+    }
   }
   __syncthreads();
   const int64_t base_kept = S.excl_kept;
   const int64_t base_heads = S.excl_heads;
 
-  // ---- one thread per bucket, rows in order -----------------------------------------------------
+  // ---- emit: consecutive kept candles -> consecutive addresses --------------------------------------------------------
   for (int j = tid; j < n_heads; j += TB_THREADS) {
-    const int b0 = S.bstart[j], b1 = S.bstart[j + 1];
-    const int64_t b = S.ts[b0];
+    const int b0 = S.bstart[j];
     const bool kept = (S.kept_mask[j >> 5] >> (j & 31)) & 1u;
     const int64_t krank = base_kept + S.kept_base[j >> 5] + __popc(S.kept_mask[j >> 5] & ((1u << (j & 31)) - 1u));
-    const bool symstart = (S.symhead_mask[b0 >> 5] >> (b0 & 31)) & 1u;
-    int64_t sym = -1;
-    if (symstart) {
-      sym = symbol_of_row(P.in_off, P.n_sym, r0 + b0);
+    if ((S.symhead_mask[b0 >> 5] >> (b0 & 31)) & 1u) {
+      const int64_t sym = symbol_of_row(P.in_off, P.n_sym, r0 + b0);
       P.raw_out_off[sym] = krank;
       P.raw_group_off[sym] = base_heads + j;
     }
-    Candle cd;
-    cd.init();
-    for (int i = b0; i < b1; ++i)
-      cd.feed(S.col[0][i], S.col[1][i], S.col[2][i], S.col[3][i], S.col[4][i],
-              P.sym_valid ? (S.valid[i] != 0) : true, r0 + i);
-    int cnt = b1 - b0;
-    if (j == n_heads - 1 && S.last_count_ext > 0) {
-      for (int64_t r = r0 + rows; r < r0 + rows + S.last_count_ext; ++r) {
-        cd.feed(__ldg(P.col[0] + r), __ldg(P.col[1] + r), __ldg(P.col[2] + r), __ldg(P.col[3] + r),
-                __ldg(P.col[4] + r), P.sym_valid ? (P.sym_valid[r] != 0) : true, r);
-        ++cnt;
-      }
-    }
-    uint32_t flags = cd.flags;
     if (kept && krank < P.capacity) {
-      st_stream(P.o_ts + krank, b * P.bucket_ticks);
-      st_stream(P.o_col[0] + krank, cd.open);
-      st_stream(P.o_col[1] + krank, cd.high);
-      st_stream(P.o_col[2] + krank, cd.low);
-      st_stream(P.o_col[3] + krank, cd.close);
-      st_stream(P.o_col[4] + krank, cd.sum);
+      const int cnt = (int)S.bstart[j + 1] - b0 + (j == n_heads - 1 ? S.last_count_ext : 0);
+      st_stream(P.o_ts + krank, S.ts[b0] * P.bucket_ticks);
+      st_stream(P.o_col[0] + krank, S.col[0][b0]);
+      st_stream(P.o_col[1] + krank, S.col[1][b0]);
+      st_stream(P.o_col[2] + krank, S.col[2][b0]);
+      st_stream(P.o_col[3] + krank, S.col[3][b0]);
+      st_stream(P.o_col[4] + krank, S.col[4][b0]);
       st_stream(P.o_count + krank, cnt);
-      if (P.o_sym_row) st_stream(P.o_sym_row + krank, cd.sym_row);
+      if (P.o_sym_row) st_stream(P.o_sym_row + krank, S.symrow[b0]);
       if (P.o_group) st_stream(P.o_group + krank, base_heads + j);
-      flags |= row_flags(cd.open, cd.high, cd.low, cd.close, cd.sum) << 3;  // IVX_FLAG_OUT_*
-    }
-    if (flags && P.sym_flags) {
-      if (sym < 0) sym = symbol_of_row(P.in_off, P.n_sym, r0 + b0);
-      atomicOr(P.sym_flags + sym, flags);
     }
   }
 }
