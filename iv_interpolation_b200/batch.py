@@ -1,0 +1,126 @@
+"""DB-free batch drivers with the reference's per-symbol status / summary dictionaries.
+
+The reference's drivers wrap the two hot-path classes in PostgreSQL I/O: fetch one symbol, call the class,
+INSERT the rows, update a progress table (reference src/interpolation/batch_processor.py:67-142,202-293;
+src/candle_reconstruction/core.py:207-270).  The I/O is out of scope; what callers see —
+the status dictionaries — is kept, with frames in and frames out and ONE kernel launch per stage for the whole
+batch instead of one pandas call chain per symbol.  ``sink(symbol, frame) -> bool`` stands where the reference
+saves to the database (`_save_results`, `_save_reconstructed_candles`).
+"""
+from __future__ import annotations
+
+import time
+from typing import Callable, Dict, List, Mapping, Optional, Tuple
+
+import pandas as pd
+
+from ._lib import FLAG_IN_BAD_OHLC, FLAG_IN_NAN, FLAG_IN_NEG_VOLUME, FLAG_OUT_BAD_OHLC, FLAG_OUT_NAN, FLAG_OUT_NEG_VOLUME
+from .candle_reconstruction.core import CandleReconstructor
+from .interpolation.core import IVInterpolator
+
+Sink = Callable[[str, pd.DataFrame], bool]
+_IN_BAD = FLAG_IN_BAD_OHLC | FLAG_IN_NEG_VOLUME | FLAG_IN_NAN
+_OUT_BAD = FLAG_OUT_BAD_OHLC | FLAG_OUT_NEG_VOLUME | FLAG_OUT_NAN
+
+
+def _summary(batch_id: int, statuses: List[dict], t0: float) -> dict:
+    """batch_processor.py:287-293."""
+    return {"batch_id": batch_id,
+            "success_count": sum(s["status"] == "success" for s in statuses),
+            "error_count": sum(s["status"] == "error" for s in statuses),
+            "skip_count": sum(s["status"] == "skipped" for s in statuses),
+            "duration": time.time() - t0}
+
+
+class InterpolationBatch:
+    """``BatchProcessor.process_symbol`` for every symbol of a batch (batch_processor.py:67-142)."""
+
+    def __init__(self, method: str = "linear", min_points: int = 10, sink: Optional[Sink] = None, batch_id: Optional[int] = None):
+        self.interpolator = IVInterpolator(method=method, min_points=min_points)      # batch_processor.py:21-24
+        self.sink = sink
+        self.batch_id = int(time.time()) if batch_id is None else batch_id            # monitoring/progress.py:18-20
+
+    def run(self, frames: Mapping[str, pd.DataFrame]) -> Tuple[Dict[str, pd.DataFrame], List[dict], dict]:
+        t0 = time.time()
+        symbols = list(frames)
+        statuses: List[Optional[dict]] = [None] * len(symbols)
+        todo = []
+        for i, sym in enumerate(symbols):
+            if frames[sym] is None or frames[sym].empty:                              # :89-92
+                statuses[i] = {"symbol": sym, "status": "skipped", "reason": "No data found"}
+            else:
+                todo.append(i)
+        outs: Dict[str, pd.DataFrame] = {}
+        try:
+            results = self.interpolator.interpolate_batch([frames[symbols[i]] for i in todo]) if todo else []
+            err = None
+        except Exception as e:                                                        # :132-142
+            results, err = [None] * len(todo), str(e)
+        elapsed = time.time() - t0
+        for i, res in zip(todo, results):
+            sym = symbols[i]
+            if err is not None:
+                statuses[i] = {"symbol": sym, "status": "error", "error": err, "processing_time": elapsed}
+            elif res is None:                                                         # :99-102
+                statuses[i] = {"symbol": sym, "status": "skipped", "reason": "Interpolation failed or insufficient data"}
+            else:
+                res["batch_id"] = self.batch_id                                       # :105
+                if self.sink is None or self.sink(sym, res):                          # :108
+                    outs[sym] = res
+                    statuses[i] = {"symbol": sym, "status": "success", "input_rows": len(frames[sym]),
+                                   "output_rows": len(res), "processing_time": elapsed / max(1, len(todo))}
+                else:
+                    statuses[i] = {"symbol": sym, "status": "error", "error": "Failed to save to database"}
+        return outs, statuses, _summary(self.batch_id, statuses, t0)
+
+
+class CandleBatch:
+    """``MultiSymbolCandleReconstructor.process_symbol`` for every symbol of a batch (candle core.py:207-270):
+    validate input -> reconstruct -> validate output -> save -> stats, the two validations read from the flag
+    bits the reduction kernel produces in the same launch."""
+
+    def __init__(self, target_frequency: str = "5min", sink: Optional[Sink] = None):
+        self.reconstructor = CandleReconstructor(target_frequency)                    # candle core.py:180
+        self.sink = sink
+
+    def run(self, frames: Mapping[str, pd.DataFrame]) -> Tuple[Dict[str, pd.DataFrame], List[dict], dict]:
+        t0 = time.time()
+        symbols = list(frames)
+        statuses: List[Optional[dict]] = [None] * len(symbols)
+        todo = []
+        for i, sym in enumerate(symbols):
+            if frames[sym] is None or frames[sym].empty:                              # :225-226
+                statuses[i] = {"symbol": sym, "status": "skipped", "reason": "No minute data found"}
+            else:
+                todo.append(i)
+        flags: list = []
+        outs: Dict[str, pd.DataFrame] = {}
+        try:
+            # check_len=False: the input validation (:229) comes before the length early-out inside reconstruct (:64)
+            results = self.reconstructor.reconstruct_batch([frames[symbols[i]] for i in todo], check_len=False,
+                                                           flags_out=flags) if todo else []
+            err = None
+        except Exception as e:
+            results, err, flags = [None] * len(todo), str(e), [None] * len(todo)
+        elapsed = time.time() - t0
+        n = self.reconstructor.frequency_minutes
+        for k, (i, res) in enumerate(zip(todo, results)):
+            sym, src = symbols[i], frames[symbols[i]]
+            fl = flags[k]
+            if err is not None:
+                statuses[i] = {"symbol": sym, "status": "error", "error": err, "processing_time": elapsed}
+            elif any(c not in src.columns for c in ("open", "high", "low", "close", "volume")) or \
+                    (fl is not None and (fl & _IN_BAD)):                              # :229-230 (validate raises inside -> False)
+                statuses[i] = {"symbol": sym, "status": "error", "error": "Invalid input candle data"}
+            elif res is None or len(src) < n:                                         # :235-236 (None incl. :64-66)
+                statuses[i] = {"symbol": sym, "status": "skipped", "reason": "Reconstruction failed"}
+            elif res.empty or (fl & _OUT_BAD):                                        # :239-240: validate(empty) is False
+                statuses[i] = {"symbol": sym, "status": "error", "error": "Invalid reconstructed candle data"}
+            elif self.sink is not None and not self.sink(sym, res):
+                statuses[i] = {"symbol": sym, "status": "error", "error": "Failed to save reconstructed candles"}
+            else:
+                outs[sym] = res
+                statuses[i] = {"symbol": sym, "status": "success", "input_candles": len(src), "output_candles": len(res),
+                               "processing_time": elapsed / max(1, len(todo)),
+                               "stats": self.reconstructor.get_reconstruction_stats(src, res)}
+        return outs, statuses, _summary(int(t0), statuses, t0)

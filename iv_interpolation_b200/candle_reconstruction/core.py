@@ -52,7 +52,7 @@ class CandleReconstructor:
 
     # -- many symbols in one launch ---------------------------------------------------------------------
     def reconstruct_batch(self, frames: Sequence[pd.DataFrame], presorted: bool = False,
-                          check_len: bool = True) -> List[Optional[pd.DataFrame]]:
+                          check_len: bool = True, flags_out: Optional[list] = None) -> List[Optional[pd.DataFrame]]:
         """``[reconstruct_symbol_candles(f) for f in frames]`` with a single kernel launch.
 
         ``presorted=True, check_len=False`` is the contract of the reference's second entry,
@@ -68,6 +68,8 @@ class CandleReconstructor:
             raise IvxError("no CUDA device: iv_interpolation_b200 has no CPU path")
         n = self.frequency_minutes
         results: List[Optional[pd.DataFrame]] = [None] * len(frames)
+        if flags_out is not None:           # per frame: IVX_FLAG_* bits of the launch (validate_candle_data of input and output), None = not run
+            flags_out[:] = [None] * len(frames)
         inputs, srcs, slots = [], [], []
         for i, df in enumerate(frames):
             if df.empty:
@@ -127,6 +129,10 @@ class CandleReconstructor:
             status = res.sym_status.cpu().numpy()
             out_off = res.out_off.cpu().numpy()
             goff = res.sym_group_off.cpu().numpy()
+            if flags_out is not None:
+                fl = res.sym_flags.cpu().numpy()
+                for g, j in enumerate(members):
+                    flags_out[slots[j]] = int(fl[g])
             o_ts = res.ts.cpu().numpy()
             o_cols = [t.cpu().numpy() for t in (res.open, res.high, res.low, res.close, res.volume)]
             o_sym = res.sym_row.cpu().numpy()
@@ -168,7 +174,7 @@ class CandleReconstructor:
             from .._lib import FLAG_IN_BAD_OHLC, FLAG_IN_NAN, FLAG_IN_NEG_VOLUME
 
             dev = torch.device("cuda")
-            cols = [torch.from_numpy(np.ascontiguousarray(df[c].to_numpy(dtype=np.float64))).to(dev)
+            cols = [torch.from_numpy(np.array(df[c].to_numpy(dtype=np.float64), dtype=np.float64, copy=True)).to(dev)
                     for c in ("open", "high", "low", "close", "volume")]
             m = len(df)
             off = torch.tensor([0, m], dtype=torch.int64, device=dev)

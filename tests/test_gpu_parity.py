@@ -348,3 +348,58 @@ def test_time_major_candles_vs_oracle(dev):
             assert _eq(got[:, s][full], w[key][full]), key
             assert np.isnan(got[:, s][~full]).all()
     assert _eq(cnt.cpu().numpy(), np.diff(np.r_[start, n_t]))
+
+
+# ---------------------------------------------------------------------------------------------
+# batch drivers: the reference's status dictionaries, one launch per stage
+# ---------------------------------------------------------------------------------------------
+def test_batch_drivers_status_contract(dev, golden_interp, golden_candles):
+    from iv_interpolation_b200.batch import CandleBatch, InterpolationBatch
+    from oracle.df_oracle import OracleCandleReconstructor
+    import pandas as pd
+    names = [n for n in json.loads(str(golden_interp["names"])) if json.loads(str(golden_interp[f"{n}/kwargs"])) == {}][:25]
+    frames = {n: golden_io.dict_to_frame(f"{n}/in", golden_interp) for n in names}
+    frames["empty"] = pd.DataFrame()
+    saved = {}
+    outs, statuses, summary = InterpolationBatch(sink=lambda s, f: saved.setdefault(s, f) is f, batch_id=7).run(frames)
+    assert [s["symbol"] for s in statuses] == list(frames)
+    for st in statuses:
+        n = st["symbol"]
+        want = None if n == "empty" else golden_io.dict_to_frame(f"{n}/out", golden_interp)
+        if n == "empty":
+            assert st == {"symbol": n, "status": "skipped", "reason": "No data found"}
+        elif want is None:
+            assert st["status"] == "skipped" and st["reason"] == "Interpolation failed or insufficient data"
+        else:
+            assert st["status"] == "success" and st["input_rows"] == len(frames[n]) and st["output_rows"] == len(want)
+            assert (outs[n]["batch_id"] == 7).all() and saved[n] is outs[n]
+            golden_io.assert_frames_match(want, outs[n].drop(columns=["batch_id"]))
+    assert summary["success_count"] + summary["skip_count"] + summary["error_count"] == len(frames) and summary["batch_id"] == 7
+
+    cnames = [n for n in json.loads(str(golden_candles["names"])) if str(golden_candles[f"{n}/freq"]) == "5min"][:30]
+    cframes = {n: golden_io.dict_to_frame(f"{n}/in", golden_candles) for n in cnames}
+    cframes = {n: f for n, f in cframes.items() if all(c in f.columns for c in ("symbol", "timestamp", "open", "high", "low", "close", "volume"))}
+    outs, statuses, summary = CandleBatch("5min").run(cframes)
+    ref = OracleCandleReconstructor("5min")
+    kinds = set()
+    for st in statuses:
+        f = cframes[st["symbol"]]
+        # the reference's sequence (candle core.py:225-257), spelled with the oracle classes
+        if f.empty:
+            want = ("skipped", "No minute data found")
+        elif not ref.validate_candle_data(f):
+            want = ("error", "Invalid input candle data")
+        else:
+            r = ref.reconstruct_symbol_candles(f)
+            if r is None:
+                want = ("skipped", "Reconstruction failed")
+            elif not ref.validate_candle_data(r):
+                want = ("error", "Invalid reconstructed candle data")
+            else:
+                want = ("success", None)
+        assert (st["status"], st.get("reason") or st.get("error")) == want, st["symbol"]
+        kinds.add(want[0])
+        if want[0] == "success":
+            assert st["input_candles"] == len(f) and st["output_candles"] == len(outs[st["symbol"]])
+            assert st["stats"]["original_candles"] == len(f)
+    assert "success" in kinds and len(kinds) >= 2
