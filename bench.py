@@ -335,7 +335,7 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
     """Through the host-facing entry (surface.HostSurfaceStream): every step copies the whole day's quotes
     H2D from pinned memory, chunk by chunk, and the candles D2H.  The host tape holds RING distinct chunks
     (pinned) that are re-sent cyclically until the day's stamps are covered — every byte crosses PCIe.
-    layout "chain": S per stamp, K per contract (sent once), T per (stamp, expiry) — 9 B per quote;
+    layout "chain": S per stamp, K and call/put per contract (sent once), T per (stamp, expiry) — 8 B per quote;
     layout "quotes": every column per quote — 41 B per quote."""
     ring = 8
     n_chunks = max(1, n_t // CHUNK_T)
@@ -348,7 +348,7 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
     for i in range(ring):
         sl, tl = slice(i * per, (i + 1) * per), slice(i * CHUNK_T, (i + 1) * CHUNK_T)
         if layout == "chain":
-            host.append(SF.HostChainChunk(ts=pin(sc.ts[tl]), price=pin(sc.price[sl]), is_call=pin(sc.is_call[sl]), S_t=pin(sc.S_t[tl]),
+            host.append(SF.HostChainChunk(ts=pin(sc.ts[tl]), price=pin(sc.price[sl]), S_t=pin(sc.S_t[tl]),
                                           T_te=pin(sc.T_te[i * CHUNK_T * N_EXP:(i + 1) * CHUNK_T * N_EXP]), r_t=pin(sc.r_t[tl])))
         else:
             cols = {name: pin(getattr(chain, name)[sl]) for name in SF.QUOTE_F64 + ("is_call",)}
@@ -356,7 +356,7 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
     chunks = [host[i % ring] for i in range(n_chunks)]
     nb_chunk = CHUNK_T // 60
     stream = SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=nb_chunk + 1,
-                                  K_ek=sc.K_ek if sc is not None else None)
+                                  K_ek=sc.K_ek if sc is not None else None, is_call_ek=sc.is_call if sc is not None else None)
     nb_total = n_chunks * (nb_chunk + 1)
     out = [torch.empty(nb_total * cspec.n_series, dtype=torch.float64).pin_memory() for _ in range(4)]
     out_ts = torch.empty(nb_total, dtype=torch.int64).pin_memory()

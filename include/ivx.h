@@ -159,11 +159,13 @@ int ivx_bs_implied_vol(int64_t n, const double* price, const double* S, const do
                        int32_t* iters, ivx_stream_t stream);
 /* Chain layout (one underlying, one day): quote (t, e, k) sits at price[(t*n_exp + e)*n_strike + k]; the
  * underlying S_t[n_t] and rate r_t[n_t] are per stamp, the strike K_ek[n_exp*n_strike] per contract, the time to
- * expiry T_te[n_t*n_exp] per (stamp, expiry): 9 B/quote in, 8 B out instead of 41 + 8.  ln S, ln K, rT and
+ * expiry T_te[n_t*n_exp] per (stamp, expiry), call/put per contract or per quote: 8-9 B/quote in, 8 B out
+ * instead of 41 + 8.  ln S, ln K, rT and
  * e^{-rT} are formed once per stamp / contract / (stamp, expiry) in `workspace`. */
 int64_t ivx_bs_chain_workspace_bytes(int64_t n_t, int64_t n_exp, int64_t n_strike);
 int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
-                             const uint8_t* is_call, const double* S_t, const double* K_ek,
+                             const uint8_t* is_call /* [t][e][k] if is_call_per_quote, else [e][k] */,
+                             int32_t is_call_per_quote, const double* S_t, const double* K_ek,
                              const double* T_te, const double* r_t, double* sigma, int32_t* iters,
                              void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
 int ivx_bs_price(int64_t n, const double* S, const double* K, const double* T, const double* r,

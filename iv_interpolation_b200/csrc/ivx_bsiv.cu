@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) k_chain_terms(int64_t n_t, int64_t n_exp,
 // grid: x over the n_exp*n_strike contracts of one stamp, y over stamps
 __global__ void __launch_bounds__(256) k_bs_implied_vol_chain(int64_t t0, int32_t n_exp, int32_t n_strike, int64_t n_t,
                                                               const double* __restrict__ price, const uint8_t* __restrict__ is_call,
-                                                              const double* __restrict__ S_t, const double* __restrict__ K_ek,
+                                                              int32_t call_per_quote, const double* __restrict__ S_t, const double* __restrict__ K_ek,
                                                               const double* __restrict__ T_te, const double* __restrict__ terms,
                                                               double* __restrict__ sigma, int32_t* __restrict__ iters) {
   const int32_t n_ek = n_exp * n_strike;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol_chain(int64_t t0, int32_
     const int32_t e = j / n_strike;
     const int64_t te = t * n_exp + e;
     const int64_t n_te = n_t * (int64_t)n_exp;
-    p = ld_stream(price + i); call = is_call[i] != 0;
+    p = ld_stream(price + i); call = (call_per_quote ? is_call[i] : __ldg(is_call + j)) != 0;
     s_ = __ldg(S_t + t); k_ = __ldg(K_ek + j); t_ = __ldg(T_te + te);
     const double lnS = __ldg(terms + t), lnK = __ldg(terms + n_t + j);
     const double rt = __ldg(terms + n_t + n_ek + te);
@@ -363,7 +363,8 @@ extern "C" int64_t ivx_bs_chain_workspace_bytes(int64_t n_t, int64_t n_exp, int6
 }
 
 extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
-                                        const uint8_t* is_call, const double* S_t, const double* K_ek, const double* T_te,
+                                        const uint8_t* is_call, int32_t is_call_per_quote, const double* S_t,
+                                        const double* K_ek, const double* T_te,
                                         const double* r_t, double* sigma, int32_t* iters, void* workspace,
                                         int64_t workspace_bytes, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -379,7 +380,7 @@ extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_st
   const unsigned gx = (unsigned)((n_exp * n_strike + 255) / 256);
   for (int64_t t0 = 0; t0 < n_t; t0 += 65535) {
     const unsigned gy = (unsigned)(n_t - t0 < 65535 ? n_t - t0 : 65535);
-    k_bs_implied_vol_chain<<<dim3(gx, gy), 256, 0, stream>>>(t0, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, S_t, K_ek,
+    k_bs_implied_vol_chain<<<dim3(gx, gy), 256, 0, stream>>>(t0, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, is_call_per_quote, S_t, K_ek,
                                                              T_te, terms, sigma, iters);
     IVX_LAUNCH_CHECK("k_bs_implied_vol_chain");
   }

@@ -328,11 +328,14 @@ def bs_implied_vol(price, S, K, T, r, is_call, *, want_iters: bool = False, out:
 def bs_implied_vol_chain(price, is_call, S_t, K_ek, T_te, r_t, *, n_t: int, n_exp: int, n_strike: int,
                          out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
                          want_iters: bool = False):
-    """Chain layout: ``price``/``is_call`` per quote [t][e][k]; ``S_t``, ``r_t`` per stamp, ``K_ek`` per contract,
-    ``T_te`` per (stamp, expiry).  9 B/quote read instead of 41."""
+    """Chain layout: ``price`` per quote [t][e][k]; ``S_t``, ``r_t`` per stamp, ``K_ek`` per contract, ``T_te`` per
+    (stamp, expiry); ``is_call`` per contract [e][k] (8 B/quote read) or per quote (9 B/quote) instead of 41."""
     n = n_t * n_exp * n_strike
     _req(price, torch.float64, "price"); _req(is_call, torch.uint8, "is_call")
-    for t, m, name in ((price, n, "price"), (is_call, n, "is_call"), (S_t, n_t, "S_t"), (r_t, n_t, "r_t"),
+    per_quote = is_call.numel() == n and n != n_exp * n_strike
+    if not per_quote and is_call.numel() != n_exp * n_strike:
+        raise _lib.IvxError(f"is_call: expected {n_exp * n_strike} (per contract) or {n} (per quote) elements")
+    for t, m, name in ((price, n, "price"), (S_t, n_t, "S_t"), (r_t, n_t, "r_t"),
                        (K_ek, n_exp * n_strike, "K_ek"), (T_te, n_t * n_exp, "T_te")):
         if t.numel() != m:
             raise _lib.IvxError(f"{name}: expected {m} elements, got {t.numel()}")
@@ -343,7 +346,7 @@ def bs_implied_vol_chain(price, is_call, S_t, K_ek, T_te, r_t, *, n_t: int, n_ex
     ws = workspace if workspace is not None and workspace.numel() >= wsb else _empty(wsb, torch.uint8, price)
     sigma = out if out is not None else _empty(n, torch.float64, price)
     iters = _empty(n, torch.int32, price) if want_iters else None
-    check(L.ivx_bs_implied_vol_chain(n_t, n_exp, n_strike, _ptr(price), _ptr(is_call), _ptr(S_t), _ptr(K_ek), _ptr(T_te),
+    check(L.ivx_bs_implied_vol_chain(n_t, n_exp, n_strike, _ptr(price), _ptr(is_call), int(per_quote), _ptr(S_t), _ptr(K_ek), _ptr(T_te),
                                      _ptr(r_t), _ptr(sigma), _ptr(iters), _ptr(ws), ws.numel(), _stream()),
           "ivx_bs_implied_vol_chain")
     _count("bs_implied_vol_chain")

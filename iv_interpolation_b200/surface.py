@@ -80,7 +80,7 @@ class StructuredChain:
     spec: ChainSpec
     ts: torch.Tensor              # int64[n_t]
     price: torch.Tensor           # float64[n_quotes], [t][e][k]
-    is_call: torch.Tensor         # uint8[n_quotes]
+    is_call: torch.Tensor         # uint8[n_exp * n_strike] (call/put is a property of the contract) or uint8[n_quotes]
     S_t: torch.Tensor             # float64[n_t]
     K_ek: torch.Tensor            # float64[n_exp * n_strike], ascending inside an expiry
     T_te: torch.Tensor            # float64[n_t * n_exp], ascending inside a stamp
@@ -93,7 +93,10 @@ class StructuredChain:
         """Strip the redundancy of a per-quote chain (tests and benches; assumes the chain IS structured)."""
         sp = q.spec
         v = lambda t: t.view(sp.n_t, sp.n_exp, sp.n_strike)
-        return StructuredChain(sp, q.ts, q.price, q.is_call, v(q.S)[:, 0, 0].contiguous(), v(q.K)[0].reshape(-1).contiguous(),
+        call3 = v(q.is_call)
+        per_contract = bool((call3 == call3[:1]).all().item())
+        is_call = call3[0].reshape(-1).contiguous() if per_contract else q.is_call
+        return StructuredChain(sp, q.ts, q.price, is_call, v(q.S)[:, 0, 0].contiguous(), v(q.K)[0].reshape(-1).contiguous(),
                                v(q.T)[:, :, 0].reshape(-1).contiguous(), v(q.r)[:, 0, 0].contiguous(), q.grid_k, q.grid_m)
 
 
@@ -218,15 +221,15 @@ class HostQuoteChunk:
 
 @dataclass
 class HostChainChunk:
-    """The same run in the chain layout: per-quote ``price`` and ``is_call``; ``S_t``, ``r_t`` float64[n_t];
-    ``T_te`` float64[n_t*n_exp].  The strike ladder ``K_ek`` belongs to the stream (contracts do not change intraday)."""
+    """The same run in the chain layout: per-quote ``price``; ``S_t``, ``r_t`` float64[n_t]; ``T_te`` float64[n_t*n_exp].
+    The strike ladder ``K_ek`` and the call/put flags ``is_call_ek`` belong to the stream (contracts do not change
+    intraday): 8 B per quote cross PCIe."""
     ts: torch.Tensor
     price: torch.Tensor
-    is_call: torch.Tensor
     S_t: torch.Tensor
     T_te: torch.Tensor
     r_t: torch.Tensor
-    FIELDS = ("ts", "price", "is_call", "S_t", "T_te", "r_t")
+    FIELDS = ("ts", "price", "S_t", "T_te", "r_t")
 
     @property
     def n_t(self) -> int:
@@ -241,16 +244,19 @@ class HostSurfaceStream:
     while chunk i is being solved on the compute stream, chunk i+1 is on its way over PCIe on the copy
     stream, and the candles of chunk i-1 are on their way back.  A chunk must hold whole time buckets
     (the caller cuts the tape at bucket boundaries) and exactly ``chunk_spec.n_t`` stamps.  ``K_ek`` selects
-    the chain layout (HostChainChunk); without it chunks are per-quote (HostQuoteChunk).
+    the chain layout (HostChainChunk, with ``is_call_ek``); without it chunks are per-quote (HostQuoteChunk).
     """
 
     def __init__(self, chunk_spec: ChainSpec, device: torch.device, grid_k: torch.Tensor, grid_m: torch.Tensor,
-                 max_buckets_per_chunk: int, K_ek: Optional[torch.Tensor] = None):
+                 max_buckets_per_chunk: int, K_ek: Optional[torch.Tensor] = None, is_call_ek: Optional[torch.Tensor] = None):
         self.spec = chunk_spec
         self.device = device
         self.grid_k = grid_k.to(device)
         self.grid_m = grid_m.to(device)
         self.K_ek = None if K_ek is None else K_ek.to(device)
+        if (K_ek is None) != (is_call_ek is None):
+            raise IvxError("the chain layout needs both K_ek and is_call_ek")
+        self.is_call_ek = None if is_call_ek is None else is_call_ek.to(device)
         self.chunk_type = HostQuoteChunk if K_ek is None else HostChainChunk
         self.copy_stream = torch.cuda.Stream(device=device)
         self.out_stream = torch.cuda.Stream(device=device)
@@ -303,7 +309,7 @@ class HostSurfaceStream:
             if self.K_ek is None:
                 q = QuoteChain(sp, c["ts"], c["price"], c["S"], c["K"], c["T"], c["r"], c["is_call"], self.grid_k, self.grid_m)
             else:
-                q = StructuredChain(sp, c["ts"], c["price"], c["is_call"], c["S_t"], self.K_ek, c["T_te"], c["r_t"],
+                q = StructuredChain(sp, c["ts"], c["price"], self.is_call_ek, c["S_t"], self.K_ek, c["T_te"], c["r_t"],
                                     self.grid_k, self.grid_m)
             pipe = slot["pipe"]
             # time_buckets reads its count back (8 bytes): the host already knows nb, so plan without the sync

@@ -270,7 +270,7 @@ def make_quote_chain(seed: int, spec, device, s0: float = 4500.0, t0: int = T0_U
 
     spot: geometric random walk; strikes: a fixed ladder over [0.5, 1.5] s0; T_e(t) = (7 + 12 e) days - t;
     sigma: a skewed smile in ln(K/S)/sqrt(T) clipped to [0.05, 1.5] plus 0.3 vol-point noise; 90 % of the
-    quotes are out-of-the-money options, 10 % their in-the-money twins; r = 0.05.  Prices come from the
+    contracts are out-of-the-money at the open, 10 % their in-the-money twins (call/put is per contract); r = 0.05.  Prices come from the
     library's own forward pricer (ivx_bs_price).  ``drop_frac`` of the prices are set to NaN (missing quotes).
     Returns a surface.QuoteChain.
     """
@@ -294,6 +294,8 @@ def make_quote_chain(seed: int, spec, device, s0: float = 4500.0, t0: int = T0_U
     is_call = torch.empty(n, dtype=torch.uint8, device=device)
     per_t = n_e * n_k
     ke = (torch.arange(n_e, device=device)[:, None] * 3 + torch.arange(n_k, device=device)[None, :] * 7)
+    # call/put is a property of the contract: out-of-the-money side at the open, every tenth contract the other side
+    call_ek = ((ladder[None, :] >= s0).expand(n_e, n_k) ^ ((ke % 10) == 0)).to(torch.uint8)
     for a in range(0, n_t, chunk_t):
         b = min(n_t, a + chunk_t)
         sl = slice(a * per_t, b * per_t)
@@ -304,10 +306,8 @@ def make_quote_chain(seed: int, spec, device, s0: float = 4500.0, t0: int = T0_U
         sg = level[a:b, None, None] + 0.35 * m * m - 0.08 * m + 0.003 * torch.randn(b - a, n_e, n_k, generator=g, **f64)
         S[sl] = s_.reshape(-1); K[sl] = k_.reshape(-1); T[sl] = t_.reshape(-1)
         sigma[sl] = sg.clamp_(0.05, 1.5).reshape(-1)
-        otm_call = k_ >= s_
-        flip = ((ke[None] + torch.arange(a, b, device=device)[:, None, None]) % 10) == 0
-        is_call[sl] = (otm_call ^ flip).to(torch.uint8).reshape(-1)
-        del s_, k_, t_, m, sg, otm_call, flip
+        is_call[sl] = call_ek[None].expand(b - a, n_e, n_k).reshape(-1)
+        del s_, k_, t_, m, sg
     r = torch.full((n,), 0.05, **f64)
     price = D.bs_price(S, K, T, r, sigma, is_call)
     if drop_frac > 0:
@@ -339,8 +339,8 @@ def make_quote_chain_np(seed: int, n_t: int, n_exp: int, n_strike: int, pricer, 
     m = np.log(K / S) / np.sqrt(T)
     sigma = np.clip(level[:, None, None] + 0.35 * m * m - 0.08 * m + 0.003 * rng.standard_normal(shape), 0.05, 1.5)
     ke = np.arange(n_exp)[:, None] * 3 + np.arange(n_strike)[None, :] * 7
-    flip = ((ke[None] + np.arange(n_t)[:, None, None]) % 10) == 0
-    is_call = ((K >= S) ^ flip).astype(np.uint8)
+    call_ek = (np.broadcast_to(ladder[None, :] >= s0, (n_exp, n_strike)) ^ ((ke % 10) == 0))
+    is_call = np.broadcast_to(call_ek[None], shape).astype(np.uint8)
     flat = lambda a: np.ascontiguousarray(a).reshape(-1)
     S, K, T, sigma, is_call = flat(S), flat(K), flat(T), flat(sigma), flat(is_call)
     r = np.full(S.shape, 0.05)

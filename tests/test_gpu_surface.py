@@ -80,9 +80,13 @@ def test_chain_layout_matches_per_quote_layout(dev):
     from iv_interpolation_b200 import surface as SF
     spec, chain = _chain(dev, seed=6, n_t=70, n_exp=6, n_strike=300, nk=64, nm=16, drop=0.03, min_count=10)
     sc = SF.StructuredChain.from_quotes(chain)
-    assert sc.S_t.numel() == 70 and sc.K_ek.numel() == 1800 and sc.T_te.numel() == 420
+    assert sc.S_t.numel() == 70 and sc.K_ek.numel() == 1800 and sc.T_te.numel() == 420 and sc.is_call.numel() == 1800
     a = SF.SurfacePipeline(spec, dev).run(chain)
     b = SF.SurfacePipeline(spec, dev).run(sc)
+    # call/put flags given per quote instead of per contract: same bits
+    import dataclasses
+    b2 = SF.SurfacePipeline(spec, dev).run(dataclasses.replace(sc, is_call=chain.is_call))
+    assert _eq(b.iv.cpu().numpy(), b2.iv.cpu().numpy())
     _stagewise_check(spec, chain, b)
     iva, ivb = a.iv.cpu().numpy(), b.iv.cpu().numpy()
     assert _eq(np.isnan(iva), np.isnan(ivb))
@@ -128,18 +132,18 @@ def test_host_stream_equals_resident_pipeline(dev):
     for got, want in zip(out, (full.open, full.high, full.low, full.close)):
         assert _eq(got[: rows * cspec.n_series].numpy(), want.cpu().numpy())
     assert stream.h2d_bytes == n_chunks * (per * 41 + chunk_t * 8)
-    # the same tape in the chain layout: 9 B per quote over PCIe, same candles to within the IV tolerance
+    # the same tape in the chain layout: 8 B per quote over PCIe, same candles to within the IV tolerance
     sc = SF.StructuredChain.from_quotes(chain)
     cchunks = []
     for i in range(n_chunks):
         sl, tl = slice(i * per, (i + 1) * per), slice(i * chunk_t, (i + 1) * chunk_t)
         pin = lambda t: t.cpu().pin_memory()
-        cchunks.append(SF.HostChainChunk(ts=pin(sc.ts[tl]), price=pin(sc.price[sl]), is_call=pin(sc.is_call[sl]), S_t=pin(sc.S_t[tl]),
+        cchunks.append(SF.HostChainChunk(ts=pin(sc.ts[tl]), price=pin(sc.price[sl]), S_t=pin(sc.S_t[tl]),
                                          T_te=pin(sc.T_te[i * chunk_t * 4:(i + 1) * chunk_t * 4]), r_t=pin(sc.r_t[tl])))
-    cstream = SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=3, K_ek=sc.K_ek)
+    cstream = SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=3, K_ek=sc.K_ek, is_call_ek=sc.is_call)
     out2 = [torch.full((nb * cspec.n_series,), -1.0, dtype=torch.float64).pin_memory() for _ in range(4)]
     rows2 = cstream.run(cchunks, out2, out_ts, out_cnt, bucket_counts=[2] * n_chunks)
-    assert rows2 == rows and cstream.h2d_bytes == n_chunks * (per * 9 + chunk_t * (8 + 8 + 8 + 4 * 8))
+    assert rows2 == rows and cstream.h2d_bytes == n_chunks * (per * 8 + chunk_t * (8 + 8 + 8 + 4 * 8)) and sc.is_call.numel() == 4 * 48
     for got, want in zip(out2, out):
         g, w = got[: rows * cspec.n_series].numpy(), want[: rows * cspec.n_series].numpy()
         assert _eq(np.isnan(g), np.isnan(w)) and np.nanmax(np.abs(g - w)) <= 1e-8
