@@ -15,8 +15,8 @@
 namespace ivx {
 namespace {
 
-constexpr int TB_THREADS = 256;
-constexpr int TB_ROWS = 1024;
+constexpr int TB_THREADS = 128;
+constexpr int TB_ROWS = 512;
 constexpr int TB_GROUPS = TB_ROWS / 32;
 constexpr int64_t BID_NAT = INT64_MIN;  // bucket id given to rows without a timestamp
 
@@ -54,11 +54,11 @@ struct TileSmem {
   int64_t ts[TB_ROWS];       // timestamps, overwritten in place by bucket ids
   double col[5][TB_ROWS];
   uint8_t valid[TB_ROWS];
-  uint32_t head_mask[TB_GROUPS];
-  uint32_t symhead_mask[TB_GROUPS];
-  uint32_t kept_mask[TB_GROUPS];
-  int32_t head_base[TB_GROUPS + 1];
-  int32_t kept_base[TB_GROUPS + 1];
+  uint32_t head_mask[32];     // one word per 32 rows; sized for a warp-wide scan, words past TB_GROUPS stay 0
+  uint32_t symhead_mask[32];
+  uint32_t kept_mask[32];
+  int32_t head_base[33];
+  int32_t kept_base[33];
   uint16_t bstart[TB_ROWS + 1];
   int64_t symrow[TB_ROWS];   // per candle (at its first row): global row of the first non-null symbol
   int32_t last_count_ext;    // rows of the tile's last bucket that live beyond the tile
@@ -66,6 +66,7 @@ struct TileSmem {
   uint32_t excl_kept, excl_heads;
   int32_t tile_id;
   int32_t s_lo;
+  int32_t next_bucket;       // work counter of the bucket walk
   uint64_t bar;
 };
 
@@ -102,7 +103,6 @@ struct Candle {
     sum = 0.0; comp = 0.0; has_open = false; sym_row = -1; flags = 0;
   }
   __device__ __forceinline__ void feed(double o, double h, double l, double c, double v, bool sv, int64_t grow) {
-    flags |= row_flags(o, h, l, c, v);
     if (!has_open && !isnan(o)) { open = o; has_open = true; }      // 'first' non-null
     if (!isnan(c)) close = c;                                       // 'last' non-null
     if (!isnan(h)) high = isnan(high) ? h : fmax(high, h);          // NaN-skipping max
@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
     mbar_init(&S.bar, 1);
     fence_mbar_init();
   }
-  if (tid < TB_GROUPS) { S.symhead_mask[tid] = 0; S.kept_mask[tid] = 0; }
+  if (tid < 32) { S.symhead_mask[tid] = 0; S.kept_mask[tid] = 0; S.head_mask[tid] = 0; }
+  if (tid == 0) S.next_bucket = 0;
   __syncthreads();
   const int tile = S.tile_id;
   const int64_t r0 = (int64_t)tile * TB_ROWS;
@@ -171,17 +172,21 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
   __syncthreads();
 
   // ---- bucket ids (in place) and sortedness ------------------------------------------------------
+  // the per-row input checks of validate_candle_data (core.py:115-137) ride along here, row-parallel
   int64_t bid[TB_ROWS / TB_THREADS];
   uint32_t unsorted_rows = 0;
+  uint32_t rflags[TB_ROWS / TB_THREADS];
 #pragma unroll
   for (int k = 0; k < TB_ROWS / TB_THREADS; ++k) {
     int i = tid + k * TB_THREADS;
+    rflags[k] = 0;
     if (i < rows) {
       int64_t t = S.ts[i];
       bid[k] = bucket_of(t, P.fd);
       int64_t tp = (i > 0) ? S.ts[i - 1] : (r0 > 0 ? __ldg(P.ts + r0 - 1) : IVX_NAT);
       bool symstart = (S.symhead_mask[i >> 5] >> (i & 31)) & 1u;
       if (!symstart && t != IVX_NAT && tp != IVX_NAT && t < tp) unsorted_rows |= 1u << k;
+      if (P.sym_flags) rflags[k] = row_flags(S.col[0][i], S.col[1][i], S.col[2][i], S.col[3][i], S.col[4][i]);
     }
   }
   __syncthreads();
@@ -190,11 +195,12 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
     int i = tid + k * TB_THREADS;
     if (i < rows) S.ts[i] = bid[k];
   }
-  if (unsorted_rows && P.sym_flags) {
+  if (P.sym_flags) {
 #pragma unroll
-    for (int k = 0; k < TB_ROWS / TB_THREADS; ++k)
-      if (unsorted_rows & (1u << k))
-        atomicOr(P.sym_flags + symbol_of_row(P.in_off, P.n_sym, r0 + tid + k * TB_THREADS), IVX_FLAG_UNSORTED);
+    for (int k = 0; k < TB_ROWS / TB_THREADS; ++k) {
+      const uint32_t f = rflags[k] | ((unsorted_rows >> k) & 1u ? IVX_FLAG_UNSORTED : 0u);
+      if (f) atomicOr(P.sym_flags + symbol_of_row(P.in_off, P.n_sym, r0 + tid + k * TB_THREADS), f);
+    }
   }
   __syncthreads();
 
@@ -230,16 +236,23 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
     uint32_t m = S.head_mask[g];
     if ((m >> lane) & 1u) S.bstart[S.head_base[g] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(g * 32 + lane);
   }
-  if (tid == 0) {
-    S.bstart[n_heads] = (uint16_t)rows;
-    // rows of the last bucket that lie beyond this tile (ts only)
+  if (warp == 0) {
+    // rows of the last bucket that lie beyond this tile (ts only), 32 at a time
     int ext = 0;
     if (n_heads > 0) {
-      int64_t b = S.ts[rows - 1];
+      const int64_t b = S.ts[rows - 1];
       int64_t r = r0 + rows;
-      while (r < S.tile_sym_end && bucket_of(__ldg(P.ts + r), P.fd) == b) { ++ext; ++r; }
+      while (true) {
+        const int64_t rr = r + lane;
+        const bool same = rr < S.tile_sym_end && bucket_of(__ldg(P.ts + rr), P.fd) == b;
+        const uint32_t m = __ballot_sync(IVX_FULL_MASK, same);
+        const int run = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;     // leading rows still in the bucket
+        ext += run;
+        if (run < 32) break;
+        r += 32;
+      }
     }
-    S.last_count_ext = ext;
+    if (lane == 0) { S.bstart[n_heads] = (uint16_t)rows; S.last_count_ext = ext; }
   }
   __syncthreads();
 
@@ -302,8 +315,9 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
       if (tile == P.n_tiles - 1 && P.total) *P.total = (int64_t)ex_k + agg_kept;
     }
   } else {
-    // ---- warps 1..7: one thread per bucket, rows in order; the candle is parked in the tile at its first row -----
+    // ---- the other warps: one thread per bucket, rows in order; the candle is parked in the tile at its first row -----
     for (int j = tid - 32; j < n_heads; j += TB_THREADS - 32) {
+      {
       const int b0 = S.bstart[j], b1 = S.bstart[j + 1];
       const bool kept = (S.kept_mask[j >> 5] >> (j & 31)) & 1u;
       Candle cd;
@@ -321,6 +335,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
       S.col[0][b0] = cd.open; S.col[1][b0] = cd.high; S.col[2][b0] = cd.low; S.col[3][b0] = cd.close; S.col[4][b0] = cd.sum;
       S.symrow[b0] = cd.sym_row;
       if (flags && P.sym_flags) atomicOr(P.sym_flags + symbol_of_row(P.in_off, P.n_sym, r0 + b0), flags);
+      }
     }
   }
   __syncthreads();
