@@ -35,9 +35,14 @@ def _summary(batch_id: int, statuses: List[dict], t0: float) -> dict:
 class InterpolationBatch:
     """``BatchProcessor.process_symbol`` for every symbol of a batch (batch_processor.py:67-142)."""
 
-    def __init__(self, method: str = "linear", min_points: int = 10, sink: Optional[Sink] = None, batch_id: Optional[int] = None):
+    def __init__(self, method: str = "linear", min_points: int = 10, sink: Optional[Sink] = None, batch_id: Optional[int] = None,
+                 recompute_greeks: bool = False, reference_put_rho_sign: bool = True):
         self.interpolator = IVInterpolator(method=method, min_points=min_points)      # batch_processor.py:21-24
         self.sink = sink
+        # the reference promises Greeks on the interpolated rows (config.py:46 preserve_greeks, schema.py:36-40) but never
+        # wires greeks.py in; here they are one more launch over the batch's rows (SURVEY.md section 8 f-4)
+        self.recompute_greeks = recompute_greeks
+        self.reference_put_rho_sign = reference_put_rho_sign
         self.batch_id = int(time.time()) if batch_id is None else batch_id            # monitoring/progress.py:18-20
 
     def run(self, frames: Mapping[str, pd.DataFrame]) -> Tuple[Dict[str, pd.DataFrame], List[dict], dict]:
@@ -56,6 +61,11 @@ class InterpolationBatch:
             err = None
         except Exception as e:                                                        # :132-142
             results, err = [None] * len(todo), str(e)
+        if self.recompute_greeks and err is None:
+            try:
+                self._add_greeks([r for r in results if r is not None])
+            except Exception as e:
+                results, err = [None] * len(todo), str(e)
         elapsed = time.time() - t0
         for i, res in zip(todo, results):
             sym = symbols[i]
@@ -72,6 +82,30 @@ class InterpolationBatch:
                 else:
                     statuses[i] = {"symbol": sym, "status": "error", "error": "Failed to save to database"}
         return outs, statuses, _summary(self.batch_id, statuses, t0)
+
+
+    def _add_greeks(self, frames: List[pd.DataFrame]) -> None:
+        """delta, gamma, theta, vega, rho per interpolated row (reference src/interpolation/greeks.py:12-43) with
+        S = underlying_price, K = strike, T = time_to_maturity, r = interest_rate, sigma = iv, type from callput."""
+        import numpy as np
+        import torch
+
+        from . import device as D
+        frames = [f for f in frames if len(f) and all(c in f.columns for c in ("strike", "callput", "interest_rate"))]
+        if not frames:
+            return
+        dev = torch.device("cuda")
+        cat = lambda c: torch.from_numpy(np.concatenate([f[c].to_numpy(dtype=np.float64) for f in frames])).to(dev)
+        call = np.concatenate([(f["callput"].astype(str).str.lower().str[0] == "c").to_numpy() for f in frames]).astype(np.uint8)
+        g = D.bs_greeks(cat("underlying_price"), cat("strike"), cat("time_to_maturity"), cat("interest_rate"), cat("iv"),
+                        torch.from_numpy(call).to(dev), reference_put_rho_sign=self.reference_put_rho_sign)
+        host = {k: v.cpu().numpy() for k, v in g.items()}
+        a = 0
+        for f in frames:
+            b = a + len(f)
+            for k in ("delta", "gamma", "theta", "vega", "rho"):
+                f[k] = host[k][a:b]
+            a = b
 
 
 class CandleBatch:

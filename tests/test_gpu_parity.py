@@ -403,3 +403,23 @@ def test_batch_drivers_status_contract(dev, golden_interp, golden_candles):
             assert st["input_candles"] == len(f) and st["output_candles"] == len(outs[st["symbol"]])
             assert st["stats"]["original_candles"] == len(f)
     assert "success" in kinds and len(kinds) >= 2
+
+
+def test_batch_greeks_epilogue(dev, golden_interp):
+    """delta..rho on the interpolated rows (greeks.py:12-43 conventions; schema.py:36-40 columns), checked against
+    the numpy restatement of the reference's formulas on the same rows."""
+    from iv_interpolation_b200.batch import InterpolationBatch
+    tp = tapes.make_contract_tape(31, 6, rows_per_contract=25)
+    frames = {tp.symbols[i] + f"#{i}": tp.frame(i) for i in range(tp.n_sym)}
+    outs, statuses, _ = InterpolationBatch(recompute_greeks=True).run(frames)
+    assert all(s["status"] == "success" for s in statuses)
+    n_call = 0
+    for f in outs.values():
+        call = (f["callput"] == "c").to_numpy()
+        n_call += int(call.sum())
+        want = O.bs_greeks(f["underlying_price"].to_numpy(), f["strike"].to_numpy(), f["time_to_maturity"].to_numpy(),
+                           f["interest_rate"].to_numpy(), f["iv"].to_numpy(), call)
+        for k in ("delta", "gamma", "theta", "vega", "rho"):
+            got = f[k].to_numpy()
+            assert np.all(np.abs(got - want[k]) <= 1e-12 * np.maximum(1.0, np.abs(want[k]))), k
+    assert n_call > 0

@@ -167,3 +167,33 @@ def test_two_rank_shard_and_gather_over_gloo():
     shards = SH.lpt_partition([float(c) for c in costs], 2)
     want_units = [u for s in shards for u in s for _ in range(costs[u])]
     assert table["unit"] == want_units
+
+
+def test_columnar_round_trip_at_db_precision(tmp_path):
+    """Frames -> Arrow/Parquet with the reference's DECIMAL(p, s) columns -> per-symbol frames ordered by time."""
+    import pyarrow as pa
+    from iv_interpolation_b200 import columnar as CO
+    ts = pd.date_range("2023-03-15", periods=6, freq="1min")
+    f1 = pd.DataFrame({"date": ts, "symbol": "btc-17mar23-24500-c", "iv": [0.123456789012, 0.5, 0.25, 1.0, 0.3333333349, 0.75],
+                       "underlying_price": 25000.12345, "time_to_maturity": 0.0123456789, "strike": 24500.0, "callput": "c",
+                       "interest_rate": 0.05, "mark_price": 0.0312, "index_price": 25001.5, "volume": 1.123456789123,
+                       "quote_volume": 3.5, "record_time": "rt", "is_interpolated": False, "batch_id": 7})
+    f2 = f1.assign(symbol="btc-17mar23-25000-p", callput="p").iloc[::-1]
+    t = CO.interpolated_to_table({"a": f1, "b": f2, "none": None})
+    assert t.schema.field("iv").type == pa.decimal128(12, 8) and t.schema.field("underlying_price").type == pa.decimal128(15, 4)
+    assert t.schema.field("volume").type == pa.decimal128(20, 8) and t.num_rows == 12
+    assert t.column_names[:3] == ["symbol", "date", "record_time"]
+    path = str(tmp_path / "interp.parquet")
+    CO.write_parquet(t, path)
+    back = CO.read_symbol_frames(path, "date")
+    assert set(back) == {"btc-17mar23-24500-c", "btc-17mar23-25000-p"}
+    b1, b2 = back["btc-17mar23-24500-c"], back["btc-17mar23-25000-p"]
+    assert np.allclose(b1["iv"], np.round(f1["iv"], 8), atol=0, rtol=0) and b1["underlying_price"].iloc[0] == 25000.1234 + 0.0
+    assert list(b2["date"]) == list(ts)                                   # re-ordered by time
+    assert b1["volume"].iloc[0] == 1.12345679
+    c = pd.DataFrame({"symbol": "s", "timestamp": ts[:2], "open": [1.00004, 2.0], "high": [2.5, 3.0], "low": [0.5, 1.0],
+                      "close": [1.5, 2.5], "volume": [10.0, 0.123456785], "frequency": "5min", "source_candles": 5,
+                      "created_at": ts[:2]})
+    ct = CO.candles_to_table({"s": c})
+    assert ct.schema.field("open").type == pa.decimal128(15, 4) and ct.column_names == list(CO.CANDLE_ORDER[:9]) + ["created_at"]
+    assert float(ct.column("open")[0].as_py()) == 1.0
