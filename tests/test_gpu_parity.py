@@ -423,3 +423,78 @@ def test_batch_greeks_epilogue(dev, golden_interp):
             got = f[k].to_numpy()
             assert np.all(np.abs(got - want[k]) <= 1e-12 * np.maximum(1.0, np.abs(want[k]))), k
     assert n_call > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs 3 and 5 at test size
+# ---------------------------------------------------------------------------------------------
+def test_config3_sharded_by_underlying_equals_unsharded(dev):
+    """Contracts of several underlyings, dealt to 4 'ranks' by LPT over expected output rows (the reference's
+    row_count x interpolation_factor, optimized_batch_processor.py:129-133): each shard's A -> B result equals the
+    corresponding slice of the unsharded run, bit for bit — units are independent, no exchange is needed."""
+    from iv_interpolation_b200 import device as D, sharding as SH
+    parts = [tapes.make_contract_tape(40 + u, 9 + u, rows_per_contract=25 + 24 * u, underlying=f"und{u}") for u in range(4)]
+    off = np.r_[0, np.cumsum(np.concatenate([np.diff(p.off) for p in parts]))].astype(np.int64)
+    date = np.concatenate([p.date for p in parts])
+    cols = {c: np.concatenate([p.cols[c] for p in parts]) for c in tapes.INTERP_COLS + tapes.FILL_NUM_COLS}
+    n_sym = len(off) - 1
+    kw = dict(step=tapes.MINUTE_US, max_span=30 * tapes.DAY_US)
+
+    def run(idx):
+        lens = off[idx + 1] - off[idx]
+        o = np.r_[0, np.cumsum(lens)].astype(np.int64)
+        rows = np.concatenate([np.arange(off[i], off[i + 1]) for i in idx])
+        res = D.interp_linear_ffill(_t(o, dev), _t(date[rows], dev), [_t(cols[c][rows], dev) for c in tapes.INTERP_COLS],
+                                    [_t(cols[c][rows], dev) for c in tapes.FILL_NUM_COLS], [None], **kw)
+        S = res.interp[1]
+        cb = D.ohlcv_reduce(res.out_off, res.ts, S, S + 1.0, S - 1.0, S, res.fill[4], bucket_ticks=5 * tapes.MINUTE_US, min_count=5)
+        h = lambda t: t.cpu().numpy()
+        return h(res.out_off), h(res.interp[0]), h(cb.out_off), h(cb.ts), h(cb.close), h(cb.volume)
+
+    full = run(np.arange(n_sym))
+    costs = SH.contract_costs(off, date, tapes.MINUTE_US)
+    shards = SH.lpt_partition(costs, 4)
+    assert SH.imbalance(costs, shards) < 1.2 and sorted(i for s in shards for i in s) == list(range(n_sym))
+    for sh in shards:
+        idx = np.asarray(sh)
+        got = run(idx)
+        for k, i in enumerate(idx):
+            a, b = full[0][i], full[0][i + 1]
+            ga, gb = got[0][k], got[0][k + 1]
+            assert _eq(got[1][ga:gb], full[1][a:b])
+            ca, cb_ = full[2][i], full[2][i + 1]
+            gca, gcb = got[2][k], got[2][k + 1]
+            for j in (3, 4, 5):
+                assert _eq(got[j][gca:gcb], full[j][ca:cb_])
+
+
+def test_config5_long_replay_in_30_day_windows(dev):
+    """A contract quoted for 75 days with 30 % NaN IVs and 10 % absent rows: whole, the reference refuses it
+    (span > 30 days, core.py:36-39); cut into <= 30-day windows every window passes the guards and matches the oracle."""
+    from iv_interpolation_b200 import device as D
+    tp = tapes.make_contract_tape(55, 3, rows_per_contract=75 * 24 + 1, nan_frac=0.3, missing_frac=0.1, offgrid_frac=0.0)
+    icols = [tp.cols[c] for c in tapes.INTERP_COLS]
+    fcols = [tp.cols[c] for c in tapes.FILL_NUM_COLS]
+    kw = dict(step=tapes.MINUTE_US, max_span=30 * tapes.DAY_US)
+    whole = D.interp_linear_ffill(_t(tp.off, dev), _t(tp.date, dev), [_t(c, dev) for c in icols], [_t(c, dev) for c in fcols], [None], **kw)
+    assert whole.total == 0 and (whole.sym_status.cpu().numpy() == 2).all()          # IVX_SYM_SPAN
+    # windows of 30 days anchored at each contract's first stamp
+    w_off, rows = [0], []
+    for i in range(tp.n_sym):
+        a, b = int(tp.off[i]), int(tp.off[i + 1])
+        w = (tp.date[a:b] - tp.date[a]) // (30 * tapes.DAY_US)
+        for k in np.unique(w):
+            r = np.flatnonzero(w == k) + a
+            rows.append(r); w_off.append(w_off[-1] + len(r))
+    rows = np.concatenate(rows); w_off = np.asarray(w_off, np.int64)
+    res = D.interp_linear_ffill(_t(w_off, dev), _t(tp.date[rows], dev), [_t(c[rows], dev) for c in icols],
+                                [_t(c[rows], dev) for c in fcols], [None], **kw)
+    status = res.sym_status.cpu().numpy()
+    out_off = res.out_off.cpu().numpy()
+    iv = res.interp[0].cpu().numpy(); vol = res.fill[4].cpu().numpy()
+    assert len(status) == 9 and (status == 0).all()
+    for k in range(len(status)):
+        r = rows[w_off[k]:w_off[k + 1]]
+        w = O.interp_linear_ffill(tp.date[r], [c[r] for c in icols], [c[r] for c in fcols], [np.ones(len(r), bool)], **kw)
+        assert w["status"] == 0 and _eq(iv[out_off[k]:out_off[k + 1]], w["interp"][0]) and _eq(vol[out_off[k]:out_off[k + 1]], w["fill"][4])
+    assert res.total > 3 * 70 * 1440 * 0.9
