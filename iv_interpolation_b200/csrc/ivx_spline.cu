@@ -328,73 +328,13 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
 }
 
 // ---- many small systems, [knot][system] layout ----------------------------------------------------------
-// blockIdx.y = batch: batch b has its own abscissae x[b*x_batch_stride + i*x_knot_stride] and its own
-// [knot][system] / [query][system] planes of y / yq
-__global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, const double* __restrict__ x,
-                                                        int64_t x_batch_stride, int64_t x_knot_stride,
-                                                        const double* __restrict__ y, int n_q,
-                                                        const double* __restrict__ xq, int extrap,
-                                                        double* __restrict__ yq) {
-  __shared__ double s_x[STRIDED_MAXK], s_cp[STRIDED_MAXK], s_inv[STRIDED_MAXK];
-  __shared__ int s_x_ok;
-  x += (int64_t)blockIdx.y * x_batch_stride;
-  y += (int64_t)blockIdx.y * nk * n_sys;
-  yq += (int64_t)blockIdx.y * n_q * n_sys;
-  // LU factors of the shared abscissae (valid when a system has every knot)
-  if (threadIdx.x == 0) {
-    bool okx = true;
-    for (int i = 0; i < nk; ++i) { s_x[i] = x[i * x_knot_stride]; okx = okx && isfinite(s_x[i]); }
-    s_x_ok = okx;
-    double c_prev = 0.0;
-    for (int i = 1; i + 1 < nk; ++i) {
-      const double hm = s_x[i] - s_x[i - 1], hp = s_x[i + 1] - s_x[i];
-      const double inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
-      c_prev = hp * inv;
-      s_cp[i] = c_prev; s_inv[i] = inv;
-    }
-  }
-  __syncthreads();
-  const int64_t sys = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (sys >= n_sys) return;
-
-  double yk[STRIDED_MAXK];     // y, then compacted y
-  double Mk[STRIDED_MAXK];
-  bool all_ok = s_x_ok != 0;
-  for (int i = 0; i < nk; ++i) {
-    yk[i] = ld_stream(y + (int64_t)i * n_sys + sys);
-    all_ok = all_ok && isfinite(yk[i]);
-  }
-
-  if (all_ok && nk >= 3) {
-    // shared-LU path: only the right-hand side is per system
-    double d_prev = 0.0;
-    double sm = (yk[1] - yk[0]) / (s_x[1] - s_x[0]);
-    for (int i = 1; i + 1 < nk; ++i) {
-      const double hm = s_x[i] - s_x[i - 1];
-      const double sp = (yk[i + 1] - yk[i]) / (s_x[i + 1] - s_x[i]);
-      d_prev = (6.0 * (sp - sm) - hm * d_prev) * s_inv[i];
-      Mk[i] = d_prev;
-      sm = sp;
-    }
-    double M = 0.0;
-    Mk[nk - 1] = 0.0;
-    for (int i = nk - 2; i >= 1; --i) { M = Mk[i] - s_cp[i] * M; Mk[i] = M; }
-    Mk[0] = 0.0;
-    int j = 0;
-    for (int q = 0; q < n_q; ++q) {
-      const double xv = __ldg(xq + q);
-      while (j < nk - 2 && xv >= s_x[j + 1]) ++j;
-      const double v = spline_eval(s_x[j], s_x[j + 1], yk[j], yk[j + 1], Mk[j], Mk[j + 1], xv);
-      st_stream(yq + (int64_t)q * n_sys + sys, apply_extrap(v, xv, s_x[0], s_x[nk - 1], yk[0], yk[nk - 1], extrap));
-    }
-    return;
-  }
-
-  // generic path: drop unusable knots, private abscissae
-  double xk[STRIDED_MAXK], ck[STRIDED_MAXK];
+// generic path of the strided kernel: some knots of this system are unusable -> private abscissae (rare)
+__device__ __noinline__ void strided_generic(int64_t n_sys, int64_t sys, int nk, const double* s_x, const double* __restrict__ y,
+                                             int n_q, const double* __restrict__ xq, int extrap, double* __restrict__ yq) {
+  double xk[STRIDED_MAXK], yk[STRIDED_MAXK], ck[STRIDED_MAXK], Mk[STRIDED_MAXK];
   int n = 0;
   for (int i = 0; i < nk; ++i) {
-    const double xv = s_x[i], yv = yk[i];
+    const double xv = s_x[i], yv = __ldg(y + (int64_t)i * n_sys + sys);
     if (isfinite(xv) && isfinite(yv)) { xk[n] = xv; yk[n] = yv; ++n; }
   }
   if (n < 2) {
@@ -423,6 +363,102 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
     while (j < n - 2 && xv >= xk[j + 1]) ++j;
     const double v = spline_eval(xk[j], xk[j + 1], yk[j], yk[j + 1], Mk[j], Mk[j + 1], xv);
     st_stream(yq + (int64_t)q * n_sys + sys, apply_extrap(v, xv, xk[0], xk[n - 1], yk[0], yk[n - 1], extrap));
+  }
+}
+
+// blockIdx.y = batch: batch b has its own abscissae x[b*x_batch_stride + i*x_knot_stride] and its own
+// [knot][system] / [query][system] planes of y / yq.
+// Fast path (every knot usable): the LU factors depend only on the shared abscissae and are formed once per CTA;
+// a thread streams its system's y forward (coalesced loads), parks Thomas' d' in shared memory [knot][thread]
+// (conflict-free), and evaluates the grid points of each segment on the way back down — no per-thread arrays,
+// no division.  A non-finite y sends the thread to the generic path.
+__global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, const double* __restrict__ x,
+                                                        int64_t x_batch_stride, int64_t x_knot_stride,
+                                                        const double* __restrict__ y, int n_q,
+                                                        const double* __restrict__ xq, int extrap,
+                                                        double* __restrict__ yq) {
+  __shared__ double s_x[STRIDED_MAXK], s_cp[STRIDED_MAXK], s_inv[STRIDED_MAXK], s_ih[STRIDED_MAXK];
+  __shared__ int s_x_ok;
+  extern __shared__ __align__(16) double s_d[];          // [nk][128]
+  x += (int64_t)blockIdx.y * x_batch_stride;
+  y += (int64_t)blockIdx.y * nk * n_sys;
+  yq += (int64_t)blockIdx.y * n_q * n_sys;
+  if (threadIdx.x == 0) {
+    bool okx = true;
+    for (int i = 0; i < nk; ++i) { s_x[i] = x[i * x_knot_stride]; okx = okx && isfinite(s_x[i]); }
+    s_x_ok = okx;
+    double c_prev = 0.0;
+    for (int i = 0; i + 1 < nk; ++i) s_ih[i] = 1.0 / (s_x[i + 1] - s_x[i]);
+    for (int i = 1; i + 1 < nk; ++i) {
+      const double hm = s_x[i] - s_x[i - 1], hp = s_x[i + 1] - s_x[i];
+      const double inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
+      c_prev = hp * inv;
+      s_cp[i] = c_prev; s_inv[i] = inv;
+    }
+  }
+  __syncthreads();
+  const int64_t sys = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (sys >= n_sys) return;
+  if (!s_x_ok || nk < 3) { strided_generic(n_sys, sys, nk, s_x, y, n_q, xq, extrap, yq); return; }
+
+  double* sd = s_d + threadIdx.x;                         // sd[i * 128]
+  constexpr int PF = 8;                                   // loads in flight per thread: y is fetched 8 knots ahead
+  // ---- forward: d'[i] = (6 (slope[i] - slope[i-1]) - h[i-1] d'[i-1]) / den[i], y streamed ------------------------
+  const double* yp = y + sys;
+  double y_prev = __ldg(yp), y_cur = __ldg(yp + n_sys);
+  const double y_first = y_prev;
+  bool ok = isfinite(y_prev) && isfinite(y_cur);
+  double sm = (y_cur - y_prev) * s_ih[0], d_prev = 0.0;
+  for (int ib = 1; ib + 1 < nk; ib += PF) {
+    double yb[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) yb[u] = (ib + u + 1 < nk) ? __ldg(yp + (int64_t)(ib + u + 1) * n_sys) : 0.0;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int i = ib + u;
+      if (i + 1 < nk) {
+        const double y_next = yb[u];
+        ok = ok && isfinite(y_next);
+        const double sp = (y_next - y_cur) * s_ih[i];
+        d_prev = (6.0 * (sp - sm) - (s_x[i] - s_x[i - 1]) * d_prev) * s_inv[i];
+        sd[i * 128] = d_prev;
+        sm = sp; y_cur = y_next;
+      }
+    }
+  }
+  if (!ok) { strided_generic(n_sys, sys, nk, s_x, y, n_q, xq, extrap, yq); return; }
+  const double y_last = y_cur;
+  // ---- backward: M[i] = d'[i] - c'[i] M[i+1]; the grid points of segment [x[i], x[i+1]) are evaluated as soon as its
+  //      two moments are known (descending); segment 0 also takes the points below x[0], segment nk-2 those above ------
+  const double xlo = s_x[0], xhi = s_x[nk - 1];
+  int q = n_q - 1;
+  double* outp = yq + (int64_t)q * n_sys + sys;
+  double M_hi = 0.0, y_hi = y_last;
+  for (int ib = nk - 2; ib >= 0; ib -= PF) {
+    double yb[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) yb[u] = (ib - u >= 0) ? __ldg(yp + (int64_t)(ib - u) * n_sys) : 0.0;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int i = ib - u;
+      if (i >= 0) {
+        const double M_lo = i >= 1 ? sd[i * 128] - s_cp[i] * M_hi : 0.0;
+        const double y_lo = yb[u];
+        // the segment's cubic about its left knot: y = a0 + B (a1 + B (a2 + B a3)),  B = x - x[i]
+        const double xl = s_x[i], h = s_x[i + 1] - xl, ih = s_ih[i];
+        const double a1 = (y_hi - y_lo) * ih - h * (2.0 * M_lo + M_hi) * (1.0 / 6.0);
+        const double a2 = 0.5 * M_lo, a3 = (M_hi - M_lo) * ih * (1.0 / 6.0);
+        while (q >= 0) {
+          const double xv = __ldg(xq + q);
+          if (!(i == 0 || xv >= xl || isnan(xv))) break;
+          const double B = xv - xl;
+          const double v = fma(B, fma(B, fma(B, a3, a2), a1), y_lo);
+          st_stream(outp, apply_extrap(v, xv, xlo, xhi, y_first, y_last, extrap));
+          --q; outp -= n_sys;
+        }
+        M_hi = M_lo; y_hi = y_lo;
+      }
+    }
   }
 }
 
@@ -477,6 +513,13 @@ extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, in
   return ivx_spline_fit_eval_xoff(n_slices, knot_off, nullptr, max_knots, x, y, n_q, xq, extrap, yq, stream_);
 }
 
+static cudaError_t strided_smem_attr() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  done = true;
+  return cudaFuncSetAttribute(k_spline_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIDED_MAXK * 128 * (int)sizeof(double));
+}
+
 extern "C" int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x, const double* y, int32_t n_q,
                                   const double* xq, int32_t extrap, double* yq, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -485,7 +528,8 @@ extern "C" int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const doub
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_strided: extrap must be 0, 1 or 2");
   if (n_systems == 0 || n_q == 0) return IVX_OK;
   IVX_REQUIRE(x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_strided: null pointer");
-  k_spline_strided<<<(unsigned)((n_systems + 127) / 128), 128, 0, stream>>>(n_systems, n_knots, x, 0, 1, y, n_q, xq, extrap, yq);
+  IVX_CUDA(strided_smem_attr());
+  k_spline_strided<<<(unsigned)((n_systems + 127) / 128), 128, (size_t)n_knots * 128 * sizeof(double), stream>>>(n_systems, n_knots, x, 0, 1, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_strided");
   return IVX_OK;
 }
@@ -500,11 +544,12 @@ extern "C" int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, 
   IVX_REQUIRE(x_batch_stride >= 0 && x_knot_stride >= 1, IVX_ERR_INVALID_ARG, "ivx_spline_strided_batched: bad abscissa strides");
   if (n_batches == 0 || n_systems == 0 || n_q == 0) return IVX_OK;
   IVX_REQUIRE(x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_strided_batched: null pointer");
+  IVX_CUDA(strided_smem_attr());
   const int64_t gx = (n_systems + 127) / 128;
   for (int64_t b0 = 0; b0 < n_batches; b0 += 65535) {   // gridDim.y limit
     const int64_t nb = n_batches - b0 < 65535 ? n_batches - b0 : 65535;
     dim3 grid((unsigned)gx, (unsigned)nb);
-    k_spline_strided<<<grid, 128, 0, stream>>>(n_systems, n_knots, x + b0 * x_batch_stride, x_batch_stride, x_knot_stride,
+    k_spline_strided<<<grid, 128, (size_t)n_knots * 128 * sizeof(double), stream>>>(n_systems, n_knots, x + b0 * x_batch_stride, x_batch_stride, x_knot_stride,
                                                y + b0 * n_knots * n_systems, n_q, xq, extrap, yq + b0 * n_q * n_systems);
     IVX_LAUNCH_CHECK("k_spline_strided(batched)");
   }
