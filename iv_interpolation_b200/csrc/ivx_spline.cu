@@ -32,6 +32,7 @@ namespace {
 
 constexpr int SPL_RMAX = 8;       // rows per thread
 constexpr int STRIDED_MAXK = 64;
+constexpr int STRIDED_SPT = 4;      // systems per thread in the strided kernel
 
 __device__ __forceinline__ double spline_eval(double xl, double xr, double yl, double yr, double Ml, double Mr, double xq) {
   const double h = xr - xl;
@@ -383,12 +384,14 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
   x += (int64_t)blockIdx.y * x_batch_stride;
   y += (int64_t)blockIdx.y * nk * n_sys;
   yq += (int64_t)blockIdx.y * n_q * n_sys;
+  if (threadIdx.x < STRIDED_MAXK && threadIdx.x < nk) s_x[threadIdx.x] = x[threadIdx.x * x_knot_stride];
+  __syncthreads();
+  if (threadIdx.x + 1 < nk && threadIdx.x < STRIDED_MAXK) s_ih[threadIdx.x] = 1.0 / (s_x[threadIdx.x + 1] - s_x[threadIdx.x]);
   if (threadIdx.x == 0) {
     bool okx = true;
-    for (int i = 0; i < nk; ++i) { s_x[i] = x[i * x_knot_stride]; okx = okx && isfinite(s_x[i]); }
+    for (int i = 0; i < nk; ++i) okx = okx && isfinite(s_x[i]);
     s_x_ok = okx;
     double c_prev = 0.0;
-    for (int i = 0; i + 1 < nk; ++i) s_ih[i] = 1.0 / (s_x[i + 1] - s_x[i]);
     for (int i = 1; i + 1 < nk; ++i) {
       const double hm = s_x[i] - s_x[i - 1], hp = s_x[i + 1] - s_x[i];
       const double inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
@@ -397,12 +400,14 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
     }
   }
   __syncthreads();
-  const int64_t sys = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (sys >= n_sys) return;
-  if (!s_x_ok || nk < 3) { strided_generic(n_sys, sys, nk, s_x, y, n_q, xq, extrap, yq); return; }
-
   double* sd = s_d + threadIdx.x;                         // sd[i * 128]
   constexpr int PF = 8;                                   // loads in flight per thread: y is fetched 8 knots ahead
+  // STRIDED_SPT systems per thread, one after the other: the CTA's factorisation is shared by 128 * STRIDED_SPT systems
+  for (int rep = 0; rep < STRIDED_SPT; ++rep) {
+  const int64_t sys = ((int64_t)blockIdx.x * STRIDED_SPT + rep) * blockDim.x + threadIdx.x;
+  if (sys >= n_sys) return;
+  if (!s_x_ok || nk < 3) { strided_generic(n_sys, sys, nk, s_x, y, n_q, xq, extrap, yq); continue; }
+
   // ---- forward: d'[i] = (6 (slope[i] - slope[i-1]) - h[i-1] d'[i-1]) / den[i], y streamed ------------------------
   const double* yp = y + sys;
   double y_prev = __ldg(yp), y_cur = __ldg(yp + n_sys);
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
       }
     }
   }
-  if (!ok) { strided_generic(n_sys, sys, nk, s_x, y, n_q, xq, extrap, yq); return; }
+  if (!ok) { strided_generic(n_sys, sys, nk, s_x, y, n_q, xq, extrap, yq); continue; }
   const double y_last = y_cur;
   // ---- backward: M[i] = d'[i] - c'[i] M[i+1]; the grid points of segment [x[i], x[i+1]) are evaluated as soon as its
   //      two moments are known (descending); segment 0 also takes the points below x[0], segment nk-2 those above ------
@@ -460,6 +465,7 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
       }
     }
   }
+  }  // rep
 }
 
 }  // namespace
@@ -529,7 +535,7 @@ extern "C" int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const doub
   if (n_systems == 0 || n_q == 0) return IVX_OK;
   IVX_REQUIRE(x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_strided: null pointer");
   IVX_CUDA(strided_smem_attr());
-  k_spline_strided<<<(unsigned)((n_systems + 127) / 128), 128, (size_t)n_knots * 128 * sizeof(double), stream>>>(n_systems, n_knots, x, 0, 1, y, n_q, xq, extrap, yq);
+  k_spline_strided<<<(unsigned)((n_systems + 128 * STRIDED_SPT - 1) / (128 * STRIDED_SPT)), 128, (size_t)n_knots * 128 * sizeof(double), stream>>>(n_systems, n_knots, x, 0, 1, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_strided");
   return IVX_OK;
 }
@@ -545,7 +551,7 @@ extern "C" int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, 
   if (n_batches == 0 || n_systems == 0 || n_q == 0) return IVX_OK;
   IVX_REQUIRE(x && y && xq && yq, IVX_ERR_INVALID_ARG, "ivx_spline_strided_batched: null pointer");
   IVX_CUDA(strided_smem_attr());
-  const int64_t gx = (n_systems + 127) / 128;
+  const int64_t gx = (n_systems + 128 * STRIDED_SPT - 1) / (128 * STRIDED_SPT);
   for (int64_t b0 = 0; b0 < n_batches; b0 += 65535) {   // gridDim.y limit
     const int64_t nb = n_batches - b0 < 65535 ? n_batches - b0 : 65535;
     dim3 grid((unsigned)gx, (unsigned)nb);
