@@ -277,6 +277,19 @@ def run_gpu(args):
                 "traffic": None, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes per launch / CUDA-event duration of that launch inside the timed steps"}
 
+    # DRAM traffic of the dominant kernel, from the committed ncu capture (per unit, scaled to this launch)
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as f:
+            tr = json.load(f).get(roofline["kernel"])
+        if tr:
+            n_units = {"quote": n_quotes, "knot": n_quotes, "grid point": n_t * N_GRID_M * N_GRID_K, "surface row": n_t * N_GRID_M * N_GRID_K}[tr["unit"]]
+            roofline["traffic"] = tr["bytes_per_unit"] * n_units
+            roofline["traffic_source"] = f"profiles/ncu_traffic_r1.json: {tr['bytes_per_unit']} DRAM B per {tr['unit']} (ncu --set full) x {n_units}"
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline["limiter"] = ("instruction issue (ncu: issue slots 87 % busy, fp64 pipe 43 %, DRAM 17 %): the solver is transcendental-heavy "
+                           "fp64, ~1050 instructions per quote") if dom == "implied_vol" else None
+
     # ---- fp64 FMA peak, measured in the same run (kernel C is fp64-pipe bound) -------------
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
     n_thr, iters = 148 * 2048, 4096
