@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_emit = None
 METRIC = "iv_solves_per_sec_full_path"
 UNIT = "quotes/s"
 N_EXP, N_STRIKE, N_T_DAY = 30, 2000, 23_400
@@ -116,7 +117,7 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _workload_name(n_t):
@@ -338,7 +339,7 @@ def run_gpu(args):
                 "candles_per_step": world * n_buckets * N_GRID_M * N_GRID_K,
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
                 "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -377,7 +378,7 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
     counts = [nb_chunk] * n_chunks                 # 1-s stamps starting on a minute: the host knows its bucket layout
     for _ in range(min(2, args.warmup)):
         stream.run(chunks[: min(8, n_chunks)], out, out_ts, out_cnt, bucket_counts=counts)
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 3)) if layout == "chain" else 1      # the per-quote layout is the secondary figure
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -467,6 +468,18 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: fewer than 3 warm-up steps breaks the timing rules; continuing as asked", file=sys.stderr)
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+
+    def _emit(line: dict) -> None:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
         run_reference(args)
     else:
