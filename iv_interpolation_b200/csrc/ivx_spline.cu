@@ -118,10 +118,17 @@ struct SplLayout {
   static constexpr size_t SMEM = (size_t)SPB * PER_SLICE * sizeof(double);
 };
 
-template <int G, int SPL_R>
+// LADDER: the slices' abscissae come from shared ladders whose Thomas factors c'[i], 1/den[i], 1/h[i] were formed once
+// (k_spline_ladder_factor) and sit in lu_cp/lu_inv/lu_ih, parallel to x.  A slice with every knot usable then only
+// has its right-hand side to eliminate: d'[i] = (r[i] - h[i-1] d'[i-1]) / den[i] is an affine map per row — a prefix scan
+// of 2-vectors, no matrices, no division.  Slices with missing knots take the general path below.
+template <int G, int SPL_R, bool LADDER>
 __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
                                                                        const int64_t* __restrict__ x_off,
-                                                                       const double* __restrict__ x, const double* __restrict__ y,
+                                                                       const double* __restrict__ x,
+                                                                       const double* __restrict__ lu_cp, const double* __restrict__ lu_inv,
+                                                                       const double* __restrict__ lu_ih,
+                                                                       const double* __restrict__ y,
                                                                        int n_q, const double* __restrict__ xq, int extrap,
                                                                        double* __restrict__ yq) {
   using L = SplLayout<G, SPL_R>;
@@ -203,6 +210,63 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
     return;
   }
 
+  double cv[SPL_R], dv[SPL_R];
+  // row i0+j is an equation of the system iff 1 <= i0+j <= n-2
+  auto interior = [&](int j) { const int i = i0 + j; return i >= 1 && i <= n - 2; };
+  if (LADDER && n == m) {
+    // ---- shared-ladder path: slopes through the tabulated 1/h, right-hand side as affine maps of d' ------------------
+    const double* __restrict__ cp_t = lu_cp + xk0;
+    const double* __restrict__ inv_t = lu_inv + xk0;
+    const double* __restrict__ ih_t = lu_ih + xk0;
+    const double xp = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yp = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
+    const double yn = ys[spl_pad(i0 + SPL_R)];
+    double sl[SPL_R + 1];                 // sl[k] = slope of segment i0+k-1
+#pragma unroll
+    for (int k = 0; k <= SPL_R; ++k) {
+      const int seg = i0 + k - 1;
+      const double ihv = (seg >= 0 && seg <= n - 2) ? __ldg(ih_t + seg) : 0.0;
+      const double yl = k == 0 ? yp : yv[k - 1 < SPL_R ? (k - 1 < 0 ? 0 : k - 1) : 0];
+      const double yr = k == SPL_R ? yn : yv[k < SPL_R ? k : 0];
+      sl[k] = (yr - yl) * ihv;
+    }
+    double al[SPL_R], bt[SPL_R];
+    double A = 0.0, B = 1.0;              // d'[last row of the chunk] = A + B d'[last row of the previous chunk]
+#pragma unroll
+    for (int j = 0; j < SPL_R; ++j) {
+      al[j] = 0.0; bt[j] = 0.0;
+      if (interior(j)) {
+        const double inv = __ldg(inv_t + i0 + j);
+        const double hm = xv[j] - (j == 0 ? xp : xv[j > 0 ? j - 1 : 0]);
+        al[j] = 6.0 * (sl[j + 1] - sl[j]) * inv;
+        bt[j] = -hm * inv;
+        A = fma(bt[j], A, al[j]); B *= bt[j];
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double A2 = __shfl_up_sync(IVX_FULL_MASK, A, d), B2 = __shfl_up_sync(IVX_FULL_MASK, B, d);
+      if (lane >= d) { A = fma(B, A2, A); B *= B2; }
+    }
+    double XA = __shfl_up_sync(IVX_FULL_MASK, A, 1), XB = __shfl_up_sync(IVX_FULL_MASK, B, 1);
+    if (lane == 0) { XA = 0.0; XB = 1.0; }
+    double d = 0.0;                       // d' before row 1
+    if (L::NW > 1) {
+      if (lane == 31) { wa[w * 2] = A; wa[w * 2 + 1] = B; }
+      group_sync<G>(grp);
+      for (int ww = 0; ww < w; ++ww) d = fma(wa[ww * 2 + 1], d, wa[ww * 2]);
+      group_sync<G>(grp);                 // wa is reused by the backward scan
+    }
+    d = fma(XB, d, XA);
+#pragma unroll
+    for (int j = 0; j < SPL_R; ++j) {
+      cv[j] = 0.0; dv[j] = 0.0;
+      if (interior(j)) {
+        d = fma(bt[j], d, al[j]);
+        dv[j] = d;
+        cv[j] = __ldg(cp_t + i0 + j);
+      }
+    }
+  } else {
   // ---- row coefficients.  Row i (1 <= i <= n-2) is multiplied by h[i-1] h[i], which clears both slope
   //      divisions:  a = hm^2 hp,  b = 2 (hm+hp) hm hp,  c = hm hp^2,  r = 6 (dy[i] hm - dy[i-1] hp);
   //      the q recurrence needs a[i] c[i-1] = h[i-2] hm^4 hp.  hh[k] = x[i0+k-1] - x[i0+k-2], k = 0..9 ---------
@@ -217,8 +281,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
     for (int k = 1; k < SPL_R; ++k) { hh[k + 1] = xv[k] - xv[k - 1]; dy[k] = yv[k] - yv[k - 1]; }
     hh[SPL_R + 1] = xn - xv[SPL_R - 1]; dy[SPL_R] = yn - yv[SPL_R - 1];
   }
-  // row i0+j is an equation of the system iff 1 <= i0+j <= n-2; its hm = hh[j+1], hp = hh[j+2], h[i-2] = hh[j]
-  auto interior = [&](int j) { const int i = i0 + j; return i >= 1 && i <= n - 2; };
+  // row i0+j: hm = hh[j+1], hp = hh[j+2], h[i-2] = hh[j]
 
   // ---- forward: chunk transition matrix, prefix over the group ----------------------------------------------
   Mat3 P = mat_identity();
@@ -262,7 +325,6 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
     q = nq * sc; qp = nqp * sc; D = nD * sc;
   }
   // ---- re-walk the rows from the exact incoming state: Thomas' c', d' ---------------------------------------
-  double cv[SPL_R], dv[SPL_R];
 #pragma unroll
   for (int j = 0; j < SPL_R; ++j) {
     cv[j] = 0.0; dv[j] = 0.0;
@@ -276,6 +338,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
       dv[j] = Dn * inv;
       qp = q; q = qn; D = Dn;
     }
+  }
   }
   // ---- backward: M[i] = d'[i] - c'[i] M[i+1] as affine maps, suffix scan ---------------------------------------
   double al = 0.0, be = 1.0;             // M[first row of the chunk] = al + be * M[first row of the next chunk]
@@ -475,26 +538,47 @@ using namespace ivx;
 
 extern "C" int64_t ivx_spline_workspace_bytes(int64_t, int64_t) { return 256; }
 
-template <int G, int SPL_R>
-static int launch_spline(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const double* x, const double* y, int n_q,
+template <int G, int SPL_R, bool LADDER>
+static int launch_spline_t(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const double* x, const double* lu_cp,
+                           const double* lu_inv, const double* lu_ih, const double* y, int n_q,
                          const double* xq, int extrap, double* yq, cudaStream_t stream) {
   using L = SplLayout<G, SPL_R>;
   static bool attr_set = false;
   if (!attr_set) {
-    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R, LADDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     attr_set = true;
   }
   const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
   IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
-  k_spline_fit_eval<G, SPL_R><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, y, n_q, xq, extrap, yq);
+  k_spline_fit_eval<G, SPL_R, LADDER><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_fit_eval");
   return IVX_OK;
 }
 
-extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
-                                        const double* x, const double* y, int64_t n_q, const double* xq, int32_t extrap,
-                                        double* yq, ivx_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// one thread per ladder: the x-only half of Thomas' elimination, once for every slice that uses the ladder
+__global__ void k_spline_ladder_factor(int64_t n_ladders, const int64_t* __restrict__ ladder_off, const double* __restrict__ x,
+                                       double* __restrict__ lu_cp, double* __restrict__ lu_inv, double* __restrict__ lu_ih) {
+  const int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (l >= n_ladders) return;
+  const int64_t a = ladder_off[l], n = ladder_off[l + 1] - a;
+  double c_prev = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double hp = i + 1 < n ? x[a + i + 1] - x[a + i] : qnan();
+    lu_ih[a + i] = 1.0 / hp;
+    double cp = 0.0, inv = 0.0;
+    if (i >= 1 && i + 1 < n) {
+      const double hm = x[a + i] - x[a + i - 1];
+      inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
+      cp = hp * inv;
+      c_prev = cp;
+    }
+    lu_cp[a + i] = cp; lu_inv[a + i] = inv;
+  }
+}
+
+static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots, const double* x,
+                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
+                           const double* xq, int32_t extrap, double* yq, cudaStream_t stream) {
   IVX_REQUIRE(n_slices >= 0 && max_knots >= 0 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: extrap must be 0, 1 or 2");
   if (n_slices == 0 || n_q == 0) return IVX_OK;
@@ -502,7 +586,10 @@ extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_of
   IVX_REQUIRE(max_knots <= 1024 * SPL_RMAX, IVX_ERR_UNSUPPORTED, "ivx_spline_fit_eval: at most %d knots per slice (got max_knots %lld)", 1024 * SPL_RMAX, (long long)max_knots);
   // slices longer than the capacity the launch is sized for come back as NaN rows
   const int nq = (int)n_q;
-#define IVX_SPL(G, R) return launch_spline<G, R>(n_slices, knot_off, x_off, x, y, nq, xq, extrap, yq, stream)
+  const bool ladder = lu_cp != nullptr;
+#define IVX_SPL(G, R)                                                                                                          \
+  return ladder ? launch_spline_t<G, R, true>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, y, nq, xq, extrap, yq, stream) \
+                : launch_spline_t<G, R, false>(n_slices, knot_off, x_off, x, nullptr, nullptr, nullptr, y, nq, xq, extrap, yq, stream)
   if (max_knots <= 32 * 8) IVX_SPL(32, 8);
   if (max_knots <= 64 * 8) IVX_SPL(64, 8);
   if (max_knots <= 128 * 8) IVX_SPL(128, 8);
@@ -510,6 +597,30 @@ extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_of
   if (max_knots <= 512 * 8) IVX_SPL(512, 8);
   IVX_SPL(1024, 8);
 #undef IVX_SPL
+}
+
+extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
+                                        const double* x, const double* y, int64_t n_q, const double* xq, int32_t extrap,
+                                        double* yq, ivx_stream_t stream_) {
+  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, nullptr, nullptr, nullptr, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
+}
+
+extern "C" int ivx_spline_ladder_factor(int64_t n_ladders, const int64_t* ladder_off, const double* x, double* lu_cp,
+                                        double* lu_inv, double* lu_ih, ivx_stream_t stream_) {
+  IVX_REQUIRE(n_ladders >= 0, IVX_ERR_INVALID_ARG, "ivx_spline_ladder_factor: negative count");
+  if (n_ladders == 0) return IVX_OK;
+  IVX_REQUIRE(ladder_off && x && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG, "ivx_spline_ladder_factor: null pointer");
+  k_spline_ladder_factor<<<(unsigned)((n_ladders + 31) / 32), 32, 0, (cudaStream_t)stream_>>>(n_ladders, ladder_off, x, lu_cp, lu_inv, lu_ih);
+  IVX_LAUNCH_CHECK("k_spline_ladder_factor");
+  return IVX_OK;
+}
+
+extern "C" int ivx_spline_fit_eval_ladder(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
+                                          const double* x, const double* lu_cp, const double* lu_inv, const double* lu_ih,
+                                          const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq,
+                                          ivx_stream_t stream_) {
+  IVX_REQUIRE(x_off && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_ladder: x_off and the three factor arrays are required");
+  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, lu_cp, lu_inv, lu_ih, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
 }
 
 extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots, const double* x,

@@ -21,7 +21,7 @@ _LAUNCHES = 0     # kernels of ours enqueued since the last reset (bench.py repo
 _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
-    "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2,
+    "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2, "spline_ladder_factor": 1,
 }
 
 
@@ -377,7 +377,11 @@ def bs_greeks(S, K, T, r, sigma, is_call, reference_put_rho_sign: bool = True) -
 # ------------------------------------------------------------------------------------------------
 def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, *,
                     max_knots: int, extrap: int = 1, out: Optional[torch.Tensor] = None,
-                    workspace: Optional[torch.Tensor] = None, x_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    workspace: Optional[torch.Tensor] = None, x_off: Optional[torch.Tensor] = None,
+                    lu: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    """Natural cubic spline per slice, evaluated on the shared grid ``xq``.  ``x_off`` (one int64 per slice) reads the
+    abscissae from shared ladders; ``lu`` = the three factor arrays of ``spline_ladder_factor`` additionally lets
+    slices without missing knots skip the x-only half of the elimination."""
     n_slices = knot_off.numel() - 1
     n_q = xq.numel()
     _req(knot_off, torch.int64, "knot_off")
@@ -393,10 +397,28 @@ def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq
         _req(x_off, torch.int64, "x_off")
         if x_off.numel() < n_slices:
             raise _lib.IvxError("spline_fit_eval: x_off must have one entry per slice")
-    check(lib().ivx_spline_fit_eval_xoff(n_slices, _ptr(knot_off), _ptr(x_off), int(max_knots), _ptr(x), _ptr(y), n_q,
-                                         _ptr(xq), int(extrap), _ptr(yq), _stream()), "ivx_spline_fit_eval_xoff")
+    if lu is not None:
+        if x_off is None or len(lu) != 3 or any(t.numel() != x.numel() or t.dtype != torch.float64 for t in lu):
+            raise _lib.IvxError("spline_fit_eval: lu needs x_off and three float64 arrays parallel to x")
+        check(lib().ivx_spline_fit_eval_ladder(n_slices, _ptr(knot_off), _ptr(x_off), int(max_knots), _ptr(x), _ptr(lu[0]),
+                                               _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q, _ptr(xq), int(extrap), _ptr(yq),
+                                               _stream()), "ivx_spline_fit_eval_ladder")
+    else:
+        check(lib().ivx_spline_fit_eval_xoff(n_slices, _ptr(knot_off), _ptr(x_off), int(max_knots), _ptr(x), _ptr(y), n_q,
+                                             _ptr(xq), int(extrap), _ptr(yq), _stream()), "ivx_spline_fit_eval_xoff")
     _count("spline_fit_eval")
     return yq
+
+
+def spline_ladder_factor(ladder_off: torch.Tensor, x: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
+    """Thomas factors (c', 1/den, 1/h) of the natural-spline systems of the ladders x[ladder_off[l]:ladder_off[l+1]],
+    three arrays parallel to ``x`` (one tiny launch; reusable by every slice on those ladders)."""
+    _req(ladder_off, torch.int64, "ladder_off"); _req(x, torch.float64, "x")
+    lu = out if out is not None else [_empty(x.numel(), torch.float64, x) for _ in range(3)]
+    check(lib().ivx_spline_ladder_factor(ladder_off.numel() - 1, _ptr(ladder_off), _ptr(x), _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]),
+                                         _stream()), "ivx_spline_ladder_factor")
+    _count("spline_ladder_factor")
+    return lu
 
 
 def spline_strided(x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, n_systems: int, *, extrap: int = 1,

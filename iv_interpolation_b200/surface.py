@@ -165,6 +165,8 @@ class SurfacePipeline:
                 self._chain_ws = torch.empty(lib().ivx_bs_chain_workspace_bytes(sp.n_t, sp.n_exp, sp.n_strike), dtype=torch.uint8,
                                              device=self.device)
                 self._x_off = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp) * sp.n_strike
+                self._ladder_off = torch.arange(sp.n_exp + 1, dtype=torch.int64, device=self.device) * sp.n_strike
+                self._lu = [torch.empty(sp.n_exp * sp.n_strike, dtype=torch.float64, device=self.device) for _ in range(3)]
             D.bs_implied_vol_chain(q.price, q.is_call, q.S_t, q.K_ek, q.T_te, q.r_t, n_t=sp.n_t, n_exp=sp.n_exp,
                                    n_strike=sp.n_strike, out=self.iv, workspace=self._chain_ws)
         else:
@@ -173,8 +175,10 @@ class SurfacePipeline:
         mark("spline_strike", 0)
         # knots of slice (t, e): x = the quoted strikes, read in place from the K column / the expiry's ladder
         if structured:
+            # the x-only half of the elimination once per expiry ladder (one 30-thread launch), then right-hand sides only
+            D.spline_ladder_factor(self._ladder_off, q.K_ek, out=self._lu)
             D.spline_fit_eval(self.knot_off, q.K_ek, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
-                              out=self.smile, x_off=self._x_off)
+                              out=self.smile, x_off=self._x_off, lu=self._lu)
         else:
             D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile)
         mark("spline_strike", 1)

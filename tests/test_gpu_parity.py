@@ -498,3 +498,36 @@ def test_config5_long_replay_in_30_day_windows(dev):
         w = O.interp_linear_ffill(tp.date[r], [c[r] for c in icols], [c[r] for c in fcols], [np.ones(len(r), bool)], **kw)
         assert w["status"] == 0 and _eq(iv[out_off[k]:out_off[k + 1]], w["interp"][0]) and _eq(vol[out_off[k]:out_off[k + 1]], w["fill"][4])
     assert res.total > 3 * 70 * 1440 * 0.9
+
+
+@pytest.mark.parametrize("n_knots,n_ladders,per_ladder", [(2000, 3, 7), (37, 5, 20), (300, 2, 9), (1025, 2, 4)])
+def test_spline_shared_ladder_path(dev, n_knots, n_ladders, per_ladder):
+    """Slices that share strike ladders: with the ladders' factors tabulated once, complete slices take the affine-scan
+    path, slices with missing knots (and prefixes of a ladder) are still right — all in one launch, all against scipy."""
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(n_knots)
+    ladders = [2000.0 + np.cumsum(rng.uniform(0.5, 4.0, n_knots)) for _ in range(n_ladders)]
+    x = np.concatenate(ladders)
+    ladder_off = (np.arange(n_ladders + 1) * n_knots).astype(np.int64)
+    n_slices = n_ladders * per_ladder
+    lens = np.full(n_slices, n_knots)
+    lens[1] = max(2, n_knots // 2)                       # a prefix of its ladder
+    knot_off = np.r_[0, np.cumsum(lens)].astype(np.int64)
+    x_off = np.array([(s % n_ladders) * n_knots for s in range(n_slices)], np.int64)
+    y = np.empty(int(knot_off[-1]))
+    for s in range(n_slices):
+        xs = x[x_off[s]: x_off[s] + lens[s]]
+        y[knot_off[s]:knot_off[s + 1]] = 0.2 + 0.3 * np.log(xs / 3000.0) ** 2 + 0.004 * rng.standard_normal(lens[s])
+    y[knot_off[2] + 5] = np.nan                          # slice 2 falls back to the general path
+    y[knot_off[3]] = np.nan                              # so does slice 3 (first knot missing)
+    xq = np.linspace(x.min() - 10, x.max() + 10, 257)
+    lu = D.spline_ladder_factor(_t(ladder_off, dev), _t(x, dev))
+    got = D.spline_fit_eval(_t(knot_off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=n_knots, extrap=1,
+                            x_off=_t(x_off, dev), lu=lu).cpu().numpy().reshape(n_slices, -1)
+    ref = D.spline_fit_eval(_t(knot_off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=n_knots, extrap=1,
+                            x_off=_t(x_off, dev)).cpu().numpy().reshape(n_slices, -1)
+    for s in range(n_slices):
+        want = O.natural_spline_eval(x[x_off[s]: x_off[s] + lens[s]], y[knot_off[s]:knot_off[s + 1]], xq, 1)
+        scale = max(1.0, np.abs(want).max())             # extrapolated cubics grow far outside the ladder
+        assert np.abs(got[s] - want).max() <= 1e-8 * scale, f"slice {s}: {np.abs(got[s] - want).max()}"
+        assert np.abs(got[s] - ref[s]).max() <= 1e-10 * scale, f"slice {s}: ladder vs general path"
