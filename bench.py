@@ -291,6 +291,28 @@ def run_gpu(args):
     roofline["limiter"] = ("instruction issue (ncu: issue slots 87 % busy, fp64 pipe 43 %, DRAM 17 %): the solver is transcendental-heavy "
                            "fp64, ~1050 instructions per quote") if dom == "implied_vol" else None
 
+    # ---- the same step in the chain layout (S per stamp, K and call/put per contract, T per (stamp, expiry)) -----
+    sc = SF.StructuredChain.from_quotes(chain)
+    for _ in range(args.warmup):
+        pipe.run(sc)
+    evc = [{s: [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for s in pipe.STAGES}
+           for _ in range(args.steps)]
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    c0.record()
+    for k in range(args.steps):
+        resc = pipe.run(sc, events=evc[k])
+    c1.record()
+    barrier()
+    ms_chain = max_over_ranks(c0.elapsed_time(c1)) / args.steps
+    chain_layout = {"value": world * n_quotes / (ms_chain / 1e3), "unit": UNIT, "ms_per_step": ms_chain,
+                    "stage_ms": {s: round(sum(evc[k][s][0].elapsed_time(evc[k][s][1]) for k in range(args.steps)) / args.steps, 4)
+                                 for s in pipe.STAGES},
+                    "input_bytes_per_quote": 8,
+                    "checksum_close": float(torch.nan_to_num(resc.close).sum().item()),
+                    "note": "k_bs_implied_vol_chain + shared-ladder spline path; same quotes, same candles to within the IV tolerance"}
+    del resc
+
     # ---- fp64 FMA peak, measured in the same run (kernel C is fp64-pipe bound) -------------
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
     n_thr, iters = 148 * 2048, 4096
@@ -337,7 +359,7 @@ def run_gpu(args):
                            "full_day": n_t == N_T_DAY},
                 "surface_points_per_sec": world * n_t * N_GRID_M * N_GRID_K / (ms_step / 1e3),
                 "candles_per_step": world * n_buckets * N_GRID_M * N_GRID_K,
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
+                "roofline": roofline, "kernels": kernels, "chain_layout_resident": chain_layout, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
                 "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv}
         _emit(line)
     if world > 1:

@@ -195,16 +195,19 @@ int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const in
                              const double* x, const double* y, int64_t n_q, const double* xq,
                              int32_t extrap, double* yq, ivx_stream_t stream);
 /* Shared ladders: when many slices use the same abscissae (a chain's strike ladder per expiry), the x-only half of
- * the elimination is done once per ladder — lu_cp/lu_inv/lu_ih are three arrays parallel to x, filled for the ladders
- * x[ladder_off[l] : ladder_off[l+1]) — and ivx_spline_fit_eval_ladder only eliminates each slice's right-hand side
- * (slice i uses x[x_off[i] + j], j < its knot count, i.e. a ladder or a prefix of one).  Slices with unusable knots
- * fall back to the general solve inside the same launch; results agree with ivx_spline_fit_eval to rounding. */
-int ivx_spline_ladder_factor(int64_t n_ladders, const int64_t* ladder_off, const double* x, double* lu_cp,
-                             double* lu_inv, double* lu_ih, ivx_stream_t stream);
-int ivx_spline_fit_eval_ladder(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
-                               const double* x, const double* lu_cp, const double* lu_inv, const double* lu_ih,
-                               const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq,
-                               ivx_stream_t stream);
+ * the elimination is done once per ladder.  ivx_spline_ladder_factor fills three tables of
+ * ivx_spline_ladder_table_len(n_ladders, max_knots) doubles for the ladders x[ladder_off[l] : ladder_off[l+1]) (stored in
+ * the order the evaluation kernel reads them; use the same max_knots in both calls).  ivx_spline_fit_eval_ladder then only
+ * eliminates each slice's right-hand side: slice i uses ladder slice_ladder[i], whose abscissae start at x[x_off[i]]
+ * (= x[ladder_off[slice_ladder[i]]]); its knots are the ladder or a prefix of it.  Slices with unusable knots fall back
+ * to the general solve inside the same launch; results agree with ivx_spline_fit_eval to rounding. */
+int64_t ivx_spline_ladder_table_len(int64_t n_ladders, int64_t max_knots);
+int ivx_spline_ladder_factor(int64_t n_ladders, const int64_t* ladder_off, int64_t max_knots, const double* x,
+                             double* lu_cp, double* lu_inv, double* lu_ih, ivx_stream_t stream);
+int ivx_spline_fit_eval_ladder(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off,
+                               const int32_t* slice_ladder, int64_t max_knots, const double* x,
+                               const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y,
+                               int64_t n_q, const double* xq, int32_t extrap, double* yq, ivx_stream_t stream);
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);

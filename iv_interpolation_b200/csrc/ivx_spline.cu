@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
                                                                        const double* __restrict__ x,
                                                                        const double* __restrict__ lu_cp, const double* __restrict__ lu_inv,
                                                                        const double* __restrict__ lu_ih,
+                                                                       const int32_t* __restrict__ slice_ladder,
                                                                        const double* __restrict__ y,
                                                                        int n_q, const double* __restrict__ xq, int extrap,
                                                                        double* __restrict__ yq) {
@@ -215,16 +216,19 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
   auto interior = [&](int j) { const int i = i0 + j; return i >= 1 && i <= n - 2; };
   if (LADDER && n == m) {
     // ---- shared-ladder path: slopes through the tabulated 1/h, right-hand side as affine maps of d' ------------------
-    const double* __restrict__ cp_t = lu_cp + xk0;
-    const double* __restrict__ inv_t = lu_inv + xk0;
-    const double* __restrict__ ih_t = lu_ih + xk0;
+    // tables are stored the way they are read: row i = R g + j of ladder l sits at l CAP + j G + g, so that the 32 lanes
+    // of a warp read 32 consecutive doubles
+    const int64_t tb = (int64_t)slice_ladder[sl] * L::CAP;
+    const double* __restrict__ cp_t = lu_cp + tb;
+    const double* __restrict__ inv_t = lu_inv + tb;
+    const double* __restrict__ ih_t = lu_ih + tb;
     const double xp = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yp = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
     const double yn = ys[spl_pad(i0 + SPL_R)];
     double sl[SPL_R + 1];                 // sl[k] = slope of segment i0+k-1
 #pragma unroll
     for (int k = 0; k <= SPL_R; ++k) {
       const int seg = i0 + k - 1;
-      const double ihv = (seg >= 0 && seg <= n - 2) ? __ldg(ih_t + seg) : 0.0;
+      const double ihv = (seg >= 0 && seg <= n - 2) ? __ldg(ih_t + (k == 0 ? (SPL_R - 1) * G + g - 1 : (k - 1) * G + g)) : 0.0;
       const double yl = k == 0 ? yp : yv[k - 1 < SPL_R ? (k - 1 < 0 ? 0 : k - 1) : 0];
       const double yr = k == SPL_R ? yn : yv[k < SPL_R ? k : 0];
       sl[k] = (yr - yl) * ihv;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
     for (int j = 0; j < SPL_R; ++j) {
       al[j] = 0.0; bt[j] = 0.0;
       if (interior(j)) {
-        const double inv = __ldg(inv_t + i0 + j);
+        const double inv = __ldg(inv_t + j * G + g);
         const double hm = xv[j] - (j == 0 ? xp : xv[j > 0 ? j - 1 : 0]);
         al[j] = 6.0 * (sl[j + 1] - sl[j]) * inv;
         bt[j] = -hm * inv;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
       if (interior(j)) {
         d = fma(bt[j], d, al[j]);
         dv[j] = d;
-        cv[j] = __ldg(cp_t + i0 + j);
+        cv[j] = __ldg(cp_t + j * G + g);
       }
     }
   } else {
@@ -540,7 +544,7 @@ extern "C" int64_t ivx_spline_workspace_bytes(int64_t, int64_t) { return 256; }
 
 template <int G, int SPL_R, bool LADDER>
 static int launch_spline_t(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const double* x, const double* lu_cp,
-                           const double* lu_inv, const double* lu_ih, const double* y, int n_q,
+                           const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder, const double* y, int n_q,
                          const double* xq, int extrap, double* yq, cudaStream_t stream) {
   using L = SplLayout<G, SPL_R>;
   static bool attr_set = false;
@@ -550,35 +554,60 @@ static int launch_spline_t(int64_t n_slices, const int64_t* knot_off, const int6
   }
   const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
   IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
-  k_spline_fit_eval<G, SPL_R, LADDER><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, y, n_q, xq, extrap, yq);
+  k_spline_fit_eval<G, SPL_R, LADDER><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_fit_eval");
   return IVX_OK;
 }
 
-// one thread per ladder: the x-only half of Thomas' elimination, once for every slice that uses the ladder
-__global__ void k_spline_ladder_factor(int64_t n_ladders, const int64_t* __restrict__ ladder_off, const double* __restrict__ x,
-                                       double* __restrict__ lu_cp, double* __restrict__ lu_inv, double* __restrict__ lu_ih) {
-  const int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (l >= n_ladders) return;
-  const int64_t a = ladder_off[l], n = ladder_off[l + 1] - a;
-  double c_prev = 0.0;
-  for (int64_t i = 0; i < n; ++i) {
-    const double hp = i + 1 < n ? x[a + i + 1] - x[a + i] : qnan();
-    lu_ih[a + i] = 1.0 / hp;
-    double cp = 0.0, inv = 0.0;
-    if (i >= 1 && i + 1 < n) {
-      const double hm = x[a + i] - x[a + i - 1];
-      inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
-      cp = hp * inv;
-      c_prev = cp;
+// threads per slice for a given max_knots (the kernels are instantiated for these widths, 8 rows per thread)
+static int spline_group_width(int64_t max_knots) {
+  for (int g = 32; g < 1024; g <<= 1)
+    if (max_knots <= (int64_t)g * SPL_RMAX) return g;
+  return 1024;
+}
+
+// one CTA per ladder: the x-only half of Thomas' elimination, once for every slice that uses the ladder.  The abscissae
+// are staged into shared memory by the whole CTA (the recurrence itself is a serial chain of divisions, run by thread 0
+// out of shared memory), results leave through coalesced stores.
+// Row i of ladder l goes to l*cap + (i % 8)*G + i/8 — the order in which the evaluation kernel's threads read it.
+__global__ void __launch_bounds__(256) k_spline_ladder_factor(int64_t n_ladders, const int64_t* __restrict__ ladder_off,
+                                                             const double* __restrict__ x, int G, double* __restrict__ lu_cp,
+                                                             double* __restrict__ lu_inv, double* __restrict__ lu_ih) {
+  extern __shared__ __align__(16) double sm[];      // x[n], cp[n], inv[n]
+  const int64_t l = blockIdx.x;
+  const int64_t a = ladder_off[l], cap = (int64_t)G * SPL_RMAX;
+  int64_t n64 = ladder_off[l + 1] - a;
+  if (n64 > cap) n64 = cap;
+  const int n = (int)n64;
+  double* sx = sm;
+  double* scp = sm + cap;
+  double* sinv = sm + 2 * cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = x[a + i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c_prev = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double cp = 0.0, inv = 0.0;
+      if (i >= 1 && i + 1 < n) {
+        const double hm = sx[i] - sx[i - 1], hp = sx[i + 1] - sx[i];
+        inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
+        cp = hp * inv;
+        c_prev = cp;
+      }
+      scp[i] = cp; sinv[i] = inv;
     }
-    lu_cp[a + i] = cp; lu_inv[a + i] = inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t o = l * cap + (int64_t)(i % SPL_RMAX) * G + i / SPL_RMAX;
+    lu_ih[o] = i + 1 < n ? 1.0 / (sx[i + 1] - sx[i]) : qnan();
+    lu_cp[o] = scp[i]; lu_inv[o] = sinv[i];
   }
 }
 
 static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots, const double* x,
-                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
-                           const double* xq, int32_t extrap, double* yq, cudaStream_t stream) {
+                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder,
+                           const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq, cudaStream_t stream) {
   IVX_REQUIRE(n_slices >= 0 && max_knots >= 0 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: extrap must be 0, 1 or 2");
   if (n_slices == 0 || n_q == 0) return IVX_OK;
@@ -587,40 +616,54 @@ static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int6
   // slices longer than the capacity the launch is sized for come back as NaN rows
   const int nq = (int)n_q;
   const bool ladder = lu_cp != nullptr;
-#define IVX_SPL(G, R)                                                                                                          \
-  return ladder ? launch_spline_t<G, R, true>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, y, nq, xq, extrap, yq, stream) \
-                : launch_spline_t<G, R, false>(n_slices, knot_off, x_off, x, nullptr, nullptr, nullptr, y, nq, xq, extrap, yq, stream)
-  if (max_knots <= 32 * 8) IVX_SPL(32, 8);
-  if (max_knots <= 64 * 8) IVX_SPL(64, 8);
-  if (max_knots <= 128 * 8) IVX_SPL(128, 8);
-  if (max_knots <= 256 * 8) IVX_SPL(256, 8);     // measured on B200: 8 rows x 256 threads beats 4 rows x 512 threads (24 vs 30 ms per day)
-  if (max_knots <= 512 * 8) IVX_SPL(512, 8);
-  IVX_SPL(1024, 8);
+#define IVX_SPL(G, R)                                                                                                                        \
+  return ladder ? launch_spline_t<G, R, true>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, y, nq, xq, extrap, yq, stream) \
+                : launch_spline_t<G, R, false>(n_slices, knot_off, x_off, x, nullptr, nullptr, nullptr, nullptr, y, nq, xq, extrap, yq, stream)
+  switch (spline_group_width(max_knots)) {
+    case 32: IVX_SPL(32, 8);
+    case 64: IVX_SPL(64, 8);
+    case 128: IVX_SPL(128, 8);
+    case 256: IVX_SPL(256, 8);     // measured on B200: 8 rows x 256 threads beats 4 rows x 512 threads (24 vs 30 ms per day)
+    case 512: IVX_SPL(512, 8);
+    default: IVX_SPL(1024, 8);
+  }
 #undef IVX_SPL
 }
 
 extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
                                         const double* x, const double* y, int64_t n_q, const double* xq, int32_t extrap,
                                         double* yq, ivx_stream_t stream_) {
-  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, nullptr, nullptr, nullptr, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
+  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, nullptr, nullptr, nullptr, nullptr, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
 }
 
-extern "C" int ivx_spline_ladder_factor(int64_t n_ladders, const int64_t* ladder_off, const double* x, double* lu_cp,
-                                        double* lu_inv, double* lu_ih, ivx_stream_t stream_) {
-  IVX_REQUIRE(n_ladders >= 0, IVX_ERR_INVALID_ARG, "ivx_spline_ladder_factor: negative count");
+extern "C" int64_t ivx_spline_ladder_table_len(int64_t n_ladders, int64_t max_knots) {
+  if (n_ladders < 0 || max_knots < 0 || max_knots > 1024 * SPL_RMAX) return -1;
+  return n_ladders * (int64_t)spline_group_width(max_knots) * SPL_RMAX;
+}
+
+extern "C" int ivx_spline_ladder_factor(int64_t n_ladders, const int64_t* ladder_off, int64_t max_knots, const double* x,
+                                        double* lu_cp, double* lu_inv, double* lu_ih, ivx_stream_t stream_) {
+  IVX_REQUIRE(n_ladders >= 0 && max_knots >= 0 && max_knots <= 1024 * SPL_RMAX, IVX_ERR_INVALID_ARG, "ivx_spline_ladder_factor: bad sizes");
   if (n_ladders == 0) return IVX_OK;
   IVX_REQUIRE(ladder_off && x && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG, "ivx_spline_ladder_factor: null pointer");
-  k_spline_ladder_factor<<<(unsigned)((n_ladders + 31) / 32), 32, 0, (cudaStream_t)stream_>>>(n_ladders, ladder_off, x, lu_cp, lu_inv, lu_ih);
+  const int G = spline_group_width(max_knots);
+  const size_t smem = (size_t)3 * G * SPL_RMAX * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    IVX_CUDA(cudaFuncSetAttribute(k_spline_ladder_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 1024 * SPL_RMAX * (int)sizeof(double)));
+    attr_set = true;
+  }
+  k_spline_ladder_factor<<<(unsigned)n_ladders, 256, smem, (cudaStream_t)stream_>>>(n_ladders, ladder_off, x, G, lu_cp, lu_inv, lu_ih);
   IVX_LAUNCH_CHECK("k_spline_ladder_factor");
   return IVX_OK;
 }
 
-extern "C" int ivx_spline_fit_eval_ladder(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
-                                          const double* x, const double* lu_cp, const double* lu_inv, const double* lu_ih,
-                                          const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq,
-                                          ivx_stream_t stream_) {
-  IVX_REQUIRE(x_off && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_ladder: x_off and the three factor arrays are required");
-  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, lu_cp, lu_inv, lu_ih, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
+extern "C" int ivx_spline_fit_eval_ladder(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const int32_t* slice_ladder,
+                                          int64_t max_knots, const double* x, const double* lu_cp, const double* lu_inv,
+                                          const double* lu_ih, const double* y, int64_t n_q, const double* xq, int32_t extrap,
+                                          double* yq, ivx_stream_t stream_) {
+  IVX_REQUIRE(x_off && slice_ladder && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_ladder: x_off, slice_ladder and the three factor tables are required");
+  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, lu_cp, lu_inv, lu_ih, slice_ladder, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
 }
 
 extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots, const double* x,

@@ -378,7 +378,7 @@ def bs_greeks(S, K, T, r, sigma, is_call, reference_put_rho_sign: bool = True) -
 def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, *,
                     max_knots: int, extrap: int = 1, out: Optional[torch.Tensor] = None,
                     workspace: Optional[torch.Tensor] = None, x_off: Optional[torch.Tensor] = None,
-                    lu: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+                    lu: Optional[Sequence[torch.Tensor]] = None, slice_ladder: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Natural cubic spline per slice, evaluated on the shared grid ``xq``.  ``x_off`` (one int64 per slice) reads the
     abscissae from shared ladders; ``lu`` = the three factor arrays of ``spline_ladder_factor`` additionally lets
     slices without missing knots skip the x-only half of the elimination."""
@@ -398,11 +398,12 @@ def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq
         if x_off.numel() < n_slices:
             raise _lib.IvxError("spline_fit_eval: x_off must have one entry per slice")
     if lu is not None:
-        if x_off is None or len(lu) != 3 or any(t.numel() != x.numel() or t.dtype != torch.float64 for t in lu):
-            raise _lib.IvxError("spline_fit_eval: lu needs x_off and three float64 arrays parallel to x")
-        check(lib().ivx_spline_fit_eval_ladder(n_slices, _ptr(knot_off), _ptr(x_off), int(max_knots), _ptr(x), _ptr(lu[0]),
-                                               _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q, _ptr(xq), int(extrap), _ptr(yq),
-                                               _stream()), "ivx_spline_fit_eval_ladder")
+        if x_off is None or slice_ladder is None or len(lu) != 3 or any(t.dtype != torch.float64 for t in lu):
+            raise _lib.IvxError("spline_fit_eval: lu needs x_off, slice_ladder and the three float64 tables of spline_ladder_factor")
+        _req(slice_ladder, torch.int32, "slice_ladder")
+        check(lib().ivx_spline_fit_eval_ladder(n_slices, _ptr(knot_off), _ptr(x_off), _ptr(slice_ladder), int(max_knots), _ptr(x),
+                                               _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q, _ptr(xq), int(extrap),
+                                               _ptr(yq), _stream()), "ivx_spline_fit_eval_ladder")
     else:
         check(lib().ivx_spline_fit_eval_xoff(n_slices, _ptr(knot_off), _ptr(x_off), int(max_knots), _ptr(x), _ptr(y), n_q,
                                              _ptr(xq), int(extrap), _ptr(yq), _stream()), "ivx_spline_fit_eval_xoff")
@@ -410,13 +411,21 @@ def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq
     return yq
 
 
-def spline_ladder_factor(ladder_off: torch.Tensor, x: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
-    """Thomas factors (c', 1/den, 1/h) of the natural-spline systems of the ladders x[ladder_off[l]:ladder_off[l+1]],
-    three arrays parallel to ``x`` (one tiny launch; reusable by every slice on those ladders)."""
+def spline_ladder_factor(ladder_off: torch.Tensor, x: torch.Tensor, *, max_knots: int,
+                         out: Optional[Sequence[torch.Tensor]] = None):
+    """Thomas factors (c', 1/den, 1/h) of the natural-spline systems of the ladders x[ladder_off[l]:ladder_off[l+1]]: three
+    tables in the order the evaluation kernel reads them (one tiny launch; reusable by every slice on those ladders; pass
+    the same ``max_knots`` to ``spline_fit_eval``)."""
     _req(ladder_off, torch.int64, "ladder_off"); _req(x, torch.float64, "x")
-    lu = out if out is not None else [_empty(x.numel(), torch.float64, x) for _ in range(3)]
-    check(lib().ivx_spline_ladder_factor(ladder_off.numel() - 1, _ptr(ladder_off), _ptr(x), _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]),
-                                         _stream()), "ivx_spline_ladder_factor")
+    n_ladders = ladder_off.numel() - 1
+    n_tab = lib().ivx_spline_ladder_table_len(n_ladders, int(max_knots))
+    if n_tab < 0:
+        raise _lib.IvxError("spline_ladder_factor: bad sizes")
+    lu = out if out is not None else [torch.zeros(n_tab, dtype=torch.float64, device=x.device) for _ in range(3)]
+    if any(t.numel() < n_tab for t in lu):
+        raise _lib.IvxError(f"spline_ladder_factor: tables need {n_tab} elements")
+    check(lib().ivx_spline_ladder_factor(n_ladders, _ptr(ladder_off), int(max_knots), _ptr(x), _ptr(lu[0]), _ptr(lu[1]),
+                                         _ptr(lu[2]), _stream()), "ivx_spline_ladder_factor")
     _count("spline_ladder_factor")
     return lu
 

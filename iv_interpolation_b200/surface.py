@@ -137,6 +137,7 @@ class SurfacePipeline:
         # chain layout: every slice (t, e) reads its abscissae from the shared ladder of expiry e
         self._x_off = None
         self._chain_ws = None
+        self._lu_key = None
 
     def plan_buckets(self, ts: torch.Tensor):
         """Bucket boundaries of the day's stamps (one tiny kernel + an 8-byte read-back, done once per tape)."""
@@ -166,7 +167,9 @@ class SurfacePipeline:
                                              device=self.device)
                 self._x_off = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp) * sp.n_strike
                 self._ladder_off = torch.arange(sp.n_exp + 1, dtype=torch.int64, device=self.device) * sp.n_strike
-                self._lu = [torch.empty(sp.n_exp * sp.n_strike, dtype=torch.float64, device=self.device) for _ in range(3)]
+                n_tab = lib().ivx_spline_ladder_table_len(sp.n_exp, sp.n_strike)
+                self._lu = [torch.zeros(n_tab, dtype=torch.float64, device=self.device) for _ in range(3)]
+                self._slice_ladder = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp).to(torch.int32)
             D.bs_implied_vol_chain(q.price, q.is_call, q.S_t, q.K_ek, q.T_te, q.r_t, n_t=sp.n_t, n_exp=sp.n_exp,
                                    n_strike=sp.n_strike, out=self.iv, workspace=self._chain_ws)
         else:
@@ -175,10 +178,14 @@ class SurfacePipeline:
         mark("spline_strike", 0)
         # knots of slice (t, e): x = the quoted strikes, read in place from the K column / the expiry's ladder
         if structured:
-            # the x-only half of the elimination once per expiry ladder (one 30-thread launch), then right-hand sides only
-            D.spline_ladder_factor(self._ladder_off, q.K_ek, out=self._lu)
+            # the x-only half of the elimination once per expiry ladder — and only when the ladders changed (contracts do
+            # not change intraday) — then right-hand sides only
+            key = (q.K_ek.data_ptr(), q.K_ek._version)
+            if self._lu_key != key:
+                D.spline_ladder_factor(self._ladder_off, q.K_ek, max_knots=sp.n_strike, out=self._lu)
+                self._lu_key = key
             D.spline_fit_eval(self.knot_off, q.K_ek, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
-                              out=self.smile, x_off=self._x_off, lu=self._lu)
+                              out=self.smile, x_off=self._x_off, lu=self._lu, slice_ladder=self._slice_ladder)
         else:
             D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile)
         mark("spline_strike", 1)

@@ -521,9 +521,10 @@ def test_spline_shared_ladder_path(dev, n_knots, n_ladders, per_ladder):
     y[knot_off[2] + 5] = np.nan                          # slice 2 falls back to the general path
     y[knot_off[3]] = np.nan                              # so does slice 3 (first knot missing)
     xq = np.linspace(x.min() - 10, x.max() + 10, 257)
-    lu = D.spline_ladder_factor(_t(ladder_off, dev), _t(x, dev))
+    lu = D.spline_ladder_factor(_t(ladder_off, dev), _t(x, dev), max_knots=n_knots)
+    slice_ladder = np.array([s % n_ladders for s in range(n_slices)], np.int32)
     got = D.spline_fit_eval(_t(knot_off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=n_knots, extrap=1,
-                            x_off=_t(x_off, dev), lu=lu).cpu().numpy().reshape(n_slices, -1)
+                            x_off=_t(x_off, dev), lu=lu, slice_ladder=_t(slice_ladder, dev)).cpu().numpy().reshape(n_slices, -1)
     ref = D.spline_fit_eval(_t(knot_off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=n_knots, extrap=1,
                             x_off=_t(x_off, dev)).cpu().numpy().reshape(n_slices, -1)
     for s in range(n_slices):
@@ -531,3 +532,5 @@ def test_spline_shared_ladder_path(dev, n_knots, n_ladders, per_ladder):
         scale = max(1.0, np.abs(want).max())             # extrapolated cubics grow far outside the ladder
         assert np.abs(got[s] - want).max() <= 1e-8 * scale, f"slice {s}: {np.abs(got[s] - want).max()}"
         assert np.abs(got[s] - ref[s]).max() <= 1e-10 * scale, f"slice {s}: ladder vs general path"
+    # the two paths round differently: identical bits on a complete slice would mean the table path was not taken
+    assert np.abs(got[4] - ref[4]).max() > 0 and _eq(got[2], ref[2])
