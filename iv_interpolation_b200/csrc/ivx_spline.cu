@@ -123,7 +123,7 @@ struct SplLayout {
 // has its right-hand side to eliminate: d'[i] = (r[i] - h[i-1] d'[i-1]) / den[i] is an affine map per row — a prefix scan
 // of 2-vectors, no matrices, no division.  Slices with missing knots take the general path below.
 template <int G, int SPL_R, bool LADDER>
-__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
+__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? (LADDER ? 4 : 3) : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
                                                                        const int64_t* __restrict__ x_off,
                                                                        const double* __restrict__ x,
                                                                        const double* __restrict__ lu_cp, const double* __restrict__ lu_inv,
@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
   const double xlo = xs[spl_pad(0)], xhi = xs[spl_pad(n - 1)], ylo = ys[spl_pad(0)], yhi = ys[spl_pad(n - 1)];
   const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
   const bool owns_last = (n - 2) <= i0 + SPL_R - 1;
+  const bool edge = g == 0 || owns_last;
   int qi = qs[g];
   const int qhi = owns_last ? n_q : qs[g + 1];
 #pragma unroll
@@ -388,7 +389,8 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 3 : 1)) k
         const double xv_q = __ldg(xq + qi);
         if (!(lastseg || xv_q < xr_)) break;
         const double v = spline_eval(xv[j], xr_, yv[j], yr_, dv[j], Mr_, xv_q);
-        st_stream(out + qi, apply_extrap(v, xv_q, xlo, xhi, ylo, yhi, extrap));
+        // only the first thread can see points below the first knot, only the last segment's owner points above the last
+        st_stream(out + qi, edge ? apply_extrap(v, xv_q, xlo, xhi, ylo, yhi, extrap) : v);
         ++qi;
       }
     }
