@@ -226,6 +226,9 @@ int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, int32_t n_k
 int ivx_exclusive_scan_i64(int64_t n, const int64_t* in, int64_t* out /*n+1*/, ivx_stream_t stream);
 int ivx_probe_copy(int64_t n_f64, const double* src, double* dst, ivx_stream_t stream);
 int ivx_probe_fp64_fma(int64_t n_threads, int32_t iters, double* sink, ivx_stream_t stream);
+/* kernel A's store pattern alone (11 fp64 + one int32 + one uint8 stream of n_rows, arrays stride_f64 doubles apart):
+ * the write-side ceiling kernel A is measured against */
+int ivx_probe_write_streams(int64_t n_rows, double* base, int64_t stride_f64, ivx_stream_t stream);
 /* host-side evaluation of the multiply-high floor division the bucket kernels use (tests) */
 int64_t ivx_host_floor_div(int64_t t, int64_t d);
 

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ivx_exclusive_scan_i64": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_copy": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_fp64_fma": (C.c_int, [_i64, _i32, _p, _p]),
+    "ivx_probe_write_streams": (C.c_int, [_i64, _p, _i64, _p]),
     "ivx_host_floor_div": (_i64, [_i64, _i64]),
 }
 

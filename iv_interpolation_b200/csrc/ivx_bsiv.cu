@@ -402,6 +402,19 @@ __global__ void __launch_bounds__(256) k_probe_copy(int64_t n2, const double2* _
     dst[i] = src[i];
 }
 
+// kernel A's store pattern with nothing else: tiles of 1024 rows, 11 x 8-byte + 4-byte + 1-byte streams per row
+__global__ void __launch_bounds__(256) k_probe_write_streams(int64_t n_rows, double* const base, int64_t stride_f64) {
+  const int64_t r0 = blockIdx.x * (int64_t)1024;
+  for (int it = 0; it < 4; ++it) {
+    const int64_t o = r0 + it * 256 + threadIdx.x;
+    if (o >= n_rows) return;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) __stcs(base + k * stride_f64 + o, (double)o);
+    __stcs(reinterpret_cast<int32_t*>(base + 11 * stride_f64) + o, (int32_t)o);
+    reinterpret_cast<uint8_t*>(base + 12 * stride_f64)[o] = 0;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_probe_fp64(int32_t iters, double* sink) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 0.999999, c = 1e-7;
@@ -486,6 +499,13 @@ extern "C" int ivx_probe_copy(int64_t n_f64, const double* src, double* dst, ivx
   IVX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0, IVX_ERR_INVALID_ARG, "ivx_probe_copy: buffers must be 16-byte aligned");
   k_probe_copy<<<sm_count() * 16, 256, 0, (cudaStream_t)stream>>>(n_f64 / 2, (const double2*)src, (double2*)dst);
   IVX_LAUNCH_CHECK("k_probe_copy");
+  return IVX_OK;
+}
+
+extern "C" int ivx_probe_write_streams(int64_t n_rows, double* base, int64_t stride_f64, ivx_stream_t stream) {
+  IVX_REQUIRE(n_rows > 0 && base && stride_f64 >= n_rows, IVX_ERR_INVALID_ARG, "ivx_probe_write_streams: bad arguments");
+  k_probe_write_streams<<<(unsigned)((n_rows + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(n_rows, base, stride_f64);
+  IVX_LAUNCH_CHECK("k_probe_write_streams");
   return IVX_OK;
 }
 

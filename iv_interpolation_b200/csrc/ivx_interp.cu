@@ -19,18 +19,29 @@ constexpr int TA_THREADS = 256;
 constexpr int TA_ROWS = 1024;
 constexpr int PLAN_WARPS = 8;
 
+// everything exec needs about the interval that starts at one on-grid source row, in ONE record: a row's ~20 parameter
+// loads then fall into two or three cache lines shared by the whole warp, at constant offsets from one address
+struct __align__(16) IntervalRec {
+  int64_t gts;
+  int32_t grow, pad_;
+  double y0[3], y1[3], slope[3];
+  int32_t x0[3], x1[3];
+  double fval[IVX_MAX_FILL_COLS];
+  int32_t fidx[IVX_MAX_IDX_COLS];
+};
+static_assert(sizeof(IntervalRec) == 192, "IntervalRec layout");
+
 struct InterpWs {
   // per compacted on-grid source row
-  int32_t* gpos;
-  int64_t* gts;
-  int32_t* grow;
-  double* y0[3];
-  double* y1[3];
-  double* slope[3];
-  int32_t* x0[3];
-  int32_t* x1[3];
-  double* fval[IVX_MAX_FILL_COLS];
-  int32_t* fidx[IVX_MAX_IDX_COLS];
+  int32_t* gpos;          // dense: searched by exec
+  IntervalRec* rec;       // assembled by the plan's backward sweep, read by exec
+  // column-wise scratch of the plan's forward sweep (coalesced per column)
+  int64_t* s_gts;
+  int32_t* s_grow;
+  double* s_y0[3];
+  int32_t* s_x0[3];
+  double* s_fval[IVX_MAX_FILL_COLS];
+  int32_t* s_fidx[IVX_MAX_IDX_COLS];
   // per contract
   int32_t* n_on;
   int32_t* p0;
@@ -42,17 +53,12 @@ InterpWs carve(void* ws, int64_t bytes, int64_t n_sym, int64_t n_src, int n_fill
   Carver cv(ws, bytes);
   InterpWs W;
   W.gpos = cv.take<int32_t>(n_src);
-  W.gts = cv.take<int64_t>(n_src);
-  W.grow = cv.take<int32_t>(n_src);
-  for (int c = 0; c < 3; ++c) {
-    W.y0[c] = cv.take<double>(n_src);
-    W.y1[c] = cv.take<double>(n_src);
-    W.slope[c] = cv.take<double>(n_src);
-    W.x0[c] = cv.take<int32_t>(n_src);
-    W.x1[c] = cv.take<int32_t>(n_src);
-  }
-  for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) W.fval[k] = k < n_fill ? cv.take<double>(n_src) : nullptr;
-  for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) W.fidx[k] = k < n_idx ? cv.take<int32_t>(n_src) : nullptr;
+  W.rec = cv.take<IntervalRec>(n_src);
+  W.s_gts = cv.take<int64_t>(n_src);
+  W.s_grow = cv.take<int32_t>(n_src);
+  for (int c = 0; c < 3; ++c) { W.s_y0[c] = cv.take<double>(n_src); W.s_x0[c] = cv.take<int32_t>(n_src); }
+  for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) W.s_fval[k] = k < n_fill ? cv.take<double>(n_src) : nullptr;
+  for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) W.s_fidx[k] = k < n_idx ? cv.take<int32_t>(n_src) : nullptr;
   W.n_on = cv.take<int32_t>(n_sym);
   W.p0 = cv.take<int32_t>(n_sym);
   W.tile_count = cv.take<int64_t>(n_sym + 1);
@@ -87,6 +93,7 @@ __device__ __forceinline__ int lowest_bit_gt(uint32_t m, int lane) {   // lowest
 }
 
 __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParams P) {
+  __shared__ IntervalRec s_rec[PLAN_WARPS * 32];   // 48 KB: one record per lane, copied out coalesced
   const int lane = threadIdx.x & 31;
   const int64_t s = blockIdx.x * (int64_t)PLAN_WARPS + (threadIdx.x >> 5);
   if (s >= P.n_sym) return;
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
     const uint32_t le = 0xffffffffu >> (31 - lane);
     const int32_t pos = (int32_t)k + carry_dups + __popc(m_dup & le);
     const int64_t g = a + carry_on + __popc(m_on & (le >> 1));
-    if (on) { W.gpos[g] = pos; W.gts[g] = t; W.grow[g] = (int32_t)r; }
+    if (on) { W.gpos[g] = pos; W.s_gts[g] = t; W.s_grow[g] = (int32_t)r; }
 
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
       int32_t ppos = __shfl_sync(IVX_FULL_MASK, pos, sl < 0 ? 0 : sl);
       double pval = __shfl_sync(IVX_FULL_MASK, v, sl < 0 ? 0 : sl);
       if (sl < 0) { ppos = cpos[c]; pval = cval[c]; }
-      if (on) { W.x0[c][g] = ppos; W.y0[c][g] = pval; }
+      if (on) { W.s_x0[c][g] = ppos; W.s_y0[c][g] = pval; }
       if (m_v) {
         const int last = 31 - __clz(m_v);
         if (first_pos[c] == INT32_MAX) first_pos[c] = __shfl_sync(IVX_FULL_MASK, pos, __ffs(m_v) - 1);
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
         const int sl = highest_bit_le(m_v, lane);
         double pval = __shfl_sync(IVX_FULL_MASK, v, sl < 0 ? 0 : sl);
         if (sl < 0) pval = cfill[kf];
-        if (on) W.fval[kf][g] = pval;
+        if (on) W.s_fval[kf][g] = pval;
         if (m_v) cfill[kf] = __shfl_sync(IVX_FULL_MASK, v, 31 - __clz(m_v));
       }
     }
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
         const int sl = highest_bit_le(m_v, lane);
         int32_t pidx = __shfl_sync(IVX_FULL_MASK, (int32_t)r, sl < 0 ? 0 : sl);
         if (sl < 0) pidx = cidx[ki];
-        if (on) W.fidx[ki][g] = pidx;
+        if (on) W.s_fidx[ki][g] = pidx;
         if (m_v) {
           if (ki == 0 && first_sym_pos == INT32_MAX) first_sym_pos = __shfl_sync(IVX_FULL_MASK, pos, __ffs(m_v) - 1);
           cidx[ki] = __shfl_sync(IVX_FULL_MASK, (int32_t)r, 31 - __clz(m_v));
@@ -232,29 +239,42 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
     const int64_t g = hi - 32 + lane;              // chunk [hi-32, hi), may start before a
     const bool ing = g >= a;
     const int32_t pos = ing ? W.gpos[g] : -1;
+    IntervalRec& R = s_rec[threadIdx.x];             // this lane's record, assembled in shared memory
+    R.gts = ing ? W.s_gts[g] : 0; R.grow = ing ? W.s_grow[g] : -1; R.pad_ = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const int32_t x0 = ing ? W.x0[c][g] : -1;
-      const double y0 = ing ? W.y0[c][g] : 0.0;
+      const int32_t x0 = ing ? W.s_x0[c][g] : -1;
+      const double y0 = ing ? W.s_y0[c][g] : 0.0;
       const bool valid = ing && (x0 == pos);       // the row's own value is a knot
       const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
       const int sl = lowest_bit_gt(m_v, lane);
       int32_t x1 = __shfl_sync(IVX_FULL_MASK, pos, sl < 0 ? 0 : sl);
       double y1 = __shfl_sync(IVX_FULL_MASK, y0, sl < 0 ? 0 : sl);
       if (sl < 0) { x1 = npos[c]; y1 = nval[c]; }
-      if (ing) {
-        W.x1[c][g] = x1;
-        W.y1[c][g] = y1;
-        double slope = 0.0;
-        if (x0 >= 0 && x1 >= 0) slope = __ddiv_rn(__dsub_rn(y1, y0), (double)(x1 - x0));   // np.interp slope
-        W.slope[c][g] = slope;
-      }
+      double slope = 0.0;
+      if (x0 >= 0 && x1 >= 0) slope = __ddiv_rn(__dsub_rn(y1, y0), (double)(x1 - x0));   // np.interp slope
+      R.x0[c] = x0; R.y0[c] = y0; R.x1[c] = x1; R.y1[c] = y1; R.slope[c] = slope;
       if (m_v) {
         const int first = __ffs(m_v) - 1;
         npos[c] = __shfl_sync(IVX_FULL_MASK, pos, first);
         nval[c] = __shfl_sync(IVX_FULL_MASK, y0, first);
       }
     }
+#pragma unroll
+    for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) R.fval[k] = (ing && k < P.n_fill) ? W.s_fval[k][g] : 0.0;
+#pragma unroll
+    for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) R.fidx[k] = (ing && k < P.n_idx) ? W.s_fidx[k][g] : -1;
+    __syncwarp();
+    // the chunk's records [hi-32, hi) are contiguous in global memory: the warp copies them out 16 bytes per lane at a time
+    {
+      const int64_t g_lo = max(hi - 32, a);
+      const int first_lane = (int)(g_lo - (hi - 32));
+      const uint4* src = reinterpret_cast<const uint4*>(&s_rec[(threadIdx.x & ~31) + first_lane]);
+      uint4* dst = reinterpret_cast<uint4*>(W.rec + g_lo);
+      const int n16 = (int)(hi - g_lo) * (int)(sizeof(IntervalRec) / 16);
+      for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
   }
 
   // ---- dropna (core.py:74): rows before the first valid value of any key column go ------------------------
@@ -387,28 +407,35 @@ __global__ void __launch_bounds__(TA_THREADS) k_interp_exec(const ExecParams P) 
     if (!act) continue;
     const int64_t g = a + l2;
     const int32_t gp = __ldg(W.gpos + g);
+    const IntervalRec* __restrict__ R = W.rec + g;
     const int64_t o = obase + q;
-    st_stream(P.o_ts + o, __ldg(W.gts + g) + (int64_t)(p - gp) * P.step);
+    st_stream(P.o_ts + o, __ldg(&R->gts) + (int64_t)(p - gp) * P.step);
     bool keep = true;
+    // every parameter of the interval is requested up front (independent loads, one latency round) — no load waits on a
+    // branch taken on an earlier one
+    int32_t x0v[3], x1v[3];
+    double y0v[3], slv[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const int32_t x0 = __ldg(W.x0[c] + g);
+      x0v[c] = __ldg(&R->x0[c]); x1v[c] = __ldg(&R->x1[c]);
+      y0v[c] = __ldg(&R->y0[c]); slv[c] = __ldg(&R->slope[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int32_t x0 = x0v[c], x1 = x1v[c];
+      const double y0 = y0v[c];
       double v;
       if (x0 < 0) {
         v = qnan();                                              // leading NaNs are preserved
+      } else if (x1 < 0 || p == x0) {
+        v = y0;                                                  // a knot itself / flat tail
       } else {
-        const double y0 = __ldg(W.y0[c] + g);
-        const int32_t x1 = __ldg(W.x1[c] + g);
-        if (x1 < 0 || p == x0) {
-          v = y0;                                                // a knot itself / flat tail
-        } else {
-          const double sl = __ldg(W.slope[c] + g);
-          v = __dadd_rn(__dmul_rn(sl, (double)(p - x0)), y0);    // np.interp: slope*(x-x0)+y0, no FMA
-          if (isnan(v)) {
-            const double y1 = __ldg(W.y1[c] + g);
-            v = __dadd_rn(__dmul_rn(sl, (double)(p - x1)), y1);
-            if (isnan(v) && y0 == y1) v = y0;
-          }
+        const double sl = slv[c];
+        v = __dadd_rn(__dmul_rn(sl, (double)(p - x0)), y0);      // np.interp: slope*(x-x0)+y0, no FMA
+        if (isnan(v)) {
+          const double y1 = __ldg(&R->y1[c]);
+          v = __dadd_rn(__dmul_rn(sl, (double)(p - x1)), y1);
+          if (isnan(v) && y0 == y1) v = y0;
         }
       }
       keep = keep && !isnan(v);
@@ -416,16 +443,16 @@ __global__ void __launch_bounds__(TA_THREADS) k_interp_exec(const ExecParams P) 
     }
 #pragma unroll
     for (int k = 0; k < IVX_MAX_FILL_COLS; ++k)
-      if (k < P.n_fill && P.o_fill[k]) st_stream(P.o_fill[k] + o, __ldg(W.fval[k] + g));
+      if (k < P.n_fill && P.o_fill[k]) st_stream(P.o_fill[k] + o, __ldg(&R->fval[k]));
 #pragma unroll
     for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) {
       if (k < P.n_idx) {
-        const int32_t ix = __ldg(W.fidx[k] + g);
+        const int32_t ix = __ldg(&R->fidx[k]);
         if (k == 0) keep = keep && ix >= 0;
         if (P.o_idx[k]) st_stream(P.o_idx[k] + o, ix);
       }
     }
-    if (P.o_src_row) st_stream(P.o_src_row + o, p == gp ? __ldg(W.grow + g) : -1);
+    if (P.o_src_row) st_stream(P.o_src_row + o, p == gp ? __ldg(&R->grow) : -1);
     if (P.o_pos) st_stream(P.o_pos + o, p);
     if (P.o_keep) P.o_keep[o] = keep ? 1 : 0;
     if (P.o_isint) P.o_isint[o] = 0;                             // core.py:71, always False
@@ -439,8 +466,8 @@ using namespace ivx;
 
 extern "C" int64_t ivx_interp_workspace_bytes(int64_t n_sym, int64_t n_src, int32_t n_fill, int32_t n_idx) {
   if (n_sym < 0 || n_src < 0 || n_fill < 0 || n_idx < 0) return -1;
-  int64_t per_row = 4 + 8 + 4 + 3 * (8 + 8 + 8 + 4 + 4) + 8 * (int64_t)n_fill + 4 * (int64_t)n_idx;
-  int64_t arrays = 3 + 15 + n_fill + n_idx + 4;
+  int64_t per_row = 4 + (int64_t)sizeof(IntervalRec) + 8 + 4 + 3 * (8 + 4) + 8 * (int64_t)n_fill + 4 * (int64_t)n_idx;
+  int64_t arrays = 2 + 2 + 6 + n_fill + n_idx + 4;
   return per_row * n_src + (4 + 4 + 8 + 8) * (n_sym + 2) + 256 * (arrays + 2);
 }
 
