@@ -14,7 +14,7 @@
 //   * beta >= b(s_c): root in the concave branch — solve b(s) = beta directly.
 // The fp64 pipe is this kernel's roofline (ncu: profiles/), so the solver is split in two phases:
 //   1. an fp32 PRE-SOLVE (FP32 pipe + MUFU, runs in the shadow of other warps' fp64 work): the
-//      closed-form guess (tangent and log-match at the inflection point, blended) followed by two bracketed Halley iterations
+//      closed-form guess (tangent and log-match at the inflection point, blended) followed by one bracketed third-order Householder step
 //      in single precision — leaves s to ~1e-7 relative on all but a few 1e-4 of the quotes;
 //   2. an fp64 POLISH: bracketed Halley iterations (third order; two divisions, two erfcx|erfc
 //      and one log|exp each) until a step is below 1e-4 s — after such a step the remaining
@@ -33,7 +33,7 @@ constexpr double SQRT_2PI = 2.5066282746310002;
 constexpr double INV_SQRT_2PI = 0.3989422804014327;
 constexpr double S_MAX = 40.0;   // sigma*sqrt(T) bracket; fp64 prices cannot encode more than ~17
 constexpr int MAX_ITERS = 64;
-constexpr int PRE_ITERS = 2;
+constexpr int PRE_ITERS = 1;
 constexpr double ACCEPT_STEP = 1e-4;   // relative size of a Halley step after which s is converged (cubic)
 
 __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * INV_SQRT2); }
@@ -121,22 +121,29 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
   for (int it = 0; it < PRE_ITERS; ++it) {
     const float inv_s = __fdividef(1.0f, s);
     const float h = -x * inv_s, t = 0.5f * s;        // h >= 0
-    const float r2 = h * h * inv_s - 0.25f * s;      // b''/b'
-    float g, newton, den;
+    const float hs = h * inv_s;
+    const float r2 = h * hs - 0.25f * s;              // b2/b1: second over first derivative of b
+    const float r3 = r2 * r2 - 3.0f * hs * hs - 0.25f;  // b3/b1
+    // Householder's third-order step (quartic convergence): dn (1 + A dn/2) / (1 + dn (A + B dn/6)),
+    // dn = -g/g1, A = g2/g1, B = g3/g1 (derivatives of the objective g)
+    float g, newton, A, B;
     if (lower) {
       const float q1 = (h - t) * kInvSqrt2;           // < 0 only if s overshot the inflection point
       const float D = (q1 >= 0.0f ? erfcx_pos_f(q1) : erfcxf(q1)) - erfcx_pos_f((h + t) * kInvSqrt2);
       g = -0.5f * (h * h + t * t) + __logf(0.5f * D) - lnbeta;
-      newton = -g * D * (0.5f * kSqrt2Pi);           // -g / (ln b)',  (ln b)' = 2 / (sqrt(2 pi) D)
-      den = 1.0f + 0.5f * newton * r2 + 0.5f * g;    // 1 + newton/2 * ((ln b)''/(ln b)'),  newton (ln b)' = -g
+      newton = -g * D * (0.5f * kSqrt2Pi);           // -g / d1,  d1 = (ln b)' = 2 / (sqrt(2 pi) D)
+      const float d1 = __fdividef(2.0f / kSqrt2Pi, D);
+      A = r2 - d1;
+      B = r3 - 3.0f * r2 * d1 + 2.0f * d1 * d1;
     } else {
       const float b = 0.5f * (ex2 * erfcf((h - t) * kInvSqrt2) - iex2 * erfcf((h + t) * kInvSqrt2));
       g = b - beta;
       newton = -g * kSqrt2Pi * __expf(0.5f * (h * h + t * t));
-      den = 1.0f + 0.5f * newton * r2;
+      A = r2; B = r3;
     }
     if (g > 0.0f) hi = s; else lo = s;
-    float sn = s + ((den > 0.5f && den < 2.0f) ? __fdividef(newton, den) : newton);
+    const float fac = __fdividef(fmaf(0.5f * A, newton, 1.0f), fmaf(newton, fmaf(B * (1.0f / 6.0f), newton, A), 1.0f));
+    float sn = s + ((fac > 0.3f && fac < 3.0f) ? newton * fac : newton);
     if (!(sn >= lo && sn <= hi && sn > 0.0f)) sn = 0.5f * (lo + hi);   // also catches NaN
     s = sn;
   }
