@@ -209,7 +209,8 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double inv_b
         if (q1 >= 0.0 && q2 < 1e70) erfcx_pair_pos(q1, q2, e1, e2);
         else { e1 = erfcx(q1); e2 = erfcx(q2); }      // s overshot the inflection point (q1 < 0), or absurd inputs
         const double D = e1 - e2;
-        g = log(0.5 * D * inv_beta) - e - lnbeta_off;
+        const double arg = 0.5 * D * inv_beta;
+        g = ((arg >= 2.3e-308 && arg <= 1e300) ? log_normal(arg) : log(arg)) - e - lnbeta_off;
         newton = -g * D * (0.5 * SQRT_2PI);
         den = 1.0 + 0.5 * newton * r2 + 0.5 * g;
       } else {
