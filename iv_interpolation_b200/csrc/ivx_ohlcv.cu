@@ -15,8 +15,9 @@
 namespace ivx {
 namespace {
 
-constexpr int TB_THREADS = 128;
+constexpr int TB_THREADS = 160;   // warp 0 runs the look-back while 4 warps walk ~103 five-row buckets of a tile in one pass
 constexpr int TB_ROWS = 512;
+constexpr int TB_PER = (TB_ROWS + TB_THREADS - 1) / TB_THREADS;   // rows per thread in the row-parallel phases
 constexpr int TB_GROUPS = TB_ROWS / 32;
 constexpr int64_t BID_NAT = INT64_MIN;  // bucket id given to rows without a timestamp
 
@@ -173,11 +174,11 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
 
   // ---- bucket ids (in place) and sortedness ------------------------------------------------------
   // the per-row input checks of validate_candle_data (core.py:115-137) ride along here, row-parallel
-  int64_t bid[TB_ROWS / TB_THREADS];
+  int64_t bid[TB_PER];
   uint32_t unsorted_rows = 0;
-  uint32_t rflags[TB_ROWS / TB_THREADS];
+  uint32_t rflags[TB_PER];
 #pragma unroll
-  for (int k = 0; k < TB_ROWS / TB_THREADS; ++k) {
+  for (int k = 0; k < TB_PER; ++k) {
     int i = tid + k * TB_THREADS;
     rflags[k] = 0;
     if (i < rows) {
@@ -191,13 +192,13 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < TB_ROWS / TB_THREADS; ++k) {
+  for (int k = 0; k < TB_PER; ++k) {
     int i = tid + k * TB_THREADS;
     if (i < rows) S.ts[i] = bid[k];
   }
   if (P.sym_flags) {
 #pragma unroll
-    for (int k = 0; k < TB_ROWS / TB_THREADS; ++k) {
+    for (int k = 0; k < TB_PER; ++k) {
       const uint32_t f = rflags[k] | ((unsorted_rows >> k) & 1u ? IVX_FLAG_UNSORTED : 0u);
       if (f) atomicOr(P.sym_flags + symbol_of_row(P.in_off, P.n_sym, r0 + tid + k * TB_THREADS), f);
     }
