@@ -123,7 +123,7 @@ struct SplLayout {
 // has its right-hand side to eliminate: d'[i] = (r[i] - h[i-1] d'[i-1]) / den[i] is an affine map per row — a prefix scan
 // of 2-vectors, no matrices, no division.  Slices with missing knots take the general path below.
 template <int G, int SPL_R, bool LADDER>
-__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? (LADDER ? 4 : 3) : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
+__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
                                                                        const int64_t* __restrict__ x_off,
                                                                        const double* __restrict__ x,
                                                                        const double* __restrict__ lu_cp, const double* __restrict__ lu_inv,
