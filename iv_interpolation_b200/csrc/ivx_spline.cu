@@ -274,30 +274,37 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   // ---- row coefficients.  Row i (1 <= i <= n-2) is multiplied by h[i-1] h[i], which clears both slope
   //      divisions:  a = hm^2 hp,  b = 2 (hm+hp) hm hp,  c = hm hp^2,  r = 6 (dy[i] hm - dy[i-1] hp);
   //      the q recurrence needs a[i] c[i-1] = h[i-2] hm^4 hp.  hh[k] = x[i0+k-1] - x[i0+k-2], k = 0..9 ---------
-  double hh[SPL_R + 2], dy[SPL_R + 1];
-  {
-    const double xp = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yp = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
-    const double xpp = g > 0 ? xs[spl_pad(i0 - 2)] : qnan();
-    const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
-    hh[0] = xp - xpp;
-    hh[1] = xv[0] - xp; dy[0] = yv[0] - yp;
+  // The differences are formed from shared memory twice (before the scan and after it) instead of being kept in
+  // registers across the scan: the live set during the scan is then the two matrices only, which is what lets four
+  // CTAs share an SM without spilling.
+  auto load_diffs = [&](double (&hh)[SPL_R + 2], double (&dy)[SPL_R + 1]) {
+    double xl = g > 0 ? xs[spl_pad(i0 - 2)] : qnan();
+    double xc = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yc = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
+    hh[0] = xc - xl;
 #pragma unroll
-    for (int k = 1; k < SPL_R; ++k) { hh[k + 1] = xv[k] - xv[k - 1]; dy[k] = yv[k] - yv[k - 1]; }
-    hh[SPL_R + 1] = xn - xv[SPL_R - 1]; dy[SPL_R] = yn - yv[SPL_R - 1];
-  }
+    for (int k = 0; k <= SPL_R; ++k) {
+      const double xk = xs[spl_pad(i0 + k)], yk = ys[spl_pad(i0 + k)];
+      hh[k + 1] = xk - xc; dy[k] = yk - yc;
+      xc = xk; yc = yk;
+    }
+  };
   // row i0+j: hm = hh[j+1], hp = hh[j+2], h[i-2] = hh[j]
 
   // ---- forward: chunk transition matrix, prefix over the group ----------------------------------------------
   Mat3 P = mat_identity();
+  {
+    double hh[SPL_R + 2], dy[SPL_R + 1];
+    load_diffs(hh, dy);
 #pragma unroll
-  for (int j = 0; j < SPL_R; ++j) {
-    if (interior(j)) {
-      const double hm = hh[j + 1], hp = hh[j + 2], hmp = hm * hp;
-      const double a = hm * hmp, b = 2.0 * (hm + hp) * hmp, r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
-      const double ag = (i0 + j == 1) ? 0.0 : hh[j] * hm * hm * a;     // multiplies q[-1] = 0 in row 1
-      const double nA = b * P.A - ag * P.C, nB = b * P.B - ag * P.E;
-      const double nF = r * P.A - a * P.F, nG = r * P.B - a * P.G;
-      P.C = P.A; P.E = P.B; P.A = nA; P.B = nB; P.F = nF; P.G = nG; P.H = -a * P.H;
+    for (int j = 0; j < SPL_R; ++j) {
+      if (interior(j)) {
+        const double hm = hh[j + 1], hp = hh[j + 2], hmp = hm * hp;
+        const double a = hm * hmp, b = 2.0 * (hm + hp) * hmp, r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
+        const double ag = (i0 + j == 1) ? 0.0 : hh[j] * hm * hm * a;     // multiplies q[-1] = 0 in row 1
+        const double nA = b * P.A - ag * P.C, nB = b * P.B - ag * P.E;
+        const double nF = r * P.A - a * P.F, nG = r * P.B - a * P.G;
+        P.C = P.A; P.E = P.B; P.A = nA; P.B = nB; P.F = nF; P.G = nG; P.H = -a * P.H;
+      }
     }
   }
   mat_normalize(P);
@@ -329,6 +336,8 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
     q = nq * sc; qp = nqp * sc; D = nD * sc;
   }
   // ---- re-walk the rows from the exact incoming state: Thomas' c', d' ---------------------------------------
+  double hh[SPL_R + 2], dy[SPL_R + 1];
+  load_diffs(hh, dy);
 #pragma unroll
   for (int j = 0; j < SPL_R; ++j) {
     cv[j] = 0.0; dv[j] = 0.0;
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
 
   // ---- evaluate the grid points inside my segments ------------------------------------------------------------
   // the grid is sorted: thread g's points start at the first one >= x[i0] and end where thread g+1's start
-  qs[g] = (g == 0) ? 0 : ((i0 <= n - 2) ? lower_bound_q(xq, n_q, xv[0]) : n_q);
+  qs[g] = (g == 0) ? 0 : ((i0 <= n - 2) ? lower_bound_q(xq, n_q, xs[spl_pad(i0)]) : n_q);
   if (g == 0) qs[G] = n_q;
   group_sync<G>(grp);
   if (i0 > n - 2) return;
@@ -375,6 +384,8 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
   const bool owns_last = (n - 2) <= i0 + SPL_R - 1;
   const bool edge = g == 0 || owns_last;
+#pragma unroll
+  for (int j = 0; j < SPL_R; ++j) { xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)]; }   // reloaded, not kept across the scans
   int qi = qs[g];
   const int qhi = owns_last ? n_q : qs[g + 1];
 #pragma unroll
