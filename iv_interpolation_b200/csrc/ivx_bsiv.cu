@@ -40,6 +40,13 @@ __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * IN
 __device__ __forceinline__ double norm_pdf(double z) { return INV_SQRT_2PI * exp(-0.5 * z * z); }
 
 // ---- set-up helpers: cheaper than the general library routines on the ranges the solver feeds them ---------------
+// Polynomial coefficients live in constant memory: as immediates every fp64 coefficient costs two UMOV issue slots
+// next to the DFMA that uses it, and this kernel is bound by instruction issue (profiles/README.md).
+__constant__ double ATANH_C[10] = {1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0,
+                                   1.0 / 11.0, 1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
+__constant__ double EXP_C[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                 1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
+                                 1.0 / 6.0,          0.5,               1.0,              1.0};
 // ln a for a finite, positive, normal a: a = m 2^e with m in [1/sqrt2, sqrt2], ln m = 2 atanh((m-1)/(m+1)), |s| <= 0.172,
 // series to s^21 (truncation 6e-19).  ~1 ulp.
 __device__ __forceinline__ double log_normal(double a) {
@@ -48,24 +55,36 @@ __device__ __forceinline__ double log_normal(double a) {
   double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));   // [1, 2)
   if (m > SQRT2) { m *= 0.5; e += 1; }
   const double s = (m - 1.0) / (m + 1.0), s2 = s * s;
-  double p = 1.0 / 21.0;
-  p = fma(p, s2, 1.0 / 19.0); p = fma(p, s2, 1.0 / 17.0); p = fma(p, s2, 1.0 / 15.0); p = fma(p, s2, 1.0 / 13.0);
-  p = fma(p, s2, 1.0 / 11.0); p = fma(p, s2, 1.0 / 9.0); p = fma(p, s2, 1.0 / 7.0); p = fma(p, s2, 1.0 / 5.0);
-  p = fma(p, s2, 1.0 / 3.0);
+  double p = ATANH_C[0];
+#pragma unroll
+  for (int k = 1; k < 10; ++k) p = fma(p, s2, ATANH_C[k]);
   const double l = fma(2.0 * s * s2, p, 2.0 * s);
   const double ed = (double)e;
   return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, l));   // ln2 split hi + lo
 }
-// e^{-z} for |z| <= 1/4 (discount factors): Taylor to z^13 (truncation 4e-20); the library exp elsewhere
+// e^{w} for |w| <= 0.35: Taylor to w^13 (truncation 2e-18 at ln2/2)
+__device__ __forceinline__ double exp_poly(double w) {
+  double p = EXP_C[0];
+#pragma unroll
+  for (int k = 1; k < 14; ++k) p = fma(p, w, EXP_C[k]);
+  return p;
+}
+// e^{-z} for |z| <= 1/4 (discount factors); the library exp elsewhere
 __device__ __forceinline__ double exp_neg_small(double z) {
   if (!(fabs(z) <= 0.25)) return exp(-z);
-  const double w = -z;
-  double p = 1.0 / 6227020800.0;
-  p = fma(p, w, 1.0 / 479001600.0); p = fma(p, w, 1.0 / 39916800.0); p = fma(p, w, 1.0 / 3628800.0);
-  p = fma(p, w, 1.0 / 362880.0); p = fma(p, w, 1.0 / 40320.0); p = fma(p, w, 1.0 / 5040.0); p = fma(p, w, 1.0 / 720.0);
-  p = fma(p, w, 1.0 / 120.0); p = fma(p, w, 1.0 / 24.0); p = fma(p, w, 1.0 / 6.0); p = fma(p, w, 0.5);
-  p = fma(p, w, 1.0);
-  return fma(p, w, 1.0);
+  return exp_poly(-z);
+}
+// e^{-z} for 0 <= z <= 700: z = n ln2 + r, |r| <= ln2/2, e^{-z} = 2^{-n} e^{-r}; the library exp outside that range
+__device__ __forceinline__ double exp_neg(double z) {
+  if (!(z >= 0.0 && z <= 700.0)) return exp(-z);
+  const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52: the low word of z*log2e + MAGIC is rint(z*log2e)
+  const double tn = fma(z, 1.4426950408889634, MAGIC);
+  const int n = __double2loint(tn);
+  const double nd = tn - MAGIC;
+  double r = fma(nd, -6.93147180369123816490e-01, z);
+  r = fma(nd, -1.90821492927058770002e-10, r);
+  const double pw = exp_poly(-r);
+  return pw * __hiloint2double((1023 - n) << 20, 0);
 }
 
 // erfcx(x) for x >= 0 in single precision: (1 + 2x) erfcx(x) is smooth in t = (x-2)/(x+2) on [-1, 1);
@@ -136,9 +155,11 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
       A = r2 - d1;
       B = r3 - 3.0f * r2 * d1 + 2.0f * d1 * d1;
     } else {
-      const float b = 0.5f * (ex2 * erfcf((h - t) * kInvSqrt2) - iex2 * erfcf((h + t) * kInvSqrt2));
+      // same identity as the fp64 polish: b = e^{x/2} - E/2 [erfcx((t-h)/sqrt2) + erfcx((t+h)/sqrt2)], E = e^{-(h^2+t^2)/2}
+      const float E = __expf(-0.5f * (h * h + t * t));
+      const float b = ex2 - 0.5f * E * (erfcx_pos_f(fmaxf(t - h, 0.0f) * kInvSqrt2) + erfcx_pos_f((h + t) * kInvSqrt2));
       g = b - beta;
-      newton = -g * kSqrt2Pi * __expf(0.5f * (h * h + t * t));
+      newton = __fdividef(-g * kSqrt2Pi, E);
       A = r2; B = r3;
     }
     if (g > 0.0f) hi = s; else lo = s;
@@ -154,46 +175,52 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
 // erfcx(q1), erfcx(q2) for q1, q2 >= 0 with ONE division: (1 + 2q) erfcx(q) is smooth in t = (q-4)/(q+4) on [-1, 1)
 // (degree-24 fit, 3.5 ulp; own Chebyshev interpolation against mpmath at 50 digits), and the four reciprocals
 // 1/(q+4), 1/(1+2q) are peeled off one reciprocal of their product.  The two Horner chains interleave.
+__constant__ double ERFCX_C[25] = {
+    -2.764120233734578e-10,
+    9.297625263709659e-10,
+    3.2323973445082033e-09,
+    -1.2338731403798444e-08,
+    -2.0725802488181963e-08,
+    1.0631817593818149e-07,
+    7.771943241086912e-08,
+    -8.210647933297337e-07,
+    2.9173425573089733e-07,
+    5.70657829924074e-06,
+    -1.1221135665965907e-05,
+    -2.4397731143023292e-05,
+    0.00015062142608651945,
+    -0.0001992571524726518,
+    -0.0007577732435942576,
+    0.005031970069102256,
+    -0.01619773406293477,
+    0.037167515526338006,
+    -0.06633036581186058,
+    0.09373283499911264,
+    -0.10103906603631811,
+    0.06809705425466839,
+    0.015379652102619974,
+    -0.13962111684056228,
+    1.2329951186255526};
+
 __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1, double& e2) {
   const double a1 = q1 + 4.0, a2 = q2 + 4.0, b1 = fma(2.0, q1, 1.0), b2 = fma(2.0, q2, 1.0);
   const double aa = a1 * a2, bb = b1 * b2;
   const double r = 1.0 / (aa * bb);
   const double ra = r * bb, rb = r * aa;             // 1/(a1 a2), 1/(b1 b2)
   const double t1 = (q1 - 4.0) * (ra * a2), t2 = (q2 - 4.0) * (ra * a1);
-  double p1 = -2.764120233734578e-10, p2 = -2.764120233734578e-10;
-  p1 = fma(p1, t1, 9.297625263709659e-10); p2 = fma(p2, t2, 9.297625263709659e-10);
-  p1 = fma(p1, t1, 3.2323973445082033e-09); p2 = fma(p2, t2, 3.2323973445082033e-09);
-  p1 = fma(p1, t1, -1.2338731403798444e-08); p2 = fma(p2, t2, -1.2338731403798444e-08);
-  p1 = fma(p1, t1, -2.0725802488181963e-08); p2 = fma(p2, t2, -2.0725802488181963e-08);
-  p1 = fma(p1, t1, 1.0631817593818149e-07); p2 = fma(p2, t2, 1.0631817593818149e-07);
-  p1 = fma(p1, t1, 7.771943241086912e-08); p2 = fma(p2, t2, 7.771943241086912e-08);
-  p1 = fma(p1, t1, -8.210647933297337e-07); p2 = fma(p2, t2, -8.210647933297337e-07);
-  p1 = fma(p1, t1, 2.9173425573089733e-07); p2 = fma(p2, t2, 2.9173425573089733e-07);
-  p1 = fma(p1, t1, 5.70657829924074e-06); p2 = fma(p2, t2, 5.70657829924074e-06);
-  p1 = fma(p1, t1, -1.1221135665965907e-05); p2 = fma(p2, t2, -1.1221135665965907e-05);
-  p1 = fma(p1, t1, -2.4397731143023292e-05); p2 = fma(p2, t2, -2.4397731143023292e-05);
-  p1 = fma(p1, t1, 0.00015062142608651945); p2 = fma(p2, t2, 0.00015062142608651945);
-  p1 = fma(p1, t1, -0.0001992571524726518); p2 = fma(p2, t2, -0.0001992571524726518);
-  p1 = fma(p1, t1, -0.0007577732435942576); p2 = fma(p2, t2, -0.0007577732435942576);
-  p1 = fma(p1, t1, 0.005031970069102256); p2 = fma(p2, t2, 0.005031970069102256);
-  p1 = fma(p1, t1, -0.01619773406293477); p2 = fma(p2, t2, -0.01619773406293477);
-  p1 = fma(p1, t1, 0.037167515526338006); p2 = fma(p2, t2, 0.037167515526338006);
-  p1 = fma(p1, t1, -0.06633036581186058); p2 = fma(p2, t2, -0.06633036581186058);
-  p1 = fma(p1, t1, 0.09373283499911264); p2 = fma(p2, t2, 0.09373283499911264);
-  p1 = fma(p1, t1, -0.10103906603631811); p2 = fma(p2, t2, -0.10103906603631811);
-  p1 = fma(p1, t1, 0.06809705425466839); p2 = fma(p2, t2, 0.06809705425466839);
-  p1 = fma(p1, t1, 0.015379652102619974); p2 = fma(p2, t2, 0.015379652102619974);
-  p1 = fma(p1, t1, -0.13962111684056228); p2 = fma(p2, t2, -0.13962111684056228);
-  p1 = fma(p1, t1, 1.2329951186255526); p2 = fma(p2, t2, 1.2329951186255526);
+  double p1 = ERFCX_C[0], p2 = ERFCX_C[0];
+#pragma unroll
+  for (int k = 1; k < 25; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }   // operands straight from the constant bank
   e1 = p1 * (rb * b2);
   e2 = p2 * (rb * b1);
 }
 
 // lower: g = ln b - ln beta = ln(b / beta), one logarithm per evaluation: inv_beta = 1/beta, lnbeta_off = 0
 // (for beta below 1e-290, where 1/beta is not finite, inv_beta = 1 and lnbeta_off = ln beta)
-__device__ __forceinline__ double polish_f64(double x, double beta, double inv_beta, double lnbeta_off, double ex2, double iex2,
+__device__ __forceinline__ double polish_f64(double x, double beta, double inv_beta, double lnbeta_off, double ex2,
                                              bool lower, double s, int& iters) {
   double lo = 0.0, hi = S_MAX;
+  const double tvc = ex2 - beta;                     // > 0: what the price lacks to its s -> inf limit
   bool done = false;
   int it = 0;
   while (true) {
@@ -213,15 +240,30 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double inv_b
         g = ((arg >= 2.3e-308 && arg <= 1e300) ? log_normal(arg) : log(arg)) - e - lnbeta_off;
         newton = -g * D * (0.5 * SQRT_2PI);
         den = 1.0 + 0.5 * newton * r2 + 0.5 * g;
+        if (!(den > 0.5 && den < 2.0)) den = 1.0;
       } else {
-        const double b = 0.5 * (ex2 * erfc((h - t) * INV_SQRT2) - iex2 * erfc((h + t) * INV_SQRT2));
-        g = b - beta;
-        newton = -g * SQRT_2PI * exp(e);
-        den = 1.0 + 0.5 * newton * r2;
+        // above the inflection point t > h:  Phi(t-h) = 1 - erfc((t-h)/sqrt2)/2, and both e^{+-x/2} e^{-q^2} collapse to
+        // E = e^{-e}  =>  b = e^{x/2} - E/2 [erfcx((t-h)/sqrt2) + erfcx((t+h)/sqrt2)]: one exp, no library erfc
+        const double q1 = (t - h) * INV_SQRT2, q2 = (h + t) * INV_SQRT2;
+        if (q1 >= 0.0 && q2 < 1e70) {
+          double e1, e2;
+          erfcx_pair_pos(q1, q2, e1, e2);
+          const double E = exp_neg(e);
+          g = tvc - 0.5 * E * (e1 + e2);
+          newton = -g * SQRT_2PI;                      // times 1/E, folded into the one division below
+          den = fma(0.5 * newton, r2, E);
+          if (!(den > 0.5 * E && den < 2.0 * E)) den = E;
+                  } else {                                       // s undershot the inflection point
+          const double b = 0.5 * (ex2 * erfc(-q1) - erfc(q2) / ex2);
+          g = b - beta;
+          newton = -g * SQRT_2PI * exp(e);
+          den = 1.0 + 0.5 * newton * r2;
+          if (!(den > 0.5 && den < 2.0)) den = 1.0;
+        }
       }
       ++it;
       if (g > 0.0) hi = s; else lo = s;
-      double step = (den > 0.5 && den < 2.0) ? newton / den : newton;
+      double step = newton / den;
       double sn = s + step;
       const bool safe = (sn >= lo) && (sn <= hi) && (sn > 0.0);          // false for NaN
       if (!safe) { sn = 0.5 * (lo + hi); step = sn - s; }
@@ -248,17 +290,20 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   ok = ok && (target > 0.0);
   // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}
   const double mx = fmax(s_, kd), mn = fmin(s_, kd);
-  const double ratio = ok ? mn / mx : 0.9;
-  // ratio is in (0, 1]; below the normal range the library log takes over
-  double x = PRE_X ? -fabs(x_pre) : (ratio >= 2.3e-308 ? log_normal(ratio) : log(ratio));
-  double ex2 = sqrt(ratio);
-  double beta = ok ? target / (mx * ex2) : 0.05;
+  // one reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta
+  const double rmx = 1.0 / mx;
+  double ratio = ok ? mn * rmx : 0.9;
+  if (!(ratio >= 2.3e-308)) { ok = false; ratio = 0.9; }          // S/Kd beyond 1e308: nothing to solve
+  const double rsq = rsqrt(ratio);
+  // ratio is in (0, 1]
+  double x = PRE_X ? -fabs(x_pre) : log_normal(ratio);
+  double ex2 = ratio * rsq;
+  double beta = ok ? (target * rmx) * rsq : 0.05;
   if (ok && !(beta < ex2)) ok = false;                           // rounding pushed it onto the bound
   if (!ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9: solved alongside, result dropped
-  const double iex2 = 1.0 / ex2;
 
   const float xf = (float)x;
-  const float ex2f = (float)ex2, iex2f = (float)iex2;
+  const float ex2f = (float)ex2, iex2f = __fdividef(1.0f, ex2f);
   const float s_cf = sqrtf(-2.0f * xf);
   // b(s_c) = (e^{x/2} - e^{-x/2} erfc(sqrt|x|)) / 2 and erfc(z) = erfcx(z) e^{-z^2} with e^{-|x|} = (e^{x/2})^2
   const float b_cf = 0.5f * ex2f * (1.0f - erfcx_pos_f(s_cf * 0.70710678f));
@@ -275,7 +320,7 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
     if (beta < 1e-290) lnbeta_off = log(beta); else inv_beta = 1.0 / beta;
   }
   int it = 0;
-  s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, iex2, lower, s, it);
+  s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, lower, s, it);
   sigma_out = ok ? s * rsqrt(t_) : qnan();
   iters_out = ok ? it : 0;
 }
