@@ -27,7 +27,6 @@
 namespace ivx {
 namespace {
 
-constexpr double SQRT2 = 1.4142135623730951;
 constexpr double INV_SQRT2 = 0.7071067811865476;
 constexpr double SQRT_2PI = 2.5066282746310002;
 constexpr double INV_SQRT_2PI = 0.3989422804014327;
@@ -42,25 +41,116 @@ __device__ __forceinline__ double norm_pdf(double z) { return INV_SQRT_2PI * exp
 // ---- set-up helpers: cheaper than the general library routines on the ranges the solver feeds them ---------------
 // Polynomial coefficients live in constant memory: as immediates every fp64 coefficient costs two UMOV issue slots
 // next to the DFMA that uses it, and this kernel is bound by instruction issue (profiles/README.md).
-__constant__ double ATANH_C[10] = {1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0,
-                                   1.0 / 11.0, 1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
 __constant__ double EXP_C[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
                                  1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
                                  1.0 / 6.0,          0.5,               1.0,              1.0};
-// ln a for a finite, positive, normal a: a = m 2^e with m in [1/sqrt2, sqrt2], ln m = 2 atanh((m-1)/(m+1)), |s| <= 0.172,
-// series to s^21 (truncation 6e-19).  ~1 ulp.
+// Reciprocal and reciprocal square root of a NORMAL a (1e-300 < a < 1e300) without the IEEE special-case tail of the
+// compiler's division: the 20-bit hardware seed (MUFU.RCP64H / RSQ64H) and two Newton steps (2^-20 -> 2^-40 -> 2^-80).
+__device__ __forceinline__ double rcp_fast(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double rcp_fast1(double a) {   // one Newton step: 2^-40
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  return fma(y, fma(-a, y, 1.0), y);
+}
+__device__ __forceinline__ double rsqrt_fast(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-(a * y), y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-(a * y), y, 1.0);
+  return fma(0.5 * y, fma(0.375 * e, e, e), y);      // y (1 + e/2 + 3 e^2/8)
+}
+// positive, finite and normal: high word in [0x00100000, 0x7ff00000)
+__device__ __forceinline__ bool pos_normal(double v) { return (unsigned)(__double2hiint(v) - 0x00100000) < 0x7fe00000u; }
+
+// ln a for a finite, positive, normal a: a = m 2^e, m in [1, 2); the top six mantissa bits pick c_j = 1 + (j + 1/2)/64 from a
+// table of {rc_j ~ 1/c_j, -ln rc_j}; u = m rc_j - 1 is exact to 2^-60 in one fma, |u| < 2^-7, and ln(1+u) is its series to
+// u^8 (remainder 1e-20).  No division.  Absolute error ~1e-16 (the result is a log-moneyness, used to that accuracy).
+__device__ const double2 LOG_TAB[64] = {
+    {0.9922480620155039, 0.007782140442054963},
+    {0.9770992366412213, 0.023167059281534418},
+    {0.9624060150375939, 0.03831886430213666},
+    {0.9481481481481482, 0.05324451451881224},
+    {0.9343065693430657, 0.06795066190850778},
+    {0.920863309352518, 0.08244366921107454},
+    {0.9078014184397163, 0.09672962645855114},
+    {0.8951048951048951, 0.11081436634029011},
+    {0.8827586206896552, 0.12470347850095725},
+    {0.8707482993197279, 0.1384023228591192},
+    {0.8590604026845637, 0.151916042025842},
+    {0.847682119205298, 0.16524957289530717},
+    {0.8366013071895425, 0.17840765747281825},
+    {0.8258064516129032, 0.19139485299962947},
+    {0.8152866242038217, 0.20421554142869083},
+    {0.8050314465408805, 0.2168739383006143},
+    {0.7950310559006211, 0.2293741010648459},
+    {0.7852760736196319, 0.24171993688714513},
+    {0.7757575757575758, 0.25391520998096345},
+    {0.7664670658682635, 0.2659635484971379},
+    {0.757396449704142, 0.2778684510034563},
+    {0.7485380116959064, 0.2896332925830427},
+    {0.7398843930635838, 0.30126133057816185},
+    {0.7314285714285714, 0.3127557100038969},
+    {0.7231638418079096, 0.324119468654212},
+    {0.7150837988826816, 0.3353555419211378},
+    {0.7071823204419889, 0.3464667673462086},
+    {0.6994535519125683, 0.3574558889218038},
+    {0.6918918918918919, 0.36832556115870757},
+    {0.6844919786096256, 0.3790783529349695},
+    {0.6772486772486772, 0.38971675114002524},
+    {0.6701570680628273, 0.40024316412701266},
+    {0.6632124352331606, 0.4106599249852683},
+    {0.6564102564102564, 0.42096929464412963},
+    {0.649746192893401, 0.43117346481837143},
+    {0.6432160804020101, 0.4412745608048752},
+    {0.6368159203980099, 0.4512746441394586},
+    {0.6305418719211823, 0.46117571512217015},
+    {0.624390243902439, 0.470979715218791},
+    {0.6183574879227053, 0.48068852934575196},
+    {0.6124401913875598, 0.4903039880451939},
+    {0.6066350710900474, 0.49982786955644926},
+    {0.6009389671361502, 0.5092619017898079},
+    {0.5953488372093023, 0.5186077642080457},
+    {0.5898617511520737, 0.5278670896208424},
+    {0.5844748858447488, 0.5370414658968837},
+    {0.579185520361991, 0.5461324375981356},
+    {0.5739910313901345, 0.5551415075405016},
+    {0.5688888888888889, 0.564070138284803},
+    {0.5638766519823789, 0.5729197535617854},
+    {0.5589519650655022, 0.5816917396346225},
+    {0.5541125541125541, 0.5903874466021763},
+    {0.5493562231759657, 0.5990081896460834},
+    {0.5446808510638298, 0.6075552502245418},
+    {0.540084388185654, 0.616029877215514},
+    {0.5355648535564853, 0.6244332880118936},
+    {0.5311203319502075, 0.6327666695710378},
+    {0.5267489711934157, 0.6410311794209312},
+    {0.5224489795918368, 0.6492279466251097},
+    {0.5182186234817814, 0.65735807270836},
+    {0.5140562248995983, 0.6654226325450905},
+    {0.5099601593625498, 0.6734226752121667},
+    {0.5059288537549407, 0.6813592248079031},
+    {0.5019607843137255, 0.689233281238809}};
+__constant__ double LOG1P_C[7] = {-1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5};
 __device__ __forceinline__ double log_normal(double a) {
-  int hi = __double2hiint(a);
-  int e = (hi >> 20) - 1023;
-  double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));   // [1, 2)
-  if (m > SQRT2) { m *= 0.5; e += 1; }
-  const double s = (m - 1.0) / (m + 1.0), s2 = s * s;
-  double p = ATANH_C[0];
+  const int hi = __double2hiint(a);
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));   // [1, 2)
+  const double2 tb = __ldg(&LOG_TAB[(hi >> 14) & 63]);
+  const double u = fma(m, tb.x, -1.0);
+  double p = LOG1P_C[0];
 #pragma unroll
-  for (int k = 1; k < 10; ++k) p = fma(p, s2, ATANH_C[k]);
-  const double l = fma(2.0 * s * s2, p, 2.0 * s);
+  for (int k = 1; k < 7; ++k) p = fma(p, u, LOG1P_C[k]);
+  const double l = fma(u * u, p, u);
   const double ed = (double)e;
-  return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, l));   // ln2 split hi + lo
+  return fma(ed, 6.93147180369123816490e-01, tb.y + fma(ed, 1.90821492927058770002e-10, l));   // ln2 split hi + lo
 }
 // e^{w} for |w| <= 0.35: Taylor to w^13 (truncation 2e-18 at ln2/2)
 __device__ __forceinline__ double exp_poly(double w) {
@@ -205,7 +295,7 @@ __constant__ double ERFCX_C[25] = {
 __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1, double& e2) {
   const double a1 = q1 + 4.0, a2 = q2 + 4.0, b1 = fma(2.0, q1, 1.0), b2 = fma(2.0, q2, 1.0);
   const double aa = a1 * a2, bb = b1 * b2;
-  const double r = 1.0 / (aa * bb);
+  const double r = rcp_fast(aa * bb);               // q < 1e70: the product is normal
   const double ra = r * bb, rb = r * aa;             // 1/(a1 a2), 1/(b1 b2)
   const double t1 = (q1 - 4.0) * (ra * a2), t2 = (q2 - 4.0) * (ra * a1);
   double p1 = ERFCX_C[0], p2 = ERFCX_C[0];
@@ -225,7 +315,7 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double inv_b
   int it = 0;
   while (true) {
     if (!done) {
-      const double inv_s = 1.0 / s;
+      const double inv_s = rcp_fast(s);              // s >= 1e-45 2^-64: normal
       const double h = -x * inv_s, t = 0.5 * s;      // h >= 0
       const double r2 = h * h * inv_s - 0.25 * s;
       const double e = 0.5 * (h * h + t * t);
@@ -237,7 +327,13 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double inv_b
         else { e1 = erfcx(q1); e2 = erfcx(q2); }      // s overshot the inflection point (q1 < 0), or absurd inputs
         const double D = e1 - e2;
         const double arg = 0.5 * D * inv_beta;
-        g = ((arg >= 2.3e-308 && arg <= 1e300) ? log_normal(arg) : log(arg)) - e - lnbeta_off;
+        // ln(b/beta) with b/beta = arg e^{-e} = 1 + dl: after the pre-solve dl is ~1e-5, and ln(1+dl) is its series
+        // (dl^6/6 < 1e-17 below 2e-3) — an exponential instead of a logarithm, and no cancellation against ln beta
+        const double dl = fma(arg, exp_neg(e), -1.0);
+        if (fabs(dl) < 2e-3 && lnbeta_off == 0.0)
+          g = dl * fma(dl, fma(dl, fma(dl, fma(dl, 0.2, -0.25), 1.0 / 3.0), -0.5), 1.0);
+        else
+          g = log(arg) - e - lnbeta_off;
         newton = -g * D * (0.5 * SQRT_2PI);
         den = 1.0 + 0.5 * newton * r2 + 0.5 * g;
         if (!(den > 0.5 && den < 2.0)) den = 1.0;
@@ -263,7 +359,7 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double inv_b
       }
       ++it;
       if (g > 0.0) hi = s; else lo = s;
-      double step = newton / den;
+      double step = newton * rcp_fast1(den);         // the step is ~1e-5 s: 2^-40 relative is ample; a flushed den gives NaN -> bisection
       double sn = s + step;
       const bool safe = (sn >= lo) && (sn <= hi) && (sn > 0.0);          // false for NaN
       if (!safe) { sn = 0.5 * (lo + hi); step = sn - s; }
@@ -282,24 +378,33 @@ __device__ __forceinline__ double polish_f64(double x, double beta, double inv_b
 template <bool PRE_X>
 __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double kd, double t_, bool call, double x_pre,
                                             double& sigma_out, int& iters_out) {
-  const double intrinsic = call ? (s_ - kd) : (kd - s_);
-  const double lower_bound = fmax(intrinsic, 0.0);
+  // ok: S, Kd and T are positive normal numbers (no NaN below).  mx/mn = max/min(S, Kd); the in-the-money side is the
+  // call when S > Kd, the put when S < Kd, and its intrinsic value is mx - mn.
+  const bool sg = s_ > kd;
+  const double mx = ok ? (sg ? s_ : kd) : 1.0, mn = ok ? (sg ? kd : s_) : 0.9;
+  const double diff = mx - mn;
+  const bool itm = (call == sg);
+  const double lower_bound = itm ? diff : 0.0;
   const double upper_bound = call ? s_ : kd;
-  ok = ok && (p > lower_bound) && (p < upper_bound);
-  const double target = intrinsic > 0.0 ? p - intrinsic : p;    // the out-of-the-money twin
-  ok = ok && (target > 0.0);
-  // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}
-  const double mx = fmax(s_, kd), mn = fmin(s_, kd);
-  // one reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta
-  const double rmx = 1.0 / mx;
-  double ratio = ok ? mn * rmx : 0.9;
-  if (!(ratio >= 2.3e-308)) { ok = false; ratio = 0.9; }          // S/Kd beyond 1e308: nothing to solve
-  const double rsq = rsqrt(ratio);
-  // ratio is in (0, 1]
-  double x = PRE_X ? -fabs(x_pre) : log_normal(ratio);
+  ok = ok && (p > lower_bound) && (p < upper_bound);               // false for NaN prices
+  const double target = ok ? (itm ? p - diff : p) : 0.04;          // the out-of-the-money twin, > 0
+  // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}, beta = target / sqrt(S Kd).
+  // One reciprocal (of target * max) and one reciprocal square root serve ratio, e^{x/2}, beta and 1/beta.
+  const double prod = target * mx;
+  double rmx, rtg;
+  if (prod >= 1e-290 && prod <= 1e290) {
+    const double R = rcp_fast(prod);
+    rmx = R * target; rtg = R * mx;
+  } else {
+    rmx = 1.0 / mx; rtg = 1.0 / target;
+  }
+  double ratio = mn * rmx;                                         // (0, 1]
+  if (!(ratio >= 2.3e-308)) { ok = false; ratio = 0.9; }           // S/Kd beyond 1e308: nothing to solve
+  const double rsq = rsqrt_fast(ratio);
+  double x = PRE_X ? -fabs(x_pre) : (ratio == 1.0 ? 0.0 : log_normal(ratio));
   double ex2 = ratio * rsq;
-  double beta = ok ? (target * rmx) * rsq : 0.05;
-  if (ok && !(beta < ex2)) ok = false;                           // rounding pushed it onto the bound
+  double beta = (target * rmx) * rsq;
+  if (ok && !(beta < ex2)) ok = false;                             // rounding pushed it onto the bound
   if (!ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9: solved alongside, result dropped
 
   const float xf = (float)x;
@@ -315,13 +420,11 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   float s0 = presolve_f32(xf, (float)beta, lnbeta_f, ex2f, iex2f, s_cf, b_cf, lower);
   double s = (double)s0;
   if (!(s > 0.0 && s < S_MAX)) s = 1.0;   // fp32 range exhausted: the bracketed fp64 loop takes it from anywhere
-  double inv_beta = 1.0, lnbeta_off = 0.0;
-  if (lower) {
-    if (beta < 1e-290) lnbeta_off = log(beta); else inv_beta = 1.0 / beta;
-  }
+  double inv_beta = ok ? (rtg * mx) * ex2 : 20.0, lnbeta_off = 0.0;     // sqrt(S Kd) / target
+  if (beta < 1e-290) { lnbeta_off = log(beta); inv_beta = 1.0; }
   int it = 0;
   s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, lower, s, it);
-  sigma_out = ok ? s * rsqrt(t_) : qnan();
+  sigma_out = ok ? s * rsqrt_fast(t_) : qnan();
   iters_out = ok ? it : 0;
 }
 
@@ -340,8 +443,8 @@ __global__ void __launch_bounds__(256, 5) k_bs_implied_vol(int64_t n, const doub
     t_ = ld_stream(T + i); r_ = ld_stream(r + i); call = is_call[i] != 0;
   }
   const double kd = k_ * exp_neg_small(r_ * t_);
-  const bool ok = inr && isfinite(p) && isfinite(s_) && isfinite(k_) && isfinite(t_) && isfinite(r_) &&
-                  (s_ > 0.0) && (k_ > 0.0) && (t_ > 0.0);
+  // S, K, T and Kd positive, finite and normal (a NaN or infinite r shows in Kd); the price is checked against its bounds
+  const bool ok = inr && pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
   double out;
   int it;
   solve_quote<false>(ok, p, s_, kd, t_, call, 0.0, out, it);
@@ -397,8 +500,7 @@ __global__ void __launch_bounds__(256, 5) k_bs_implied_vol_chain(int64_t t0, int
     xi = (lnS - lnK) + rt;                                         // ln(S / (K e^{-rT}))
   }
   const double kd = k_ * disc;
-  const bool ok = inr && isfinite(p) && isfinite(s_) && isfinite(k_) && isfinite(t_) && isfinite(disc) &&
-                  (s_ > 0.0) && (k_ > 0.0) && (t_ > 0.0) && isfinite(xi);
+  const bool ok = inr && pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd) && isfinite(xi);
   double out;
   int it;
   solve_quote<true>(ok, p, s_, kd, t_, call, xi, out, it);
