@@ -177,10 +177,20 @@ __device__ __forceinline__ double exp_neg(double z) {
   return pw * __hiloint2double((1023 - n) << 20, 0);
 }
 
+// single-precision MUFU operations without the denormal-range fix-ups the compiler wraps around __fdividef, __logf,
+// __expf, sqrtf and rsqrtf (flush-to-zero is fine here: the pre-solve only has to land near the root)
+__device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_rsq(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_log(float x) { return 0.69314718f * f_lg2(x); }
+__device__ __forceinline__ float f_exp(float x) { return f_ex2(1.44269504f * x); }
+
 // erfcx(x) for x >= 0 in single precision: (1 + 2x) erfcx(x) is smooth in t = (x-2)/(x+2) on [-1, 1);
 // degree-9 fit, 5e-7 relative (own Chebyshev fit against scipy.special.erfcx) — 16 instructions.
 __device__ __forceinline__ float erfcx_pos_f(float x) {
-  const float t = __fdividef(x - 2.0f, x + 2.0f);
+  const float t = (x - 2.0f) * f_rcp(x + 2.0f);
   float p = -1.836544373e-04f;
   p = fmaf(p, t, -9.936979918e-04f);
   p = fmaf(p, t, 1.043144582e-03f);
@@ -191,7 +201,7 @@ __device__ __forceinline__ float erfcx_pos_f(float x) {
   p = fmaf(p, t, -1.660467991e-01f);
   p = fmaf(p, t, -9.276308205e-02f);
   p = fmaf(p, t, 1.276978705e+00f);
-  return __fdividef(p, fmaf(2.0f, x, 1.0f));
+  return p * f_rcp(fmaf(2.0f, x, 1.0f));
 }
 
 // ---- phase 1: single precision -------------------------------------------------------------------------
@@ -207,11 +217,11 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
     //   s_lo = |x| / sqrt(2 ln(b_c/beta) + |x|/2),
     // the tangent at s_c overshoots (b is convex below s_c).  The root sits at s_lo^(1-w) s_tan^w with w a tight
     // function of ln(beta/b_c) alone (fitted on 1e6 quotes: |w - fit| < 0.04 rms) -> 2 % median, 12 % p99 error.
-    const float lr = lnbeta - __logf(b_c);
-    const float s_lo = -x * rsqrtf(-2.0f * lr - 0.5f * x);
+    const float lr = lnbeta - f_log(b_c);
+    const float s_lo = -x * f_rsq(-2.0f * lr - 0.5f * x);
     s = s_lo;
     if (s_tan > s_lo && s_lo > 0.0f) {
-      const float z = __fdividef(4.0f, 4.0f - lr);
+      const float z = 4.0f * f_rcp(4.0f - lr);
       float w = 16.8094143f;
       w = fmaf(w, z, -43.9016092f);
       w = fmaf(w, z, 37.3072543f);
@@ -219,7 +229,7 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
       w = fmaf(w, z, 1.71174781f);
       w = fmaf(w, z, -0.0284488434f);
       w = fminf(fmaxf(w, 0.0f), 1.0f);
-      s = s_lo * __expf(w * __logf(__fdividef(s_tan, s_lo)));
+      s = s_lo * f_ex2(w * f_lg2(s_tan * f_rcp(s_lo)));
     }
   } else {
     lo = s_c; hi = (float)S_MAX;
@@ -228,7 +238,7 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
   if (!(s > lo && s < hi)) s = 0.5f * (lo + hi);
 #pragma unroll
   for (int it = 0; it < PRE_ITERS; ++it) {
-    const float inv_s = __fdividef(1.0f, s);
+    const float inv_s = f_rcp(s);
     const float h = -x * inv_s, t = 0.5f * s;        // h >= 0
     const float hs = h * inv_s;
     const float r2 = h * hs - 0.25f * s;              // b2/b1: second over first derivative of b
@@ -238,22 +248,24 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
     float g, newton, A, B;
     if (lower) {
       const float q1 = (h - t) * kInvSqrt2;           // < 0 only if s overshot the inflection point
-      const float D = (q1 >= 0.0f ? erfcx_pos_f(q1) : erfcxf(q1)) - erfcx_pos_f((h + t) * kInvSqrt2);
-      g = -0.5f * (h * h + t * t) + __logf(0.5f * D) - lnbeta;
+      float e1 = erfcx_pos_f(fabsf(q1));
+      if (q1 < 0.0f) e1 = 2.0f * f_exp(q1 * q1) - e1;   // erfcx(-a) = 2 e^{a^2} - erfcx(a)
+      const float D = e1 - erfcx_pos_f((h + t) * kInvSqrt2);
+      g = -0.5f * (h * h + t * t) + f_log(0.5f * D) - lnbeta;
       newton = -g * D * (0.5f * kSqrt2Pi);           // -g / d1,  d1 = (ln b)' = 2 / (sqrt(2 pi) D)
-      const float d1 = __fdividef(2.0f / kSqrt2Pi, D);
+      const float d1 = (2.0f / kSqrt2Pi) * f_rcp(D);
       A = r2 - d1;
       B = r3 - 3.0f * r2 * d1 + 2.0f * d1 * d1;
     } else {
       // same identity as the fp64 polish: b = e^{x/2} - E/2 [erfcx((t-h)/sqrt2) + erfcx((t+h)/sqrt2)], E = e^{-(h^2+t^2)/2}
-      const float E = __expf(-0.5f * (h * h + t * t));
+      const float E = f_exp(-0.5f * (h * h + t * t));
       const float b = ex2 - 0.5f * E * (erfcx_pos_f(fmaxf(t - h, 0.0f) * kInvSqrt2) + erfcx_pos_f((h + t) * kInvSqrt2));
       g = b - beta;
-      newton = __fdividef(-g * kSqrt2Pi, E);
+      newton = (-g * kSqrt2Pi) * f_rcp(E);
       A = r2; B = r3;
     }
     if (g > 0.0f) hi = s; else lo = s;
-    const float fac = __fdividef(fmaf(0.5f * A, newton, 1.0f), fmaf(newton, fmaf(B * (1.0f / 6.0f), newton, A), 1.0f));
+    const float fac = fmaf(0.5f * A, newton, 1.0f) * f_rcp(fmaf(newton, fmaf(B * (1.0f / 6.0f), newton, A), 1.0f));
     float sn = s + ((fac > 0.3f && fac < 3.0f) ? newton * fac : newton);
     if (!(sn >= lo && sn <= hi && sn > 0.0f)) sn = 0.5f * (lo + hi);   // also catches NaN
     s = sn;
@@ -408,15 +420,15 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   if (!ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9: solved alongside, result dropped
 
   const float xf = (float)x;
-  const float ex2f = (float)ex2, iex2f = __fdividef(1.0f, ex2f);
-  const float s_cf = sqrtf(-2.0f * xf);
+  const float ex2f = (float)ex2, iex2f = f_rcp(ex2f);
+  const float s_cf = f_sqrt(-2.0f * xf);
   // b(s_c) = (e^{x/2} - e^{-x/2} erfc(sqrt|x|)) / 2 and erfc(z) = erfcx(z) e^{-z^2} with e^{-|x|} = (e^{x/2})^2
   const float b_cf = 0.5f * ex2f * (1.0f - erfcx_pos_f(s_cf * 0.70710678f));
   const bool lower = beta < (double)b_cf;
   // ln beta to single precision from the exponent and the leading mantissa bits (beta may be far below FLT_MIN)
   const int bhi = __double2hiint(beta);
   const float lnbeta_f = fmaf((float)(((bhi >> 20) & 0x7ff) - 1023), 0.69314718f,
-                              __logf((float)__hiloint2double((bhi & 0x000fffff) | 0x3ff00000, __double2loint(beta))));
+                              f_log((float)__hiloint2double((bhi & 0x000fffff) | 0x3ff00000, __double2loint(beta))));
   float s0 = presolve_f32(xf, (float)beta, lnbeta_f, ex2f, iex2f, s_cf, b_cf, lower);
   double s = (double)s0;
   if (!(s > 0.0 && s < S_MAX)) s = 1.0;   // fp32 range exhausted: the bracketed fp64 loop takes it from anywhere
