@@ -164,7 +164,17 @@ __device__ __forceinline__ double exp_neg_small(double z) {
   if (!(fabs(z) <= 0.25)) return exp(-z);
   return exp_poly(-z);
 }
-// e^{-z} for 0 <= z <= 700: z = n ln2 + r, |r| <= ln2/2, e^{-z} = 2^{-n} e^{-r}; the library exp outside that range
+// e^{-z} for 0 <= z <= 700: z = n ln2 + r, |r| <= ln2/2, e^{-z} = 2^{-n} e^{-r}
+__device__ __forceinline__ double exp_neg_core(double z) {
+  const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52: the low word of z*log2e + MAGIC is rint(z*log2e)
+  const double tn = fma(z, 1.4426950408889634, MAGIC);
+  const int n = __double2loint(tn);
+  const double nd = tn - MAGIC;
+  double r = fma(nd, -6.93147180369123816490e-01, z);
+  r = fma(nd, -1.90821492927058770002e-10, r);
+  return exp_poly(-r) * __hiloint2double((1023 - n) << 20, 0);
+}
+// the library exp outside that range
 __device__ __forceinline__ double exp_neg(double z) {
   if (!(z >= 0.0 && z <= 700.0)) return exp(-z);
   const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52: the low word of z*log2e + MAGIC is rint(z*log2e)
@@ -319,7 +329,7 @@ __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1,
 
 // lower: g = ln b - ln beta = ln(b / beta), one logarithm per evaluation: inv_beta = 1/beta, lnbeta_off = 0
 // (for beta below 1e-290, where 1/beta is not finite, inv_beta = 1 and lnbeta_off = ln beta)
-__device__ __forceinline__ double polish_f64(double x, double beta, double inv_beta, double lnbeta_off, double ex2,
+__device__ __noinline__ double polish_f64(double x, double beta, double inv_beta, double lnbeta_off, double ex2,
                                              bool lower, double s, int& iters) {
   double lo = 0.0, hi = S_MAX;
   const double tvc = ex2 - beta;                     // > 0: what the price lacks to its s -> inf limit
@@ -401,15 +411,8 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   ok = ok && (p > lower_bound) && (p < upper_bound);               // false for NaN prices
   const double target = ok ? (itm ? p - diff : p) : 0.04;          // the out-of-the-money twin, > 0
   // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}, beta = target / sqrt(S Kd).
-  // One reciprocal (of target * max) and one reciprocal square root serve ratio, e^{x/2}, beta and 1/beta.
-  const double prod = target * mx;
-  double rmx, rtg;
-  if (prod >= 1e-290 && prod <= 1e290) {
-    const double R = rcp_fast(prod);
-    rmx = R * target; rtg = R * mx;
-  } else {
-    rmx = 1.0 / mx; rtg = 1.0 / target;
-  }
+  // One reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta.
+  const double rmx = rcp_fast(mx);
   double ratio = mn * rmx;                                         // (0, 1]
   if (!(ratio >= 2.3e-308)) { ok = false; ratio = 0.9; }           // S/Kd beyond 1e308: nothing to solve
   const double rsq = rsqrt_fast(ratio);
@@ -432,10 +435,38 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   float s0 = presolve_f32(xf, (float)beta, lnbeta_f, ex2f, iex2f, s_cf, b_cf, lower);
   double s = (double)s0;
   if (!(s > 0.0 && s < S_MAX)) s = 1.0;   // fp32 range exhausted: the bracketed fp64 loop takes it from anywhere
-  double inv_beta = ok ? (rtg * mx) * ex2 : 20.0, lnbeta_off = 0.0;     // sqrt(S Kd) / target
-  if (beta < 1e-290) { lnbeta_off = log(beta); inv_beta = 1.0; }
-  int it = 0;
-  s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, lower, s, it);
+  // ---- fast path: ONE fp64 Halley step on b(s) - beta, the same expression on both sides of the inflection point:
+  //   b = [h < t] e^{x/2} + E/2 (sgn(h-t) erfcx(|h-t|/sqrt2) - erfcx((h+t)/sqrt2)),  b' = E / sqrt(2 pi),  b''/b' = r2.
+  // Accepted when the step is below 1e-4 s (cubic convergence: what is left is ~1e-12 s); anything else — a pre-solve
+  // that landed far away, arguments outside the ranges of the fast helpers — goes to the bracketed loop below.
+  int it = 1;
+  bool accept;
+  {
+    const double inv_s = rcp_fast(s);
+    const double h = -x * inv_s, t = 0.5 * s;        // h >= 0
+    const double r2 = h * h * inv_s - 0.25 * s;
+    const double e = 0.5 * (h * h + t * t);
+    const double d = h - t;
+    double e1, e2;
+    erfcx_pair_pos(fabs(d) * INV_SQRT2, (h + t) * INV_SQRT2, e1, e2);
+    const double E = exp_neg_core(e);
+    const bool above = d < 0.0;
+    const double g = fma(0.5 * E, (above ? -e1 : e1) - e2, above ? ex2 - beta : -beta);
+    const double np = -g * SQRT_2PI;
+    const double den = fma(0.5 * np, r2, E);
+    const double step = np * rcp_fast1(den);
+    const double sn = s + step;
+    // s >= 1e-30 keeps every argument of the pair finite; e <= 700 keeps E normal; den ~ E keeps the step a Halley step
+    accept = (fabs(step) <= ACCEPT_STEP * sn) && (s >= 1e-30) && (e <= 700.0) && (den > 0.5 * E);
+    if (accept) s = sn;
+  }
+  if (!accept) {
+    double inv_beta = 1.0, lnbeta_off = 0.0;
+    if (beta < 1e-290) lnbeta_off = log(beta); else inv_beta = 1.0 / beta;
+    int it2 = 0;
+    s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, lower, s, it2);
+    it += it2;
+  }
   sigma_out = ok ? s * rsqrt_fast(t_) : qnan();
   iters_out = ok ? it : 0;
 }
