@@ -267,6 +267,49 @@ def test_implied_vol_vs_oracle(dev):
         f"call={q.is_call[worst]} sigma_true={q.sigma_true[worst]!r} got={sig[worst]!r} oracle={want[worst]!r}")
 
 
+def test_implied_vol_regimes(dev):
+    """The solver's fast path (one fp64 evaluation) and its bracketed fallback over every regime at once: moneyness from
+    1e-7 to e^3, maturities from an hour to 30 years, vols from 1 % to 500 %, negative and large rates."""
+    from iv_interpolation_b200 import device as D
+    from oracle import surface_oracle as SO
+    rng = np.random.default_rng(66)
+    n = 300_000
+    S = 10.0 ** rng.uniform(-2, 5, n)
+    m = np.where(rng.random(n) < 0.3, 10.0 ** rng.uniform(-7, -1, n), rng.uniform(0.0, 3.0, n)) * rng.choice([-1.0, 1.0], n)
+    m[:64] = 0.0                                            # at the money, forward or spot
+    K = S * np.exp(m)
+    T = 10.0 ** rng.uniform(-4, 1.5, n)
+    r = rng.uniform(-0.02, 0.15, n)
+    r[:32] = 0.0
+    sigma = 10.0 ** rng.uniform(-2, 0.7, n)
+    is_call = (rng.random(n) < 0.5).astype(np.uint8)
+    price = O.bs_price(S, K, T, r, sigma, is_call)
+    sig = D.bs_implied_vol(*(_t(a, dev) for a in (price, S, K, T, r)), _t(is_call, dev)).cpu().numpy()
+    want = SO.implied_vol_fast(price, S, K, T, r, is_call)
+    both = ~np.isnan(want) & ~np.isnan(sig)
+    assert both.mean() > 0.5
+    mism = np.isnan(want) != np.isnan(sig)
+    assert mism.mean() <= 5e-3, f"NaN mask differs on {mism.sum()} quotes"
+    err = np.abs(sig[both] - want[both])
+    fwd_ok = err <= 1e-8
+    rep = O.bs_price(S[both], K[both], T[both], r[both], sig[both], is_call[both])
+    back_ok = np.abs(rep - price[both]) <= 64 * np.spacing(np.maximum(np.abs(price[both]), S[both]))
+    bad = np.flatnonzero(~(fwd_ok | back_ok))
+    j = np.flatnonzero(both)[bad[:3]]
+    assert len(bad) == 0, (f"{len(bad)} quotes fail both forward and backward error, e.g. S={S[j]!r} K={K[j]!r} T={T[j]!r} "
+                           f"r={r[j]!r} sigma={sigma[j]!r} got={sig[j]!r} oracle={want[j]!r}")
+    # well-conditioned quotes (time value above 1e-6 S) must meet the forward bound itself
+    with np.errstate(all="ignore"):
+        kd = K * np.exp(-r * T)
+        tv = price - np.maximum(np.where(is_call != 0, S - kd, kd - S), 0.0)
+    core = both & (tv > 1e-6 * S) & (sigma * np.sqrt(T) < 3.0)
+    rt = np.abs(sig - sigma)
+    worst = int(np.argmax(np.where(core, rt, 0.0)))
+    assert core.sum() > 50_000 and rt[worst] <= 1e-8, (
+        f"round trip worst {rt[worst]:.3e} at S={S[worst]!r} K={K[worst]!r} T={T[worst]!r} r={r[worst]!r} "
+        f"sigma={sigma[worst]!r} got={sig[worst]!r} oracle={want[worst]!r}")
+
+
 @pytest.mark.parametrize("extrap", [0, 1, 2])
 def test_spline_fit_eval_vs_scipy(dev, extrap):
     from iv_interpolation_b200 import device as D
