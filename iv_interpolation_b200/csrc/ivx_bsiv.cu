@@ -153,10 +153,11 @@ __device__ __forceinline__ double log_normal(double a) {
   return fma(ed, 6.93147180369123816490e-01, tb.y + fma(ed, 1.90821492927058770002e-10, l));   // ln2 split hi + lo
 }
 // e^{w} for |w| <= 0.35: Taylor to w^13 (truncation 2e-18 at ln2/2)
+template <int FIRST = 0>                               // FIRST = 3: Taylor to w^10 (2e-13 at ln2/2)
 __device__ __forceinline__ double exp_poly(double w) {
-  double p = EXP_C[0];
+  double p = EXP_C[FIRST];
 #pragma unroll
-  for (int k = 1; k < 14; ++k) p = fma(p, w, EXP_C[k]);
+  for (int k = FIRST + 1; k < 14; ++k) p = fma(p, w, EXP_C[k]);
   return p;
 }
 // e^{-z} for |z| <= 1/4 (discount factors); the library exp elsewhere
@@ -165,6 +166,7 @@ __device__ __forceinline__ double exp_neg_small(double z) {
   return exp_poly(-z);
 }
 // e^{-z} for 0 <= z <= 700: z = n ln2 + r, |r| <= ln2/2, e^{-z} = 2^{-n} e^{-r}
+template <int FIRST = 0>
 __device__ __forceinline__ double exp_neg_core(double z) {
   const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52: the low word of z*log2e + MAGIC is rint(z*log2e)
   const double tn = fma(z, 1.4426950408889634, MAGIC);
@@ -172,7 +174,7 @@ __device__ __forceinline__ double exp_neg_core(double z) {
   const double nd = tn - MAGIC;
   double r = fma(nd, -6.93147180369123816490e-01, z);
   r = fma(nd, -1.90821492927058770002e-10, r);
-  return exp_poly(-r) * __hiloint2double((1023 - n) << 20, 0);
+  return exp_poly<FIRST>(-r) * __hiloint2double((1023 - n) << 20, 0);
 }
 // the library exp outside that range
 __device__ __forceinline__ double exp_neg(double z) {
@@ -219,10 +221,9 @@ __device__ __forceinline__ float erfcx_pos_f(float x) {
 __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta, float ex2, float iex2, float s_c,
                                               float b_c, bool lower) {
   const float kInvSqrt2 = 0.70710678f, kSqrt2Pi = 2.50662827f;
-  float lo, hi, s;
+  float s;
   const float s_tan = s_c + (beta - b_c) * kSqrt2Pi * iex2;   // tangent at the inflection point: b'(s_c) = e^{x/2} / sqrt(2 pi)
   if (lower) {
-    lo = 0.0f; hi = s_c;
     // two one-sided guesses: matching ln b ~ C - x^2/(2 s^2) at s_c undershoots (it ignores the s^3 prefactor),
     //   s_lo = |x| / sqrt(2 ln(b_c/beta) + |x|/2),
     // the tangent at s_c overshoots (b is convex below s_c).  The root sits at s_lo^(1-w) s_tan^w with w a tight
@@ -242,10 +243,10 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
       s = s_lo * f_ex2(w * f_lg2(s_tan * f_rcp(s_lo)));
     }
   } else {
-    lo = s_c; hi = (float)S_MAX;
     s = s_tan;                                       // Newton step from the inflection point
   }
-  if (!(s > lo && s < hi)) s = 0.5f * (lo + hi);
+  s = fminf(s, (float)S_MAX);
+  if (!(s > 0.0f)) s = 1.0f;                       // no usable guess: the fp64 fallback sorts it out
 #pragma unroll
   for (int it = 0; it < PRE_ITERS; ++it) {
     const float inv_s = f_rcp(s);
@@ -274,10 +275,9 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
       newton = (-g * kSqrt2Pi) * f_rcp(E);
       A = r2; B = r3;
     }
-    if (g > 0.0f) hi = s; else lo = s;
     const float fac = fmaf(0.5f * A, newton, 1.0f) * f_rcp(fmaf(newton, fmaf(B * (1.0f / 6.0f), newton, A), 1.0f));
     float sn = s + ((fac > 0.3f && fac < 3.0f) ? newton * fac : newton);
-    if (!(sn >= lo && sn <= hi && sn > 0.0f)) sn = 0.5f * (lo + hi);   // also catches NaN
+    if (!(sn > 0.5f * s && sn < 2.0f * s)) sn = s;   // also catches NaN; no bracket here, the fp64 phase checks the result
     s = sn;
   }
   return s;
@@ -285,33 +285,30 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
 
 // ---- phase 2: double precision ---------------------------------------------------------------------------
 // erfcx(q1), erfcx(q2) for q1, q2 >= 0 with ONE division: (1 + 2q) erfcx(q) is smooth in t = (q-4)/(q+4) on [-1, 1)
-// (degree-24 fit, 3.5 ulp; own Chebyshev interpolation against mpmath at 50 digits), and the four reciprocals
+// (degree-20 Chebyshev interpolant computed with mpmath at 50 digits: 8e-15 relative, smooth in q, so the
+// difference of two nearby values keeps that relative accuracy), and the four reciprocals
 // 1/(q+4), 1/(1+2q) are peeled off one reciprocal of their product.  The two Horner chains interleave.
-__constant__ double ERFCX_C[25] = {
-    -2.764120233734578e-10,
-    9.297625263709659e-10,
-    3.2323973445082033e-09,
-    -1.2338731403798444e-08,
-    -2.0725802488181963e-08,
-    1.0631817593818149e-07,
-    7.771943241086912e-08,
-    -8.210647933297337e-07,
-    2.9173425573089733e-07,
-    5.70657829924074e-06,
-    -1.1221135665965907e-05,
-    -2.4397731143023292e-05,
-    0.00015062142608651945,
-    -0.0001992571524726518,
-    -0.0007577732435942576,
-    0.005031970069102256,
-    -0.01619773406293477,
-    0.037167515526338006,
-    -0.06633036581186058,
-    0.09373283499911264,
-    -0.10103906603631811,
-    0.06809705425466839,
-    0.015379652102619974,
-    -0.13962111684056228,
+__constant__ double ERFCX_C[21] = {
+    -8.109180782116146e-09,
+    5.618350779659161e-08,
+    5.2566685922104696e-08,
+    -7.19142159951017e-07,
+    3.2140549400576467e-07,
+    5.5849674461555396e-06,
+    -1.1243141084157668e-05,
+    -2.4306876339027035e-05,
+    0.00015063187276799855,
+    -0.00019930049902749502,
+    -0.0007577763782834405,
+    0.005031983120919141,
+    -0.01619773349428245,
+    0.03716751315298436,
+    -0.06633036586880472,
+    0.09373283523715431,
+    -0.10103906603369428,
+    0.06809705424369002,
+    0.015379652102584254,
+    -0.13962111684041278,
     1.2329951186255526};
 
 __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1, double& e2) {
@@ -322,7 +319,7 @@ __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1,
   const double t1 = (q1 - 4.0) * (ra * a2), t2 = (q2 - 4.0) * (ra * a1);
   double p1 = ERFCX_C[0], p2 = ERFCX_C[0];
 #pragma unroll
-  for (int k = 1; k < 25; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }   // operands straight from the constant bank
+  for (int k = 1; k < 21; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }   // operands straight from the constant bank
   e1 = p1 * (rb * b2);
   e2 = p2 * (rb * b1);
 }
@@ -403,18 +400,18 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   // ok: S, Kd and T are positive normal numbers (no NaN below).  mx/mn = max/min(S, Kd); the in-the-money side is the
   // call when S > Kd, the put when S < Kd, and its intrinsic value is mx - mn.
   const bool sg = s_ > kd;
-  const double mx = ok ? (sg ? s_ : kd) : 1.0, mn = ok ? (sg ? kd : s_) : 0.9;
+  const double mx = sg ? s_ : kd, mn = sg ? kd : s_;     // garbage in, garbage through: replaced by a dummy quote below
   const double diff = mx - mn;
   const bool itm = (call == sg);
   const double lower_bound = itm ? diff : 0.0;
   const double upper_bound = call ? s_ : kd;
   ok = ok && (p > lower_bound) && (p < upper_bound);               // false for NaN prices
-  const double target = ok ? (itm ? p - diff : p) : 0.04;          // the out-of-the-money twin, > 0
+  const double target = itm ? p - diff : p;                         // the out-of-the-money twin, > 0 when ok
   // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}, beta = target / sqrt(S Kd).
   // One reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta.
   const double rmx = rcp_fast(mx);
   double ratio = mn * rmx;                                         // (0, 1]
-  if (!(ratio >= 2.3e-308)) { ok = false; ratio = 0.9; }           // S/Kd beyond 1e308: nothing to solve
+  if (!(ratio >= 2.3e-308)) ok = false;                            // S/Kd beyond 1e308 (or max(S, Kd) above 1e300)
   const double rsq = rsqrt_fast(ratio);
   double x = PRE_X ? -fabs(x_pre) : (ratio == 1.0 ? 0.0 : log_normal(ratio));
   double ex2 = ratio * rsq;
@@ -449,7 +446,7 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
     const double d = h - t;
     double e1, e2;
     erfcx_pair_pos(fabs(d) * INV_SQRT2, (h + t) * INV_SQRT2, e1, e2);
-    const double E = exp_neg_core(e);
+    const double E = exp_neg_core<3>(e);            // relative error of E = relative error of b: 2e-13 is ample
     const bool above = d < 0.0;
     const double g = fma(0.5 * E, (above ? -e1 : e1) - e2, above ? ex2 - beta : -beta);
     const double np = -g * SQRT_2PI;
