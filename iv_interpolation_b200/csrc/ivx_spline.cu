@@ -34,10 +34,21 @@ constexpr int SPL_RMAX = 8;       // rows per thread
 constexpr int STRIDED_MAXK = 64;
 constexpr int STRIDED_SPT = 4;      // systems per thread in the strided kernel
 
+// 1/a for a normal a (1e-300 < |a| < 1e300): 20-bit hardware seed and two Newton steps, without the special-case tail
+// of the compiler's division (a zero or denormal a gives inf/NaN, like the division it replaces would give inf)
+__device__ __forceinline__ double rcp_fast(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+
 __device__ __forceinline__ double spline_eval(double xl, double xr, double yl, double yr, double Ml, double Mr, double xq) {
   const double h = xr - xl;
   const double A = xr - xq, B = xq - xl;
-  const double ih = 1.0 / h;
+  const double ih = rcp_fast(h);
   return (Ml * A * A * A + Mr * B * B * B) * (ih * (1.0 / 6.0)) + (yl * ih - Ml * h * (1.0 / 6.0)) * A +
          (yr * ih - Mr * h * (1.0 / 6.0)) * B;
 }
@@ -152,59 +163,68 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   double* out = yq + sl * (int64_t)n_q;
 
   // ---- stage the slice (coalesced), NaN beyond its end ------------------------------------------------
+  bool fin = true;
 #pragma unroll
   for (int r = 0; r < SPL_R + 1; ++r) {
     const int j = r * G + g;
     if (j < L::CAP + 2) {
       double xv = qnan(), yv = qnan();
-      if (j < m) { xv = x_off ? __ldg(x + xk0 + j) : ld_stream(x + xk0 + j); yv = ld_stream(y + k0 + j); }
+      if (j < m) {
+        xv = x_off ? __ldg(x + xk0 + j) : ld_stream(x + xk0 + j); yv = ld_stream(y + k0 + j);
+        fin = fin && (fabs(xv) < INFINITY) && (fabs(yv) < INFINITY);
+      }
       xs[spl_pad(j)] = xv; ys[spl_pad(j)] = yv;
     }
   }
-  group_sync<G>(grp);
+  // a slice with every knot usable (the common case) is known at the barrier itself when the group is the whole CTA
+  bool clean = false;
+  if (G >= 256) clean = __syncthreads_and(fin) != 0;
+  else group_sync<G>(grp);
 
   // ---- own rows; squeeze out unusable knots if there are any -----------------------------------------------
   const int i0 = g * SPL_R;
   double xv[SPL_R], yv[SPL_R];
-  int cnt = 0;
-#pragma unroll
-  for (int j = 0; j < SPL_R; ++j) {
-    xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)];
-    cnt += (isfinite(xv[j]) && isfinite(yv[j])) ? 1 : 0;
-  }
-  int incl = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int u = __shfl_up_sync(IVX_FULL_MASK, incl, d);
-    if (lane >= d) incl += u;
-  }
-  int before = incl - cnt, n = __shfl_sync(IVX_FULL_MASK, incl, 31);
-  if (L::NW > 1) {
-    if (lane == 31) wc[w] = incl;
-    group_sync<G>(grp);
-    n = 0;
-#pragma unroll
-    for (int ww = 0; ww < L::NW; ++ww) {
-      const int c = wc[ww];
-      if (ww < w) before += c;
-      n += c;
-    }
-  }
-  if (n != m) {                          // group-uniform
-    group_sync<G>(grp);                  // every thread holds its rows in registers by now
-    int o = before;
+  int n = m;
+  if (!clean) {                          // group-uniform
+    int cnt = 0;
 #pragma unroll
     for (int j = 0; j < SPL_R; ++j) {
-      if (isfinite(xv[j]) && isfinite(yv[j])) { xs[spl_pad(o)] = xv[j]; ys[spl_pad(o)] = yv[j]; ++o; }
+      xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)];
+      cnt += (isfinite(xv[j]) && isfinite(yv[j])) ? 1 : 0;
     }
+    int incl = cnt;
 #pragma unroll
-    for (int r = 0; r < SPL_R; ++r) {
-      const int j = r * G + g;
-      if (j >= n && j < m) { xs[spl_pad(j)] = qnan(); ys[spl_pad(j)] = qnan(); }
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(IVX_FULL_MASK, incl, d);
+      if (lane >= d) incl += u;
     }
-    group_sync<G>(grp);
+    int before = incl - cnt;
+    n = __shfl_sync(IVX_FULL_MASK, incl, 31);
+    if (L::NW > 1) {
+      if (lane == 31) wc[w] = incl;
+      group_sync<G>(grp);
+      n = 0;
 #pragma unroll
-    for (int j = 0; j < SPL_R; ++j) { xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)]; }
+      for (int ww = 0; ww < L::NW; ++ww) {
+        const int c = wc[ww];
+        if (ww < w) before += c;
+        n += c;
+      }
+    }
+    if (n != m) {                          // group-uniform
+      group_sync<G>(grp);                  // every thread holds its rows in registers by now
+      int o = before;
+#pragma unroll
+      for (int j = 0; j < SPL_R; ++j) {
+        if (isfinite(xv[j]) && isfinite(yv[j])) { xs[spl_pad(o)] = xv[j]; ys[spl_pad(o)] = yv[j]; ++o; }
+      }
+#pragma unroll
+      for (int r = 0; r < SPL_R; ++r) {
+        const int j = r * G + g;
+        if (j >= n && j < m) { xs[spl_pad(j)] = qnan(); ys[spl_pad(j)] = qnan(); }
+      }
+      group_sync<G>(grp);
+    }
   }
   if (n < 2) {
     for (int q = g; q < n_q; q += G) st_stream(out + q, qnan());
@@ -222,6 +242,8 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
     const double* __restrict__ cp_t = lu_cp + tb;
     const double* __restrict__ inv_t = lu_inv + tb;
     const double* __restrict__ ih_t = lu_ih + tb;
+#pragma unroll
+    for (int j = 0; j < SPL_R; ++j) { xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)]; }
     const double xp = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yp = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
     const double yn = ys[spl_pad(i0 + SPL_R)];
     double sl[SPL_R + 1];                 // sl[k] = slope of segment i0+k-1
@@ -323,11 +345,10 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
       t[0] = P.A; t[1] = P.B; t[2] = P.C; t[3] = P.E; t[4] = P.F; t[5] = P.G; t[6] = P.H;
     }
     group_sync<G>(grp);
-    for (int ww = 0; ww < w; ++ww) {
+    for (int ww = 0; ww < w; ++ww) {     // normalised warp totals (largest entry in [1,2)) move the state by at most 6x each: no rescaling inside
       const double* t = wm + ww * 7;
       const double nq = t[0] * q + t[1] * qp, nqp = t[2] * q + t[3] * qp, nD = t[4] * q + t[5] * qp + t[6] * D;
-      const double sc = pow2_inv(fmax(fmax(fabs(nq), fabs(nqp)), fabs(nD)));
-      q = nq * sc; qp = nqp * sc; D = nD * sc;
+      q = nq; qp = nqp; D = nD;
     }
   }
   {
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
       const double a = hm * hmp, b = 2.0 * (hm + hp) * hmp, r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
       const double ag = (i0 + j == 1) ? 0.0 : hh[j] * hm * hm * a;
       const double qn = b * q - ag * qp, Dn = r * q - a * D;
-      const double inv = 1.0 / qn;
+      const double inv = rcp_fast(qn);     // the state was renormalised on entry and grows by h^3 per row: normal range
       cv[j] = hmp * hp * q * inv;
       dv[j] = Dn * inv;
       qp = q; q = qn; D = Dn;
@@ -388,22 +409,25 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   for (int j = 0; j < SPL_R; ++j) { xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)]; }   // reloaded, not kept across the scans
   int qi = qs[g];
   const int qhi = owns_last ? n_q : qs[g + 1];
+  // the current grid point rides in a register (+inf once the thread's range is exhausted); a segment takes points while
+  // they lie left of its right knot — the last segment's right knot is +inf here, so it takes whatever is left
+  const double* __restrict__ xqp = xq + qi;
+  double* __restrict__ op = out + qi;
+  int left = qhi - qi;
+  double xq_cur = left > 0 ? __ldg(xqp) : INFINITY;
 #pragma unroll
   for (int j = 0; j < SPL_R; ++j) {
     const int i = i0 + j;
-    if (i <= n - 2) {
-      const bool lastseg = (i == n - 2);
-      const double xr_ = j < SPL_R - 1 ? xv[j + 1 < SPL_R ? j + 1 : j] : xn;
-      const double yr_ = j < SPL_R - 1 ? yv[j + 1 < SPL_R ? j + 1 : j] : yn;
-      const double Mr_ = j < SPL_R - 1 ? dv[j + 1 < SPL_R ? j + 1 : j] : Mn;
-      while (qi < qhi) {
-        const double xv_q = __ldg(xq + qi);
-        if (!(lastseg || xv_q < xr_)) break;
-        const double v = spline_eval(xv[j], xr_, yv[j], yr_, dv[j], Mr_, xv_q);
-        // only the first thread can see points below the first knot, only the last segment's owner points above the last
-        st_stream(out + qi, edge ? apply_extrap(v, xv_q, xlo, xhi, ylo, yhi, extrap) : v);
-        ++qi;
-      }
+    const double xr_ = j < SPL_R - 1 ? xv[j + 1 < SPL_R ? j + 1 : j] : xn;
+    const double yr_ = j < SPL_R - 1 ? yv[j + 1 < SPL_R ? j + 1 : j] : yn;
+    const double Mr_ = j < SPL_R - 1 ? dv[j + 1 < SPL_R ? j + 1 : j] : Mn;
+    const double xr_take = (i >= n - 2) ? INFINITY : xr_;          // rows past n-2 are never reached with points left
+    while (!(xq_cur >= xr_take)) {                                  // a NaN grid point is taken where it stands and yields NaN
+      const double v = spline_eval(xv[j], xr_, yv[j], yr_, dv[j], Mr_, xq_cur);
+      // only the first thread can see points below the first knot, only the last segment's owner points above the last
+      st_stream(op, edge ? apply_extrap(v, xq_cur, xlo, xhi, ylo, yhi, extrap) : v);
+      ++op; ++xqp; --left;
+      xq_cur = left > 0 ? __ldg(xqp) : INFINITY;
     }
   }
 }
