@@ -77,15 +77,20 @@ __device__ __forceinline__ Mat3 mat_mul(const Mat3& L, const Mat3& R) {
   o.H = L.H * R.H;
   return o;
 }
-// 2^-e for a finite positive m = 1.f x 2^e (1.0 for zero, subnormal, inf, NaN)
-__device__ __forceinline__ double pow2_inv(double m) {
-  const int e = (__double2hiint(m) >> 20) & 0x7ff;
+// 2^-e for the largest of the magnitudes whose high words (sign stripped) have maximum hw: 1.f x 2^e  (1.0 for zero,
+// subnormal, inf, NaN).  Magnitudes compare like their high words, so the maximum is taken on integers.
+__device__ __forceinline__ double pow2_inv_hw(int hw) {
+  const int e = hw >> 20;
   return (e == 0 || e == 0x7ff) ? 1.0 : __hiloint2double((2046 - e) << 20, 0);
 }
+__device__ __forceinline__ int abs_hw(double v) { return __double2hiint(v) & 0x7fffffff; }
+__device__ __forceinline__ double pow2_inv3(double a, double b, double c) {
+  return pow2_inv_hw(max(max(abs_hw(a), abs_hw(b)), abs_hw(c)));
+}
 __device__ __forceinline__ void mat_normalize(Mat3& P) {
-  const double m = fmax(fmax(fmax(fabs(P.A), fabs(P.B)), fmax(fabs(P.C), fabs(P.E))),
-                        fmax(fmax(fabs(P.F), fabs(P.G)), fabs(P.H)));
-  const double sc = pow2_inv(m);
+  const int hw = max(max(max(abs_hw(P.A), abs_hw(P.B)), max(abs_hw(P.C), abs_hw(P.E))),
+                     max(max(abs_hw(P.F), abs_hw(P.G)), abs_hw(P.H)));
+  const double sc = pow2_inv_hw(hw);
   P.A *= sc; P.B *= sc; P.C *= sc; P.E *= sc; P.F *= sc; P.G *= sc; P.H *= sc;
 }
 __device__ __forceinline__ Mat3 mat_shfl_up(const Mat3& P, int d) {
@@ -181,11 +186,11 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   if (G >= 256) clean = __syncthreads_and(fin) != 0;
   else group_sync<G>(grp);
 
-  // ---- own rows; squeeze out unusable knots if there are any -----------------------------------------------
+  // ---- squeeze out unusable knots if there are any (chunks of SPL_R knots per thread, stable) ------------------------
   const int i0 = g * SPL_R;
-  double xv[SPL_R], yv[SPL_R];
   int n = m;
   if (!clean) {                          // group-uniform
+    double xv[SPL_R], yv[SPL_R];
     int cnt = 0;
 #pragma unroll
     for (int j = 0; j < SPL_R; ++j) {
@@ -231,41 +236,47 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
     return;
   }
 
+  // Thread g owns the equations (rows) i = R g + 1 + j, j = 0..R-1 — row 0 is not an equation, so every thread's rows
+  // are equations up to the end of the slice — and the segments [x[i], x[i+1]] with the same numbers; thread 0 also
+  // owns segment 0.  Rows past n-2 are computed like the others on whatever the NaN padding gives and zeroed afterwards:
+  // the elimination only flows forward, so they cannot reach a valid row, and no per-row test is left in the loops.
   double cv[SPL_R], dv[SPL_R];
-  // row i0+j is an equation of the system iff 1 <= i0+j <= n-2
-  auto interior = [&](int j) { const int i = i0 + j; return i >= 1 && i <= n - 2; };
+  const int nvalid = min(max(n - 2 - i0, 0), SPL_R);      // rows i0+1 .. i0+nvalid are equations
   if (LADDER && n == m) {
     // ---- shared-ladder path: slopes through the tabulated 1/h, right-hand side as affine maps of d' ------------------
-    // tables are stored the way they are read: row i = R g + j of ladder l sits at l CAP + j G + g, so that the 32 lanes
-    // of a warp read 32 consecutive doubles
+    // tables are stored the way they are read: row i = R g + 1 + j of ladder l sits at l CAP + j G + g, so that the 32
+    // lanes of a warp read 32 consecutive doubles; ih at row i is 1 / (x[i] - x[i-1])
     const int64_t tb = (int64_t)slice_ladder[sl] * L::CAP;
     const double* __restrict__ cp_t = lu_cp + tb;
     const double* __restrict__ inv_t = lu_inv + tb;
     const double* __restrict__ ih_t = lu_ih + tb;
+    double slp[SPL_R + 1];                // slp[k] = slope of segment i0+k
+    {
+      double yl = ys[spl_pad(i0)];
 #pragma unroll
-    for (int j = 0; j < SPL_R; ++j) { xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)]; }
-    const double xp = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yp = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
-    const double yn = ys[spl_pad(i0 + SPL_R)];
-    double sl[SPL_R + 1];                 // sl[k] = slope of segment i0+k-1
-#pragma unroll
-    for (int k = 0; k <= SPL_R; ++k) {
-      const int seg = i0 + k - 1;
-      const double ihv = (seg >= 0 && seg <= n - 2) ? __ldg(ih_t + (k == 0 ? (SPL_R - 1) * G + g - 1 : (k - 1) * G + g)) : 0.0;
-      const double yl = k == 0 ? yp : yv[k - 1 < SPL_R ? (k - 1 < 0 ? 0 : k - 1) : 0];
-      const double yr = k == SPL_R ? yn : yv[k < SPL_R ? k : 0];
-      sl[k] = (yr - yl) * ihv;
+      for (int k = 0; k <= SPL_R; ++k) {
+        const double yr = ys[spl_pad(i0 + k + 1)];
+        const bool segok = i0 + k <= n - 2;
+        const double ihv = segok ? __ldg(ih_t + (k < SPL_R ? k * G + g : g + 1)) : 0.0;
+        slp[k] = segok ? (yr - yl) * ihv : 0.0;
+        yl = yr;
+      }
     }
     double al[SPL_R], bt[SPL_R];
     double A = 0.0, B = 1.0;              // d'[last row of the chunk] = A + B d'[last row of the previous chunk]
+    {
+      double xl = xs[spl_pad(i0)];
 #pragma unroll
-    for (int j = 0; j < SPL_R; ++j) {
-      al[j] = 0.0; bt[j] = 0.0;
-      if (interior(j)) {
-        const double inv = __ldg(inv_t + j * G + g);
-        const double hm = xv[j] - (j == 0 ? xp : xv[j > 0 ? j - 1 : 0]);
-        al[j] = 6.0 * (sl[j + 1] - sl[j]) * inv;
-        bt[j] = -hm * inv;
-        A = fma(bt[j], A, al[j]); B *= bt[j];
+      for (int j = 0; j < SPL_R; ++j) {
+        const double xr = xs[spl_pad(i0 + j + 1)];
+        al[j] = 0.0; bt[j] = 0.0;
+        if (j < nvalid) {
+          const double inv = __ldg(inv_t + j * G + g);
+          al[j] = 6.0 * (slp[j + 1] - slp[j]) * inv;
+          bt[j] = -(xr - xl) * inv;
+          A = fma(bt[j], A, al[j]); B *= bt[j];
+        }
+        xl = xr;
       }
     }
 #pragma unroll
@@ -286,93 +297,99 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
 #pragma unroll
     for (int j = 0; j < SPL_R; ++j) {
       cv[j] = 0.0; dv[j] = 0.0;
-      if (interior(j)) {
+      if (j < nvalid) {
         d = fma(bt[j], d, al[j]);
         dv[j] = d;
         cv[j] = __ldg(cp_t + j * G + g);
       }
     }
   } else {
-  // ---- row coefficients.  Row i (1 <= i <= n-2) is multiplied by h[i-1] h[i], which clears both slope
-  //      divisions:  a = hm^2 hp,  b = 2 (hm+hp) hm hp,  c = hm hp^2,  r = 6 (dy[i] hm - dy[i-1] hp);
-  //      the q recurrence needs a[i] c[i-1] = h[i-2] hm^4 hp.  hh[k] = x[i0+k-1] - x[i0+k-2], k = 0..9 ---------
-  // The differences are formed from shared memory twice (before the scan and after it) instead of being kept in
-  // registers across the scan: the live set during the scan is then the two matrices only, which is what lets four
-  // CTAs share an SM without spilling.
-  auto load_diffs = [&](double (&hh)[SPL_R + 2], double (&dy)[SPL_R + 1]) {
-    double xl = g > 0 ? xs[spl_pad(i0 - 2)] : qnan();
-    double xc = g > 0 ? xs[spl_pad(i0 - 1)] : qnan(), yc = g > 0 ? ys[spl_pad(i0 - 1)] : qnan();
-    hh[0] = xc - xl;
+    // ---- row coefficients.  Row i (1 <= i <= n-2) is multiplied by h[i-1] h[i], which clears both slope
+    //      divisions:  a = hm^2 hp,  b = 2 (hm+hp) hm hp,  c = hm hp^2,  r = 6 (dy[i] hm - dy[i-1] hp), hm = h[i-1], hp = h[i];
+    //      the q recurrence needs a[i] c[i-1], and c is carried from row to row.
+    // The differences are formed from shared memory twice (before the scan and after it) instead of being kept in
+    // registers across the scan: the live set during the scan is then the two matrices only, which is what lets four
+    // CTAs share an SM.   hh[k] = x[i0+k] - x[i0+k-1], k = 0..R+1;  dy[k] = y[i0+k+1] - y[i0+k], k = 0..R
+    auto load_diffs = [&](double (&hh)[SPL_R + 2], double (&dy)[SPL_R + 1]) {
+      double xc = g > 0 ? xs[spl_pad(i0 - 1)] : qnan();
+      double yc = qnan();
 #pragma unroll
-    for (int k = 0; k <= SPL_R; ++k) {
-      const double xk = xs[spl_pad(i0 + k)], yk = ys[spl_pad(i0 + k)];
-      hh[k + 1] = xk - xc; dy[k] = yk - yc;
-      xc = xk; yc = yk;
-    }
-  };
-  // row i0+j: hm = hh[j+1], hp = hh[j+2], h[i-2] = hh[j]
+      for (int k = 0; k <= SPL_R + 1; ++k) {
+        const double xk = xs[spl_pad(i0 + k)], yk = ys[spl_pad(i0 + k)];
+        hh[k] = xk - xc;
+        if (k > 0) dy[k - 1] = yk - yc;
+        xc = xk; yc = yk;
+      }
+    };
+    // row j (i = i0+1+j): hm = hh[j+1], hp = hh[j+2], dy[i-1] = dy[j], dy[i] = dy[j+1]; c of row i0 (before j = 0) = hh[0] hh[1]^2
 
-  // ---- forward: chunk transition matrix, prefix over the group ----------------------------------------------
-  Mat3 P = mat_identity();
-  {
-    double hh[SPL_R + 2], dy[SPL_R + 1];
-    load_diffs(hh, dy);
+    // ---- forward: chunk transition matrix, prefix over the group ----------------------------------------------
+    Mat3 P = mat_identity();
+    {
+      double hh[SPL_R + 2], dy[SPL_R + 1];
+      load_diffs(hh, dy);
+      double c_prev = g > 0 ? hh[0] * hh[1] * hh[1] : 0.0;           // multiplies q[-1] = 0 in row 1
 #pragma unroll
-    for (int j = 0; j < SPL_R; ++j) {
-      if (interior(j)) {
+      for (int j = 0; j < SPL_R; ++j) {
         const double hm = hh[j + 1], hp = hh[j + 2], hmp = hm * hp;
-        const double a = hm * hmp, b = 2.0 * (hm + hp) * hmp, r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
-        const double ag = (i0 + j == 1) ? 0.0 : hh[j] * hm * hm * a;     // multiplies q[-1] = 0 in row 1
+        const double a = hm * hmp, b = (hm + hp) * (hmp + hmp), r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
+        const double ag = a * c_prev;
+        c_prev = hmp * hp;
         const double nA = b * P.A - ag * P.C, nB = b * P.B - ag * P.E;
         const double nF = r * P.A - a * P.F, nG = r * P.B - a * P.G;
         P.C = P.A; P.E = P.B; P.A = nA; P.B = nB; P.F = nF; P.G = nG; P.H = -a * P.H;
       }
     }
-  }
-  mat_normalize(P);
+    mat_normalize(P);
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {       // products of normalised matrices grow by at most 3x per level: no rescaling inside
-    const Mat3 Q = mat_shfl_up(P, d);
-    if (lane >= d) P = mat_mul(P, Q);
-  }
-  mat_normalize(P);
-  Mat3 X = mat_shfl_up(P, 1);            // exclusive prefix inside the warp
-  if (lane == 0) X = mat_identity();
-  double q = 1.0, qp = 0.0, D = 0.0;     // state before row 1: q[0] = 1, q[-1] = 0, D[0] = 0
-  if (L::NW > 1) {
-    if (lane == 31) {
-      double* t = wm + w * 7;
-      t[0] = P.A; t[1] = P.B; t[2] = P.C; t[3] = P.E; t[4] = P.F; t[5] = P.G; t[6] = P.H;
+    for (int d = 1; d < 32; d <<= 1) {       // products of normalised matrices grow by at most 3x per level: no rescaling inside
+      const Mat3 Q = mat_shfl_up(P, d);
+      if (lane >= d) P = mat_mul(P, Q);
     }
-    group_sync<G>(grp);
-    for (int ww = 0; ww < w; ++ww) {     // normalised warp totals (largest entry in [1,2)) move the state by at most 6x each: no rescaling inside
-      const double* t = wm + ww * 7;
-      const double nq = t[0] * q + t[1] * qp, nqp = t[2] * q + t[3] * qp, nD = t[4] * q + t[5] * qp + t[6] * D;
-      q = nq; qp = nqp; D = nD;
+    mat_normalize(P);
+    Mat3 X = mat_shfl_up(P, 1);            // exclusive prefix inside the warp
+    if (lane == 0) X = mat_identity();
+    double q = 1.0, qp = 0.0, D = 0.0;     // state before row 1: q[0] = 1, q[-1] = 0, D[0] = 0
+    if (L::NW > 1) {
+      if (lane == 31) {
+        double* t = wm + w * 7;
+        t[0] = P.A; t[1] = P.B; t[2] = P.C; t[3] = P.E; t[4] = P.F; t[5] = P.G; t[6] = P.H;
+      }
+      group_sync<G>(grp);
+      for (int ww = 0; ww < w; ++ww) {     // normalised warp totals (largest entry in [1,2)) move the state by at most 6x each: no rescaling inside
+        const double* t = wm + ww * 7;
+        const double nq = t[0] * q + t[1] * qp, nqp = t[2] * q + t[3] * qp, nD = t[4] * q + t[5] * qp + t[6] * D;
+        q = nq; qp = nqp; D = nD;
+      }
     }
-  }
-  {
-    const double nq = X.A * q + X.B * qp, nqp = X.C * q + X.E * qp, nD = X.F * q + X.G * qp + X.H * D;
-    const double sc = pow2_inv(fmax(fmax(fabs(nq), fabs(nqp)), fabs(nD)));
-    q = nq * sc; qp = nqp * sc; D = nD * sc;
-  }
-  // ---- re-walk the rows from the exact incoming state: Thomas' c', d' ---------------------------------------
-  double hh[SPL_R + 2], dy[SPL_R + 1];
-  load_diffs(hh, dy);
+    {
+      const double nq = X.A * q + X.B * qp, nqp = X.C * q + X.E * qp, nD = X.F * q + X.G * qp + X.H * D;
+      const double sc = pow2_inv3(nq, nqp, nD);
+      q = nq * sc; qp = nqp * sc; D = nD * sc;
+    }
+    // ---- re-walk the rows from the exact incoming state: Thomas' c', d' ---------------------------------------
+    {
+      double hh[SPL_R + 2], dy[SPL_R + 1];
+      load_diffs(hh, dy);
+      double c_prev = g > 0 ? hh[0] * hh[1] * hh[1] : 0.0;
 #pragma unroll
-  for (int j = 0; j < SPL_R; ++j) {
-    cv[j] = 0.0; dv[j] = 0.0;
-    if (interior(j)) {
-      const double hm = hh[j + 1], hp = hh[j + 2], hmp = hm * hp;
-      const double a = hm * hmp, b = 2.0 * (hm + hp) * hmp, r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
-      const double ag = (i0 + j == 1) ? 0.0 : hh[j] * hm * hm * a;
-      const double qn = b * q - ag * qp, Dn = r * q - a * D;
-      const double inv = rcp_fast(qn);     // the state was renormalised on entry and grows by h^3 per row: normal range
-      cv[j] = hmp * hp * q * inv;
-      dv[j] = Dn * inv;
-      qp = q; q = qn; D = Dn;
+      for (int j = 0; j < SPL_R; ++j) {
+        const double hm = hh[j + 1], hp = hh[j + 2], hmp = hm * hp;
+        const double a = hm * hmp, b = (hm + hp) * (hmp + hmp), r = 6.0 * (dy[j + 1] * hm - dy[j] * hp);
+        const double ag = a * c_prev;
+        c_prev = hmp * hp;
+        const double qn = b * q - ag * qp, Dn = r * q - a * D;
+        const double inv = rcp_fast(qn);     // the state was renormalised on entry and grows by h^3 per row: normal range
+        cv[j] = c_prev * q * inv;
+        dv[j] = Dn * inv;
+        qp = q; q = qn; D = Dn;
+      }
     }
-  }
+    if (nvalid < SPL_R) {                  // the thread that holds the end of the slice, and those after it
+#pragma unroll
+      for (int j = 0; j < SPL_R; ++j)
+        if (j >= nvalid) { cv[j] = 0.0; dv[j] = 0.0; }
+    }
   }
   // ---- backward: M[i] = d'[i] - c'[i] M[i+1] as affine maps, suffix scan ---------------------------------------
   double al = 0.0, be = 1.0;             // M[first row of the chunk] = al + be * M[first row of the next chunk]
@@ -393,42 +410,43 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   double Mn = __shfl_down_sync(IVX_FULL_MASK, m_first, 1);
   if (lane == 31) Mn = z;
 #pragma unroll
-  for (int j = SPL_R - 1; j >= 0; --j) { dv[j] = dv[j] - cv[j] * (j == SPL_R - 1 ? Mn : dv[j + 1]); }   // dv = M now
+  for (int j = SPL_R - 1; j >= 0; --j) { dv[j] = dv[j] - cv[j] * (j == SPL_R - 1 ? Mn : dv[j + 1]); }   // dv[j] = M[i0+1+j] now
 
   // ---- evaluate the grid points inside my segments ------------------------------------------------------------
-  // the grid is sorted: thread g's points start at the first one >= x[i0] and end where thread g+1's start
-  qs[g] = (g == 0) ? 0 : ((i0 <= n - 2) ? lower_bound_q(xq, n_q, xs[spl_pad(i0)]) : n_q);
+  // the grid is sorted: thread g's points start at the first one >= x[i0+1] (thread 0: at the first point) and end
+  // where thread g+1's start; the owner of the last segment (n-2) also takes everything above it
+  const bool has_seg = i0 + 1 <= n - 2;
+  qs[g] = (g == 0) ? 0 : (has_seg ? lower_bound_q(xq, n_q, xs[spl_pad(i0 + 1)]) : n_q);
   if (g == 0) qs[G] = n_q;
   group_sync<G>(grp);
-  if (i0 > n - 2) return;
+  if (!has_seg && g > 0) return;
   const double xlo = xs[spl_pad(0)], xhi = xs[spl_pad(n - 1)], ylo = ys[spl_pad(0)], yhi = ys[spl_pad(n - 1)];
-  const double xn = xs[spl_pad(i0 + SPL_R)], yn = ys[spl_pad(i0 + SPL_R)];
-  const bool owns_last = (n - 2) <= i0 + SPL_R - 1;
+  const bool owns_last = (has_seg && n - 2 <= i0 + SPL_R) || !has_seg;   // !has_seg here: thread 0 of a 2- or 3-knot... (n <= 2)
   const bool edge = g == 0 || owns_last;
-#pragma unroll
-  for (int j = 0; j < SPL_R; ++j) { xv[j] = xs[spl_pad(i0 + j)]; yv[j] = ys[spl_pad(i0 + j)]; }   // reloaded, not kept across the scans
-  int qi = qs[g];
-  const int qhi = owns_last ? n_q : qs[g + 1];
+  int left = (owns_last ? n_q : qs[g + 1]) - qs[g];
   // the current grid point rides in a register (+inf once the thread's range is exhausted); a segment takes points while
-  // they lie left of its right knot — the last segment's right knot is +inf here, so it takes whatever is left
-  const double* __restrict__ xqp = xq + qi;
-  double* __restrict__ op = out + qi;
-  int left = qhi - qi;
+  // they lie left of its right knot — the last segment's right knot counts as +inf, so it takes whatever is left
+  const double* __restrict__ xqp = xq + qs[g];
+  double* __restrict__ op = out + qs[g];
   double xq_cur = left > 0 ? __ldg(xqp) : INFINITY;
-#pragma unroll
-  for (int j = 0; j < SPL_R; ++j) {
-    const int i = i0 + j;
-    const double xr_ = j < SPL_R - 1 ? xv[j + 1 < SPL_R ? j + 1 : j] : xn;
-    const double yr_ = j < SPL_R - 1 ? yv[j + 1 < SPL_R ? j + 1 : j] : yn;
-    const double Mr_ = j < SPL_R - 1 ? dv[j + 1 < SPL_R ? j + 1 : j] : Mn;
-    const double xr_take = (i >= n - 2) ? INFINITY : xr_;          // rows past n-2 are never reached with points left
+  auto take = [&](double xl_, double xr_, double yl_, double yr_, double Ml_, double Mr_, bool last) {
+    const double xr_take = last ? INFINITY : xr_;
     while (!(xq_cur >= xr_take)) {                                  // a NaN grid point is taken where it stands and yields NaN
-      const double v = spline_eval(xv[j], xr_, yv[j], yr_, dv[j], Mr_, xq_cur);
+      const double v = spline_eval(xl_, xr_, yl_, yr_, Ml_, Mr_, xq_cur);
       // only the first thread can see points below the first knot, only the last segment's owner points above the last
       st_stream(op, edge ? apply_extrap(v, xq_cur, xlo, xhi, ylo, yhi, extrap) : v);
       ++op; ++xqp; --left;
       xq_cur = left > 0 ? __ldg(xqp) : INFINITY;
     }
+  };
+  double xl_ = xs[spl_pad(i0 + 1)], yl_ = ys[spl_pad(i0 + 1)];
+  if (g == 0) take(xlo, xl_, ylo, yl_, 0.0, n > 2 ? dv[0] : 0.0, n <= 2);   // segment 0 (M[0] = 0; M[1] = 0 too when n == 2)
+#pragma unroll
+  for (int j = 0; j < SPL_R; ++j) {
+    const double xr_ = xs[spl_pad(i0 + j + 2)], yr_ = ys[spl_pad(i0 + j + 2)];
+    const double Mr_ = j < SPL_R - 1 ? dv[j + 1 < SPL_R ? j + 1 : j] : Mn;
+    take(xl_, xr_, yl_, yr_, dv[j], Mr_, i0 + 1 + j >= n - 2);        // segments past n-2 are never reached with points left
+    xl_ = xr_; yl_ = yr_;
   }
 }
 
@@ -606,7 +624,8 @@ static int spline_group_width(int64_t max_knots) {
 // one CTA per ladder: the x-only half of Thomas' elimination, once for every slice that uses the ladder.  The abscissae
 // are staged into shared memory by the whole CTA (the recurrence itself is a serial chain of divisions, run by thread 0
 // out of shared memory), results leave through coalesced stores.
-// Row i of ladder l goes to l*cap + (i % 8)*G + i/8 — the order in which the evaluation kernel's threads read it.
+// Row i >= 1 of ladder l goes to l*cap + ((i-1) % 8)*G + (i-1)/8 — the order in which the evaluation kernel's threads
+// read it (thread g owns rows 8g+1 .. 8g+8).
 __global__ void __launch_bounds__(256) k_spline_ladder_factor(int64_t n_ladders, const int64_t* __restrict__ ladder_off,
                                                              const double* __restrict__ x, int G, double* __restrict__ lu_cp,
                                                              double* __restrict__ lu_inv, double* __restrict__ lu_ih) {
@@ -635,9 +654,9 @@ __global__ void __launch_bounds__(256) k_spline_ladder_factor(int64_t n_ladders,
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t o = l * cap + (int64_t)(i % SPL_RMAX) * G + i / SPL_RMAX;
-    lu_ih[o] = i + 1 < n ? 1.0 / (sx[i + 1] - sx[i]) : qnan();
+  for (int i = threadIdx.x + 1; i < n; i += blockDim.x) {      // row i >= 1; ih at row i belongs to the segment left of knot i
+    const int64_t o = l * cap + (int64_t)((i - 1) % SPL_RMAX) * G + (i - 1) / SPL_RMAX;
+    lu_ih[o] = 1.0 / (sx[i] - sx[i - 1]);
     lu_cp[o] = scp[i]; lu_inv[o] = sinv[i];
   }
 }
