@@ -350,6 +350,33 @@ def test_spline_fit_eval_every_group_width(dev, lo, hi, n_slices, nq):
         assert np.isnan(short).all()
 
 
+@pytest.mark.parametrize("cap", [256, 2048])
+def test_spline_fit_eval_chunk_boundaries(dev, cap):
+    """Knot counts around the 8-row chunk boundaries and at the exact capacity of the launch (the thread that holds the
+    end of the slice changes with n mod 8; at n = capacity there is no padding row left inside the last chunk)."""
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(cap)
+    sizes = [2, 3, 4, 8, 9, 10, 11, 16, 17, 18, 19, 33, 34] + list(range(cap - 9, cap + 1))
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum(sizes, out=off[1:])
+    x = np.empty(int(off[-1])); y = np.empty(int(off[-1]))
+    for i, nk in enumerate(sizes):
+        xi = 0.5 + np.cumsum(rng.uniform(0.2, 1.8, nk)) / nk
+        x[off[i]:off[i + 1]] = xi
+        y[off[i]:off[i + 1]] = 0.2 + 0.3 * np.log(xi) ** 2 + 0.003 * rng.standard_normal(nk)
+    xq = np.linspace(0.45, 1.6, 301)
+    for extrap in (0, 1):
+        got = D.spline_fit_eval(_t(off, dev), _t(x, dev), _t(y, dev), _t(xq, dev), max_knots=cap, extrap=extrap).cpu().numpy()
+        got = got.reshape(len(sizes), -1)
+        for i in range(len(sizes)):
+            want = O.natural_spline_eval(x[off[i]:off[i + 1]], y[off[i]:off[i + 1]], xq, extrap)
+            assert _eq(np.isnan(got[i]), np.isnan(want)), f"n={sizes[i]}: NaN mask"
+            ok = ~np.isnan(want)
+            # cubic extrapolation beyond the last knot of a 2000-knot noisy smile reaches 1e3: the bound is relative there
+            err = np.abs(got[i] - want)[ok] / np.maximum(1.0, np.abs(want[ok]))
+            assert err.max(initial=0.0) <= 1e-8, f"n={sizes[i]}: {err.max()}"
+
+
 @pytest.mark.parametrize("extrap", [1, 2])
 def test_spline_strided_vs_scipy(dev, extrap):
     from iv_interpolation_b200 import device as D
