@@ -168,17 +168,30 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   double* out = yq + sl * (int64_t)n_q;
 
   // ---- stage the slice (coalesced), NaN beyond its end ------------------------------------------------
+  // All of a thread's loads are issued before the first one is used (clamped addresses, no branch around them): one
+  // round trip to HBM per slice instead of one per row of the loop.
   bool fin = true;
+  {
+    double xl[SPL_R + 1], yl[SPL_R + 1];
 #pragma unroll
-  for (int r = 0; r < SPL_R + 1; ++r) {
-    const int j = r * G + g;
-    if (j < L::CAP + 2) {
-      double xv = qnan(), yv = qnan();
-      if (j < m) {
-        xv = x_off ? __ldg(x + xk0 + j) : ld_stream(x + xk0 + j); yv = ld_stream(y + k0 + j);
-        fin = fin && (fabs(xv) < INFINITY) && (fabs(yv) < INFINITY);
+    for (int r = 0; r < SPL_R + 1; ++r) { xl[r] = qnan(); yl[r] = qnan(); }
+    if (m > 0) {                           // group-uniform; an empty slice may sit at the very end of the arrays
+#pragma unroll
+      for (int r = 0; r < SPL_R + 1; ++r) {
+        const int jc = min(r * G + g, m - 1);
+        xl[r] = x_off ? __ldg(x + xk0 + jc) : ld_stream(x + xk0 + jc);
+        yl[r] = ld_stream(y + k0 + jc);
       }
-      xs[spl_pad(j)] = xv; ys[spl_pad(j)] = yv;
+    }
+#pragma unroll
+    for (int r = 0; r < SPL_R + 1; ++r) {
+      const int j = r * G + g;
+      if (j < L::CAP + 2) {
+        const bool in = j < m;
+        const double xv = in ? xl[r] : qnan(), yv = in ? yl[r] : qnan();
+        fin = fin && (!in || ((fabs(xv) < INFINITY) && (fabs(yv) < INFINITY)));
+        xs[spl_pad(j)] = xv; ys[spl_pad(j)] = yv;
+      }
     }
   }
   // a slice with every knot usable (the common case) is known at the barrier itself when the group is the whole CTA
@@ -432,7 +445,11 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   auto take = [&](double xl_, double xr_, double yl_, double yr_, double Ml_, double Mr_, bool last) {
     const double xr_take = last ? INFINITY : xr_;
     while (!(xq_cur >= xr_take)) {                                  // a NaN grid point is taken where it stands and yields NaN
-      const double v = spline_eval(xl_, xr_, yl_, yr_, Ml_, Mr_, xq_cur);
+      // most segments receive no grid point (8 segments, ~2 points per thread): the opaque move keeps the segment's
+      // reciprocal and products inside the loop instead of being hoisted in front of every segment's (empty) loop
+      double xl_in = xl_;
+      asm volatile("" : "+d"(xl_in));
+      const double v = spline_eval(xl_in, xr_, yl_, yr_, Ml_, Mr_, xq_cur);
       // only the first thread can see points below the first knot, only the last segment's owner points above the last
       st_stream(op, edge ? apply_extrap(v, xq_cur, xlo, xhi, ylo, yhi, extrap) : v);
       ++op; ++xqp; --left;
