@@ -123,6 +123,23 @@ __device__ __forceinline__ int lower_bound_q(const double* __restrict__ xq, int 
   return lo;
 }
 
+// the same with a starting guess: on a (near-)uniform grid the answer is within one of (v - xq[0]) * scale, so four
+// independent loads around the guess settle it in one L1 round trip; anything else falls back to the bisection
+__device__ __forceinline__ int lower_bound_q_guess(const double* __restrict__ xq, int n_q, double v, double xq0, double scale) {
+  const double t = (v - xq0) * scale;
+  const int gi = (t > 0.0) ? ((t < (double)n_q) ? (int)t : n_q) : 0;      // NaN -> 0
+  const int base = gi - 1;
+  double wv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = base + k;
+    const double ld = __ldg(xq + min(max(i, 0), n_q - 1));
+    wv[k] = i < 0 ? -INFINITY : (i >= n_q ? INFINITY : ld);
+  }
+  if ((wv[0] < v) && (wv[3] >= v)) return base + 1 + (wv[1] < v ? 1 : 0) + (wv[2] < v ? 1 : 0);
+  return lower_bound_q(xq, n_q, v);
+}
+
 template <int G, int SPL_R>
 struct SplLayout {
   static constexpr int BT = G < 256 ? 256 : G;
@@ -263,15 +280,20 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
     const double* __restrict__ cp_t = lu_cp + tb;
     const double* __restrict__ inv_t = lu_inv + tb;
     const double* __restrict__ ih_t = lu_ih + tb;
+    // table positions are always inside the table (j G + g < CAP): the loads are unconditional, issued together, and
+    // entries past the end of the ladder (never written) are discarded by the selects below
+    double ihv[SPL_R + 1], invv[SPL_R];
+#pragma unroll
+    for (int k = 0; k <= SPL_R; ++k) ihv[k] = __ldg(ih_t + (k < SPL_R ? k * G + g : (g + 1 < G ? g + 1 : g)));
+#pragma unroll
+    for (int j = 0; j < SPL_R; ++j) invv[j] = __ldg(inv_t + j * G + g);
     double slp[SPL_R + 1];                // slp[k] = slope of segment i0+k
     {
       double yl = ys[spl_pad(i0)];
 #pragma unroll
       for (int k = 0; k <= SPL_R; ++k) {
         const double yr = ys[spl_pad(i0 + k + 1)];
-        const bool segok = i0 + k <= n - 2;
-        const double ihv = segok ? __ldg(ih_t + (k < SPL_R ? k * G + g : g + 1)) : 0.0;
-        slp[k] = segok ? (yr - yl) * ihv : 0.0;
+        slp[k] = (i0 + k <= n - 2) ? (yr - yl) * ihv[k] : 0.0;
         yl = yr;
       }
     }
@@ -282,13 +304,10 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
 #pragma unroll
       for (int j = 0; j < SPL_R; ++j) {
         const double xr = xs[spl_pad(i0 + j + 1)];
-        al[j] = 0.0; bt[j] = 0.0;
-        if (j < nvalid) {
-          const double inv = __ldg(inv_t + j * G + g);
-          al[j] = 6.0 * (slp[j + 1] - slp[j]) * inv;
-          bt[j] = -(xr - xl) * inv;
-          A = fma(bt[j], A, al[j]); B *= bt[j];
-        }
+        const bool rowok = j < nvalid;
+        al[j] = rowok ? 6.0 * (slp[j + 1] - slp[j]) * invv[j] : 0.0;
+        bt[j] = rowok ? -(xr - xl) * invv[j] : 0.0;
+        if (rowok) { A = fma(bt[j], A, al[j]); B *= bt[j]; }
         xl = xr;
       }
     }
@@ -308,13 +327,13 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
     }
     d = fma(XB, d, XA);
 #pragma unroll
+    for (int j = 0; j < SPL_R; ++j) cv[j] = __ldg(cp_t + j * G + g);
+#pragma unroll
     for (int j = 0; j < SPL_R; ++j) {
-      cv[j] = 0.0; dv[j] = 0.0;
-      if (j < nvalid) {
-        d = fma(bt[j], d, al[j]);
-        dv[j] = d;
-        cv[j] = __ldg(cp_t + j * G + g);
-      }
+      const bool rowok = j < nvalid;
+      d = fma(bt[j], d, al[j]);            // rows past the end: bt = al = 0
+      dv[j] = rowok ? d : 0.0;
+      cv[j] = rowok ? cv[j] : 0.0;
     }
   } else {
     // ---- row coefficients.  Row i (1 <= i <= n-2) is multiplied by h[i-1] h[i], which clears both slope
@@ -429,7 +448,11 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   // the grid is sorted: thread g's points start at the first one >= x[i0+1] (thread 0: at the first point) and end
   // where thread g+1's start; the owner of the last segment (n-2) also takes everything above it
   const bool has_seg = i0 + 1 <= n - 2;
-  qs[g] = (g == 0) ? 0 : (has_seg ? lower_bound_q(xq, n_q, xs[spl_pad(i0 + 1)]) : n_q);
+  {
+    const double xq0 = __ldg(xq), xqN = __ldg(xq + n_q - 1);
+    const double scale = (double)(n_q - 1) * rcp_fast(xqN - xq0);    // inf/NaN on a degenerate grid: the guess fails, bisection runs
+    qs[g] = (g == 0) ? 0 : (has_seg ? lower_bound_q_guess(xq, n_q, xs[spl_pad(i0 + 1)], xq0, scale) : n_q);
+  }
   if (g == 0) qs[G] = n_q;
   group_sync<G>(grp);
   if (!has_seg && g > 0) return;
