@@ -220,6 +220,37 @@ int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, int32_t n_k
                                ivx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Data bridge — interpolated minute rows -> synthetic 1-minute OHLCV candles.
+ * Replaces reference src/data_bridge/ohlcv_converter.py:138-400 (InterpolatedToOHLCVConverter.
+ * _generate_ohlcv_from_interpolated, its four candle strategies, _process_volume :359-369 and
+ * _validate_ohlcv_quality :371-402) and complete_pipeline.py:473-510 (_generate_ohlcv_candles), for a
+ * CSR batch of symbols.  Rows whose base price is NaN or <= 0 emit nothing (:152).
+ * The reference draws from numpy's unseeded global generator; here the random input is passed as tapes
+ * in the reference's call order, symbol after symbol:
+ *   u  uniforms in [0,1): k per emitted row (k = 5 spread_simulation, 2 price_as_midpoint, 1 simple
+ *      spread, 4 pipeline, 0 trend_following); symbol s starts at u[k * out_off[s]];
+ *   e  standard exponentials: one per emitted row whose volume is NaN or <= 0; symbol s starts at e[e_off[s]];
+ *   z  standard normals (trend_following only): one per emitted row; symbol s starts at z[out_off[s]].
+ * With tapes drawn from a RandomState seeded like the reference's generator the candles are bit-equal to
+ * the reference's.  strategy: 0 spread_simulation (prev-close trend bias), 1 price_as_midpoint,
+ * 2 trend_following, 3 simple spread (the reference's fallback for every other string), 4 pipeline.
+ * ivx_bridge_count gives, per symbol, the emitted rows and exponential draws; their exclusive scans
+ * (ivx_exclusive_scan_i64) are out_off and e_off.  o_row[j] is the global input row of candle j
+ * (timestamps and symbols are gathered from it).  sym_quality[s]: bit 0 high<low, 1 high<open|close,
+ * 2 low>open|close, 3 (high-low)/source > 0.1, 4 a price <= 0 — the checks of _validate_ohlcv_quality,
+ * which reports the lowest set bit.
+ * ------------------------------------------------------------------------------------------- */
+int ivx_bridge_count(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
+                     int64_t* n_out /*n_sym*/, int64_t* n_e /*n_sym*/, ivx_stream_t stream);
+int ivx_bridge_ohlcv(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
+                     int32_t strategy, double base_spread_percent, double volatility_factor,
+                     const double* u, const double* e, const double* z,
+                     const int64_t* out_off /*n_sym+1*/, const int64_t* e_off /*n_sym+1*/,
+                     int64_t* o_row, double* o_open, double* o_high, double* o_low, double* o_close,
+                     double* o_volume, double* o_source, uint32_t* sym_quality /*n_sym or NULL*/,
+                     ivx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Utilities: exclusive scan of int64, stream-copy and fp64-FMA microbenchmarks that give the
  * roofline denominators measured in the same run (bench.py).
  * ------------------------------------------------------------------------------------------- */

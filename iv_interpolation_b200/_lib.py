@@ -19,6 +19,9 @@ FLAG_IN_BAD_OHLC, FLAG_IN_NEG_VOLUME, FLAG_IN_NAN = 1, 2, 4
 FLAG_OUT_BAD_OHLC, FLAG_OUT_NEG_VOLUME, FLAG_OUT_NAN = 8, 16, 32
 FLAG_UNSORTED, FLAG_NONFINITE = 64, 128
 MAX_FILL_COLS, MAX_IDX_COLS = 8, 4
+BRIDGE_STRATEGY = {"spread_simulation": 0, "price_as_midpoint": 1, "trend_following": 2, "simple_spread": 3, "pipeline": 4}
+BRIDGE_U_PER_ROW = {0: 5, 1: 2, 2: 0, 3: 1, 4: 4}
+Q_HIGH_LT_LOW, Q_HIGH_LT_OC, Q_LOW_GT_OC, Q_SPREAD, Q_NONPOSITIVE = 1, 2, 4, 8, 16
 
 
 class IvxError(RuntimeError):
@@ -58,6 +61,9 @@ SIGNATURES = {
     "ivx_bs_implied_vol_chain": (C.c_int, [_i64, _i64, _i64, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_spline_strided": (C.c_int, [_i64, _i32, _p, _p, _i32, _p, _i32, _p, _p]),
     "ivx_spline_strided_batched": (C.c_int, [_i64, _i64, _i32, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p]),
+    "ivx_bridge_count": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
+    "ivx_bridge_ohlcv": (C.c_int, [_i64, _p, _p, _p, _i32, C.c_double, C.c_double, _p, _p, _p, _p, _p,
+                                   _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ivx_exclusive_scan_i64": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_copy": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_fp64_fma": (C.c_int, [_i64, _i32, _p, _p]),

@@ -1,0 +1,236 @@
+// ivx_bridge.cu — the data bridge: interpolated minute rows -> synthetic 1-minute OHLCV candles.
+//
+// Replaces, for a CSR batch of symbols, reference src/data_bridge/ohlcv_converter.py:138-400
+// (_generate_ohlcv_from_interpolated and its four candle strategies, _process_volume, _validate_ohlcv_quality) and
+// complete_pipeline.py:473-510 (_generate_ohlcv_candles).  The reference draws from numpy's global generator row by
+// row; here the random input arrives as TAPES in the reference's call order — uniforms u (k per emitted row, k fixed
+// per strategy), standard exponentials e (one per emitted row whose volume is missing), standard normals z (one per
+// emitted row, trend_following only) — so with tapes drawn from an identically seeded RandomState every candle is
+// bit-equal to the reference's (tests/golden/bridge_cases.npz).
+//
+// This file is compiled with --fmad=false: numpy evaluates every expression with separate multiplies and adds, and a
+// fused multiply-add here would change last bits.  round(x, 4) on an np.float64 is rint(x * 1e4) / 1e4.
+//
+// k_bridge_count: one warp per symbol, coalesced pass over base/volume -> emitted rows and exponential draws per symbol
+//   (two exclusive scans then give every symbol its place in the outputs and in the tapes).
+// k_bridge_ohlcv: one warp per symbol, 32 rows per step.  Loads are coalesced (a lane's k uniforms are contiguous, the
+//   warp's 32 k are too); emitted rows are compacted with a ballot.  What cannot be row-parallel is the dependence of a
+//   candle on the ROUNDED close of the previous emitted candle (spread_simulation: trend bias; trend_following: the
+//   last five closes): that chain is walked lane by lane with the carried closes in warp-uniform registers, and only
+//   the close chain itself sits in the serial loop — opens, highs, lows, volumes and the quality checks are formed in
+//   parallel once every lane knows its predecessor's close.
+// HBM traffic: 16 B per input row + 8 k B of tape + 56 B per emitted candle.
+#include "ivx_common.cuh"
+
+namespace ivx {
+namespace {
+
+enum : int { ST_SPREAD = 0, ST_MIDPOINT = 1, ST_TREND = 2, ST_SIMPLE = 3, ST_PIPELINE = 4 };
+constexpr uint32_t Q_HIGH_LT_LOW = 1, Q_HIGH_LT_OC = 2, Q_LOW_GT_OC = 4, Q_SPREAD = 8, Q_NONPOSITIVE = 16;
+
+__device__ __forceinline__ int u_per_row(int strategy) {
+  return strategy == ST_SPREAD ? 5 : strategy == ST_MIDPOINT ? 2 : strategy == ST_PIPELINE ? 4 : strategy == ST_SIMPLE ? 1 : 0;
+}
+__device__ __forceinline__ bool row_ok(double b) { return !(isnan(b) || b <= 0.0); }            // ohlcv_converter.py:152
+__device__ __forceinline__ bool vol_missing(double v) { return isnan(v) || v <= 0.0; }          // :373
+__device__ __forceinline__ double round_np(double x, double s) { return rint(x * s) / s; }      // np.float64.__round__
+__device__ __forceinline__ double uni(double lo, double hi, double u) { return lo + (hi - lo) * u; }   // RandomState.uniform
+
+__global__ void __launch_bounds__(256) k_bridge_count(int64_t n_sym, const int64_t* __restrict__ in_off,
+                                                      const double* __restrict__ base, const double* __restrict__ volume,
+                                                      int64_t* __restrict__ n_out, int64_t* __restrict__ n_e) {
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_sym) return;
+  const int lane = lane_id();
+  const int64_t a = in_off[s], b = in_off[s + 1];
+  int64_t c_ok = 0, c_e = 0;
+  for (int64_t r = a + lane; r < b; r += 32) {
+    const bool ok = row_ok(ld_stream(base + r));
+    c_ok += ok ? 1 : 0;
+    c_e += (ok && vol_missing(ld_stream(volume + r))) ? 1 : 0;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    c_ok += __shfl_xor_sync(IVX_FULL_MASK, c_ok, d);
+    c_e += __shfl_xor_sync(IVX_FULL_MASK, c_e, d);
+  }
+  if (lane == 0) { n_out[s] = c_ok; n_e[s] = c_e; }
+}
+
+struct BridgeParams {
+  int64_t n_sym;
+  const int64_t* in_off;
+  const double *base, *volume;
+  int strategy;
+  double base_spread_percent, volatility_factor;
+  const double *u, *e, *z;
+  const int64_t *out_off, *e_off;
+  int64_t* o_row;
+  double *o_open, *o_high, *o_low, *o_close, *o_volume, *o_source;
+  uint32_t* sym_quality;
+};
+
+template <int STRATEGY>
+__global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= P.n_sym) return;
+  const int lane = lane_id();
+  const uint32_t lt = (1u << lane) - 1u;
+  constexpr int K = STRATEGY == ST_SPREAD ? 5 : STRATEGY == ST_MIDPOINT ? 2 : STRATEGY == ST_PIPELINE ? 4 : STRATEGY == ST_SIMPLE ? 1 : 0;
+  const int64_t a = P.in_off[s], b = P.in_off[s + 1];
+  int64_t o_base = P.out_off[s], e_base = P.e_off[s];
+  // closes of the candles emitted so far (rounded, newest first): warp-uniform
+  double pc1 = 0.0, pc2 = 0.0, pc3 = 0.0, pc4 = 0.0, pc5 = 0.0;
+  int n_prev = 0;
+  uint32_t qflags = 0;
+  for (int64_t r0 = a; r0 < b; r0 += 32) {
+    const int64_t r = r0 + lane;
+    const bool in = r < b;
+    const double bp = in ? ld_stream(P.base + r) : qnan();
+    const double vin = in ? ld_stream(P.volume + r) : 1.0;
+    const bool ok = in && row_ok(bp);
+    const bool nv = ok && vol_missing(vin);
+    const uint32_t okm = __ballot_sync(IVX_FULL_MASK, ok), nvm = __ballot_sync(IVX_FULL_MASK, nv);
+    const int64_t o = o_base + __popc(okm & lt);
+    double uu[K > 0 ? K : 1];
+#pragma unroll
+    for (int k = 0; k < K; ++k) uu[k] = ok ? ld_stream(P.u + o * K + k) : 0.0;
+    const double ev = nv ? ld_stream(P.e + e_base + __popc(nvm & lt)) : 0.0;
+    double op = 0.0, hp = 0.0, lp = 0.0, cp = 0.0;         // unrounded open/high/low, ROUNDED close
+    if (STRATEGY == ST_SPREAD) {
+      const double vm = uni(0.5, P.volatility_factor, uu[0]);                  // :215
+      const double spread = bp * P.base_spread_percent * vm;                   // :216
+      const double third = spread / 3.0;
+      const double oo = uni(-third, third, uu[1]), co = uni(-third, third, uu[2]);
+      // ---- the close chain: close = base + (co + ((base - prev_close) * 0.3) * 0.5), rounded, lane after lane ----
+      double prev = 0.0;                                   // my predecessor's rounded close
+      bool has_prev = false;
+      uint32_t mm = okm;
+      while (mm) {
+        const int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (lane == src) {
+          prev = pc1; has_prev = n_prev > 0;
+          const double tb = has_prev ? (bp - pc1) * 0.3 : 0.0;                 // :219-222
+          cp = round_np(bp + (co + tb * 0.5), 1e4);                             // :228-229, :256
+        }
+        pc1 = __shfl_sync(IVX_FULL_MASK, cp, src);
+        n_prev = 1;
+      }
+      const double tb = has_prev ? (bp - prev) * 0.3 : 0.0;
+      op = bp + (oo + tb * 0.2);                                                // :225-226
+      const double cu = bp + (co + tb * 0.5);                                   // the unrounded close
+      const double mid = (op + cu) / 2.0;                                       // :232
+      const double he = uni(0.0, spread / 2.0, uu[3]), lr = uni(0.0, spread / 2.0, uu[4]);
+      hp = (cu > op ? cu : op) + he;                                            // :236  max(open, close)
+      lp = (cu < op ? cu : op) - lr;                                            // :237
+      if (hp - lp < bp * 0.0005) { hp = mid + bp * 0.00025; lp = mid - bp * 0.00025; }   // :240-242
+    } else if (STRATEGY == ST_MIDPOINT) {
+      const double spread = bp * 0.001, q = spread / 4.0;                       // :268-269
+      op = bp + uni(-q, q, uu[0]);
+      cp = round_np(bp + uni(-q, q, uu[1]), 1e4);
+      hp = bp + spread / 2.0; lp = bp - spread / 2.0;
+    } else if (STRATEGY == ST_SIMPLE) {
+      const double spread = bp * 0.001, hs = spread / 2.0;                      // :345
+      op = bp;
+      cp = round_np(bp + uni(-hs, hs, uu[0]), 1e4);
+      hp = bp + hs; lp = bp - hs;
+    } else if (STRATEGY == ST_PIPELINE) {                                       // complete_pipeline.py:483-492
+      const double spread = bp * 0.001, third = spread / 3.0;
+      op = bp + uni(-third, third, uu[0]);
+      const double cu = bp + uni(-third, third, uu[1]);
+      hp = (cu > op ? cu : op) + fabs(uni(0.0, spread / 2.0, uu[2]));
+      lp = (cu < op ? cu : op) - fabs(uni(0.0, spread / 2.0, uu[3]));
+      cp = round_np(cu, 1e4);
+    } else {                                                                    // trend_following :293-340
+      const double zv = ok ? ld_stream(P.z + o) : 0.0;
+      const double noise = 0.0 + (bp * 0.001) * zv;                             // np.random.normal(0, base * 0.001)
+      uint32_t mm = okm;
+      while (mm) {
+        const int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (lane == src) {
+          const int lookback = n_prev < 5 ? n_prev : 5;                         // :296
+          double trend = 0.0;
+          if (lookback > 1) {
+            const double oldest = lookback == 2 ? pc2 : lookback == 3 ? pc3 : lookback == 4 ? pc4 : pc5;
+            trend = (pc1 - oldest) / (double)lookback;                          // :302
+          }
+          const double ts = trend * 0.6;
+          op = bp + ts + noise;                                                 // :308
+          const double cu = bp + ts * 1.2 + noise;                              // :309
+          const double at = fabs(trend);
+          const double mx = cu > op ? cu : op, mn = cu < op ? cu : op;
+          if (trend > 0.0) { hp = mx + at * 0.5; lp = mn - at * 0.2; }          // :312-317
+          else { hp = mx + at * 0.2; lp = mn - at * 0.5; }
+          cp = round_np(cu, 1e4);
+        }
+        pc5 = pc4; pc4 = pc3; pc3 = pc2; pc2 = pc1;
+        pc1 = __shfl_sync(IVX_FULL_MASK, cp, src);
+        ++n_prev;
+      }
+    }
+    if (ok) {
+      double v = nv ? 50.0 * ev : vin;                                          // :373-376
+      v = v > 0.0 ? v : 0.0;                                                    // max(0, volume) :378
+      const double ro = round_np(op, 1e4), rh = round_np(hp, 1e4), rl = round_np(lp, 1e4);
+      st_stream(P.o_row + o, r);
+      st_stream(P.o_open + o, ro); st_stream(P.o_high + o, rh); st_stream(P.o_low + o, rl); st_stream(P.o_close + o, cp);
+      st_stream(P.o_volume + o, round_np(v, 1e6));
+      st_stream(P.o_source + o, bp);
+      // _validate_ohlcv_quality :385-405
+      if (rh < rl) qflags |= Q_HIGH_LT_LOW;
+      if (rh < ro || rh < cp) qflags |= Q_HIGH_LT_OC;
+      if (rl > ro || rl > cp) qflags |= Q_LOW_GT_OC;
+      if ((rh - rl) / bp > 0.1) qflags |= Q_SPREAD;
+      if (ro <= 0.0 || rh <= 0.0 || rl <= 0.0 || cp <= 0.0) qflags |= Q_NONPOSITIVE;
+    }
+    o_base += __popc(okm);
+    e_base += __popc(nvm);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) qflags |= __shfl_xor_sync(IVX_FULL_MASK, qflags, d);
+  if (lane == 0 && P.sym_quality) P.sym_quality[s] = qflags;
+}
+
+}  // namespace
+}  // namespace ivx
+
+using namespace ivx;
+
+extern "C" int ivx_bridge_count(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
+                                int64_t* n_out, int64_t* n_e, ivx_stream_t stream) {
+  IVX_REQUIRE(n_sym >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_count: negative n_sym");
+  if (n_sym == 0) return IVX_OK;
+  IVX_REQUIRE(in_off && base && volume && n_out && n_e, IVX_ERR_INVALID_ARG, "ivx_bridge_count: null pointer");
+  k_bridge_count<<<(unsigned)((n_sym + 7) / 8), 256, 0, (cudaStream_t)stream>>>(n_sym, in_off, base, volume, n_out, n_e);
+  IVX_LAUNCH_CHECK("k_bridge_count");
+  return IVX_OK;
+}
+
+extern "C" int ivx_bridge_ohlcv(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
+                                int32_t strategy, double base_spread_percent, double volatility_factor, const double* u,
+                                const double* e, const double* z, const int64_t* out_off, const int64_t* e_off,
+                                int64_t* o_row, double* o_open, double* o_high, double* o_low, double* o_close,
+                                double* o_volume, double* o_source, uint32_t* sym_quality, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_sym >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: negative n_sym");
+  IVX_REQUIRE(strategy >= ST_SPREAD && strategy <= ST_PIPELINE, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: unknown strategy %d", strategy);
+  if (n_sym == 0) return IVX_OK;
+  IVX_REQUIRE(in_off && base && volume && out_off && e_off && o_row && o_open && o_high && o_low && o_close && o_volume && o_source,
+              IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: null pointer");
+  IVX_REQUIRE(strategy == ST_TREND ? z != nullptr : u != nullptr, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: the strategy's tape is missing");
+  IVX_REQUIRE(e != nullptr, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: the exponential tape is missing (pass any valid pointer when it is empty)");
+  BridgeParams P{n_sym, in_off, base, volume, strategy, base_spread_percent, volatility_factor, u, e, z, out_off, e_off,
+                 o_row, o_open, o_high, o_low, o_close, o_volume, o_source, sym_quality};
+  const unsigned blocks = (unsigned)((n_sym + 3) / 4);
+  switch (strategy) {
+    case ST_SPREAD: k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P); break;
+    case ST_MIDPOINT: k_bridge_ohlcv<ST_MIDPOINT><<<blocks, 128, 0, stream>>>(P); break;
+    case ST_TREND: k_bridge_ohlcv<ST_TREND><<<blocks, 128, 0, stream>>>(P); break;
+    case ST_SIMPLE: k_bridge_ohlcv<ST_SIMPLE><<<blocks, 128, 0, stream>>>(P); break;
+    default: k_bridge_ohlcv<ST_PIPELINE><<<blocks, 128, 0, stream>>>(P); break;
+  }
+  IVX_LAUNCH_CHECK("k_bridge_ohlcv");
+  return IVX_OK;
+}

@@ -1,0 +1,223 @@
+"""InterpolatedToOHLCVConverter — the reference's data bridge (src/data_bridge/ohlcv_converter.py:16-418) on the B200.
+
+Same class name, constructor and method names as the reference; the candle arithmetic runs in libivx.so
+(``k_bridge_count`` + ``k_bridge_ohlcv``, include/ivx.h "Data bridge").  No CPU fallback.
+
+Randomness.  The reference calls ``np.random.uniform / exponential / normal`` row by row on numpy's GLOBAL generator.
+This class takes its draws from the same place in the same order (one ``random_sample`` per uniform or exponential,
+``standard_normal`` for the trend-following noise), so after ``np.random.seed(s)`` it returns the frames the
+reference returns after ``np.random.seed(s)`` — bit for bit — and leaves the generator in the same state.  Pass
+``rng=np.random.RandomState(...)`` to use a private stream instead.
+
+Database I/O (``get_interpolated_symbols``, ``convert_symbol_to_ohlcv``'s SELECT, ``_save_ohlcv_candles``,
+``convert_batch``: reference :31-136, :420-520) is out of scope; ``convert_frames`` is the DB-free
+batch entry with the reference's per-symbol status dictionaries (:113-135).
+"""
+from __future__ import annotations
+
+import logging
+import math
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+logger = logging.getLogger(__name__)
+
+PRICE_PRIORITY = ["underlying_price", "mark_price", "index_price"]            # reference :192
+_METHOD_NAME = {"spread_simulation": "spread_simulation", "price_as_midpoint": "price_midpoint",
+                "trend_following": "trend_following", "simple_spread": "simple_spread"}
+_Q_REASONS = ((1, "High < Low found"), (2, "High < Open/Close found"), (4, "Low > Open/Close found"),
+              (8, "Unrealistic spreads detected"), (16, "Negative or zero prices found"))
+_U_PER_ROW = {"spread_simulation": 5, "price_as_midpoint": 2, "trend_following": 0, "simple_spread": 1, "pipeline": 4}
+
+
+def canonical_strategy(name: str) -> str:
+    """The reference's dispatch (:158-166): unknown strings — including the 'price_midpoint' its own config comment
+    suggests (config.py:60) — take the simple-spread fallback."""
+    return name if name in ("spread_simulation", "price_as_midpoint", "trend_following", "pipeline") else "simple_spread"
+
+
+def draw_tapes(rs, strategy: str, ok: np.ndarray, need_vol: np.ndarray):
+    """Draw (u, e, z) for the emitted rows of one or more symbols from ``rs`` (``np.random`` or a ``RandomState``) in the
+    reference's call order.  ``ok``: rows that emit a candle; ``need_vol``: rows among them whose volume is drawn."""
+    nv = need_vol[ok]
+    n_rows, n_e = int(ok.sum()), int(nv.sum())
+    if strategy == "trend_following":
+        if n_e == 0:
+            return np.zeros(0), np.zeros(0), np.asarray(rs.standard_normal(n_rows), dtype=np.float64).reshape(-1)
+        z, e = np.empty(n_rows), []
+        for i, need in enumerate(nv):              # normals and exponentials interleave in the generator: call by call
+            z[i] = rs.standard_normal()
+            if need:
+                e.append(rs.standard_exponential())
+        return np.zeros(0), np.asarray(e, dtype=np.float64), z
+    k = _U_PER_ROW[strategy]
+    per_row = k + nv.astype(np.int64)
+    stream = np.asarray(rs.random_sample(int(per_row.sum())), dtype=np.float64).reshape(-1)
+    start = np.cumsum(per_row) - per_row
+    u = stream[(start[:, None] + np.arange(k)[None, :]).reshape(-1)] if n_rows else np.zeros(0)
+    # legacy standard_exponential is -log(1 - u) through the C library's log; math.log is that function
+    e = np.asarray([-math.log(1.0 - float(stream[s + k])) for s in start[nv]], dtype=np.float64)
+    return u, e, np.zeros(0)
+
+
+class InterpolatedToOHLCVConverter:
+    """Convert Task 1 interpolated rows to Task 2 OHLCV candles (B200 implementation)."""
+
+    def __init__(self, db_manager=None, config=None, rng=None, device=None):
+        self.db_manager = db_manager
+        self.config = config
+        bridge = getattr(config, "data_bridge", None)
+        self.conversion_strategy = getattr(bridge, "conversion_strategy", "spread_simulation")      # :26
+        self.spread_method = getattr(bridge, "spread_method", "adaptive")
+        self.quality_checks = getattr(bridge, "enable_quality_checks", True)
+        self._spread_parameters = getattr(bridge, "spread_parameters", None) or {}
+        self._rng = rng
+        self._device = device
+
+    # -- the reference's per-frame entry (:138-188) ------------------------------------------------------
+    def _generate_ohlcv_from_interpolated(self, df: pd.DataFrame) -> Optional[pd.DataFrame]:
+        if df.empty:
+            return None
+        try:
+            out = self._generate_many([df], self.conversion_strategy)[0]
+            return out["frame"]
+        except Exception as e:                                                    # :186-188
+            logger.error(f"OHLCV generation failed: {e}")
+            return None
+
+    # complete_pipeline.py:473-510 — same bridge, fixed 0.1 % spread, no clean-up; returns an EMPTY frame when nothing is emitted
+    def _generate_ohlcv_candles(self, data: pd.DataFrame) -> pd.DataFrame:
+        res = self._generate_many([data], "pipeline")[0]["frame"]
+        return res if res is not None else pd.DataFrame()
+
+    def _select_price_column(self, df: pd.DataFrame) -> str:
+        """Reference :189-207."""
+        for col in PRICE_PRIORITY:
+            if col in df.columns:
+                non_null_count = df[col].notna().sum()
+                if non_null_count > len(df) * 0.8:
+                    logger.debug(f"Using {col} as primary price source ({non_null_count}/{len(df)} valid)")
+                    return col
+        for col in PRICE_PRIORITY:
+            if col in df.columns:
+                logger.warning(f"Using {col} as fallback price source (limited data)")
+                return col
+        raise ValueError("No suitable price column found")
+
+    def _validate_ohlcv_quality(self, ohlcv_df: pd.DataFrame) -> Dict:
+        """Reference :371-402, on a frame (host arithmetic on a frame already on the host; the batch path gets the same
+        verdict from the kernel's flag bits)."""
+        try:
+            o, h, l, c = (ohlcv_df[k].to_numpy(dtype=np.float64) for k in ("open", "high", "low", "close"))
+            src = ohlcv_df["source_price"].to_numpy(dtype=np.float64)
+            flags = 0
+            with np.errstate(invalid="ignore", divide="ignore"):
+                flags |= 1 if (h < l).any() else 0
+                flags |= 2 if ((h < o) | (h < c)).any() else 0
+                flags |= 4 if ((l > o) | (l > c)).any() else 0
+                flags |= 8 if (((h - l) / src) > 0.1).any() else 0
+                flags |= 16 if ((o <= 0) | (h <= 0) | (l <= 0) | (c <= 0)).any() else 0
+            return self._quality_verdict(flags)
+        except Exception as e:
+            return {"valid": False, "reason": f"Validation error: {str(e)}"}
+
+    @staticmethod
+    def _quality_verdict(flags: int) -> Dict:
+        for bit, reason in _Q_REASONS:
+            if flags & bit:
+                return {"valid": False, "reason": reason}
+        return {"valid": True, "reason": "All quality checks passed"}
+
+    # -- DB-free batch entry: frames in, frames + the reference's status dictionaries out (:113-135) --------------------
+    def convert_frames(self, frames: Sequence[pd.DataFrame], symbols: Optional[Sequence[str]] = None) -> List[Dict]:
+        t0 = time.time()
+        symbols = list(symbols) if symbols is not None else [
+            (str(f["symbol"].iloc[0]) if len(f) and "symbol" in f.columns else f"#{i}") for i, f in enumerate(frames)]
+        results: List[Dict] = []
+        try:
+            gen = self._generate_many(frames, self.conversion_strategy)
+        except Exception as e:                                                    # :127-136
+            return [{"symbol": s, "status": "error", "error": str(e), "processing_time": time.time() - t0} for s in symbols]
+        dt = time.time() - t0
+        for sym, f, g in zip(symbols, frames, gen):
+            if f.empty:
+                results.append({"symbol": sym, "status": "skipped", "reason": "No interpolated data found"})       # :92
+            elif g["frame"] is None or g["frame"].empty:
+                results.append({"symbol": sym, "status": "error", "error": "OHLCV conversion failed"})            # :98
+            elif self.quality_checks and not g["quality"]["valid"]:
+                results.append({"symbol": sym, "status": "error", "error": f"Quality check failed: {g['quality']['reason']}"})
+            else:
+                results.append({"symbol": sym, "status": "success", "input_points": len(f), "output_candles": len(g["frame"]),
+                                "processing_time": dt / max(1, len(frames)), "conversion_method": self.conversion_strategy,
+                                "ohlcv": g["frame"]})
+        return results
+
+    # -- one launch for any number of frames -------------------------------------------------------------------------
+    def _generate_many(self, frames: Sequence[pd.DataFrame], strategy_name: str) -> List[Dict]:
+        import torch
+
+        from .. import device as D
+
+        strategy = canonical_strategy(strategy_name)
+        rs = self._rng if self._rng is not None else np.random
+        dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        pipeline = strategy == "pipeline"
+        ts_col = "date" if pipeline else "timestamp"
+        bases, vols, lens = [], [], []
+        for f in frames:
+            if f.empty:
+                bases.append(np.zeros(0)); vols.append(np.zeros(0)); lens.append(0)
+                continue
+            if pipeline:                                   # complete_pipeline.py:478: a or b or c on floats (NaN truthy, 0.0 not)
+                u_, m_, i_ = (f[c].to_numpy(dtype=np.float64) for c in PRICE_PRIORITY)
+                b = np.where(u_ != 0, u_, np.where(m_ != 0, m_, i_))
+            else:
+                col = self._select_price_column(f)         # raises ValueError -> caller's except, like :144-148
+                b = f[col].to_numpy(dtype=np.float64)
+            v = f["volume"].to_numpy(dtype=np.float64) if "volume" in f.columns else np.zeros(len(f))   # row.get('volume', 0)
+            bases.append(b); vols.append(v); lens.append(len(f))
+        off = np.zeros(len(frames) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        base = np.concatenate(bases) if bases else np.zeros(0)
+        vol = np.concatenate(vols) if vols else np.zeros(0)
+        with np.errstate(invalid="ignore"):
+            ok = ~(np.isnan(base) | (base <= 0))
+            need = ok & (np.isnan(vol) | (vol <= 0))
+        u, e, z = draw_tapes(rs, strategy, ok, need)       # symbol after symbol, row after row: the reference's order
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d_off, d_base, d_vol = t(off), t(base), t(vol)
+        plan = D.bridge_plan(d_off, d_base, d_vol)
+        if plan.total != int(ok.sum()) or plan.total_e != int(need.sum()):
+            raise RuntimeError("bridge plan disagrees with the host's row classification")
+        res = D.bridge_ohlcv(d_off, d_base, d_vol, plan, strategy, u=t(u) if len(u) else None, e=t(e), z=t(z) if len(z) else None,
+                             base_spread_percent=self._spread_parameters.get("base_spread_percent", 0.002),      # :210-211
+                             volatility_factor=self._spread_parameters.get("volatility_factor", 1.5))
+        out_off = res.out_off.cpu().numpy()
+        row = res.row.cpu().numpy()
+        cols = {k: getattr(res, k).cpu().numpy() for k in ("open", "high", "low", "close", "volume", "source_price")}
+        quality = res.sym_quality.cpu().numpy()
+        out: List[Dict] = []
+        for i, f in enumerate(frames):
+            a, b_ = int(out_off[i]), int(out_off[i + 1])
+            if b_ == a:
+                out.append({"frame": None, "quality": self._quality_verdict(0)})          # :170-171 no candles -> None
+                continue
+            src = row[a:b_] - off[i]
+            data = {"symbol": f["symbol"].to_numpy()[src] if "symbol" in f.columns else None}
+            if data["symbol"] is None:
+                raise KeyError("symbol")
+            data["timestamp"] = pd.to_datetime(f[ts_col]).to_numpy()[src]
+            for k in ("open", "high", "low", "close", "volume", "source_price"):
+                data[k] = cols[k][a:b_]
+            if not pipeline:
+                data["conversion_method"] = _METHOD_NAME[strategy]
+            data["is_synthetic"] = True
+            frame = pd.DataFrame(data)
+            if not pipeline:                               # _cleanup_ohlcv_data :404-418
+                frame = frame.dropna(subset=["open", "high", "low", "close"])
+                frame = frame.sort_values("timestamp")
+            out.append({"frame": frame, "quality": self._quality_verdict(int(quality[i]))})
+        return out

@@ -22,6 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2, "spline_ladder_factor": 1,
+    "bridge_count": 1, "bridge_ohlcv": 1,
 }
 
 
@@ -464,6 +465,75 @@ def spline_strided_batched(x: torch.Tensor, x_batch_stride: int, x_knot_stride: 
     global _LAUNCHES
     _LAUNCHES += max(1, _LAUNCH_EXTRA)
     return yq
+
+
+# ------------------------------------------------------------------------------------------------
+# Data bridge
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class BridgePlan:
+    out_off: torch.Tensor          # int64[n_sym+1] emitted candles before each symbol
+    e_off: torch.Tensor            # int64[n_sym+1] exponential draws before each symbol
+    total: int
+    total_e: int
+
+
+@dataclass
+class BridgeBatch:
+    out_off: torch.Tensor          # int64[n_sym+1]
+    row: torch.Tensor              # int64[m] global input row of each candle
+    open: torch.Tensor
+    high: torch.Tensor
+    low: torch.Tensor
+    close: torch.Tensor
+    volume: torch.Tensor
+    source_price: torch.Tensor
+    sym_quality: torch.Tensor      # int32[n_sym] bit flags of _validate_ohlcv_quality
+    total: int
+
+
+def bridge_plan(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor) -> BridgePlan:
+    """Rows that emit a candle (base price neither NaN nor <= 0, ohlcv_converter.py:152) and rows among them whose
+    volume is drawn (NaN or <= 0, :373), per symbol, as exclusive scans: the tape layout of ``bridge_ohlcv``."""
+    n_sym = in_off.numel() - 1
+    n_out = _empty(n_sym, torch.int64, in_off)
+    n_e = _empty(n_sym, torch.int64, in_off)
+    check(lib().ivx_bridge_count(n_sym, _ptr(_req(in_off, torch.int64, "in_off")), _ptr(_req(base, torch.float64, "base")),
+                                 _ptr(_req(volume, torch.float64, "volume")), _ptr(n_out), _ptr(n_e), _stream()), "ivx_bridge_count")
+    _count("bridge_count")
+    out_off, e_off = exclusive_scan(n_out), exclusive_scan(n_e)
+    totals = torch.stack([out_off[-1], e_off[-1]]).cpu()          # 16 bytes: sizes of the outputs and of the tapes
+    return BridgePlan(out_off, e_off, int(totals[0]), int(totals[1]))
+
+
+def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor, plan: BridgePlan, strategy: str, *,
+                 u: Optional[torch.Tensor] = None, e: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
+                 base_spread_percent: float = 0.002, volatility_factor: float = 1.5) -> BridgeBatch:
+    """Synthetic 1-minute candles from interpolated rows, every candle bit-equal to the reference's given the same
+    random tapes (see include/ivx.h).  ``strategy`` is one of _lib.BRIDGE_STRATEGY."""
+    code = _lib.BRIDGE_STRATEGY[strategy]
+    k = _lib.BRIDGE_U_PER_ROW[code]
+    n_sym = in_off.numel() - 1
+    m = plan.total
+    if k and (u is None or u.numel() < k * m):
+        raise _lib.IvxError(f"bridge_ohlcv: strategy {strategy} needs {k * m} uniforms, got {0 if u is None else u.numel()}")
+    if code == 2 and (z is None or z.numel() < m):
+        raise _lib.IvxError(f"bridge_ohlcv: trend_following needs {m} normals, got {0 if z is None else z.numel()}")
+    if e is None or e.numel() < plan.total_e:
+        raise _lib.IvxError(f"bridge_ohlcv: {plan.total_e} exponential draws needed, got {0 if e is None else e.numel()}")
+    if e.numel() == 0:
+        e = _empty(1, torch.float64, base)
+    cols = [_empty(m, torch.float64, base) for _ in range(6)]
+    row = _empty(m, torch.int64, base)
+    q = torch.zeros(n_sym, dtype=torch.int32, device=base.device)
+    check(lib().ivx_bridge_ohlcv(n_sym, _ptr(in_off), _ptr(_req(base, torch.float64, "base")), _ptr(_req(volume, torch.float64, "volume")),
+                                 code, float(base_spread_percent), float(volatility_factor),
+                                 _ptr(_req(u, torch.float64, "u")) if u is not None else None, _ptr(_req(e, torch.float64, "e")),
+                                 _ptr(_req(z, torch.float64, "z")) if z is not None else None,
+                                 _ptr(plan.out_off), _ptr(plan.e_off), _ptr(row), *(_ptr(c) for c in cols), _ptr(q), _stream()),
+          "ivx_bridge_ohlcv")
+    _count("bridge_ohlcv")
+    return BridgeBatch(plan.out_off, row, *cols, q, m)
 
 
 # ------------------------------------------------------------------------------------------------

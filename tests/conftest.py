@@ -31,3 +31,9 @@ def golden_kats():
     import json
     with open(os.path.join(GOLDEN, "kats.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_bridge():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "bridge_cases.npz"), allow_pickle=False)

@@ -87,6 +87,36 @@ def test_dropin_contract_without_gpu():
             CandleReconstructor("5min").reconstruct_batch([df])
 
 
+def test_bridge_contract_without_gpu():
+    """The bridge class keeps the reference's never-raise contract (ohlcv_converter.py:141-142, :186-188) and, without a
+    device, fails inside (logged) instead of producing candles on the CPU; its tape draws still follow numpy's generator."""
+    import types
+    import torch
+    from iv_interpolation_b200.data_bridge import ohlcv_converter as OC
+    cfg = types.SimpleNamespace(data_bridge=types.SimpleNamespace(conversion_strategy="price_midpoint", spread_method="adaptive",
+                                                                  enable_quality_checks=True, spread_parameters=None))
+    conv = OC.InterpolatedToOHLCVConverter(None, cfg)
+    assert conv._generate_ohlcv_from_interpolated(pd.DataFrame()) is None
+    assert OC.canonical_strategy("price_midpoint") == "simple_spread"          # the config comment's name is not a strategy
+    ts = pd.date_range("2024-01-01", periods=10, freq="1min")
+    df = pd.DataFrame({"symbol": "s", "timestamp": ts, "underlying_price": 100.0, "mark_price": np.nan, "volume": 1.0})
+    assert conv._select_price_column(df) == "underlying_price"
+    assert conv._select_price_column(df.assign(underlying_price=np.nan)) == "underlying_price"      # fallback: first present
+    with pytest.raises(ValueError):
+        conv._select_price_column(df[["symbol", "timestamp", "volume"]])
+    ok = np.array([True, False, True, True])
+    need = np.array([False, False, True, False])
+    a, b = np.random.RandomState(4), np.random.RandomState(4)
+    u, e, z = OC.draw_tapes(a, "spread_simulation", ok, need)
+    want = [b.uniform(0, 1) for _ in range(5)] + [b.uniform(0, 1) for _ in range(5)]
+    we = b.exponential(1.0)
+    want += [b.uniform(0, 1) for _ in range(5)]
+    assert np.array_equal(u, want) and np.array_equal(e, [we]) and len(z) == 0 and a.random_sample() == b.random_sample()
+    if not torch.cuda.is_available():
+        assert conv._generate_ohlcv_from_interpolated(df) is None                                   # no device -> error -> None
+        assert all(r["status"] == "error" for r in conv.convert_frames([df]))
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "iv_interpolation_b200")
     for dirpath, _, files in os.walk(pkg):

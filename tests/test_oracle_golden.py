@@ -109,3 +109,51 @@ def test_kahan_differs_from_naive_and_matches_golden(golden_candles):
     kahan = O.kahan_group_sum(v, np.arange(0, len(v), 5), np.arange(5, len(v) + 5, 5))
     assert (kahan == want["volume"].to_numpy()).all()
     assert (naive != kahan).sum() > 100          # compensation matters: a naive sum is NOT bit-equal
+
+
+def test_bridge_oracle_matches_reference_golden(golden_bridge):
+    """oracle/bridge_oracle.py against candles produced by the reference's own data bridge under a seeded generator
+    (oracle/make_golden_bridge.py): every strategy, NaN / zero / negative base prices and volumes, bit for bit."""
+    from oracle import bridge_oracle as B
+    man = json.loads(str(golden_bridge["manifest"]))
+    assert len(man["cases"]) >= 36
+    seen = set()
+    for c in man["cases"]:
+        k = c["key"]
+        r = B.bridge_ohlcv(c["strategy"], golden_bridge[k + "/base"], golden_bridge[k + "/volume"],
+                           golden_bridge[k + "/u"], golden_bridge[k + "/e"], golden_bridge[k + "/z"])
+        assert (r["n_u"], r["n_e"], r["n_z"]) == tuple(len(golden_bridge[k + "/" + t]) for t in "uez"), c
+        if k + "/none" in golden_bridge.files:
+            assert len(r["row"]) == 0, c
+            continue
+        for col in ("open", "high", "low", "close", "volume", "source_price"):
+            assert np.array_equal(golden_bridge[k + "/out_" + col], r[col]), (c, col)
+        assert np.array_equal(golden_bridge[k + "/ts"][r["row"]], golden_bridge[k + "/out_ts"]), c
+        if k + "/quality" in golden_bridge.files:
+            assert B.quality_verdict(r["quality"]) == json.loads(str(golden_bridge[k + "/quality"])), c
+        seen.add(B.canonical_strategy(c["strategy"]))
+    assert seen == set(B.STRATEGIES)
+
+
+def test_bridge_tapes_follow_the_generator():
+    """draw_tapes consumes a RandomState exactly like row-by-row uniform/exponential/normal calls would."""
+    from oracle import bridge_oracle as B
+    rng = np.random.default_rng(5)
+    base = 100 + rng.normal(0, 1, 200)
+    base[::17] = np.nan
+    vol = rng.exponential(3, 200)
+    vol[::5] = np.nan
+    for strat, k in (("spread_simulation", 5), ("pipeline", 4), ("trend_following", 0)):
+        a, b = np.random.RandomState(9), np.random.RandomState(9)
+        u, e, z = B.draw_tapes(a, strat, base, vol)
+        uu, ee, zz = [], [], []
+        for bp, v in zip(base, vol):
+            if np.isnan(bp) or bp <= 0:
+                continue
+            if strat == "trend_following":
+                zz.append(b.normal(0, 1))
+            uu += [b.uniform(0, 1) for _ in range(k)]
+            if np.isnan(v) or v <= 0:
+                ee.append(b.exponential(1))
+        assert np.array_equal(u, uu) and np.array_equal(e, ee) and np.array_equal(z, zz), strat
+        assert a.random_sample() == b.random_sample()
