@@ -33,7 +33,20 @@ __device__ __forceinline__ int u_per_row(int strategy) {
 }
 __device__ __forceinline__ bool row_ok(double b) { return !(isnan(b) || b <= 0.0); }            // ohlcv_converter.py:152
 __device__ __forceinline__ bool vol_missing(double v) { return isnan(v) || v <= 0.0; }          // :373
-__device__ __forceinline__ double round_np(double x, double s) { return rint(x * s) / s; }      // np.float64.__round__
+// np.float64.__round__(x, d) = rint(x * 10^d) / 10^d.  The division is by a constant: with rc = RN(1/s), q0 = RN(a rc),
+// r = a - s q0 (exact in one fma) and q = RN(q0 + r rc) is the correctly rounded quotient (Markstein) — three dependent
+// operations instead of the ~10 of a general division, and this sits in the serial chain of the carried close.  The
+// result is compared bit for bit with numpy's over millions of values in tests/test_gpu_bridge.py.
+template <int D>
+__device__ __forceinline__ double round_np(double x) {
+  constexpr double s = D == 4 ? 1e4 : 1e6;
+  constexpr double rc = D == 4 ? 1e-4 : 1e-6;            // RN(1/s)
+  const double a = rint(x * s);
+  const double q0 = a * rc;
+  const double r = fma(-s, q0, a);
+  const double q = fma(r, rc, q0);
+  return (fabs(a) < 1e300) ? q : a / s;                  // inf/NaN/overflow: let the division decide
+}
 __device__ __forceinline__ double uni(double lo, double hi, double u) { return lo + (hi - lo) * u; }   // RandomState.uniform
 
 __global__ void __launch_bounds__(256) k_bridge_count(int64_t n_sym, const int64_t* __restrict__ in_off,
@@ -109,12 +122,11 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
       while (mm) {
         const int src = __ffs(mm) - 1;
         mm &= mm - 1;
-        if (lane == src) {
-          prev = pc1; has_prev = n_prev > 0;
-          const double tb = has_prev ? (bp - pc1) * 0.3 : 0.0;                 // :219-222
-          cp = round_np(bp + (co + tb * 0.5), 1e4);                             // :228-229, :256
-        }
-        pc1 = __shfl_sync(IVX_FULL_MASK, cp, src);
+        // every lane forms the candidate from the carried close (no divergence inside the chain); lane src's is the real one
+        const double tbc = n_prev > 0 ? (bp - pc1) * 0.3 : 0.0;                 // :219-222
+        const double cand = round_np<4>(bp + (co + tbc * 0.5));                 // :228-229, :256
+        if (lane == src) { prev = pc1; has_prev = n_prev > 0; cp = cand; }
+        pc1 = __shfl_sync(IVX_FULL_MASK, cand, src);
         n_prev = 1;
       }
       const double tb = has_prev ? (bp - prev) * 0.3 : 0.0;
@@ -128,12 +140,12 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
     } else if (STRATEGY == ST_MIDPOINT) {
       const double spread = bp * 0.001, q = spread / 4.0;                       // :268-269
       op = bp + uni(-q, q, uu[0]);
-      cp = round_np(bp + uni(-q, q, uu[1]), 1e4);
+      cp = round_np<4>(bp + uni(-q, q, uu[1]));
       hp = bp + spread / 2.0; lp = bp - spread / 2.0;
     } else if (STRATEGY == ST_SIMPLE) {
       const double spread = bp * 0.001, hs = spread / 2.0;                      // :345
       op = bp;
-      cp = round_np(bp + uni(-hs, hs, uu[0]), 1e4);
+      cp = round_np<4>(bp + uni(-hs, hs, uu[0]));
       hp = bp + hs; lp = bp - hs;
     } else if (STRATEGY == ST_PIPELINE) {                                       // complete_pipeline.py:483-492
       const double spread = bp * 0.001, third = spread / 3.0;
@@ -141,7 +153,7 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
       const double cu = bp + uni(-third, third, uu[1]);
       hp = (cu > op ? cu : op) + fabs(uni(0.0, spread / 2.0, uu[2]));
       lp = (cu < op ? cu : op) - fabs(uni(0.0, spread / 2.0, uu[3]));
-      cp = round_np(cu, 1e4);
+      cp = round_np<4>(cu);
     } else {                                                                    // trend_following :293-340
       const double zv = ok ? ld_stream(P.z + o) : 0.0;
       const double noise = 0.0 + (bp * 0.001) * zv;                             // np.random.normal(0, base * 0.001)
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
           const double mx = cu > op ? cu : op, mn = cu < op ? cu : op;
           if (trend > 0.0) { hp = mx + at * 0.5; lp = mn - at * 0.2; }          // :312-317
           else { hp = mx + at * 0.2; lp = mn - at * 0.5; }
-          cp = round_np(cu, 1e4);
+          cp = round_np<4>(cu);
         }
         pc5 = pc4; pc4 = pc3; pc3 = pc2; pc2 = pc1;
         pc1 = __shfl_sync(IVX_FULL_MASK, cp, src);
@@ -173,10 +185,10 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
     if (ok) {
       double v = nv ? 50.0 * ev : vin;                                          // :373-376
       v = v > 0.0 ? v : 0.0;                                                    // max(0, volume) :378
-      const double ro = round_np(op, 1e4), rh = round_np(hp, 1e4), rl = round_np(lp, 1e4);
+      const double ro = round_np<4>(op), rh = round_np<4>(hp), rl = round_np<4>(lp);
       st_stream(P.o_row + o, r);
       st_stream(P.o_open + o, ro); st_stream(P.o_high + o, rh); st_stream(P.o_low + o, rl); st_stream(P.o_close + o, cp);
-      st_stream(P.o_volume + o, round_np(v, 1e6));
+      st_stream(P.o_volume + o, round_np<6>(v));
       st_stream(P.o_source + o, bp);
       // _validate_ohlcv_quality :385-405
       if (rh < rl) qflags |= Q_HIGH_LT_LOW;

@@ -178,3 +178,22 @@ def test_bridge_convert_frames_status_dicts(dev, golden_bridge):
         assert conv._generate_ohlcv_from_interpolated(good.drop(columns=["underlying_price", "mark_price", "index_price"])) is None
     finally:
         logging.disable(logging.NOTSET)
+
+
+def test_bridge_rounding_matches_numpy_over_millions(dev):
+    """The constant division behind round(x, 4) / round(x, 6) (three dependent operations instead of a general
+    division) against numpy's rint(x * 10^d) / 10^d on 4 million values across twelve decades, bit for bit."""
+    rng = np.random.default_rng(2024)
+    n = 2_000_000
+    base = 10.0 ** rng.uniform(-5, 7, n)
+    base[:1000] = np.round(rng.uniform(0, 100, 1000), 4) + 0.00005          # decimal ties of the 4th place
+    vol = 10.0 ** rng.uniform(-7, 6, n)
+    u = rng.random(n)
+    got = _run(dev, "simple_spread", np.array([0, n], np.int64), base, vol, u, np.zeros(0), np.zeros(0))
+    r4 = lambda x: np.rint(x * 1e4) / 1e4
+    spread = base * 0.001
+    hs = spread / 2
+    assert np.array_equal(got["open"], r4(base))
+    assert np.array_equal(got["high"], r4(base + hs)) and np.array_equal(got["low"], r4(base - hs))
+    assert np.array_equal(got["close"], r4(base + (-hs + (hs - -hs) * u)))
+    assert np.array_equal(got["volume"], np.rint(vol * 1e6) / 1e6)
