@@ -45,7 +45,7 @@ __device__ __forceinline__ double round_np(double x) {
   const double q0 = a * rc;
   const double r = fma(-s, q0, a);
   const double q = fma(r, rc, q0);
-  return (fabs(a) < 1e300) ? q : a / s;                  // inf/NaN/overflow: let the division decide
+  return fabs(q0) <= 1.7976931348623157e308 ? q : q0;    // x * s overflowed: inf / s = inf (the residual would be NaN)
 }
 __device__ __forceinline__ double uni(double lo, double hi, double u) { return lo + (hi - lo) * u; }   // RandomState.uniform
 
