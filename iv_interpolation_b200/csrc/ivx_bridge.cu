@@ -37,7 +37,7 @@ __device__ __forceinline__ bool vol_missing(double v) { return isnan(v) || v <= 
 // r = a - s q0 (exact in one fma) and q = RN(q0 + r rc) is the correctly rounded quotient (Markstein) — three dependent
 // operations instead of the ~10 of a general division, and this sits in the serial chain of the carried close.  The
 // result is compared bit for bit with numpy's over millions of values in tests/test_gpu_bridge.py.
-template <int D>
+template <int D, bool CHECKED = true>
 __device__ __forceinline__ double round_np(double x) {
   constexpr double s = D == 4 ? 1e4 : 1e6;
   constexpr double rc = D == 4 ? 1e-4 : 1e-6;            // RN(1/s)
@@ -45,6 +45,7 @@ __device__ __forceinline__ double round_np(double x) {
   const double q0 = a * rc;
   const double r = fma(-s, q0, a);
   const double q = fma(r, rc, q0);
+  if (!CHECKED) return q;                                // callers that know |x| < 1e290
   return fabs(q0) <= 1.7976931348623157e308 ? q : q0;    // x * s overflowed: inf / s = inf (the residual would be NaN)
 }
 __device__ __forceinline__ double uni(double lo, double hi, double u) { return lo + (hi - lo) * u; }   // RandomState.uniform
@@ -92,15 +93,25 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
   constexpr int K = STRATEGY == ST_SPREAD ? 5 : STRATEGY == ST_MIDPOINT ? 2 : STRATEGY == ST_PIPELINE ? 4 : STRATEGY == ST_SIMPLE ? 1 : 0;
   const int64_t a = P.in_off[s], b = P.in_off[s + 1];
   int64_t o_base = P.out_off[s], e_base = P.e_off[s];
+  constexpr int CHAIN_W = 12;                              // warm-up ranks of the parallel close walk: 0.15^12 = 1.3e-10
+  __shared__ double s_b[STRATEGY == ST_SPREAD ? 4 : 1][32], s_c[STRATEGY == ST_SPREAD ? 4 : 1][32], s_f[STRATEGY == ST_SPREAD ? 4 : 1][32];
+  (void)s_b; (void)s_c; (void)s_f;
   // closes of the candles emitted so far (rounded, newest first): warp-uniform
   double pc1 = 0.0, pc2 = 0.0, pc3 = 0.0, pc4 = 0.0, pc5 = 0.0;
   int n_prev = 0;
   uint32_t qflags = 0;
+  // base/volume of the next chunk are requested before this chunk's (latency-bound) close walk
+  double bp_next = (a + lane < b) ? ld_stream(P.base + a + lane) : qnan();
+  double vin_next = (a + lane < b) ? ld_stream(P.volume + a + lane) : 1.0;
   for (int64_t r0 = a; r0 < b; r0 += 32) {
     const int64_t r = r0 + lane;
     const bool in = r < b;
-    const double bp = in ? ld_stream(P.base + r) : qnan();
-    const double vin = in ? ld_stream(P.volume + r) : 1.0;
+    const double bp = bp_next, vin = vin_next;
+    {
+      const int64_t rn = r + 32;
+      bp_next = rn < b ? ld_stream(P.base + rn) : qnan();
+      vin_next = rn < b ? ld_stream(P.volume + rn) : 1.0;
+    }
     const bool ok = in && row_ok(bp);
     const bool nv = ok && vol_missing(vin);
     const uint32_t okm = __ballot_sync(IVX_FULL_MASK, ok), nvm = __ballot_sync(IVX_FULL_MASK, nv);
@@ -115,19 +126,58 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
       const double spread = bp * P.base_spread_percent * vm;                   // :216
       const double third = spread / 3.0;
       const double oo = uni(-third, third, uu[1]), co = uni(-third, third, uu[2]);
-      // ---- the close chain: close = base + (co + ((base - prev_close) * 0.3) * 0.5), rounded, lane after lane ----
+      // ---- the close chain: close[j] = round4(base[j] + (co[j] + ((base[j] - close[j-1]) * 0.3) * 0.5)) over the emitted rows.
+      // Rounding makes it non-affine (no scan), but it CONTRACTS: a change of close[j-1] moves close[j] by 0.15 of it, and
+      // two walks that ever round to the same value stay identical.  So every emitted row of the chunk is walked in
+      // parallel: the rows are compacted by rank into shared memory; lane j starts CHAIN_W ranks back from a guess (ranks
+      // 0..CHAIN_W start from the true carried close) and walks up to its own rank — 13 dependent steps for the whole chunk
+      // instead of 32.  The result is then PROVEN, not assumed: lane j's value for rank j-1 must equal lane j-1's own final
+      // value bit for bit; by induction from the exact lanes every close is then the sequential one.  A chunk that fails
+      // the check (expected ~1e-3 of chunks: a 1e-9 residue straddling a rounding boundary) is redone sequentially.
       double prev = 0.0;                                   // my predecessor's rounded close
       bool has_prev = false;
-      uint32_t mm = okm;
-      while (mm) {
-        const int src = __ffs(mm) - 1;
-        mm &= mm - 1;
-        // every lane forms the candidate from the carried close (no divergence inside the chain); lane src's is the real one
-        const double tbc = n_prev > 0 ? (bp - pc1) * 0.3 : 0.0;                 // :219-222
-        const double cand = round_np<4>(bp + (co + tbc * 0.5));                 // :228-229, :256
-        if (lane == src) { prev = pc1; has_prev = n_prev > 0; cp = cand; }
-        pc1 = __shfl_sync(IVX_FULL_MASK, cand, src);
-        n_prev = 1;
+      const int wi = threadIdx.x >> 5;
+      const int rank = __popc(okm & lt), n = __popc(okm);
+      __syncwarp();                                        // the previous chunk's readers are done with the staging rows
+      if (ok) { s_b[wi][rank] = bp; s_c[wi][rank] = co; }
+      __syncwarp();
+      double p = pc1, p_before = pc1;
+      const bool spec = lane > CHAIN_W;
+      if (lane < n) {
+        int i = lane - CHAIN_W;
+        if (spec) p = s_b[wi][i - 1];                      // the guess: no trend bias at the row before the walk
+#pragma unroll
+        for (int t = 0; t <= CHAIN_W; ++t, ++i) {
+          if (i >= 0) {
+            const double b_ = s_b[wi][i], c_ = s_c[wi][i];
+            const double tb_ = (i == 0 && n_prev == 0) ? 0.0 : (b_ - p) * 0.3;      // :219-222
+            p_before = p;
+            p = round_np<4, false>(b_ + (c_ + tb_ * 0.5));                            // :228-229, :256
+          }
+        }
+      }
+      const double up = __shfl_up_sync(IVX_FULL_MASK, p, 1);
+      const bool bad = (lane < n && spec && !(p_before == up)) || (ok && !(fabs(bp) < 1e290));
+      if (!__any_sync(IVX_FULL_MASK, bad)) {
+        if (lane < n) s_f[wi][lane] = p;
+        __syncwarp();
+        if (ok) {
+          cp = s_f[wi][rank];
+          prev = rank > 0 ? s_f[wi][rank - 1] : pc1;
+          has_prev = rank > 0 || n_prev > 0;
+        }
+        if (n > 0) { pc1 = s_f[wi][n - 1]; n_prev = 1; }
+      } else {                                             // sequential walk, lane after lane
+        uint32_t mm = okm;
+        while (mm) {
+          const int src = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const double tbc = n_prev > 0 ? (bp - pc1) * 0.3 : 0.0;
+          const double cand = round_np<4>(bp + (co + tbc * 0.5));
+          if (lane == src) { prev = pc1; has_prev = n_prev > 0; cp = cand; }
+          pc1 = __shfl_sync(IVX_FULL_MASK, cand, src);
+          n_prev = 1;
+        }
       }
       const double tb = has_prev ? (bp - prev) * 0.3 : 0.0;
       op = bp + (oo + tb * 0.2);                                                // :225-226

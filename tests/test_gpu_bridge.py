@@ -86,11 +86,15 @@ def test_bridge_kernel_vs_oracle_ragged(dev, strategy):
     """Ragged symbols (0 to 3000 rows, chunk boundaries at 31/32/33/64/65 rows), 4-decimal prices where the rounding of
     the carried close matters, missing prices and volumes."""
     rng = np.random.default_rng(123)
-    lens = [0, 1, 2, 31, 32, 33, 64, 65, 100, 999, 3000, 1, 0, 257]
+    lens = [0, 1, 2, 31, 32, 33, 64, 65, 100, 999, 3000, 1, 0, 257, 700, 90]
     rs = np.random.RandomState(77)
     bases, vols, us, es, zs, want = [], [], [], [], [], []
     for i, n in enumerate(lens):
         price = [25000.0, 0.37, 1e-3, 64000.0][i % 4]
+        if n == 700:
+            price = 3e11            # 2^53 / 1e4 < price: rint(x * 1e4) is the identity, closes move in steps of 6e-5
+        if n == 90:
+            price = 1e295           # x * 1e4 overflows: the sequential fallback and numpy's inf / 1e4 = inf
         b = price + np.cumsum(rng.normal(0, price * 0.002, n))
         v = rng.exponential(5.0, n)
         b[rng.random(n) < 0.07] = np.nan
@@ -98,7 +102,8 @@ def test_bridge_kernel_vs_oracle_ragged(dev, strategy):
         v[rng.random(n) < 0.2] = np.nan
         v[rng.random(n) < 0.05] = -1.0
         u, e, z = B.draw_tapes(rs, strategy, b, v)
-        want.append(B.bridge_ohlcv(strategy, b, v, u, e, z))
+        with np.errstate(all="ignore"):
+            want.append(B.bridge_ohlcv(strategy, b, v, u, e, z))
         bases.append(b); vols.append(v); us.append(u); es.append(e); zs.append(z)
     off = np.zeros(len(lens) + 1, np.int64)
     np.cumsum(lens, out=off[1:])
@@ -107,7 +112,7 @@ def test_bridge_kernel_vs_oracle_ragged(dev, strategy):
         a, b = int(got["out_off"][i]), int(got["out_off"][i + 1])
         assert b - a == len(w["row"]), (i, lens[i])
         for col in COLS:
-            assert np.array_equal(w[col], got[col][a:b]), (strategy, i, lens[i], col, np.flatnonzero(w[col] != got[col][a:b])[:4])
+            assert np.array_equal(w[col], got[col][a:b], equal_nan=True), (strategy, i, lens[i], col, np.flatnonzero(w[col] != got[col][a:b])[:4])
         assert np.array_equal(w["row"], got["row"][a:b] - off[i])
         assert int(got["quality"][i]) == w["quality"], (i, lens[i])
 
