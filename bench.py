@@ -288,8 +288,8 @@ def run_gpu(args):
             roofline["traffic_source"] = f"profiles/ncu_traffic_r1.json: {tr['bytes_per_unit']} DRAM B per {tr['unit']} (ncu --set full) x {n_units}"
     except (OSError, ValueError, KeyError):
         pass
-    roofline["limiter"] = ("instruction issue (ncu: issue slots 87 % busy, fp64 pipe 43 %, DRAM 17 %): the solver is transcendental-heavy "
-                           "fp64, ~1050 instructions per quote") if dom == "implied_vol" else None
+    roofline["limiter"] = ("instruction issue and the fp64 pipe together (ncu, profiles/ncu_r1_final_summary.json: issue slots 78 % busy, "
+                           "fp64 pipe 50 %, DRAM 29 %): 558 instructions per quote, 190 of them fp64 at two issue cycles each") if dom == "implied_vol" else None
 
     # ---- the same step in the chain layout (S per stamp, K and call/put per contract, T per (stamp, expiry)) -----
     sc = SF.StructuredChain.from_quotes(chain)
