@@ -12,15 +12,18 @@
 //     erfcx so that deep-wing prices never underflow: b = E/2 [erfcx(q1) - erfcx(q2)],
 //     E = exp(-(h^2+t^2)/2), h = |x|/s, t = s/2, q1,2 = (h -+ t)/sqrt2, b' = E/sqrt(2 pi);
 //   * beta >= b(s_c): root in the concave branch — solve b(s) = beta directly.
-// The fp64 pipe is this kernel's roofline (ncu: profiles/), so the solver is split in two phases:
-//   1. an fp32 PRE-SOLVE (FP32 pipe + MUFU, runs in the shadow of other warps' fp64 work): the
-//      closed-form guess (tangent and log-match at the inflection point, blended) followed by one bracketed third-order Householder step
-//      in single precision — leaves s to ~1e-7 relative on all but a few 1e-4 of the quotes;
-//   2. an fp64 POLISH: bracketed Halley iterations (third order; two divisions, two erfcx|erfc
-//      and one log|exp each) until a step is below 1e-4 s — after such a step the remaining
-//      error is ~1e-13 s — with bisection of the bracket whenever a step leaves it
-//      ("Newton/Brent" safeguarding).  Nearly every warp leaves after ONE fp64 evaluation; a
-//      warp leaves the loop when all its lanes have converged (warp vote).
+// The kernel is bound by instruction issue and the fp64 pipe together (ncu: profiles/README.md), so it is built to
+// execute as few instructions as possible, in three phases:
+//   1. an fp32 PRE-SOLVE (FP32 pipe + raw MUFU ops, runs in the shadow of other warps' fp64 work): the closed-form
+//      guess (tangent and log-match at the inflection point, blended) followed by one third-order Householder step in
+//      single precision — leaves s to ~1e-6 relative on all but a few 1e-4 of the quotes;
+//   2. an fp64 FAST PATH, straight-line: ONE Halley step on b(s) - beta with b written so that the same expression
+//      holds on both sides of the inflection point (solve_quote); accepted when the step is below 1e-4 s — after such
+//      a step the remaining error is ~1e-12 s;
+//   3. the out-of-line FALLBACK for everything the fast path does not accept: bracketed Halley iterations (third
+//      order) with bisection of the bracket whenever a step leaves it ("Newton/Brent" safeguarding), a warp vote to
+//      leave the loop (polish_f64).  It takes a quote from anywhere; on realistic tapes it runs for ~0 % of the quotes.
+// Inputs: S, K, T positive NORMAL numbers below 1e300 (subnormal or larger inputs return NaN), any finite r.
 // Loads are structure-of-arrays, one coalesced stream per column.
 #include "ivx_common.cuh"
 
