@@ -149,8 +149,9 @@ int ivx_interp_exec(int64_t n_sym, const int64_t* src_off, int64_t n_src, const 
  * Kernel C — Black-Scholes implied volatility, one thread per quote (north_star kernel 1; the
  * reference has no solver, its conventions come from interpolation/greeks.py:21-22: continuous
  * rate r, no dividend, T in years).  sigma[i] = NaN outside the invertible domain
- * (non-finite/non-positive inputs, or price not strictly inside the no-arbitrage bounds).
- * iters may be NULL.  ivx_bs_price is the forward pricer (used to build synthetic tapes),
+ * (non-finite/non-positive inputs, or price not strictly inside the no-arbitrage bounds; S, K, T
+ * and K e^{-rT} must be NORMAL doubles below 1e300 — subnormal or larger values also give NaN).
+ * iters[i] = fp64 price evaluations spent on quote i (1 on the fast path); may be NULL.  ivx_bs_price is the forward pricer (used to build synthetic tapes),
  * ivx_bs_greeks the Greeks of greeks.py:24-35 (put rho keeps the reference's sign when
  * reference_put_rho_sign != 0).
  * ------------------------------------------------------------------------------------------- */
