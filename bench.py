@@ -336,6 +336,13 @@ def run_gpu(args):
         ab = _bench_ab(args, torch, D, tapes, dev, peak, rank, world, barrier, max_over_ranks)
         kernels.update(ab)
 
+    if rank == 0 and world == 1 and not args.skip_cpu and not args.skip_kernels:
+        try:
+            for k, v in _cpu_port_ab(tapes).items():
+                kernels[k]["cpu_port"] = v
+        except Exception as e:  # reported baselines only
+            kernels["interp_linear_ffill"]["cpu_port"] = {"failed": repr(e)}
+
     cb = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         # the CPU leg runs in a fresh interpreter (no CUDA context to fork, BLAS pinned to one thread per worker)
@@ -485,6 +492,45 @@ def _bench_ab(args, torch, D, tapes, dev, peak, rank, world, barrier, max_over_r
                                 f"{rows} minute rows -> {n_candles} 5-min candles per GPU: memsets + k_ohlcv_reduce + k_ohlcv_finalize, "
                                 "48 B read per row + 52 B written per candle")
     return out
+
+
+def _cpu_port_ab(tapes):
+    """The oracle restatements of kernels A, B and the bridge (oracle/np_oracle.py, oracle/bridge_oracle.py — the reference's
+    pandas path cannot travel to the GPU box) timed on ONE host core on a bounded sample of the same config-3-shaped tape:
+    reported next to the GPU figures, as SURVEY.md 8(d) asks."""
+    import time
+    import numpy as np
+    from oracle import bridge_oracle as BO, np_oracle as O
+    n_c = 12
+    tp = tapes.make_contract_tape(3, n_c, rows_per_contract=481)
+    kw = dict(step=tapes.MINUTE_US, max_span=30 * tapes.DAY_US)
+    outs, rows = [], 0
+    t0 = time.perf_counter()
+    for i in range(n_c):
+        a, b = int(tp.off[i]), int(tp.off[i + 1])
+        w = O.interp_linear_ffill(tp.date[a:b], [tp.cols[c][a:b] for c in tapes.INTERP_COLS], [tp.cols[c][a:b] for c in tapes.FILL_NUM_COLS],
+                                  [np.ones(b - a, bool)], **kw)
+        outs.append(w)
+        rows += len(w["interp"][0])
+    t_a = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for w in outs:
+        S = w["interp"][1]
+        O.ohlcv_reduce(w["date"], S, S + 3.0, S - 3.0, S + 0.5, w["fill"][4], bucket_ticks=5 * tapes.MINUTE_US, min_count=5)
+    t_b = time.perf_counter() - t0
+    rs = np.random.RandomState(1)
+    t0 = time.perf_counter()
+    br_rows = 0
+    for w in outs[:2]:
+        S, vol = w["interp"][1], w["fill"][4]
+        u, e, z = BO.draw_tapes(rs, "spread_simulation", S, vol)
+        BO.bridge_ohlcv("spread_simulation", S, vol, u, e, z)
+        br_rows += len(S)
+    t_br = time.perf_counter() - t0
+    mk = lambda r, t, what: {"rate": r / t, "rate_unit": "minute-rows/s", "cores": 1, "kind": "port", "sample": what}
+    return {"interp_linear_ffill": mk(rows, t_a, f"oracle/np_oracle.interp_linear_ffill on {n_c} contracts x 481 hourly rows -> {rows} minute rows"),
+            "ohlcv_reduce": mk(rows, t_b, f"oracle/np_oracle.ohlcv_reduce on the same {rows} minute rows, 5-min buckets"),
+            "bridge_ohlcv": mk(br_rows, t_br, f"oracle/bridge_oracle.bridge_ohlcv (row loop, like the reference's iterrows) on {br_rows} minute rows")}
 
 
 def main():
