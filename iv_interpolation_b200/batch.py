@@ -158,3 +158,78 @@ class CandleBatch:
                                "processing_time": elapsed / max(1, len(todo)),
                                "stats": self.reconstructor.get_reconstruction_stats(src, res)}
         return outs, statuses, _summary(int(t0), statuses, t0)
+
+
+class PipelineBatch:
+    """``CompleteOptimizedPipeline``'s three stages for a batch of symbols, DB-free (reference complete_pipeline.py):
+    Task 1 interpolation (:318), the data bridge ``_convert_symbol_to_ohlcv`` / ``_generate_ohlcv_candles`` (:437-510) and
+    Task 2 ``_reconstruct_symbol_candles`` / ``_aggregate_to_5min`` (:641-710) — each stage ONE launch for all symbols, the
+    reference's per-symbol status dictionaries per stage.  The bridge draws from numpy's global generator (or ``rng``) in
+    the order the reference does when it loops over the symbols, so a seeded run reproduces the reference's candles."""
+
+    def __init__(self, rng=None, batch_id: Optional[int] = None):
+        self.batch_id = int(time.time()) if batch_id is None else batch_id
+        self.rng = rng
+
+    def run(self, frames: Mapping[str, pd.DataFrame]):
+        from .data_bridge.ohlcv_converter import InterpolatedToOHLCVConverter
+
+        t0 = time.time()
+        # ---- Task 1 (complete_pipeline.py:49 default-constructs the interpolator) --------------------------------------
+        interp, st1, sum1 = InterpolationBatch(batch_id=self.batch_id).run(frames)
+        # ---- bridge: SELECT symbol, date, underlying_price, mark_price, index_price, volume ... ORDER BY date (:441-446) ----
+        syms = list(frames)
+        st2: List[dict] = []
+        have = [s for s in syms if s in interp]
+        conv = InterpolatedToOHLCVConverter(None, None, rng=self.rng)
+        try:
+            gen = conv._generate_many([interp[s][["symbol", "date", "underlying_price", "mark_price", "index_price", "volume"]]
+                                       for s in have], "pipeline") if have else []
+            err = None
+        except Exception as e:                                                        # :470-471
+            gen, err = [], str(e)
+        minute: Dict[str, pd.DataFrame] = {}
+        for s in syms:
+            if s not in interp:
+                st2.append({"symbol": s, "status": "skipped", "reason": "No interpolated data"})              # :451-452
+            elif err is not None:
+                st2.append({"symbol": s, "status": "error", "error": err})
+            else:
+                f = gen[have.index(s)]["frame"]
+                if f is None or f.empty:
+                    st2.append({"symbol": s, "status": "error", "error": "OHLCV generation failed"})          # :456-457
+                else:
+                    minute[s] = f
+                    st2.append({"symbol": s, "status": "success", "input_rows": len(interp[s]), "output_rows": len(f), "error": None})
+        # ---- Task 2 (:641-684): N = 5 fixed, rows in the stored order, no sort, the caller's len < 5 early-out ----------
+        st3: List[dict] = []
+        todo = [s for s in syms if s in minute and len(minute[s]) >= 5]
+        rec = CandleReconstructor("5min")
+        try:
+            res = rec.reconstruct_batch([minute[s][["symbol", "timestamp", "open", "high", "low", "close", "volume"]] for s in todo],
+                                        presorted=True, check_len=False) if todo else []
+            err = None
+        except Exception as e:
+            res, err = [], str(e)
+        candles: Dict[str, pd.DataFrame] = {}
+        for s in syms:
+            if s not in minute:
+                st3.append({"symbol": s, "status": "skipped", "reason": "No minute candles found"})           # :657-658
+            elif len(minute[s]) < 5:
+                st3.append({"symbol": s, "status": "skipped", "reason": "Insufficient data for 5-min candles"})   # :660-661
+            elif err is not None:
+                st3.append({"symbol": s, "status": "error", "error": err})                                     # :683-684
+            else:
+                r = res[todo.index(s)]
+                if r is None or r.empty:
+                    st3.append({"symbol": s, "status": "error", "error": "Reconstruction failed"})            # :665-666
+                else:
+                    out = r[["timestamp", "open", "high", "low", "close", "volume", "symbol"]].copy()          # :693-704
+                    out["frequency"] = "5min"                                                                  # :669-671
+                    out["source_candles"] = 5
+                    out["batch_id"] = self.batch_id
+                    candles[s] = out
+                    st3.append({"symbol": s, "status": "success", "input_candles": len(minute[s]), "output_candles": len(out), "error": None})
+        stages = {"interpolation": (st1, sum1), "bridge": (st2, _summary(self.batch_id, st2, t0)),
+                  "reconstruction": (st3, _summary(self.batch_id, st3, t0))}
+        return candles, minute, interp, stages

@@ -202,3 +202,44 @@ def test_bridge_rounding_matches_numpy_over_millions(dev):
     assert np.array_equal(got["high"], r4(base + hs)) and np.array_equal(got["low"], r4(base - hs))
     assert np.array_equal(got["close"], r4(base + (-hs + (hs - -hs) * u)))
     assert np.array_equal(got["volume"], np.rint(vol * 1e6) / 1e6)
+
+
+def test_pipeline_batch_equals_the_oracle_chain(dev):
+    """Task 1 -> bridge -> Task 2 of complete_pipeline.py for a batch of contracts, against the three oracle restatements
+    chained symbol after symbol with the bridge tapes drawn from an identically seeded generator."""
+    from iv_interpolation_b200 import tapes
+    from iv_interpolation_b200.batch import PipelineBatch
+    from oracle import np_oracle as O
+    from oracle.df_oracle import OracleIVInterpolator
+    tp = tapes.make_contract_tape(21, 9, rows_per_contract=49)
+    frames = {f"C{i}": tp.frame(i) for i in range(tp.n_sym)}
+    frames["C3"] = frames["C3"].iloc[:4]                     # too few rows: Task 1 returns None
+    frames["gone"] = pd.DataFrame()
+    candles, minute, interp, stages = PipelineBatch(rng=np.random.RandomState(11), batch_id=5).run(frames)
+    rs = np.random.RandomState(11)
+    ref = OracleIVInterpolator()
+    n_ok = 0
+    for sym, f in frames.items():
+        w1 = None if f.empty else ref.interpolate_symbol(f)
+        st1, st2, st3 = (next(s for s in stages[k][0] if s["symbol"] == sym) for k in ("interpolation", "bridge", "reconstruction"))
+        if w1 is None:
+            assert st1["status"] == "skipped" and st2 == {"symbol": sym, "status": "skipped", "reason": "No interpolated data"}
+            assert st3 == {"symbol": sym, "status": "skipped", "reason": "No minute candles found"} and sym not in candles
+            continue
+        base = B.pipeline_base(*(w1[c].to_numpy(dtype=np.float64) for c in ("underlying_price", "mark_price", "index_price")))
+        vol = w1["volume"].to_numpy(dtype=np.float64)
+        u, e, z = B.draw_tapes(rs, "pipeline", base, vol)
+        w2 = B.bridge_ohlcv("pipeline", base, vol, u, e, z)
+        assert st2["status"] == "success" and st2["output_rows"] == len(w2["row"]) and st2["input_rows"] == len(w1)
+        for col in ("open", "high", "low", "close", "volume"):
+            assert np.array_equal(minute[sym][col].to_numpy(), w2[col]), (sym, col)
+        ts = w1["date"].to_numpy().astype("datetime64[us]").view(np.int64)[w2["row"]]
+        w3 = O.ohlcv_reduce(ts, w2["open"], w2["high"], w2["low"], w2["close"], w2["volume"], bucket_ticks=5 * tapes.MINUTE_US,
+                            min_count=5, presorted=True, check_len=False)
+        got = candles[sym]
+        assert list(got.columns) == ["timestamp", "open", "high", "low", "close", "volume", "symbol", "frequency", "source_candles", "batch_id"]
+        for col in ("open", "high", "low", "close", "volume"):
+            assert np.array_equal(got[col].to_numpy(), w3[col], equal_nan=True), (sym, col)
+        assert st3["status"] == "success" and st3["output_candles"] == len(w3["close"]) and (got["batch_id"] == 5).all()
+        n_ok += 1
+    assert n_ok >= 7
