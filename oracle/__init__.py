@@ -13,6 +13,9 @@ Parity status:
     the survey's known-answer cases; the outputs are committed under
     ``tests/golden/`` and ``tests/test_oracle_golden.py`` holds this oracle to
     them bit-for-bit.
+  * the data bridge (``oracle/bridge_oracle.py``): PINNED - ``oracle/make_golden_bridge.py`` ran the reference's
+    own ``InterpolatedToOHLCVConverter`` / ``_generate_ohlcv_candles`` under a seeded generator;
+    ``tests/golden/bridge_cases.npz``, held bit-for-bit including the generator's end state.
   * kernels C (Black-Scholes implied vol) and D (natural cubic spline): the
     reference contains no such code ("parity unpinned" by the reference);
     the oracle is scipy (brentq / CubicSpline) and the Greeks formulas of
