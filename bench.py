@@ -474,13 +474,14 @@ def _bench_ab(args, torch, D, tapes, dev, peak, rank, world, barrier, max_over_r
     S, vol = res.interp[1], res.fill[4]
     # the step between A and B in the reference (data_bridge/ohlcv_converter.py:138-263, default strategy): minute rows ->
     # synthetic 1-min candles, uniform/exponential tapes resident on the device (5 uniforms per emitted row)
-    bplan = D.bridge_plan(res.out_off, S, vol)
+    bp_ms, bplan = timed(lambda: D.bridge_plan(res.out_off, S, vol))
+    out["bridge_plan"] = entry(bp_ms, rows * 16, rows, "ivx_bridge_plan: per-segment counts, two scans, per-symbol offsets (16 B read per row) + a 16-byte read-back")
     u_tape = torch.rand(5 * bplan.total, dtype=torch.float64, device=dev)
     e_tape = torch.empty(max(1, bplan.total_e), dtype=torch.float64, device=dev).exponential_()
     br_ms, br = timed(lambda: D.bridge_ohlcv(res.out_off, S, vol, bplan, "spread_simulation", u=u_tape, e=e_tape))
     bytes_br = rows * 16 + br.total * (40 + 56) + bplan.total_e * 8
     out["bridge_ohlcv"] = entry(br_ms, bytes_br, rows,
-                                f"k_bridge_ohlcv (spread_simulation): {rows} minute rows -> {br.total} synthetic 1-min candles per GPU, "
+                                f"k_bridge_ohlcv_seg + k_bridge_check (spread_simulation): {rows} minute rows -> {br.total} synthetic 1-min candles per GPU, "
                                 "16 B read per row + 40 B of uniform tape and 56 B written per candle; output allocation inside the timed call")
     del u_tape, e_tape, br
     # five DISTINCT input columns (the same array passed four times would be served from L2)

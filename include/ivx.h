@@ -235,21 +235,32 @@ int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, int32_t n_k
  * With tapes drawn from a RandomState seeded like the reference's generator the candles are bit-equal to
  * the reference's.  strategy: 0 spread_simulation (prev-close trend bias), 1 price_as_midpoint,
  * 2 trend_following, 3 simple spread (the reference's fallback for every other string), 4 pipeline.
- * ivx_bridge_count gives, per symbol, the emitted rows and exponential draws; their exclusive scans
- * (ivx_exclusive_scan_i64) are out_off and e_off.  o_row[j] is the global input row of candle j
- * (timestamps and symbols are gathered from it).  sym_quality[s]: bit 0 high<low, 1 high<open|close,
- * 2 low>open|close, 3 (high-low)/source > 0.1, 4 a price <= 0 — the checks of _validate_ohlcv_quality,
- * which reports the lowest set bit.
+ * ivx_bridge_plan counts, per segment of 2048 consecutive rows (ivx_bridge_n_segments(n_rows) of them, symbol
+ * boundaries ignored) and per symbol, the candles and exponential draws that precede it: seg_out / seg_e
+ * (n_seg + 1 entries) and out_off / e_off (n_sym + 1 entries; the last entries are the totals, which size the
+ * outputs and the tapes).  o_row[j] is the global input row of candle j (timestamps and symbols are gathered
+ * from it).  sym_quality[s]: bit 0 high<low, 1 high<open|close, 2 low>open|close, 3 (high-low)/source > 0.1,
+ * 4 a price <= 0 — the checks of _validate_ohlcv_quality, which reports the lowest set bit.
+ * ivx_bridge_ohlcv with seg_out, seg_e and a workspace of ivx_bridge_workspace_bytes(n_rows): one warp per segment,
+ * whatever the symbols' lengths (a segment that starts inside a symbol derives the carried close by a 256-row warm-up
+ * walk, which a check kernel compares bit for bit with what the previous segment produced; on a mismatch the
+ * per-symbol kernel recomputes the batch in stream order).  With seg_out, seg_e or workspace NULL: one warp per
+ * symbol.  Results are identical either way; trend_following always runs one warp per symbol.
  * ------------------------------------------------------------------------------------------- */
-int ivx_bridge_count(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
-                     int64_t* n_out /*n_sym*/, int64_t* n_e /*n_sym*/, ivx_stream_t stream);
-int ivx_bridge_ohlcv(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
+int64_t ivx_bridge_n_segments(int64_t n_rows);
+int64_t ivx_bridge_workspace_bytes(int64_t n_rows);
+int ivx_bridge_plan(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
+                    int64_t* seg_out /*n_seg+1*/, int64_t* seg_e /*n_seg+1*/, int64_t* out_off /*n_sym+1*/,
+                    int64_t* e_off /*n_sym+1*/, void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
                      int32_t strategy, double base_spread_percent, double volatility_factor,
                      const double* u, const double* e, const double* z,
                      const int64_t* out_off /*n_sym+1*/, const int64_t* e_off /*n_sym+1*/,
+                     const int64_t* seg_out /*n_seg+1 or NULL*/, const int64_t* seg_e /*n_seg+1 or NULL*/,
                      int64_t* o_row, double* o_open, double* o_high, double* o_low, double* o_close,
                      double* o_volume, double* o_source, uint32_t* sym_quality /*n_sym or NULL*/,
-                     ivx_stream_t stream);
+                     void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+void ivx_bridge_test_force_fallback(int32_t on);   /* test hook: the segment check reports a mismatch, the fallback runs */
 
 /* ---------------------------------------------------------------------------------------------
  * Utilities: exclusive scan of int64, stream-copy and fp64-FMA microbenchmarks that give the

@@ -61,9 +61,12 @@ SIGNATURES = {
     "ivx_bs_implied_vol_chain": (C.c_int, [_i64, _i64, _i64, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_spline_strided": (C.c_int, [_i64, _i32, _p, _p, _i32, _p, _i32, _p, _p]),
     "ivx_spline_strided_batched": (C.c_int, [_i64, _i64, _i32, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p]),
-    "ivx_bridge_count": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
-    "ivx_bridge_ohlcv": (C.c_int, [_i64, _p, _p, _p, _i32, C.c_double, C.c_double, _p, _p, _p, _p, _p,
-                                   _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ivx_bridge_n_segments": (_i64, [_i64]),
+    "ivx_bridge_workspace_bytes": (_i64, [_i64]),
+    "ivx_bridge_test_force_fallback": (None, [_i32]),
+    "ivx_bridge_plan": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "ivx_bridge_ohlcv": (C.c_int, [_i64, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _p, _p, _p, _p, _p, _p, _p,
+                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_exclusive_scan_i64": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_copy": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_fp64_fma": (C.c_int, [_i64, _i32, _p, _p]),

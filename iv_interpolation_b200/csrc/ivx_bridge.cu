@@ -11,14 +11,17 @@
 // This file is compiled with --fmad=false: numpy evaluates every expression with separate multiplies and adds, and a
 // fused multiply-add here would change last bits.  round(x, 4) on an np.float64 is rint(x * 1e4) / 1e4.
 //
-// k_bridge_count: one warp per symbol, coalesced pass over base/volume -> emitted rows and exponential draws per symbol
-//   (two exclusive scans then give every symbol its place in the outputs and in the tapes).
-// k_bridge_ohlcv: one warp per symbol, 32 rows per step.  Loads are coalesced (a lane's k uniforms are contiguous, the
-//   warp's 32 k are too); emitted rows are compacted with a ballot.  What cannot be row-parallel is the dependence of a
-//   candle on the ROUNDED close of the previous emitted candle (spread_simulation: trend bias; trend_following: the
-//   last five closes): that chain is walked lane by lane with the carried closes in warp-uniform registers, and only
-//   the close chain itself sits in the serial loop — opens, highs, lows, volumes and the quality checks are formed in
-//   parallel once every lane knows its predecessor's close.
+// ivx_bridge_plan (k_bridge_count_seg, two scans, k_bridge_sym_off): the candles and exponential draws that precede every
+//   2048-row segment and every symbol.  The global candle index of a row is the number of emitting rows before it —
+//   symbol boundaries do not enter — so these prefixes place every segment and every symbol in the outputs and the tapes.
+// k_bridge_ohlcv_seg: one warp per SEGMENT (k_bridge_ohlcv: one warp per symbol), 32 rows per step.  Loads are coalesced
+//   (a lane's k uniforms are contiguous, the warp's 32 k are too); emitted rows are compacted with a ballot.  What cannot
+//   be row-parallel is the dependence of a candle on the ROUNDED close of the previous emitted candle (spread_simulation:
+//   trend bias; trend_following: the last five closes).  For spread_simulation that chain contracts by 0.15 per emitted
+//   row, which is used twice, both times with an exact check instead of an error bound: inside a chunk the 32 rows are
+//   walked in parallel from a 12-rank warm-up (bridge_piece), and a segment that starts inside a symbol walks the 256
+//   rows before it (k_bridge_ohlcv_seg + k_bridge_check); a failed check falls back to the sequential walk.  Opens,
+//   highs, lows, volumes and the quality checks are formed in parallel once every lane knows its predecessor's close.
 // HBM traffic: 16 B per input row + 8 k B of tape + 56 B per emitted candle.
 #include "ivx_common.cuh"
 
@@ -50,27 +53,6 @@ __device__ __forceinline__ double round_np(double x) {
 }
 __device__ __forceinline__ double uni(double lo, double hi, double u) { return lo + (hi - lo) * u; }   // RandomState.uniform
 
-__global__ void __launch_bounds__(256) k_bridge_count(int64_t n_sym, const int64_t* __restrict__ in_off,
-                                                      const double* __restrict__ base, const double* __restrict__ volume,
-                                                      int64_t* __restrict__ n_out, int64_t* __restrict__ n_e) {
-  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= n_sym) return;
-  const int lane = lane_id();
-  const int64_t a = in_off[s], b = in_off[s + 1];
-  int64_t c_ok = 0, c_e = 0;
-  for (int64_t r = a + lane; r < b; r += 32) {
-    const bool ok = row_ok(ld_stream(base + r));
-    c_ok += ok ? 1 : 0;
-    c_e += (ok && vol_missing(ld_stream(volume + r))) ? 1 : 0;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    c_ok += __shfl_xor_sync(IVX_FULL_MASK, c_ok, d);
-    c_e += __shfl_xor_sync(IVX_FULL_MASK, c_e, d);
-  }
-  if (lane == 0) { n_out[s] = c_ok; n_e[s] = c_e; }
-}
-
 struct BridgeParams {
   int64_t n_sym;
   const int64_t* in_off;
@@ -84,22 +66,29 @@ struct BridgeParams {
   uint32_t* sym_quality;
 };
 
-template <int STRATEGY>
-__global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
-  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= P.n_sym) return;
+// closes of the candles emitted so far in the current symbol (rounded, newest first) — warp-uniform
+struct BridgeState {
+  double pc1, pc2, pc3, pc4, pc5;
+  int n_prev;
+};
+__device__ __forceinline__ BridgeState fresh_state() { return BridgeState{0.0, 0.0, 0.0, 0.0, 0.0, 0}; }
+
+constexpr int CHAIN_W = 12;                                // warm-up ranks of the parallel close walk: 0.15^12 = 1.3e-10
+struct BridgeSmem {
+  double b[4][32], c[4][32], f[4][32];                     // per warp: base and close offset by rank, final closes by rank
+};
+
+// Rows [a, b) of ONE symbol, in chunks of 32, continuing from `st`.  o_base / e_base: candles and exponential draws before
+// row a.  WRITE = false walks the close chain only (the warm-up of a segment that starts inside a symbol).
+template <int STRATEGY, bool WRITE>
+__device__ __forceinline__ void bridge_piece(const BridgeParams& P, const int64_t a, const int64_t b, int64_t& o_base, int64_t& e_base,
+                                             BridgeState& st, uint32_t& qflags, BridgeSmem& sm) {
   const int lane = lane_id();
   const uint32_t lt = (1u << lane) - 1u;
   constexpr int K = STRATEGY == ST_SPREAD ? 5 : STRATEGY == ST_MIDPOINT ? 2 : STRATEGY == ST_PIPELINE ? 4 : STRATEGY == ST_SIMPLE ? 1 : 0;
-  const int64_t a = P.in_off[s], b = P.in_off[s + 1];
-  int64_t o_base = P.out_off[s], e_base = P.e_off[s];
-  constexpr int CHAIN_W = 12;                              // warm-up ranks of the parallel close walk: 0.15^12 = 1.3e-10
-  __shared__ double s_b[STRATEGY == ST_SPREAD ? 4 : 1][32], s_c[STRATEGY == ST_SPREAD ? 4 : 1][32], s_f[STRATEGY == ST_SPREAD ? 4 : 1][32];
-  (void)s_b; (void)s_c; (void)s_f;
-  // closes of the candles emitted so far (rounded, newest first): warp-uniform
-  double pc1 = 0.0, pc2 = 0.0, pc3 = 0.0, pc4 = 0.0, pc5 = 0.0;
-  int n_prev = 0;
-  uint32_t qflags = 0;
+  double (*s_b)[32] = sm.b; double (*s_c)[32] = sm.c; double (*s_f)[32] = sm.f;
+  double &pc1 = st.pc1, &pc2 = st.pc2, &pc3 = st.pc3, &pc4 = st.pc4, &pc5 = st.pc5;
+  int& n_prev = st.n_prev;
   // base/volume of the next chunk are requested before this chunk's (latency-bound) close walk
   double bp_next = (a + lane < b) ? ld_stream(P.base + a + lane) : qnan();
   double vin_next = (a + lane < b) ? ld_stream(P.volume + a + lane) : 1.0;
@@ -118,8 +107,8 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
     const int64_t o = o_base + __popc(okm & lt);
     double uu[K > 0 ? K : 1];
 #pragma unroll
-    for (int k = 0; k < K; ++k) uu[k] = ok ? ld_stream(P.u + o * K + k) : 0.0;
-    const double ev = nv ? ld_stream(P.e + e_base + __popc(nvm & lt)) : 0.0;
+    for (int k = 0; k < K; ++k) uu[k] = (ok && (WRITE || k == 0 || k == 2)) ? ld_stream(P.u + o * K + k) : 0.0;
+    const double ev = (WRITE && nv) ? ld_stream(P.e + e_base + __popc(nvm & lt)) : 0.0;
     double op = 0.0, hp = 0.0, lp = 0.0, cp = 0.0;         // unrounded open/high/low, ROUNDED close
     if (STRATEGY == ST_SPREAD) {
       const double vm = uni(0.5, P.volatility_factor, uu[0]);                  // :215
@@ -179,6 +168,7 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
           n_prev = 1;
         }
       }
+      if (!WRITE) { o_base += __popc(okm); continue; }
       const double tb = has_prev ? (bp - prev) * 0.3 : 0.0;
       op = bp + (oo + tb * 0.2);                                                // :225-226
       const double cu = bp + (co + tb * 0.5);                                   // the unrounded close
@@ -250,9 +240,142 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
     o_base += __popc(okm);
     e_base += __popc(nvm);
   }
+}
+
+// ---- one warp per SYMBOL: exact by construction.  Used for trend_following (a five-close memory: its contraction is too
+// slow for the segment warm-up below) and, with `only_if` set, as the stream-ordered fallback of the segmented kernel ----
+template <int STRATEGY>
+__global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P, const int32_t* __restrict__ only_if) {
+  if (only_if && *only_if == 0) return;
+  __shared__ BridgeSmem sm;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= P.n_sym) return;
+  int64_t o_base = P.out_off[s], e_base = P.e_off[s];
+  BridgeState st = fresh_state();
+  uint32_t qflags = 0;
+  bridge_piece<STRATEGY, true>(P, P.in_off[s], P.in_off[s + 1], o_base, e_base, st, qflags, sm);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) qflags |= __shfl_xor_sync(IVX_FULL_MASK, qflags, d);
-  if (lane == 0 && P.sym_quality) P.sym_quality[s] = qflags;
+  if (lane_id() == 0 && P.sym_quality) P.sym_quality[s] = qflags;
+}
+
+// ---- one warp per SEGMENT of SEG consecutive rows, whatever symbols they belong to: the parallelism no longer depends
+// on how many symbols there are or how long they are (2 400 contracts x 28 801 rows gave 16 warps per SM).  The global
+// candle index of a row is the number of emitting rows before it — symbol boundaries do not enter — so two scans over
+// per-segment counts place every segment in the outputs and in the tapes.
+// A segment that starts INSIDE a symbol needs the carried close of the row before it.  It is obtained by walking the
+// close chain over the WARM rows before the segment from a fresh state: the chain forgets its start at 0.15 per emitted
+// row (see bridge_piece), so after a few dozen emitted rows the walk is ON the true trajectory — and that is CHECKED,
+// not assumed: every segment records the state it entered with and the state it left with, k_bridge_check compares each
+// speculative entry with its predecessor's exit bit for bit (by induction from the segments that start a symbol or
+// whose warm-up reaches the symbol's start, all states are then the sequential ones), and any mismatch raises a flag on
+// which the per-symbol kernel above — enqueued right behind, idle otherwise — recomputes the batch exactly.
+constexpr int SEG = 2048, WARM = 256;
+struct SegArrays {
+  int64_t n_seg;
+  const int64_t *seg_out, *seg_e;       // [n_seg + 1] candles / exponential draws before each segment
+  double *entry_pc, *exit_pc;           // [n_seg]
+  int32_t *entry_has, *exit_has, *spec; // [n_seg]
+  int32_t* flag;
+};
+
+__global__ void __launch_bounds__(256) k_bridge_count_seg(int64_t n_rows, const double* __restrict__ base, const double* __restrict__ volume,
+                                                          int64_t n_seg, int64_t* __restrict__ n_out, int64_t* __restrict__ n_e) {
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= n_seg) return;
+  const int lane = lane_id();
+  const int64_t a = g * SEG, b = min(n_rows, a + SEG);
+  int c_ok = 0, c_e = 0;
+  for (int64_t r = a + lane; r < b; r += 32) {
+    const bool ok = row_ok(ld_stream(base + r));
+    c_ok += ok ? 1 : 0;
+    c_e += (ok && vol_missing(ld_stream(volume + r))) ? 1 : 0;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    c_ok += __shfl_xor_sync(IVX_FULL_MASK, c_ok, d);
+    c_e += __shfl_xor_sync(IVX_FULL_MASK, c_e, d);
+  }
+  if (lane == 0) { n_out[g] = c_ok; n_e[g] = c_e; }
+}
+
+// out_off[s] / e_off[s] = candles / exponential draws before the first row of symbol s (s = n_sym: the totals): the
+// segment prefix plus a count over at most SEG rows
+__global__ void __launch_bounds__(256) k_bridge_sym_off(int64_t n_sym, int64_t n_rows, const int64_t* __restrict__ in_off,
+                                                        const double* __restrict__ base, const double* __restrict__ volume,
+                                                        int64_t n_seg, const int64_t* __restrict__ seg_out, const int64_t* __restrict__ seg_e,
+                                                        int64_t* __restrict__ out_off, int64_t* __restrict__ e_off) {
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s > n_sym) return;
+  const int lane = lane_id();
+  const int64_t r = s < n_sym ? in_off[s] : n_rows;
+  const int64_t g = min(r / SEG, n_seg);
+  int c_ok = 0, c_e = 0;
+  for (int64_t q = g * SEG + lane; q < r; q += 32) {
+    const bool ok = row_ok(ld_stream(base + q));
+    c_ok += ok ? 1 : 0;
+    c_e += (ok && vol_missing(ld_stream(volume + q))) ? 1 : 0;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    c_ok += __shfl_xor_sync(IVX_FULL_MASK, c_ok, d);
+    c_e += __shfl_xor_sync(IVX_FULL_MASK, c_e, d);
+  }
+  if (lane == 0) { out_off[s] = seg_out[g] + c_ok; e_off[s] = seg_e[g] + c_e; }
+}
+
+template <int STRATEGY>
+__global__ void __launch_bounds__(128) k_bridge_ohlcv_seg(const BridgeParams P, const SegArrays A, int64_t n_rows) {
+  __shared__ BridgeSmem sm;
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= A.n_seg) return;
+  const int lane = lane_id();
+  const int64_t r0 = g * SEG, r1 = min(n_rows, r0 + SEG);
+  int64_t o_base = A.seg_out[g], e_base = A.seg_e[g];
+  // the symbol that owns row r0: the last s with in_off[s] <= r0 (empty symbols before it share that offset)
+  int64_t sym = warp_upper_le<int64_t>(P.in_off, 0, P.n_sym, r0, lane);
+  int64_t sym_start = __ldg(P.in_off + sym), sym_end = __ldg(P.in_off + sym + 1);
+  BridgeState st = fresh_state();
+  uint32_t dummy_flags = 0;
+  int32_t spec = 0;
+  if (STRATEGY == ST_SPREAD && r0 > sym_start) {
+    const int64_t ws = max(sym_start, r0 - WARM);
+    spec = ws > sym_start ? 1 : 0;
+    int cnt = 0;                                       // emitting rows in [ws, r0): where the warm-up's uniforms start
+    for (int64_t r = ws + lane; r < r0; r += 32) cnt += row_ok(ld_stream(P.base + r)) ? 1 : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(IVX_FULL_MASK, cnt, d);
+    int64_t o_w = o_base - cnt, e_w = 0;
+    bridge_piece<STRATEGY, false>(P, ws, r0, o_w, e_w, st, dummy_flags, sm);
+  }
+  if (lane == 0) { A.entry_pc[g] = st.pc1; A.entry_has[g] = st.n_prev > 0; A.spec[g] = spec; }
+  // the segment's rows, symbol piece after symbol piece
+  int64_t a = r0;
+  while (a < r1) {
+    const int64_t b = min(r1, sym_end);
+    if (b > a) {
+      uint32_t qflags = 0;
+      bridge_piece<STRATEGY, true>(P, a, b, o_base, e_base, st, qflags, sm);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) qflags |= __shfl_xor_sync(IVX_FULL_MASK, qflags, d);
+      if (lane == 0 && P.sym_quality && qflags) atomicOr(P.sym_quality + sym, qflags);
+      a = b;
+    }
+    if (a < r1) {                                      // next symbol: fresh state
+      ++sym;
+      sym_start = sym_end; sym_end = __ldg(P.in_off + sym + 1);
+      st = fresh_state();
+    }
+  }
+  if (lane == 0) { A.exit_pc[g] = st.pc1; A.exit_has[g] = st.n_prev > 0; }
+}
+
+__global__ void __launch_bounds__(256) k_bridge_check(const SegArrays A, int32_t force) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (force && g == 0) atomicOr(A.flag, 1);
+  if (g < 1 || g >= A.n_seg || !A.spec[g]) return;
+  const bool same = (__double_as_longlong(A.entry_pc[g]) == __double_as_longlong(A.exit_pc[g - 1])) && (A.entry_has[g] == A.exit_has[g - 1]);
+  if (!same) atomicOr(A.flag, 1);
 }
 
 }  // namespace
@@ -260,25 +383,54 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P) {
 
 using namespace ivx;
 
-extern "C" int ivx_bridge_count(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
-                                int64_t* n_out, int64_t* n_e, ivx_stream_t stream) {
-  IVX_REQUIRE(n_sym >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_count: negative n_sym");
-  if (n_sym == 0) return IVX_OK;
-  IVX_REQUIRE(in_off && base && volume && n_out && n_e, IVX_ERR_INVALID_ARG, "ivx_bridge_count: null pointer");
-  k_bridge_count<<<(unsigned)((n_sym + 7) / 8), 256, 0, (cudaStream_t)stream>>>(n_sym, in_off, base, volume, n_out, n_e);
-  IVX_LAUNCH_CHECK("k_bridge_count");
+static int32_t g_force_fallback = 0;
+// test hook: make the segment check fail so that the stream-ordered per-symbol fallback runs (tests/test_gpu_bridge.py)
+extern "C" void ivx_bridge_test_force_fallback(int32_t on) { g_force_fallback = on; }
+
+extern "C" int64_t ivx_bridge_n_segments(int64_t n_rows) { return n_rows < 0 ? -1 : (n_rows + SEG - 1) / SEG; }
+
+extern "C" int64_t ivx_bridge_workspace_bytes(int64_t n_rows) {
+  if (n_rows < 0) return -1;
+  const int64_t g = (n_rows + SEG - 1) / SEG;
+  return 8 * 2 * g + 4 * (3 * g + 1) + 8 * 256;            // the larger of the plan's (two count arrays) and the candle call's (entry/exit states, spec, flag) needs
+}
+
+extern "C" int ivx_bridge_plan(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
+                               int64_t* seg_out, int64_t* seg_e, int64_t* out_off, int64_t* e_off, void* workspace,
+                               int64_t workspace_bytes, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_sym >= 0 && n_rows >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_plan: negative size");
+  IVX_REQUIRE(in_off && seg_out && seg_e && out_off && e_off && workspace && (n_rows == 0 || (base && volume)), IVX_ERR_INVALID_ARG,
+              "ivx_bridge_plan: null pointer");
+  IVX_REQUIRE(workspace_bytes >= ivx_bridge_workspace_bytes(n_rows), IVX_ERR_INVALID_ARG, "ivx_bridge_plan: workspace too small");
+  const int64_t g = (n_rows + SEG - 1) / SEG;
+  Carver cv(workspace, workspace_bytes);
+  int64_t* n_out_seg = cv.take<int64_t>(g);
+  int64_t* n_e_seg = cv.take<int64_t>(g);
+  if (g > 0) {
+    k_bridge_count_seg<<<(unsigned)((g + 7) / 8), 256, 0, stream>>>(n_rows, base, volume, g, n_out_seg, n_e_seg);
+    IVX_LAUNCH_CHECK("k_bridge_count_seg");
+  }
+  int rc = ivx_exclusive_scan_i64(g, n_out_seg, seg_out, stream_);
+  if (rc != IVX_OK) return rc;
+  rc = ivx_exclusive_scan_i64(g, n_e_seg, seg_e, stream_);
+  if (rc != IVX_OK) return rc;
+  k_bridge_sym_off<<<(unsigned)((n_sym + 1 + 7) / 8), 256, 0, stream>>>(n_sym, n_rows, in_off, base, volume, g, seg_out, seg_e, out_off, e_off);
+  IVX_LAUNCH_CHECK("k_bridge_sym_off");
   return IVX_OK;
 }
 
-extern "C" int ivx_bridge_ohlcv(int64_t n_sym, const int64_t* in_off, const double* base, const double* volume,
+extern "C" int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
                                 int32_t strategy, double base_spread_percent, double volatility_factor, const double* u,
                                 const double* e, const double* z, const int64_t* out_off, const int64_t* e_off,
+                                const int64_t* seg_out, const int64_t* seg_e,
                                 int64_t* o_row, double* o_open, double* o_high, double* o_low, double* o_close,
-                                double* o_volume, double* o_source, uint32_t* sym_quality, ivx_stream_t stream_) {
+                                double* o_volume, double* o_source, uint32_t* sym_quality, void* workspace,
+                                int64_t workspace_bytes, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  IVX_REQUIRE(n_sym >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: negative n_sym");
+  IVX_REQUIRE(n_sym >= 0 && n_rows >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: negative size");
   IVX_REQUIRE(strategy >= ST_SPREAD && strategy <= ST_PIPELINE, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: unknown strategy %d", strategy);
-  if (n_sym == 0) return IVX_OK;
+  if (n_sym == 0 || n_rows == 0) return IVX_OK;
   IVX_REQUIRE(in_off && base && volume && out_off && e_off && o_row && o_open && o_high && o_low && o_close && o_volume && o_source,
               IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: null pointer");
   IVX_REQUIRE(strategy == ST_TREND ? z != nullptr : u != nullptr, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: the strategy's tape is missing");
@@ -286,13 +438,44 @@ extern "C" int ivx_bridge_ohlcv(int64_t n_sym, const int64_t* in_off, const doub
   BridgeParams P{n_sym, in_off, base, volume, strategy, base_spread_percent, volatility_factor, u, e, z, out_off, e_off,
                  o_row, o_open, o_high, o_low, o_close, o_volume, o_source, sym_quality};
   const unsigned blocks = (unsigned)((n_sym + 3) / 4);
-  switch (strategy) {
-    case ST_SPREAD: k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P); break;
-    case ST_MIDPOINT: k_bridge_ohlcv<ST_MIDPOINT><<<blocks, 128, 0, stream>>>(P); break;
-    case ST_TREND: k_bridge_ohlcv<ST_TREND><<<blocks, 128, 0, stream>>>(P); break;
-    case ST_SIMPLE: k_bridge_ohlcv<ST_SIMPLE><<<blocks, 128, 0, stream>>>(P); break;
-    default: k_bridge_ohlcv<ST_PIPELINE><<<blocks, 128, 0, stream>>>(P); break;
+  if (strategy == ST_TREND || workspace == nullptr || seg_out == nullptr || seg_e == nullptr) {   // one warp per symbol
+    switch (strategy) {
+      case ST_SPREAD: k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      case ST_MIDPOINT: k_bridge_ohlcv<ST_MIDPOINT><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      case ST_TREND: k_bridge_ohlcv<ST_TREND><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      case ST_SIMPLE: k_bridge_ohlcv<ST_SIMPLE><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      default: k_bridge_ohlcv<ST_PIPELINE><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+    }
+    IVX_LAUNCH_CHECK("k_bridge_ohlcv");
+    return IVX_OK;
   }
-  IVX_LAUNCH_CHECK("k_bridge_ohlcv");
+  // one warp per segment of SEG rows
+  IVX_REQUIRE(workspace_bytes >= ivx_bridge_workspace_bytes(n_rows), IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: workspace too small");
+  const int64_t g = (n_rows + SEG - 1) / SEG;
+  Carver cv(workspace, workspace_bytes);
+  SegArrays A;
+  A.n_seg = g; A.seg_out = seg_out; A.seg_e = seg_e;
+  A.entry_pc = cv.take<double>(g); A.exit_pc = cv.take<double>(g);
+  A.entry_has = cv.take<int32_t>(g); A.exit_has = cv.take<int32_t>(g); A.spec = cv.take<int32_t>(g);
+  A.flag = cv.take<int32_t>(1);
+  IVX_REQUIRE(cv.ok(), IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: workspace too small");
+  IVX_CUDA(cudaMemsetAsync(A.flag, 0, sizeof(int32_t), stream));
+  if (sym_quality) IVX_CUDA(cudaMemsetAsync(sym_quality, 0, (size_t)n_sym * sizeof(uint32_t), stream));
+  const unsigned sblocks = (unsigned)((g + 3) / 4);
+  switch (strategy) {
+    case ST_SPREAD: k_bridge_ohlcv_seg<ST_SPREAD><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+    case ST_MIDPOINT: k_bridge_ohlcv_seg<ST_MIDPOINT><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+    case ST_SIMPLE: k_bridge_ohlcv_seg<ST_SIMPLE><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+    default: k_bridge_ohlcv_seg<ST_PIPELINE><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+  }
+  IVX_LAUNCH_CHECK("k_bridge_ohlcv_seg");
+  if (strategy == ST_SPREAD) {
+    // the carried closes the segments assumed are checked against the ones their predecessors produced; on a mismatch
+    // (never seen; ~1e-9 per boundary by the contraction argument) the per-symbol kernel recomputes the batch, stream-ordered
+    k_bridge_check<<<(unsigned)((g + 255) / 256), 256, 0, stream>>>(A, g_force_fallback);
+    IVX_LAUNCH_CHECK("k_bridge_check");
+    k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P, A.flag);
+    IVX_LAUNCH_CHECK("k_bridge_ohlcv(fallback)");
+  }
   return IVX_OK;
 }

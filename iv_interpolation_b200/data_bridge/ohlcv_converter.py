@@ -1,7 +1,7 @@
 """InterpolatedToOHLCVConverter — the reference's data bridge (src/data_bridge/ohlcv_converter.py:16-418) on the B200.
 
 Same class name, constructor and method names as the reference; the candle arithmetic runs in libivx.so
-(``k_bridge_count`` + ``k_bridge_ohlcv``, include/ivx.h "Data bridge").  No CPU fallback.
+(``ivx_bridge_plan`` + ``ivx_bridge_ohlcv``, include/ivx.h "Data bridge").  No CPU fallback.
 
 Randomness.  The reference calls ``np.random.uniform / exponential / normal`` row by row on numpy's GLOBAL generator.
 This class takes its draws from the same place in the same order (one ``random_sample`` per uniform or exponential,

@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2, "spline_ladder_factor": 1,
-    "bridge_count": 1, "bridge_ohlcv": 1,
+    "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
 
@@ -474,6 +474,8 @@ def spline_strided_batched(x: torch.Tensor, x_batch_stride: int, x_knot_stride: 
 class BridgePlan:
     out_off: torch.Tensor          # int64[n_sym+1] emitted candles before each symbol
     e_off: torch.Tensor            # int64[n_sym+1] exponential draws before each symbol
+    seg_out: torch.Tensor          # int64[n_seg+1] the same before each 2048-row segment
+    seg_e: torch.Tensor
     total: int
     total_e: int
 
@@ -494,23 +496,28 @@ class BridgeBatch:
 
 def bridge_plan(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor) -> BridgePlan:
     """Rows that emit a candle (base price neither NaN nor <= 0, ohlcv_converter.py:152) and rows among them whose
-    volume is drawn (NaN or <= 0, :373), per symbol, as exclusive scans: the tape layout of ``bridge_ohlcv``."""
-    n_sym = in_off.numel() - 1
-    n_out = _empty(n_sym, torch.int64, in_off)
-    n_e = _empty(n_sym, torch.int64, in_off)
-    check(lib().ivx_bridge_count(n_sym, _ptr(_req(in_off, torch.int64, "in_off")), _ptr(_req(base, torch.float64, "base")),
-                                 _ptr(_req(volume, torch.float64, "volume")), _ptr(n_out), _ptr(n_e), _stream()), "ivx_bridge_count")
-    _count("bridge_count")
-    out_off, e_off = exclusive_scan(n_out), exclusive_scan(n_e)
+    volume is drawn (NaN or <= 0, :359-369), counted before every symbol and before every 2048-row segment: the layout of
+    the outputs and of the tapes of ``bridge_ohlcv``."""
+    n_sym, n_rows = in_off.numel() - 1, base.numel()
+    n_seg = lib().ivx_bridge_n_segments(n_rows)
+    seg_out, seg_e = _empty(n_seg + 1, torch.int64, in_off), _empty(n_seg + 1, torch.int64, in_off)
+    out_off, e_off = _empty(n_sym + 1, torch.int64, in_off), _empty(n_sym + 1, torch.int64, in_off)
+    wsb = lib().ivx_bridge_workspace_bytes(n_rows)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=in_off.device)
+    check(lib().ivx_bridge_plan(n_sym, n_rows, _ptr(_req(in_off, torch.int64, "in_off")), _ptr(_req(base, torch.float64, "base")),
+                                _ptr(_req(volume, torch.float64, "volume")), _ptr(seg_out), _ptr(seg_e), _ptr(out_off), _ptr(e_off),
+                                _ptr(ws), wsb, _stream()), "ivx_bridge_plan")
+    _count("bridge_plan")
     totals = torch.stack([out_off[-1], e_off[-1]]).cpu()          # 16 bytes: sizes of the outputs and of the tapes
-    return BridgePlan(out_off, e_off, int(totals[0]), int(totals[1]))
+    return BridgePlan(out_off, e_off, seg_out, seg_e, int(totals[0]), int(totals[1]))
 
 
 def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor, plan: BridgePlan, strategy: str, *,
                  u: Optional[torch.Tensor] = None, e: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
-                 base_spread_percent: float = 0.002, volatility_factor: float = 1.5) -> BridgeBatch:
+                 base_spread_percent: float = 0.002, volatility_factor: float = 1.5, segmented: bool = True) -> BridgeBatch:
     """Synthetic 1-minute candles from interpolated rows, every candle bit-equal to the reference's given the same
-    random tapes (see include/ivx.h).  ``strategy`` is one of _lib.BRIDGE_STRATEGY."""
+    random tapes (see include/ivx.h).  ``strategy`` is one of _lib.BRIDGE_STRATEGY.  ``segmented=False`` runs one warp per
+    symbol instead of one per 2048-row segment (same results)."""
     code = _lib.BRIDGE_STRATEGY[strategy]
     k = _lib.BRIDGE_U_PER_ROW[code]
     n_sym = in_off.numel() - 1
@@ -526,13 +533,20 @@ def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor,
     cols = [_empty(m, torch.float64, base) for _ in range(6)]
     row = _empty(m, torch.int64, base)
     q = torch.zeros(n_sym, dtype=torch.int32, device=base.device)
-    check(lib().ivx_bridge_ohlcv(n_sym, _ptr(in_off), _ptr(_req(base, torch.float64, "base")), _ptr(_req(volume, torch.float64, "volume")),
+    use_seg = segmented and code != 2
+    ws, wsb = None, 0
+    if use_seg:
+        wsb = lib().ivx_bridge_workspace_bytes(base.numel())
+        ws = torch.empty(wsb, dtype=torch.uint8, device=base.device)
+    check(lib().ivx_bridge_ohlcv(n_sym, base.numel(), _ptr(in_off), _ptr(_req(base, torch.float64, "base")), _ptr(_req(volume, torch.float64, "volume")),
                                  code, float(base_spread_percent), float(volatility_factor),
                                  _ptr(_req(u, torch.float64, "u")) if u is not None else None, _ptr(_req(e, torch.float64, "e")),
                                  _ptr(_req(z, torch.float64, "z")) if z is not None else None,
-                                 _ptr(plan.out_off), _ptr(plan.e_off), _ptr(row), *(_ptr(c) for c in cols), _ptr(q), _stream()),
+                                 _ptr(plan.out_off), _ptr(plan.e_off), _ptr(plan.seg_out) if use_seg else None,
+                                 _ptr(plan.seg_e) if use_seg else None, _ptr(row), *(_ptr(c) for c in cols), _ptr(q),
+                                 _ptr(ws), wsb, _stream()),
           "ivx_bridge_ohlcv")
-    _count("bridge_ohlcv")
+    _count("bridge_ohlcv_seg" if use_seg else "bridge_ohlcv")
     return BridgeBatch(plan.out_off, row, *cols, q, m)
 
 

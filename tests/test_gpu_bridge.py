@@ -1,4 +1,4 @@
-"""GPU parity of the data bridge (k_bridge_count + k_bridge_ohlcv, through the C ABI) against goldens produced by the
+"""GPU parity of the data bridge (ivx_bridge_plan + ivx_bridge_ohlcv through the C ABI: one warp per segment, one warp per symbol, and the forced fallback) against goldens produced by the
 reference's own code under a seeded generator, and against the oracle restatement on larger tapes.  Bit-exact."""
 import json
 import logging
@@ -24,13 +24,13 @@ def _t(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-def _run(dev, strategy, off, base, volume, u, e, z):
+def _run(dev, strategy, off, base, volume, u, e, z, segmented=True):
     from iv_interpolation_b200 import device as D
     canon = B.canonical_strategy(strategy)
     d_off, d_base, d_vol = _t(off, dev), _t(base, dev), _t(volume, dev)
     plan = D.bridge_plan(d_off, d_base, d_vol)
     res = D.bridge_ohlcv(d_off, d_base, d_vol, plan, canon, u=_t(u, dev) if len(u) else None, e=_t(e, dev),
-                         z=_t(z, dev) if len(z) else None)
+                         z=_t(z, dev) if len(z) else None, segmented=segmented)
     h = lambda x: x.cpu().numpy()
     return dict(out_off=h(res.out_off), e_off=h(plan.e_off), row=h(res.row), open=h(res.open), high=h(res.high), low=h(res.low),
                 close=h(res.close), volume=h(res.volume), source_price=h(res.source_price), quality=h(res.sym_quality))
@@ -81,12 +81,17 @@ def test_bridge_batch_equals_symbol_after_symbol(dev, golden_bridge):
         assert got["out_off"][-1] == got["out_off"][-2]
 
 
+@pytest.mark.parametrize("mode", ["segments", "symbols", "fallback"])
 @pytest.mark.parametrize("strategy", ["spread_simulation", "trend_following", "price_as_midpoint", "simple_spread", "pipeline"])
-def test_bridge_kernel_vs_oracle_ragged(dev, strategy):
+def test_bridge_kernel_vs_oracle_ragged(dev, strategy, mode):
     """Ragged symbols (0 to 3000 rows, chunk boundaries at 31/32/33/64/65 rows), 4-decimal prices where the rounding of
     the carried close matters, missing prices and volumes."""
     rng = np.random.default_rng(123)
-    lens = [0, 1, 2, 31, 32, 33, 64, 65, 100, 999, 3000, 1, 0, 257, 700, 90]
+    if mode == "fallback" and strategy != "spread_simulation":
+        pytest.skip("only the spread strategy carries state across segments")
+    # 7000- and 3000-row symbols span several 2048-row segments (warm-up walk + boundary check); 5 rows before a segment
+    # boundary and symbols that start exactly on one are in there too
+    lens = [0, 1, 2, 31, 32, 33, 64, 65, 100, 999, 3000, 1, 0, 257, 700, 90, 7000, 1788, 2048, 5]
     rs = np.random.RandomState(77)
     bases, vols, us, es, zs, want = [], [], [], [], [], []
     for i, n in enumerate(lens):
@@ -107,7 +112,13 @@ def test_bridge_kernel_vs_oracle_ragged(dev, strategy):
         bases.append(b); vols.append(v); us.append(u); es.append(e); zs.append(z)
     off = np.zeros(len(lens) + 1, np.int64)
     np.cumsum(lens, out=off[1:])
-    got = _run(dev, strategy, off, np.concatenate(bases), np.concatenate(vols), np.concatenate(us), np.concatenate(es), np.concatenate(zs))
+    from iv_interpolation_b200 import _lib
+    _lib.lib().ivx_bridge_test_force_fallback(1 if mode == "fallback" else 0)
+    try:
+        got = _run(dev, strategy, off, np.concatenate(bases), np.concatenate(vols), np.concatenate(us), np.concatenate(es), np.concatenate(zs),
+                   segmented=mode != "symbols")
+    finally:
+        _lib.lib().ivx_bridge_test_force_fallback(0)
     for i, w in enumerate(want):
         a, b = int(got["out_off"][i]), int(got["out_off"][i + 1])
         assert b - a == len(w["row"]), (i, lens[i])
