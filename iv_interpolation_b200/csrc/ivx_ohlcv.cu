@@ -2,7 +2,7 @@
 //
 // Replaces reference src/candle_reconstruction/core.py:59-89 (sort excluded: rows arrive sorted)
 // and complete_pipeline.py:685-710 for a CSR batch of symbols in ONE pass over HBM:
-//   * a tile of TB_ROWS rows (6 columns, 48 KB) is staged into shared memory with 1-D bulk async
+//   * a tile of TB_ROWS rows (6 columns, 23 KB) is staged into shared memory with 1-D bulk async
 //     copies (TMA engine) completing on an mbarrier;
 //   * bucket ids come from a multiply-high floor division (no 64-bit divide per row);
 //   * bucket heads are found with warp ballots, one thread then walks each bucket IN ROW ORDER —
@@ -15,8 +15,8 @@
 namespace ivx {
 namespace {
 
-constexpr int TB_THREADS = 160;   // warp 0 runs the look-back while 4 warps walk ~103 five-row buckets of a tile in one pass
-constexpr int TB_ROWS = 512;
+constexpr int TB_THREADS = 160;   // warp 0 runs the look-back while 4 warps walk ~96 five-row buckets of a tile in one pass
+constexpr int TB_ROWS = 480;
 constexpr int TB_PER = (TB_ROWS + TB_THREADS - 1) / TB_THREADS;   // rows per thread in the row-parallel phases
 constexpr int TB_GROUPS = TB_ROWS / 32;
 constexpr int64_t BID_NAT = INT64_MIN;  // bucket id given to rows without a timestamp
@@ -486,10 +486,9 @@ extern "C" int ivx_ohlcv_reduce(int64_t n_sym, const int64_t* in_off, int64_t n_
   int64_t* raw_out = cv.take<int64_t>(n_sym + 1);
   int64_t* raw_grp = cv.take<int64_t>(n_sym + 1);
 
-  IVX_CUDA(cudaMemsetAsync(counter, 0, 256 * 4, stream));
-  IVX_CUDA(cudaMemsetAsync(tile_state, 0, (n_tiles + 1) * 8, stream));
-  IVX_CUDA(cudaMemsetAsync(raw_out, 0xFF, (n_sym + 1) * 8, stream));
-  IVX_CUDA(cudaMemsetAsync(raw_grp, 0xFF, (n_sym + 1) * 8, stream));
+  // the carved arrays are adjacent (256-byte aligned): one memset for the zeroed pair, one for the -1 pair
+  IVX_CUDA(cudaMemsetAsync(counter, 0, (size_t)((char*)(tile_state + n_tiles + 1) - (char*)counter), stream));
+  IVX_CUDA(cudaMemsetAsync(raw_out, 0xFF, (size_t)((char*)(raw_grp + n_sym + 1) - (char*)raw_out), stream));
   IVX_CUDA(cudaMemsetAsync(total, 0, 8, stream));
   if (sym_flags && n_sym) IVX_CUDA(cudaMemsetAsync(sym_flags, 0, n_sym * 4, stream));
 
