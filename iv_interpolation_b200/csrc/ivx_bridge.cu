@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv_seg(const BridgeParams P, 
       a = b;
     }
     if (a < r1) {                                      // next symbol: fresh state
+      if (sym + 1 >= P.n_sym) break;                   // rows beyond in_off[n_sym] (inconsistent arguments): not ours
       ++sym;
       sym_start = sym_end; sym_end = __ldg(P.in_off + sym + 1);
       st = fresh_state();
