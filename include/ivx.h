@@ -260,6 +260,9 @@ int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const
                      int64_t* o_row, double* o_open, double* o_high, double* o_low, double* o_close,
                      double* o_volume, double* o_source, uint32_t* sym_quality /*n_sym or NULL*/,
                      void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+/* the same quality bits for candles that already exist (ohlcv_converter.py:371-402 on a frame): *flags = OR over n rows */
+int ivx_bridge_quality(int64_t n, const double* open, const double* high, const double* low, const double* close,
+                       const double* source_price, uint32_t* flags /*1*/, ivx_stream_t stream);
 void ivx_bridge_test_force_fallback(int32_t on);   /* test hook: the segment check reports a mismatch, the fallback runs */
 
 /* ---------------------------------------------------------------------------------------------

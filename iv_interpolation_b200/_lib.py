@@ -64,6 +64,7 @@ SIGNATURES = {
     "ivx_bridge_n_segments": (_i64, [_i64]),
     "ivx_bridge_workspace_bytes": (_i64, [_i64]),
     "ivx_bridge_test_force_fallback": (None, [_i32]),
+    "ivx_bridge_quality": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "ivx_bridge_plan": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_bridge_ohlcv": (C.c_int, [_i64, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),

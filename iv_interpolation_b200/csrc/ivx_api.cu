@@ -39,7 +39,7 @@ extern "C" const char* ivx_last_error_string(void) { return ivx::g_err; }
 extern "C" const char* ivx_build_info(void) {
   return "libivx sm_100a: k_interp_plan,k_interp_exec,k_scan_i64,k_ohlcv_reduce,k_ohlcv_finalize,k_time_buckets,"
          "k_ohlc_time_major,k_bs_implied_vol,k_bs_price,k_bs_greeks,k_spline_fit_eval,k_spline_strided,"
-         "k_bridge_count_seg,k_bridge_sym_off,k_bridge_ohlcv_seg,k_bridge_check,k_bridge_ohlcv,k_probe_copy,k_probe_fp64";
+         "k_bridge_count_seg,k_bridge_sym_off,k_bridge_ohlcv_seg,k_bridge_check,k_bridge_ohlcv,k_bridge_quality,k_probe_copy,k_probe_fp64";
 }
 
 // host-side check of the multiply-high floor division used by the bucket kernels (tests call this)

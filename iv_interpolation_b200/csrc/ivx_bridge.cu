@@ -371,6 +371,24 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv_seg(const BridgeParams P, 
   if (lane == 0) { A.exit_pc[g] = st.pc1; A.exit_has[g] = st.n_prev > 0; }
 }
 
+// _validate_ohlcv_quality (:371-402) on candles that are already there (a frame the caller hands in): flag bits OR-ed
+__global__ void __launch_bounds__(256) k_bridge_quality(int64_t n, const double* __restrict__ o, const double* __restrict__ h,
+                                                        const double* __restrict__ l, const double* __restrict__ c,
+                                                        const double* __restrict__ src, uint32_t* __restrict__ flags) {
+  uint32_t f = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ro = o[i], rh = h[i], rl = l[i], cp = c[i], bp = src[i];
+    if (rh < rl) f |= Q_HIGH_LT_LOW;
+    if (rh < ro || rh < cp) f |= Q_HIGH_LT_OC;
+    if (rl > ro || rl > cp) f |= Q_LOW_GT_OC;
+    if ((rh - rl) / bp > 0.1) f |= Q_SPREAD;
+    if (ro <= 0.0 || rh <= 0.0 || rl <= 0.0 || cp <= 0.0) f |= Q_NONPOSITIVE;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) f |= __shfl_xor_sync(IVX_FULL_MASK, f, d);
+  if (lane_id() == 0 && f) atomicOr(flags, f);
+}
+
 __global__ void __launch_bounds__(256) k_bridge_check(const SegArrays A, int32_t force) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (force && g == 0) atomicOr(A.flag, 1);
@@ -478,5 +496,18 @@ extern "C" int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in
     k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P, A.flag);
     IVX_LAUNCH_CHECK("k_bridge_ohlcv(fallback)");
   }
+  return IVX_OK;
+}
+
+extern "C" int ivx_bridge_quality(int64_t n, const double* open, const double* high, const double* low, const double* close,
+                                  const double* source_price, uint32_t* flags, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n >= 0 && flags, IVX_ERR_INVALID_ARG, "ivx_bridge_quality: bad arguments");
+  IVX_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t), stream));
+  if (n == 0) return IVX_OK;
+  IVX_REQUIRE(open && high && low && close && source_price, IVX_ERR_INVALID_ARG, "ivx_bridge_quality: null pointer");
+  const int64_t blocks = (n + 255) / 256;
+  k_bridge_quality<<<(unsigned)(blocks < 4 * 148 ? blocks : 4 * 148), 256, 0, stream>>>(n, open, high, low, close, source_price, flags);
+  IVX_LAUNCH_CHECK("k_bridge_quality");
   return IVX_OK;
 }

@@ -108,19 +108,16 @@ class InterpolatedToOHLCVConverter:
         raise ValueError("No suitable price column found")
 
     def _validate_ohlcv_quality(self, ohlcv_df: pd.DataFrame) -> Dict:
-        """Reference :371-402, on a frame (host arithmetic on a frame already on the host; the batch path gets the same
-        verdict from the kernel's flag bits)."""
+        """Reference :371-402 on a frame: the five checks run on the device (``ivx_bridge_quality``), the verdict is the
+        first failing one in the reference's order; any error inside is reported the way the reference reports it."""
         try:
-            o, h, l, c = (ohlcv_df[k].to_numpy(dtype=np.float64) for k in ("open", "high", "low", "close"))
-            src = ohlcv_df["source_price"].to_numpy(dtype=np.float64)
-            flags = 0
-            with np.errstate(invalid="ignore", divide="ignore"):
-                flags |= 1 if (h < l).any() else 0
-                flags |= 2 if ((h < o) | (h < c)).any() else 0
-                flags |= 4 if ((l > o) | (l > c)).any() else 0
-                flags |= 8 if (((h - l) / src) > 0.1).any() else 0
-                flags |= 16 if ((o <= 0) | (h <= 0) | (l <= 0) | (c <= 0)).any() else 0
-            return self._quality_verdict(flags)
+            import torch
+
+            from .. import device as D
+            dev = torch.device(self._device) if self._device is not None else torch.device("cuda")
+            cols = [torch.from_numpy(np.array(ohlcv_df[k].to_numpy(dtype=np.float64), copy=True)).to(dev)
+                    for k in ("open", "high", "low", "close", "source_price")]
+            return self._quality_verdict(D.bridge_quality(*cols))
         except Exception as e:
             return {"valid": False, "reason": f"Validation error: {str(e)}"}
 

@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2, "spline_ladder_factor": 1,
-    "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
+    "bridge_quality": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
 
@@ -548,6 +548,15 @@ def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor,
           "ivx_bridge_ohlcv")
     _count("bridge_ohlcv_seg" if use_seg else "bridge_ohlcv")
     return BridgeBatch(plan.out_off, row, *cols, q, m)
+
+
+def bridge_quality(o: torch.Tensor, h: torch.Tensor, l: torch.Tensor, c: torch.Tensor, src: torch.Tensor) -> int:
+    """Flag bits of _validate_ohlcv_quality (ohlcv_converter.py:371-402) over existing candles."""
+    flags = torch.zeros(1, dtype=torch.int32, device=o.device)
+    check(lib().ivx_bridge_quality(o.numel(), *(_ptr(_req(t, torch.float64, "ohlc")) for t in (o, h, l, c, src)), _ptr(flags), _stream()),
+          "ivx_bridge_quality")
+    _count("bridge_quality")
+    return int(flags.item())
 
 
 # ------------------------------------------------------------------------------------------------

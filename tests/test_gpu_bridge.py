@@ -254,3 +254,22 @@ def test_pipeline_batch_equals_the_oracle_chain(dev):
         assert st3["status"] == "success" and st3["output_candles"] == len(w3["close"]) and (got["batch_id"] == 5).all()
         n_ok += 1
     assert n_ok >= 7
+
+
+def test_bridge_quality_verdicts_on_frames(dev):
+    """_validate_ohlcv_quality on a frame (device flag reduction): the reference's reasons, first failing check first."""
+    from iv_interpolation_b200.data_bridge.ohlcv_converter import InterpolatedToOHLCVConverter
+    conv = InterpolatedToOHLCVConverter(None, None, device=dev)
+    good = pd.DataFrame({"open": [10.0, 11.0], "high": [10.5, 11.5], "low": [9.5, 10.5], "close": [10.2, 11.1], "source_price": [10.0, 11.0]})
+    assert conv._validate_ohlcv_quality(good) == {"valid": True, "reason": "All quality checks passed"}
+    cases = [({"high": [9.0, 11.5]}, "High < Low found"),
+             ({"high": [10.1, 11.5]}, "High < Open/Close found"),
+             ({"low": [10.1, 10.5]}, "Low > Open/Close found"),
+             ({"high": [12.0, 11.5], "low": [9.5, 10.5]}, "Unrealistic spreads detected"),
+             ({"open": [-1.0, 11.0], "low": [-2.0, 10.5], "source_price": [1000.0, 11.0]}, "Negative or zero prices found")]
+    for patch, reason in cases:
+        f = good.copy()
+        for k, v in patch.items():
+            f[k] = v
+        assert conv._validate_ohlcv_quality(f) == {"valid": False, "reason": reason}, (patch, conv._validate_ohlcv_quality(f))
+    assert conv._validate_ohlcv_quality(good.drop(columns=["source_price"]))["reason"].startswith("Validation error")
