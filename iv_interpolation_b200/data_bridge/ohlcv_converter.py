@@ -152,6 +152,20 @@ class InterpolatedToOHLCVConverter:
                                 "ohlcv": g["frame"]})
         return results
 
+    # -- the reference's database entries (:31-136, :420-520): out of scope, and saying so beats an AttributeError ------------
+    def _no_database(self, name: str):
+        raise NotImplementedError(f"InterpolatedToOHLCVConverter.{name} is PostgreSQL I/O in the reference (DESIGN.md section 7); "
+                                  "read the frames yourself (iv_interpolation_b200.columnar) and call convert_frames(frames)")
+
+    def get_interpolated_symbols(self, batch_id=None):
+        self._no_database("get_interpolated_symbols")
+
+    def convert_symbol_to_ohlcv(self, symbol: str, batch_id=None):
+        self._no_database("convert_symbol_to_ohlcv")
+
+    def convert_batch(self, symbols=None, batch_id=None):
+        self._no_database("convert_batch")
+
     # -- one launch for any number of frames -------------------------------------------------------------------------
     def _generate_many(self, frames: Sequence[pd.DataFrame], strategy_name: str) -> List[Dict]:
         import torch
