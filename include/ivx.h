@@ -209,6 +209,15 @@ int ivx_spline_fit_eval_ladder(int64_t n_slices, const int64_t* knot_off, const 
                                const int32_t* slice_ladder, int64_t max_knots, const double* x,
                                const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y,
                                int64_t n_q, const double* xq, int32_t extrap, double* yq, ivx_stream_t stream);
+/* The same when the caller does NOT know whether its slices share ladders: slice i brings its own abscissae
+ * x_own[knot_off[i] + j] and is only presumed to sit on ladder slice_ladder[i] (abscissae x[x_off[i] + j], length
+ * ladder_off[l+1] - ladder_off[l]).  The kernel compares the two bit for bit while staging and uses the tabulated
+ * factors only where every knot matches; every other slice takes the general solve inside the same launch. */
+int ivx_spline_fit_eval_ladder_verify(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off,
+                                      const int32_t* slice_ladder, const int64_t* ladder_off, int64_t max_knots,
+                                      const double* x, const double* x_own, const double* lu_cp, const double* lu_inv,
+                                      const double* lu_ih, const double* y, int64_t n_q, const double* xq,
+                                      int32_t extrap, double* yq, ivx_stream_t stream);
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);

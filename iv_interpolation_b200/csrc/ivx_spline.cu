@@ -155,17 +155,20 @@ struct SplLayout {
 // (k_spline_ladder_factor) and sit in lu_cp/lu_inv/lu_ih, parallel to x.  A slice with every knot usable then only
 // has its right-hand side to eliminate: d'[i] = (r[i] - h[i-1] d'[i-1]) / den[i] is an affine map per row — a prefix scan
 // of 2-vectors, no matrices, no division.  Slices with missing knots take the general path below.
-template <int G, int SPL_R, bool LADDER>
+template <int G, int SPL_R, int MODE>   // MODE 0: general; 1: slices sit on tabulated ladders; 2: presumed to — verified per slice
 __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
                                                                        const int64_t* __restrict__ x_off,
                                                                        const double* __restrict__ x,
                                                                        const double* __restrict__ lu_cp, const double* __restrict__ lu_inv,
                                                                        const double* __restrict__ lu_ih,
                                                                        const int32_t* __restrict__ slice_ladder,
+                                                                       const double* __restrict__ x_own,
+                                                                       const int64_t* __restrict__ ladder_off,
                                                                        const double* __restrict__ y,
                                                                        int n_q, const double* __restrict__ xq, int extrap,
                                                                        double* __restrict__ yq) {
   using L = SplLayout<G, SPL_R>;
+  constexpr bool LADDER = MODE != 0;
   auto spl_pad = [](int i) { return spl_pad_t<SPL_R>(i); };
   extern __shared__ __align__(16) double smem[];
   const int grp = threadIdx.x / G, g = threadIdx.x % G;
@@ -187,6 +190,10 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   // ---- stage the slice (coalesced), NaN beyond its end ------------------------------------------------
   // All of a thread's loads are issued before the first one is used (clamped addresses, no branch around them): one
   // round trip to HBM per slice instead of one per row of the loop.
+  // VERIFY mode (LADDER with x_own): the slice brings its own abscissae and is only PRESUMED to sit on ladder
+  // slice_ladder[sl]; its x is compared with the ladder's (L2-resident) bit for bit, and the tabulated factors are used
+  // only when every knot matches — a caller that does not know whether its slices share ladders loses nothing.
+  constexpr bool verify = MODE == 2;
   bool fin = true;
   {
     double xl[SPL_R + 1], yl[SPL_R + 1];
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
 #pragma unroll
       for (int r = 0; r < SPL_R + 1; ++r) {
         const int jc = min(r * G + g, m - 1);
-        xl[r] = x_off ? __ldg(x + xk0 + jc) : ld_stream(x + xk0 + jc);
+        xl[r] = verify ? ld_stream(x_own + k0 + jc) : (x_off ? __ldg(x + xk0 + jc) : ld_stream(x + xk0 + jc));
         yl[r] = ld_stream(y + k0 + jc);
       }
     }
@@ -211,10 +218,30 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
       }
     }
   }
+  // VERIFY: the ladder's abscissae are requested before the barrier (the staging registers are free by now), so their L2
+  // round trip overlaps with the wait for the other warps' staging
+  double xd[SPL_R + 1];
+  int64_t llen = 0;
+  if (verify && G >= 256 && m > 0) {                       // group-uniform
+    const int lad = slice_ladder[sl];
+    llen = ladder_off[lad + 1] - ladder_off[lad];
+#pragma unroll
+    for (int r = 0; r < SPL_R + 1; ++r) xd[r] = __ldg(x + xk0 + min((int64_t)min(r * G + g, m - 1), llen - 1));
+  }
   // a slice with every knot usable (the common case) is known at the barrier itself when the group is the whole CTA
   bool clean = false;
   if (G >= 256) clean = __syncthreads_and(fin) != 0;
   else group_sync<G>(grp);
+  bool on_ladder = LADDER && !verify;                      // told so by the caller ...
+  if (verify && G >= 256 && clean) {                       // ... or found out (group-uniform branch)
+    bool same = (int64_t)m <= llen;
+#pragma unroll
+    for (int r = 0; r < SPL_R + 1; ++r) {
+      const int j = r * G + g;
+      if (j < m) same = same && (xd[r] == xs[spl_pad(j)]);
+    }
+    on_ladder = __syncthreads_and(same) != 0;
+  }
 
   // ---- squeeze out unusable knots if there are any (chunks of SPL_R knots per thread, stable) ------------------------
   const int i0 = g * SPL_R;
@@ -272,7 +299,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   // the elimination only flows forward, so they cannot reach a valid row, and no per-row test is left in the loops.
   double cv[SPL_R], dv[SPL_R];
   const int nvalid = min(max(n - 2 - i0, 0), SPL_R);      // rows i0+1 .. i0+nvalid are equations
-  if (LADDER && n == m) {
+  if (LADDER && n == m && on_ladder) {
     // ---- shared-ladder path: slopes through the tabulated 1/h, right-hand side as affine maps of d' ------------------
     // tables are stored the way they are read: row i = R g + 1 + j of ladder l sits at l CAP + j G + g, so that the 32
     // lanes of a warp read 32 consecutive doubles; ih at row i is 1 / (x[i] - x[i-1])
@@ -637,19 +664,20 @@ using namespace ivx;
 
 extern "C" int64_t ivx_spline_workspace_bytes(int64_t, int64_t) { return 256; }
 
-template <int G, int SPL_R, bool LADDER>
+template <int G, int SPL_R, int MODE>
 static int launch_spline_t(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const double* x, const double* lu_cp,
-                           const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder, const double* y, int n_q,
+                           const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder, const double* x_own,
+                           const int64_t* ladder_off, const double* y, int n_q,
                          const double* xq, int extrap, double* yq, cudaStream_t stream) {
   using L = SplLayout<G, SPL_R>;
   static bool attr_set = false;
   if (!attr_set) {
-    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R, LADDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     attr_set = true;
   }
   const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
   IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
-  k_spline_fit_eval<G, SPL_R, LADDER><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, y, n_q, xq, extrap, yq);
+  k_spline_fit_eval<G, SPL_R, MODE><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y, n_q, xq, extrap, yq);
   IVX_LAUNCH_CHECK("k_spline_fit_eval");
   return IVX_OK;
 }
@@ -703,7 +731,7 @@ __global__ void __launch_bounds__(256) k_spline_ladder_factor(int64_t n_ladders,
 
 static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots, const double* x,
                            const double* lu_cp, const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder,
-                           const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq, cudaStream_t stream) {
+                           const double* x_own, const int64_t* ladder_off, const double* y, int64_t n_q, const double* xq, int32_t extrap, double* yq, cudaStream_t stream) {
   IVX_REQUIRE(n_slices >= 0 && max_knots >= 0 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval: extrap must be 0, 1 or 2");
   if (n_slices == 0 || n_q == 0) return IVX_OK;
@@ -713,8 +741,9 @@ static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int6
   const int nq = (int)n_q;
   const bool ladder = lu_cp != nullptr;
 #define IVX_SPL(G, R)                                                                                                                        \
-  return ladder ? launch_spline_t<G, R, true>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, y, nq, xq, extrap, yq, stream) \
-                : launch_spline_t<G, R, false>(n_slices, knot_off, x_off, x, nullptr, nullptr, nullptr, nullptr, y, nq, xq, extrap, yq, stream)
+  return !ladder ? launch_spline_t<G, R, 0>(n_slices, knot_off, x_off, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, y, nq, xq, extrap, yq, stream) \
+         : x_own ? launch_spline_t<G, R, 2>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y, nq, xq, extrap, yq, stream) \
+                 : launch_spline_t<G, R, 1>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, nullptr, nullptr, y, nq, xq, extrap, yq, stream)
   switch (spline_group_width(max_knots)) {
     case 32: IVX_SPL(32, 8);
     case 64: IVX_SPL(64, 8);
@@ -729,7 +758,7 @@ static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int6
 extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,
                                         const double* x, const double* y, int64_t n_q, const double* xq, int32_t extrap,
                                         double* yq, ivx_stream_t stream_) {
-  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, nullptr, nullptr, nullptr, nullptr, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
+  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
 }
 
 extern "C" int64_t ivx_spline_ladder_table_len(int64_t n_ladders, int64_t max_knots) {
@@ -759,7 +788,16 @@ extern "C" int ivx_spline_fit_eval_ladder(int64_t n_slices, const int64_t* knot_
                                           const double* lu_ih, const double* y, int64_t n_q, const double* xq, int32_t extrap,
                                           double* yq, ivx_stream_t stream_) {
   IVX_REQUIRE(x_off && slice_ladder && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_ladder: x_off, slice_ladder and the three factor tables are required");
-  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, lu_cp, lu_inv, lu_ih, slice_ladder, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
+  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, lu_cp, lu_inv, lu_ih, slice_ladder, nullptr, nullptr, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
+}
+
+extern "C" int ivx_spline_fit_eval_ladder_verify(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const int32_t* slice_ladder,
+                                                 const int64_t* ladder_off, int64_t max_knots, const double* x, const double* x_own,
+                                                 const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y,
+                                                 int64_t n_q, const double* xq, int32_t extrap, double* yq, ivx_stream_t stream_) {
+  IVX_REQUIRE(x_off && slice_ladder && ladder_off && x_own && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG,
+              "ivx_spline_fit_eval_ladder_verify: x_off, slice_ladder, ladder_off, x_own and the three factor tables are required");
+  return spline_dispatch(n_slices, knot_off, x_off, max_knots, x, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y, n_q, xq, extrap, yq, (cudaStream_t)stream_);
 }
 
 extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots, const double* x,

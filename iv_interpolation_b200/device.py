@@ -379,10 +379,13 @@ def bs_greeks(S, K, T, r, sigma, is_call, reference_put_rho_sign: bool = True) -
 def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, *,
                     max_knots: int, extrap: int = 1, out: Optional[torch.Tensor] = None,
                     workspace: Optional[torch.Tensor] = None, x_off: Optional[torch.Tensor] = None,
-                    lu: Optional[Sequence[torch.Tensor]] = None, slice_ladder: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    lu: Optional[Sequence[torch.Tensor]] = None, slice_ladder: Optional[torch.Tensor] = None,
+                    x_own: Optional[torch.Tensor] = None, ladder_off: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Natural cubic spline per slice, evaluated on the shared grid ``xq``.  ``x_off`` (one int64 per slice) reads the
     abscissae from shared ladders; ``lu`` = the three factor arrays of ``spline_ladder_factor`` additionally lets
-    slices without missing knots skip the x-only half of the elimination."""
+    slices without missing knots skip the x-only half of the elimination.  With ``x_own`` (+ ``ladder_off``) the slices
+    bring their own abscissae and are only presumed to sit on their ladders: the kernel checks, bit for bit, and falls
+    back to the general solve per slice."""
     n_slices = knot_off.numel() - 1
     n_q = xq.numel()
     _req(knot_off, torch.int64, "knot_off")
@@ -402,6 +405,16 @@ def spline_fit_eval(knot_off: torch.Tensor, x: torch.Tensor, y: torch.Tensor, xq
         if x_off is None or slice_ladder is None or len(lu) != 3 or any(t.dtype != torch.float64 for t in lu):
             raise _lib.IvxError("spline_fit_eval: lu needs x_off, slice_ladder and the three float64 tables of spline_ladder_factor")
         _req(slice_ladder, torch.int32, "slice_ladder")
+        if x_own is not None:
+            if ladder_off is None or x_own.numel() != y.numel():
+                raise _lib.IvxError("spline_fit_eval: x_own needs ladder_off and one abscissa per knot")
+            check(lib().ivx_spline_fit_eval_ladder_verify(n_slices, _ptr(knot_off), _ptr(x_off), _ptr(slice_ladder),
+                                                          _ptr(_req(ladder_off, torch.int64, "ladder_off")), int(max_knots), _ptr(x),
+                                                          _ptr(_req(x_own, torch.float64, "x_own")), _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]),
+                                                          _ptr(y), n_q, _ptr(xq), int(extrap), _ptr(yq), _stream()),
+                  "ivx_spline_fit_eval_ladder_verify")
+            _count("spline_fit_eval")
+            return yq
         check(lib().ivx_spline_fit_eval_ladder(n_slices, _ptr(knot_off), _ptr(x_off), _ptr(slice_ladder), int(max_knots), _ptr(x),
                                                _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q, _ptr(xq), int(extrap),
                                                _ptr(yq), _stream()), "ivx_spline_fit_eval_ladder")

@@ -138,6 +138,8 @@ class SurfacePipeline:
         self._x_off = None
         self._chain_ws = None
         self._lu_key = None
+        self._q_lu = None
+        self._q_lu_key = None
 
     def plan_buckets(self, ts: torch.Tensor):
         """Bucket boundaries of the day's stamps (one tiny kernel + an 8-byte read-back, done once per tape)."""
@@ -187,7 +189,23 @@ class SurfacePipeline:
             D.spline_fit_eval(self.knot_off, q.K_ek, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
                               out=self.smile, x_off=self._x_off, lu=self._lu, slice_ladder=self._slice_ladder)
         else:
-            D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile)
+            # per-quote strikes: a chain's strike ladders normally do not change during the day, but nothing says so here.
+            # The first stamp's ladders are factored (30 small launches' worth of work) and every slice is PRESUMED to
+            # sit on its expiry's; the kernel verifies that bit for bit while staging and solves the others in full.
+            if self._q_lu is None:
+                from ._lib import lib
+                n_tab = lib().ivx_spline_ladder_table_len(sp.n_exp, sp.n_strike)
+                self._q_lu = [torch.zeros(n_tab, dtype=torch.float64, device=self.device) for _ in range(3)]
+                self._q_x_off = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp) * sp.n_strike
+                self._q_ladder_off = torch.arange(sp.n_exp + 1, dtype=torch.int64, device=self.device) * sp.n_strike
+                self._q_slice_ladder = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp).to(torch.int32)
+            key = (q.K.data_ptr(), q.K._version)             # tables follow the column: refactored whenever it is written
+            if self._q_lu_key != key:
+                D.spline_ladder_factor(self._q_ladder_off, q.K, max_knots=sp.n_strike, out=self._q_lu)
+                self._q_lu_key = key
+            D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile,
+                              x_off=self._q_x_off, lu=self._q_lu, slice_ladder=self._q_slice_ladder, x_own=q.K,
+                              ladder_off=self._q_ladder_off)
         mark("spline_strike", 1)
         mark("spline_maturity", 0)
         # plane t: n_grid_k systems with n_exp knots at x = T[t][e], read in place

@@ -604,3 +604,47 @@ def test_spline_shared_ladder_path(dev, n_knots, n_ladders, per_ladder):
         assert np.abs(got[s] - ref[s]).max() <= 1e-10 * scale, f"slice {s}: ladder vs general path"
     # the two paths round differently: identical bits on a complete slice would mean the table path was not taken
     assert np.abs(got[4] - ref[4]).max() > 0 and _eq(got[2], ref[2])
+
+
+def test_spline_ladder_verify_mode(dev):
+    """Slices that bring their own abscissae and are only PRESUMED to sit on a ladder: those that do take the tabulated
+    path, those that differ in one knot (or are longer / shorter than the ladder, or hold a NaN) take the general solve —
+    every slice must equal the general kernel's result to rounding, and the matching ones the ladder kernel's."""
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(31)
+    nk, n_lad, per = 2000, 3, 6
+    ladders = [4500.0 * (0.5 + np.cumsum(rng.uniform(0.2, 1.8, nk)) / nk) for _ in range(n_lad)]
+    lx = np.concatenate(ladders)
+    ladder_off = (np.arange(n_lad + 1) * nk).astype(np.int64)
+    xs, ys, lens, lad_of = [], [], [], []
+    for s in range(n_lad * per):
+        l = s % n_lad
+        x = ladders[l].copy()
+        kind = s // n_lad
+        if kind == 1:
+            x[777] = np.nextafter(x[777], np.inf)           # one knot off by an ulp
+        elif kind == 2:
+            x = x[:1500]                                     # a prefix of the ladder: still on it
+        elif kind == 3:
+            x = np.r_[x, x[-1] + 1.0][:nk]                   # same length, nothing changed
+        m = np.log(x / 4500.0)
+        y = 0.2 + 0.35 * m * m - 0.08 * m + 0.003 * rng.standard_normal(len(x))
+        if kind == 4:
+            y[100] = np.nan                                  # a missing quote: squeezed, general path
+        xs.append(x); ys.append(y); lens.append(len(x)); lad_of.append(l)
+    off = np.r_[0, np.cumsum(lens)].astype(np.int64)
+    X, Y = np.concatenate(xs), np.concatenate(ys)
+    xq = 4500.0 * np.linspace(0.55, 1.45, 512)
+    lu = D.spline_ladder_factor(_t(ladder_off, dev), _t(lx, dev), max_knots=nk)
+    x_off = _t(ladder_off[:-1][np.asarray(lad_of)], dev)
+    got = D.spline_fit_eval(_t(off, dev), _t(lx, dev), _t(Y, dev), _t(xq, dev), max_knots=nk, extrap=1, x_off=x_off, lu=lu,
+                            slice_ladder=_t(np.asarray(lad_of, np.int32), dev), x_own=_t(X, dev), ladder_off=_t(ladder_off, dev))
+    got = got.cpu().numpy().reshape(len(lens), -1)
+    gen = D.spline_fit_eval(_t(off, dev), _t(X, dev), _t(Y, dev), _t(xq, dev), max_knots=nk, extrap=1).cpu().numpy().reshape(len(lens), -1)
+    for i in range(len(lens)):
+        want = O.natural_spline_eval(xs[i], ys[i], xq, 1)
+        assert np.abs(got[i] - want).max() <= 1e-8 and np.abs(got[i] - gen[i]).max() <= 1e-9, i
+    # slices that differ from the ladder must be EXACTLY the general kernel's (same code path), matching ones generally not
+    for i in range(len(lens)):
+        if i // n_lad in (1, 4):
+            assert np.array_equal(got[i], gen[i]), i
