@@ -189,13 +189,14 @@ class PipelineBatch:
         except Exception as e:                                                        # :470-471
             gen, err = [], str(e)
         minute: Dict[str, pd.DataFrame] = {}
+        have_pos = {s: i for i, s in enumerate(have)}
         for s in syms:
             if s not in interp:
                 st2.append({"symbol": s, "status": "skipped", "reason": "No interpolated data"})              # :451-452
             elif err is not None:
                 st2.append({"symbol": s, "status": "error", "error": err})
             else:
-                f = gen[have.index(s)]["frame"]
+                f = gen[have_pos[s]]["frame"]
                 if f is None or f.empty:
                     st2.append({"symbol": s, "status": "error", "error": "OHLCV generation failed"})          # :456-457
                 else:
@@ -212,6 +213,7 @@ class PipelineBatch:
         except Exception as e:
             res, err = [], str(e)
         candles: Dict[str, pd.DataFrame] = {}
+        todo_pos = {s: i for i, s in enumerate(todo)}
         for s in syms:
             if s not in minute:
                 st3.append({"symbol": s, "status": "skipped", "reason": "No minute candles found"})           # :657-658
@@ -220,7 +222,7 @@ class PipelineBatch:
             elif err is not None:
                 st3.append({"symbol": s, "status": "error", "error": err})                                     # :683-684
             else:
-                r = res[todo.index(s)]
+                r = res[todo_pos[s]]
                 if r is None or r.empty:
                     st3.append({"symbol": s, "status": "error", "error": "Reconstruction failed"})            # :665-666
                 else:
