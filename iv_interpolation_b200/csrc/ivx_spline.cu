@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
     const int lad = slice_ladder[sl];
     llen = ladder_off[lad + 1] - ladder_off[lad];
 #pragma unroll
-    for (int r = 0; r < SPL_R + 1; ++r) xd[r] = __ldg(x + xk0 + min((int64_t)min(r * G + g, m - 1), llen - 1));
+    for (int r = 0; r < SPL_R + 1; ++r) xd[r] = __ldg(x + xk0 + max((int64_t)0, min((int64_t)min(r * G + g, m - 1), llen - 1)));
   }
   // a slice with every knot usable (the common case) is known at the barrier itself when the group is the whole CTA
   bool clean = false;
