@@ -107,6 +107,30 @@ def test_surface_pipeline_full_width_slices(dev):
     _stagewise_check(spec, chain, res)
 
 
+def test_surface_pipeline_moving_ladders(dev):
+    """Per-quote layout at full width when the strike ladders are NOT the same at every stamp: the spline presumes the first
+    stamp's ladders and verifies per slice; stamps whose strikes moved (even by one ulp in one knot) must take the general
+    solve and still pass the oracle; a rewritten K column refactors the tables."""
+    from iv_interpolation_b200 import device as D, surface as SF
+    spec, chain = _chain(dev, seed=12, n_t=8, n_exp=30, n_strike=2000, nk=512, nm=64, drop=0.0, min_count=1)
+    per_t = spec.n_exp * spec.n_strike
+    K = chain.K.clone()
+    K[2 * per_t:3 * per_t] *= 1.001                                            # a whole stamp on other strikes
+    K[5 * per_t + 777] = torch.nextafter(K[5 * per_t + 777], K.new_tensor(float("inf")))   # one knot, one ulp
+    chain.K = K
+    chain.price = D.bs_price(chain.S, chain.K, chain.T, chain.r, chain.sigma_true, chain.is_call)
+    pipe = SF.SurfacePipeline(spec, dev)
+    res = pipe.run(chain)
+    _stagewise_check(spec, chain, res)
+    # the same pipeline object, the K column rewritten in place: stale tables would be wrong for the slices that now match
+    first_smile = res.smile.clone()
+    chain.K.mul_(1.0005)
+    chain.price.copy_(D.bs_price(chain.S, chain.K, chain.T, chain.r, chain.sigma_true, chain.is_call))
+    res2 = pipe.run(chain)
+    _stagewise_check(spec, chain, res2)
+    assert not _eq(first_smile.cpu().numpy(), res2.smile.cpu().numpy())
+
+
 def test_host_stream_equals_resident_pipeline(dev):
     """The host-facing entry (pinned host columns in, host candles out, double-buffered chunks) gives the same
     bits as the resident pipeline over the whole tape."""
