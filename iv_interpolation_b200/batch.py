@@ -235,3 +235,80 @@ class PipelineBatch:
         stages = {"interpolation": (st1, sum1), "bridge": (st2, _summary(self.batch_id, st2, t0)),
                   "reconstruction": (st3, _summary(self.batch_id, st3, t0))}
         return candles, minute, interp, stages
+
+
+class ProductionInterpolationBatch(InterpolationBatch):
+    """``ProductionBatchProcessor._process_single_symbol`` for every symbol of a batch (reference
+    src/interpolation/optimized_batch_processor.py:267-331): symbols with more than ``streaming_threshold`` (10 000) rows
+    are read ``fetch_size`` (5 000) rows at a time in date order and EVERY CHUNK IS INTERPOLATED ON ITS OWN (:333-360) — no
+    interpolation across chunk boundaries, the guards of ``interpolate_symbol`` apply per chunk.  Small symbols and the
+    chunks of large ones all go through one launch.
+
+    The reference then evaluates ``len(interpolated_data)`` on the integer its streaming helper returned (:319), which
+    raises, so after saving every chunk it reports the symbol as ``'error'``.  Here the symbol is reported as a success
+    with the summed row count; ``mirror_reference_status=True`` reproduces the reference's status dictionary instead."""
+
+    def __init__(self, streaming_threshold: int = 10_000, fetch_size: int = 5_000, mirror_reference_status: bool = False, **kw):
+        super().__init__(**kw)
+        self.streaming_threshold = streaming_threshold
+        self.fetch_size = fetch_size
+        self.mirror_reference_status = mirror_reference_status
+
+    def run(self, frames: Mapping[str, pd.DataFrame]) -> Tuple[Dict[str, pd.DataFrame], List[dict], dict]:
+        t0 = time.time()
+        pieces: List[pd.DataFrame] = []
+        owner: List[Tuple[str, bool]] = []
+        for sym, f in frames.items():
+            if f is None or f.empty:
+                continue
+            if len(f) > self.streaming_threshold:                                # :290-291
+                g = f.sort_values("date", kind="stable") if "date" in f.columns else f   # the SQL's ORDER BY date
+                for a in range(0, len(g), self.fetch_size):
+                    pieces.append(g.iloc[a:a + self.fetch_size])
+                    owner.append((sym, True))
+            else:
+                pieces.append(f)
+                owner.append((sym, False))
+        try:
+            results = self.interpolator.interpolate_batch(pieces) if pieces else []
+            err = None
+        except Exception as e:
+            results, err = [None] * len(pieces), str(e)
+        elapsed = time.time() - t0
+        chunks: Dict[str, List[pd.DataFrame]] = {}
+        small: Dict[str, Optional[pd.DataFrame]] = {}
+        for (sym, streamed), res in zip(owner, results):
+            if res is not None:
+                res["batch_id"] = self.batch_id                                   # :312 / :352
+            if streamed:
+                chunks.setdefault(sym, [])
+                if res is not None:
+                    chunks[sym].append(res)
+            else:
+                small[sym] = res
+        outs: Dict[str, pd.DataFrame] = {}
+        statuses: List[dict] = []
+        for sym, f in frames.items():
+            n_in = 0 if f is None else len(f)
+            if n_in == 0:
+                statuses.append({"symbol": sym, "status": "skipped", "reason": "No data found"})                 # :286-287
+            elif err is not None:
+                statuses.append({"symbol": sym, "status": "error", "error": err, "processing_time": elapsed})      # :324-331
+            elif sym in chunks:
+                parts = chunks[sym]
+                if parts:
+                    outs[sym] = pd.concat(parts, ignore_index=True)
+                total = sum(len(p) for p in parts)
+                if self.mirror_reference_status:
+                    statuses.append({"symbol": sym, "status": "error", "error": "object of type 'int' has no len()",
+                                     "processing_time": elapsed})
+                else:
+                    statuses.append({"symbol": sym, "status": "success", "input_rows": n_in, "output_rows": total,
+                                     "processing_time": elapsed / max(1, len(frames))})
+            elif small.get(sym) is None:
+                statuses.append({"symbol": sym, "status": "skipped", "reason": "Interpolation failed"})           # :307-308
+            else:
+                outs[sym] = small[sym]
+                statuses.append({"symbol": sym, "status": "success", "input_rows": n_in, "output_rows": len(small[sym]),
+                                 "processing_time": elapsed / max(1, len(frames))})
+        return outs, statuses, _summary(self.batch_id, statuses, t0)

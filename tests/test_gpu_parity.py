@@ -5,6 +5,7 @@ import json
 import logging
 
 import numpy as np
+import pandas as pd
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -648,3 +649,38 @@ def test_spline_ladder_verify_mode(dev):
     for i in range(len(lens)):
         if i // n_lad in (1, 4):
             assert np.array_equal(got[i], gen[i]), i
+
+
+def test_production_batch_streams_large_symbols_in_chunks(dev):
+    """optimized_batch_processor.py:267-360: symbols above 10 000 rows are interpolated 5 000 rows at a time, every chunk on
+    its own; smaller ones whole.  One launch for all pieces; each piece equals the oracle class on that piece."""
+    from iv_interpolation_b200.batch import ProductionInterpolationBatch
+    from oracle.df_oracle import OracleIVInterpolator
+    big = tapes.make_contract_tape(71, 2, rows_per_contract=12_345, spacing_us=2 * tapes.MINUTE_US, nan_frac=0.05, offgrid_frac=0.01)
+    small = tapes.make_contract_tape(72, 3, rows_per_contract=300)
+    frames = {f"big{i}": big.frame(i) for i in range(2)}
+    frames.update({f"small{i}": small.frame(i) for i in range(3)})
+    frames["tiny"] = small.frame(0).iloc[:3]
+    frames["none"] = small.frame(0).iloc[:0]
+    outs, statuses, summary = ProductionInterpolationBatch(batch_id=9).run(frames)
+    ref = OracleIVInterpolator()
+    by = {s["symbol"]: s for s in statuses}
+    assert by["none"] == {"symbol": "none", "status": "skipped", "reason": "No data found"}
+    assert by["tiny"]["status"] == "skipped" and by["tiny"]["reason"] == "Interpolation failed"
+    for i in range(3):
+        w = ref.interpolate_symbol(frames[f"small{i}"])
+        golden_io.assert_frames_match(w, outs[f"small{i}"].drop(columns=["batch_id"]))
+        assert by[f"small{i}"]["output_rows"] == len(w)
+    for i in range(2):
+        f = frames[f"big{i}"]
+        parts = [ref.interpolate_symbol(f.iloc[a:a + 5000]) for a in range(0, len(f), 5000)]
+        parts = [p for p in parts if p is not None]
+        want = pd.concat(parts, ignore_index=True)
+        got = outs[f"big{i}"].drop(columns=["batch_id"])
+        assert len(got) == len(want) == by[f"big{i}"]["output_rows"] and by[f"big{i}"]["input_rows"] == 12_345
+        golden_io.assert_frames_match(want, got)
+        # chunks are not stitched: the gap between two chunks (one 2-minute step) is NOT filled with a minute row
+        assert len(want) < (12_345 - 1) * 2 + 1
+    assert summary["success_count"] == 5 and summary["skip_count"] == 2
+    mirrored = ProductionInterpolationBatch(batch_id=9, mirror_reference_status=True).run({"big0": frames["big0"]})[1][0]
+    assert mirrored["status"] == "error" and "has no len()" in mirrored["error"]
