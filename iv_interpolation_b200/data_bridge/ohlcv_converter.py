@@ -73,7 +73,9 @@ class InterpolatedToOHLCVConverter:
         self.conversion_strategy = getattr(bridge, "conversion_strategy", "spread_simulation")      # :26
         self.spread_method = getattr(bridge, "spread_method", "adaptive")
         self.quality_checks = getattr(bridge, "enable_quality_checks", True)
-        self._spread_parameters = getattr(bridge, "spread_parameters", None) or {}
+        # without a config: the reference's defaults (config.py:69-75); with one: whatever it holds — a None there makes the
+        # reference's spread strategy fail on ``None.get`` (:210) and return None, and so does this class
+        self._spread_parameters = {} if bridge is None else getattr(bridge, "spread_parameters", None)
         self._rng = rng
         self._device = device
 
@@ -166,6 +168,12 @@ class InterpolatedToOHLCVConverter:
     def convert_batch(self, symbols=None, batch_id=None):
         self._no_database("convert_batch")
 
+    def _spread_kwargs(self, strategy: str) -> Dict:
+        if strategy != "spread_simulation":
+            return {}
+        cfg = self._spread_parameters                       # reference :207-211; raises on None like the reference does
+        return {"base_spread_percent": cfg.get("base_spread_percent", 0.002), "volatility_factor": cfg.get("volatility_factor", 1.5)}
+
     # -- one launch for any number of frames -------------------------------------------------------------------------
     def _generate_many(self, frames: Sequence[pd.DataFrame], strategy_name: str) -> List[Dict]:
         import torch
@@ -204,8 +212,7 @@ class InterpolatedToOHLCVConverter:
         if plan.total != int(ok.sum()) or plan.total_e != int(need.sum()):
             raise RuntimeError("bridge plan disagrees with the host's row classification")
         res = D.bridge_ohlcv(d_off, d_base, d_vol, plan, strategy, u=t(u) if len(u) else None, e=t(e), z=t(z) if len(z) else None,
-                             base_spread_percent=self._spread_parameters.get("base_spread_percent", 0.002),      # :210-211
-                             volatility_factor=self._spread_parameters.get("volatility_factor", 1.5))
+                             **self._spread_kwargs(strategy))
         out_off = res.out_off.cpu().numpy()
         row = res.row.cpu().numpy()
         cols = {k: getattr(res, k).cpu().numpy() for k in ("open", "high", "low", "close", "volume", "source_price")}

@@ -177,9 +177,18 @@ def test_bridge_convert_frames_status_dicts(dev, golden_bridge):
     import types
     from iv_interpolation_b200.data_bridge.ohlcv_converter import InterpolatedToOHLCVConverter
     cfg = types.SimpleNamespace(data_bridge=types.SimpleNamespace(conversion_strategy="spread_simulation", spread_method="adaptive",
-                                                                  enable_quality_checks=True, spread_parameters=None))
+                                                                  enable_quality_checks=True,
+                                                                  spread_parameters={"base_spread_percent": 0.002, "volatility_factor": 1.5}))
     conv = InterpolatedToOHLCVConverter(None, cfg, rng=np.random.RandomState(3), device=dev)
     good = _frame(golden_bridge, "case1")
+    # a config whose spread_parameters is None makes the reference's spread strategy fail on None.get (:210) -> None
+    broken = types.SimpleNamespace(data_bridge=types.SimpleNamespace(conversion_strategy="spread_simulation", spread_method="adaptive",
+                                                                     enable_quality_checks=True, spread_parameters=None))
+    logging.disable(logging.CRITICAL)
+    try:
+        assert InterpolatedToOHLCVConverter(None, broken, device=dev)._generate_ohlcv_from_interpolated(good) is None
+    finally:
+        logging.disable(logging.NOTSET)
     dead = good.copy()
     dead["underlying_price"] = np.nan
     dead["mark_price"] = np.nan
