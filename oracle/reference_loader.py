@@ -1,9 +1,10 @@
-"""Import the reference's own hot-path classes from /root/reference.  TEST INFRASTRUCTURE ONLY.
+"""Import the reference's own hot-path classes.  TEST INFRASTRUCTURE ONLY.
 
-Used by ``oracle/make_golden.py`` (golden-vector generation) and by the container-only
-cross-checks in ``tests/test_oracle_vs_reference.py`` (skipped where /root/reference is
-absent, i.e. on the GPU box).  Nothing here is copied from the reference: the modules are
-imported from where they lie.
+Root, in this order: ``$IVX_REFERENCE_ROOT``; ``/root/reference`` (the build container — the modules are imported
+from where they lie); ``oracle/_ref`` (the byte-for-byte copy ``oracle/make_ref.py`` makes of the path's four files:
+git-ignored, it travels to the GPU box with the snapshot, so the reference's classes can be timed and cross-checked
+there too).  Used by ``oracle/make_golden*.py`` (golden-vector generation), ``tests/test_oracle_vs_reference.py`` and
+the CPU legs of ``bench.py`` (``cpu_baseline.kind: "reference"``).
 
 Task 1 needs a shim in this image: reference src/interpolation/core.py:68 calls
 ``Series.fillna(method='ffill')``, an argument pandas 3 removed; the resulting TypeError is
@@ -18,11 +19,31 @@ import logging
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("IVX_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_COPY = os.path.join(_HERE, "_ref")
+
+
+def _has_path(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "src", "interpolation", "core.py"))
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("IVX_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if _has_path("/root/reference") else _REF_COPY
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "interpolation", "core.py"))
+    return _has_path(REFERENCE_ROOT)
+
+
+def where() -> str:
+    """'reference' = imported from /root/reference where it lies; '_ref' = the untouched copy under oracle/_ref."""
+    return "_ref" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_REF_COPY) else "reference"
 
 
 @contextlib.contextmanager
@@ -51,7 +72,7 @@ def _import(modname: str):
     src = os.path.join(REFERENCE_ROOT, "src")
     if src not in sys.path:
         sys.path.insert(0, src)
-    for name in ("interpolation", "candle_reconstruction"):
+    for name in ("interpolation", "candle_reconstruction", "data_bridge"):
         mod = sys.modules.get(name)
         if mod is not None and not str(getattr(mod, "__file__", "") or getattr(mod, "__path__", [""])[0]).startswith(REFERENCE_ROOT):
             raise RuntimeError(f"{name} already imported from elsewhere: {mod}")
@@ -61,6 +82,7 @@ def _import(modname: str):
 def quiet():
     logging.getLogger("interpolation.core").setLevel(logging.CRITICAL)
     logging.getLogger("candle_reconstruction.core").setLevel(logging.CRITICAL)
+    logging.getLogger("data_bridge.ohlcv_converter").setLevel(logging.CRITICAL)
 
 
 def load_interpolator_cls():
@@ -87,3 +109,17 @@ def reference_interpolate(df, method: str = "linear", min_points: int = 10):
 def reference_reconstruct(df, target_frequency: str = "5min"):
     cls = load_reconstructor_cls()
     return cls(target_frequency).reconstruct_symbol_candles(df)
+
+
+def load_converter_cls():
+    quiet()
+    return _import("data_bridge.ohlcv_converter").InterpolatedToOHLCVConverter
+
+
+def reference_converter(strategy: str = "spread_simulation", params=None):
+    """InterpolatedToOHLCVConverter(None, config) with the reference's default bridge configuration (config.py:57-75)."""
+    import types
+    cfg = types.SimpleNamespace(data_bridge=types.SimpleNamespace(
+        conversion_strategy=strategy, spread_method="adaptive", enable_quality_checks=True,
+        spread_parameters=params if params is not None else {"base_spread_percent": 0.002, "volatility_factor": 1.5}))
+    return load_converter_cls()(None, cfg)

@@ -1,6 +1,6 @@
-"""Randomised cross-check of the oracle restatements against the reference's OWN classes, imported from /root/reference.
-Runs in the build container only (the GPU box has no /root/reference: skipped there) — the committed goldens of
-tests/golden/ are the portable pin, this is the wide one: several hundred random frames per kernel, bit for bit."""
+"""Randomised cross-check of the oracle restatements against the reference's OWN classes, imported from /root/reference
+(build container) or from its untouched copy oracle/_ref (oracle/make_ref.py; travels to the GPU box).  The committed
+goldens of tests/golden/ are the portable pin, this is the wide one: several hundred random frames per kernel, bit for bit."""
 import logging
 import sys
 import types
@@ -12,7 +12,7 @@ import pytest
 from oracle import bridge_oracle as B, golden_io, reference_loader as RL
 from oracle.df_oracle import OracleCandleReconstructor, OracleIVInterpolator
 
-pytestmark = pytest.mark.skipif(not RL.available(), reason="/root/reference is not present (GPU box)")
+pytestmark = pytest.mark.skipif(not RL.available(), reason="neither /root/reference nor oracle/_ref is present")
 
 
 def _interp_frame(rng, n):
