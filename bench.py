@@ -16,6 +16,13 @@ timed region.  `e2e` streams the same day from pinned host memory, chunk by chun
 back.  `roofline` is kernel C's (the dominant kernel), from CUDA events around it in the timed steps.
 `kernels` adds the same figures for every stage and for the two reference-pinned kernels (A: time-linear
 interpolation + ffill; B: OHLCV bucket reduce) on a config-3-shaped tape.  One JSON line on stdout.
+
+`--workload contracts` (and the `contracts` object of the default line) is the path the reference really has, on
+BASELINE.json configs[2]: 100 underlyings x ~1200 contracts x 481 hourly rows (20 days), dealt to the N ranks by
+underlying (LPT), every rank Task 1 -> data bridge -> Task 2 on its shard, the 5-minute candle tables gathered on
+rank 0 over NCCL — ONE fixed tape whatever N (strong scaling).  Its CPU arm runs the reference's OWN classes
+(oracle/_ref, copied untouched by oracle/make_ref.py) on one core and on a ProcessPoolExecutor of all cores, the
+way reference src/interpolation/batch_processor.py:234-239 fans contracts out.
 """
 from __future__ import annotations
 
@@ -38,6 +45,11 @@ N_EXP, N_STRIKE, N_T_DAY = 30, 2000, 23_400
 N_GRID_K, N_GRID_M = 512, 64
 BYTES_PER_QUOTE = 49                      # 5 x f64 + u8 read, f64 written
 CHUNK_T = 120                             # e2e: stamps per host chunk (two 1-minute buckets)
+# contracts workload (BASELINE.json configs[2])
+CT_METRIC = "interpolated_points_per_sec_full_path"
+CT_UNIT = "minute-rows/s"
+CT_UNDERLYINGS, CT_ROWS, CT_SEED = 100, 481, 1000
+CT_OUT_ROWS = (CT_ROWS - 1) * 60 + 1       # 28 801 minute rows per contract
 
 
 def _peaks():
@@ -109,14 +121,37 @@ def run_reference(args):
         return
     for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):   # one thread per worker process
         os.environ.setdefault(k, "1")
+    if args.workload == "contracts":
+        cb = cpu_contracts_ref()
+        if "unavailable" in cb:
+            _emit({"impl": "reference", "unavailable": cb["unavailable"]})
+            return
+        n_c, _ = _ct_plan(args.ct_underlyings)
+        _emit({"impl": "reference", "metric": CT_METRIC, "value": cb["value"], "unit": CT_UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 1,
+               "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": _ct_workload_name(args.ct_underlyings, int(n_c.sum())),
+                          "note": "the step is a bounded sample of the workload's contracts, see cpu_baseline.sample"},
+               "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": CT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0})
+        return
     cb, ms, n_quotes = cpu_arm(args.steps, args.warmup)
+    contracts_ref = None
+    if not args.skip_contracts:
+        try:
+            contracts_ref = cpu_contracts_ref()
+        except Exception as e:      # a reported baseline: never lose the line
+            contracts_ref = {"failed": repr(e)}
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": _workload_name(N_T_DAY), "note": "each step is a bounded sample of the workload, see cpu_baseline.sample"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "contracts": {"metric": CT_METRIC, "unit": CT_UNIT, "cpu_baseline": contracts_ref,
+                          "note": "the reference's OWN classes on the contracts workload's tape (the surface line above is the oracle port: "
+                                  "the reference has no IV solver and no spline)"}}
     _emit(line)
 
 
@@ -180,38 +215,73 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+class _Ctx:
+    """One process per GPU: device, rank plumbing, barrier and max/sum over ranks."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (there is no CPU path; use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # NCCL's INFO log (rank/communicator lines the driver counts) goes to stderr with everything else: stdout is
+            # redirected in main(), the one JSON line is written through the saved descriptor
+            os.environ.setdefault("NCCL_DEBUG", os.environ.get("IVX_NCCL_DEBUG", "INFO"))
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            dist.init_process_group("nccl", device_id=self.dev)
+        if args.gpus != self.world:
+            if self.rank == 0:
+                print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={self.world}; launch with torch.distributed.run", file=sys.stderr)
+            args.gpus = self.world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x: float, op) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.MAX)
+
+    def sum_over_ranks(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.SUM)
+
+    def gather_floats(self, x: float):
+        if self.world == 1:
+            return [x]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.dev)
+        t[self.rank] = x
+        self.dist.all_reduce(t)
+        return t.tolist()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
 def run_gpu(args):
-    import torch
-    import torch.distributed as dist
+    ctx = _Ctx(args)
+    torch, dist = ctx.torch, ctx.dist
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
+    barrier, max_over_ranks = ctx.barrier, ctx.max_over_ranks
 
     from iv_interpolation_b200 import device as D, surface as SF, tapes
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (there is no CPU path; use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("IVX_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    if args.gpus != world:
-        if rank == 0:
-            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run", file=sys.stderr)
-        args.gpus = world
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    if args.workload == "contracts":
+        return run_gpu_contracts(ctx, args)
 
     # ---- size the chain to the GPU (the full day needs ~80 GB; shrink the day only if it does not fit) ----
     free, total = torch.cuda.mem_get_info(dev)
@@ -345,16 +415,16 @@ def run_gpu(args):
 
     cb = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        # the CPU leg runs in a fresh interpreter (no CUDA context to fork, BLAS pinned to one thread per worker)
-        env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
-        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
-            env.pop(k, None)
-        try:
-            pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                                env=env, capture_output=True, text=True, timeout=600)
-            cb = json.loads(pr.stdout.strip().splitlines()[-1])["cpu_baseline"]
-        except Exception as e:  # the CPU leg is a reported baseline; its failure must not lose the GPU numbers
-            cb = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
+        cb = _cpu_leg_subprocess("surface", "cpu_baseline")
+        if cb.get("unit") is None:
+            cb["unit"] = UNIT
+
+    contracts = None
+    if not args.skip_contracts:
+        torch.cuda.empty_cache()
+        contracts = bench_contracts(ctx, args, peak)
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            contracts["cpu_baseline"] = _cpu_leg_subprocess("contracts", "cpu_baseline")
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -367,11 +437,50 @@ def run_gpu(args):
                 "surface_points_per_sec": world * n_t * N_GRID_M * N_GRID_K / (ms_step / 1e3),
                 "candles_per_step": world * n_buckets * N_GRID_M * N_GRID_K,
                 "roofline": roofline, "kernels": kernels, "chain_layout_resident": chain_layout, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
-                "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv}
+                "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv, "contracts": contracts}
         _emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
+
+
+def _cpu_leg_subprocess(workload: str, key: str):
+    """The CPU leg in a fresh interpreter (no CUDA context to fork, BLAS pinned to one thread per worker)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "1",
+                             "--warmup", "0", "--skip-contracts"], env=env, capture_output=True, text=True, timeout=900)
+        return json.loads(pr.stdout.strip().splitlines()[-1])[key]
+    except Exception as e:  # the CPU leg is a reported baseline; its failure must not lose the GPU numbers
+        return {"value": None, "cores": None, "kind": None, "sample": f"failed: {e!r}"}
+
+
+def run_gpu_contracts(ctx, args):
+    """`--workload contracts`: the contracts workload as the line's top level."""
+    torch = ctx.torch
+    peak, peak_src = _peaks()
+    sampler = ClockSampler(ctx.local)
+    if ctx.rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    t_begin = time.perf_counter()
+    c = bench_contracts(ctx, args, peak)
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end) if ctx.rank == 0 else None
+    cb = None
+    if ctx.rank == 0 and ctx.world == 1 and not args.skip_cpu:
+        cb = _cpu_leg_subprocess("contracts", "cpu_baseline")
+    if ctx.rank == 0:
+        c["roofline"]["peak_source"] = peak_src
+        line = {"metric": CT_METRIC, "value": c["value"], "unit": CT_UNIT, "n_gpus": ctx.world, "steps": c["steps"], "warmup": c["warmup"],
+                "ms_per_step": c["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": c["workload"], "sharding": c["sharding"],
+                           "l2": "every stage streams inputs far larger than the 126 MB L2 (>= 2.9 GB per batch); no flush needed"},
+                "roofline": c["roofline"], "stages": c["stages"], "cpu_baseline": cb, "e2e": c["e2e"], "gpu_launches": c["gpu_launches"],
+                "clocks": clocks, "counts": {k: c[k] for k in ("interp_rows", "minute_candles", "candles_5min", "source_rows", "batches_per_rank")}}
+        _emit(line)
+    ctx.close()
 
 
 def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, layout):
@@ -534,6 +643,233 @@ def _cpu_port_ab(tapes):
             "bridge_ohlcv": mk(br_rows, t_br, f"oracle/bridge_oracle.bridge_ohlcv (row loop, like the reference's iterrows) on {br_rows} minute rows")}
 
 
+# ------------------------------------------------------------------------------------------------------
+# contracts workload (BASELINE.json configs[2]): the path the reference has — Task 1 -> bridge -> Task 2
+# ------------------------------------------------------------------------------------------------------
+def _ct_plan(n_und: int):
+    """Contracts per underlying of THE fixed tape (seeded, the same whatever N) and the cost of each underlying."""
+    import numpy as np
+    n_c = np.random.default_rng(CT_SEED).integers(900, 1501, size=n_und)          # 1200 on average
+    return n_c, n_c.astype(np.float64) * CT_OUT_ROWS
+
+
+def _ct_workload_name(n_und: int, n_contracts: int) -> str:
+    return (f"contracts (BASELINE.json configs[2]): {n_und} underlyings x ~1200 contracts ({n_contracts} in all) x {CT_ROWS} hourly rows "
+            f"(20 days) -> {CT_OUT_ROWS} minute rows each -> synthetic 1-min candles -> 5-min candles")
+
+
+def _ct_build_shard(mine, n_c, pin=True):
+    import numpy as np
+    from iv_interpolation_b200 import contracts as CT, tapes
+    first = np.concatenate([[0], np.cumsum(n_c)])
+    parts = []
+    for u in mine:
+        tp = tapes.make_underlying_tape(CT_SEED + 1 + int(u), int(n_c[u]), CT_ROWS, underlying=f"u{u}")
+        parts.append(CT.HostContractShard.from_tape(tp, ids=first[u] + np.arange(n_c[u]), pin=False))
+    return CT.HostContractShard.concat(parts, pin=pin)
+
+
+def bench_contracts(ctx, args, peak):
+    """Strong scaling of one fixed tape: the underlyings are dealt to the ranks longest-first (sharding.lpt_partition),
+    every rank runs Task 1 -> bridge -> Task 2 on its shard in batches, the 5-minute candle tables are gathered on rank 0
+    over NCCL.  `resident`: the shard's source columns already in HBM.  `e2e`: pinned host columns in (H2D inside the timed
+    region), every batch's candle table back to pinned host memory (D2H inside), then the gather."""
+    import numpy as np
+    torch, dist, dev, rank, world = ctx.torch, ctx.dist, ctx.dev, ctx.rank, ctx.world
+    from iv_interpolation_b200 import contracts as CT, device as D, sharding as SH, tapes
+
+    n_und = args.ct_underlyings
+    n_c, costs = _ct_plan(n_und)
+    shards = SH.lpt_partition(costs, world)
+    mine = shards[rank]
+    t0 = time.perf_counter()
+    shard = _ct_build_shard(mine, n_c)
+    t_tape = time.perf_counter() - t0
+    stream = CT.HostContractStream(dev, max_rows_per_batch=args.ct_batch_rows, seed=7)
+    cuts = stream.batches(shard)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
+
+    # ---- resident: source columns of the whole shard on the device -------------------------------------------------
+    d_off = shard.off.to(dev)
+    d_date = shard.date.to(dev)
+    d_cols = {c: shard.cols[c].to(dev) for c in CT.SRC_COLS}
+    views = []
+    for a, b in cuts:
+        r0, r1 = int(shard.off[a]), int(shard.off[b])
+        views.append(((d_off[a:b + 1] - r0).contiguous(), d_date[r0:r1], [d_cols[c][r0:r1] for c in tapes.INTERP_COLS],
+                      [d_cols[c][r0:r1] for c in tapes.FILL_NUM_COLS], int(shard.ids[a])))
+
+    def resident(ev=None):
+        rows = minute = candles = 0
+        for k, (o, d, ic, fc, first) in enumerate(views):
+            res = stream.pipe.run(o, d, ic, fc, first_contract=first, events=ev[k] if ev is not None else None)
+            rows += res.interp.total; minute += res.minute.total; candles += res.candles.total
+        return rows, minute, candles
+
+    mk_ev = lambda: [{st: [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for st in CT.STAGES} for _ in cuts]
+    for _ in range(warmup):
+        resident()
+    evs = [mk_ev() for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    D.reset_launch_count()
+    e0.record()
+    for k in range(steps):
+        rows, minute, candles = resident(evs[k])
+    e1.record()
+    ctx.barrier()
+    launches = D.launch_count()
+    ms_res = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    tot = lambda x: int(ctx.sum_over_ranks(float(x)))
+    rows_all, minute_all, candles_all = tot(rows), tot(minute), tot(candles)
+    stage_ms = {st: sum(ev[st][0].elapsed_time(ev[st][1]) for step in evs for ev in step) / steps for st in CT.STAGES}
+    n_src = int(shard.off[-1])
+    m_e = 0.03 * minute                       # ~3 % of the volumes are NULL in the tape: exponential draws
+    alg = {"interp_plan": n_src * 80, "interp_exec": rows * 85, "bridge_plan": rows * 16, "bridge_tapes": (5 * minute + m_e) * 8,
+           "bridge_ohlcv": rows * 16 + minute * (40 + 56 + 8) + m_e * 8, "candle_ts": minute * 24,
+           "ohlcv_reduce": minute * 48 + candles * 52}
+    kern = {"interp_plan": "k_interp_plan + k_scan_i64 x2", "interp_exec": "k_interp_exec", "bridge_plan": "k_bridge_count_seg + scans + k_bridge_sym_off",
+            "bridge_tapes": "k_random_tape x2", "bridge_ohlcv": "k_bridge_ohlcv_seg + k_bridge_check", "candle_ts": "k_gather<i64>",
+            "ohlcv_reduce": "k_ohlcv_reduce + k_ohlcv_finalize"}
+    stages = {}
+    for st in CT.STAGES:
+        gbs = alg[st] / (stage_ms[st] / 1e3) / 1e9 if stage_ms[st] > 0 else 0.0
+        stages[st] = {"ms": round(stage_ms[st], 4), "kernels": kern[st], "algorithmic_bytes": int(alg[st]), "gbs": round(gbs, 1),
+                      "frac_hbm": round(gbs / peak, 4), "share_of_step": round(stage_ms[st] / (e0.elapsed_time(e1) / steps), 4)}
+    dom = max(CT.STAGES, key=lambda st: stage_ms[st])
+    del views, d_off, d_date, d_cols
+    torch.cuda.empty_cache()
+
+    # ---- e2e: pinned host columns in, candle tables out to pinned host memory, then the gather over NCCL ------------
+    def e2e_step(gev=None):
+        out = stream.run(shard)
+        tab = {k: torch.cat([t[k] for t in out["tables"]]) for k in out["tables"][0]} if out["tables"] else {}
+        if gev is not None:
+            gev[0].record()
+        got = SH.gather_tables(tab, dst=0) if world > 1 and tab else tab
+        if gev is not None:
+            gev[1].record()
+        n_got = int(got["timestamp"].numel()) if got is not None and "timestamp" in got else 0
+        return out, n_got
+
+    for _ in range(warmup):
+        e2e_step()
+    gevs = [[torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for _ in range(steps)]
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    tw = time.perf_counter()
+    f0.record()
+    for k in range(steps):
+        out, n_got = e2e_step(gevs[k])
+    f1.record()
+    ctx.barrier()
+    wall = (time.perf_counter() - tw) / steps
+    ms_e2e = ctx.max_over_ranks(f0.elapsed_time(f1)) / steps
+    ms_gather = ctx.max_over_ranks(sum(g[0].elapsed_time(g[1]) for g in gevs) / steps)
+    h2d, d2h = tot(stream.h2d_bytes), tot(stream.d2h_bytes)
+    if rank == 0 and world > 1 and n_got != candles_all:
+        raise SystemExit(f"bench.py: the gather delivered {n_got} candles, the ranks produced {candles_all}")
+    per_rank_rows = ctx.gather_floats(float(rows))
+    res = {
+        "metric": CT_METRIC, "unit": CT_UNIT, "scaling": "strong",
+        "workload": _ct_workload_name(n_und, int(n_c.sum())),
+        "value": rows_all / (ms_res / 1e3), "ms_per_step": ms_res, "steps": steps, "warmup": warmup,
+        "interp_rows": rows_all, "minute_candles": minute_all, "candles_5min": candles_all,
+        "source_rows": tot(n_src), "batches_per_rank": len(cuts),
+        "sharding": {"unit": "underlying", "policy": "sharding.lpt_partition (longest first; reference analogue optimized_batch_processor.py:123-164)",
+                     "imbalance_max_over_mean": round(SH.imbalance(costs, shards), 4), "underlyings_per_rank": [len(x) for x in shards],
+                     "minute_rows_per_rank": [int(x) for x in per_rank_rows]},
+        "stages": stages,
+        "roofline": {"kernel": kern[dom], "stage": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": stages[dom]["frac_hbm"], "traffic": None},
+        "e2e": {"value": rows_all / (ms_e2e / 1e3), "unit": CT_UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e, "wall_ms_per_step": wall * 1e3, "gather_ms": ms_gather,
+                "gather": ("sharding.gather_tables over NCCL: the 5-min candle tables of all ranks land on rank 0 (point to point, "
+                           f"{candles_all * 56 >> 20} MiB)") if world > 1 else "single rank: nothing to gather",
+                "api": "iv_interpolation_b200.contracts.HostContractStream.run (pinned host source columns in, 5-min candle tables out to pinned host memory)",
+                "result": "the 5-minute candles (8 columns); the interpolated rows and the synthetic 1-minute candles stay on the device"},
+        "gpu_launches": launches * world, "tape_build_s": round(t_tape, 2),
+        "data": "synthetic (tapes.make_underlying_tape, seeds fixed per underlying); bridge random tapes from the device counter generator",
+    }
+    del out, stream
+    torch.cuda.empty_cache()
+    return res
+
+
+# ---- the reference's own classes on the host cores (oracle/_ref) ---------------------------------------------------
+def _ref_contract_worker(job):
+    """One contract through the reference's three classes, as reference batch_processor.py:67-142 -> data_bridge ->
+    candle_reconstruction do it (minus the database): returns rows and seconds per stage."""
+    seed, idx = job
+    import numpy as np
+    from iv_interpolation_b200 import tapes
+    from oracle import reference_loader as RL
+    tp = _REF_TAPE.get(seed)
+    if tp is None:
+        tp = _REF_TAPE[seed] = tapes.make_underlying_tape(seed, 64, CT_ROWS, underlying="u0")
+    df = tp.frame(idx)
+    t0 = time.perf_counter()
+    a = RL.reference_interpolate(df)                                          # interpolation/core.py:16-85 (fillna shim)
+    t1 = time.perf_counter()
+    if a is None:
+        return 0, 0, 0, t1 - t0, 0.0, 0.0
+    b_in = a[["symbol", "date", "underlying_price", "mark_price", "index_price", "volume", "is_interpolated"]].rename(columns={"date": "timestamp"})
+    t1 = time.perf_counter()
+    m = RL.reference_converter()._generate_ohlcv_from_interpolated(b_in)       # data_bridge/ohlcv_converter.py:138-187
+    t2 = time.perf_counter()
+    c = RL.reference_reconstruct(m[["symbol", "timestamp", "open", "high", "low", "close", "volume"]])   # candle core.py:36-106
+    t3 = time.perf_counter()
+    return len(a), len(m), 0 if c is None else len(c), t1 - t0, t2 - t1, t3 - t2
+
+
+_REF_TAPE = {}
+
+
+def cpu_contracts_ref(budget_s: float = 24.0):
+    """The reference's classes (oracle/_ref or /root/reference) on contracts of the same tape: one core, then a
+    ProcessPoolExecutor(max_workers=os.cpu_count()) with one future per contract (batch_processor.py:234-239)."""
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    from oracle import reference_loader as RL
+    if not RL.available():
+        return {"unavailable": "neither /root/reference nor oracle/_ref is present (run oracle/make_ref.py in the build container)"}
+    RL.quiet()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    seed = CT_SEED + 1
+    t0 = time.perf_counter()
+    one = [_ref_contract_worker((seed, 0))]
+    per_contract = time.perf_counter() - t0
+    n1 = int(max(1, min(6, budget_s * 0.35 // per_contract - 1)))
+    one += [_ref_contract_worker((seed, i)) for i in range(1, n1 + 1)]
+    t_one = time.perf_counter() - t0
+    rows_one = sum(r[0] for r in one)
+    k = int(max(1, min(8, budget_s * 0.5 // per_contract)))
+    jobs = [(seed, i % 64) for i in range(cores * k)]
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork")) as ex:
+        list(ex.map(_ref_contract_worker, [(seed, 0)] * cores))               # start the workers, import pandas, build the tape
+        t0 = time.perf_counter()
+        res = list(ex.map(_ref_contract_worker, jobs))
+        t_pool = time.perf_counter() - t0
+    rows_pool = sum(r[0] for r in res)
+    st = lambda rs, j: sum(r[j] for r in rs)
+    return {
+        "value": rows_pool / t_pool, "unit": CT_UNIT, "cores": cores, "kind": "reference",
+        "source": f"{RL.where()}: IVInterpolator.interpolate_symbol -> InterpolatedToOHLCVConverter._generate_ohlcv_from_interpolated -> "
+                  "CandleReconstructor.reconstruct_symbol_candles, the reference's own modules (oracle/make_ref.py copies them untouched), "
+                  "Task 1 under the pandas-3 fillna(method=) shim (SURVEY.md 0.3); no database",
+        "sample": f"{len(jobs)} contracts x {CT_ROWS} hourly rows ({rows_pool} minute rows) of the workload's tape, ProcessPoolExecutor({cores}), "
+                  f"one future per contract; {t_pool:.1f} s",
+        "one_core": {"value": rows_one / t_one, "unit": CT_UNIT, "contracts": len(one), "seconds": round(t_one, 2),
+                     "stage_rows_per_s": {"interpolate_symbol": rows_one / max(1e-9, st(one, 3)), "bridge": st(one, 1) / max(1e-9, st(one, 4)),
+                                          "reconstruct_symbol_candles": st(one, 1) / max(1e-9, st(one, 5))},
+                     "stage_seconds": {"interpolate_symbol": round(st(one, 3), 3), "bridge": round(st(one, 4), 3),
+                                       "reconstruct_symbol_candles": round(st(one, 5), 3)}},
+        "pool_stage_seconds_summed": {"interpolate_symbol": round(st(res, 3), 2), "bridge": round(st(res, 4), 2),
+                                      "reconstruct_symbol_candles": round(st(res, 5), 2)},
+        "candles_5min_per_contract": res[0][2], "ms_per_step": t_pool * 1e3,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -545,6 +881,10 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--workload", choices=("surface", "contracts"), default="surface")
+    ap.add_argument("--skip-contracts", action="store_true", help="leave the contracts object out of the surface line")
+    ap.add_argument("--ct-underlyings", type=int, default=CT_UNDERLYINGS)
+    ap.add_argument("--ct-batch-rows", type=int, default=160_000_000, help="minute rows per batch of contracts (HBM working set)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: fewer than 3 warm-up steps breaks the timing rules; continuing as asked", file=sys.stderr)

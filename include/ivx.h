@@ -279,6 +279,16 @@ void ivx_bridge_test_force_fallback(int32_t on);   /* test hook: the segment che
  * roofline denominators measured in the same run (bench.py).
  * ------------------------------------------------------------------------------------------- */
 int ivx_exclusive_scan_i64(int64_t n, const int64_t* in, int64_t* out /*n+1*/, ivx_stream_t stream);
+/* out[i] = src[idx[i]] (NaT / NaN where idx[i] is outside [0, n_src)): the timestamps and source prices of the bridge's
+ * candles from o_row, so that the candles can feed ivx_ohlcv_reduce without leaving the device
+ * (the reference does this through a DataFrame: ohlcv_converter.py:168-184, complete_pipeline.py:641-652) */
+int ivx_gather_i64(int64_t n, const int64_t* idx, int64_t n_src, const int64_t* src, int64_t* out, ivx_stream_t stream);
+int ivx_gather_f64(int64_t n, const int64_t* idx, int64_t n_src, const double* src, double* out, ivx_stream_t stream);
+/* Random tapes for ivx_bridge_ohlcv produced on the device: element i is a function of (seed, stream_id, i) alone
+ * (Philox4x32-10 counter generator; 53-bit uniforms built like numpy's random_sample).  kind 0: uniform [0,1);
+ * kind 1: standard exponential.  This is the reference's normal mode — np.random unseeded (ohlcv_converter.py:213-263,
+ * 359-369) — without the host drawing 5 numbers per row; parity runs pass host-drawn numpy tapes instead. */
+int ivx_random_tape(int64_t n, uint64_t seed, uint32_t stream_id, int32_t kind, double* out, ivx_stream_t stream);
 int ivx_probe_copy(int64_t n_f64, const double* src, double* dst, ivx_stream_t stream);
 int ivx_probe_fp64_fma(int64_t n_threads, int32_t iters, double* sink, ivx_stream_t stream);
 /* kernel A's store pattern alone (11 fp64 + one int32 + one uint8 stream of n_rows, arrays stride_f64 doubles apart):

@@ -70,6 +70,9 @@ SIGNATURES = {
     "ivx_bridge_ohlcv": (C.c_int, [_i64, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_exclusive_scan_i64": (C.c_int, [_i64, _p, _p, _p]),
+    "ivx_gather_i64": (C.c_int, [_i64, _p, _i64, _p, _p, _p]),
+    "ivx_gather_f64": (C.c_int, [_i64, _p, _i64, _p, _p, _p]),
+    "ivx_random_tape": (C.c_int, [_i64, C.c_uint64, C.c_uint32, _i32, _p, _p]),
     "ivx_probe_copy": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_fp64_fma": (C.c_int, [_i64, _i32, _p, _p]),
     "ivx_probe_write_streams": (C.c_int, [_i64, _p, _i64, _p]),

@@ -37,7 +37,12 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ivx::cuda_fail(e__, name);    \
   } while (0)
 
-int sm_count();
+#define IVX_MAX_DEVICES 64
+int current_device();
+int sm_count();          // of the CURRENT device
+// `static DeviceOnce once; if (once_per_device(once)) cudaFuncSetAttribute(...)`: true the first time on each device
+struct DeviceOnce { bool done[IVX_MAX_DEVICES] = {}; };
+bool once_per_device(DeviceOnce& o);
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

@@ -510,11 +510,8 @@ extern "C" int ivx_ohlcv_reduce(int64_t n_sym, const int64_t* in_off, int64_t n_
     P.n_tiles = (int32_t)n_tiles;
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
     P.use_bulk = al16(ts) && al16(open) && al16(high) && al16(low) && al16(close) && al16(volume);
-    static bool attr_set = false;
-    if (!attr_set) {
-      IVX_CUDA(cudaFuncSetAttribute(k_ohlcv_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-      attr_set = true;
-    }
+    static DeviceOnce attr_once;                       // the attribute is per device, not per process
+    if (once_per_device(attr_once)) IVX_CUDA(cudaFuncSetAttribute(k_ohlcv_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     k_ohlcv_reduce<<<(unsigned)n_tiles, TB_THREADS, sizeof(TileSmem), stream>>>(P);
     IVX_LAUNCH_CHECK("k_ohlcv_reduce");
   }

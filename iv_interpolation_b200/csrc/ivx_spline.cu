@@ -670,11 +670,8 @@ static int launch_spline_t(int64_t n_slices, const int64_t* knot_off, const int6
                            const int64_t* ladder_off, const double* y, int n_q,
                          const double* xq, int extrap, double* yq, cudaStream_t stream) {
   using L = SplLayout<G, SPL_R>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
-    attr_set = true;
-  }
+  static DeviceOnce attr_once;                       // the attribute is per device, not per process
+  if (once_per_device(attr_once)) IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
   const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
   IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
   k_spline_fit_eval<G, SPL_R, MODE><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y, n_q, xq, extrap, yq);
@@ -773,11 +770,8 @@ extern "C" int ivx_spline_ladder_factor(int64_t n_ladders, const int64_t* ladder
   IVX_REQUIRE(ladder_off && x && lu_cp && lu_inv && lu_ih, IVX_ERR_INVALID_ARG, "ivx_spline_ladder_factor: null pointer");
   const int G = spline_group_width(max_knots);
   const size_t smem = (size_t)3 * G * SPL_RMAX * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    IVX_CUDA(cudaFuncSetAttribute(k_spline_ladder_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 1024 * SPL_RMAX * (int)sizeof(double)));
-    attr_set = true;
-  }
+  static DeviceOnce attr_once;                       // the attribute is per device, not per process
+  if (once_per_device(attr_once)) IVX_CUDA(cudaFuncSetAttribute(k_spline_ladder_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 1024 * SPL_RMAX * (int)sizeof(double)));
   k_spline_ladder_factor<<<(unsigned)n_ladders, 256, smem, (cudaStream_t)stream_>>>(n_ladders, ladder_off, x, G, lu_cp, lu_inv, lu_ih);
   IVX_LAUNCH_CHECK("k_spline_ladder_factor");
   return IVX_OK;
@@ -808,9 +802,8 @@ extern "C" int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, in
 }
 
 static cudaError_t strided_smem_attr() {
-  static bool done = false;
-  if (done) return cudaSuccess;
-  done = true;
+  static DeviceOnce attr_once;                         // per device, not per process
+  if (!once_per_device(attr_once)) return cudaSuccess;
   return cudaFuncSetAttribute(k_spline_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIDED_MAXK * 128 * (int)sizeof(double));
 }
 

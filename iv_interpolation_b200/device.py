@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2, "spline_ladder_factor": 1,
-    "bridge_quality": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
+    "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
 
@@ -579,6 +579,41 @@ def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
     out = _empty(x.numel() + 1, torch.int64, x)
     check(lib().ivx_exclusive_scan_i64(x.numel(), _ptr(_req(x, torch.int64, "x")), _ptr(out), _stream()), "ivx_exclusive_scan_i64")
     _count("scan")
+    return out
+
+
+def gather(idx: torch.Tensor, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``src[idx]`` for int64 or float64 ``src`` (NaT / NaN where ``idx`` is out of range)."""
+    _req(idx, torch.int64, "idx")
+    n = idx.numel()
+    out = out if out is not None else _empty(n, src.dtype, src)
+    if out.numel() < n or out.dtype != src.dtype:
+        raise _lib.IvxError("gather: output too small or of the wrong dtype")
+    if src.dtype == torch.int64:
+        fn = lib().ivx_gather_i64
+    elif src.dtype == torch.float64:
+        fn = lib().ivx_gather_f64
+    else:
+        raise _lib.IvxError(f"gather: int64 or float64 source, got {src.dtype}")
+    check(fn(n, _ptr(idx), src.numel(), _ptr(src), _ptr(out), _stream()), "ivx_gather")
+    _count("gather")
+    return out[:n]
+
+
+def random_tape(n: int, seed: int, stream_id: int = 0, kind: str = "uniform", like: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``n`` uniforms in [0, 1) or standard exponentials from the device's counter generator (element i depends on
+    (seed, stream_id, i) only): the bridge's tapes without a host draw."""
+    if out is None:
+        if like is None:
+            raise _lib.IvxError("random_tape: pass `like` (a CUDA tensor) or `out`")
+        out = _empty(max(1, n), torch.float64, like)
+    _req(out, torch.float64, "out")
+    if out.numel() < n:
+        raise _lib.IvxError("random_tape: output too small")
+    check(lib().ivx_random_tape(int(n), int(seed) & (2 ** 64 - 1), int(stream_id) & 0xffffffff, {"uniform": 0, "exponential": 1}[kind],
+                                _ptr(out), _stream()), "ivx_random_tape")
+    _count("random_tape")
     return out
 
 

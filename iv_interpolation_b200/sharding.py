@@ -48,12 +48,13 @@ def contract_costs(src_off: np.ndarray, src_ts: np.ndarray, step: int) -> np.nda
     """Output rows each contract will produce (span / step + 1): the cost model of kernels A and B, the
     analogue of the reference's ``row_count * interpolation_factor`` (optimized_batch_processor.py:129-133)."""
     src_off = np.asarray(src_off, dtype=np.int64)
+    src_ts = np.asarray(src_ts, dtype=np.int64)
     n = len(src_off) - 1
     out = np.zeros(n, dtype=np.float64)
-    for i in range(n):
-        a, b = int(src_off[i]), int(src_off[i + 1])
-        if b > a:
-            out[i] = (int(src_ts[b - 1]) - int(src_ts[a])) // step + 1
+    a, b = src_off[:-1], src_off[1:]
+    ok = b > a
+    if ok.any():
+        out[ok] = (src_ts[b[ok] - 1] - src_ts[a[ok]]) // step + 1
     return out
 
 
@@ -65,8 +66,10 @@ def my_units(costs: Sequence[float], rank: Optional[int] = None, world: Optional
 
 def gather_tables(local: Dict[str, torch.Tensor], dst: int = 0, group=None) -> Optional[Dict[str, torch.Tensor]]:
     """Final gather: every rank contributes a table (dict of equally long 1-D tensors, same keys and dtypes on
-    all ranks); ``dst`` receives their concatenation in rank order, the others ``None``.  Row counts are
-    exchanged first (all_gather), tables travel padded to the longest (all_gather: works on NCCL and gloo)."""
+    all ranks); ``dst`` receives their concatenation in rank order (+ a ``_rank`` column), the others ``None``.
+    Row counts are exchanged first (one small all_gather); the columns then travel point to point, each rank's rows
+    landing directly in their slice of ``dst``'s output — no padding, nothing sent to ranks that do not need it
+    (NCCL send/recv over NVLink on GPUs, gloo in the CPU tests)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     keys = sorted(local)
@@ -77,17 +80,27 @@ def gather_tables(local: Dict[str, torch.Tensor], dst: int = 0, group=None) -> O
     dev = local[keys[0]].device if keys else torch.device("cpu")
     counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=dev), group=group)
-    counts = [int(c.item()) for c in counts]
-    n_max = max(counts) if counts else 0
-    out: Dict[str, torch.Tensor] = {}
-    for k in keys:
-        padded = torch.zeros(n_max, dtype=local[k].dtype, device=dev)
-        padded[:n_local] = local[k]
-        parts = [torch.empty_like(padded) for _ in range(world)]
-        dist.all_gather(parts, padded, group=group)
-        if rank == dst:
-            out[k] = torch.cat([p[:c] for p, c in zip(parts, counts)])
+    counts = [int(c) for c in torch.cat(counts).tolist()]
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    ops, out = [], {}
+    if rank == dst:
+        for k in keys:
+            out[k] = torch.empty(int(starts[-1]), dtype=local[k].dtype, device=dev)
+            out[k][int(starts[rank]):int(starts[rank + 1])] = local[k]
+        for r in range(world):
+            if r == dst or counts[r] == 0:
+                continue
+            for k in keys:
+                ops.append(dist.P2POp(dist.irecv, out[k][int(starts[r]):int(starts[r + 1])], peer(r), group))
+    elif n_local:
+        for k in keys:
+            ops.append(dist.P2POp(dist.isend, local[k].contiguous(), peer(dst), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     if rank != dst:
         return None
-    out["_rank"] = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(counts)])
+    out["_rank"] = torch.repeat_interleave(torch.arange(world, dtype=torch.int32, device=dev),
+                                           torch.tensor(counts, dtype=torch.int64, device=dev))
     return out

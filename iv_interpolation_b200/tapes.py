@@ -132,6 +132,49 @@ def make_contract_tape(
     )
 
 
+def make_underlying_tape(seed: int, n_contracts: int, rows_per_contract: int = 481, spacing_us: int = HOUR_US,
+                         nan_frac: float = 0.05, offgrid_frac: float = 0.02, underlying: str = "u0", t0: int = T0_US,
+                         s0: float = 25_000.0) -> ContractTape:
+    """All contracts of ONE underlying over ``rows_per_contract`` hourly stamps (481 = 20 days): the unit BASELINE.json
+    configs[2] shards by.  Same distributions as ``make_contract_tape`` (5 % NaN iv incl. leading/trailing ones, 2 % of
+    rows 30 s off the grid, NaN volumes), drawn in whole-underlying arrays so that 100 underlyings take seconds."""
+    rng = np.random.default_rng(seed)
+    n, m = int(n_contracts), int(rows_per_contract)
+    base_t = t0 + np.arange(m, dtype=np.int64) * spacing_us
+    spot = s0 + np.cumsum(rng.normal(0.0, 50.0, m))
+    t = np.broadcast_to(base_t, (n, m)).copy()
+    og = rng.random((n, m)) < offgrid_frac
+    og[:, 0] = og[:, -1] = False
+    t[og] += 30 * US
+    iv = rng.uniform(0.2, 1.2, (n, m))
+    nanm = rng.random((n, m)) < nan_frac
+    idx = np.arange(n)
+    nanm[idx % 7 == 3, 0] = True
+    nanm[idx % 11 == 5, -1] = True
+    iv[nanm] = np.nan
+    n_strikes = max(2, (n + 11) // 12)
+    strikes = np.round(s0 * np.linspace(0.5, 1.5, n_strikes) / 100.0) * 100.0
+    exp_i, k_i, cp = (idx // 2) % 6, (idx // 12) % n_strikes, idx % 2
+    ttm0 = (7 + 30 * exp_i) / 365.0
+    vol = rng.exponential(5.0, (n, m))
+    vol[rng.random((n, m)) < 0.03] = np.nan
+    cols = {
+        "iv": iv,
+        "underlying_price": spot[None, :] + rng.normal(0.0, 1.0, (n, m)),
+        "time_to_maturity": ttm0[:, None] - (t - t0) / (365.0 * DAY_US),
+        "strike": np.broadcast_to(strikes[k_i][:, None], (n, m)),
+        "interest_rate": np.full((n, m), 0.05),
+        "mark_price": rng.uniform(0.001, 0.2, (n, m)),
+        "index_price": np.broadcast_to(spot[None, :], (n, m)),
+        "volume": vol,
+        "quote_volume": vol * spot[None, :],
+    }
+    symbols = [f"{underlying}-{15 + int(e)}mar23-{int(strikes[k])}-{'c' if c else 'p'}" for e, k, c in zip(exp_i, k_i, cp)]
+    return ContractTape(np.arange(n + 1, dtype=np.int64) * m, t.reshape(-1),
+                        {k: np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for k, v in cols.items()}, symbols,
+                        cp.astype(np.uint8))
+
+
 @dataclass
 class CandleTape:
     """Task-2 input, CSR-packed 1-min (or finer) OHLCV rows per symbol, sorted by timestamp."""

@@ -227,3 +227,20 @@ def test_columnar_round_trip_at_db_precision(tmp_path):
     ct = CO.candles_to_table({"s": c})
     assert ct.schema.field("open").type == pa.decimal128(15, 4) and ct.column_names == list(CO.CANDLE_ORDER[:9]) + ["created_at"]
     assert float(ct.column("open")[0].as_py()) == 1.0
+
+
+def test_contracts_workload_plan_is_fixed_and_balanced():
+    """bench.py's contracts workload (BASELINE.json configs[2]): the tape plan does not depend on the number of ranks, every
+    underlying lands on exactly one rank, and longest-first dealing keeps max/mean shard load within a few percent at 8 ranks."""
+    import bench
+    from iv_interpolation_b200 import sharding as SH
+    n_c, costs = bench._ct_plan(100)
+    n_c2, _ = bench._ct_plan(100)
+    assert (n_c == n_c2).all() and 900 <= n_c.min() and n_c.max() <= 1500 and abs(n_c.mean() - 1200) < 60
+    for world in (1, 2, 4, 8):
+        shards = SH.lpt_partition(costs, world)
+        assert sorted(u for s in shards for u in s) == list(range(100))
+        assert SH.imbalance(costs, shards) < 1.03
+    shard = bench._ct_build_shard([3, 5], n_c, pin=False)
+    assert shard.n_contracts == n_c[3] + n_c[5] and int(shard.off[-1]) == shard.n_contracts * bench.CT_ROWS
+    assert shard.ids[0] == n_c[:3].sum() and shard.ids[-1] == n_c[:6].sum() - 1 and (shard.out_rows == bench.CT_OUT_ROWS).all()
