@@ -121,6 +121,9 @@ def run_reference(args):
         return
     for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):   # one thread per worker process
         os.environ.setdefault(k, "1")
+    if args.workload == "dropin":
+        _emit({"impl": "reference", "dropin": cpu_dropin_ref()})
+        return
     if args.workload == "contracts":
         cb = cpu_contracts_ref()
         if "unavailable" in cb:
@@ -283,6 +286,24 @@ def run_gpu(args):
     if args.workload == "contracts":
         return run_gpu_contracts(ctx, args)
 
+    # ---- the contracts workload first (its working set is released before the chain is built) ------------------------
+    contracts = None
+    if not args.skip_contracts:
+        contracts = bench_contracts(ctx, args, _peaks()[0])
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            contracts["cpu_baseline"] = _cpu_leg_subprocess("contracts", "cpu_baseline")
+        torch.cuda.empty_cache()
+
+    dropin = None
+    if rank == 0 and world == 1 and not args.skip_dropin:
+        try:
+            dropin = bench_dropin(args)
+            if not args.skip_cpu:
+                dropin["cpu_baseline"] = _cpu_leg_subprocess("dropin", "dropin")
+        except Exception as e:       # host-side figures: never lose the line
+            dropin = {"failed": repr(e)}
+        torch.cuda.empty_cache()
+
     # ---- size the chain to the GPU (the full day needs ~80 GB; shrink the day only if it does not fit) ----
     free, total = torch.cuda.mem_get_info(dev)
     per_stamp = N_EXP * N_STRIKE * (BYTES_PER_QUOTE + 8) + N_EXP * N_GRID_K * 8 + N_GRID_M * N_GRID_K * 8 + 1200   # + sigma_true
@@ -419,13 +440,6 @@ def run_gpu(args):
         if cb.get("unit") is None:
             cb["unit"] = UNIT
 
-    contracts = None
-    if not args.skip_contracts:
-        torch.cuda.empty_cache()
-        contracts = bench_contracts(ctx, args, peak)
-        if rank == 0 and world == 1 and not args.skip_cpu:
-            contracts["cpu_baseline"] = _cpu_leg_subprocess("contracts", "cpu_baseline")
-
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -437,7 +451,7 @@ def run_gpu(args):
                 "surface_points_per_sec": world * n_t * N_GRID_M * N_GRID_K / (ms_step / 1e3),
                 "candles_per_step": world * n_buckets * N_GRID_M * N_GRID_K,
                 "roofline": roofline, "kernels": kernels, "chain_layout_resident": chain_layout, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
-                "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv, "contracts": contracts}
+                "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv, "contracts": contracts, "e2e_dropin": dropin}
         _emit(line)
     ctx.close()
 
@@ -870,6 +884,135 @@ def cpu_contracts_ref(budget_s: float = 24.0):
     }
 
 
+# ------------------------------------------------------------------------------------------------------
+# drop-in classes, frames in -> frames out (BASELINE.json configs[0]: 2 400 contracts x 25 hourly rows, one day)
+# ------------------------------------------------------------------------------------------------------
+DROPIN_CONTRACTS = 2400
+
+
+def _dropin_frames(n):
+    from iv_interpolation_b200 import tapes
+    tp = tapes.make_contract_tape(0, n)
+    return [tp.frame(i) for i in range(tp.n_sym)]
+
+
+def bench_dropin(args):
+    """What a user of the reference swaps in: IVInterpolator.interpolate_batch, InterpolatedToOHLCVConverter.convert_frames,
+    CandleReconstructor.reconstruct_batch and PipelineBatch.run — DataFrames in, DataFrames out, wall clock, on the config-1
+    batch.  The CPU comparator (cpu_dropin_ref) loops the reference's own classes over frames of the same tape."""
+    import numpy as np
+    import pandas as pd
+    from iv_interpolation_b200.batch import PipelineBatch
+    from iv_interpolation_b200.candle_reconstruction.core import CandleReconstructor
+    from iv_interpolation_b200.data_bridge.ohlcv_converter import InterpolatedToOHLCVConverter
+    from iv_interpolation_b200.interpolation.core import IVInterpolator
+    import logging
+    logging.getLogger("iv_interpolation_b200").setLevel(logging.ERROR)
+    frames = _dropin_frames(args.dropin_contracts)
+    out = {"workload": f"config 1 (BASELINE.json configs[0]): {len(frames)} contracts x 25 hourly rows -> 1 441 minute rows each; DataFrames in, DataFrames out",
+           "timer": "time.perf_counter around the call (host work, H2D, kernels, D2H, frame assembly), best of 3 after one warm-up"}
+
+    def best(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); r = fn(); ts.append(time.perf_counter() - t0)
+        return min(ts), r
+
+    itp = IVInterpolator()
+    timing = {}
+    t_a, res_a = best(lambda: itp.interpolate_batch(frames, timing=timing))
+    rows = sum(len(r) for r in res_a if r is not None)
+    reps_done = 4
+    out["interpolate_batch"] = {"api": "IVInterpolator.interpolate_batch(frames)", "rows_out": rows, "seconds": round(t_a, 4), "rate": rows / t_a,
+                                "rate_unit": "minute-rows/s", "frames_ok": sum(r is not None for r in res_a),
+                                "split_s": {k: round(v / reps_done, 4) for k, v in timing.items()}}
+    one = frames[7]
+    t_1, _ = best(lambda: itp.interpolate_symbol(one), reps=5)
+    out["interpolate_symbol"] = {"api": "IVInterpolator.interpolate_symbol(frame) — one contract per call, as the reference's drivers call it",
+                                 "seconds_per_call": round(t_1, 5), "rate": 1441 / t_1, "rate_unit": "minute-rows/s"}
+    ok = [r for r in res_a if r is not None]
+    b_in = [r[["symbol", "date", "underlying_price", "mark_price", "index_price", "volume", "is_interpolated"]].rename(columns={"date": "timestamp"}) for r in ok]
+    conv = InterpolatedToOHLCVConverter(None, None, rng=np.random.RandomState(1))
+    t_br, res_br = best(lambda: conv.convert_frames(b_in), reps=2)
+    minute = [r["ohlcv"][["symbol", "timestamp", "open", "high", "low", "close", "volume"]] for r in res_br if r["status"] == "success"]
+    m_rows = sum(len(m) for m in minute)
+    out["convert_frames"] = {"api": "InterpolatedToOHLCVConverter.convert_frames(frames) (spread_simulation; numpy's MT19937 draws the tapes on the host, "
+                                    "in the reference's order, so a seeded run reproduces the reference's candles)",
+                             "rows_in": rows, "candles_out": m_rows, "seconds": round(t_br, 4), "rate": rows / t_br, "rate_unit": "minute-rows/s"}
+    rec = CandleReconstructor("5min")
+    t_b, res_b = best(lambda: rec.reconstruct_batch(minute))
+    out["reconstruct_batch"] = {"api": "CandleReconstructor('5min').reconstruct_batch(frames)", "rows_in": m_rows,
+                                "candles_out": sum(len(r) for r in res_b if r is not None), "seconds": round(t_b, 4), "rate": m_rows / t_b,
+                                "rate_unit": "minute-rows/s"}
+    fr = {f"c{i}": f for i, f in enumerate(frames)}
+    t_p, res_p = best(lambda: PipelineBatch(rng=np.random.RandomState(2), batch_id=1).run(fr), reps=2)
+    out["pipeline_batch"] = {"api": "PipelineBatch.run(frames): Task 1 -> bridge -> Task 2 (complete_pipeline.py's order), frames at every stage",
+                             "seconds": round(t_p, 4), "rate": rows / t_p, "rate_unit": "minute-rows/s (Task-1 output rows)",
+                             "candles_5min": sum(len(v) for v in res_p[0].values())}
+    return out
+
+
+def _dropin_ref_worker(job):
+    kind, idx = job
+    from oracle import reference_loader as RL
+    fr = _DROPIN_REF["frames"]
+    if kind == "a":
+        t0 = time.perf_counter(); r = RL.reference_interpolate(fr[idx]); return (0 if r is None else len(r)), time.perf_counter() - t0
+    m = _DROPIN_REF["minute"][idx % len(_DROPIN_REF["minute"])]
+    t0 = time.perf_counter(); r = RL.reference_reconstruct(m, "5min"); return len(m), time.perf_counter() - t0
+
+
+_DROPIN_REF = {}
+
+
+def cpu_dropin_ref():
+    """The reference's classes looped over frames of the same config-1 tape: one core, and (Task 1, Task 2) a
+    ProcessPoolExecutor over all cores, one future per frame (batch_processor.py:234-239)."""
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    from oracle import reference_loader as RL
+    if not RL.available():
+        return {"unavailable": "neither /root/reference nor oracle/_ref is present"}
+    RL.quiet()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = 240
+    frames = _dropin_frames(n)
+    _DROPIN_REF["frames"] = frames
+    RL.reference_interpolate(frames[0])
+    t0 = time.perf_counter()
+    outs = [RL.reference_interpolate(f) for f in frames[:96]]
+    t_a = time.perf_counter() - t0
+    rows_a = sum(len(o) for o in outs if o is not None)
+    ok = [o for o in outs if o is not None]
+    conv = RL.reference_converter()
+    b_in = [o[["symbol", "date", "underlying_price", "mark_price", "index_price", "volume", "is_interpolated"]].rename(columns={"date": "timestamp"}) for o in ok[:40]]
+    t0 = time.perf_counter()
+    minute = [conv._generate_ohlcv_from_interpolated(b) for b in b_in]
+    t_br = time.perf_counter() - t0
+    rows_br = sum(len(b) for b in b_in)
+    minute = [m[["symbol", "timestamp", "open", "high", "low", "close", "volume"]] for m in minute if m is not None]
+    _DROPIN_REF["minute"] = minute
+    RL.reference_reconstruct(minute[0], "5min")
+    t0 = time.perf_counter()
+    for k in range(96):
+        RL.reference_reconstruct(minute[k % len(minute)], "5min")
+    t_b = time.perf_counter() - t0
+    rows_b = sum(len(minute[k % len(minute)]) for k in range(96))
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork")) as ex:
+        list(ex.map(_dropin_ref_worker, [("a", 0)] * cores))
+        t0 = time.perf_counter(); ra = list(ex.map(_dropin_ref_worker, [("a", i % n) for i in range(cores * 24)])); tp_a = time.perf_counter() - t0
+        t0 = time.perf_counter(); rb = list(ex.map(_dropin_ref_worker, [("b", i) for i in range(cores * 24)])); tp_b = time.perf_counter() - t0
+    return {"kind": "reference", "source": RL.where(), "cores": cores,
+            "one_core": {"interpolate_symbol": {"rate": rows_a / t_a, "seconds_per_call": t_a / 96, "frames": 96},
+                         "_generate_ohlcv_from_interpolated": {"rate": rows_br / t_br, "seconds_per_call": t_br / len(b_in), "frames": len(b_in)},
+                         "reconstruct_symbol_candles": {"rate": rows_b / t_b, "seconds_per_call": t_b / 96, "frames": 96},
+                         "pipeline": {"rate": 1.0 / (t_a / rows_a + t_br / rows_br + t_b / rows_b)}},
+            "all_cores": {"interpolate_symbol": {"rate": sum(r[0] for r in ra) / tp_a, "frames": len(ra)},
+                          "reconstruct_symbol_candles": {"rate": sum(r[0] for r in rb) / tp_b, "frames": len(rb)}},
+            "rate_unit": "minute-rows/s", "sample": "frames of the same config-1 tape (tapes.make_contract_tape(0, n)): see `frames` per entry"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -881,10 +1024,12 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workload", choices=("surface", "contracts"), default="surface")
+    ap.add_argument("--workload", choices=("surface", "contracts", "dropin"), default="surface")
+    ap.add_argument("--skip-dropin", action="store_true")
+    ap.add_argument("--dropin-contracts", type=int, default=DROPIN_CONTRACTS)
     ap.add_argument("--skip-contracts", action="store_true", help="leave the contracts object out of the surface line")
     ap.add_argument("--ct-underlyings", type=int, default=CT_UNDERLYINGS)
-    ap.add_argument("--ct-batch-rows", type=int, default=160_000_000, help="minute rows per batch of contracts (HBM working set)")
+    ap.add_argument("--ct-batch-rows", type=int, default=48_000_000, help="minute rows per batch of contracts (HBM working set)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: fewer than 3 warm-up steps breaks the timing rules; continuing as asked", file=sys.stderr)

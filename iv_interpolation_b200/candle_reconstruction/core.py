@@ -70,6 +70,18 @@ class CandleReconstructor:
         results: List[Optional[pd.DataFrame]] = [None] * len(frames)
         if flags_out is not None:           # per frame: IVX_FLAG_* bits of the launch (validate_candle_data of input and output), None = not run
             flags_out[:] = [None] * len(frames)
+        from .. import hostpath as H
+        live = [i for i, df in enumerate(frames) if not df.empty]
+        if n >= 1 and len(live) > 1 and H.task2_uniform([frames[i] for i in live]):
+            got = H.reconstruct_uniform([frames[i] for i in live], n, self.target_frequency, datetime.now(),
+                                        presorted=presorted, check_len=check_len)
+            if got is not None:
+                outs, fl = got
+                for k, i in enumerate(live):
+                    results[i] = outs[k]
+                    if flags_out is not None:
+                        flags_out[i] = fl[k]
+                return results
         inputs, srcs, slots = [], [], []
         for i, df in enumerate(frames):
             if df.empty:

@@ -42,7 +42,7 @@ class IVInterpolator:
             return None
 
     # -- many contracts in one launch --------------------------------------------------------------
-    def interpolate_batch(self, frames: Sequence[pd.DataFrame]) -> List[Optional[pd.DataFrame]]:
+    def interpolate_batch(self, frames: Sequence[pd.DataFrame], timing: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
         """``[interpolate_symbol(f) for f in frames]`` with one plan + one exec launch for all."""
         import torch
         from .. import device as D
@@ -55,6 +55,16 @@ class IVInterpolator:
         if self.method not in _LINEAR_METHODS:
             logger.error(f"Interpolation failed: method {self.method!r} is not available "
                          f"(supported: {_LINEAR_METHODS})")
+            return results
+        # frames in the reference's plain schema: one concat, one launch, one result frame (hostpath.py)
+        from .. import hostpath as H
+        big_enough = [i for i, df in enumerate(frames) if len(df) >= self.min_points]
+        if len(big_enough) > 1 and H.task1_uniform([frames[i] for i in big_enough]):
+            outs = H.interpolate_uniform([frames[i] for i in big_enough], self.min_points, timing=timing)
+            for i, out in zip(big_enough, outs):
+                if out is None:
+                    logger.debug("No valid data after interpolation or guard failed")
+                results[i] = out
             return results
         inputs, srcs, slots = [], [], []
         for i, df in enumerate(frames):
@@ -110,8 +120,10 @@ class IVInterpolator:
             else:
                 masks = [cat(lambda p, c=c: p.fill_idx_valid[p.fill_idx_names.index(c)]) for c in sym_first]
                 order_names = sym_first
-            if len(fcols) > 8 or len(masks) > 4:
-                raise IvxError("too many forward-fill columns for one launch")
+            if len(fcols) > 8 or len(masks) > 4:        # only these frames fail (the reference would handle them: logged)
+                logger.error(f"Interpolation failed: {len(fcols)} numeric and {len(masks)} non-numeric forward-fill columns exceed "
+                             "one launch (8 / 4); convert string columns you do not need or split the frame")
+                continue
             valid = [None if m.all() else torch.from_numpy(m.astype(np.uint8)).to(dev) for m in masks]
             first = inputs[members[0]][0]
             res = D.interp_linear_ffill(
