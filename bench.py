@@ -945,6 +945,18 @@ def bench_dropin(args):
     out["reconstruct_batch"] = {"api": "CandleReconstructor('5min').reconstruct_batch(frames)", "rows_in": m_rows,
                                 "candles_out": sum(len(r) for r in res_b if r is not None), "seconds": round(t_b, 4), "rate": m_rows / t_b,
                                 "rate_unit": "minute-rows/s"}
+    # the columnar entries: ONE Arrow table with every contract's rows in, one table out (tables.py) — no DataFrame per symbol
+    import pyarrow as pa
+    from iv_interpolation_b200 import tables as TB
+    big = pa.Table.from_pandas(pd.concat(frames, ignore_index=True), preserve_index=False)
+    t_t, (tab, _) = best(lambda: TB.interpolate_table(big))
+    out["interpolate_table"] = {"api": "tables.interpolate_table(arrow_table): all contracts in one table, symbol as dictionary codes, "
+                                       "result columns through pinned memory with one synchronisation", "rows_out": len(tab),
+                                "seconds": round(t_t, 4), "rate": len(tab) / t_t, "rate_unit": "minute-rows/s"}
+    t_pt, res_pt = best(lambda: TB.pipeline_table(big, seed=3))
+    out["pipeline_table"] = {"api": "tables.pipeline_table(arrow_table): Task 1 -> bridge -> Task 2 chained on the device, the 5-min candle table back",
+                             "seconds": round(t_pt, 4), "rate": rows / t_pt, "rate_unit": "minute-rows/s (Task-1 output rows)",
+                             "candles_5min": len(res_pt["candles"])}
     fr = {f"c{i}": f for i, f in enumerate(frames)}
     t_p, res_p = best(lambda: PipelineBatch(rng=np.random.RandomState(2), batch_id=1).run(fr), reps=2)
     out["pipeline_batch"] = {"api": "PipelineBatch.run(frames): Task 1 -> bridge -> Task 2 (complete_pipeline.py's order), frames at every stage",

@@ -68,6 +68,24 @@ def candles_to_table(frames: Mapping[str, pd.DataFrame]) -> pa.Table:
     return pa.concat_tables(parts, promote_options="default") if parts else pa.table({})
 
 
+def table_to_db_precision(table: pa.Table, decimals: Mapping[str, tuple]) -> pa.Table:
+    """An Arrow table with every column named in ``decimals`` rounded (half to even) and stored as ``DECIMAL(p, s)`` —
+    NaN becomes NULL, as the reference's INSERT does with ``None`` — and everything else untouched: what the reference's
+    tables would hold (schema.py:20-52, candle_schema.py:22-49), without going through pandas."""
+    import pyarrow.compute as pc
+    for i, name in enumerate(table.column_names):
+        if name not in decimals:
+            continue
+        p, s = decimals[name]
+        col = table.column(i)
+        if not pa.types.is_floating(col.type):
+            continue
+        col = pc.if_else(pc.is_nan(col), pa.scalar(None, pa.float64()), col)
+        col = pc.round(col, ndigits=s, round_mode="half_to_even").cast(pa.decimal128(p, s), safe=False)
+        table = table.set_column(i, name, col)
+    return table
+
+
 def write_parquet(table: pa.Table, path: str) -> None:
     pq.write_table(table, path, compression="zstd")
 

@@ -175,33 +175,76 @@ class InterpolatedToOHLCVConverter:
         return {"base_spread_percent": cfg.get("base_spread_percent", 0.002), "volatility_factor": cfg.get("volatility_factor", 1.5)}
 
     # -- one launch for any number of frames -------------------------------------------------------------------------
+    def _uniform(self, frames: Sequence[pd.DataFrame], ts_col: str) -> bool:
+        """Frames sharing one column layout with a tz-naive datetime64 stamp column, float64 prices/volume and a symbol column:
+        they are concatenated once and the result is handed out as slices of one frame (see hostpath.py)."""
+        live = [f for f in frames if not f.empty]
+        if len(live) < 2:
+            return False
+        first = live[0]
+        cols, dtypes = list(first.columns), list(first.dtypes)
+        if "symbol" not in cols or ts_col not in cols or "volume" not in cols:
+            return False
+        dt = first[ts_col].dtype
+        if not (isinstance(dt, np.dtype) and dt.kind == "M"):
+            return False
+        if any(c in cols and first[c].dtype != np.float64 for c in PRICE_PRIORITY + ["volume"]) or not any(c in cols for c in PRICE_PRIORITY):
+            return False
+        return all(list(f.columns) == cols and list(f.dtypes) == dtypes for f in live[1:])
+
     def _generate_many(self, frames: Sequence[pd.DataFrame], strategy_name: str) -> List[Dict]:
         import torch
 
         from .. import device as D
+        from ..hostpath import d2h_many
 
         strategy = canonical_strategy(strategy_name)
         rs = self._rng if self._rng is not None else np.random
         dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         pipeline = strategy == "pipeline"
         ts_col = "date" if pipeline else "timestamp"
-        bases, vols, lens = [], [], []
-        for f in frames:
-            if f.empty:
-                bases.append(np.zeros(0)); vols.append(np.zeros(0)); lens.append(0)
-                continue
-            if pipeline:                                   # complete_pipeline.py:478: a or b or c on floats (NaN truthy, 0.0 not)
-                u_, m_, i_ = (f[c].to_numpy(dtype=np.float64) for c in PRICE_PRIORITY)
-                b = np.where(u_ != 0, u_, np.where(m_ != 0, m_, i_))
-            else:
-                col = self._select_price_column(f)         # raises ValueError -> caller's except, like :144-148
-                b = f[col].to_numpy(dtype=np.float64)
-            v = f["volume"].to_numpy(dtype=np.float64) if "volume" in f.columns else np.zeros(len(f))   # row.get('volume', 0)
-            bases.append(b); vols.append(v); lens.append(len(f))
+        lens = np.fromiter((len(f) for f in frames), dtype=np.int64, count=len(frames))
         off = np.zeros(len(frames) + 1, np.int64)
         np.cumsum(lens, out=off[1:])
-        base = np.concatenate(bases) if bases else np.zeros(0)
-        vol = np.concatenate(vols) if vols else np.zeros(0)
+        uniform = self._uniform(frames, ts_col)
+        big = None
+        if uniform:
+            big = pd.concat([f for f in frames if not f.empty], ignore_index=True)
+            nz = np.flatnonzero(lens)
+            starts = off[:-1][nz]
+            if pipeline:                                   # complete_pipeline.py:478: a or b or c on floats (NaN truthy, 0.0 not)
+                u_, m_, i_ = (big[c].to_numpy(dtype=np.float64) for c in PRICE_PRIORITY)
+                base = np.where(u_ != 0, u_, np.where(m_ != 0, m_, i_))
+            else:                                          # _select_price_column per frame (:189-207), all frames at once
+                have = [c for c in PRICE_PRIORITY if c in big.columns]
+                counts = np.stack([np.add.reduceat(big[c].notna().to_numpy(dtype=np.int64), starts) for c in have])
+                good = counts > lens[nz][None, :] * 0.8
+                choice = np.where(good.any(axis=0), good.argmax(axis=0), 0)
+                if not good.any(axis=0).all():
+                    logger.warning(f"Using {have[0]} as fallback price source (limited data)")
+                per_row = np.repeat(choice, lens[nz])
+                base = big[have[0]].to_numpy(dtype=np.float64).copy()
+                for k in range(1, len(have)):
+                    sel = per_row == k
+                    if sel.any():
+                        base[sel] = big[have[k]].to_numpy(dtype=np.float64)[sel]
+            vol = big["volume"].to_numpy(dtype=np.float64)
+        else:
+            bases, vols = [], []
+            for f in frames:
+                if f.empty:
+                    bases.append(np.zeros(0)); vols.append(np.zeros(0))
+                    continue
+                if pipeline:
+                    u_, m_, i_ = (f[c].to_numpy(dtype=np.float64) for c in PRICE_PRIORITY)
+                    b = np.where(u_ != 0, u_, np.where(m_ != 0, m_, i_))
+                else:
+                    col = self._select_price_column(f)         # raises ValueError -> caller's except, like :144-148
+                    b = f[col].to_numpy(dtype=np.float64)
+                v = f["volume"].to_numpy(dtype=np.float64) if "volume" in f.columns else np.zeros(len(f))   # row.get('volume', 0)
+                bases.append(b); vols.append(v)
+            base = np.concatenate(bases) if bases else np.zeros(0)
+            vol = np.concatenate(vols) if vols else np.zeros(0)
         with np.errstate(invalid="ignore"):
             ok = ~(np.isnan(base) | (base <= 0))
             need = ok & (np.isnan(vol) | (vol <= 0))
@@ -213,10 +256,14 @@ class InterpolatedToOHLCVConverter:
             raise RuntimeError("bridge plan disagrees with the host's row classification")
         res = D.bridge_ohlcv(d_off, d_base, d_vol, plan, strategy, u=t(u) if len(u) else None, e=t(e), z=t(z) if len(z) else None,
                              **self._spread_kwargs(strategy))
-        out_off = res.out_off.cpu().numpy()
-        row = res.row.cpu().numpy()
-        cols = {k: getattr(res, k).cpu().numpy() for k in ("open", "high", "low", "close", "volume", "source_price")}
-        quality = res.sym_quality.cpu().numpy()
+        names = ("open", "high", "low", "close", "volume", "source_price")
+        host = d2h_many([res.out_off, res.row, res.sym_quality] + [getattr(res, k) for k in names])
+        out_off, row, quality = host[:3]
+        cols = dict(zip(names, host[3:]))
+        if uniform:
+            got = self._assemble_uniform(frames, big, ts_col, out_off, row, cols, quality, pipeline, strategy)
+            if got is not None:
+                return got
         out: List[Dict] = []
         for i, f in enumerate(frames):
             a, b_ = int(out_off[i]), int(out_off[i + 1])
@@ -228,7 +275,7 @@ class InterpolatedToOHLCVConverter:
             if data["symbol"] is None:
                 raise KeyError("symbol")
             data["timestamp"] = pd.to_datetime(f[ts_col]).to_numpy()[src]
-            for k in ("open", "high", "low", "close", "volume", "source_price"):
+            for k in names:
                 data[k] = cols[k][a:b_]
             if not pipeline:
                 data["conversion_method"] = _METHOD_NAME[strategy]
@@ -238,4 +285,35 @@ class InterpolatedToOHLCVConverter:
                 frame = frame.dropna(subset=["open", "high", "low", "close"])
                 frame = frame.sort_values("timestamp")
             out.append({"frame": frame, "quality": self._quality_verdict(int(quality[i]))})
+        return out
+
+    def _assemble_uniform(self, frames, big, ts_col, out_off, row, cols, quality, pipeline, strategy):
+        """All candles as ONE frame, handed out as per-symbol slices.  Returns None (-> per-frame assembly) when the clean-up
+        of :404-418 would actually change something: a NaN among the OHLC columns or stamps out of order inside a symbol."""
+        nf = len(frames)
+        n_out = np.diff(out_off)
+        ts_all = big[ts_col].to_numpy()
+        ts = ts_all[row]
+        if not pipeline:
+            if any(np.isnan(cols[k]).any() for k in ("open", "high", "low", "close")):
+                return None
+            if len(ts) > 1:
+                fid = np.repeat(np.arange(nf), n_out)
+                if ((ts[1:] < ts[:-1]) & (fid[1:] == fid[:-1])).any():
+                    return None
+        data = {"symbol": big["symbol"].array.take(row), "timestamp": ts}
+        for k in ("open", "high", "low", "close", "volume", "source_price"):
+            data[k] = cols[k]
+        if not pipeline:
+            data["conversion_method"] = _METHOD_NAME[strategy]
+        data["is_synthetic"] = True
+        local = np.arange(len(row), dtype=np.int64) - np.repeat(out_off[:-1], n_out)
+        frame = pd.DataFrame(data, index=pd.Index(local, copy=False))
+        out: List[Dict] = []
+        for i in range(nf):
+            a, b_ = int(out_off[i]), int(out_off[i + 1])
+            if b_ == a:
+                out.append({"frame": None, "quality": self._quality_verdict(0)})
+            else:
+                out.append({"frame": frame.iloc[a:b_], "quality": self._quality_verdict(int(quality[i]))})
         return out
