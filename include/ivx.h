@@ -155,14 +155,19 @@ int ivx_interp_exec(int64_t n_sym, const int64_t* src_off, int64_t n_src, const 
  * ivx_bs_greeks the Greeks of greeks.py:24-35 (put rho keeps the reference's sign when
  * reference_put_rho_sign != 0).
  * ------------------------------------------------------------------------------------------- */
+/* With a workspace (ivx_bs_implied_vol_workspace_bytes(n); 4 B per 32 quotes) the solve is two launches: a fast kernel
+ * with no fallback code in it records the warps that hold a quote its straight-line path does not accept, a retry kernel
+ * re-solves those warps with the bracketed loop.  workspace == NULL: one launch, fallback in line.  Same results. */
+int64_t ivx_bs_implied_vol_workspace_bytes(int64_t n);
 int ivx_bs_implied_vol(int64_t n, const double* price, const double* S, const double* K,
                        const double* T, const double* r, const uint8_t* is_call, double* sigma,
-                       int32_t* iters, ivx_stream_t stream);
+                       int32_t* iters, void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
 /* Chain layout (one underlying, one day): quote (t, e, k) sits at price[(t*n_exp + e)*n_strike + k]; the
  * underlying S_t[n_t] and rate r_t[n_t] are per stamp, the strike K_ek[n_exp*n_strike] per contract, the time to
  * expiry T_te[n_t*n_exp] per (stamp, expiry), call/put per contract or per quote: 8-9 B/quote in, 8 B out
  * instead of 41 + 8.  ln S, ln K, rT and
- * e^{-rT} are formed once per stamp / contract / (stamp, expiry) in `workspace`. */
+ * e^{-rT} are formed once per stamp / contract / (stamp, expiry) in `workspace`, which also holds the retry list
+ * (the chain solve is always fast kernel + retry kernel). */
 int64_t ivx_bs_chain_workspace_bytes(int64_t n_t, int64_t n_exp, int64_t n_strike);
 int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
                              const uint8_t* is_call /* [t][e][k] if is_call_per_quote, else [e][k] */,

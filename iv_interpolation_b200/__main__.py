@@ -35,6 +35,10 @@ def _read(path: str, test: bool) -> pa.Table:
     return t
 
 
+def _n_symbols(t: pa.Table) -> int:
+    return len(pc.unique(t["symbol"]))
+
+
 def _summary(title: str, statuses: dict, verbose: bool) -> bool:
     ok = sum(s["status"] == "success" for s in statuses.values())
     err = sum(s["status"] == "error" for s in statuses.values())
@@ -53,7 +57,7 @@ def _summary(title: str, statuses: dict, verbose: bool) -> bool:
 def run_task_1(args) -> bool:
     print("TASK 1: IV Interpolation (Hourly → 1-minute)")
     t = _read(args.inp, args.test)
-    print(f"PROCESSING: Found {pc.count_distinct(t['symbol']).as_py()} symbols")
+    print(f"PROCESSING: Found {_n_symbols(t)} symbols")
     out, st = tables.interpolate_table(t, method=args.method, min_points=args.min_points)
     out = out.append_column("batch_id", pa.array([args.batch_id] * len(out), pa.int64()))
     columnar.write_parquet(columnar.table_to_db_precision(out, columnar.INTERPOLATED_DECIMALS), args.out)
@@ -66,14 +70,14 @@ def run_task_1(args) -> bool:
 def run_data_bridge(args, inp=None, out_path=None) -> bool:
     print("BRIDGE: Converting interpolated data to OHLCV format")
     t = _read(inp or args.inp, args.test and inp is None)
-    n_sym = pc.count_distinct(t["symbol"]).as_py()
+    n_sym = _n_symbols(t)
     if n_sym == 0:
         print("FAILED: No interpolated data found for conversion\nHINT: Run Task 1 first: python -m iv_interpolation_b200 --task interpolation")
         return False
     print(f"CONVERTING: Found {n_sym} symbols with interpolated data")
     out = tables.bridge_table(t, strategy=args.strategy, seed=args.seed)
     columnar.write_parquet(columnar.table_to_db_precision(out, columnar.CANDLE_DECIMALS), out_path or args.out)
-    done = pc.count_distinct(out["symbol"]).as_py()
+    done = _n_symbols(out)
     print(f"\nBRIDGE COMPLETE:\n   Success: {done}\n   Errors: 0\n   Skipped: {n_sym - done}")
     print("✅ Data bridge successful - ready for Task 2" if done else "❌ No symbols converted successfully")
     return done > 0
@@ -83,7 +87,7 @@ def run_task_2(args) -> bool:
     """The function reference main.py:553-587 calls and never defines."""
     print(f"TASK 2: Candle Reconstruction (1-minute → {args.frequency})")
     t = _read(args.inp, args.test)
-    n_sym = pc.count_distinct(t["symbol"]).as_py()
+    n_sym = _n_symbols(t)
     if n_sym == 0:
         print("FAILED: No symbols with minute candle data found")
         return False

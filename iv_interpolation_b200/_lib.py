@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libivx.so")
+LIB_PATH = os.environ.get("IVX_LIB_PATH") or os.path.join(_HERE, "csrc", "libivx.so")   # IVX_LIB_PATH: profiling builds
 
 # error / status codes (include/ivx.h)
 IVX_OK = 0
@@ -48,7 +48,8 @@ SIGNATURES = {
                                   _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_interp_exec": (C.c_int, [_i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _pp, _pp, _pp, _p, _p, _p,
                                   _p, _p, _i64, _p]),
-    "ivx_bs_implied_vol": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ivx_bs_implied_vol_workspace_bytes": (_i64, [_i64]),
+    "ivx_bs_implied_vol": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_bs_price": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ivx_bs_greeks": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "ivx_spline_workspace_bytes": (_i64, [_i64, _i64]),

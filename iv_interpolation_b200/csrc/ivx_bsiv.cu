@@ -14,9 +14,10 @@
 //   * beta >= b(s_c): root in the concave branch — solve b(s) = beta directly.
 // The kernel is bound by instruction issue and the fp64 pipe together (ncu: profiles/README.md), so it is built to
 // execute as few instructions as possible, in three phases:
-//   1. an fp32 PRE-SOLVE (FP32 pipe + raw MUFU ops, runs in the shadow of other warps' fp64 work): the closed-form
-//      guess (tangent and log-match at the inflection point, blended) followed by one third-order Householder step in
-//      single precision — leaves s to ~1e-6 relative on all but a few 1e-4 of the quotes;
+//   1. an fp32 PRE-SOLVE (FP32 pipe + raw MUFU ops, runs in the shadow of other warps' fp64 work): a TABLE guess — log2 s is
+//      asymptotically linear in (log2 sqrt(2|x|), log2(-ln(beta e^{-x/2}))) in both the wing and the at-the-money regime,
+//      so a 76 x 79 table with bilinear interpolation is ~1e-3 accurate (tools/gen_iv_guess_table.py) — followed by one
+//      third-order Householder step in single precision: s to fp32 precision on all but a few 1e-5 of the quotes;
 //   2. an fp64 FAST PATH, straight-line: ONE Halley step on b(s) - beta with b written so that the same expression
 //      holds on both sides of the inflection point (solve_quote); accepted when the step is below 1e-4 s — after such
 //      a step the remaining error is ~1e-12 s;
@@ -48,14 +49,12 @@ __constant__ double EXP_C[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39
                                  1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
                                  1.0 / 6.0,          0.5,               1.0,              1.0};
 // Reciprocal and reciprocal square root of a NORMAL a (1e-300 < a < 1e300) without the IEEE special-case tail of the
-// compiler's division: the 20-bit hardware seed (MUFU.RCP64H / RSQ64H) and two Newton steps (2^-20 -> 2^-40 -> 2^-80).
+// compiler's division: the 20-bit hardware seed (MUFU.RCP64H / RSQ64H) and ONE third-order step (2^-20 -> 2^-60).
 __device__ __forceinline__ double rcp_fast(double a) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double e = fma(-a, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-a, y, 1.0);
-  return fma(y, e, y);
+  const double e = fma(-a, y, 1.0);                  // 2^-20
+  return fma(y, fma(e, e, e), y);                    // y (1 + e + e^2): one cubic step, 2^-60
 }
 __device__ __forceinline__ double rcp_fast1(double a) {   // one Newton step: 2^-40
   double y;
@@ -65,10 +64,8 @@ __device__ __forceinline__ double rcp_fast1(double a) {   // one Newton step: 2^
 __device__ __forceinline__ double rsqrt_fast(double a) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double e = fma(-(a * y), y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-(a * y), y, 1.0);
-  return fma(0.5 * y, fma(0.375 * e, e, e), y);      // y (1 + e/2 + 3 e^2/8)
+  const double e = fma(-(a * y), y, 1.0);            // 2^-20
+  return fma(y, e * fma(0.375, e, 0.5), y);          // y (1 + e/2 + 3 e^2/8): one cubic step, 2^-60
 }
 // positive, finite and normal: high word in [0x00100000, 0x7ff00000)
 __device__ __forceinline__ bool pos_normal(double v) { return (unsigned)(__double2hiint(v) - 0x00100000) < 0x7fe00000u; }
@@ -220,36 +217,26 @@ __device__ __forceinline__ float erfcx_pos_f(float x) {
 }
 
 // ---- phase 1: single precision -------------------------------------------------------------------------
-// x <= 0, 0 < beta < e^{x/2}; lnbeta only used (and only valid) when `lower`.  Returns the guess for s.
-__device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta, float ex2, float iex2, float s_c,
-                                              float b_c, bool lower) {
+#include "ivx_bsiv_guess.inc"
+// log2 s by bilinear interpolation in P = log2 sqrt(-2x), V = log2(-ln(beta e^{-x/2})) (clamped to the table: x = 0 gives
+// P = -inf -> first row, which IS the at-the-money limit).  NaN coordinates clamp to 0 (fmaxf returns the other operand).
+__device__ __forceinline__ float guess_table(float x, float lnbeta) {
+  const float P = 0.5f * f_lg2(-2.0f * x);
+  const float V = f_lg2(fmaf(0.5f, x, -lnbeta));
+  const float fp = fminf(fmaxf((P - GUESS_P0) * GUESS_CELLS, 0.0f), (float)(GUESS_NP - 1) - 0.001f);
+  const float fv = fminf(fmaxf((V - GUESS_V0) * GUESS_CELLS, 0.0f), (float)(GUESS_NV - 1) - 0.001f);
+  const int i = (int)fp, j = (int)fv;
+  const float wp = fp - (float)i, wv = fv - (float)j;
+  const float* t = GUESS_TAB + (i * GUESS_NV + j);
+  const float t00 = __ldg(t), t01 = __ldg(t + 1), t10 = __ldg(t + GUESS_NV), t11 = __ldg(t + GUESS_NV + 1);
+  const float a0 = fmaf(wv, t01 - t00, t00), a1 = fmaf(wv, t11 - t10, t10);
+  return f_ex2(fmaf(wp, a1 - a0, a0));
+}
+
+// x <= 0, 0 < beta < e^{x/2}; s = the table guess; `lower`: the root sits below the inflection point sqrt(2|x|) (objective
+// ln b there, b above).  Returns s after one Householder step.
+__device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta, float ex2, float s, bool lower) {
   const float kInvSqrt2 = 0.70710678f, kSqrt2Pi = 2.50662827f;
-  float s;
-  const float s_tan = s_c + (beta - b_c) * kSqrt2Pi * iex2;   // tangent at the inflection point: b'(s_c) = e^{x/2} / sqrt(2 pi)
-  if (lower) {
-    // two one-sided guesses: matching ln b ~ C - x^2/(2 s^2) at s_c undershoots (it ignores the s^3 prefactor),
-    //   s_lo = |x| / sqrt(2 ln(b_c/beta) + |x|/2),
-    // the tangent at s_c overshoots (b is convex below s_c).  The root sits at s_lo^(1-w) s_tan^w with w a tight
-    // function of ln(beta/b_c) alone (fitted on 1e6 quotes: |w - fit| < 0.04 rms) -> 2 % median, 12 % p99 error.
-    const float lr = lnbeta - f_log(b_c);
-    const float s_lo = -x * f_rsq(-2.0f * lr - 0.5f * x);
-    s = s_lo;
-    if (s_tan > s_lo && s_lo > 0.0f) {
-      const float z = 4.0f * f_rcp(4.0f - lr);
-      float w = 16.8094143f;
-      w = fmaf(w, z, -43.9016092f);
-      w = fmaf(w, z, 37.3072543f);
-      w = fmaf(w, z, -10.9011223f);
-      w = fmaf(w, z, 1.71174781f);
-      w = fmaf(w, z, -0.0284488434f);
-      w = fminf(fmaxf(w, 0.0f), 1.0f);
-      s = s_lo * f_ex2(w * f_lg2(s_tan * f_rcp(s_lo)));
-    }
-  } else {
-    s = s_tan;                                       // Newton step from the inflection point
-  }
-  s = fminf(s, (float)S_MAX);
-  if (!(s > 0.0f)) s = 1.0f;                       // no usable guess: the fp64 fallback sorts it out
 #pragma unroll
   for (int it = 0; it < PRE_ITERS; ++it) {
     const float inv_s = f_rcp(s);
@@ -322,7 +309,11 @@ __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1,
   const double t1 = (q1 - 4.0) * (ra * a2), t2 = (q2 - 4.0) * (ra * a1);
   double p1 = ERFCX_C[0], p2 = ERFCX_C[0];
 #pragma unroll
+#ifdef IVX_EXP_DEG12
+  for (int k = 9; k < 21; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }
+#else
   for (int k = 1; k < 21; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }   // operands straight from the constant bank
+#endif
   e1 = p1 * (rb * b2);
   e2 = p2 * (rb * b1);
 }
@@ -397,8 +388,11 @@ __device__ __noinline__ double polish_f64(double x, double beta, double inv_beta
 // One quote, given Kd = K e^{-rT}.  `ok` says the inputs are finite and positive; every lane of the warp must call
 // (the polish loop votes), lanes that are not ok solve a dummy alongside.  PRE_X: x_pre = ln(S/Kd) was formed
 // from precomputed logarithms (chain layout) and the fp64 log is skipped.
-template <bool PRE_X>
-__device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double kd, double t_, bool call, double x_pre,
+// DEFER: a quote the fast path does not accept is NOT polished here — the function returns true, the caller records the
+// warp, and the retry kernel (the same function with DEFER = false) re-solves the recorded warps.  The fast kernels then
+// contain no call, no loop and no vote.
+template <bool PRE_X, bool DEFER>
+__device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double kd, double t_, bool call, double x_pre,
                                             double& sigma_out, int& iters_out) {
   // ok: S, Kd and T are positive normal numbers (no NaN below).  mx/mn = max/min(S, Kd); the in-the-money side is the
   // call when S > Kd, the put when S < Kd, and its intrinsic value is mx - mn.
@@ -423,16 +417,17 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   if (!ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9: solved alongside, result dropped
 
   const float xf = (float)x;
-  const float ex2f = (float)ex2, iex2f = f_rcp(ex2f);
-  const float s_cf = f_sqrt(-2.0f * xf);
-  // b(s_c) = (e^{x/2} - e^{-x/2} erfc(sqrt|x|)) / 2 and erfc(z) = erfcx(z) e^{-z^2} with e^{-|x|} = (e^{x/2})^2
-  const float b_cf = 0.5f * ex2f * (1.0f - erfcx_pos_f(s_cf * 0.70710678f));
-  const bool lower = beta < (double)b_cf;
   // ln beta to single precision from the exponent and the leading mantissa bits (beta may be far below FLT_MIN)
   const int bhi = __double2hiint(beta);
   const float lnbeta_f = fmaf((float)(((bhi >> 20) & 0x7ff) - 1023), 0.69314718f,
                               f_log((float)__hiloint2double((bhi & 0x000fffff) | 0x3ff00000, __double2loint(beta))));
-  float s0 = presolve_f32(xf, (float)beta, lnbeta_f, ex2f, iex2f, s_cf, b_cf, lower);
+  const float s_tab = guess_table(xf, lnbeta_f);
+  const bool lower = s_tab * s_tab < -2.0f * xf;                           // below the inflection point s_c = sqrt(2|x|)
+#ifdef IVX_EXP_NOPRE
+  float s0 = s_tab;
+#else
+  float s0 = presolve_f32(xf, (float)beta, lnbeta_f, (float)ex2, s_tab, lower);
+#endif
   double s = (double)s0;
   if (!(s > 0.0 && s < S_MAX)) s = 1.0;   // fp32 range exhausted: the bracketed fp64 loop takes it from anywhere
   // ---- fast path: ONE fp64 Halley step on b(s) - beta, the same expression on both sides of the inflection point:
@@ -458,9 +453,12 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
     const double sn = s + step;
     // s >= 1e-30 keeps every argument of the pair finite; e <= 700 keeps E normal; den ~ E keeps the step a Halley step
     accept = (fabs(step) <= ACCEPT_STEP * sn) && (s >= 1e-30) && (e <= 700.0) && (den > 0.5 * E);
+#ifdef IVX_EXP_FORCE
+    accept = true;
+#endif
     if (accept) s = sn;
   }
-  if (!accept) {
+  if (!DEFER && !accept) {
     double inv_beta = 1.0, lnbeta_off = 0.0;
     if (beta < 1e-290) lnbeta_off = log(beta); else inv_beta = 1.0 / beta;
     int it2 = 0;
@@ -469,31 +467,66 @@ __device__ __forceinline__ void solve_quote(bool ok, double p, double s_, double
   }
   sigma_out = ok ? s * rsqrt_fast(t_) : qnan();
   iters_out = ok ? it : 0;
+  return DEFER && ok && !accept;
 }
 
-__global__ void __launch_bounds__(256, 5) k_bs_implied_vol(int64_t n, const double* __restrict__ price,
+// warps with a deferred quote: one entry each (the lane-0 atomic is rare: realistic tapes defer ~0 % of the quotes)
+__device__ __forceinline__ void record_deferred(bool deferred, uint32_t warp_id, uint32_t* __restrict__ list, uint32_t* __restrict__ counter) {
+  if (__any_sync(IVX_FULL_MASK, deferred) && (threadIdx.x & 31) == 0) list[atomicAdd(counter, 1u)] = warp_id;
+}
+
+// One launch covers at most 2^31 quotes (the wrapper offsets the pointers): a 32-bit quote index keeps the address
+// arithmetic of the six loads to one IMAD.WIDE each.  ITERS = false: the iteration counts are not wanted (the hot path).
+template <bool ITERS, bool DEFER>
+__global__ void __launch_bounds__(256, 5) k_bs_implied_vol(uint32_t n, const double* __restrict__ price,
                                                         const double* __restrict__ S, const double* __restrict__ K,
                                                         const double* __restrict__ T, const double* __restrict__ r,
                                                         const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
-                                                        int32_t* __restrict__ iters) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  // every lane takes part in the convergence vote; lanes past the end carry an already-solved dummy
+                                                        int32_t* __restrict__ iters, uint32_t* __restrict__ list,
+                                                        uint32_t* __restrict__ counter) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   const bool inr = i < n;
-  double p = 0, s_ = 1, k_ = 1, t_ = 1, r_ = 0;
-  bool call = true;
-  if (inr) {
-    p = ld_stream(price + i); s_ = ld_stream(S + i); k_ = ld_stream(K + i);
-    t_ = ld_stream(T + i); r_ = ld_stream(r + i); call = is_call[i] != 0;
-  }
+  const uint32_t j = inr ? i : 0u;                   // n >= 1: lanes past the end re-read quote 0 and drop the result
+  const double p = ld_stream(price + j), s_ = ld_stream(S + j), k_ = ld_stream(K + j);
+  const double t_ = ld_stream(T + j), r_ = ld_stream(r + j);
+  const bool call = is_call[j] != 0;
   const double kd = k_ * exp_neg_small(r_ * t_);
   // S, K, T and Kd positive, finite and normal (a NaN or infinite r shows in Kd); the price is checked against its bounds
-  const bool ok = inr && pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+  const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
   double out;
   int it;
-  solve_quote<false>(ok, p, s_, kd, t_, call, 0.0, out, it);
+  const bool deferred = solve_quote<false, DEFER>(ok, p, s_, kd, t_, call, 0.0, out, it);
   if (inr) {
     st_stream(sigma + i, out);
-    if (iters) st_stream(iters + i, it);
+    if (ITERS) st_stream(iters + i, it);
+  }
+  if (DEFER) record_deferred(deferred && inr, i >> 5, list, counter);
+}
+
+// the recorded warps again, with the bracketed loop in line: one warp per entry, grid-stride
+template <bool ITERS>
+__global__ void __launch_bounds__(256) k_bs_implied_vol_retry(uint32_t n, const double* __restrict__ price,
+                                                              const double* __restrict__ S, const double* __restrict__ K,
+                                                              const double* __restrict__ T, const double* __restrict__ r,
+                                                              const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
+                                                              int32_t* __restrict__ iters, const uint32_t* __restrict__ list,
+                                                              const uint32_t* __restrict__ counter) {
+  const uint32_t count = *counter;
+  for (uint32_t e = blockIdx.x * 8u + (threadIdx.x >> 5); e < count; e += gridDim.x * 8u) {
+    const uint32_t i = list[e] * 32u + (threadIdx.x & 31u);
+    const bool inr = i < n;
+    const uint32_t j = inr ? i : 0u;
+    const double p = price[j], s_ = S[j], k_ = K[j], t_ = T[j], r_ = r[j];
+    const bool call = is_call[j] != 0;
+    const double kd = k_ * exp_neg_small(r_ * t_);
+    const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+    double out;
+    int it;
+    solve_quote<false, false>(ok, p, s_, kd, t_, call, 0.0, out, it);
+    if (inr) {
+      sigma[i] = out;
+      if (ITERS) iters[i] = it;
+    }
   }
 }
 
@@ -518,15 +551,13 @@ __global__ void __launch_bounds__(256) k_chain_terms(int64_t n_t, int64_t n_exp,
   }
 }
 
-// grid: x over the n_exp*n_strike contracts of one stamp, y over stamps
-__global__ void __launch_bounds__(256, 5) k_bs_implied_vol_chain(int64_t t0, int32_t n_exp, int32_t n_strike, int64_t n_t,
-                                                              const double* __restrict__ price, const uint8_t* __restrict__ is_call,
-                                                              int32_t call_per_quote, const double* __restrict__ S_t, const double* __restrict__ K_ek,
-                                                              const double* __restrict__ T_te, const double* __restrict__ terms,
-                                                              double* __restrict__ sigma, int32_t* __restrict__ iters) {
+// one quote of the chain layout: loads + solve; (j, t) = contract and stamp
+template <bool DEFER>
+__device__ __forceinline__ bool chain_quote(int32_t j, int64_t t, int32_t n_exp, int32_t n_strike, int64_t n_t, const double* __restrict__ price,
+                                            const uint8_t* __restrict__ is_call, int32_t call_per_quote, const double* __restrict__ S_t,
+                                            const double* __restrict__ K_ek, const double* __restrict__ T_te, const double* __restrict__ terms,
+                                            double* __restrict__ sigma, int32_t* __restrict__ iters) {
   const int32_t n_ek = n_exp * n_strike;
-  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;        // contract (e, k)
-  const int64_t t = t0 + blockIdx.y;
   const bool inr = j < n_ek;
   const int64_t i = t * n_ek + j;
   double p = 0, s_ = 1, k_ = 1, t_ = 1, disc = 1, xi = 0;
@@ -546,10 +577,39 @@ __global__ void __launch_bounds__(256, 5) k_bs_implied_vol_chain(int64_t t0, int
   const bool ok = inr && pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd) && isfinite(xi);
   double out;
   int it;
-  solve_quote<true>(ok, p, s_, kd, t_, call, xi, out, it);
+  const bool deferred = solve_quote<true, DEFER>(ok, p, s_, kd, t_, call, xi, out, it);
   if (inr) {
     st_stream(sigma + i, out);
     if (iters) st_stream(iters + i, it);
+  }
+  return deferred;
+}
+
+// grid: x over the n_exp*n_strike contracts of one stamp, y over stamps
+template <bool DEFER>
+__global__ void __launch_bounds__(256, 5) k_bs_implied_vol_chain(int64_t t0, int32_t n_exp, int32_t n_strike, int64_t n_t,
+                                                              const double* __restrict__ price, const uint8_t* __restrict__ is_call,
+                                                              int32_t call_per_quote, const double* __restrict__ S_t, const double* __restrict__ K_ek,
+                                                              const double* __restrict__ T_te, const double* __restrict__ terms,
+                                                              double* __restrict__ sigma, int32_t* __restrict__ iters,
+                                                              uint32_t* __restrict__ list, uint32_t* __restrict__ counter) {
+  const int32_t j = blockIdx.x * 256 + threadIdx.x;               // contract (e, k)
+  const bool deferred = chain_quote<DEFER>(j, t0 + blockIdx.y, n_exp, n_strike, n_t, price, is_call, call_per_quote, S_t, K_ek, T_te, terms, sigma, iters);
+  if (DEFER) record_deferred(deferred, (blockIdx.y * gridDim.x + blockIdx.x) * 8u + (threadIdx.x >> 5), list, counter);
+}
+
+__global__ void __launch_bounds__(256) k_bs_implied_vol_chain_retry(int64_t t0, uint32_t gx, int32_t n_exp, int32_t n_strike, int64_t n_t,
+                                                                    const double* __restrict__ price, const uint8_t* __restrict__ is_call,
+                                                                    int32_t call_per_quote, const double* __restrict__ S_t, const double* __restrict__ K_ek,
+                                                                    const double* __restrict__ T_te, const double* __restrict__ terms,
+                                                                    double* __restrict__ sigma, int32_t* __restrict__ iters,
+                                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ counter) {
+  const uint32_t count = *counter;
+  for (uint32_t e = blockIdx.x * 8u + (threadIdx.x >> 5); e < count; e += gridDim.x * 8u) {
+    const uint32_t w = list[e];
+    const uint32_t blk = w >> 3;                                   // (y * gx + x)
+    const int32_t j = (int32_t)((blk % gx) * 256u + (w & 7u) * 32u + (threadIdx.x & 31u));
+    chain_quote<false>(j, t0 + blk / gx, n_exp, n_strike, n_t, price, is_call, call_per_quote, S_t, K_ek, T_te, terms, sigma, iters);
   }
 }
 
@@ -629,20 +689,55 @@ __global__ void __launch_bounds__(256) k_probe_fp64(int32_t iters, double* sink)
 
 using namespace ivx;
 
+// workspace of the two-kernel form: a counter (256 B) + one uint32 per warp of the largest launch
+extern "C" int64_t ivx_bs_implied_vol_workspace_bytes(int64_t n) {
+  if (n < 0) return -1;
+  const int64_t CH = (int64_t)1 << 31;
+  const int64_t m = n < CH ? n : CH;
+  return 256 + 4 * ((m + 31) / 32 + 8);
+}
+
 extern "C" int ivx_bs_implied_vol(int64_t n, const double* price, const double* S, const double* K, const double* T,
                                   const double* r, const uint8_t* is_call, double* sigma, int32_t* iters,
-                                  ivx_stream_t stream) {
+                                  void* workspace, int64_t workspace_bytes, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n >= 0, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol: negative n");
   if (n == 0) return IVX_OK;
   IVX_REQUIRE(price && S && K && T && r && is_call && sigma, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol: null pointer");
-  k_bs_implied_vol<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, price, S, K, T, r, is_call, sigma, iters);
-  IVX_LAUNCH_CHECK("k_bs_implied_vol");
+  IVX_REQUIRE(!workspace || workspace_bytes >= ivx_bs_implied_vol_workspace_bytes(n), IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol: workspace too small");
+  uint32_t* counter = (uint32_t*)workspace;
+  uint32_t* list = workspace ? (uint32_t*)((char*)workspace + 256) : nullptr;
+  const int64_t CH = (int64_t)1 << 31;
+  for (int64_t o = 0; o < n; o += CH) {
+    const uint32_t m = (uint32_t)(n - o < CH ? n - o : CH);
+    const unsigned blocks = (unsigned)(((int64_t)m + 255) / 256);
+    int32_t* it = iters ? iters + o : nullptr;
+#define IVX_IV_ARGS m, price + o, S + o, K + o, T + o, r + o, is_call + o, sigma + o, it, list, counter
+    if (workspace) {
+      // fast kernel (no fallback code in it) + retry kernel over the warps it recorded; stream order makes the pair one operation
+      IVX_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
+      if (iters) k_bs_implied_vol<true, true><<<blocks, 256, 0, stream>>>(IVX_IV_ARGS);
+      else k_bs_implied_vol<false, true><<<blocks, 256, 0, stream>>>(IVX_IV_ARGS);
+      IVX_LAUNCH_CHECK("k_bs_implied_vol");
+      const unsigned rb = (unsigned)(sm_count() * 2);
+      if (iters) k_bs_implied_vol_retry<true><<<rb, 256, 0, stream>>>(IVX_IV_ARGS);
+      else k_bs_implied_vol_retry<false><<<rb, 256, 0, stream>>>(IVX_IV_ARGS);
+      IVX_LAUNCH_CHECK("k_bs_implied_vol_retry");
+    } else {
+      if (iters) k_bs_implied_vol<true, false><<<blocks, 256, 0, stream>>>(IVX_IV_ARGS);
+      else k_bs_implied_vol<false, false><<<blocks, 256, 0, stream>>>(IVX_IV_ARGS);
+      IVX_LAUNCH_CHECK("k_bs_implied_vol");
+    }
+#undef IVX_IV_ARGS
+  }
   return IVX_OK;
 }
 
+// terms (8 B each: n_t + n_ek + 2 n_te) + counter + one uint32 per warp of a launch (at most 65535 stamps per launch)
 extern "C" int64_t ivx_bs_chain_workspace_bytes(int64_t n_t, int64_t n_exp, int64_t n_strike) {
   if (n_t < 0 || n_exp < 0 || n_strike < 0) return -1;
-  return 8 * (n_t + n_exp * n_strike + 2 * n_t * n_exp) + 256;
+  const int64_t gx = (n_exp * n_strike + 255) / 256, gy = n_t < 65535 ? n_t : 65535;
+  return 8 * (n_t + n_exp * n_strike + 2 * n_t * n_exp) + 256 + 256 + 4 * (gx * gy * 8 + 8);
 }
 
 extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
@@ -653,19 +748,26 @@ extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_st
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_t >= 0 && n_exp >= 0 && n_strike >= 0, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_chain: negative size");
   if (n_t == 0 || n_exp == 0 || n_strike == 0) return IVX_OK;
-  IVX_REQUIRE(n_exp * n_strike < ((int64_t)1 << 30), IVX_ERR_TOO_LARGE, "ivx_bs_implied_vol_chain: more than 2^30 contracts per stamp");
+  IVX_REQUIRE(n_exp * n_strike < ((int64_t)1 << 24), IVX_ERR_TOO_LARGE, "ivx_bs_implied_vol_chain: more than 2^24 contracts per stamp");
   IVX_REQUIRE(price && is_call && S_t && K_ek && T_te && r_t && sigma && workspace, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_chain: null pointer");
   IVX_REQUIRE(workspace_bytes >= ivx_bs_chain_workspace_bytes(n_t, n_exp, n_strike), IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_chain: workspace too small");
   double* terms = (double*)workspace;
   const int64_t n_terms = n_t + n_exp * n_strike + n_t * n_exp;
+  const int64_t terms_bytes = align_up(8 * (n_terms + n_t * n_exp), 256);
+  uint32_t* counter = (uint32_t*)((char*)workspace + terms_bytes);
+  uint32_t* list = counter + 64;
   k_chain_terms<<<(unsigned)((n_terms + 255) / 256), 256, 0, stream>>>(n_t, n_exp, n_strike, S_t, K_ek, T_te, r_t, terms);
   IVX_LAUNCH_CHECK("k_chain_terms");
   const unsigned gx = (unsigned)((n_exp * n_strike + 255) / 256);
   for (int64_t t0 = 0; t0 < n_t; t0 += 65535) {
     const unsigned gy = (unsigned)(n_t - t0 < 65535 ? n_t - t0 : 65535);
-    k_bs_implied_vol_chain<<<dim3(gx, gy), 256, 0, stream>>>(t0, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, is_call_per_quote, S_t, K_ek,
-                                                             T_te, terms, sigma, iters);
+    IVX_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
+    k_bs_implied_vol_chain<true><<<dim3(gx, gy), 256, 0, stream>>>(t0, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, is_call_per_quote, S_t, K_ek,
+                                                                   T_te, terms, sigma, iters, list, counter);
     IVX_LAUNCH_CHECK("k_bs_implied_vol_chain");
+    k_bs_implied_vol_chain_retry<<<(unsigned)(sm_count() * 2), 256, 0, stream>>>(t0, gx, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, is_call_per_quote,
+                                                                                 S_t, K_ek, T_te, terms, sigma, iters, list, counter);
+    IVX_LAUNCH_CHECK("k_bs_implied_vol_chain_retry");
   }
   return IVX_OK;
 }

@@ -20,8 +20,8 @@ _LAUNCHES = 0     # kernels of ours enqueued since the last reset (bench.py repo
 # kernels each entry point enqueues (memsets are not kernels of ours and are not counted)
 _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
-    "bs_implied_vol": 1, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
-    "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 2, "spline_ladder_factor": 1,
+    "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
+    "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 3, "spline_ladder_factor": 1,
     "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
@@ -311,7 +311,10 @@ def interp_linear_ffill(src_off: torch.Tensor, ts: torch.Tensor, interp_cols: Se
 # ------------------------------------------------------------------------------------------------
 # Kernel C
 # ------------------------------------------------------------------------------------------------
-def bs_implied_vol(price, S, K, T, r, is_call, *, want_iters: bool = False, out: Optional[torch.Tensor] = None):
+def bs_implied_vol(price, S, K, T, r, is_call, *, want_iters: bool = False, out: Optional[torch.Tensor] = None,
+                   workspace: Optional[torch.Tensor] = None, two_kernels: bool = True):
+    """``two_kernels``: fast kernel + retry kernel over the warps it recorded (needs a small workspace, allocated here unless
+    passed); False: one launch with the fallback in line.  Same results."""
     n = price.numel()
     for t in (price, S, K, T, r):
         _req(t, torch.float64, "quote column")
@@ -320,9 +323,13 @@ def bs_implied_vol(price, S, K, T, r, is_call, *, want_iters: bool = False, out:
     _req(is_call, torch.uint8, "is_call")
     sigma = out if out is not None else _empty(n, torch.float64, price)
     iters = _empty(n, torch.int32, price) if want_iters else None
+    ws, wsb = None, 0
+    if two_kernels and n:
+        wsb = lib().ivx_bs_implied_vol_workspace_bytes(n)
+        ws = workspace if workspace is not None and workspace.numel() >= wsb else _empty(wsb, torch.uint8, price)
     check(lib().ivx_bs_implied_vol(n, _ptr(price), _ptr(S), _ptr(K), _ptr(T), _ptr(r), _ptr(is_call), _ptr(sigma),
-                                   _ptr(iters), _stream()), "ivx_bs_implied_vol")
-    _count("bs_implied_vol")
+                                   _ptr(iters), _ptr(ws), wsb, _stream()), "ivx_bs_implied_vol")
+    _count("bs_implied_vol_2k" if ws is not None else "bs_implied_vol")
     return (sigma, iters) if want_iters else sigma
 
 

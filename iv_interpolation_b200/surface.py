@@ -137,6 +137,7 @@ class SurfacePipeline:
         # chain layout: every slice (t, e) reads its abscissae from the shared ladder of expiry e
         self._x_off = None
         self._chain_ws = None
+        self._iv_ws = None
         self._lu_key = None
         self._q_lu = None
         self._q_lu_key = None
@@ -175,7 +176,10 @@ class SurfacePipeline:
             D.bs_implied_vol_chain(q.price, q.is_call, q.S_t, q.K_ek, q.T_te, q.r_t, n_t=sp.n_t, n_exp=sp.n_exp,
                                    n_strike=sp.n_strike, out=self.iv, workspace=self._chain_ws)
         else:
-            D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv)
+            if self._iv_ws is None:
+                from ._lib import lib
+                self._iv_ws = torch.empty(lib().ivx_bs_implied_vol_workspace_bytes(sp.n_quotes), dtype=torch.uint8, device=self.device)
+            D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv, workspace=self._iv_ws)
         mark("implied_vol", 1)
         mark("spline_strike", 0)
         # knots of slice (t, e): x = the quoted strikes, read in place from the K column / the expiry's ladder

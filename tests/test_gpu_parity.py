@@ -684,3 +684,29 @@ def test_production_batch_streams_large_symbols_in_chunks(dev):
     assert summary["success_count"] == 5 and summary["skip_count"] == 2
     mirrored = ProductionInterpolationBatch(batch_id=9, mirror_reference_status=True).run({"big0": frames["big0"]})[1][0]
     assert mirrored["status"] == "error" and "has no len()" in mirrored["error"]
+
+
+def test_implied_vol_two_kernel_form_equals_the_one_launch_form(dev):
+    """ivx_bs_implied_vol with a workspace (fast kernel + retry kernel over the recorded warps) and without (fallback in line):
+    bit-identical sigmas and iteration counts on a tape that sends many quotes to the fallback, ragged length included."""
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(77)
+    n = 200_003
+    S = np.full(n, 4500.0) * np.exp(rng.normal(0, 0.02, n))
+    K = S * np.exp(rng.uniform(-3.0, 3.0, n) * (rng.random(n) < 0.3))
+    T = np.exp(rng.uniform(np.log(1e-4), np.log(30.0), n))
+    r = rng.uniform(-0.02, 0.1, n)
+    sigma = np.exp(rng.uniform(np.log(0.01), np.log(5.0), n))
+    is_call = (rng.random(n) < 0.5).astype(np.uint8)
+    price = O.bs_price(S, K, T, r, sigma, is_call)
+    price[::97] = np.nan
+    price[5::113] *= 3.0                                                   # many outside the no-arbitrage bounds
+    args = [_t(a, dev) for a in (price, S, K, T, r)] + [_t(is_call, dev)]
+    s1, i1 = D.bs_implied_vol(*args, want_iters=True, two_kernels=False)
+    s2, i2 = D.bs_implied_vol(*args, want_iters=True, two_kernels=True)
+    s3 = D.bs_implied_vol(*args, two_kernels=True)
+    a, b, c = s1.cpu().numpy(), s2.cpu().numpy(), s3.cpu().numpy()
+    assert np.array_equal(a, b, equal_nan=True) and np.array_equal(a, c, equal_nan=True)
+    assert np.array_equal(i1.cpu().numpy(), i2.cpu().numpy())
+    it = i1.cpu().numpy()
+    assert (it > 1).sum() > 100, "the tape must exercise the fallback"

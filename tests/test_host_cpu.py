@@ -58,7 +58,7 @@ def test_host_floor_div_matches_python():
 def test_argument_errors_come_back_as_codes_not_crashes():
     from iv_interpolation_b200 import _lib
     L = _lib.lib()
-    rc = L.ivx_bs_implied_vol(-1, None, None, None, None, None, None, None, None, None)
+    rc = L.ivx_bs_implied_vol(-1, None, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"negative" in L.ivx_last_error_string()
     rc = L.ivx_ohlcv_reduce(1, None, 4, None, None, None, None, None, None, None, 0, 5, 1, 0, None, None, None, None, None,
                             None, None, None, None, None, None, None, None, None, None, 0, None)
