@@ -223,6 +223,25 @@ int ivx_spline_fit_eval_ladder_verify(int64_t n_slices, const int64_t* knot_off,
                                       const double* x, const double* x_own, const double* lu_cp, const double* lu_inv,
                                       const double* lu_ih, const double* y, int64_t n_q, const double* xq,
                                       int32_t extrap, double* yq, ivx_stream_t stream);
+/* Shared ladders as a BANDED operator (ivx_spline_band.cu).  For a fixed ladder and a fixed grid, fit + evaluate is a fixed
+ * linear map y -> yq whose rows decay geometrically away from the grid point's bracket: ivx_spline_band_build tabulates,
+ * per (ladder, grid point), the 48 knot weights that matter at 1e-12 and where they start (band_w: ivx_spline_band_len
+ * doubles, band_k0: n_ladders*n_q int32, -1 = the point evaluates to NaN), and CHECKS the band against a full solve of
+ * two probe vectors — ladder_ok[l] = 0 (fewer than 48 or more than 2048 knots, not increasing, band misses 2e-12)
+ * sends that ladder's slices to the exact solve.  ivx_spline_fit_eval_banded evaluates every slice as n_q (<= 512) dot
+ * products out of shared memory; slices with a non-finite y, another knot count than their ladder, or (x_own != NULL) abscissae
+ * that differ from the ladder's in any bit are appended to fb_list (int32[n_slices], count in *fb_count) and solved by
+ * the exact scan kernel right behind, in the same stream, with the ladder tables lu_* of ivx_spline_ladder_factor.
+ * order / lad_slice_off: the slices grouped by ladder (CSR); max_slices_per_ladder sizes the grid. */
+int64_t ivx_spline_band_len(int64_t n_ladders, int64_t n_q);
+int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
+                          int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok, ivx_stream_t stream);
+int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const int32_t* slice_ladder,
+                               const int32_t* order, const int64_t* lad_slice_off, int64_t n_ladders, int64_t max_slices_per_ladder,
+                               const int64_t* ladder_off, int64_t max_knots, const double* x_ladder, const double* x_own /*or NULL*/,
+                               const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
+                               const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
+                               const uint8_t* ladder_ok, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream);
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);

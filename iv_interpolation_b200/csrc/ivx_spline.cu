@@ -156,17 +156,17 @@ struct SplLayout {
 // has its right-hand side to eliminate: d'[i] = (r[i] - h[i-1] d'[i-1]) / den[i] is an affine map per row — a prefix scan
 // of 2-vectors, no matrices, no division.  Slices with missing knots take the general path below.
 template <int G, int SPL_R, int MODE>   // MODE 0: general; 1: slices sit on tabulated ladders; 2: presumed to — verified per slice
-__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k_spline_fit_eval(int64_t n_slices, const int64_t* __restrict__ knot_off,
-                                                                       const int64_t* __restrict__ x_off,
-                                                                       const double* __restrict__ x,
-                                                                       const double* __restrict__ lu_cp, const double* __restrict__ lu_inv,
-                                                                       const double* __restrict__ lu_ih,
-                                                                       const int32_t* __restrict__ slice_ladder,
-                                                                       const double* __restrict__ x_own,
-                                                                       const int64_t* __restrict__ ladder_off,
-                                                                       const double* __restrict__ y,
-                                                                       int n_q, const double* __restrict__ xq, int extrap,
-                                                                       double* __restrict__ yq) {
+__device__ __forceinline__ void spline_slice(const int64_t sl, const int64_t* __restrict__ knot_off,
+                                             const int64_t* __restrict__ x_off,
+                                             const double* __restrict__ x,
+                                             const double* __restrict__ lu_cp, const double* __restrict__ lu_inv,
+                                             const double* __restrict__ lu_ih,
+                                             const int32_t* __restrict__ slice_ladder,
+                                             const double* __restrict__ x_own,
+                                             const int64_t* __restrict__ ladder_off,
+                                             const double* __restrict__ y,
+                                             int n_q, const double* __restrict__ xq, int extrap,
+                                             double* __restrict__ yq) {
   using L = SplLayout<G, SPL_R>;
   constexpr bool LADDER = MODE != 0;
   auto spl_pad = [](int i) { return spl_pad_t<SPL_R>(i); };
@@ -179,8 +179,6 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   double* wa = wm + L::NW * 7;          // [NW][2] warp totals of the backward scan
   int* wc = reinterpret_cast<int*>(wa + L::NW * 2);   // [NW] valid-knot counts
   int* qs = reinterpret_cast<int*>(wa + L::NW * 3);   // [G+1] first grid point of every thread
-  const int64_t sl = (int64_t)blockIdx.x * L::SPB + grp;
-  if (sl >= n_slices) return;           // a whole group leaves together (named barriers / warp sync below)
   const int64_t k0 = knot_off[sl];
   const int64_t xk0 = x_off ? x_off[sl] : k0;      // abscissae may live elsewhere (a strike ladder shared by many slices)
   int m = (int)min((int64_t)L::CAP + 1, knot_off[sl + 1] - k0);
@@ -517,6 +515,34 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
   }
 }
 
+#define IVX_SPL_PARAMS const int64_t* __restrict__ knot_off, const int64_t* __restrict__ x_off, const double* __restrict__ x,                      \
+                       const double* __restrict__ lu_cp, const double* __restrict__ lu_inv, const double* __restrict__ lu_ih,                 \
+                       const int32_t* __restrict__ slice_ladder, const double* __restrict__ x_own, const int64_t* __restrict__ ladder_off,    \
+                       const double* __restrict__ y, int n_q, const double* __restrict__ xq, int extrap, double* __restrict__ yq
+#define IVX_SPL_ARGS knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y, n_q, xq, extrap, yq
+
+// one group of G threads per slice, slices in order
+template <int G, int SPL_R, int MODE>
+__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k_spline_fit_eval(int64_t n_slices, IVX_SPL_PARAMS) {
+  const int64_t sl = (int64_t)blockIdx.x * SplLayout<G, SPL_R>::SPB + threadIdx.x / G;
+  if (sl >= n_slices) return;           // a whole group leaves together (named barriers / warp sync inside)
+  spline_slice<G, SPL_R, MODE>(sl, IVX_SPL_ARGS);
+}
+
+// the slices named in list[0 .. *count): what the banded kernel (ivx_spline_band.cu) could not take — a missing knot, a
+// slice off its ladder, a ladder whose band failed its exactness check.  Fixed grid, groups stride over the list.
+template <int G, int SPL_R, int MODE>
+__global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k_spline_fit_eval_list(const int32_t* __restrict__ list,
+                                                                                                  const uint32_t* __restrict__ count, IVX_SPL_PARAMS) {
+  constexpr int SPB = SplLayout<G, SPL_R>::SPB;
+  const int grp = threadIdx.x / G;
+  const uint32_t n = *count;
+  for (uint32_t slot = blockIdx.x * SPB + grp; slot < n; slot += gridDim.x * SPB) {
+    spline_slice<G, SPL_R, MODE>((int64_t)list[slot], IVX_SPL_ARGS);
+    group_sync<G>(grp);                 // the group's shared memory is rewritten by its next slice
+  }
+}
+
 // ---- many small systems, [knot][system] layout ----------------------------------------------------------
 // generic path of the strided kernel: some knots of this system are unusable -> private abscissae (rare)
 __device__ __noinline__ void strided_generic(int64_t n_sys, int64_t sys, int nk, const double* s_x, const double* __restrict__ y,
@@ -674,7 +700,7 @@ static int launch_spline_t(int64_t n_slices, const int64_t* knot_off, const int6
   if (once_per_device(attr_once)) IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval<G, SPL_R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
   const int64_t blocks = (n_slices + L::SPB - 1) / L::SPB;
   IVX_REQUIRE(blocks < ((int64_t)1 << 31), IVX_ERR_TOO_LARGE, "ivx_spline_fit_eval: too many slices for one launch; split the batch");
-  k_spline_fit_eval<G, SPL_R, MODE><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, knot_off, x_off, x, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y, n_q, xq, extrap, yq);
+  k_spline_fit_eval<G, SPL_R, MODE><<<(unsigned)blocks, L::BT, L::SMEM, stream>>>(n_slices, IVX_SPL_ARGS);
   IVX_LAUNCH_CHECK("k_spline_fit_eval");
   return IVX_OK;
 }
@@ -750,6 +776,39 @@ static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int6
     default: IVX_SPL(1024, 8);
   }
 #undef IVX_SPL
+}
+
+template <int G, int SPL_R, int MODE>
+static int launch_spline_list_t(const int32_t* list, const uint32_t* count, const int64_t* knot_off, const int64_t* x_off, const double* x,
+                                const double* lu_cp, const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder,
+                                const double* x_own, const int64_t* ladder_off, const double* y, int n_q, const double* xq, int extrap,
+                                double* yq, cudaStream_t stream) {
+  using L = SplLayout<G, SPL_R>;
+  static DeviceOnce attr_once;
+  if (once_per_device(attr_once)) IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval_list<G, SPL_R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+  const unsigned blocks = (unsigned)(sm_count() * (G <= 256 ? 4 : 1));
+  k_spline_fit_eval_list<G, SPL_R, MODE><<<blocks, L::BT, L::SMEM, stream>>>(list, count, IVX_SPL_ARGS);
+  IVX_LAUNCH_CHECK("k_spline_fit_eval_list");
+  return IVX_OK;
+}
+
+// the exact solve for the slices a list names (device-side count): ladder tables where a slice may use them (MODE 1 when the
+// slices are known to sit on their ladders, MODE 2 when that is verified per slice), the general scan otherwise
+int ivx::spline_fit_eval_list(const int32_t* list, const uint32_t* count, int64_t max_knots, const int64_t* knot_off, const int64_t* x_off,
+                              const double* x, const double* lu_cp, const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder,
+                              const double* x_own, const int64_t* ladder_off, const double* y, int n_q, const double* xq, int extrap,
+                              double* yq, cudaStream_t stream) {
+#define IVX_SPLL(G, R)                                                                                                                   \
+  return x_own ? launch_spline_list_t<G, R, 2>(list, count, IVX_SPL_ARGS, stream) : launch_spline_list_t<G, R, 1>(list, count, IVX_SPL_ARGS, stream)
+  switch (spline_group_width(max_knots)) {
+    case 32: IVX_SPLL(32, 8);
+    case 64: IVX_SPLL(64, 8);
+    case 128: IVX_SPLL(128, 8);
+    case 256: IVX_SPLL(256, 8);
+    case 512: IVX_SPLL(512, 8);
+    default: IVX_SPLL(1024, 8);
+  }
+#undef IVX_SPLL
 }
 
 extern "C" int ivx_spline_fit_eval_xoff(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, int64_t max_knots,

@@ -1,0 +1,380 @@
+// ivx_spline_band.cu — kernel D on shared ladders as a BANDED linear operator.
+//
+// For a fixed ladder of abscissae x[0..n) and a fixed evaluation grid xq[0..n_q), "fit the natural cubic spline through
+// (x, y) and evaluate it on xq" is a fixed LINEAR map  yq = W y.  Row q of W is
+//     ta e_{i} + tb e_{i+1} + C row_i(A^{-1} R) + D row_{i+1}(A^{-1} R),        i = bracket of xq[q],
+// (A the tridiagonal matrix of the second-derivative system, R the second-difference operator), and the rows of A^{-1}
+// decay geometrically away from the diagonal — by 2 - sqrt 3 = 0.268 per knot on a uniform ladder — so BAND_L = 22 rows
+// either side of the bracket carry everything above 1e-12 and a slice is n_q short dot products of BAND_W = 48 terms:
+// ~25 k fused multiply-adds instead of the ~500 k instructions of the scan-based solve, and the abscissae are not needed
+// (8 B/knot instead of 16; they are still read where a slice has to be VERIFIED to sit on its ladder).
+//   * k_band_build   one thread per (ladder, grid point): the two local Thomas solves (46 rows), the 48 weights, the
+//                    window start.  Truncation is never trusted: k_band_check fits two probe vectors exactly (full Thomas)
+//                    and compares; a ladder whose band misses 2e-12 is marked not ok and its slices take the exact solve.
+//   * k_band_apply   one CTA per (ladder, batch of slices), one thread per grid point holding its 48 weights in
+//                    REGISTERS for the whole batch; a slice's y (and x, when verified) is brought into shared memory by a
+//                    3-deep cp.async pipeline, ONE block barrier per slice (it also votes "every knot finite and on the
+//                    ladder"); grid points are dealt to lanes 32 apart so that the 16 lanes of a half-warp read 16
+//                    different banks; results leave through a shared-memory transpose, coalesced.
+//                    Slices that cannot be taken (a missing knot, off the ladder, odd length) are appended to a list.
+//   * the list is then solved by the exact kernel (ivx_spline.cu, k_spline_fit_eval_list) in the same stream.
+#include "ivx_common.cuh"
+
+namespace ivx {
+namespace {
+
+constexpr int BAND_L = 22;
+constexpr int BAND_W = 2 * BAND_L + 4;      // 48
+constexpr int BAND_MAXQ = 512;
+constexpr int BAND_MAXK = 2048;
+constexpr int BAND_NBUF = 3;
+constexpr int BAND_THREADS = 512;
+constexpr int BAND_BATCH = 48;              // slices per CTA at most: the 200 KB of weights are read once per batch
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- build ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_band_build(int32_t n_ladders, const int64_t* __restrict__ ladder_off, const double* __restrict__ x,
+                                                    int32_t n_q, const double* __restrict__ xq, int32_t extrap,
+                                                    int32_t* __restrict__ band_k0, double* __restrict__ band_w, uint8_t* __restrict__ ladder_ok) {
+  const int l = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_q) return;
+  const int64_t a0 = ladder_off[l];
+  const int64_t n64 = ladder_off[l + 1] - a0;
+  const double* __restrict__ X = x + a0;
+  double* __restrict__ w = band_w + ((int64_t)l * n_q + q) * BAND_W;
+  int32_t* k0p = band_k0 + (int64_t)l * n_q + q;
+  for (int j = 0; j < BAND_W; ++j) w[j] = 0.0;
+  *k0p = 0;
+  bool usable = n64 >= BAND_W && n64 <= BAND_MAXK && n_q <= BAND_MAXQ;
+  if (usable && q == 0) {                   // strictly increasing, finite abscissae
+    for (int i = 0; i < (int)n64; ++i) {
+      const double xi = X[i];
+      if (!(fabs(xi) < INFINITY) || (i > 0 && !(xi > X[i - 1]))) usable = false;
+    }
+  }
+  if (q == 0) ladder_ok[l] = usable ? 1 : 0;           // k_band_check may still clear it
+  if (!(n64 >= BAND_W && n64 <= BAND_MAXK)) return;
+  const int n = (int)n64;
+  const double xv = xq[q];
+  if (isnan(xv)) { *k0p = -1; return; }
+  const bool below = xv < X[0], above = xv > X[n - 1];
+  if ((below || above) && extrap == 0) { *k0p = -1; return; }
+  if ((below || above) && extrap == 2) {               // flat: the end knot's value
+    const int kk = below ? 0 : n - 1;
+    const int k0 = below ? 0 : n - BAND_W;
+    *k0p = k0; w[kk - k0] = 1.0;
+    return;
+  }
+  // bracket: largest i with X[i] <= xv, clamped to a segment
+  int lo_ = 0, hi_ = n;
+  while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (X[mid] <= xv) lo_ = mid + 1; else hi_ = mid; }
+  int i0 = lo_ - 1;
+  i0 = i0 < 0 ? 0 : (i0 > n - 2 ? n - 2 : i0);
+  const int lo = max(1, i0 - BAND_L), hi = min(n - 2, i0 + 1 + BAND_L);   // interior equations kept
+  const int m = hi - lo + 1;                            // <= 2 BAND_L + 2; n >= 48 -> m >= 1
+  double cp[2 * BAND_L + 2], z1[2 * BAND_L + 2], z2[2 * BAND_L + 2];
+  {
+    double cprev = 0.0, d1 = 0.0, d2 = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const int i = lo + j;
+      const double hm = X[i] - X[i - 1], hp = X[i + 1] - X[i];
+      const double inv = 1.0 / (2.0 * (hm + hp) - hm * cprev);
+      cprev = hp * inv;
+      d1 = ((i == i0 ? 1.0 : 0.0) - hm * d1) * inv;
+      d2 = ((i == i0 + 1 ? 1.0 : 0.0) - hm * d2) * inv;
+      cp[j] = cprev; z1[j] = d1; z2[j] = d2;
+    }
+    double m1 = 0.0, m2 = 0.0;
+    for (int j = m - 1; j >= 0; --j) {
+      m1 = z1[j] - cp[j] * m1; m2 = z2[j] - cp[j] * m2;
+      z1[j] = m1; z2[j] = m2;
+    }
+  }
+  const double hseg = X[i0 + 1] - X[i0];
+  const double ta = (X[i0 + 1] - xv) / hseg, tb = (xv - X[i0]) / hseg;
+  const double C = (ta * ta * ta - ta) * hseg * hseg * (1.0 / 6.0), D = (tb * tb * tb - tb) * hseg * hseg * (1.0 / 6.0);
+  int k0 = lo - 1;
+  k0 = k0 < 0 ? 0 : (k0 > n - BAND_W ? n - BAND_W : k0);
+  *k0p = k0;
+  auto zc = [&](int i) -> double { return (i >= lo && i <= hi) ? fma(C, z1[i - lo], D * z2[i - lo]) : 0.0; };   // C z_i0 + D z_{i0+1} at row i
+  for (int k = lo - 1; k <= hi + 1; ++k) {
+    // d/dy[k] of sum_i zc(i) r[i],  r[i] = 6 ((y[i+1]-y[i])/h[i] - (y[i]-y[i-1])/h[i-1]),  h[i] = X[i+1]-X[i]
+    double v = 0.0;
+    if (k >= 1) v += zc(k - 1) / (X[k] - X[k - 1]);                                       // row k-1: + y[k]/h[k-1]
+    if (k >= 1 && k <= n - 2) v -= zc(k) * (1.0 / (X[k] - X[k - 1]) + 1.0 / (X[k + 1] - X[k]));
+    if (k <= n - 2) v += zc(k + 1) / (X[k + 1] - X[k]);                                   // row k+1: + y[k]/h[k]
+    v *= 6.0;
+    if (k == i0) v += ta;
+    if (k == i0 + 1) v += tb;
+    w[k - k0] = v;
+  }
+}
+
+// ---- exactness check: two probe vectors per ladder, banded against the full Thomas solve -------------------------------
+__device__ __forceinline__ double probe_value(int k, int which) {
+  uint32_t h = (uint32_t)k * 2654435761u + 0x9E3779B9u * (uint32_t)(which + 1);
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+  const double noise = (double)h * (1.0 / 4294967296.0) - 0.5;
+  return which == 0 ? sin(0.37 * k) + 0.25 * noise : 2.0 * noise;
+}
+
+__global__ void __launch_bounds__(256) k_band_check(const int64_t* __restrict__ ladder_off, const double* __restrict__ x, int32_t n_q,
+                                                    const double* __restrict__ xq, int32_t extrap, const int32_t* __restrict__ band_k0,
+                                                    const double* __restrict__ band_w, uint8_t* __restrict__ ladder_ok) {
+  __shared__ double sM[BAND_MAXK], scp[BAND_MAXK];      // the probe y is a function of (k, which): recomputed where needed
+  __shared__ int bad;
+  const int l = blockIdx.x;
+  if (!ladder_ok[l]) return;
+  const int64_t a0 = ladder_off[l];
+  const int n = (int)(ladder_off[l + 1] - a0);
+  const double* __restrict__ X = x + a0;
+  if (threadIdx.x == 0) bad = 0;
+  for (int which = 0; which < 2; ++which) {
+    auto sy = [&](int k) { return probe_value(k, which); };
+    __syncthreads();
+    if (threadIdx.x == 0) {                       // the reference: plain Thomas over the whole ladder
+      double cprev = 0.0, dprev = 0.0;
+      sM[0] = 0.0; sM[n - 1] = 0.0;
+      for (int i = 1; i <= n - 2; ++i) {
+        const double hm = X[i] - X[i - 1], hp = X[i + 1] - X[i];
+        const double inv = 1.0 / (2.0 * (hm + hp) - hm * cprev);
+        cprev = hp * inv;
+        dprev = (6.0 * ((sy(i + 1) - sy(i)) / hp - (sy(i) - sy(i - 1)) / hm) - hm * dprev) * inv;
+        scp[i] = cprev; sM[i] = dprev;
+      }
+      double M = 0.0;
+      for (int i = n - 2; i >= 1; --i) { M = sM[i] - scp[i] * M; sM[i] = M; }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_q; q += blockDim.x) {
+      const int k0 = band_k0[(int64_t)l * n_q + q];
+      const double xv = xq[q];
+      double exact;
+      if (isnan(xv) || ((xv < X[0] || xv > X[n - 1]) && extrap == 0)) exact = qnan();
+      else if (xv < X[0] && extrap == 2) exact = sy(0);
+      else if (xv > X[n - 1] && extrap == 2) exact = sy(n - 1);
+      else {
+        int lo_ = 0, hi_ = n;
+        while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (X[mid] <= xv) lo_ = mid + 1; else hi_ = mid; }
+        int i0 = lo_ - 1;
+        i0 = i0 < 0 ? 0 : (i0 > n - 2 ? n - 2 : i0);
+        const double h = X[i0 + 1] - X[i0], A = X[i0 + 1] - xv, B = xv - X[i0];
+        exact = (sM[i0] * A * A * A + sM[i0 + 1] * B * B * B) / (6.0 * h) + (sy(i0) / h - sM[i0] * h / 6.0) * A + (sy(i0 + 1) / h - sM[i0 + 1] * h / 6.0) * B;
+      }
+      double got;
+      if (k0 < 0) got = qnan();
+      else {
+        const double* __restrict__ w = band_w + ((int64_t)l * n_q + q) * BAND_W;
+        got = 0.0;
+        for (int j = 0; j < BAND_W; ++j) got = fma(w[j], sy(k0 + j), got);
+      }
+      const bool same = (isnan(exact) && isnan(got)) || fabs(got - exact) <= 2e-12 * (1.0 + fabs(exact));
+      if (!same) bad = 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && bad) ladder_ok[l] = 0;
+}
+
+// ---- apply -----------------------------------------------------------------------------------------------------------
+struct BandParams {
+  const int64_t* knot_off;       // [n_slices+1]
+  const int32_t* order;          // slices grouped by ladder
+  const int64_t* lad_slice_off;  // [n_ladders+1] into order
+  const int64_t* ladder_off;     // [n_ladders+1] into x_ladder
+  const double* x_ladder;
+  const double* x_own;           // per-knot abscissae of the slices (verified against the ladder) or NULL
+  const double* y;
+  const int32_t* band_k0;
+  const double* band_w;
+  const uint8_t* ladder_ok;
+  double* yq;
+  int32_t* fb_list;
+  uint32_t* fb_count;
+  int32_t n_q;
+  int32_t batch;                 // slices per CTA
+};
+
+template <bool VERIFY>
+__global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
+  extern __shared__ __align__(16) double sm[];
+  double* ybuf = sm;                                         // [NBUF][MAXK]
+  double* obuf = ybuf + BAND_NBUF * BAND_MAXK;               // [2][MAXQ]
+  double* xbuf = obuf + 2 * BAND_MAXQ;                       // [NBUF][MAXK]   (VERIFY)
+  double* ladx = xbuf + BAND_NBUF * BAND_MAXK;               // [MAXK]         (VERIFY)
+  const int l = blockIdx.y;
+  const int64_t s_begin = P.lad_slice_off[l] + (int64_t)blockIdx.x * P.batch;
+  const int64_t s_end_all = P.lad_slice_off[l + 1];
+  if (s_begin >= s_end_all) return;
+  const int ns = (int)min((int64_t)P.batch, s_end_all - s_begin);
+  const int32_t* __restrict__ ord = P.order + s_begin;
+  const int t = threadIdx.x;
+  if (!P.ladder_ok[l]) {                                     // no usable band for this ladder: everything to the exact solve
+    for (int i = t; i < ns; i += BAND_THREADS) P.fb_list[atomicAdd(P.fb_count, 1u)] = ord[i];
+    return;
+  }
+  const int n = (int)(P.ladder_off[l + 1] - P.ladder_off[l]);      // BAND_W <= n <= BAND_MAXK (k_band_build)
+  const int n_q = P.n_q;
+  // grid point of this thread: lanes of a half-warp sit 32 points apart -> their windows start ~32 n/n_q knots apart, which
+  // spreads them over the banks
+  const int q = (t & 15) * 32 + (t >> 4);
+  const bool has_q = q < n_q;
+  double w[BAND_W];
+  int k0 = 0;
+  if (has_q) {
+    k0 = P.band_k0[(int64_t)l * n_q + q];
+    const double* __restrict__ wp = P.band_w + ((int64_t)l * n_q + q) * BAND_W;
+#pragma unroll
+    for (int j = 0; j < BAND_W; ++j) w[j] = __ldg(wp + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < BAND_W; ++j) w[j] = 0.0;
+  }
+  const bool nan_q = k0 < 0;
+  if (nan_q) k0 = 0;
+  if (VERIFY) {
+    for (int k = t; k < n; k += BAND_THREADS) ladx[k] = __ldg(P.x_ladder + P.ladder_off[l] + k);
+  }
+  // knots this thread moves: k = t + r * 512, r = 0..3
+  auto issue = [&](int i) {
+    if (i < ns) {
+      const int64_t s = ord[i];
+      const int64_t ko = P.knot_off[s];
+      const int len = (int)min((int64_t)BAND_MAXK + 1, P.knot_off[s + 1] - ko);
+      if (len == n) {
+        double* yb = ybuf + (i % BAND_NBUF) * BAND_MAXK;
+        double* xb = xbuf + (i % BAND_NBUF) * BAND_MAXK;
+#pragma unroll
+        for (int r = 0; r < BAND_MAXK / BAND_THREADS; ++r) {
+          const int k = t + r * BAND_THREADS;
+          if (k < n) {
+            cp_async8(yb + k, P.y + ko + k);
+            if (VERIFY) cp_async8(xb + k, P.x_own + ko + k);
+          }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  bool prev_ok = false;                                      // CTA-uniform: slice i-1 was computed here (its results sit in obuf)
+  for (int i = 0; i < ns; ++i) {
+    cp_async_wait<1>();                                      // this thread's part of slice i has landed
+    const int64_t s = ord[i];
+    const int64_t ko = P.knot_off[s];
+    const bool len_ok = (P.knot_off[s + 1] - ko) == (int64_t)n;
+    const double* yb = ybuf + (i % BAND_NBUF) * BAND_MAXK;
+    bool ok = len_ok;
+    if (len_ok) {                                            // every thread checks the knots it moved itself
+      const double* xb = xbuf + (i % BAND_NBUF) * BAND_MAXK;
+#pragma unroll
+      for (int r = 0; r < BAND_MAXK / BAND_THREADS; ++r) {
+        const int k = t + r * BAND_THREADS;
+        if (k < n) {
+          ok = ok && (fabs(yb[k]) < INFINITY);
+          if (VERIFY) ok = ok && (xb[k] == ladx[k]);        // ladx[k] was written by this same thread
+        }
+      }
+    }
+    const bool all_ok = __syncthreads_and(ok) != 0;          // the one barrier per slice: data visible, vote, buffers free
+    issue(i + 2);                                            // into the buffer slice i-1 was read from
+    if (i > 0 && prev_ok && t < n_q)                         // slice i-1: transposed through shared memory, stored coalesced
+      st_stream(P.yq + (int64_t)ord[i - 1] * n_q + t, obuf[((i - 1) & 1) * BAND_MAXQ + t]);
+    if (all_ok) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      const double* yw = yb + k0;
+#pragma unroll
+      for (int j = 0; j < BAND_W; j += 4) {
+        a0 = fma(w[j], yw[j], a0);
+        a1 = fma(w[j + 1], yw[j + 1], a1);
+        a2 = fma(w[j + 2], yw[j + 2], a2);
+        a3 = fma(w[j + 3], yw[j + 3], a3);
+      }
+      if (has_q) obuf[(i & 1) * BAND_MAXQ + q] = nan_q ? qnan() : (a0 + a1) + (a2 + a3);
+    } else if (t == 0) {
+      P.fb_list[atomicAdd(P.fb_count, 1u)] = (int32_t)s;     // a missing knot, off the ladder, another length: the exact solve
+    }
+    prev_ok = all_ok;
+  }
+  __syncthreads();
+  if (prev_ok && t < n_q) st_stream(P.yq + (int64_t)ord[ns - 1] * n_q + t, obuf[((ns - 1) & 1) * BAND_MAXQ + t]);
+  cp_async_wait<0>();
+}
+
+}  // namespace
+}  // namespace ivx
+
+using namespace ivx;
+
+extern "C" int64_t ivx_spline_band_len(int64_t n_ladders, int64_t n_q) {
+  if (n_ladders < 0 || n_q < 0) return -1;
+  return n_ladders * n_q * BAND_W;
+}
+
+extern "C" int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
+                                     int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_ladders >= 0 && n_ladders < 65536 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_band_build: bad sizes");
+  IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_band_build: extrap must be 0, 1 or 2");
+  if (n_ladders == 0 || n_q == 0) return IVX_OK;
+  IVX_REQUIRE(ladder_off && x_ladder && xq && band_k0 && band_w && ladder_ok, IVX_ERR_INVALID_ARG, "ivx_spline_band_build: null pointer");
+  k_band_build<<<dim3((unsigned)((n_q + 127) / 128), (unsigned)n_ladders), 128, 0, stream>>>((int32_t)n_ladders, ladder_off, x_ladder, (int32_t)n_q, xq, extrap,
+                                                                                             band_k0, band_w, ladder_ok);
+  IVX_LAUNCH_CHECK("k_band_build");
+  if (n_q <= BAND_MAXQ) {
+    k_band_check<<<(unsigned)n_ladders, 256, 0, stream>>>(ladder_off, x_ladder, (int32_t)n_q, xq, extrap, band_k0, band_w, ladder_ok);
+    IVX_LAUNCH_CHECK("k_band_check");
+  }
+  return IVX_OK;
+}
+
+extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const int32_t* slice_ladder,
+                                          const int32_t* order, const int64_t* lad_slice_off, int64_t n_ladders, int64_t max_slices_per_ladder,
+                                          const int64_t* ladder_off, int64_t max_knots, const double* x_ladder, const double* x_own,
+                                          const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
+                                          const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
+                                          const uint8_t* ladder_ok, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_slices >= 0 && n_slices < ((int64_t)1 << 31) && n_ladders >= 0 && n_ladders < 65536 && max_slices_per_ladder >= 0,
+              IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: bad sizes");
+  IVX_REQUIRE(n_q >= 0 && n_q <= BAND_MAXQ, IVX_ERR_UNSUPPORTED, "ivx_spline_fit_eval_banded: at most %d grid points (got %lld)", BAND_MAXQ, (long long)n_q);
+  IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: extrap must be 0, 1 or 2");
+  if (n_slices == 0 || n_q == 0 || n_ladders == 0) return IVX_OK;
+  IVX_REQUIRE(knot_off && x_off && slice_ladder && order && lad_slice_off && ladder_off && x_ladder && lu_cp && lu_inv && lu_ih && y && xq && band_k0 &&
+                  band_w && ladder_ok && yq && fb_list && fb_count,
+              IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: null pointer");
+  IVX_CUDA(cudaMemsetAsync(fb_count, 0, 4, stream));
+  BandParams P;
+  P.knot_off = knot_off; P.order = order; P.lad_slice_off = lad_slice_off; P.ladder_off = ladder_off; P.x_ladder = x_ladder; P.x_own = x_own;
+  P.y = y; P.band_k0 = band_k0; P.band_w = band_w; P.ladder_ok = ladder_ok; P.yq = yq; P.fb_list = fb_list; P.fb_count = fb_count; P.n_q = (int32_t)n_q;
+  // slices per CTA: as many as 48 (the weights are loaded once per CTA), but no fewer than ~3 CTAs per SM in the launch
+  int64_t batch = (max_slices_per_ladder * n_ladders + 3 * (int64_t)sm_count() - 1) / (3 * (int64_t)sm_count());
+  batch = batch < 4 ? 4 : (batch > BAND_BATCH ? BAND_BATCH : batch);
+  P.batch = (int32_t)batch;
+  const dim3 grid((unsigned)((max_slices_per_ladder + batch - 1) / batch), (unsigned)n_ladders);
+  if (grid.x > 0) {
+    if (x_own) {
+      const size_t smem = (size_t)(2 * BAND_NBUF * BAND_MAXK + 2 * BAND_MAXQ + BAND_MAXK) * sizeof(double);
+      static DeviceOnce once;
+      if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_band_apply<true><<<grid, BAND_THREADS, smem, stream>>>(P);
+    } else {
+      const size_t smem = (size_t)(BAND_NBUF * BAND_MAXK + 2 * BAND_MAXQ) * sizeof(double);
+      static DeviceOnce once;
+      if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_band_apply<false><<<grid, BAND_THREADS, smem, stream>>>(P);
+    }
+    IVX_LAUNCH_CHECK("k_band_apply");
+  }
+  // whatever the banded kernel listed: the exact solve (ladder tables where a slice may use them), same stream
+  return spline_fit_eval_list(fb_list, fb_count, max_knots, knot_off, x_off, x_ladder, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y,
+                              (int)n_q, xq, extrap, yq, stream);
+}

@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 3, "spline_ladder_factor": 1,
-    "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
+    "spline_band_build": 2, "spline_fit_eval_banded": 2, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
 
@@ -449,6 +449,60 @@ def spline_ladder_factor(ladder_off: torch.Tensor, x: torch.Tensor, *, max_knots
                                          _ptr(lu[2]), _stream()), "ivx_spline_ladder_factor")
     _count("spline_ladder_factor")
     return lu
+
+
+@dataclass
+class SplineBand:
+    """Banded evaluation operators of a set of ladders on one grid (``spline_band_build``) + the slices grouped by ladder."""
+    k0: torch.Tensor                # int32[n_ladders * n_q]
+    w: torch.Tensor                 # float64[n_ladders * n_q * 48]
+    ok: torch.Tensor                # uint8[n_ladders]
+    n_q: int
+    extrap: int
+
+
+def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torch.Tensor, *, extrap: int = 1,
+                      out: Optional[SplineBand] = None) -> SplineBand:
+    """Per (ladder, grid point): the 48 knot weights of "fit the natural spline, evaluate at xq[q]" and their start, checked
+    against a full solve of two probe vectors (``ok[l] == 0``: that ladder's slices take the exact solve)."""
+    _req(ladder_off, torch.int64, "ladder_off"); _req(x_ladder, torch.float64, "x_ladder"); _req(xq, torch.float64, "xq")
+    n_l, n_q = ladder_off.numel() - 1, xq.numel()
+    if out is None or out.n_q != n_q or out.ok.numel() != n_l:
+        out = SplineBand(_empty(n_l * n_q, torch.int32, xq), _empty(lib().ivx_spline_band_len(n_l, n_q), torch.float64, xq),
+                         _empty(n_l, torch.uint8, xq), n_q, int(extrap))
+    out.extrap = int(extrap)
+    check(lib().ivx_spline_band_build(n_l, _ptr(ladder_off), _ptr(x_ladder), n_q, _ptr(xq), int(extrap), _ptr(out.k0), _ptr(out.w),
+                                      _ptr(out.ok), _stream()), "ivx_spline_band_build")
+    _count("spline_band_build")
+    return out
+
+
+def spline_fit_eval_banded(knot_off: torch.Tensor, x_off: torch.Tensor, slice_ladder: torch.Tensor, order: torch.Tensor,
+                           lad_slice_off: torch.Tensor, max_slices_per_ladder: int, ladder_off: torch.Tensor, x_ladder: torch.Tensor,
+                           lu: Sequence[torch.Tensor], y: torch.Tensor, xq: torch.Tensor, band: SplineBand, *, max_knots: int,
+                           x_own: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                           fb: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    """Slices on tabulated ladders through the banded operators; whatever cannot be taken that way (a non-finite knot, a slice
+    off its ladder when ``x_own`` is given, a ladder without a usable band) goes through the exact scan right behind.
+    ``fb`` = (int32[n_slices] list, uint32[1] count) scratch, allocated when not passed."""
+    n_slices, n_q, n_l = knot_off.numel() - 1, xq.numel(), ladder_off.numel() - 1
+    if band.n_q != n_q:
+        raise _lib.IvxError("spline_fit_eval_banded: the band was built for another grid")
+    _req(order, torch.int32, "order"); _req(slice_ladder, torch.int32, "slice_ladder")
+    for t_ in (knot_off, x_off, lad_slice_off, ladder_off):
+        _req(t_, torch.int64, "offsets")
+    yq = out if out is not None else _empty(n_slices * n_q, torch.float64, y)
+    if yq.numel() < n_slices * n_q:
+        raise _lib.IvxError("spline_fit_eval_banded: output too small")
+    if fb is None:
+        fb = (_empty(max(1, n_slices), torch.int32, y), _empty(1, torch.int32, y))
+    check(lib().ivx_spline_fit_eval_banded(n_slices, _ptr(knot_off), _ptr(x_off), _ptr(slice_ladder), _ptr(order), _ptr(lad_slice_off), n_l,
+                                           int(max_slices_per_ladder), _ptr(ladder_off), int(max_knots), _ptr(x_ladder),
+                                           _ptr(x_own) if x_own is not None else None, _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q,
+                                           _ptr(xq), int(band.extrap), _ptr(band.k0), _ptr(band.w), _ptr(band.ok), _ptr(yq), _ptr(fb[0]),
+                                           _ptr(fb[1]), _stream()), "ivx_spline_fit_eval_banded")
+    _count("spline_fit_eval_banded")
+    return yq
 
 
 def spline_strided(x: torch.Tensor, y: torch.Tensor, xq: torch.Tensor, n_systems: int, *, extrap: int = 1,

@@ -119,7 +119,7 @@ class SurfacePipeline:
 
     STAGES = ("implied_vol", "spline_strike", "spline_maturity", "candles")
 
-    def __init__(self, spec: ChainSpec, device: torch.device, max_buckets: Optional[int] = None):
+    def __init__(self, spec: ChainSpec, device: torch.device, max_buckets: Optional[int] = None, banded: bool = True):
         if device.type != "cuda":
             raise IvxError("SurfacePipeline needs a CUDA device (no CPU path exists)")
         self.spec = spec
@@ -136,11 +136,26 @@ class SurfacePipeline:
         self._buckets = None       # (ts tensor identity, bucket_ts, bucket_start, n_buckets)
         # chain layout: every slice (t, e) reads its abscissae from the shared ladder of expiry e
         self._x_off = None
+        # strike spline on shared ladders: banded operators (ivx_spline_band.cu) when the shapes allow, else the scan kernel
+        self.banded = banded and spec.n_grid_k <= 512 and 48 <= spec.n_strike <= 2048
+        self._band = self._q_band = None
+        self._order = None
         self._chain_ws = None
         self._iv_ws = None
         self._lu_key = None
         self._q_lu = None
         self._q_lu_key = None
+
+    def _group_slices(self):
+        """Slices (t, e) grouped by ladder e (CSR), once: slice id = t * n_exp + e."""
+        if self._order is None:
+            sp = self.spec
+            e = torch.arange(sp.n_exp, dtype=torch.int64, device=self.device)
+            t = torch.arange(sp.n_t, dtype=torch.int64, device=self.device)
+            self._order = (t[None, :] * sp.n_exp + e[:, None]).reshape(-1).to(torch.int32).contiguous()
+            self._lad_slice_off = torch.arange(sp.n_exp + 1, dtype=torch.int64, device=self.device) * sp.n_t
+            self._fb = (torch.empty(sp.n_t * sp.n_exp, dtype=torch.int32, device=self.device),
+                        torch.zeros(1, dtype=torch.int32, device=self.device))
 
     def plan_buckets(self, ts: torch.Tensor):
         """Bucket boundaries of the day's stamps (one tiny kernel + an 8-byte read-back, done once per tape)."""
@@ -186,12 +201,21 @@ class SurfacePipeline:
         if structured:
             # the x-only half of the elimination once per expiry ladder — and only when the ladders changed (contracts do
             # not change intraday) — then right-hand sides only
-            key = (q.K_ek.data_ptr(), q.K_ek._version)
+            key = (q.K_ek.data_ptr(), q.K_ek._version, q.grid_k.data_ptr(), q.grid_k._version)
             if self._lu_key != key:
                 D.spline_ladder_factor(self._ladder_off, q.K_ek, max_knots=sp.n_strike, out=self._lu)
+                self._band = D.spline_band_build(self._ladder_off, q.K_ek, q.grid_k, extrap=sp.extrap, out=self._band) if self.banded else None
                 self._lu_key = key
-            D.spline_fit_eval(self.knot_off, q.K_ek, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
-                              out=self.smile, x_off=self._x_off, lu=self._lu, slice_ladder=self._slice_ladder)
+            if self.banded:
+                # every slice is n_grid_k dot products of 48 terms against its ladder's banded operator; slices with a missing
+                # knot take the exact scan right behind (same call)
+                self._group_slices()
+                D.spline_fit_eval_banded(self.knot_off, self._x_off, self._slice_ladder, self._order, self._lad_slice_off, sp.n_t,
+                                         self._ladder_off, q.K_ek, self._lu, self.iv, q.grid_k, self._band, max_knots=sp.n_strike,
+                                         out=self.smile, fb=self._fb)
+            else:
+                D.spline_fit_eval(self.knot_off, q.K_ek, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap,
+                                  out=self.smile, x_off=self._x_off, lu=self._lu, slice_ladder=self._slice_ladder)
         else:
             # per-quote strikes: a chain's strike ladders normally do not change during the day, but nothing says so here.
             # The first stamp's ladders are factored (30 small launches' worth of work) and every slice is PRESUMED to
@@ -203,13 +227,22 @@ class SurfacePipeline:
                 self._q_x_off = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp) * sp.n_strike
                 self._q_ladder_off = torch.arange(sp.n_exp + 1, dtype=torch.int64, device=self.device) * sp.n_strike
                 self._q_slice_ladder = (torch.arange(sp.n_t * sp.n_exp, dtype=torch.int64, device=self.device) % sp.n_exp).to(torch.int32)
-            key = (q.K.data_ptr(), q.K._version)             # tables follow the column: refactored whenever it is written
+            key = (q.K.data_ptr(), q.K._version, q.grid_k.data_ptr(), q.grid_k._version)   # tables follow the columns: rebuilt whenever one is written
             if self._q_lu_key != key:
                 D.spline_ladder_factor(self._q_ladder_off, q.K, max_knots=sp.n_strike, out=self._q_lu)
+                self._q_band = D.spline_band_build(self._q_ladder_off, q.K, q.grid_k, extrap=sp.extrap, out=self._q_band) if self.banded else None
                 self._q_lu_key = key
-            D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile,
-                              x_off=self._q_x_off, lu=self._q_lu, slice_ladder=self._q_slice_ladder, x_own=q.K,
-                              ladder_off=self._q_ladder_off)
+            if self.banded:
+                # the first stamp's ladders as banded operators; a slice is taken that way only if its own strikes equal its
+                # ladder's bit for bit (checked while its knots are staged), the exact scan solves the others right behind
+                self._group_slices()
+                D.spline_fit_eval_banded(self.knot_off, self._q_x_off, self._q_slice_ladder, self._order, self._lad_slice_off, sp.n_t,
+                                         self._q_ladder_off, q.K, self._q_lu, self.iv, q.grid_k, self._q_band, max_knots=sp.n_strike,
+                                         x_own=q.K, out=self.smile, fb=self._fb)
+            else:
+                D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile,
+                                  x_off=self._q_x_off, lu=self._q_lu, slice_ladder=self._q_slice_ladder, x_own=q.K,
+                                  ladder_off=self._q_ladder_off)
         mark("spline_strike", 1)
         mark("spline_maturity", 0)
         # plane t: n_grid_k systems with n_exp knots at x = T[t][e], read in place

@@ -710,3 +710,88 @@ def test_implied_vol_two_kernel_form_equals_the_one_launch_form(dev):
     assert np.array_equal(i1.cpu().numpy(), i2.cpu().numpy())
     it = i1.cpu().numpy()
     assert (it > 1).sum() > 100, "the tape must exercise the fallback"
+
+
+def _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify):
+    """Run ivx_spline_fit_eval_banded on slices (xs[i], ys[i]) presumed to sit on ladders[lad_of[i]]; returns (yq, fallback ids, ok)."""
+    import torch
+    from iv_interpolation_b200 import device as D
+    lens = [len(l) for l in ladders]
+    ladder_off = np.r_[0, np.cumsum(lens)].astype(np.int64)
+    lx = np.concatenate(ladders)
+    off = np.r_[0, np.cumsum([len(y) for y in ys])].astype(np.int64)
+    lad_of = np.asarray(lad_of, np.int32)
+    order = np.argsort(lad_of, kind="stable").astype(np.int32)
+    counts = np.bincount(lad_of, minlength=len(ladders))
+    lad_slice_off = np.r_[0, np.cumsum(counts)].astype(np.int64)
+    max_knots = max(max(lens), max(len(y) for y in ys))
+    lu = D.spline_ladder_factor(_t(ladder_off, dev), _t(lx, dev), max_knots=max_knots)
+    band = D.spline_band_build(_t(ladder_off, dev), _t(lx, dev), _t(xq, dev), extrap=extrap)
+    fb = (torch.full((len(ys),), -1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+    yq = D.spline_fit_eval_banded(_t(off, dev), _t(ladder_off[:-1][lad_of], dev), _t(lad_of, dev), _t(order, dev), _t(lad_slice_off, dev),
+                                  int(counts.max()), _t(ladder_off, dev), _t(lx, dev), lu, _t(np.concatenate(ys), dev), _t(xq, dev), band,
+                                  max_knots=max_knots, x_own=_t(np.concatenate(xs), dev) if verify else None, fb=fb)
+    n_fb = int(fb[1].item())
+    return yq.cpu().numpy().reshape(len(ys), -1), sorted(fb[0].cpu().numpy()[:n_fb].tolist()), band.ok.cpu().numpy()
+
+
+@pytest.mark.parametrize("n_knots,n_q,extrap", [(2000, 512, 1), (2048, 512, 0), (333, 257, 2), (48, 100, 1), (1001, 512, 1)])
+def test_spline_banded_operator_vs_scipy(dev, n_knots, n_q, extrap):
+    """Slices on tabulated ladders through the banded operators (ivx_spline_band.cu): scipy to 1e-8, the exact scan kernel to
+    1e-10; slices with a missing knot or another length than their ladder are listed and solved by the exact kernel, and only those."""
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(n_knots + n_q)
+    n_lad, per = 3, 21
+    ladders = [2000.0 + np.cumsum(rng.uniform(0.7, 1.6, n_knots)) for _ in range(n_lad)]
+    lad_of = [s % n_lad for s in range(n_lad * per)]
+    xs, ys = [], []
+    for s, l in enumerate(lad_of):
+        x = ladders[l]
+        if s == 7:
+            x = x[: n_knots - 5]                                        # a prefix: another length -> exact solve
+        y = 0.2 + 0.3 * np.log(x / 3000.0) ** 2 + 0.004 * rng.standard_normal(len(x))
+        if s in (4, 11):
+            y[rng.integers(0, len(y))] = np.nan                          # a missing quote -> exact solve
+        xs.append(x); ys.append(y)
+    lo, hi = min(l[0] for l in ladders), max(l[-1] for l in ladders)
+    xq = np.linspace(lo - 10, hi + 10, n_q)
+    got, fb, ok = _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify=False)
+    assert ok.all() and fb == [4, 7, 11]
+    X, Y = np.concatenate(xs), np.concatenate(ys)
+    off = np.r_[0, np.cumsum([len(y) for y in ys])].astype(np.int64)
+    gen = D.spline_fit_eval(_t(off, dev), _t(X, dev), _t(Y, dev), _t(xq, dev), max_knots=n_knots, extrap=extrap).cpu().numpy().reshape(len(ys), -1)
+    for s in range(len(ys)):
+        want = O.natural_spline_eval(xs[s], ys[s], xq, extrap)
+        assert np.array_equal(np.isnan(got[s]), np.isnan(want)), s
+        fin = ~np.isnan(want)
+        scale = max(1.0, np.abs(want[fin]).max())
+        assert np.abs(got[s][fin] - want[fin]).max() <= 1e-8 * scale, (s, np.abs(got[s][fin] - want[fin]).max())
+        assert np.abs(got[s][fin] - gen[s][fin]).max() <= 1e-10 * scale, s
+
+
+def test_spline_banded_verify_and_unusable_ladders(dev):
+    """x_own given: a slice is taken by the band only if its abscissae equal its ladder's bit for bit (one knot off by an ulp ->
+    exact solve with its OWN abscissae).  Ladders the band cannot serve — fewer than 48 knots, or spacing so uneven that 22 rows
+    do not reach 2e-12 (found by the probe check) — send all their slices to the exact solve; results are right either way."""
+    rng = np.random.default_rng(5)
+    nk = 600
+    good = 100.0 + np.cumsum(rng.uniform(0.8, 1.2, nk))
+    short = 100.0 + np.cumsum(rng.uniform(0.8, 1.2, 30))
+    wild = 100.0 + np.cumsum(np.where(np.arange(nk) % 2 == 0, 1e-3, 5.0))           # alternating tiny / huge steps: slow decay
+    ladders = [good, short, wild]
+    lad_of = [0, 1, 2] * 6
+    xs, ys = [], []
+    for s, l in enumerate(lad_of):
+        x = ladders[l].copy()
+        if s == 3:
+            x[100] = np.nextafter(x[100], np.inf)
+        xs.append(x); ys.append(np.sin(x / 40.0) + 0.01 * rng.standard_normal(len(x)))
+    xq = np.linspace(90.0, good[-1] + 5, 300)
+    got, fb, ok = _banded(dev, ladders, lad_of, xs, ys, xq, 1, verify=True)
+    assert ok[0] == 1 and ok[1] == 0
+    expected_fb = sorted([s for s, l in enumerate(lad_of) if l == 1 or (l == 2 and not ok[2])] + [3])
+    assert fb == expected_fb, (fb, expected_fb, ok)
+    for s in range(len(ys)):
+        want = O.natural_spline_eval(xs[s], ys[s], xq, 1)
+        scale = max(1.0, np.abs(want).max())
+        assert np.abs(got[s] - want).max() <= 1e-8 * scale, (s, lad_of[s], np.abs(got[s] - want).max())
