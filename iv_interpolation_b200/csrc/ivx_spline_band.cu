@@ -183,6 +183,38 @@ __global__ void __launch_bounds__(256) k_band_check(const int64_t* __restrict__ 
   if (threadIdx.x == 0 && bad) ladder_ok[l] = 0;
 }
 
+// ---- which grid point each thread of k_band_apply takes ------------------------------------------------------------------
+// Thread t reads y[k0(q_t) + j], j = 0..47, one 64-bit shared-memory load per j; the 16 lanes of a half-warp are served
+// together and collide when two window starts agree modulo 16.  Grid points are therefore dealt to half-warps so that each
+// holds 16 different residues k0 mod 16 (possible whenever the residues are evenly spread, which a regular grid over a
+// regular ladder gives; leftovers go wherever there is room).  perm[l * 512 + t] = grid point of thread t, -1 = none.
+__global__ void __launch_bounds__(32) k_band_perm(int32_t n_q, const int32_t* __restrict__ band_k0, int16_t* __restrict__ perm) {
+  __shared__ int16_t bucket[16][BAND_MAXQ];
+  __shared__ int cnt[16];
+  const int l = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  for (int r = 0; r < 16; ++r) cnt[r] = 0;
+  for (int q = 0; q < n_q; ++q) {
+    const int k0 = band_k0[(int64_t)l * n_q + q];
+    const int r = (k0 < 0 ? 0 : k0) & 15;
+    bucket[r][cnt[r]++] = (int16_t)q;
+  }
+  int16_t* __restrict__ out = perm + (int64_t)l * BAND_THREADS;
+  for (int t = 0; t < BAND_THREADS; ++t) out[t] = -1;
+  int taken[16];
+  for (int r = 0; r < 16; ++r) taken[r] = 0;
+  int spare = 0;                                   // half-warps are filled front to back; slots nobody claimed are filled afterwards
+  for (int hw = 0; hw < BAND_THREADS / 16; ++hw)
+    for (int r = 0; r < 16; ++r)
+      if (taken[r] < cnt[r]) out[hw * 16 + r] = bucket[r][taken[r]++];
+  for (int r = 0; r < 16; ++r)
+    while (taken[r] < cnt[r]) {
+      while (spare < BAND_THREADS && out[spare] >= 0) ++spare;
+      if (spare >= BAND_THREADS) break;
+      out[spare] = bucket[r][taken[r]++];
+    }
+}
+
 // ---- apply -----------------------------------------------------------------------------------------------------------
 struct BandParams {
   const int64_t* knot_off;       // [n_slices+1]
@@ -195,6 +227,7 @@ struct BandParams {
   const int32_t* band_k0;
   const double* band_w;
   const uint8_t* ladder_ok;
+  const int16_t* perm;           // [n_ladders][512] grid point of every thread (k_band_perm)
   double* yq;
   int32_t* fb_list;
   uint32_t* fb_count;
@@ -207,7 +240,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
   extern __shared__ __align__(16) double sm[];
   double* ybuf = sm;                                         // [NBUF][MAXK]
   double* obuf = ybuf + BAND_NBUF * BAND_MAXK;               // [2][MAXQ]
-  double* xbuf = obuf + 2 * BAND_MAXQ;                       // [NBUF][MAXK]   (VERIFY)
+  double* xbuf = obuf + 2 * (BAND_MAXQ + 16);                // [NBUF][MAXK]   (VERIFY)
   double* ladx = xbuf + BAND_NBUF * BAND_MAXK;               // [MAXK]         (VERIFY)
   const int l = blockIdx.y;
   const int64_t s_begin = P.lad_slice_off[l] + (int64_t)blockIdx.x * P.batch;
@@ -222,10 +255,10 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
   }
   const int n = (int)(P.ladder_off[l + 1] - P.ladder_off[l]);      // BAND_W <= n <= BAND_MAXK (k_band_build)
   const int n_q = P.n_q;
-  // grid point of this thread: lanes of a half-warp sit 32 points apart -> their windows start ~32 n/n_q knots apart, which
-  // spreads them over the banks
-  const int q = (t & 15) * 32 + (t >> 4);
-  const bool has_q = q < n_q;
+  // grid point of this thread: dealt so that the 16 lanes of a half-warp start their windows in 16 different banks
+  const int q_raw = P.perm[(int64_t)l * BAND_THREADS + t];
+  const bool has_q = q_raw >= 0;
+  const int q = has_q ? q_raw : 0;
   double w[BAND_W];
   int k0 = 0;
   if (has_q) {
@@ -242,52 +275,66 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
   if (VERIFY) {
     for (int k = t; k < n; k += BAND_THREADS) ladx[k] = __ldg(P.x_ladder + P.ladder_off[l] + k);
   }
+  // per-slice bookkeeping once per batch: first knot of slice i (or -1: another length than the ladder -> exact solve) and its id
+  __shared__ int64_t sbase[BAND_BATCH];
+  __shared__ int32_t sid[BAND_BATCH];
+  if (t < ns) {
+    const int32_t s = ord[t];
+    const int64_t ko = P.knot_off[s];
+    sid[t] = s;
+    sbase[t] = (P.knot_off[s + 1] - ko) == (int64_t)n ? ko : (int64_t)-1;
+  }
+  __syncthreads();
   // knots this thread moves: k = t + r * 512, r = 0..3
-  auto issue = [&](int i) {
-    if (i < ns) {
-      const int64_t s = ord[i];
-      const int64_t ko = P.knot_off[s];
-      const int len = (int)min((int64_t)BAND_MAXK + 1, P.knot_off[s + 1] - ko);
-      if (len == n) {
-        double* yb = ybuf + (i % BAND_NBUF) * BAND_MAXK;
-        double* xb = xbuf + (i % BAND_NBUF) * BAND_MAXK;
+  bool pr[BAND_MAXK / BAND_THREADS];
 #pragma unroll
-        for (int r = 0; r < BAND_MAXK / BAND_THREADS; ++r) {
-          const int k = t + r * BAND_THREADS;
-          if (k < n) {
-            cp_async8(yb + k, P.y + ko + k);
-            if (VERIFY) cp_async8(xb + k, P.x_own + ko + k);
-          }
+  for (int r = 0; r < BAND_MAXK / BAND_THREADS; ++r) pr[r] = t + r * BAND_THREADS < n;
+  auto issue = [&](int i, int buf) {
+    if (i < ns) {
+      const int64_t ko = sbase[i];
+      if (ko >= 0) {
+        const double* __restrict__ ysrc = P.y + ko + t;
+        double* yb = ybuf + buf * BAND_MAXK + t;
+#pragma unroll
+        for (int r = 0; r < BAND_MAXK / BAND_THREADS; ++r)
+          if (pr[r]) cp_async8(yb + r * BAND_THREADS, ysrc + r * BAND_THREADS);
+        if (VERIFY) {
+          const double* __restrict__ xsrc = P.x_own + ko + t;
+          double* xb = xbuf + buf * BAND_MAXK + t;
+#pragma unroll
+          for (int r = 0; r < BAND_MAXK / BAND_THREADS; ++r)
+            if (pr[r]) cp_async8(xb + r * BAND_THREADS, xsrc + r * BAND_THREADS);
         }
       }
     }
     cp_async_commit();
   };
-  issue(0);
-  issue(1);
+  issue(0, 0);
+  issue(1, 1);
   bool prev_ok = false;                                      // CTA-uniform: slice i-1 was computed here (its results sit in obuf)
+  int buf = 0, buf_next2 = 2;                                // buffers of slice i and of slice i+2 (= the one slice i-1 used)
+  // obuf is written at the thread's grid point and read back in thread order: one pad double per 32 keeps both conflict-free
+  const int oq = q + (q >> 5), ot = t + (t >> 5);
   for (int i = 0; i < ns; ++i) {
     cp_async_wait<1>();                                      // this thread's part of slice i has landed
-    const int64_t s = ord[i];
-    const int64_t ko = P.knot_off[s];
-    const bool len_ok = (P.knot_off[s + 1] - ko) == (int64_t)n;
-    const double* yb = ybuf + (i % BAND_NBUF) * BAND_MAXK;
+    const bool len_ok = sbase[i] >= 0;
+    const double* yb = ybuf + buf * BAND_MAXK;
     bool ok = len_ok;
     if (len_ok) {                                            // every thread checks the knots it moved itself
-      const double* xb = xbuf + (i % BAND_NBUF) * BAND_MAXK;
+      const double* xb = xbuf + buf * BAND_MAXK;
 #pragma unroll
       for (int r = 0; r < BAND_MAXK / BAND_THREADS; ++r) {
         const int k = t + r * BAND_THREADS;
-        if (k < n) {
+        if (pr[r]) {
           ok = ok && (fabs(yb[k]) < INFINITY);
           if (VERIFY) ok = ok && (xb[k] == ladx[k]);        // ladx[k] was written by this same thread
         }
       }
     }
     const bool all_ok = __syncthreads_and(ok) != 0;          // the one barrier per slice: data visible, vote, buffers free
-    issue(i + 2);                                            // into the buffer slice i-1 was read from
+    issue(i + 2, buf_next2);                                 // into the buffer slice i-1 was read from
     if (i > 0 && prev_ok && t < n_q)                         // slice i-1: transposed through shared memory, stored coalesced
-      st_stream(P.yq + (int64_t)ord[i - 1] * n_q + t, obuf[((i - 1) & 1) * BAND_MAXQ + t]);
+      st_stream(P.yq + (int64_t)sid[i - 1] * n_q + t, obuf[((i - 1) & 1) * (BAND_MAXQ + 16) + ot]);
     if (all_ok) {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       const double* yw = yb + k0;
@@ -298,14 +345,16 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
         a2 = fma(w[j + 2], yw[j + 2], a2);
         a3 = fma(w[j + 3], yw[j + 3], a3);
       }
-      if (has_q) obuf[(i & 1) * BAND_MAXQ + q] = nan_q ? qnan() : (a0 + a1) + (a2 + a3);
+      if (has_q) obuf[(i & 1) * (BAND_MAXQ + 16) + oq] = nan_q ? qnan() : (a0 + a1) + (a2 + a3);
     } else if (t == 0) {
-      P.fb_list[atomicAdd(P.fb_count, 1u)] = (int32_t)s;     // a missing knot, off the ladder, another length: the exact solve
+      P.fb_list[atomicAdd(P.fb_count, 1u)] = sid[i];         // a missing knot, off the ladder, another length: the exact solve
     }
     prev_ok = all_ok;
+    buf_next2 = buf;                                         // slice i+3 reuses slice i's buffer
+    buf = buf + 1 == BAND_NBUF ? 0 : buf + 1;
   }
   __syncthreads();
-  if (prev_ok && t < n_q) st_stream(P.yq + (int64_t)ord[ns - 1] * n_q + t, obuf[((ns - 1) & 1) * BAND_MAXQ + t]);
+  if (prev_ok && t < n_q) st_stream(P.yq + (int64_t)sid[ns - 1] * n_q + t, obuf[((ns - 1) & 1) * (BAND_MAXQ + 16) + ot]);
   cp_async_wait<0>();
 }
 
@@ -320,18 +369,20 @@ extern "C" int64_t ivx_spline_band_len(int64_t n_ladders, int64_t n_q) {
 }
 
 extern "C" int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
-                                     int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok, ivx_stream_t stream_) {
+                                     int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok, int16_t* band_perm, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_ladders >= 0 && n_ladders < 65536 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_band_build: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_band_build: extrap must be 0, 1 or 2");
   if (n_ladders == 0 || n_q == 0) return IVX_OK;
-  IVX_REQUIRE(ladder_off && x_ladder && xq && band_k0 && band_w && ladder_ok, IVX_ERR_INVALID_ARG, "ivx_spline_band_build: null pointer");
+  IVX_REQUIRE(ladder_off && x_ladder && xq && band_k0 && band_w && ladder_ok && band_perm, IVX_ERR_INVALID_ARG, "ivx_spline_band_build: null pointer");
   k_band_build<<<dim3((unsigned)((n_q + 127) / 128), (unsigned)n_ladders), 128, 0, stream>>>((int32_t)n_ladders, ladder_off, x_ladder, (int32_t)n_q, xq, extrap,
                                                                                              band_k0, band_w, ladder_ok);
   IVX_LAUNCH_CHECK("k_band_build");
   if (n_q <= BAND_MAXQ) {
     k_band_check<<<(unsigned)n_ladders, 256, 0, stream>>>(ladder_off, x_ladder, (int32_t)n_q, xq, extrap, band_k0, band_w, ladder_ok);
     IVX_LAUNCH_CHECK("k_band_check");
+    k_band_perm<<<(unsigned)n_ladders, 32, 0, stream>>>((int32_t)n_q, band_k0, band_perm);
+    IVX_LAUNCH_CHECK("k_band_perm");
   }
   return IVX_OK;
 }
@@ -341,7 +392,7 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
                                           const int64_t* ladder_off, int64_t max_knots, const double* x_ladder, const double* x_own,
                                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                           const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
-                                          const uint8_t* ladder_ok, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
+                                          const uint8_t* ladder_ok, const int16_t* band_perm, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_slices >= 0 && n_slices < ((int64_t)1 << 31) && n_ladders >= 0 && n_ladders < 65536 && max_slices_per_ladder >= 0,
               IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: bad sizes");
@@ -349,12 +400,12 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: extrap must be 0, 1 or 2");
   if (n_slices == 0 || n_q == 0 || n_ladders == 0) return IVX_OK;
   IVX_REQUIRE(knot_off && x_off && slice_ladder && order && lad_slice_off && ladder_off && x_ladder && lu_cp && lu_inv && lu_ih && y && xq && band_k0 &&
-                  band_w && ladder_ok && yq && fb_list && fb_count,
+                  band_w && ladder_ok && band_perm && yq && fb_list && fb_count,
               IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: null pointer");
   IVX_CUDA(cudaMemsetAsync(fb_count, 0, 4, stream));
   BandParams P;
   P.knot_off = knot_off; P.order = order; P.lad_slice_off = lad_slice_off; P.ladder_off = ladder_off; P.x_ladder = x_ladder; P.x_own = x_own;
-  P.y = y; P.band_k0 = band_k0; P.band_w = band_w; P.ladder_ok = ladder_ok; P.yq = yq; P.fb_list = fb_list; P.fb_count = fb_count; P.n_q = (int32_t)n_q;
+  P.y = y; P.band_k0 = band_k0; P.band_w = band_w; P.ladder_ok = ladder_ok; P.perm = band_perm; P.yq = yq; P.fb_list = fb_list; P.fb_count = fb_count; P.n_q = (int32_t)n_q;
   // slices per CTA: as many as 48 (the weights are loaded once per CTA), but no fewer than ~3 CTAs per SM in the launch
   int64_t batch = (max_slices_per_ladder * n_ladders + 3 * (int64_t)sm_count() - 1) / (3 * (int64_t)sm_count());
   batch = batch < 4 ? 4 : (batch > BAND_BATCH ? BAND_BATCH : batch);
@@ -362,12 +413,12 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
   const dim3 grid((unsigned)((max_slices_per_ladder + batch - 1) / batch), (unsigned)n_ladders);
   if (grid.x > 0) {
     if (x_own) {
-      const size_t smem = (size_t)(2 * BAND_NBUF * BAND_MAXK + 2 * BAND_MAXQ + BAND_MAXK) * sizeof(double);
+      const size_t smem = (size_t)(2 * BAND_NBUF * BAND_MAXK + 2 * (BAND_MAXQ + 16) + BAND_MAXK) * sizeof(double);
       static DeviceOnce once;
       if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_band_apply<true><<<grid, BAND_THREADS, smem, stream>>>(P);
     } else {
-      const size_t smem = (size_t)(BAND_NBUF * BAND_MAXK + 2 * BAND_MAXQ) * sizeof(double);
+      const size_t smem = (size_t)(BAND_NBUF * BAND_MAXK + 2 * (BAND_MAXQ + 16)) * sizeof(double);
       static DeviceOnce once;
       if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_band_apply<false><<<grid, BAND_THREADS, smem, stream>>>(P);

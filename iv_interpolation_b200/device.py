@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 3, "spline_ladder_factor": 1,
-    "spline_band_build": 2, "spline_fit_eval_banded": 2, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
+    "spline_band_build": 3, "spline_fit_eval_banded": 2, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
 
@@ -457,6 +457,7 @@ class SplineBand:
     k0: torch.Tensor                # int32[n_ladders * n_q]
     w: torch.Tensor                 # float64[n_ladders * n_q * 48]
     ok: torch.Tensor                # uint8[n_ladders]
+    perm: torch.Tensor              # int16[n_ladders * 512]: grid point of every thread of the evaluation kernel
     n_q: int
     extrap: int
 
@@ -469,10 +470,10 @@ def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torc
     n_l, n_q = ladder_off.numel() - 1, xq.numel()
     if out is None or out.n_q != n_q or out.ok.numel() != n_l:
         out = SplineBand(_empty(n_l * n_q, torch.int32, xq), _empty(lib().ivx_spline_band_len(n_l, n_q), torch.float64, xq),
-                         _empty(n_l, torch.uint8, xq), n_q, int(extrap))
+                         _empty(n_l, torch.uint8, xq), _empty(n_l * 512, torch.int16, xq), n_q, int(extrap))
     out.extrap = int(extrap)
     check(lib().ivx_spline_band_build(n_l, _ptr(ladder_off), _ptr(x_ladder), n_q, _ptr(xq), int(extrap), _ptr(out.k0), _ptr(out.w),
-                                      _ptr(out.ok), _stream()), "ivx_spline_band_build")
+                                      _ptr(out.ok), _ptr(out.perm), _stream()), "ivx_spline_band_build")
     _count("spline_band_build")
     return out
 
@@ -499,7 +500,7 @@ def spline_fit_eval_banded(knot_off: torch.Tensor, x_off: torch.Tensor, slice_la
     check(lib().ivx_spline_fit_eval_banded(n_slices, _ptr(knot_off), _ptr(x_off), _ptr(slice_ladder), _ptr(order), _ptr(lad_slice_off), n_l,
                                            int(max_slices_per_ladder), _ptr(ladder_off), int(max_knots), _ptr(x_ladder),
                                            _ptr(x_own) if x_own is not None else None, _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q,
-                                           _ptr(xq), int(band.extrap), _ptr(band.k0), _ptr(band.w), _ptr(band.ok), _ptr(yq), _ptr(fb[0]),
+                                           _ptr(xq), int(band.extrap), _ptr(band.k0), _ptr(band.w), _ptr(band.ok), _ptr(band.perm), _ptr(yq), _ptr(fb[0]),
                                            _ptr(fb[1]), _stream()), "ivx_spline_fit_eval_banded")
     _count("spline_fit_eval_banded")
     return yq
