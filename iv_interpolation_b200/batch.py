@@ -274,12 +274,26 @@ class ProductionInterpolationBatch(InterpolationBatch):
             err = None
         except Exception as e:
             results, err = [None] * len(pieces), str(e)
+        if self.recompute_greeks and err is None:                              # one more launch over every piece's rows (f-4)
+            try:
+                self._add_greeks([r for r in results if r is not None])
+            except Exception as e:
+                results, err = [None] * len(pieces), str(e)
         elapsed = time.time() - t0
         chunks: Dict[str, List[pd.DataFrame]] = {}
         small: Dict[str, Optional[pd.DataFrame]] = {}
+        save_err: Dict[str, str] = {}
         for (sym, streamed), res in zip(owner, results):
             if res is not None:
                 res["batch_id"] = self.batch_id                                   # :312 / :352
+                # the reference saves every chunk as it is produced (:353) and every small symbol (:312); `sink` stands there.
+                # It ignores what _save_results_optimized returns; here a refused or failing save is reported on the symbol.
+                if self.sink is not None and sym not in save_err:
+                    try:
+                        if not self.sink(sym, res):
+                            save_err[sym] = "Failed to save to database"
+                    except Exception as e:
+                        save_err[sym] = str(e)
             if streamed:
                 chunks.setdefault(sym, [])
                 if res is not None:
@@ -294,6 +308,8 @@ class ProductionInterpolationBatch(InterpolationBatch):
                 statuses.append({"symbol": sym, "status": "skipped", "reason": "No data found"})                 # :286-287
             elif err is not None:
                 statuses.append({"symbol": sym, "status": "error", "error": err, "processing_time": elapsed})      # :324-331
+            elif sym in save_err:
+                statuses.append({"symbol": sym, "status": "error", "error": save_err[sym], "processing_time": elapsed})
             elif sym in chunks:
                 parts = chunks[sym]
                 if parts:

@@ -75,7 +75,8 @@ class CandleReconstructor:
         if n >= 1 and len(live) > 1 and H.task2_uniform([frames[i] for i in live]):
             got = H.reconstruct_uniform([frames[i] for i in live], n, self.target_frequency, datetime.now(),
                                         presorted=presorted, check_len=check_len)
-            if got is not None:
+            from .._lib import FLAG_UNSORTED
+            if got is not None and not (presorted and any(f & FLAG_UNSORTED for f in got[1])):
                 outs, fl = got
                 for k, i in enumerate(live):
                     results[i] = outs[k]
@@ -103,10 +104,16 @@ class CandleReconstructor:
                 logger.error("Candle reconstruction failed: non-positive frequency")
                 continue
             order = None
-            if not presorted:                                                    # core.py:60
-                key = np.where(inp.ts == F.NAT, np.iinfo(np.int64).max, inp.ts)
-                if len(key) > 1 and np.any(key[1:] < key[:-1]):
+            key = np.where(inp.ts == F.NAT, np.iinfo(np.int64).max, inp.ts)
+            if len(key) > 1 and np.any(key[1:] < key[:-1]):
+                if not presorted:                                                # core.py:60
                     order = np.argsort(key, kind="stable")
+                else:
+                    # complete_pipeline.py:685-710 does not sort, but its groupby still MERGES the rows of a bucket wherever they
+                    # stand, first/last in input order: rows are brought together bucket by bucket, input order kept inside one
+                    width = n * 60 * F.ticks_per_second(inp.unit)
+                    bucket = np.where(inp.ts == F.NAT, np.iinfo(np.int64).max, (inp.ts + inp.wall_shift) // width)
+                    order = np.argsort(bucket, kind="stable")
             inputs.append((inp, order)); srcs.append(src); slots.append(i)
         if not inputs:
             return results
@@ -128,7 +135,7 @@ class CandleReconstructor:
                     parts.append(a if order is None else a[order])
                 return np.ascontiguousarray(np.concatenate(parts))
 
-            ts = torch.from_numpy(cat(lambda p: p.ts)).to(dev)
+            ts = torch.from_numpy(cat(lambda p: np.where(p.ts == F.NAT, F.NAT, p.ts + p.wall_shift) if p.wall_shift else p.ts)).to(dev)
             cols = [torch.from_numpy(cat(lambda p, k=k: p.ohlcv[k])).to(dev) for k in range(5)]
             any_null = any(inputs[j][0].sym_valid is not None for j in members)
             sv = None

@@ -36,15 +36,28 @@ __device__ __forceinline__ int u_per_row(int strategy) {
 }
 __device__ __forceinline__ bool row_ok(double b) { return !(isnan(b) || b <= 0.0); }            // ohlcv_converter.py:152
 __device__ __forceinline__ bool vol_missing(double v) { return isnan(v) || v <= 0.0; }          // :373
-// np.float64.__round__(x, d) = rint(x * 10^d) / 10^d.  The division is by a constant: with rc = RN(1/s), q0 = RN(a rc),
-// r = a - s q0 (exact in one fma) and q = RN(q0 + r rc) is the correctly rounded quotient (Markstein) — three dependent
-// operations instead of the ~10 of a general division, and this sits in the serial chain of the carried close.  The
-// result is compared bit for bit with numpy's over millions of values in tests/test_gpu_bridge.py.
+// round(x, d) of a PYTHON float: the reference's rows come from df.iterrows() on a frame that holds strings and stamps next
+// to the prices (ohlcv_converter.py:150, complete_pipeline.py:476), so prices, draws and volumes are Python floats and
+// round() is the correctly rounded decimal rounding of the EXACT binary value, half to even — not numpy's
+// rint(x * 10^d) / 10^d, whose rounded product invents ties (100.35015 -> 100.3502 under numpy, 100.3501 in Python).
+//   n = the integer nearest to the exact x * 10^d:  p = RN(x s), e = x s - p exactly (one fma), a = rint(p), f = p - a
+//   exactly; the exact value a + f + e lies beyond the half-way point on f's side iff e points the same way and
+//   |e| > 1/2 - |f| (both exact) — then rint's answer moves by one; a true tie (e = 0, |f| = 1/2) keeps rint's even choice.
+//   result = RN(n / 10^d), which is what Python's dtoa/strtod round trip yields.  The division is by a constant: with
+//   rc = RN(1/s), q0 = RN(n rc), r = n - s q0 (exact in one fma), q = RN(q0 + r rc) is the correctly rounded quotient
+//   (Markstein) — three dependent operations instead of a general division; this sits in the serial chain of the carried
+//   close.  Compared bit for bit with Python's round over millions of values in tests/test_gpu_bridge.py.
 template <int D, bool CHECKED = true>
 __device__ __forceinline__ double round_np(double x) {
   constexpr double s = D == 4 ? 1e4 : 1e6;
   constexpr double rc = D == 4 ? 1e-4 : 1e-6;            // RN(1/s)
-  const double a = rint(x * s);
+  const double p = x * s;
+  double a = rint(p);
+  const double e = fma(x, s, -p), f = p - a;
+  if (fabs(p) < 2251799813685248.0) {                    // below 2^51: above it p is an integer and so is the exact product's rounding
+    const double g = 0.5 - fabs(f);
+    if ((f > 0.0 ? e : -e) > g) a += f > 0.0 ? 1.0 : -1.0;
+  }
   const double q0 = a * rc;
   const double r = fma(-s, q0, a);
   const double q = fma(r, rc, q0);

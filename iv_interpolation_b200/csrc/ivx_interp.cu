@@ -233,6 +233,9 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
   for (int d = 16; d > 0; d >>= 1) flags |= __shfl_xor_sync(IVX_FULL_MASK, flags, d);
 
   // ---- backward sweep: next valid knot of each interpolated column, slopes ----------------------------
+  // the forward sweep wrote gpos / s_* to global memory lane by lane; the backward sweep reads them back with another
+  // lane-to-row mapping: order the two (shuffles and ballots give no memory ordering between lanes)
+  __syncwarp();
   int32_t npos[3] = {-1, -1, -1};
   double nval[3] = {0, 0, 0};
   for (int64_t hi = a + n_on; hi > a; hi -= 32) {

@@ -80,6 +80,17 @@ class InterpInput:
     fill_idx_names: List[str] = field(default_factory=list)        # string / non-numeric fill cols
     fill_idx_valid: List[np.ndarray] = field(default_factory=list)  # bool[n] each (non-null)
     columns: List[str] = field(default_factory=list)    # input column order (incl. date)
+    fill_int_dtype: Dict[str, object] = field(default_factory=dict)  # integer forward-fill columns travelling as float64
+
+    def grid_is_dense(self) -> bool:
+        """Every grid point between min(date) and max(date) carries a source row: the left merge (core.py:54-55) then
+        introduces no NaN and pandas keeps an integer column's dtype; otherwise the column comes back float64."""
+        d = self.date[self.date != NAT]
+        if len(d) == 0:
+            return False
+        t0, step = int(d.min()), self.step
+        on = (d - t0) % step == 0
+        return int(np.unique((d[on] - t0) // step).size) == (int(d.max()) - t0) // step + 1
 
     @property
     def step(self) -> int:                               # core.py:45 freq='1min'
@@ -111,6 +122,12 @@ def interp_frame_to_arrays(df: pd.DataFrame) -> InterpInput:
         if _is_plain_numeric(col.dtype) and col.dtype.kind == "f":
             out.fill_num_names.append(c)
             out.fill_num.append(np.ascontiguousarray(col.to_numpy(dtype=np.float64)))
+        elif _is_plain_numeric(col.dtype) and col.dtype.kind in "iu" and (len(col) == 0 or int(np.abs(col.to_numpy()).max()) < 2 ** 53):
+            # integer strike / volume ...: exact in float64, and float64 is what the reference returns once the left merge has
+            # introduced a NaN (interp_arrays_to_frame restores the dtype on a dense grid, where it does not)
+            out.fill_num_names.append(c)
+            out.fill_num.append(np.ascontiguousarray(col.to_numpy(dtype=np.float64)))
+            out.fill_int_dtype[c] = col.dtype
         else:
             out.fill_idx_names.append(c)
             out.fill_idx_valid.append(np.ascontiguousarray(col.notna().to_numpy(dtype=bool)))
@@ -131,7 +148,7 @@ def interp_arrays_to_frame(
     m = len(out_date)
     cols: Dict[str, object] = {}
     cols["date"] = ticks_to_datetime(out_date, inp.unit, inp.tz).to_numpy() if inp.tz is None \
-        else ticks_to_datetime(out_date, inp.unit, inp.tz)
+        else ticks_to_datetime(out_date, inp.unit, inp.tz).array        # .array: no index alignment against the position labels
     interp_map = dict(zip(INTERP_COLS, out_interp))
     num_map = dict(zip(inp.fill_num_names, out_fill_num))
     idx_map = dict(zip(inp.fill_idx_names, out_fill_idx))
@@ -142,6 +159,8 @@ def interp_arrays_to_frame(
             cols[c] = interp_map[c]
         elif c in num_map:
             cols[c] = num_map[c]
+            if c in inp.fill_int_dtype and inp.grid_is_dense():
+                cols[c] = np.asarray(num_map[c]).astype(inp.fill_int_dtype[c])
         elif c in idx_map:
             cols[c] = _take_with_null(src[c], idx_map[c])
         else:                                           # extra column: merged but never filled
@@ -175,6 +194,7 @@ class CandleInput:
     ts: np.ndarray                   # int64[n]
     ohlcv: List[np.ndarray]          # 5 x float64[n]
     sym_valid: Optional[np.ndarray]  # bool[n] or None when every symbol is non-null
+    wall_shift: int = 0              # tz-aware stamps: ticks to add to ``ts`` (UTC) to get the local wall clock the reference floors
 
 
 def candle_frame_to_arrays(df: pd.DataFrame) -> CandleInput:
@@ -182,6 +202,17 @@ def candle_frame_to_arrays(df: pd.DataFrame) -> CandleInput:
     if "symbol" not in df.columns:
         raise KeyError("symbol")
     ts, unit, tz = datetime_to_ticks(df["timestamp"])
+    shift = 0
+    if tz is not None and len(ts):
+        # ``dt.floor`` on a tz-aware column (candle core.py:70) floors the LOCAL wall clock, not UTC: the two differ when the
+        # bucket width does not divide the UTC offset (60-minute candles in +05:30).  With one offset for the whole frame the
+        # wall clock is UTC + offset and the buckets are formed there; a frame that straddles an offset change (DST) is refused.
+        wall = pd.to_datetime(df["timestamp"]).dt.tz_localize(None).to_numpy(dtype=f"datetime64[{unit}]").view(np.int64)
+        ok = ts != NAT
+        off = np.unique(wall[ok] - ts[ok])
+        if len(off) > 1:
+            raise ValueError("the UTC offset changes inside the frame (DST): bucket boundaries are ambiguous")
+        shift = int(off[0]) if len(off) else 0
     ohlcv = []
     for c in ("open", "high", "low", "close", "volume"):
         if not _is_plain_numeric(df[c].dtype):
@@ -189,7 +220,7 @@ def candle_frame_to_arrays(df: pd.DataFrame) -> CandleInput:
         ohlcv.append(np.ascontiguousarray(df[c].to_numpy(dtype=np.float64)))
     valid = df["symbol"].notna().to_numpy(dtype=bool)
     return CandleInput(n=len(df), unit=unit, tz=tz, ts=ts, ohlcv=ohlcv,
-                       sym_valid=None if valid.all() else np.ascontiguousarray(valid))
+                       sym_valid=None if valid.all() else np.ascontiguousarray(valid), wall_shift=shift)
 
 
 def candle_arrays_to_frame(
@@ -205,10 +236,10 @@ def candle_arrays_to_frame(
 ) -> pd.DataFrame:
     """candle core.py:82-99: rename, metadata, column order; index is NOT reset."""
     m = len(out_ts)
-    ts = ticks_to_datetime(out_ts, inp.unit, inp.tz)
+    ts = ticks_to_datetime(np.asarray(out_ts, dtype=np.int64) - inp.wall_shift, inp.unit, inp.tz)   # bucket starts back from wall clock to UTC
     data = {
         "symbol": _take_with_null(src["symbol"], out_sym_row),
-        "timestamp": ts.to_numpy() if inp.tz is None else ts,
+        "timestamp": ts.to_numpy() if inp.tz is None else ts.array,      # .array: no index alignment against the group labels
         "open": out_ohlcv[0], "high": out_ohlcv[1], "low": out_ohlcv[2],
         "close": out_ohlcv[3], "volume": out_ohlcv[4],
     }

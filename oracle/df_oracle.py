@@ -95,7 +95,7 @@ class OracleCandleReconstructor:
             inp = F.candle_frame_to_arrays(minute_data)
             n = self.frequency_minutes
             res = O.ohlcv_reduce(
-                inp.ts, *inp.ohlcv, bucket_ticks=n * 60 * F.ticks_per_second(inp.unit),
+                np.where(inp.ts == F.NAT, F.NAT, inp.ts + inp.wall_shift) if inp.wall_shift else inp.ts, *inp.ohlcv, bucket_ticks=n * 60 * F.ticks_per_second(inp.unit),
                 min_count=n, sym_valid=inp.sym_valid,
             )
         except Exception:

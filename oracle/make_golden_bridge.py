@@ -76,8 +76,21 @@ def main():
                   (strat, 10, 1500, 0.02, 0.30, 64000.0), (strat, 11, 3, 0.0, 1.0, 100.0), (strat, 12, 64, 0.9, 0.5, 2.5)]
     specs.append(("spread_simulation", 13, 400, 0.05, 0.05, 1e-3))      # prices where the 4-decimal rounding bites
     specs.append(("trend_following", 14, 400, 0.05, 0.05, 1e-3))
+    # tidy prices (1 and 2 decimals) and 7-/8-decimal volumes: base +- 0.05 % and the volumes sit on decimal ties of the rounded
+    # place, where Python's round (the reference's rows are object Series: Python floats) and numpy's differ
+    for j, strat in enumerate(("simple_spread", "price_as_midpoint", "spread_simulation", "trend_following", "pipeline")):
+        specs.append((strat, 20 + j, 300, 0.03, 0.10, -(1 + j % 2)))
     for k, (strat, seed, n, nan_base, bad_vol, price) in enumerate(specs):
-        df = make_frame(seed, n, nan_base, bad_vol, price)
+        if price < 0:
+            df = make_frame(seed, n, nan_base, bad_vol, 100.0)
+            dec = int(-price)
+            tidy = np.round(np.abs(df["underlying_price"].to_numpy()) + 0.5, dec)
+            keep = df["underlying_price"].to_numpy()
+            df["underlying_price"] = np.where(np.isnan(keep) | (keep <= 0), keep, tidy)
+            df["mark_price"], df["index_price"] = df["underlying_price"] + 1.0, df["underlying_price"] - 1.0
+            df["volume"] = np.where(df["volume"].to_numpy() > 0, np.round(df["volume"].to_numpy(), 7 + seed % 2), df["volume"].to_numpy())
+        else:
+            df = make_frame(seed, n, nan_base, bad_vol, price)
         np.random.seed(1000 + seed)
         if strat == "pipeline":
             res = pipe(None, df.rename(columns={"timestamp": "date"}))

@@ -205,23 +205,34 @@ def test_bridge_convert_frames_status_dicts(dev, golden_bridge):
         logging.disable(logging.NOTSET)
 
 
-def test_bridge_rounding_matches_numpy_over_millions(dev):
-    """The constant division behind round(x, 4) / round(x, 6) (three dependent operations instead of a general
-    division) against numpy's rint(x * 10^d) / 10^d on 4 million values across twelve decades, bit for bit."""
+def test_bridge_rounding_matches_python_round_over_millions(dev):
+    """round(x, 4) / round(x, 6) as the reference evaluates them — PYTHON's round on Python floats (its rows come from iterrows on
+    a mixed frame): correctly rounded decimal rounding of the exact binary value.  2 million values across twelve decades plus
+    the cases where numpy's rint(x * 10^d) / 10^d differs: tidy 1- to 3-decimal prices whose +-0.05 % lands on a fifth-place 5,
+    and 7-/8-decimal volumes.  Bit for bit."""
     rng = np.random.default_rng(2024)
     n = 2_000_000
     base = 10.0 ** rng.uniform(-5, 7, n)
     base[:1000] = np.round(rng.uniform(0, 100, 1000), 4) + 0.00005          # decimal ties of the 4th place
+    base[1000:200_000] = np.round(rng.uniform(0.5, 5000, 199_000), 1)        # tidy prices: base * 1.0005 has a 5 in the fifth place
+    base[200_000:400_000] = np.round(rng.uniform(0.5, 5000, 200_000), 2)
+    base[400_000:500_000] = np.round(rng.uniform(0.5, 70000, 100_000), 3)
     vol = 10.0 ** rng.uniform(-7, 6, n)
+    vol[:300_000] = np.round(rng.exponential(5.0, 300_000), 7) + 5e-7
+    vol[300_000:600_000] = np.round(rng.exponential(5.0, 300_000), 8)
+    vol = np.where(vol > 0, vol, 1.0)
     u = rng.random(n)
     got = _run(dev, "simple_spread", np.array([0, n], np.int64), base, vol, u, np.zeros(0), np.zeros(0))
-    r4 = lambda x: np.rint(x * 1e4) / 1e4
+    rpy = lambda a, d: np.array([round(float(x), d) for x in a])
     spread = base * 0.001
     hs = spread / 2
-    assert np.array_equal(got["open"], r4(base))
-    assert np.array_equal(got["high"], r4(base + hs)) and np.array_equal(got["low"], r4(base - hs))
-    assert np.array_equal(got["close"], r4(base + (-hs + (hs - -hs) * u)))
-    assert np.array_equal(got["volume"], np.rint(vol * 1e6) / 1e6)
+    assert np.array_equal(got["open"], rpy(base, 4))
+    hi_w, lo_w = rpy(base + hs, 4), rpy(base - hs, 4)
+    assert np.array_equal(got["high"], hi_w) and np.array_equal(got["low"], lo_w)
+    assert np.array_equal(got["close"], rpy(base + (-hs + (hs - -hs) * u), 4))
+    assert np.array_equal(got["volume"], rpy(vol, 6))
+    # the tape must contain what separates the two roundings
+    assert (hi_w != np.rint((base + hs) * 1e4) / 1e4).sum() > 10_000
 
 
 def test_pipeline_batch_equals_the_oracle_chain(dev):

@@ -684,6 +684,23 @@ def test_production_batch_streams_large_symbols_in_chunks(dev):
     assert summary["success_count"] == 5 and summary["skip_count"] == 2
     mirrored = ProductionInterpolationBatch(batch_id=9, mirror_reference_status=True).run({"big0": frames["big0"]})[1][0]
     assert mirrored["status"] == "error" and "has no len()" in mirrored["error"]
+    # the sink stands where the reference saves (:312, :353): once per chunk of a streamed symbol, once per small symbol
+    calls = []
+    def recording(sym, frame):
+        calls.append((sym, len(frame), "delta" in frame.columns))
+        return True
+    outs2, st2, _ = ProductionInterpolationBatch(batch_id=9, sink=recording, recompute_greeks=True).run(frames)
+    assert sum(1 for c in calls if c[0] == "big0") == 3 and sum(1 for c in calls if c[0] == "small1") == 1
+    assert all(c[2] for c in calls) and "vega" in outs2["big1"].columns                     # Greeks were added before the save
+    assert sum(c[1] for c in calls if c[0] == "big0") == by["big0"]["output_rows"]
+    def failing(sym, frame):
+        if sym == "small0":
+            raise RuntimeError("disk full")
+        return sym != "big1"
+    st3 = {s["symbol"]: s for s in ProductionInterpolationBatch(batch_id=9, sink=failing).run(frames)[1]}
+    assert st3["small0"]["status"] == "error" and st3["small0"]["error"] == "disk full"
+    assert st3["big1"] == {"symbol": "big1", "status": "error", "error": "Failed to save to database", "processing_time": st3["big1"]["processing_time"]}
+    assert st3["big0"]["status"] == "success" and st3["small1"]["status"] == "success"
 
 
 def test_implied_vol_two_kernel_form_equals_the_one_launch_form(dev):
@@ -795,3 +812,23 @@ def test_spline_banded_verify_and_unusable_ladders(dev):
         want = O.natural_spline_eval(xs[s], ys[s], xq, 1)
         scale = max(1.0, np.abs(want).max())
         assert np.abs(got[s] - want).max() <= 1e-8 * scale, (s, lad_of[s], np.abs(got[s] - want).max())
+
+
+def test_aggregate_to_5min_merges_buckets_of_unsorted_input_like_groupby(dev):
+    """complete_pipeline.py:685-710 does not sort, but its groupby merges a bucket's rows wherever they stand (first/last in input
+    order).  The presorted entry used to split such a bucket into several candles; it now brings the rows together bucket by bucket."""
+    from iv_interpolation_b200.candle_reconstruction.core import CandleReconstructor
+    rng = np.random.default_rng(8)
+    n = 137
+    ts = pd.date_range("2024-03-01 09:02", periods=n, freq="1min")
+    b = 100 + np.cumsum(rng.normal(0, 1, n))
+    f = pd.DataFrame({"symbol": "S", "timestamp": ts, "open": b, "high": b + 1, "low": b - 1, "close": b + 0.3, "volume": rng.exponential(5, n)})
+    f = f.iloc[rng.permutation(n)].reset_index(drop=True)
+    got = CandleReconstructor("5min").aggregate_to_5min(f.copy())
+    g = f.copy()
+    g["time_group"] = g["timestamp"].dt.floor("5min")
+    want = g.groupby("time_group").agg({"open": "first", "high": "max", "low": "min", "close": "last", "volume": "sum", "symbol": "first"}).reset_index()
+    want = want[want["time_group"].isin(g.groupby("time_group").size().loc[lambda s: s >= 5].index)]
+    assert len(got) == len(want) and (got["timestamp"].to_numpy() == want["time_group"].to_numpy()).all()
+    for c in ("open", "high", "low", "close", "volume"):
+        assert np.array_equal(got[c].to_numpy(), want[c].to_numpy()), c

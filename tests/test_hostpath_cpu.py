@@ -115,3 +115,50 @@ def test_uniform_schema_detection():
     assert not H.task1_uniform([a, b[list(b.columns[::-1])]])                  # another column order
     assert not H.task1_uniform([a.assign(date=a["date"].dt.tz_localize("UTC"))])
     assert not H.task1_uniform([])
+
+
+@pytest.mark.skipif(not RL.available(), reason="neither /root/reference nor oracle/_ref is present")
+def test_integer_fill_columns_take_the_numeric_path_like_the_reference():
+    """Integer strike / volume columns (and five non-float fill columns in all) used to overflow the four string slots of a
+    launch; they travel as float64 (exact below 2^53) and come back float64 — or with their own dtype where the grid is dense and
+    the reference's merge introduces no NaN.  Host logic shared by the product and the DataFrame oracle, held to the reference."""
+    from iv_interpolation_b200 import frames as F
+    from oracle.df_oracle import OracleIVInterpolator
+    tp = tapes.make_contract_tape(1, 2, rows_per_contract=14)
+    f = tp.frame(0)
+    f["strike"] = f["strike"].astype(np.int64)
+    f["volume"] = np.arange(len(f), dtype=np.int64)
+    inp = F.interp_frame_to_arrays(f)
+    assert inp.fill_idx_names == ["symbol", "callput", "record_time"] and set(inp.fill_int_dtype) == {"strike", "volume"}
+    golden_io.assert_frames_match(RL.reference_interpolate(f), OracleIVInterpolator().interpolate_symbol(f))
+    g = tp.frame(1)                                              # the same on a dense 1-minute grid: dtypes survive
+    g["date"] = pd.date_range("2023-03-15", periods=len(g), freq="1min")
+    g["strike"] = g["strike"].astype(np.int64)
+    g["quote_volume"] = np.arange(len(g), dtype=np.int32)
+    want, got = RL.reference_interpolate(g), OracleIVInterpolator().interpolate_symbol(g)
+    assert want["strike"].dtype == np.int64 and got["strike"].dtype == np.int64 and got["quote_volume"].dtype == np.int32
+    golden_io.assert_frames_match(want, got)
+
+
+@pytest.mark.skipif(not RL.available(), reason="neither /root/reference nor oracle/_ref is present")
+def test_tz_aware_candles_floor_the_local_wall_clock():
+    """dt.floor on a tz-aware column floors local wall time: 60-minute candles in +05:30 start on the local hour, not the UTC one;
+    a leading partial bucket (index labels 1..) must not misalign the stamps.  Frames that straddle a DST change are refused."""
+    from oracle.df_oracle import OracleCandleReconstructor
+    n = 200
+    b = 100 + np.cumsum(np.random.default_rng(0).normal(0, 1, n))
+    for tz in ("Asia/Kolkata", "UTC", "America/New_York"):
+        ts = pd.date_range("2024-03-01 09:07", periods=n, freq="1min", tz=tz)
+        f = pd.DataFrame({"symbol": "S", "timestamp": ts, "open": b, "high": b + 1, "low": b - 1, "close": b + 0.2, "volume": 1.0})
+        for freq in ("60min", "5min", "45min"):
+            golden_io.assert_frames_match(RL.reference_reconstruct(f, freq), OracleCandleReconstructor(freq).reconstruct_symbol_candles(f))
+    dst = pd.date_range("2024-03-10 01:30", periods=90, freq="1min", tz="America/New_York")      # crosses 02:00 -> 03:00
+    f = pd.DataFrame({"symbol": "S", "timestamp": dst, "open": b[:90], "high": b[:90] + 1, "low": b[:90] - 1, "close": b[:90], "volume": 1.0})
+    assert OracleCandleReconstructor("5min").reconstruct_symbol_candles(f) is None
+    # Task 1 with tz-aware dates and dropped leading rows (index labels start above 0)
+    from oracle.df_oracle import OracleIVInterpolator
+    tp = tapes.make_contract_tape(3, 8)
+    g = tp.frame(3)
+    g["date"] = g["date"].dt.tz_localize("Asia/Kolkata")
+    g.loc[0, "iv"] = np.nan
+    golden_io.assert_frames_match(RL.reference_interpolate(g), OracleIVInterpolator().interpolate_symbol(g))

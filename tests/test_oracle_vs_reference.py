@@ -94,9 +94,14 @@ def test_bridge_oracle_equals_reference_on_random_frames():
         n = int(rng.integers(1, 400))
         price = float(rng.choice([25000.0, 0.37, 3.0, 64000.0]))
         base = price + np.cumsum(rng.normal(0, price * 0.002, n))
+        vol = rng.exponential(5.0, n)
+        if case % 3 == 1:
+            # tidy prices (1 or 2 decimals) and 7-/8-decimal volumes: base * 1.0005 and the volumes land on decimal ties of the
+            # rounded place, which is where Python's round (what the reference's object rows get) and numpy's part ways
+            base = np.round(np.abs(base) + 0.5, int(rng.integers(1, 3)))
+            vol = np.round(vol, int(rng.integers(7, 9)))
         base[rng.random(n) < 0.05] = np.nan
         base[rng.random(n) < 0.02] = 0.0
-        vol = rng.exponential(5.0, n)
         vol[rng.random(n) < rng.choice([0.0, 0.2])] = np.nan
         df = pd.DataFrame({"symbol": "S", "timestamp": pd.date_range("2024-03-01", periods=n, freq="1min"), "underlying_price": base,
                            "mark_price": base, "index_price": base, "volume": vol})
