@@ -47,22 +47,27 @@ __device__ __forceinline__ bool vol_missing(double v) { return isnan(v) || v <= 
 //   rc = RN(1/s), q0 = RN(n rc), r = n - s q0 (exact in one fma), q = RN(q0 + r rc) is the correctly rounded quotient
 //   (Markstein) — three dependent operations instead of a general division; this sits in the serial chain of the carried
 //   close.  Compared bit for bit with Python's round over millions of values in tests/test_gpu_bridge.py.
+//   Large |x| (ulp(x) above one unit of the rounded place: 2^39 for 4 decimals, 2^33 for 6; also inf and NaN) round to
+//   themselves; below that x * 10^d stays under 2^53 and every integer involved is exact.
 template <int D, bool CHECKED = true>
 __device__ __forceinline__ double round_np(double x) {
   constexpr double s = D == 4 ? 1e4 : 1e6;
   constexpr double rc = D == 4 ? 1e-4 : 1e-6;            // RN(1/s)
+  constexpr double BIG = D == 4 ? 549755813888.0 : 8589934592.0;      // 2^39, 2^33
+  if (!(fabs(x) < BIG)) return x;
   const double p = x * s;
   double a = rint(p);
-  const double e = fma(x, s, -p), f = p - a;
-  if (fabs(p) < 2251799813685248.0) {                    // below 2^51: above it p is an integer and so is the exact product's rounding
+  const double e = fma(x, s, -p), f = p - a;             // both exact
+  if (fabs(p) < 4503599627370496.0) {                    // below 2^52
     const double g = 0.5 - fabs(f);
     if ((f > 0.0 ? e : -e) > g) a += f > 0.0 ? 1.0 : -1.0;
+  } else if (fabs(e) == 0.5) {                           // p is an integer and the exact product sits half way to the next one: even wins
+    const double half = 0.5 * p;
+    if (half != rint(half)) a = p + (e + e);
   }
   const double q0 = a * rc;
   const double r = fma(-s, q0, a);
-  const double q = fma(r, rc, q0);
-  if (!CHECKED) return q;                                // callers that know |x| < 1e290
-  return fabs(q0) <= 1.7976931348623157e308 ? q : q0;    // x * s overflowed: inf / s = inf (the residual would be NaN)
+  return fma(r, rc, q0);
 }
 __device__ __forceinline__ double uni(double lo, double hi, double u) { return lo + (hi - lo) * u; }   // RandomState.uniform
 

@@ -249,7 +249,8 @@ class InterpolatedToOHLCVConverter:
             ok = ~(np.isnan(base) | (base <= 0))
             need = ok & (np.isnan(vol) | (vol <= 0))
         u, e, z = draw_tapes(rs, strategy, ok, need)       # symbol after symbol, row after row: the reference's order
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        from ..hostpath import _to_device
+        t = lambda a: _to_device(np.ascontiguousarray(a), dev)
         d_off, d_base, d_vol = t(off), t(base), t(vol)
         plan = D.bridge_plan(d_off, d_base, d_vol)
         if plan.total != int(ok.sum()) or plan.total_e != int(need.sum()):

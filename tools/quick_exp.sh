@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "banded" 2>&1 | tail -3
-python bench.py --skip-e2e --skip-contracts --skip-dropin --skip-cpu --skip-kernels --steps 5 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], {k:v['ms'] for k,v in d['kernels'].items()}, d['chain_layout_resident']['stage_ms'], d['checksum_close'], d['chain_layout_resident']['checksum_close'])"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
