@@ -421,8 +421,15 @@ def run_gpu(args):
         e2e_q = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, "quotes")
 
     # ---- reference-pinned kernels A and B on a config-3-shaped tape, every rank its own contracts --------
-    del pipe, res
+    del pipe, res, chain, sc
     torch.cuda.empty_cache()
+    stress = None
+    if rank == 0 and not args.skip_stress:
+        try:
+            stress = bench_stress(args, torch, D, SF, tapes, dev, peak)
+        except Exception as e:       # a reported extra: never lose the line
+            stress = {"failed": repr(e)}
+        torch.cuda.empty_cache()
     if not args.skip_kernels:
         ab = _bench_ab(args, torch, D, tapes, dev, peak, rank, world, barrier, max_over_ranks)
         kernels.update(ab)
@@ -451,7 +458,7 @@ def run_gpu(args):
                 "surface_points_per_sec": world * n_t * N_GRID_M * N_GRID_K / (ms_step / 1e3),
                 "candles_per_step": world * n_buckets * N_GRID_M * N_GRID_K,
                 "roofline": roofline, "kernels": kernels, "chain_layout_resident": chain_layout, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
-                "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv, "contracts": contracts, "e2e_dropin": dropin}
+                "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv, "contracts": contracts, "e2e_dropin": dropin, "kernels_stress": stress}
         _emit(line)
     ctx.close()
 
@@ -495,6 +502,78 @@ def run_gpu_contracts(ctx, args):
                 "clocks": clocks, "counts": {k: c[k] for k in ("interp_rows", "minute_candles", "candles_5min", "source_rows", "batches_per_rank")}}
         _emit(line)
     ctx.close()
+
+
+def bench_stress(args, torch, D, SF, tapes, dev, peak):
+    """The same pipeline on tapes that are NOT the friendliest possible (one tenth of the day each, times scaled to the day):
+      missing    2 % of the prices are NaN: the affected slices leave the banded spline for the exact scan (squeeze + general solve);
+      shifted    1 % of the stamps quote on a ladder shifted by half a strike step: those slices fail the bit-for-bit ladder check;
+      iid        SURVEY.md 8(d) config 2 as written: sigma ~ U(0.05, 1.5), T ~ U(1/365, 2) years, K ~ U(0.5, 1.5) S per QUOTE
+                 (IV kernel only: iid quotes form no smile to fit).
+    Reported per tape: stage times per day, the fraction of warps the IV fast path deferred to its retry kernel, the fraction of
+    slices the banded spline sent to the exact solve."""
+    n_t = max(60, (args.n_t or N_T_DAY) // 10 // 60 * 60)
+    scale = N_T_DAY / n_t
+    spec = SF.ChainSpec(n_t, N_EXP, N_STRIKE, N_GRID_K, N_GRID_M, bucket_ticks=60 * tapes.US, min_count=1)
+    out = {"stamps": n_t, "note": f"{n_t} stamps per tape, times scaled x{scale:.1f} to the {N_T_DAY}-stamp day"}
+
+    def run(chain, label):
+        pipe = SF.SurfacePipeline(spec, dev, max_buckets=n_t // 60 + 2)
+        pipe.plan_buckets(chain.ts)
+        for _ in range(2):
+            pipe.run(chain)
+        ev = {st: [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for st in pipe.STAGES}
+        res = pipe.run(chain, events=ev)
+        torch.cuda.synchronize()
+        n_warps = (spec.n_quotes + 31) // 32
+        deferred = int(pipe._iv_ws[:4].view(torch.int32).item()) if pipe._iv_ws is not None else None
+        fb = int(pipe._fb[1].item()) if getattr(pipe, "_fb", None) is not None else None
+        ok = ~torch.isnan(chain.price)
+        iv_nan = float(torch.isnan(res.iv[ok]).double().mean().item())
+        out[label] = {"stage_ms_per_day": {st: round(ev[st][0].elapsed_time(ev[st][1]) * scale, 3) for st in pipe.STAGES},
+                      "iv_warps_deferred_frac": None if deferred is None else round(deferred / n_warps, 6),
+                      "spline_slices_exact_frac": None if fb is None else round(fb / (n_t * N_EXP), 6),
+                      "iv_nan_frac_of_quoted": round(iv_nan, 6)}
+        del pipe, res
+
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    chain = tapes.make_quote_chain(201, spec, dev, drop_frac=0.02)
+    run(chain, "missing_2pct")
+    del chain
+    chain = tapes.make_quote_chain(202, spec, dev)
+    step = float(chain.K[1] - chain.K[0])
+    per_t = N_EXP * N_STRIKE
+    moved = torch.nonzero(torch.rand(n_t, generator=g, device=dev) < 0.01).flatten()
+    moved = moved[moved > 0]                                 # the first stamp defines the ladders
+    for t in moved.tolist():
+        sl = slice(t * per_t, (t + 1) * per_t)
+        chain.K[sl] += 0.5 * step
+        chain.price[sl] = D.bs_price(chain.S[sl], chain.K[sl], chain.T[sl], chain.r[sl], chain.sigma_true[sl], chain.is_call[sl])
+    run(chain, "shifted_ladder_1pct")
+    out["shifted_ladder_1pct"]["stamps_moved"] = int(moved.numel())
+    # iid config-2 quotes: per-quote sigma, T, K — the IV kernel alone
+    n = spec.n_quotes
+    f64 = dict(dtype=torch.float64, device=dev)
+    S = torch.full((n,), 4500.0, **f64)
+    K = S * (0.5 + torch.rand(n, generator=g, **f64))
+    T = 1.0 / 365.0 + torch.rand(n, generator=g, **f64) * (2.0 - 1.0 / 365.0)
+    sig = 0.05 + 1.45 * torch.rand(n, generator=g, **f64)
+    r = torch.full((n,), 0.05, **f64)
+    call = (torch.rand(n, generator=g, device=dev) < 0.5).to(torch.uint8)
+    price = D.bs_price(S, K, T, r, sig, call)
+    ws = torch.empty(D.lib().ivx_bs_implied_vol_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    iv = torch.empty(n, **f64)
+    for _ in range(2):
+        D.bs_implied_vol(price, S, K, T, r, call, out=iv, workspace=ws)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); D.bs_implied_vol(price, S, K, T, r, call, out=iv, workspace=ws); e1.record(); torch.cuda.synchronize()
+    okq = ~torch.isnan(iv)
+    err = (iv[okq] - sig[okq]).abs()
+    out["iid_cfg2"] = {"implied_vol_ms_per_day": round(e0.elapsed_time(e1) * scale, 3), "frac_hbm": round(n * BYTES_PER_QUOTE / (e0.elapsed_time(e1) / 1e3) / 1e9 / peak, 4),
+                       "iv_warps_deferred_frac": round(int(ws[:4].view(torch.int32).item()) / ((n + 31) // 32), 6),
+                       "solved_frac": round(float(okq.double().mean().item()), 6),
+                       "round_trip_within_1e-8_frac": round(float((err <= 1e-8).double().mean().item()), 6)}
+    return out
 
 
 def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, layout):
@@ -1038,6 +1117,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--workload", choices=("surface", "contracts", "dropin"), default="surface")
     ap.add_argument("--skip-dropin", action="store_true")
+    ap.add_argument("--skip-stress", action="store_true")
     ap.add_argument("--dropin-contracts", type=int, default=DROPIN_CONTRACTS)
     ap.add_argument("--skip-contracts", action="store_true", help="leave the contracts object out of the surface line")
     ap.add_argument("--ct-underlyings", type=int, default=CT_UNDERLYINGS)

@@ -115,7 +115,12 @@ def test_config2_shape_surface_two_routes(dev):
     ok = ~torch.isnan(iv_a)
     assert float(ok.double().mean()) > 0.99
     err = (iv_a[ok] - chain.sigma_true[ok]).abs()                                 # round trip sigma -> price -> sigma at full width
-    assert float((err <= 1e-8).double().mean()) >= 0.999 and float(err.max()) <= 1e-5
+    # every quote within 1e-8 plus what its own conditioning allows (64 ulps of the inverted quantity over vega): no quota, no 1e-5
+    from tests.ivcond import iv_allowed
+    g = lambda name: getattr(chain, name)[ok]
+    allowed = iv_allowed(g("price"), g("S"), g("K"), g("T"), g("r"), g("is_call"), chain.sigma_true[ok], xp=torch)
+    assert bool((err <= allowed).all()), f"worst excess {float((err - allowed).max()):.3e}"
+    assert float((allowed <= 2e-8).double().mean()) >= 0.99 and float((err <= 1e-8).double().mean()) >= 0.999
     del a
     sc = SF.StructuredChain.from_quotes(chain)
     b = SF.SurfacePipeline(spec, dev).run(sc)
