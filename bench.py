@@ -415,10 +415,15 @@ def run_gpu(args):
     roofline["fp64_fma_peak_tflops_measured"] = round(fp64_tflops, 2)
 
     # ---- e2e: the same day streamed from pinned host memory ---------------------------------------------
-    e2e = e2e_q = None
+    e2e = e2e_q = e2e_t = probe = None
     if not args.skip_e2e:
+        probe = _pcie_probe(ctx)
         e2e = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, "chain")
+        e2e_t = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, "ticks")
         e2e_q = _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, "quotes")
+        for e in (e2e, e2e_t, e2e_q):
+            e["pcie_probe_h2d_gbs_per_rank"] = probe["h2d_gbs_per_rank"]
+            e["pcie_of_probe"] = round(e["pcie_gbs"] / (sum(probe["h2d_gbs_per_rank"]) / world), 3)     # this rank's H2D rate / what the bare probe gets
 
     # ---- reference-pinned kernels A and B on a config-3-shaped tape, every rank its own contracts --------
     del pipe, res, chain, sc
@@ -457,7 +462,7 @@ def run_gpu(args):
                            "full_day": n_t == N_T_DAY},
                 "surface_points_per_sec": world * n_t * N_GRID_M * N_GRID_K / (ms_step / 1e3),
                 "candles_per_step": world * n_buckets * N_GRID_M * N_GRID_K,
-                "roofline": roofline, "kernels": kernels, "chain_layout_resident": chain_layout, "cpu_baseline": cb, "e2e": e2e, "e2e_per_quote_layout": e2e_q, "gpu_launches": launches * world,
+                "roofline": roofline, "kernels": kernels, "chain_layout_resident": chain_layout, "cpu_baseline": cb, "e2e": e2e, "e2e_tick_layout": e2e_t, "e2e_per_quote_layout": e2e_q, "pcie_probe": probe, "gpu_launches": launches * world,
                 "clocks": clocks, "checksum_close": checksum, "nan_iv_frac": nan_iv, "contracts": contracts, "e2e_dropin": dropin, "kernels_stress": stress}
         _emit(line)
     ctx.close()
@@ -522,17 +527,20 @@ def bench_stress(args, torch, D, SF, tapes, dev, peak):
         pipe.plan_buckets(chain.ts)
         for _ in range(2):
             pipe.run(chain)
+            torch.cuda.synchronize()
         ev = {st: [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for st in pipe.STAGES}
         res = pipe.run(chain, events=ev)
         torch.cuda.synchronize()
         n_warps = (spec.n_quotes + 31) // 32
         deferred = int(pipe._iv_ws[:4].view(torch.int32).item()) if pipe._iv_ws is not None else None
-        fb = int(pipe._fb[1].item()) if getattr(pipe, "_fb", None) is not None else None
+        fb = int(pipe._fb[1].item()) if getattr(pipe, "_fb", None) is not None and not pipe.banded_switched_off else None
         ok = ~torch.isnan(chain.price)
         iv_nan = float(torch.isnan(res.iv[ok]).double().mean().item())
         out[label] = {"stage_ms_per_day": {st: round(ev[st][0].elapsed_time(ev[st][1]) * scale, 3) for st in pipe.STAGES},
                       "iv_warps_deferred_frac": None if deferred is None else round(deferred / n_warps, 6),
                       "spline_slices_exact_frac": None if fb is None else round(fb / (n_t * N_EXP), 6),
+                      "strike_spline_path": "scan kernel (the pipeline left the banded operators after its first run: most slices need the exact solve)"
+                                            if pipe.banded_switched_off else "banded operators + exact solve of the flagged slices",
                       "iv_nan_frac_of_quoted": round(iv_nan, 6)}
         del pipe, res
 
@@ -576,32 +584,61 @@ def bench_stress(args, torch, D, SF, tapes, dev, peak):
     return out
 
 
+def _pcie_probe(ctx):
+    """Bare pinned-memory copies, all ranks at once: what the box's host side gives every GPU when N ranks pull together —
+    the denominator of the end-to-end figures (1 GiB per direction, best of 4; 2 GiB of pinned memory per rank)."""
+    torch = ctx.torch
+    n = 1 << 27                                                      # 1 GiB of float64
+    host = torch.empty(n, dtype=torch.float64).pin_memory()
+    host.fill_(1.0)
+    devbuf = torch.empty(n, dtype=torch.float64, device=ctx.dev)
+    res = {}
+    for name, (dst, src) in {"h2d": (devbuf, host), "d2h": (host, devbuf)}.items():
+        best = float("inf")
+        for it in range(5):
+            ctx.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); dst.copy_(src, non_blocking=True); b.record(); torch.cuda.synchronize()
+            if it:
+                best = min(best, a.elapsed_time(b))
+        res[name + "_gbs_per_rank"] = [round(x, 2) for x in ctx.gather_floats(n * 8 / (best / 1e3) / 1e9)]
+    res["how"] = "torch copy_ of 1 GiB between pinned host memory and the device, every rank at the same time (barrier before each copy), best of 4"
+    del host, devbuf
+    return res
+
+
 def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over_ranks, layout):
     """Through the host-facing entry (surface.HostSurfaceStream): every step copies the whole day's quotes
     H2D from pinned memory, chunk by chunk, and the candles D2H.  The host tape holds RING distinct chunks
     (pinned) that are re-sent cyclically until the day's stamps are covered — every byte crosses PCIe.
     layout "chain": S per stamp, K and call/put per contract (sent once), T per (stamp, expiry) — 8 B per quote;
+    layout "ticks": the chain layout with prices as int32 ticks of 1e-4 (the reference's DECIMAL(15,4)) — 4 B per quote;
     layout "quotes": every column per quote — 41 B per quote."""
-    ring = 8
     n_chunks = max(1, n_t // CHUNK_T)
-    ring = min(ring, n_chunks)
+    # the host tape: distinct pinned chunks re-sent cyclically; at least ~2 GB of them so that the tape cannot sit in the host's
+    # last-level cache (432 MiB did in round 1)
+    chunk_bytes = CHUNK_T * N_EXP * N_STRIKE * {"chain": 8, "ticks": 4, "quotes": 41}[layout]
+    ring = min(n_chunks, max(8, -(-(2 << 30) // chunk_bytes)))
     cspec = SF.ChainSpec(CHUNK_T, N_EXP, N_STRIKE, N_GRID_K, N_GRID_M, bucket_ticks=60 * tapes.US, min_count=1)
     per = cspec.n_quotes
     pin = lambda t: t.cpu().pin_memory()
     host = []
-    sc = SF.StructuredChain.from_quotes(chain) if layout == "chain" else None
+    sc = SF.StructuredChain.from_quotes(chain) if layout in ("chain", "ticks") else None
     for i in range(ring):
         sl, tl = slice(i * per, (i + 1) * per), slice(i * CHUNK_T, (i + 1) * CHUNK_T)
-        if layout == "chain":
-            host.append(SF.HostChainChunk(ts=pin(sc.ts[tl]), price=pin(sc.price[sl]), S_t=pin(sc.S_t[tl]),
-                                          T_te=pin(sc.T_te[i * CHUNK_T * N_EXP:(i + 1) * CHUNK_T * N_EXP]), r_t=pin(sc.r_t[tl])))
+        if layout in ("chain", "ticks"):
+            cls = SF.HostChainChunk if layout == "chain" else SF.HostTickChainChunk
+            price = sc.price[sl] if layout == "chain" else SF.HostTickChainChunk.encode(sc.price[sl])
+            host.append(cls(ts=pin(sc.ts[tl]), price=pin(price), S_t=pin(sc.S_t[tl]),
+                            T_te=pin(sc.T_te[i * CHUNK_T * N_EXP:(i + 1) * CHUNK_T * N_EXP]), r_t=pin(sc.r_t[tl])))
         else:
             cols = {name: pin(getattr(chain, name)[sl]) for name in SF.QUOTE_F64 + ("is_call",)}
             host.append(SF.HostQuoteChunk(ts=pin(chain.ts[tl]), **cols))
     chunks = [host[i % ring] for i in range(n_chunks)]
     nb_chunk = CHUNK_T // 60
     stream = SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=nb_chunk + 1,
-                                  K_ek=sc.K_ek if sc is not None else None, is_call_ek=sc.is_call if sc is not None else None)
+                                  K_ek=sc.K_ek if sc is not None else None, is_call_ek=sc.is_call if sc is not None else None,
+                                  price_ticks=layout == "ticks")
     nb_total = n_chunks * (nb_chunk + 1)
     out = [torch.empty(nb_total * cspec.n_series, dtype=torch.float64).pin_memory() for _ in range(4)]
     out_ts = torch.empty(nb_total, dtype=torch.int64).pin_memory()
@@ -609,7 +646,7 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
     counts = [nb_chunk] * n_chunks                 # 1-s stamps starting on a minute: the host knows its bucket layout
     for _ in range(min(2, args.warmup)):
         stream.run(chunks[: min(8, n_chunks)], out, out_ts, out_cnt, bucket_counts=counts)
-    steps = max(1, min(args.steps, 3)) if layout == "chain" else 1      # the per-quote layout is the secondary figure
+    steps = max(1, min(args.steps, 3)) if layout != "quotes" else 1      # the per-quote layout is the secondary figure
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -625,7 +662,7 @@ def _bench_e2e(args, torch, SF, tapes, dev, chain, n_t, world, barrier, max_over
             "ms_per_step": ms, "wall_ms_per_step": wall * 1e3, "steps": steps, "quotes_per_step_per_gpu": nq, "buckets": rows,
             "layout": layout, "h2d_bytes_per_quote": round(stream.h2d_bytes / nq, 2),
             "api": "iv_interpolation_b200.surface.HostSurfaceStream.run (pinned host columns in, pinned host candles out)",
-            "host_tape": f"{ring} distinct pinned chunks of {CHUNK_T} stamps ({host[0].nbytes() >> 20} MiB each) re-sent cyclically, "
+            "host_tape": f"{ring} distinct pinned chunks of {CHUNK_T} stamps ({host[0].nbytes() >> 20} MiB each, {ring * host[0].nbytes() >> 20} MiB in all) re-sent cyclically, "
                          f"{n_chunks} chunks per step; per-quote IVs stay on the device (candles are the result)",
             "pcie_gbs": stream.h2d_bytes / (ms / 1e3) / 1e9}
 

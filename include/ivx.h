@@ -174,6 +174,13 @@ int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const
                              int32_t is_call_per_quote, const double* S_t, const double* K_ek,
                              const double* T_te, const double* r_t, double* sigma, int32_t* iters,
                              void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+/* The same with the price column as int32 ticks of 1e-4 — the precision the reference stores prices at (DECIMAL(15,4),
+ * src/database/schema.py:30-45) — INT32_MIN = no quote: 4 B per quote in instead of 8.  ticks / 1e4 is formed correctly
+ * rounded, so the result is bit-equal to ivx_bs_implied_vol_chain on prices rounded to four decimals. */
+int ivx_bs_implied_vol_chain_ticks(int64_t n_t, int64_t n_exp, int64_t n_strike, const int32_t* price_ticks,
+                                   const uint8_t* is_call, int32_t is_call_per_quote, const double* S_t, const double* K_ek,
+                                   const double* T_te, const double* r_t, double* sigma, int32_t* iters,
+                                   void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
 int ivx_bs_price(int64_t n, const double* S, const double* K, const double* T, const double* r,
                  const double* sigma, const uint8_t* is_call, double* price, ivx_stream_t stream);
 int ivx_bs_greeks(int64_t n, const double* S, const double* K, const double* T, const double* r,
@@ -230,8 +237,9 @@ int ivx_spline_fit_eval_ladder_verify(int64_t n_slices, const int64_t* knot_off,
  * two probe vectors — ladder_ok[l] = 0 (fewer than 48 or more than 2048 knots, not increasing, band misses 2e-12)
  * sends that ladder's slices to the exact solve.  ivx_spline_fit_eval_banded evaluates every slice as n_q (<= 512) dot
  * products out of shared memory; slices with a non-finite y, another knot count than their ladder, or (x_own != NULL) abscissae
- * that differ from the ladder's in any bit are appended to fb_list (int32[n_slices], count in *fb_count) and solved by
- * the exact scan kernel right behind, in the same stream, with the ladder tables lu_* of ivx_spline_ladder_factor.
+ * that differ from the ladder's in any bit are flagged in fb_list (int32[n_slices]: 1 = solved by the exact scan, 0 = by the
+ * band; their number in *fb_count) and solved by the exact scan kernel right behind, in the same stream and in slice order,
+ * with the ladder tables lu_* of ivx_spline_ladder_factor.  Slices that belong to no ladder group are not touched.
  * order / lad_slice_off: the slices grouped by ladder (CSR); max_slices_per_ladder sizes the grid. */
 int64_t ivx_spline_band_len(int64_t n_ladders, int64_t n_q);
 int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
@@ -242,8 +250,7 @@ int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_off, const 
                                const int64_t* ladder_off, int64_t max_knots, const double* x_ladder, const double* x_own /*or NULL*/,
                                const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
-                               const uint8_t* ladder_ok, const int16_t* band_perm, double* yq, int32_t* fb_list, uint32_t* fb_count,
-                               ivx_stream_t stream);
+                               const uint8_t* ladder_ok, const int16_t* band_perm, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream);
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);

@@ -57,7 +57,7 @@ class InterpolationBatch:
                 todo.append(i)
         outs: Dict[str, pd.DataFrame] = {}
         try:
-            results = self.interpolator.interpolate_batch([frames[symbols[i]] for i in todo]) if todo else []
+            results = self.interpolator.interpolate_batch([frames[symbols[i]] for i in todo], extra={"batch_id": self.batch_id}) if todo else []   # :105
             err = None
         except Exception as e:                                                        # :132-142
             results, err = [None] * len(todo), str(e)
@@ -74,7 +74,6 @@ class InterpolationBatch:
             elif res is None:                                                         # :99-102
                 statuses[i] = {"symbol": sym, "status": "skipped", "reason": "Interpolation failed or insufficient data"}
             else:
-                res["batch_id"] = self.batch_id                                       # :105
                 if self.sink is None or self.sink(sym, res):                          # :108
                     outs[sym] = res
                     statuses[i] = {"symbol": sym, "status": "success", "input_rows": len(frames[sym]),

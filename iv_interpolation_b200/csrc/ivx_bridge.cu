@@ -57,13 +57,17 @@ __device__ __forceinline__ double round_np(double x) {
   if (!(fabs(x) < BIG)) return x;
   const double p = x * s;
   double a = rint(p);
-  const double e = fma(x, s, -p), f = p - a;             // both exact
-  if (fabs(p) < 4503599627370496.0) {                    // below 2^52
-    const double g = 0.5 - fabs(f);
-    if ((f > 0.0 ? e : -e) > g) a += f > 0.0 ? 1.0 : -1.0;
-  } else if (fabs(e) == 0.5) {                           // p is an integer and the exact product sits half way to the next one: even wins
-    const double half = 0.5 * p;
-    if (half != rint(half)) a = p + (e + e);
+  const double f = p - a;                                // exact
+  // the residual can only matter within |e| <= ulp(p)/2 of the half-way point: a rare branch (the common path is rint alone)
+  if (0.5 - fabs(f) <= fabs(p) * 2.220446049250313e-16) {
+    const double e = fma(x, s, -p);                      // exact
+    if (fabs(p) < 4503599627370496.0) {                  // below 2^52
+      const double g = 0.5 - fabs(f);
+      if ((f > 0.0 ? e : -e) > g) a += f > 0.0 ? 1.0 : -1.0;
+    } else if (fabs(e) == 0.5) {                         // p is an integer and the exact product sits half way to the next one: even wins
+      const double half = 0.5 * p;
+      if (half != rint(half)) a = p + (e + e);
+    }
   }
   const double q0 = a * rc;
   const double r = fma(-s, q0, a);

@@ -552,7 +552,10 @@ __global__ void __launch_bounds__(256) k_chain_terms(int64_t n_t, int64_t n_exp,
 }
 
 // one quote of the chain layout: loads + solve; (j, t) = contract and stamp
-template <bool DEFER>
+// TICKS: the price column holds int32 ticks of 1e-4 (the reference's DECIMAL(15,4) price precision: 4 B per quote over PCIe
+// instead of 8), INT32_MIN = no quote.  ticks / 1e4 is formed correctly rounded (reciprocal + exact residual, as in the
+// bridge's rounding), i.e. it is bit-equal to the double a host gets from round(price, 4).
+template <bool DEFER, bool TICKS>
 __device__ __forceinline__ bool chain_quote(int32_t j, int64_t t, int32_t n_exp, int32_t n_strike, int64_t n_t, const double* __restrict__ price,
                                             const uint8_t* __restrict__ is_call, int32_t call_per_quote, const double* __restrict__ S_t,
                                             const double* __restrict__ K_ek, const double* __restrict__ T_te, const double* __restrict__ terms,
@@ -566,7 +569,14 @@ __device__ __forceinline__ bool chain_quote(int32_t j, int64_t t, int32_t n_exp,
     const int32_t e = j / n_strike;
     const int64_t te = t * n_exp + e;
     const int64_t n_te = n_t * (int64_t)n_exp;
-    p = ld_stream(price + i); call = (call_per_quote ? is_call[i] : __ldg(is_call + j)) != 0;
+    if (TICKS) {
+      const int32_t tk = __ldcs(reinterpret_cast<const int32_t*>(price) + i);
+      const double a = (double)tk, q0 = a * 1e-4;
+      p = tk == INT32_MIN ? qnan() : fma(fma(-1e4, q0, a), 1e-4, q0);
+    } else {
+      p = ld_stream(price + i);
+    }
+    call = (call_per_quote ? is_call[i] : __ldg(is_call + j)) != 0;
     s_ = __ldg(S_t + t); k_ = __ldg(K_ek + j); t_ = __ldg(T_te + te);
     const double lnS = __ldg(terms + t), lnK = __ldg(terms + n_t + j);
     const double rt = __ldg(terms + n_t + n_ek + te);
@@ -586,7 +596,7 @@ __device__ __forceinline__ bool chain_quote(int32_t j, int64_t t, int32_t n_exp,
 }
 
 // grid: x over the n_exp*n_strike contracts of one stamp, y over stamps
-template <bool DEFER>
+template <bool DEFER, bool TICKS>
 __global__ void __launch_bounds__(256, 5) k_bs_implied_vol_chain(int64_t t0, int32_t n_exp, int32_t n_strike, int64_t n_t,
                                                               const double* __restrict__ price, const uint8_t* __restrict__ is_call,
                                                               int32_t call_per_quote, const double* __restrict__ S_t, const double* __restrict__ K_ek,
@@ -594,10 +604,11 @@ __global__ void __launch_bounds__(256, 5) k_bs_implied_vol_chain(int64_t t0, int
                                                               double* __restrict__ sigma, int32_t* __restrict__ iters,
                                                               uint32_t* __restrict__ list, uint32_t* __restrict__ counter) {
   const int32_t j = blockIdx.x * 256 + threadIdx.x;               // contract (e, k)
-  const bool deferred = chain_quote<DEFER>(j, t0 + blockIdx.y, n_exp, n_strike, n_t, price, is_call, call_per_quote, S_t, K_ek, T_te, terms, sigma, iters);
+  const bool deferred = chain_quote<DEFER, TICKS>(j, t0 + blockIdx.y, n_exp, n_strike, n_t, price, is_call, call_per_quote, S_t, K_ek, T_te, terms, sigma, iters);
   if (DEFER) record_deferred(deferred, (blockIdx.y * gridDim.x + blockIdx.x) * 8u + (threadIdx.x >> 5), list, counter);
 }
 
+template <bool TICKS>
 __global__ void __launch_bounds__(256) k_bs_implied_vol_chain_retry(int64_t t0, uint32_t gx, int32_t n_exp, int32_t n_strike, int64_t n_t,
                                                                     const double* __restrict__ price, const uint8_t* __restrict__ is_call,
                                                                     int32_t call_per_quote, const double* __restrict__ S_t, const double* __restrict__ K_ek,
@@ -609,7 +620,7 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol_chain_retry(int64_t t0, 
     const uint32_t w = list[e];
     const uint32_t blk = w >> 3;                                   // (y * gx + x)
     const int32_t j = (int32_t)((blk % gx) * 256u + (w & 7u) * 32u + (threadIdx.x & 31u));
-    chain_quote<false>(j, t0 + blk / gx, n_exp, n_strike, n_t, price, is_call, call_per_quote, S_t, K_ek, T_te, terms, sigma, iters);
+    chain_quote<false, TICKS>(j, t0 + blk / gx, n_exp, n_strike, n_t, price, is_call, call_per_quote, S_t, K_ek, T_te, terms, sigma, iters);
   }
 }
 
@@ -740,11 +751,11 @@ extern "C" int64_t ivx_bs_chain_workspace_bytes(int64_t n_t, int64_t n_exp, int6
   return 8 * (n_t + n_exp * n_strike + 2 * n_t * n_exp) + 256 + 256 + 4 * (gx * gy * 8 + 8);
 }
 
-extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
-                                        const uint8_t* is_call, int32_t is_call_per_quote, const double* S_t,
-                                        const double* K_ek, const double* T_te,
-                                        const double* r_t, double* sigma, int32_t* iters, void* workspace,
-                                        int64_t workspace_bytes, ivx_stream_t stream_) {
+static int bs_chain_launch(bool ticks, int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
+                           const uint8_t* is_call, int32_t is_call_per_quote, const double* S_t,
+                           const double* K_ek, const double* T_te,
+                           const double* r_t, double* sigma, int32_t* iters, void* workspace,
+                           int64_t workspace_bytes, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_t >= 0 && n_exp >= 0 && n_strike >= 0, IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_chain: negative size");
   if (n_t == 0 || n_exp == 0 || n_strike == 0) return IVX_OK;
@@ -762,14 +773,33 @@ extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_st
   for (int64_t t0 = 0; t0 < n_t; t0 += 65535) {
     const unsigned gy = (unsigned)(n_t - t0 < 65535 ? n_t - t0 : 65535);
     IVX_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
-    k_bs_implied_vol_chain<true><<<dim3(gx, gy), 256, 0, stream>>>(t0, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, is_call_per_quote, S_t, K_ek,
-                                                                   T_te, terms, sigma, iters, list, counter);
+#define IVX_CH_ARGS (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, is_call_per_quote, S_t, K_ek, T_te, terms, sigma, iters, list, counter
+    if (ticks) k_bs_implied_vol_chain<true, true><<<dim3(gx, gy), 256, 0, stream>>>(t0, IVX_CH_ARGS);
+    else k_bs_implied_vol_chain<true, false><<<dim3(gx, gy), 256, 0, stream>>>(t0, IVX_CH_ARGS);
     IVX_LAUNCH_CHECK("k_bs_implied_vol_chain");
-    k_bs_implied_vol_chain_retry<<<(unsigned)(sm_count() * 2), 256, 0, stream>>>(t0, gx, (int32_t)n_exp, (int32_t)n_strike, n_t, price, is_call, is_call_per_quote,
-                                                                                 S_t, K_ek, T_te, terms, sigma, iters, list, counter);
+    if (ticks) k_bs_implied_vol_chain_retry<true><<<(unsigned)(sm_count() * 2), 256, 0, stream>>>(t0, gx, IVX_CH_ARGS);
+    else k_bs_implied_vol_chain_retry<false><<<(unsigned)(sm_count() * 2), 256, 0, stream>>>(t0, gx, IVX_CH_ARGS);
     IVX_LAUNCH_CHECK("k_bs_implied_vol_chain_retry");
+#undef IVX_CH_ARGS
   }
   return IVX_OK;
+}
+
+extern "C" int ivx_bs_implied_vol_chain(int64_t n_t, int64_t n_exp, int64_t n_strike, const double* price,
+                                        const uint8_t* is_call, int32_t is_call_per_quote, const double* S_t,
+                                        const double* K_ek, const double* T_te,
+                                        const double* r_t, double* sigma, int32_t* iters, void* workspace,
+                                        int64_t workspace_bytes, ivx_stream_t stream) {
+  return bs_chain_launch(false, n_t, n_exp, n_strike, price, is_call, is_call_per_quote, S_t, K_ek, T_te, r_t, sigma, iters, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ivx_bs_implied_vol_chain_ticks(int64_t n_t, int64_t n_exp, int64_t n_strike, const int32_t* price_ticks,
+                                              const uint8_t* is_call, int32_t is_call_per_quote, const double* S_t,
+                                              const double* K_ek, const double* T_te,
+                                              const double* r_t, double* sigma, int32_t* iters, void* workspace,
+                                              int64_t workspace_bytes, ivx_stream_t stream) {
+  return bs_chain_launch(true, n_t, n_exp, n_strike, reinterpret_cast<const double*>(price_ticks), is_call, is_call_per_quote, S_t, K_ek, T_te, r_t, sigma, iters,
+                         workspace, workspace_bytes, stream);
 }
 
 extern "C" int ivx_bs_price(int64_t n, const double* S, const double* K, const double* T, const double* r,

@@ -16,8 +16,8 @@
 //                    3-deep cp.async pipeline, ONE block barrier per slice (it also votes "every knot finite and on the
 //                    ladder"); grid points are dealt to lanes 32 apart so that the 16 lanes of a half-warp read 16
 //                    different banks; results leave through a shared-memory transpose, coalesced.
-//                    Slices that cannot be taken (a missing knot, off the ladder, odd length) are appended to a list.
-//   * the list is then solved by the exact kernel (ivx_spline.cu, k_spline_fit_eval_list) in the same stream.
+//                    Slices that cannot be taken (a missing knot, off the ladder, odd length) are FLAGGED (one int32 per slice).
+//   * the flagged slices are then solved by the exact kernel (ivx_spline.cu, k_spline_fit_eval_list), in slice order, same stream.
 #include "ivx_common.cuh"
 
 namespace ivx {
@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
   const int32_t* __restrict__ ord = P.order + s_begin;
   const int t = threadIdx.x;
   if (!P.ladder_ok[l]) {                                     // no usable band for this ladder: everything to the exact solve
-    for (int i = t; i < ns; i += BAND_THREADS) P.fb_list[atomicAdd(P.fb_count, 1u)] = ord[i];
+    for (int i = t; i < ns; i += BAND_THREADS) P.fb_list[ord[i]] = 1;
+    if (t == 0) atomicAdd(P.fb_count, (uint32_t)ns);
     return;
   }
   const int n = (int)(P.ladder_off[l + 1] - P.ladder_off[l]);      // BAND_W <= n <= BAND_MAXK (k_band_build)
@@ -346,8 +347,10 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
         a3 = fma(w[j + 3], yw[j + 3], a3);
       }
       if (has_q) obuf[(i & 1) * (BAND_MAXQ + 16) + oq] = nan_q ? qnan() : (a0 + a1) + (a2 + a3);
-    } else if (t == 0) {
-      P.fb_list[atomicAdd(P.fb_count, 1u)] = sid[i];         // a missing knot, off the ladder, another length: the exact solve
+    }
+    if (t == 0) {                                            // a missing knot, off the ladder, another length: flagged for the exact solve
+      P.fb_list[sid[i]] = all_ok ? 0 : 1;
+      if (!all_ok) atomicAdd(P.fb_count, 1u);
     }
     prev_ok = all_ok;
     buf_next2 = buf;                                         // slice i+3 reuses slice i's buffer
@@ -426,6 +429,6 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
     IVX_LAUNCH_CHECK("k_band_apply");
   }
   // whatever the banded kernel listed: the exact solve (ladder tables where a slice may use them), same stream
-  return spline_fit_eval_list(fb_list, fb_count, max_knots, knot_off, x_off, x_ladder, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y,
+  return spline_fit_eval_list(n_slices, fb_list, max_knots, knot_off, x_off, x_ladder, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y,
                               (int)n_q, xq, extrap, yq, stream);
 }

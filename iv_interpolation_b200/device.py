@@ -339,7 +339,10 @@ def bs_implied_vol_chain(price, is_call, S_t, K_ek, T_te, r_t, *, n_t: int, n_ex
     """Chain layout: ``price`` per quote [t][e][k]; ``S_t``, ``r_t`` per stamp, ``K_ek`` per contract, ``T_te`` per
     (stamp, expiry); ``is_call`` per contract [e][k] (8 B/quote read) or per quote (9 B/quote) instead of 41."""
     n = n_t * n_exp * n_strike
-    _req(price, torch.float64, "price"); _req(is_call, torch.uint8, "is_call")
+    ticks = price.dtype == torch.int32             # int32 ticks of 1e-4 (DECIMAL(15,4)), INT32_MIN = no quote
+    if not ticks:
+        _req(price, torch.float64, "price")
+    _req(is_call, torch.uint8, "is_call")
     per_quote = is_call.numel() == n and n != n_exp * n_strike
     if not per_quote and is_call.numel() != n_exp * n_strike:
         raise _lib.IvxError(f"is_call: expected {n_exp * n_strike} (per contract) or {n} (per quote) elements")
@@ -354,7 +357,8 @@ def bs_implied_vol_chain(price, is_call, S_t, K_ek, T_te, r_t, *, n_t: int, n_ex
     ws = workspace if workspace is not None and workspace.numel() >= wsb else _empty(wsb, torch.uint8, price)
     sigma = out if out is not None else _empty(n, torch.float64, price)
     iters = _empty(n, torch.int32, price) if want_iters else None
-    check(L.ivx_bs_implied_vol_chain(n_t, n_exp, n_strike, _ptr(price), _ptr(is_call), int(per_quote), _ptr(S_t), _ptr(K_ek), _ptr(T_te),
+    fn = L.ivx_bs_implied_vol_chain_ticks if ticks else L.ivx_bs_implied_vol_chain
+    check(fn(n_t, n_exp, n_strike, _ptr(price), _ptr(is_call), int(per_quote), _ptr(S_t), _ptr(K_ek), _ptr(T_te),
                                      _ptr(r_t), _ptr(sigma), _ptr(iters), _ptr(ws), ws.numel(), _stream()),
           "ivx_bs_implied_vol_chain")
     _count("bs_implied_vol_chain")

@@ -107,7 +107,7 @@ def _tick(timing: Optional[dict], key: str, t0: float) -> float:
 
 
 def interpolate_uniform(frames: Sequence[pd.DataFrame], min_points: int, launch: Optional[Callable] = None,
-                        device=None, timing: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
+                        device=None, timing: Optional[dict] = None, extra: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
     """``[IVInterpolator.interpolate_symbol(f) for f in frames]`` for frames that satisfy ``task1_uniform`` and hold at
     least ``min_points`` rows each (reference core.py:26-28 is the caller's business)."""
     import torch
@@ -175,6 +175,8 @@ def interpolate_uniform(frames: Sequence[pd.DataFrame], min_points: int, launch:
     m = len(data["date"])
     out = pd.DataFrame(data, index=pd.Index(cut(o_pos).astype(np.int64), copy=False), copy=False)
     out["is_interpolated"] = np.zeros(m, dtype=bool)                    # core.py:71 — always False after the forward fill
+    for name, value in (extra or {}).items():                           # e.g. batch_id (batch_processor.py:105): once, not per symbol
+        out[name] = value
     results: List[Optional[pd.DataFrame]] = [None] * nf
     for g in range(nf):
         if status[g] != SYM_OK:

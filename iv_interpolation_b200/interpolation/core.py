@@ -42,7 +42,8 @@ class IVInterpolator:
             return None
 
     # -- many contracts in one launch --------------------------------------------------------------
-    def interpolate_batch(self, frames: Sequence[pd.DataFrame], timing: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
+    def interpolate_batch(self, frames: Sequence[pd.DataFrame], timing: Optional[dict] = None,
+                          extra: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
         """``[interpolate_symbol(f) for f in frames]`` with one plan + one exec launch for all."""
         import torch
         from .. import device as D
@@ -60,7 +61,7 @@ class IVInterpolator:
         from .. import hostpath as H
         big_enough = [i for i, df in enumerate(frames) if len(df) >= self.min_points]
         if len(big_enough) > 1 and H.task1_uniform([frames[i] for i in big_enough]):
-            outs = H.interpolate_uniform([frames[i] for i in big_enough], self.min_points, timing=timing)
+            outs = H.interpolate_uniform([frames[i] for i in big_enough], self.min_points, timing=timing, extra=extra)
             for i, out in zip(big_enough, outs):
                 if out is None:
                     logger.debug("No valid data after interpolation or guard failed")
@@ -163,4 +164,9 @@ class IVInterpolator:
                     srcs[j], inp, sl(o_ts), [sl(c) for c in o_interp], [sl(c) for c in o_fill],
                     [idx_by_name[c] for c in inp.fill_idx_names], to_orig(sl(o_src)), sl(o_pos).astype(np.int64))
                 logger.debug(f"Interpolated {inp.n} → {int(keep.sum())} rows")
+        if extra:                                      # the general path: per frame
+            for r in results:
+                if r is not None:
+                    for name, value in extra.items():
+                        r[name] = value
         return results

@@ -140,6 +140,12 @@ class SurfacePipeline:
         self.banded = banded and spec.n_grid_k <= 512 and 48 <= spec.n_strike <= 2048
         self._band = self._q_band = None
         self._order = None
+        # the band serves clean slices on their ladders; everything else is solved exactly right behind it, but a tape where MOST
+        # slices hold a missing quote (or sit off their ladders) pays for both passes: the share of such slices is read back
+        # after every run (4 bytes, asynchronously) and above 25 % the pipeline goes back to the scan kernel alone
+        self._fb_host = torch.zeros(1, dtype=torch.int32).pin_memory() if self.banded else None
+        self._fb_event = None
+        self.banded_switched_off = False
         self._chain_ws = None
         self._iv_ws = None
         self._lu_key = None
@@ -177,6 +183,10 @@ class SurfacePipeline:
                 events[stage][k].record()
 
         structured = isinstance(q, StructuredChain)
+        if self.banded and self._fb_event is not None and self._fb_event.query():
+            self._fb_event = None
+            if int(self._fb_host.item()) > 0.25 * sp.n_t * sp.n_exp:
+                self.banded, self.banded_switched_off = False, True
         mark("implied_vol", 0)
         if structured:
             if self._chain_ws is None:
@@ -243,6 +253,10 @@ class SurfacePipeline:
                 D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile,
                                   x_off=self._q_x_off, lu=self._q_lu, slice_ladder=self._q_slice_ladder, x_own=q.K,
                                   ladder_off=self._q_ladder_off)
+        if self.banded:
+            self._fb_host.copy_(self._fb[1], non_blocking=True)
+            self._fb_event = torch.cuda.Event()
+            self._fb_event.record()
         mark("spline_strike", 1)
         mark("spline_maturity", 0)
         # plane t: n_grid_k systems with n_exp knots at x = T[t][e], read in place
@@ -305,6 +319,21 @@ class HostChainChunk:
         return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
 
 
+@dataclass
+class HostTickChainChunk(HostChainChunk):
+    """The chain layout with ``price`` as int32 ticks of 1e-4 — the precision the reference stores prices at (DECIMAL(15,4),
+    reference src/database/schema.py:30-45) — ``INT32_MIN`` = no quote: 4 B per quote cross PCIe.  An explicit, separately named
+    wire format: the IVs are those of the prices ROUNDED to four decimals (bit-equal to solving ``round(price, 4)``)."""
+
+    @staticmethod
+    def encode(price: torch.Tensor) -> torch.Tensor:
+        """float64 prices -> int32 ticks (round half to even at 1e-4; NaN -> INT32_MIN; prices must stay below 214 748.3647)."""
+        t = torch.round(price * 1e4)
+        if bool((t.abs() >= 2 ** 31).any()):
+            raise IvxError("HostTickChainChunk.encode: a price does not fit int32 ticks of 1e-4")
+        return torch.where(torch.isnan(price), torch.full_like(t, -2.0 ** 31), t).to(torch.int32)
+
+
 class HostSurfaceStream:
     """Streams a day of quotes from host memory through the pipeline, chunk by chunk, double-buffered:
     while chunk i is being solved on the compute stream, chunk i+1 is on its way over PCIe on the copy
@@ -314,7 +343,8 @@ class HostSurfaceStream:
     """
 
     def __init__(self, chunk_spec: ChainSpec, device: torch.device, grid_k: torch.Tensor, grid_m: torch.Tensor,
-                 max_buckets_per_chunk: int, K_ek: Optional[torch.Tensor] = None, is_call_ek: Optional[torch.Tensor] = None):
+                 max_buckets_per_chunk: int, K_ek: Optional[torch.Tensor] = None, is_call_ek: Optional[torch.Tensor] = None,
+                 price_ticks: bool = False):
         self.spec = chunk_spec
         self.device = device
         self.grid_k = grid_k.to(device)
@@ -323,12 +353,14 @@ class HostSurfaceStream:
         if (K_ek is None) != (is_call_ek is None):
             raise IvxError("the chain layout needs both K_ek and is_call_ek")
         self.is_call_ek = None if is_call_ek is None else is_call_ek.to(device)
-        self.chunk_type = HostQuoteChunk if K_ek is None else HostChainChunk
+        if price_ticks and K_ek is None:
+            raise IvxError("the int32 tick price format belongs to the chain layout (pass K_ek and is_call_ek)")
+        self.chunk_type = HostQuoteChunk if K_ek is None else (HostTickChainChunk if price_ticks else HostChainChunk)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.out_stream = torch.cuda.Stream(device=device)
         self.max_buckets = max_buckets_per_chunk
         sp = chunk_spec
-        sizes = {"ts": (sp.n_t, torch.int64), "price": (sp.n_quotes, torch.float64), "is_call": (sp.n_quotes, torch.uint8),
+        sizes = {"ts": (sp.n_t, torch.int64), "price": (sp.n_quotes, torch.int32 if price_ticks else torch.float64), "is_call": (sp.n_quotes, torch.uint8),
                  "S": (sp.n_quotes, torch.float64), "K": (sp.n_quotes, torch.float64), "T": (sp.n_quotes, torch.float64),
                  "r": (sp.n_quotes, torch.float64), "S_t": (sp.n_t, torch.float64), "r_t": (sp.n_t, torch.float64),
                  "T_te": (sp.n_t * sp.n_exp, torch.float64)}
@@ -354,7 +386,7 @@ class HostSurfaceStream:
         for slot in self.slots:
             slot["drained"].record(compute)
         for i, ch in enumerate(chunks):
-            if not isinstance(ch, self.chunk_type):
+            if type(ch) is not self.chunk_type:
                 raise IvxError(f"chunk {i} is a {type(ch).__name__}, this stream takes {self.chunk_type.__name__}")
             if ch.n_t != sp.n_t:
                 raise IvxError(f"chunk {i} has {ch.n_t} stamps, the stream was planned for {sp.n_t} "

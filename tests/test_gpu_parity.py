@@ -755,8 +755,9 @@ def _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify):
     yq = D.spline_fit_eval_banded(_t(off, dev), _t(ladder_off[:-1][lad_of], dev), _t(lad_of, dev), _t(order, dev), _t(lad_slice_off, dev),
                                   int(counts.max()), _t(ladder_off, dev), _t(lx, dev), lu, _t(np.concatenate(ys), dev), _t(xq, dev), band,
                                   max_knots=max_knots, x_own=_t(np.concatenate(xs), dev) if verify else None, fb=fb)
-    n_fb = int(fb[1].item())
-    return yq.cpu().numpy().reshape(len(ys), -1), sorted(fb[0].cpu().numpy()[:n_fb].tolist()), band.ok.cpu().numpy()
+    flags = fb[0].cpu().numpy()
+    assert set(flags.tolist()) <= {0, 1} and int(fb[1].item()) == int(flags.sum())      # every slice decided, the count agrees
+    return yq.cpu().numpy().reshape(len(ys), -1), np.flatnonzero(flags == 1).tolist(), band.ok.cpu().numpy()
 
 
 @pytest.mark.parametrize("n_knots,n_q,extrap", [(2000, 512, 1), (2048, 512, 0), (333, 257, 2), (48, 100, 1), (1001, 512, 1)])

@@ -173,3 +173,47 @@ def test_host_stream_equals_resident_pipeline(dev):
         assert _eq(np.isnan(g), np.isnan(w)) and np.nanmax(np.abs(g - w)) <= 1e-8
     with pytest.raises(Exception):
         cstream.run(chunks[:1], out2, out_ts, out_cnt)        # wrong chunk layout for this stream
+
+
+def test_tick_price_layout_equals_prices_rounded_to_four_decimals(dev):
+    """The 4-byte wire format (int32 ticks of 1e-4, the reference's DECIMAL(15,4); INT32_MIN = no quote): the chain solver on
+    ticks is bit-equal to the chain solver on round(price, 4), a missing quote stays missing, and the host stream in the tick
+    layout returns the candles of the chain layout fed with the rounded prices."""
+    import torch
+    from iv_interpolation_b200 import device as D, surface as SF
+    spec = SF.ChainSpec(120, 4, 96, 32, 8, bucket_ticks=60 * tapes.US, min_count=10)
+    chain = tapes.make_quote_chain(17, spec, dev, drop_frac=0.01)
+    sc = SF.StructuredChain.from_quotes(chain)
+    ticks = SF.HostTickChainChunk.encode(sc.price)
+    # round(price, 4) on the host (IEEE division; torch's CUDA division by a scalar multiplies by the reciprocal)
+    p_host = sc.price.cpu().numpy()
+    rounded = torch.from_numpy(np.where(np.isnan(p_host), p_host, np.rint(p_host * 1e4) / 1e4)).to(dev)
+    assert bool((ticks[torch.isnan(sc.price)] == -2 ** 31).all()) and int(torch.isnan(sc.price).sum()) > 10
+    kw = dict(n_t=spec.n_t, n_exp=spec.n_exp, n_strike=spec.n_strike)
+    a = D.bs_implied_vol_chain(rounded, sc.is_call, sc.S_t, sc.K_ek, sc.T_te, sc.r_t, **kw)
+    b = D.bs_implied_vol_chain(ticks, sc.is_call, sc.S_t, sc.K_ek, sc.T_te, sc.r_t, **kw)
+    assert bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+    assert bool(torch.isnan(b[torch.isnan(sc.price)]).all()) and float(torch.isnan(b).double().mean()) < 0.1
+    # host stream, two chunks of 60 stamps
+    cspec = SF.ChainSpec(60, 4, 96, 32, 8, bucket_ticks=60 * tapes.US, min_count=10)
+    pin = lambda t: t.cpu().pin_memory()
+    def chunks(price, cls):
+        out = []
+        for i in range(2):
+            tl, sl = slice(i * 60, (i + 1) * 60), slice(i * cspec.n_quotes, (i + 1) * cspec.n_quotes)
+            out.append(cls(ts=pin(sc.ts[tl]), price=pin(price[sl]), S_t=pin(sc.S_t[tl]), T_te=pin(sc.T_te[i * 60 * 4:(i + 1) * 60 * 4]), r_t=pin(sc.r_t[tl])))
+        return out
+    def run(price, cls, ticks_):
+        st = SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=2, K_ek=sc.K_ek, is_call_ek=sc.is_call, price_ticks=ticks_)
+        out = [torch.empty(4 * cspec.n_series, dtype=torch.float64).pin_memory() for _ in range(4)]
+        ts, cnt = torch.empty(4, dtype=torch.int64).pin_memory(), torch.empty(4, dtype=torch.int32).pin_memory()
+        nb = st.run(chunks(price, cls), out, ts, cnt)
+        return nb, [o[: nb * cspec.n_series].clone() for o in out], st.h2d_bytes
+    nb1, c1, bytes1 = run(rounded, SF.HostChainChunk, False)
+    nb2, c2, bytes2 = run(ticks, SF.HostTickChainChunk, True)
+    assert nb1 == nb2 == 2 and bytes2 < 0.55 * bytes1
+    for x, y in zip(c1, c2):
+        assert bool(((x == y) | (torch.isnan(x) & torch.isnan(y))).all())
+    with pytest.raises(Exception):
+        SF.HostSurfaceStream(cspec, dev, chain.grid_k, chain.grid_m, max_buckets_per_chunk=2, K_ek=sc.K_ek, is_call_ek=sc.is_call).run(
+            chunks(ticks, SF.HostTickChainChunk), c1, torch.empty(4, dtype=torch.int64), torch.empty(4, dtype=torch.int32))
