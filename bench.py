@@ -523,7 +523,7 @@ def bench_stress(args, torch, D, SF, tapes, dev, peak):
     out = {"stamps": n_t, "note": f"{n_t} stamps per tape, times scaled x{scale:.1f} to the {N_T_DAY}-stamp day"}
 
     def run(chain, label):
-        pipe = SF.SurfacePipeline(spec, dev, max_buckets=n_t // 60 + 2)
+        pipe = SF.SurfacePipeline(spec, dev, max_buckets=n_t // 60 + 2, banded="auto")
         pipe.plan_buckets(chain.ts)
         for _ in range(2):
             pipe.run(chain)

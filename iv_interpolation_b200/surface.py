@@ -119,7 +119,11 @@ class SurfacePipeline:
 
     STAGES = ("implied_vol", "spline_strike", "spline_maturity", "candles")
 
-    def __init__(self, spec: ChainSpec, device: torch.device, max_buckets: Optional[int] = None, banded: bool = True):
+    def __init__(self, spec: ChainSpec, device: torch.device, max_buckets: Optional[int] = None, banded=True):
+        """``banded``: True = strike spline through the banded operators (+ exact solve of the slices they cannot take); False =
+        scan kernel; "auto" = banded for the first run, then the share of slices that needed the exact solve is read back ONCE
+        and above 25 % (a tape with missing quotes nearly everywhere) the pipeline stays on the scan kernel — the two paths
+        differ in the last bits, which is why this is opt-in."""
         if device.type != "cuda":
             raise IvxError("SurfacePipeline needs a CUDA device (no CPU path exists)")
         self.spec = spec
@@ -137,13 +141,11 @@ class SurfacePipeline:
         # chain layout: every slice (t, e) reads its abscissae from the shared ladder of expiry e
         self._x_off = None
         # strike spline on shared ladders: banded operators (ivx_spline_band.cu) when the shapes allow, else the scan kernel
-        self.banded = banded and spec.n_grid_k <= 512 and 48 <= spec.n_strike <= 2048
+        self.banded_auto = banded == "auto"
+        self.banded = bool(banded) and spec.n_grid_k <= 512 and 48 <= spec.n_strike <= 2048
         self._band = self._q_band = None
         self._order = None
-        # the band serves clean slices on their ladders; everything else is solved exactly right behind it, but a tape where MOST
-        # slices hold a missing quote (or sit off their ladders) pays for both passes: the share of such slices is read back
-        # after every run (4 bytes, asynchronously) and above 25 % the pipeline goes back to the scan kernel alone
-        self._fb_host = torch.zeros(1, dtype=torch.int32).pin_memory() if self.banded else None
+        self._fb_host = torch.zeros(1, dtype=torch.int32).pin_memory() if self.banded and self.banded_auto else None
         self._fb_event = None
         self.banded_switched_off = False
         self._chain_ws = None
@@ -183,8 +185,9 @@ class SurfacePipeline:
                 events[stage][k].record()
 
         structured = isinstance(q, StructuredChain)
-        if self.banded and self._fb_event is not None and self._fb_event.query():
-            self._fb_event = None
+        if self._fb_event is not None:                   # "auto": decided once, after the first run
+            self._fb_event.synchronize()
+            self._fb_event, self.banded_auto = None, False
             if int(self._fb_host.item()) > 0.25 * sp.n_t * sp.n_exp:
                 self.banded, self.banded_switched_off = False, True
         mark("implied_vol", 0)
@@ -253,7 +256,7 @@ class SurfacePipeline:
                 D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile,
                                   x_off=self._q_x_off, lu=self._q_lu, slice_ladder=self._q_slice_ladder, x_own=q.K,
                                   ladder_off=self._q_ladder_off)
-        if self.banded:
+        if self.banded and self.banded_auto:
             self._fb_host.copy_(self._fb[1], non_blocking=True)
             self._fb_event = torch.cuda.Event()
             self._fb_event.record()
