@@ -235,8 +235,11 @@ class _Ctx:
         if self.world > 1:
             # NCCL's INFO log (rank/communicator lines the driver counts) goes to stderr with everything else: stdout is
             # redirected in main(), the one JSON line is written through the saved descriptor
-            os.environ.setdefault("NCCL_DEBUG", os.environ.get("IVX_NCCL_DEBUG", "INFO"))
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            os.environ["NCCL_DEBUG"] = os.environ.get("IVX_NCCL_DEBUG", "INFO")          # whatever the image presets (WARN) is overridden
+            os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("IVX_NCCL_DEBUG_SUBSYS", "INIT")
+            # the final gather is point to point (rank r -> rank 0): give send/recv more than NCCL's default two channels per peer
+            os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+            os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
             dist.init_process_group("nccl", device_id=self.dev)
         if args.gpus != self.world:
             if self.rank == 0:

@@ -289,6 +289,8 @@ int ivx_spline_strided_batched(int64_t n_batches, int64_t n_systems, int32_t n_k
  * per-symbol kernel recomputes the batch in stream order).  With seg_out, seg_e or workspace NULL: one warp per
  * symbol.  Results are identical either way; trend_following always runs one warp per symbol.
  * ------------------------------------------------------------------------------------------- */
+/* or-ed into `strategy`: run the per-symbol kernel after the segment kernel whatever the segment check says (diagnostic; same results) */
+#define IVX_BRIDGE_RECOMPUTE 0x100
 int64_t ivx_bridge_n_segments(int64_t n_rows);
 int64_t ivx_bridge_workspace_bytes(int64_t n_rows);
 int ivx_bridge_plan(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
@@ -305,7 +307,6 @@ int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const
 /* the same quality bits for candles that already exist (ohlcv_converter.py:371-402 on a frame): *flags = OR over n rows */
 int ivx_bridge_quality(int64_t n, const double* open, const double* high, const double* low, const double* close,
                        const double* source_price, uint32_t* flags /*1*/, ivx_stream_t stream);
-void ivx_bridge_test_force_fallback(int32_t on);   /* test hook: the segment check reports a mismatch, the fallback runs */
 
 /* ---------------------------------------------------------------------------------------------
  * Utilities: exclusive scan of int64, stream-copy and fp64-FMA microbenchmarks that give the

@@ -21,6 +21,7 @@ FLAG_UNSORTED, FLAG_NONFINITE = 64, 128
 MAX_FILL_COLS, MAX_IDX_COLS = 8, 4
 BRIDGE_STRATEGY = {"spread_simulation": 0, "price_as_midpoint": 1, "trend_following": 2, "simple_spread": 3, "pipeline": 4}
 BRIDGE_U_PER_ROW = {0: 5, 1: 2, 2: 0, 3: 1, 4: 4}
+BRIDGE_RECOMPUTE = 0x100          # or-ed into the strategy code: per-symbol kernel after the segment kernel whatever the check says
 Q_HIGH_LT_LOW, Q_HIGH_LT_OC, Q_LOW_GT_OC, Q_SPREAD, Q_NONPOSITIVE = 1, 2, 4, 8, 16
 
 
@@ -70,7 +71,6 @@ SIGNATURES = {
     "ivx_spline_strided_batched": (C.c_int, [_i64, _i64, _i32, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p]),
     "ivx_bridge_n_segments": (_i64, [_i64]),
     "ivx_bridge_workspace_bytes": (_i64, [_i64]),
-    "ivx_bridge_test_force_fallback": (None, [_i32]),
     "ivx_bridge_quality": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "ivx_bridge_plan": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_bridge_ohlcv": (C.c_int, [_i64, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _p, _p, _p, _p, _p, _p, _p,

@@ -424,10 +424,6 @@ __global__ void __launch_bounds__(256) k_bridge_check(const SegArrays A, int32_t
 
 using namespace ivx;
 
-static int32_t g_force_fallback = 0;
-// test hook: make the segment check fail so that the stream-ordered per-symbol fallback runs (tests/test_gpu_bridge.py)
-extern "C" void ivx_bridge_test_force_fallback(int32_t on) { g_force_fallback = on; }
-
 extern "C" int64_t ivx_bridge_n_segments(int64_t n_rows) { return n_rows < 0 ? -1 : (n_rows + SEG - 1) / SEG; }
 
 extern "C" int64_t ivx_bridge_workspace_bytes(int64_t n_rows) {
@@ -470,6 +466,10 @@ extern "C" int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in
                                 int64_t workspace_bytes, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_sym >= 0 && n_rows >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: negative size");
+  // IVX_BRIDGE_RECOMPUTE (a flag or-ed into strategy): treat the segment check as failed, i.e. let the stream-ordered
+  // per-symbol kernel recompute the batch after the segment kernel — a diagnostic that exercises the fallback (no global state)
+  const int32_t force_fallback = (strategy & IVX_BRIDGE_RECOMPUTE) ? 1 : 0;
+  strategy &= ~IVX_BRIDGE_RECOMPUTE;
   IVX_REQUIRE(strategy >= ST_SPREAD && strategy <= ST_PIPELINE, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: unknown strategy %d", strategy);
   if (n_sym == 0 || n_rows == 0) return IVX_OK;
   IVX_REQUIRE(in_off && base && volume && out_off && e_off && o_row && o_open && o_high && o_low && o_close && o_volume && o_source,
@@ -513,7 +513,7 @@ extern "C" int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in
   if (strategy == ST_SPREAD) {
     // the carried closes the segments assumed are checked against the ones their predecessors produced; on a mismatch
     // (never seen; ~1e-9 per boundary by the contraction argument) the per-symbol kernel recomputes the batch, stream-ordered
-    k_bridge_check<<<(unsigned)((g + 255) / 256), 256, 0, stream>>>(A, g_force_fallback);
+    k_bridge_check<<<(unsigned)((g + 255) / 256), 256, 0, stream>>>(A, force_fallback);
     IVX_LAUNCH_CHECK("k_bridge_check");
     k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P, A.flag);
     IVX_LAUNCH_CHECK("k_bridge_ohlcv(fallback)");

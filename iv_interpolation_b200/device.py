@@ -593,7 +593,8 @@ def bridge_plan(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor) 
 
 def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor, plan: BridgePlan, strategy: str, *,
                  u: Optional[torch.Tensor] = None, e: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
-                 base_spread_percent: float = 0.002, volatility_factor: float = 1.5, segmented: bool = True) -> BridgeBatch:
+                 base_spread_percent: float = 0.002, volatility_factor: float = 1.5, segmented: bool = True,
+                 recompute: bool = False) -> BridgeBatch:
     """Synthetic 1-minute candles from interpolated rows, every candle bit-equal to the reference's given the same
     random tapes (see include/ivx.h).  ``strategy`` is one of _lib.BRIDGE_STRATEGY.  ``segmented=False`` runs one warp per
     symbol instead of one per 2048-row segment (same results)."""
@@ -618,7 +619,7 @@ def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor,
         wsb = lib().ivx_bridge_workspace_bytes(base.numel())
         ws = torch.empty(wsb, dtype=torch.uint8, device=base.device)
     check(lib().ivx_bridge_ohlcv(n_sym, base.numel(), _ptr(in_off), _ptr(_req(base, torch.float64, "base")), _ptr(_req(volume, torch.float64, "volume")),
-                                 code, float(base_spread_percent), float(volatility_factor),
+                                 code | (_lib.BRIDGE_RECOMPUTE if recompute else 0), float(base_spread_percent), float(volatility_factor),
                                  _ptr(_req(u, torch.float64, "u")) if u is not None else None, _ptr(_req(e, torch.float64, "e")),
                                  _ptr(_req(z, torch.float64, "z")) if z is not None else None,
                                  _ptr(plan.out_off), _ptr(plan.e_off), _ptr(plan.seg_out) if use_seg else None,

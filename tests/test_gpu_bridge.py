@@ -24,13 +24,13 @@ def _t(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-def _run(dev, strategy, off, base, volume, u, e, z, segmented=True):
+def _run(dev, strategy, off, base, volume, u, e, z, segmented=True, recompute=False):
     from iv_interpolation_b200 import device as D
     canon = B.canonical_strategy(strategy)
     d_off, d_base, d_vol = _t(off, dev), _t(base, dev), _t(volume, dev)
     plan = D.bridge_plan(d_off, d_base, d_vol)
     res = D.bridge_ohlcv(d_off, d_base, d_vol, plan, canon, u=_t(u, dev) if len(u) else None, e=_t(e, dev),
-                         z=_t(z, dev) if len(z) else None, segmented=segmented)
+                         z=_t(z, dev) if len(z) else None, segmented=segmented, recompute=recompute)
     h = lambda x: x.cpu().numpy()
     return dict(out_off=h(res.out_off), e_off=h(plan.e_off), row=h(res.row), open=h(res.open), high=h(res.high), low=h(res.low),
                 close=h(res.close), volume=h(res.volume), source_price=h(res.source_price), quality=h(res.sym_quality))
@@ -112,13 +112,9 @@ def test_bridge_kernel_vs_oracle_ragged(dev, strategy, mode):
         bases.append(b); vols.append(v); us.append(u); es.append(e); zs.append(z)
     off = np.zeros(len(lens) + 1, np.int64)
     np.cumsum(lens, out=off[1:])
-    from iv_interpolation_b200 import _lib
-    _lib.lib().ivx_bridge_test_force_fallback(1 if mode == "fallback" else 0)
-    try:
-        got = _run(dev, strategy, off, np.concatenate(bases), np.concatenate(vols), np.concatenate(us), np.concatenate(es), np.concatenate(zs),
-                   segmented=mode != "symbols")
-    finally:
-        _lib.lib().ivx_bridge_test_force_fallback(0)
+    # "fallback": the IVX_BRIDGE_RECOMPUTE flag — the per-symbol kernel recomputes the batch after the segment kernel
+    got = _run(dev, strategy, off, np.concatenate(bases), np.concatenate(vols), np.concatenate(us), np.concatenate(es), np.concatenate(zs),
+               segmented=mode != "symbols", recompute=mode == "fallback")
     for i, w in enumerate(want):
         a, b = int(got["out_off"][i]), int(got["out_off"][i + 1])
         assert b - a == len(w["row"]), (i, lens[i])
