@@ -61,7 +61,9 @@ struct TileSmem {
   int32_t head_base[33];
   int32_t kept_base[33];
   uint16_t bstart[TB_ROWS + 1];
-  int64_t symrow[TB_ROWS];   // per candle (at its first row): global row of the first non-null symbol
+  int32_t symrow[TB_ROWS];   // per candle (at its first row): row of the first non-null symbol RELATIVE to the tile's first row
+                             // (it may lie beyond the tile, in the last bucket's extension), INT32_MIN = none.  32 bits keep the
+                             // struct under 28 KB: eight CTAs per SM instead of seven
   int32_t last_count_ext;    // rows of the tile's last bucket that live beyond the tile
   int64_t tile_sym_end;      // end row of the symbol owning the tile's last row
   uint32_t excl_kept, excl_heads;
@@ -119,7 +121,7 @@ struct Candle {
   }
 };
 
-__global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P) {
+__global__ void __launch_bounds__(TB_THREADS, 8) k_ohlcv_reduce(const OhlcvParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
       uint32_t flags = cd.flags;
       if (kept) flags |= row_flags(cd.open, cd.high, cd.low, cd.close, cd.sum) << 3;  // IVX_FLAG_OUT_*
       S.col[0][b0] = cd.open; S.col[1][b0] = cd.high; S.col[2][b0] = cd.low; S.col[3][b0] = cd.close; S.col[4][b0] = cd.sum;
-      S.symrow[b0] = cd.sym_row;
+      S.symrow[b0] = cd.sym_row < 0 ? INT32_MIN : (int32_t)(cd.sym_row - r0);
       if (flags && P.sym_flags) atomicOr(P.sym_flags + symbol_of_row(P.in_off, P.n_sym, r0 + b0), flags);
       }
     }
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_ohlcv_reduce(const OhlcvParams P
       st_stream(P.o_col[3] + krank, S.col[3][b0]);
       st_stream(P.o_col[4] + krank, S.col[4][b0]);
       st_stream(P.o_count + krank, cnt);
-      if (P.o_sym_row) st_stream(P.o_sym_row + krank, S.symrow[b0]);
+      if (P.o_sym_row) st_stream(P.o_sym_row + krank, S.symrow[b0] == INT32_MIN ? (int64_t)-1 : r0 + S.symrow[b0]);
       if (P.o_group) st_stream(P.o_group + krank, base_heads + j);
     }
   }

@@ -1,2 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload contracts --ct-underlyings 16 --steps 2 --warmup 1 > gpurun_out/r2_ct_2gpu.json 2> gpurun_out/r2_ct_2gpu.err; echo rc=$?; tail -c 1500 gpurun_out/r2_ct_2gpu.err; grep -c "NCCL INFO" gpurun_out/r2_ct_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 --ct-underlyings 16 --skip-stress > gpurun_out/r2_d_2gpu.json 2> gpurun_out/r2_d_2gpu.err; echo rc=$?; tail -c 800 gpurun_out/r2_d_2gpu.err
+timeout 900 python -m pytest tests -m gpu -x -q -k "ohlcv or candle or reconstruct or contract" 2>&1 | tail -3
+python bench.py --skip-e2e --skip-contracts --skip-dropin --skip-cpu --skip-stress --n-t 600 --steps 10 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:(v['ms'],v['frac_hbm']) for k,v in d['kernels'].items()})"
