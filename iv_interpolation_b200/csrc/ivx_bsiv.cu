@@ -17,7 +17,7 @@
 //   1. an fp32 PRE-SOLVE (FP32 pipe + raw MUFU ops, runs in the shadow of other warps' fp64 work): a TABLE guess — log2 s is
 //      asymptotically linear in (log2 sqrt(2|x|), log2(-ln(beta e^{-x/2}))) in both the wing and the at-the-money regime,
 //      so a 76 x 79 table with bilinear interpolation is ~1e-3 accurate (tools/gen_iv_guess_table.py) — followed by one
-//      third-order Householder step in single precision: s to fp32 precision on all but a few 1e-5 of the quotes;
+//      Halley step in single precision: s to fp32 precision on all but a few 1e-5 of the quotes;
 //   2. an fp64 FAST PATH, straight-line: ONE Halley step on b(s) - beta with b written so that the same expression
 //      holds on both sides of the inflection point (solve_quote); accepted when the step is below 1e-4 s — after such
 //      a step the remaining error is ~1e-12 s;
@@ -138,6 +138,17 @@ __device__ const double2 LOG_TAB[64] = {
     {0.5099601593625498, 0.6734226752121667},
     {0.5059288537549407, 0.6813592248079031},
     {0.5019607843137255, 0.689233281238809}};
+// full-mantissa scalars of the fast path, in the constant bank for the same reason (one LDCU instead of two UMOVs each)
+__constant__ double KF[8] = {6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4426950408889634, 0.7071067811865476,
+                             2.5066282746310002, 1e-4, 1e-30, 2.3e-308};
+#define KF_LN2_HI KF[0]
+#define KF_LN2_LO KF[1]
+#define KF_LOG2E KF[2]
+#define KF_INV_SQRT2 KF[3]
+#define KF_SQRT_2PI KF[4]
+#define KF_ACCEPT KF[5]
+#define KF_1EM30 KF[6]
+#define KF_MIN_RATIO KF[7]
 __constant__ double LOG1P_C[7] = {-1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5};
 __device__ __forceinline__ double log_normal(double a) {
   const int hi = __double2hiint(a);
@@ -150,7 +161,7 @@ __device__ __forceinline__ double log_normal(double a) {
   for (int k = 1; k < 7; ++k) p = fma(p, u, LOG1P_C[k]);
   const double l = fma(u * u, p, u);
   const double ed = (double)e;
-  return fma(ed, 6.93147180369123816490e-01, tb.y + fma(ed, 1.90821492927058770002e-10, l));   // ln2 split hi + lo
+  return fma(ed, KF_LN2_HI, tb.y + fma(ed, KF_LN2_LO, l));   // ln2 split hi + lo
 }
 // e^{w} for |w| <= 0.35: Taylor to w^13 (truncation 2e-18 at ln2/2)
 template <int FIRST = 0>                               // FIRST = 3: Taylor to w^10 (2e-13 at ln2/2)
@@ -162,6 +173,7 @@ __device__ __forceinline__ double exp_poly(double w) {
 }
 // e^{-z} for |z| <= 1/4 (discount factors); the library exp elsewhere
 __device__ __forceinline__ double exp_neg_small(double z) {
+  if (fabs(z) <= 0.0625) return exp_poly<4>(-z);   // Taylor to w^9: 3e-19 at 1/16 (r T of weeks to a year at a few per cent)
   if (!(fabs(z) <= 0.25)) return exp(-z);
   return exp_poly(-z);
 }
@@ -169,11 +181,11 @@ __device__ __forceinline__ double exp_neg_small(double z) {
 template <int FIRST = 0>
 __device__ __forceinline__ double exp_neg_core(double z) {
   const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52: the low word of z*log2e + MAGIC is rint(z*log2e)
-  const double tn = fma(z, 1.4426950408889634, MAGIC);
+  const double tn = fma(z, KF_LOG2E, MAGIC);
   const int n = __double2loint(tn);
   const double nd = tn - MAGIC;
-  double r = fma(nd, -6.93147180369123816490e-01, z);
-  r = fma(nd, -1.90821492927058770002e-10, r);
+  double r = fma(nd, -KF_LN2_HI, z);
+  r = fma(nd, -KF_LN2_LO, r);
   return exp_poly<FIRST>(-r) * __hiloint2double((1023 - n) << 20, 0);
 }
 // the library exp outside that range
@@ -243,10 +255,10 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
     const float h = -x * inv_s, t = 0.5f * s;        // h >= 0
     const float hs = h * inv_s;
     const float r2 = h * hs - 0.25f * s;              // b2/b1: second over first derivative of b
-    const float r3 = r2 * r2 - 3.0f * hs * hs - 0.25f;  // b3/b1
-    // Householder's third-order step (quartic convergence): dn (1 + A dn/2) / (1 + dn (A + B dn/6)),
-    // dn = -g/g1, A = g2/g1, B = g3/g1 (derivatives of the objective g)
-    float g, newton, A, B;
+    // Halley's step (cubic convergence): dn / (1 + A dn / 2), dn = -g/g1, A = g2/g1 (derivatives of the objective g).  The table
+    // guess is within 1.6e-2 (1e-3 typically): one cubic step leaves s at single-precision rounding; the third-order Householder
+    // step the closed-form guess (12 % at the 99th percentile) needed is no longer worth its ten instructions.
+    float g, newton, A;
     if (lower) {
       const float q1 = (h - t) * kInvSqrt2;           // < 0 only if s overshot the inflection point
       float e1 = erfcx_pos_f(fabsf(q1));
@@ -256,16 +268,15 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
       newton = -g * D * (0.5f * kSqrt2Pi);           // -g / d1,  d1 = (ln b)' = 2 / (sqrt(2 pi) D)
       const float d1 = (2.0f / kSqrt2Pi) * f_rcp(D);
       A = r2 - d1;
-      B = r3 - 3.0f * r2 * d1 + 2.0f * d1 * d1;
     } else {
       // same identity as the fp64 polish: b = e^{x/2} - E/2 [erfcx((t-h)/sqrt2) + erfcx((t+h)/sqrt2)], E = e^{-(h^2+t^2)/2}
       const float E = f_exp(-0.5f * (h * h + t * t));
       const float b = ex2 - 0.5f * E * (erfcx_pos_f(fmaxf(t - h, 0.0f) * kInvSqrt2) + erfcx_pos_f((h + t) * kInvSqrt2));
       g = b - beta;
       newton = (-g * kSqrt2Pi) * f_rcp(E);
-      A = r2; B = r3;
+      A = r2;
     }
-    const float fac = fmaf(0.5f * A, newton, 1.0f) * f_rcp(fmaf(newton, fmaf(B * (1.0f / 6.0f), newton, A), 1.0f));
+    const float fac = f_rcp(fmaf(0.5f * A, newton, 1.0f));
     float sn = s + ((fac > 0.3f && fac < 3.0f) ? newton * fac : newton);
     if (!(sn > 0.5f * s && sn < 2.0f * s)) sn = s;   // also catches NaN; no bracket here, the fp64 phase checks the result
     s = sn;
@@ -408,13 +419,15 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
   // One reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta.
   const double rmx = rcp_fast(mx);
   double ratio = mn * rmx;                                         // (0, 1]
-  if (!(ratio >= 2.3e-308)) ok = false;                            // S/Kd beyond 1e308 (or max(S, Kd) above 1e300)
+  if (!(ratio >= KF_MIN_RATIO)) ok = false;                            // S/Kd beyond 1e308 (or max(S, Kd) above 1e300)
   const double rsq = rsqrt_fast(ratio);
   double x = PRE_X ? -fabs(x_pre) : (ratio == 1.0 ? 0.0 : log_normal(ratio));
   double ex2 = ratio * rsq;
   double beta = (target * rmx) * rsq;
   if (ok && !(beta < ex2)) ok = false;                             // rounding pushed it onto the bound
-  if (!ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9: solved alongside, result dropped
+  // lanes that are not ok: with the bracketed loop in line (DEFER = false) they solve a dummy alongside, since the loop votes
+  // and must terminate; the straight-line fast kernel needs nothing of the kind — NaNs flow through (the table index clamps)
+  if (!DEFER && !ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9
 
   const float xf = (float)x;
   // ln beta to single precision from the exponent and the leading mantissa bits (beta may be far below FLT_MIN)
@@ -443,16 +456,16 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
     const double e = 0.5 * (h * h + t * t);
     const double d = h - t;
     double e1, e2;
-    erfcx_pair_pos(fabs(d) * INV_SQRT2, (h + t) * INV_SQRT2, e1, e2);
+    erfcx_pair_pos(fabs(d) * KF_INV_SQRT2, (h + t) * KF_INV_SQRT2, e1, e2);
     const double E = exp_neg_core<3>(e);            // relative error of E = relative error of b: 2e-13 is ample
     const bool above = d < 0.0;
     const double g = fma(0.5 * E, (above ? -e1 : e1) - e2, above ? ex2 - beta : -beta);
-    const double np = -g * SQRT_2PI;
+    const double np = -g * KF_SQRT_2PI;
     const double den = fma(0.5 * np, r2, E);
     const double step = np * rcp_fast1(den);
     const double sn = s + step;
     // s >= 1e-30 keeps every argument of the pair finite; e <= 700 keeps E normal; den ~ E keeps the step a Halley step
-    accept = (fabs(step) <= ACCEPT_STEP * sn) && (s >= 1e-30) && (e <= 700.0) && (den > 0.5 * E);
+    accept = (fabs(step) <= KF_ACCEPT * sn) && (s >= KF_1EM30) && (e <= 700.0) && (den > 0.5 * E);
 #ifdef IVX_EXP_FORCE
     accept = true;
 #endif
