@@ -173,7 +173,7 @@ __device__ __forceinline__ double exp_poly(double w) {
 }
 // e^{-z} for |z| <= 1/4 (discount factors); the library exp elsewhere
 __device__ __forceinline__ double exp_neg_small(double z) {
-  if (fabs(z) <= 0.0625) return exp_poly<4>(-z);   // Taylor to w^9: 3e-19 at 1/16 (r T of weeks to a year at a few per cent)
+  if (fabs(z) <= 0.0625) return exp_poly<5>(-z);   // Taylor to w^8: 4e-17 at 1/16 (r T of weeks to a year at a few per cent)
   if (!(fabs(z) <= 0.25)) return exp(-z);
   return exp_poly(-z);
 }
@@ -211,21 +211,23 @@ __device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f
 __device__ __forceinline__ float f_log(float x) { return 0.69314718f * f_lg2(x); }
 __device__ __forceinline__ float f_exp(float x) { return f_ex2(1.44269504f * x); }
 
-// erfcx(x) for x >= 0 in single precision: (1 + 2x) erfcx(x) is smooth in t = (x-2)/(x+2) on [-1, 1);
-// degree-9 fit, 5e-7 relative (own Chebyshev fit against scipy.special.erfcx) — 16 instructions.
+// erfcx(x) for x >= 0 in single precision: (x + 2) erfcx(x) is smooth in t = (x-2)/(x+2) = 1 - 4/(x+2) on [-1, 1), so one
+// reciprocal serves the argument and the prefactor; degree-9 fit, 4.5e-7 relative as evaluated in fp32
+// (tools/gen_erfcx_fit.py) — 13 instructions.
 __device__ __forceinline__ float erfcx_pos_f(float x) {
-  const float t = (x - 2.0f) * f_rcp(x + 2.0f);
-  float p = -1.836544373e-04f;
-  p = fmaf(p, t, -9.936979918e-04f);
-  p = fmaf(p, t, 1.043144582e-03f);
-  p = fmaf(p, t, 8.337401823e-03f);
-  p = fmaf(p, t, -7.942721699e-03f);
-  p = fmaf(p, t, -5.408633070e-02f);
-  p = fmaf(p, t, 1.640358396e-01f);
-  p = fmaf(p, t, -1.660467991e-01f);
-  p = fmaf(p, t, -9.276308205e-02f);
-  p = fmaf(p, t, 1.276978705e+00f);
-  return p * f_rcp(fmaf(2.0f, x, 1.0f));
+  const float rc = f_rcp(x + 2.0f);
+  const float t = fmaf(-4.0f, rc, 1.0f);
+  float p = 7.254005613e-05f;
+  p = fmaf(p, t, -3.868958294e-04f);
+  p = fmaf(p, t, -8.597664146e-04f);
+  p = fmaf(p, t, 2.871722701e-03f);
+  p = fmaf(p, t, 6.485639701e-03f);
+  p = fmaf(p, t, -2.143603228e-02f);
+  p = fmaf(p, t, -3.644295417e-02f);
+  p = fmaf(p, t, 2.794629614e-01f);
+  p = fmaf(p, t, -6.871606703e-01f);
+  p = fmaf(p, t, 1.021582887e+00f);
+  return p * rc;
 }
 
 // ---- phase 1: single precision -------------------------------------------------------------------------
@@ -285,48 +287,46 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
 }
 
 // ---- phase 2: double precision ---------------------------------------------------------------------------
-// erfcx(q1), erfcx(q2) for q1, q2 >= 0 with ONE division: (1 + 2q) erfcx(q) is smooth in t = (q-4)/(q+4) on [-1, 1)
-// (degree-20 Chebyshev interpolant computed with mpmath at 50 digits: 8e-15 relative, smooth in q, so the
-// difference of two nearby values keeps that relative accuracy), and the four reciprocals
-// 1/(q+4), 1/(1+2q) are peeled off one reciprocal of their product.  The two Horner chains interleave.
+// erfcx(q1), erfcx(q2) for q1, q2 >= 0 with ONE division: g(t) = (q + 4) erfcx(q) is smooth in t = (q-4)/(q+4) = 1 - 8/(q+4)
+// on [-1, 1) (it tends to 1/sqrt(pi), analytic at t = 1), so the reciprocal of q + 4 gives both the argument and the
+// prefactor, and the two reciprocals are peeled off one reciprocal of the product (q1+4)(q2+4).  Degree-20 Chebyshev
+// interpolant converted to the monomial basis at 50 digits (tools/gen_erfcx_fit.py): 2.4e-15 relative as evaluated in
+// fp64, smooth in q, so the difference of two nearby values keeps that relative accuracy.  The two Horner chains
+// interleave.  (The first version fitted (1 + 2q) erfcx(q) — the same degree for 8e-15, but a second reciprocal 1/(1+2q)
+// per value: ten more fp64 operations per pair.)
 __constant__ double ERFCX_C[21] = {
-    -8.109180782116146e-09,
-    5.618350779659161e-08,
-    5.2566685922104696e-08,
-    -7.19142159951017e-07,
-    3.2140549400576467e-07,
-    5.5849674461555396e-06,
-    -1.1243141084157668e-05,
-    -2.4306876339027035e-05,
-    0.00015063187276799855,
-    -0.00019930049902749502,
-    -0.0007577763782834405,
-    0.005031983120919141,
-    -0.01619773349428245,
-    0.03716751315298436,
-    -0.06633036586880472,
-    0.09373283523715431,
-    -0.10103906603369428,
-    0.06809705424369002,
-    0.015379652102584254,
-    -0.13962111684041278,
-    1.2329951186255526};
+    -8.93653518802207727e-09,
+    2.22219577646707465e-09,
+    1.08269424077762936e-07,
+    -7.91273327604327001e-08,
+    -8.25704434017688251e-07,
+    1.42894055117218721e-06,
+    4.67854161930677550e-06,
+    -1.88645718924317614e-05,
+    -3.62746818991857262e-06,
+    1.76814599407607931e-04,
+    -4.55055022890642181e-04,
+    -2.80959402893106306e-04,
+    6.11205608281303880e-03,
+    -2.63700532427967073e-02,
+    7.63815148663746779e-02,
+    -1.74010937249687136e-01,
+    3.30851587879994469e-01,
+    -5.40853831312786415e-01,
+    7.73208702265210102e-01,
+    -9.76548729080888078e-01,
+    1.09599566100049106e+00};
 
 __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1, double& e2) {
-  const double a1 = q1 + 4.0, a2 = q2 + 4.0, b1 = fma(2.0, q1, 1.0), b2 = fma(2.0, q2, 1.0);
-  const double aa = a1 * a2, bb = b1 * b2;
-  const double r = rcp_fast(aa * bb);               // q < 1e70: the product is normal
-  const double ra = r * bb, rb = r * aa;             // 1/(a1 a2), 1/(b1 b2)
-  const double t1 = (q1 - 4.0) * (ra * a2), t2 = (q2 - 4.0) * (ra * a1);
+  const double a1 = q1 + 4.0, a2 = q2 + 4.0;
+  const double r = rcp_fast(a1 * a2);               // q < 1e70: the product is normal
+  const double r1 = r * a2, r2 = r * a1;             // 1/(q1+4), 1/(q2+4)
+  const double t1 = fma(-8.0, r1, 1.0), t2 = fma(-8.0, r2, 1.0);
   double p1 = ERFCX_C[0], p2 = ERFCX_C[0];
 #pragma unroll
-#ifdef IVX_EXP_DEG12
-  for (int k = 9; k < 21; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }
-#else
   for (int k = 1; k < 21; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }   // operands straight from the constant bank
-#endif
-  e1 = p1 * (rb * b2);
-  e2 = p2 * (rb * b1);
+  e1 = p1 * r1;
+  e2 = p2 * r2;
 }
 
 // lower: g = ln b - ln beta = ln(b / beta), one logarithm per evaluation: inv_beta = 1/beta, lnbeta_off = 0
@@ -413,13 +413,13 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
   const bool itm = (call == sg);
   const double lower_bound = itm ? diff : 0.0;
   const double upper_bound = call ? s_ : kd;
-  ok = ok && (p > lower_bound) && (p < upper_bound);               // false for NaN prices
-  const double target = itm ? p - diff : p;                         // the out-of-the-money twin, > 0 when ok
+  const double target = p - lower_bound;                            // the out-of-the-money twin (p - 0 is p; p - diff is exact near the bound)
+  ok = ok && (target > 0.0) && (p < upper_bound);                   // false for NaN prices
   // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}, beta = target / sqrt(S Kd).
   // One reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta.
   const double rmx = rcp_fast(mx);
   double ratio = mn * rmx;                                         // (0, 1]
-  if (!(ratio >= KF_MIN_RATIO)) ok = false;                            // S/Kd beyond 1e308 (or max(S, Kd) above 1e300)
+  if (!pos_normal(ratio)) ok = false;                              // S/Kd beyond 1e308 (or max(S, Kd) above 1e300): an integer test
   const double rsq = rsqrt_fast(ratio);
   double x = PRE_X ? -fabs(x_pre) : (ratio == 1.0 ? 0.0 : log_normal(ratio));
   double ex2 = ratio * rsq;
@@ -441,8 +441,9 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
 #else
   float s0 = presolve_f32(xf, (float)beta, lnbeta_f, (float)ex2, s_tab, lower);
 #endif
-  double s = (double)s0;
-  if (!(s > 0.0 && s < S_MAX)) s = 1.0;   // fp32 range exhausted: the bracketed fp64 loop takes it from anywhere
+  // fp32 range exhausted (or s so small that an argument of the erfcx pair would overflow): the bracketed fp64 loop takes it from anywhere
+  const bool s_ok = s0 >= 1e-30f && s0 < (float)S_MAX;
+  double s = s_ok ? (double)s0 : 1.0;
   // ---- fast path: ONE fp64 Halley step on b(s) - beta, the same expression on both sides of the inflection point:
   //   b = [h < t] e^{x/2} + E/2 (sgn(h-t) erfcx(|h-t|/sqrt2) - erfcx((h+t)/sqrt2)),  b' = E / sqrt(2 pi),  b''/b' = r2.
   // Accepted when the step is below 1e-4 s (cubic convergence: what is left is ~1e-12 s); anything else — a pre-solve
@@ -458,14 +459,21 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
     double e1, e2;
     erfcx_pair_pos(fabs(d) * KF_INV_SQRT2, (h + t) * KF_INV_SQRT2, e1, e2);
     const double E = exp_neg_core<3>(e);            // relative error of E = relative error of b: 2e-13 is ample
-    const bool above = d < 0.0;
-    const double g = fma(0.5 * E, (above ? -e1 : e1) - e2, above ? ex2 - beta : -beta);
+    // sign and mask by integer operations on the high words (an fp64 compare, negation or select costs two issue cycles each):
+    // e1 >= 0 takes the sign of d; ex2 is kept where d < 0 (h - t = 0 is +0: not above)
+    const int dhi = __double2hiint(d), above_mask = dhi >> 31;
+    const double e1s = __hiloint2double(__double2hiint(e1) | (dhi & (int)0x80000000), __double2loint(e1));
+    const double cst = __hiloint2double(__double2hiint(ex2) & above_mask, __double2loint(ex2) & above_mask);
+    const double g = fma(0.5 * E, e1s - e2, cst - beta);
     const double np = -g * KF_SQRT_2PI;
     const double den = fma(0.5 * np, r2, E);
     const double step = np * rcp_fast1(den);
     const double sn = s + step;
-    // s >= 1e-30 keeps every argument of the pair finite; e <= 700 keeps E normal; den ~ E keeps the step a Halley step
-    accept = (fabs(step) <= KF_ACCEPT * sn) && (s >= KF_1EM30) && (e <= 700.0) && (den > 0.5 * E);
+    // s >= 1e-30 keeps every argument of the pair finite; e < 700 keeps E normal (high-word compare: e >= 0, and a NaN e makes
+    // the step NaN).  With e < 700, |r2 s| <= 1400, so a step below 1e-4 s implies a Halley denominator within [E/2, 3E/2]
+    // (|correction| <= 700 |newton|/s and |1 + correction| >= 1e4 |newton|/s cannot both hold above 1.1e-4): den > 0 is all
+    // that is left to check, on the sign bit.
+    accept = (fabs(step) <= KF_ACCEPT * sn) && s_ok && (__double2hiint(e) < 0x4085E000) && (__double2hiint(den) > 0);
 #ifdef IVX_EXP_FORCE
     accept = true;
 #endif
