@@ -242,15 +242,24 @@ int ivx_spline_fit_eval_ladder_verify(int64_t n_slices, const int64_t* knot_off,
  * with the ladder tables lu_* of ivx_spline_ladder_factor.  Slices that belong to no ladder group are not touched.
  * order / lad_slice_off: the slices grouped by ladder (CSR); max_slices_per_ladder sizes the grid. */
 int64_t ivx_spline_band_len(int64_t n_ladders, int64_t n_q);
+int64_t ivx_spline_band_frag_len(int64_t n_ladders);   /* doubles of band_frag */
+int64_t ivx_spline_band_oct_len(int64_t n_ladders);    /* int32 of band_oct */
+/* band_frag / band_oct (both or neither; NULL = dot-product form only): the same weights laid out as fp64 mma B fragments per group of
+ * 8 grid points, for the tensor-path form of the evaluation (the operator applied to 8 slices at a time as a block-banded matrix
+ * product, mma.sync m8n8k4).  ladder_ok[l] bit 0 = band usable, bit 1 = tensor-path tables usable (every 8-point group spans at
+ * most 96 knots, every 64-point slab at most 512).  band_oct ends with {largest slab extent, largest step count} per ladder:
+ * the largest extent over the ladders is the slab_knots_hint of ivx_spline_fit_eval_banded (0 = unknown: 512 is assumed). */
 int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
                           int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok,
-                          int16_t* band_perm /* n_ladders*512: which grid point each thread of the evaluation takes */, ivx_stream_t stream);
+                          int16_t* band_perm /* n_ladders*512: which grid point each thread of the evaluation takes */,
+                          double* band_frag, int32_t* band_oct, ivx_stream_t stream);
 int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const int32_t* slice_ladder,
                                const int32_t* order, const int64_t* lad_slice_off, int64_t n_ladders, int64_t max_slices_per_ladder,
                                const int64_t* ladder_off, int64_t max_knots, const double* x_ladder, const double* x_own /*or NULL*/,
                                const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
-                               const uint8_t* ladder_ok, const int16_t* band_perm, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream);
+                               const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
+                               int32_t slab_knots_hint, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream);
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);

@@ -173,7 +173,7 @@ __device__ __forceinline__ double exp_poly(double w) {
 }
 // e^{-z} for |z| <= 1/4 (discount factors); the library exp elsewhere
 __device__ __forceinline__ double exp_neg_small(double z) {
-  if (fabs(z) <= 0.0625) return exp_poly<5>(-z);   // Taylor to w^8: 4e-17 at 1/16 (r T of weeks to a year at a few per cent)
+  if ((__double2hiint(z) & 0x7fffffff) < 0x3FB00000) return exp_poly<5>(-z);   // |z| < 1/16 (high-word compare): Taylor to w^8, 4e-17 (r T of weeks to a year at a few per cent)
   if (!(fabs(z) <= 0.25)) return exp(-z);
   return exp_poly(-z);
 }
@@ -187,6 +187,25 @@ __device__ __forceinline__ double exp_neg_core(double z) {
   double r = fma(nd, -KF_LN2_HI, z);
   r = fma(nd, -KF_LN2_LO, r);
   return exp_poly<FIRST>(-r) * __hiloint2double((1023 - n) << 20, 0);
+}
+// e^{-q/2} / sqrt(2 pi) for 0 <= q < 1400 (the fast path's b' = E/sqrt(2 pi), E = e^{-(h^2+t^2)/2}): q/2 = n ln2 + r; the halving is
+// folded into the constants (q log2e/2, 2 ln2, coefficients 1/(k! 2^k) to k = 10: 2e-13 at |r| = ln2/2) and 1/sqrt(2 pi) = 1.5958 x 2^-2
+// into the power of two that is assembled from n.  One multiple of ln2, not a hi + lo pair: n <= 1010 and an ulp of 2 ln2 move
+// r by 1.5e-13 at most, the size of the truncation.
+__constant__ double EXPH_C[12] = {2.69114445546737190e-10, 5.38228891093474463e-09, 9.68812003968253967e-08, 1.55009920634920635e-06,
+                                  2.17013888888888897e-05, 2.60416666666666663e-04, 2.60416666666666652e-03, 2.08333333333333322e-02,
+                                  0.125,                   0.5,                     0.7213475204444817,      1.3862943611198906};
+__device__ __forceinline__ double exp_half_neg_over_sqrt2pi(double q) {
+  const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52
+  const double tn = fma(q, EXPH_C[10], MAGIC);
+  const int n = __double2loint(tn);
+  const double nd = tn - MAGIC;
+  const double w = fma(nd, EXPH_C[11], -q);                       // -(q - 2 n ln2) = -2r
+  double p = EXPH_C[0];
+#pragma unroll
+  for (int k = 1; k < 10; ++k) p = fma(p, w, EXPH_C[k]);
+  p = fma(p, w, 1.0);
+  return p * __hiloint2double(((1021 - n) << 20) | 0x98845, 0x33d43651);   // 2^-n / sqrt(2 pi)
 }
 // the library exp outside that range
 __device__ __forceinline__ double exp_neg(double z) {
@@ -317,14 +336,40 @@ __constant__ double ERFCX_C[21] = {
     -9.76548729080888078e-01,
     1.09599566100049106e+00};
 
+// the same coefficients times sqrt(2 pi)/2: the fast path wants E/sqrt(2 pi) (= b') times [sqrt(2 pi)/2 (erfcx - erfcx)]
+__constant__ double ERFCX_CS[21] = {
+    -1.12002858897655023e-08,
+    2.78510938252897965e-09,
+    1.35695599835667513e-07,
+    -9.91714047967182288e-08,
+    -1.03486704039846220e-06,
+    1.79091139416750533e-06,
+    5.86368235349613527e-06,
+    -2.36432346471893475e-05,
+    -4.54635716508721532e-06,
+    2.21604237121331903e-04,
+    -5.70326893445270472e-04,
+    -3.52130391657651601e-04,
+    7.66032629665477915e-03,
+    -3.30499605309595643e-02,
+    9.57300324116014401e-02,
+    -2.18090367702553301e-01,
+    4.14660972443278708e-01,
+    -6.77859753005568000e-01,
+    9.69073397644359291e-01,
+    -1.22392232793456146e+00,
+    1.37362685636836201e+00};
+
+template <bool SCALED = false>
 __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1, double& e2) {
+  const double* C = SCALED ? ERFCX_CS : ERFCX_C;
   const double a1 = q1 + 4.0, a2 = q2 + 4.0;
   const double r = rcp_fast(a1 * a2);               // q < 1e70: the product is normal
   const double r1 = r * a2, r2 = r * a1;             // 1/(q1+4), 1/(q2+4)
   const double t1 = fma(-8.0, r1, 1.0), t2 = fma(-8.0, r2, 1.0);
-  double p1 = ERFCX_C[0], p2 = ERFCX_C[0];
+  double p1 = C[0], p2 = C[0];
 #pragma unroll
-  for (int k = 1; k < 21; ++k) { p1 = fma(p1, t1, ERFCX_C[k]); p2 = fma(p2, t2, ERFCX_C[k]); }   // operands straight from the constant bank
+  for (int k = 1; k < 21; ++k) { p1 = fma(p1, t1, C[k]); p2 = fma(p2, t2, C[k]); }   // operands straight from the constant bank
   e1 = p1 * r1;
   e2 = p2 * r2;
 }
@@ -412,16 +457,22 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
   const double diff = mx - mn;
   const bool itm = (call == sg);
   const double lower_bound = itm ? diff : 0.0;
-  const double upper_bound = call ? s_ : kd;
   const double target = p - lower_bound;                            // the out-of-the-money twin (p - 0 is p; p - diff is exact near the bound)
-  ok = ok && (target > 0.0) && (p < upper_bound);                   // false for NaN prices
+  // the upper bound (call: p < S, put: p < Kd) is target < min(S, Kd) for the twin, i.e. beta < e^{x/2}: tested once, below
+  ok = ok && (target > 0.0);                                        // false for NaN prices
   // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}, beta = target / sqrt(S Kd).
   // One reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta.
   const double rmx = rcp_fast(mx);
   double ratio = mn * rmx;                                         // (0, 1]
   if (!pos_normal(ratio)) ok = false;                              // S/Kd beyond 1e308 (or max(S, Kd) above 1e300): an integer test
   const double rsq = rsqrt_fast(ratio);
-  double x = PRE_X ? -fabs(x_pre) : (ratio == 1.0 ? 0.0 : log_normal(ratio));
+  double x;
+  if (PRE_X) x = -fabs(x_pre);
+  else {                                                           // ratio = 1 gives +-1e-18 from the table: positive results become 0 (sign-bit mask)
+    const double lx = log_normal(ratio);
+    const int keep = __double2hiint(lx) >> 31;
+    x = __hiloint2double(__double2hiint(lx) & keep, __double2loint(lx) & keep);
+  }
   double ex2 = ratio * rsq;
   double beta = (target * rmx) * rsq;
   if (ok && !(beta < ex2)) ok = false;                             // rounding pushed it onto the bound
@@ -451,29 +502,33 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
   int it = 1;
   bool accept;
   {
+    // Halley: step = -g / (b' - g b''/(2 b')),  b' = E/sqrt(2 pi) =: Ec,  b''/b' = h^2/s - s/4
     const double inv_s = rcp_fast(s);
     const double h = -x * inv_s, t = 0.5 * s;        // h >= 0
-    const double r2 = h * h * inv_s - 0.25 * s;
-    const double e = 0.5 * (h * h + t * t);
+    const double hh = h * h;
+    // (1/s)/2 by an exponent decrement (1/40 < 1/s <= 1e30: normal)
+    const double half_inv_s = __hiloint2double(__double2hiint(inv_s) - 0x00100000, __double2loint(inv_s));
+    const double r2h = fma(hh, half_inv_s, -0.125 * s);              // b''/(2 b')
+    const double q = fma(t, t, hh);                                  // h^2 + t^2
     const double d = h - t;
     double e1, e2;
-    erfcx_pair_pos(fabs(d) * KF_INV_SQRT2, (h + t) * KF_INV_SQRT2, e1, e2);
-    const double E = exp_neg_core<3>(e);            // relative error of E = relative error of b: 2e-13 is ample
+    erfcx_pair_pos<true>(fabs(d) * KF_INV_SQRT2, (h + t) * KF_INV_SQRT2, e1, e2);   // both times sqrt(2 pi)/2
+    const double Ec = exp_half_neg_over_sqrt2pi(q);  // relative error of E = relative error of b: 3e-13 is ample
     // sign and mask by integer operations on the high words (an fp64 compare, negation or select costs two issue cycles each):
     // e1 >= 0 takes the sign of d; ex2 is kept where d < 0 (h - t = 0 is +0: not above)
     const int dhi = __double2hiint(d), above_mask = dhi >> 31;
     const double e1s = __hiloint2double(__double2hiint(e1) | (dhi & (int)0x80000000), __double2loint(e1));
     const double cst = __hiloint2double(__double2hiint(ex2) & above_mask, __double2loint(ex2) & above_mask);
-    const double g = fma(0.5 * E, e1s - e2, cst - beta);
-    const double np = -g * KF_SQRT_2PI;
-    const double den = fma(0.5 * np, r2, E);
-    const double step = np * rcp_fast1(den);
+    const double g = fma(Ec, e1s - e2, cst - beta);                  // b(s) - beta
+    const double den = fma(-g, r2h, Ec);
+    const double step = -g * rcp_fast1(den);
     const double sn = s + step;
-    // s >= 1e-30 keeps every argument of the pair finite; e < 700 keeps E normal (high-word compare: e >= 0, and a NaN e makes
-    // the step NaN).  With e < 700, |r2 s| <= 1400, so a step below 1e-4 s implies a Halley denominator within [E/2, 3E/2]
-    // (|correction| <= 700 |newton|/s and |1 + correction| >= 1e4 |newton|/s cannot both hold above 1.1e-4): den > 0 is all
-    // that is left to check, on the sign bit.
-    accept = (fabs(step) <= KF_ACCEPT * sn) && s_ok && (__double2hiint(e) < 0x4085E000) && (__double2hiint(den) > 0);
+    // Accepted when |step| < 2^-13 s (high-word compare, unsigned so that a NaN step fails).  s >= 1e-30 keeps every argument of
+    // the pair finite; q < 1400 keeps E normal (q >= 0, and a NaN q makes the step NaN).  With q < 1400, |s b''/b'| <= 1400, so a
+    // step that small implies a Halley denominator within [Ec/2, 3 Ec/2] (|correction| <= 700 |newton|/s and
+    // |1 + correction| >= 8192 |newton|/s cannot both hold above 1.4e-4): den > 0 is all that is left to check, on the sign bit.
+    accept = ((unsigned)((__double2hiint(step) & 0x7fffffff) + (13 << 20)) < (unsigned)__double2hiint(s)) && s_ok &&
+             (__double2hiint(q) < 0x4095E000) && (__double2hiint(den) > 0);
 #ifdef IVX_EXP_FORCE
     accept = true;
 #endif
@@ -499,7 +554,7 @@ __device__ __forceinline__ void record_deferred(bool deferred, uint32_t warp_id,
 // One launch covers at most 2^31 quotes (the wrapper offsets the pointers): a 32-bit quote index keeps the address
 // arithmetic of the six loads to one IMAD.WIDE each.  ITERS = false: the iteration counts are not wanted (the hot path).
 template <bool ITERS, bool DEFER>
-__global__ void __launch_bounds__(256, 5) k_bs_implied_vol(uint32_t n, const double* __restrict__ price,
+__global__ void __launch_bounds__(256, 6) k_bs_implied_vol(uint32_t n, const double* __restrict__ price,
                                                         const double* __restrict__ S, const double* __restrict__ K,
                                                         const double* __restrict__ T, const double* __restrict__ r,
                                                         const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
@@ -618,7 +673,7 @@ __device__ __forceinline__ bool chain_quote(int32_t j, int64_t t, int32_t n_exp,
 
 // grid: x over the n_exp*n_strike contracts of one stamp, y over stamps
 template <bool DEFER, bool TICKS>
-__global__ void __launch_bounds__(256, 5) k_bs_implied_vol_chain(int64_t t0, int32_t n_exp, int32_t n_strike, int64_t n_t,
+__global__ void __launch_bounds__(256, 6) k_bs_implied_vol_chain(int64_t t0, int32_t n_exp, int32_t n_strike, int64_t n_t,
                                                               const double* __restrict__ price, const uint8_t* __restrict__ is_call,
                                                               int32_t call_per_quote, const double* __restrict__ S_t, const double* __restrict__ K_ek,
                                                               const double* __restrict__ T_te, const double* __restrict__ terms,

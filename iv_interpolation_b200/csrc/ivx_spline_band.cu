@@ -18,6 +18,15 @@
 //                    different banks; results leave through a shared-memory transpose, coalesced.
 //                    Slices that cannot be taken (a missing knot, off the ladder, odd length) are FLAGGED (one int32 per slice).
 //   * the flagged slices are then solved by the exact kernel (ivx_spline.cu, k_spline_fit_eval_list), in slice order, same stream.
+//   * k_band_apply_mma  the same operator as a BLOCK-BANDED MATRIX PRODUCT on the fp64 tensor path (mma.sync m8n8k4, SASS DMMA:
+//                    measured 37.2 TFLOP/s on B200, the DFMA rate, but 256 multiply-adds per instruction instead of 32).  With
+//                    all slices of a ladder sharing W, yq[slice][point] = sum_k y[slice][k] W[point][k] IS a contraction: a warp
+//                    owns 8 consecutive grid points, whose windows jointly span ~76 knots, keeps their weights as B fragments in
+//                    registers for a whole batch of slices, and multiplies 8 slices at a time: 19 DMMA + 19 shared-memory loads
+//                    per 8 x 8 outputs, where the dot-product form needs 96 loads and 96 x 32 DFMA lanes (its limiter, per ncu,
+//                    was the shared-memory instruction queue).  A CTA = 64 grid points (8 warps); it stages only the ~300 knots
+//                    its points touch, 8 slices per stage, two stages of cp.async, ONE block barrier per 8 slices.
+//                    Ladders whose windows are too wide for the fragment registers keep k_band_apply.
 #include "ivx_common.cuh"
 
 namespace ivx {
@@ -30,6 +39,12 @@ constexpr int BAND_MAXK = 2048;
 constexpr int BAND_NBUF = 3;
 constexpr int BAND_THREADS = 512;
 constexpr int BAND_BATCH = 48;              // slices per CTA at most: the 200 KB of weights are read once per batch
+// tensor-path form
+constexpr int MMA_KS = 24;                  // k-steps of 4 knots per 8-point group at most (96 knots): B fragments held in 48 registers
+constexpr int MMA_OCT = BAND_MAXQ / 8;      // 64 groups of 8 grid points
+constexpr int MMA_SLAB_MAX = 512;           // knots a 64-point CTA may touch
+constexpr int MMA_BATCH = 128;              // slices per CTA (16 tiles of 8): the 48 KB of fragments are read once per batch
+constexpr int LADDER_OK_BAND = 1, LADDER_OK_MMA = 2;   // bits of ladder_ok
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -215,6 +230,55 @@ __global__ void __launch_bounds__(32) k_band_perm(int32_t n_q, const int32_t* __
     }
 }
 
+// ---- tensor-path tables: per (ladder, group of 8 points) the first knot kb (even) and the number of 4-knot steps that cover
+// the union of the 8 windows, and the weights laid out as mma B fragments: frag[((l*64 + o)*MMA_KS + ks)*32 + lane] =
+// W[point 8o + (lane>>2)][knot kb + 4 ks + (lane&3)].  ladder_ok gets LADDER_OK_MMA when every group fits MMA_KS steps and
+// every 64-point slab MMA_SLAB_MAX knots.  meta[l] = {largest slab extent, largest step count}.
+__global__ void __launch_bounds__(256) k_band_frag(int32_t n_q, const int64_t* __restrict__ ladder_off, const int32_t* __restrict__ band_k0,
+                                                   const double* __restrict__ band_w, uint8_t* __restrict__ ladder_ok,
+                                                   double* __restrict__ frag, int32_t* __restrict__ oct, int32_t* __restrict__ meta) {
+  __shared__ int s_kb[MMA_OCT], s_ke[MMA_OCT];
+  __shared__ int s_bad, s_ext, s_nks;
+  const int l = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = (int)(ladder_off[l + 1] - ladder_off[l]);
+  if (threadIdx.x == 0) { s_bad = 0; s_ext = 0; s_nks = 0; }
+  __syncthreads();
+  const bool band_ok = (ladder_ok[l] & LADDER_OK_BAND) != 0;
+  for (int o = warp; o < MMA_OCT; o += 8) {
+    const int g = lane >> 2, tig = lane & 3;
+    const int q = 8 * o + g;
+    const int k0 = (band_ok && q < n_q) ? band_k0[(int64_t)l * n_q + q] : -1;
+    int lo = k0 >= 0 ? k0 : INT32_MAX, hi = k0 >= 0 ? k0 + BAND_W : 0;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { lo = min(lo, __shfl_xor_sync(IVX_FULL_MASK, lo, d)); hi = max(hi, __shfl_xor_sync(IVX_FULL_MASK, hi, d)); }
+    int kb = 0, nks = 0;
+    if (hi > 0) { kb = lo & ~1; hi = min(hi, n); nks = (hi - kb + 3) >> 2; }
+    if (nks > MMA_KS) { if (lane == 0) s_bad = 1; nks = 0; }
+    if (lane == 0) {
+      oct[((int64_t)l * MMA_OCT + o) * 2] = kb; oct[((int64_t)l * MMA_OCT + o) * 2 + 1] = nks;
+      s_kb[o] = nks > 0 ? kb : INT32_MAX; s_ke[o] = nks > 0 ? kb + 4 * nks : 0;
+      atomicMax(&s_nks, nks);
+    }
+    const double* __restrict__ wq = band_w + ((int64_t)l * n_q + (q < n_q ? q : 0)) * BAND_W;
+    for (int ks = 0; ks < MMA_KS; ++ks) {
+      const int j = kb + 4 * ks + tig - k0;
+      const double v = (k0 >= 0 && ks < nks && j >= 0 && j < BAND_W) ? wq[j] : 0.0;
+      frag[(((int64_t)l * MMA_OCT + o) * MMA_KS + ks) * 32 + lane] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < MMA_OCT / 8) {                  // slab extents
+    int lo = INT32_MAX, hi = 0;
+    for (int o = 8 * threadIdx.x; o < 8 * threadIdx.x + 8; ++o) { lo = min(lo, s_kb[o]); hi = max(hi, s_ke[o]); }
+    if (hi > 0) { if (hi - lo > MMA_SLAB_MAX) s_bad = 1; atomicMax(&s_ext, hi - lo); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (band_ok && !s_bad) ladder_ok[l] |= LADDER_OK_MMA;
+    meta[2 * l] = s_ext; meta[2 * l + 1] = s_nks;
+  }
+}
+
 // ---- apply -----------------------------------------------------------------------------------------------------------
 struct BandParams {
   const int64_t* knot_off;       // [n_slices+1]
@@ -233,6 +297,11 @@ struct BandParams {
   uint32_t* fb_count;
   int32_t n_q;
   int32_t batch;                 // slices per CTA
+  // tensor-path form (k_band_apply_mma); frag == NULL: k_band_apply takes every ladder
+  const double* frag;            // [n_ladders][64][MMA_KS][32] B fragments (k_band_frag)
+  const int32_t* oct;            // [n_ladders][64][2] first knot and step count of every 8-point group
+  int32_t row;                   // doubles per staged slice row (slab extent + padding), = 4 mod 16
+  int32_t vec_ok;                // n_q even and yq 16-byte aligned
 };
 
 template <bool VERIFY>
@@ -249,6 +318,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
   const int ns = (int)min((int64_t)P.batch, s_end_all - s_begin);
   const int32_t* __restrict__ ord = P.order + s_begin;
   const int t = threadIdx.x;
+  if (P.frag && (P.ladder_ok[l] & LADDER_OK_MMA)) return;    // k_band_apply_mma takes this ladder
   if (!P.ladder_ok[l]) {                                     // no usable band for this ladder: everything to the exact solve
     for (int i = t; i < ns; i += BAND_THREADS) P.fb_list[ord[i]] = 1;
     if (t == 0) atomicAdd(P.fb_count, (uint32_t)ns);
@@ -361,6 +431,192 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
   cp_async_wait<0>();
 }
 
+
+// ---- apply, tensor path ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// grid: x = 64-point slab, y = batch of MMA_BATCH slices, z = ladder; 256 threads; a staged row holds 32 NIT knots (+4 of padding:
+// rows 4 mod 16 doubles apart keep the fragment loads conflict-free).  Warp w stages row w of every tile (one slice's slab of knots:
+// cp.async, 16 bytes at a time where the slice's address allows), checks that row — every y finite, every x equal to the ladder's
+// bit for bit, both as integer operations on the words — votes inside the warp, and multiplies the 8-point group 8 slab + w
+// against all 8 rows.  Knots that no slab touches (the grid may be narrower than the ladder) are dealt evenly to the slabs and
+// checked straight from global memory.
+template <bool VERIFY, int NIT>
+__global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
+  constexpr int ROW = 32 * NIT + 4;
+  extern __shared__ __align__(16) double sm[];
+  double* ybuf = sm;                                         // [2][8][ROW]
+  double* xbuf = ybuf + 2 * 8 * ROW;                         // [2][8][ROW]   (VERIFY)
+  double* ladx = xbuf + (VERIFY ? 2 * 8 * ROW : 0);          // [ROW]         (VERIFY)
+  __shared__ int s_kb[8], s_ke[8], s_kfirst, s_klast;
+  __shared__ int32_t s_sid[2][8];                            // slice of every row, -1 = no store (no such row, or flagged)
+  __shared__ int64_t s_base[MMA_BATCH];                      // first knot of every slice of the batch, -1 = another length than the ladder
+  __shared__ int32_t s_id[MMA_BATCH];
+  const int l = blockIdx.z, slab = blockIdx.x;
+  if (!(P.ladder_ok[l] & LADDER_OK_MMA)) return;
+  const int64_t s_begin = P.lad_slice_off[l] + (int64_t)blockIdx.y * MMA_BATCH;
+  const int64_t s_end_all = P.lad_slice_off[l + 1];
+  if (s_begin >= s_end_all) return;
+  const int ns = (int)min((int64_t)MMA_BATCH, s_end_all - s_begin);
+  const int32_t* __restrict__ ord = P.order + s_begin;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+  const int n = (int)(P.ladder_off[l + 1] - P.ladder_off[l]);
+  const int n_q = P.n_q;
+  const int o = slab * 8 + w;                                // this warp's group of 8 grid points
+  const int32_t* __restrict__ octl = P.oct + (int64_t)l * MMA_OCT * 2;
+  const int kb = octl[o * 2], nks = octl[o * 2 + 1];
+  if (lane == 0) { s_kb[w] = nks > 0 ? kb : INT32_MAX; s_ke[w] = nks > 0 ? kb + 4 * nks : 0; }
+  if (w == 0) {                                              // knots before the first window and after the last one
+    const unsigned b0 = __ballot_sync(IVX_FULL_MASK, octl[lane * 2 + 1] > 0);
+    const unsigned b1 = __ballot_sync(IVX_FULL_MASK, octl[(32 + lane) * 2 + 1] > 0);
+    if (lane == 0) {
+      const int of = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : -1);
+      const int ol = b1 ? 63 - __clz(b1) : (b0 ? 31 - __clz(b0) : -1);
+      s_kfirst = of >= 0 ? octl[of * 2] : n;                // no window at all: every knot is "before the first"
+      s_klast = ol >= 0 ? min(n, octl[ol * 2] + 4 * octl[ol * 2 + 1]) : n;
+    }
+  }
+  if (threadIdx.x < ns) {
+    const int32_t sl = ord[threadIdx.x];
+    const int64_t ko = P.knot_off[sl];
+    s_id[threadIdx.x] = sl;
+    s_base[threadIdx.x] = (P.knot_off[sl + 1] - ko) == (int64_t)n ? ko : (int64_t)-1;
+  }
+  __syncthreads();
+  int KB = INT32_MAX, KE = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { KB = min(KB, s_kb[i]); KE = max(KE, s_ke[i]); }
+  if (KE == 0) KB = 0;                                       // every point of this slab is NaN by construction: nothing staged, NaNs written
+  const int klen = KE - KB;                                  // <= MMA_SLAB_MAX (k_band_frag); the host chose NIT from the same tables
+  if (klen > 32 * NIT) {                                     // the caller's hint was too small: the batch goes to the exact solve
+    for (int i = threadIdx.x; i < ns; i += 256)
+      if (atomicExch(P.fb_list + s_id[i], 1) == 0) atomicAdd(P.fb_count, 1u);
+    return;
+  }
+  const int nvalid = min(klen, n - KB);                      // knots of the slab that exist; the rest of the row stays 0
+  // this slab's share of the knots no slab stages: [0, kfirst) and [klast, n), dealt evenly
+  const int kfirst = s_kfirst, klast = s_klast;
+  const int n_out = kfirst + (n - klast), per = (n_out + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int out_lo = min(n_out, slab * per), out_hi = min(n_out, out_lo + per);
+  // B fragments of this warp's 8 points, for the whole batch
+  double wreg[MMA_KS];
+  {
+    const double* __restrict__ fp = P.frag + (((int64_t)l * MMA_OCT + o) * MMA_KS) * 32 + lane;
+#pragma unroll
+    for (int ks = 0; ks < MMA_KS; ++ks) wreg[ks] = __ldg(fp + ks * 32);
+  }
+  // the two points of this lane's accumulator pair: 8o + 2 tig, + 1
+  const int q0 = 8 * o + 2 * tig;
+  const bool st0 = q0 < n_q, st1 = q0 + 1 < n_q;
+  const bool nan0 = st0 && P.band_k0[(int64_t)l * n_q + q0] < 0, nan1 = st1 && P.band_k0[(int64_t)l * n_q + q0 + 1] < 0;
+  const bool vec_out = P.vec_ok && st1;                       // 16-byte stores (n_q even, yq aligned)
+  // zero both stages once (cp.async never writes past nvalid), ladder abscissae of the slab
+  for (int i = threadIdx.x; i < (VERIFY ? 4 : 2) * 8 * ROW; i += 256) ybuf[i] = 0.0;
+  if (VERIFY)
+    for (int k = threadIdx.x; k < ROW; k += 256) ladx[k] = k < nvalid ? __ldg(P.x_ladder + P.ladder_off[l] + KB + k) : 0.0;
+  __syncthreads();
+  const int ntiles = (ns + 7) >> 3;
+  auto issue = [&](int tile, int buf) {                      // row w of the tile
+    const int idx = tile * 8 + w;
+    const int64_t ko = idx < ns ? s_base[idx] : (int64_t)-1;
+    if (ko >= 0) {
+      const double* __restrict__ ysrc = P.y + ko + KB;
+      double* yb = ybuf + (buf * 8 + w) * ROW;
+      const double* __restrict__ xsrc = VERIFY ? P.x_own + ko + KB : nullptr;
+      double* xb = xbuf + (buf * 8 + w) * ROW;
+      const bool vec = (((uintptr_t)ysrc | (VERIFY ? (uintptr_t)xsrc : 0)) & 15u) == 0;      // warp-uniform
+      if (vec) {
+#pragma unroll
+        for (int r = 0; r < NIT / 2; ++r) {
+          const int k = 2 * (lane + 32 * r);
+          if (k + 1 < nvalid) { cp_async16(yb + k, ysrc + k); if (VERIFY) cp_async16(xb + k, xsrc + k); }
+          else if (k < nvalid) { cp_async8(yb + k, ysrc + k); if (VERIFY) cp_async8(xb + k, xsrc + k); }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < NIT; ++r) {
+          const int k = lane + 32 * r;
+          if (k < nvalid) { cp_async8(yb + k, ysrc + k); if (VERIFY) cp_async8(xb + k, xsrc + k); }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  issue(0, 0);
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    {
+      const int idx = tile * 8 + w;
+      const int64_t ko = idx < ns ? s_base[idx] : (int64_t)-1;
+      // knots outside every slab: loads first, they travel while the staged row is checked
+      uint32_t bad = 0;
+      if (ko >= 0) {
+        for (int i = out_lo + lane; i < out_hi; i += 32) {
+          const int k = i < kfirst ? i : klast + (i - kfirst);
+          const double yv = __ldg(P.y + ko + k);
+          bad |= ((uint32_t)__double2hiint(yv) & 0x7ff00000u) == 0x7ff00000u;
+          if (VERIFY) {
+            const double xv = __ldg(P.x_own + ko + k), lv = __ldg(P.x_ladder + P.ladder_off[l] + k);
+            bad |= (uint32_t)((__double2hiint(xv) ^ __double2hiint(lv)) | (__double2loint(xv) ^ __double2loint(lv)));
+          }
+        }
+      }
+      cp_async_wait<0>();                                    // the lanes' parts of row w have landed ...
+      __syncwarp();                                          // ... and are visible to the whole warp
+      if (ko >= 0) {
+        const double2* yb = reinterpret_cast<const double2*>(ybuf + (buf * 8 + w) * ROW);
+        const double2* xb = reinterpret_cast<const double2*>(xbuf + (buf * 8 + w) * ROW);
+        const double2* lx = reinterpret_cast<const double2*>(ladx);
+        uint32_t emax = 0;                                   // largest exponent field seen: 0x7ff = NaN or infinity (zeros past nvalid pass)
+#pragma unroll
+        for (int r = 0; r < NIT / 2; ++r) {
+          const int c = lane + 32 * r;
+          const double2 yv = yb[c];
+          emax = max(emax, max((uint32_t)__double2hiint(yv.x) & 0x7ff00000u, (uint32_t)__double2hiint(yv.y) & 0x7ff00000u));
+          if (VERIFY) {
+            const double2 xv = xb[c], lv = lx[c];
+            bad |= (uint32_t)((__double2hiint(xv.x) ^ __double2hiint(lv.x)) | (__double2loint(xv.x) ^ __double2loint(lv.x)) |
+                              (__double2hiint(xv.y) ^ __double2hiint(lv.y)) | (__double2loint(xv.y) ^ __double2loint(lv.y)));
+          }
+        }
+        bad |= emax == 0x7ff00000u;
+      }
+      const bool ok = (ko >= 0) && __all_sync(IVX_FULL_MASK, bad == 0);
+      if (lane == 0) {
+        const int32_t sl = idx < ns ? s_id[idx] : -1;
+        if (idx < ns && !ok && atomicExch(P.fb_list + sl, 1) == 0) atomicAdd(P.fb_count, 1u);   // for the exact solve, counted once
+        s_sid[buf][w] = ok ? sl : -1;
+      }
+    }
+    __syncthreads();                                         // rows and verdicts of this tile visible; the other stage is free
+    if (tile + 1 < ntiles) issue(tile + 1, buf ^ 1); else cp_async_commit();
+    // 8 slices x 8 points: two accumulator chains
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    const double* arow = ybuf + (buf * 8 + g) * ROW + (kb - KB) + tig;
+#pragma unroll
+    for (int ks = 0; ks < MMA_KS; ks += 2) {
+      if (ks < nks) dmma_884(c0, c1, arow[4 * ks], wreg[ks]);
+      if (ks + 1 < nks) dmma_884(d0, d1, arow[4 * ks + 4], wreg[ks + 1]);
+    }
+    const int32_t sl = s_sid[buf][g];
+    if (sl >= 0) {
+      double r0 = c0 + d0, r1 = c1 + d1;
+      if (nan0) r0 = qnan();
+      if (nan1) r1 = qnan();
+      double* dst = P.yq + (int64_t)sl * n_q + q0;
+      if (vec_out) __stcs(reinterpret_cast<double2*>(dst), make_double2(r0, r1));
+      else { if (st0) st_stream(dst, r0); if (st1) st_stream(dst + 1, r1); }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace
 }  // namespace ivx
 
@@ -371,8 +627,20 @@ extern "C" int64_t ivx_spline_band_len(int64_t n_ladders, int64_t n_q) {
   return n_ladders * n_q * BAND_W;
 }
 
+extern "C" int64_t ivx_spline_band_frag_len(int64_t n_ladders) {
+  if (n_ladders < 0) return -1;
+  return n_ladders * MMA_OCT * MMA_KS * 32;
+}
+
+// int32 entries of band_oct: {first knot, steps} per (ladder, group of 8 points), then {largest slab extent, largest step count} per ladder
+extern "C" int64_t ivx_spline_band_oct_len(int64_t n_ladders) {
+  if (n_ladders < 0) return -1;
+  return n_ladders * (MMA_OCT * 2 + 2);
+}
+
 extern "C" int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
-                                     int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok, int16_t* band_perm, ivx_stream_t stream_) {
+                                     int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok, int16_t* band_perm,
+                                     double* band_frag, int32_t* band_oct, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_ladders >= 0 && n_ladders < 65536 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_band_build: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_band_build: extrap must be 0, 1 or 2");
@@ -386,6 +654,11 @@ extern "C" int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_of
     IVX_LAUNCH_CHECK("k_band_check");
     k_band_perm<<<(unsigned)n_ladders, 32, 0, stream>>>((int32_t)n_q, band_k0, band_perm);
     IVX_LAUNCH_CHECK("k_band_perm");
+    if (band_frag && band_oct) {
+      k_band_frag<<<(unsigned)n_ladders, 256, 0, stream>>>((int32_t)n_q, ladder_off, band_k0, band_w, ladder_ok, band_frag, band_oct,
+                                                          band_oct + n_ladders * MMA_OCT * 2);
+      IVX_LAUNCH_CHECK("k_band_frag");
+    }
   }
   return IVX_OK;
 }
@@ -395,7 +668,8 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
                                           const int64_t* ladder_off, int64_t max_knots, const double* x_ladder, const double* x_own,
                                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                           const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
-                                          const uint8_t* ladder_ok, const int16_t* band_perm, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
+                                          const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
+                                          int32_t slab_knots_hint, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_slices >= 0 && n_slices < ((int64_t)1 << 31) && n_ladders >= 0 && n_ladders < 65536 && max_slices_per_ladder >= 0,
               IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: bad sizes");
@@ -406,9 +680,35 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
                   band_w && ladder_ok && band_perm && yq && fb_list && fb_count,
               IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: null pointer");
   IVX_CUDA(cudaMemsetAsync(fb_count, 0, 4, stream));
+  IVX_REQUIRE((band_frag == nullptr) == (band_oct == nullptr) && slab_knots_hint >= 0, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: band_frag and band_oct go together");
   BandParams P;
   P.knot_off = knot_off; P.order = order; P.lad_slice_off = lad_slice_off; P.ladder_off = ladder_off; P.x_ladder = x_ladder; P.x_own = x_own;
   P.y = y; P.band_k0 = band_k0; P.band_w = band_w; P.ladder_ok = ladder_ok; P.perm = band_perm; P.yq = yq; P.fb_list = fb_list; P.fb_count = fb_count; P.n_q = (int32_t)n_q;
+  P.frag = band_frag; P.oct = band_oct; P.row = 0; P.vec_ok = ((n_q & 1) == 0 && ((uintptr_t)yq & 15u) == 0) ? 1 : 0;
+  if (band_frag) {
+    // tensor-path form for the ladders whose tables allow it (LADDER_OK_MMA); k_band_apply below skips those.  A row holds the
+    // knots one 64-point slab touches: the caller's hint (meta of ivx_spline_band_build) or the most the tables can ask for.
+    const int64_t ext = slab_knots_hint > 0 && slab_knots_hint <= MMA_SLAB_MAX ? slab_knots_hint : MMA_SLAB_MAX;
+    const int nit = ext <= 320 ? 10 : 16;
+    P.row = 32 * nit + 4;
+    IVX_CUDA(cudaMemsetAsync(fb_list, 0, (size_t)n_slices * sizeof(int32_t), stream));
+    const dim3 mgrid((unsigned)((n_q + 63) / 64), (unsigned)((max_slices_per_ladder + MMA_BATCH - 1) / MMA_BATCH), (unsigned)n_ladders);
+    if (mgrid.y > 0 && mgrid.y < 65536) {
+      const size_t smem = (size_t)((x_own ? 33 : 16) * P.row) * sizeof(double);
+#define IVX_MMA_LAUNCH(V, N)                                                                                                          \
+  {                                                                                                                                   \
+    static DeviceOnce once;                                                                                                           \
+    if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply_mma<V, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+    k_band_apply_mma<V, N><<<mgrid, 256, smem, stream>>>(P);                                                                          \
+  }
+      if (x_own) { if (nit == 10) IVX_MMA_LAUNCH(true, 10) else IVX_MMA_LAUNCH(true, 16) }
+      else { if (nit == 10) IVX_MMA_LAUNCH(false, 10) else IVX_MMA_LAUNCH(false, 16) }
+#undef IVX_MMA_LAUNCH
+      IVX_LAUNCH_CHECK("k_band_apply_mma");
+    } else {
+      P.frag = nullptr;                                // more batches than a grid dimension holds: the dot-product form takes everything
+    }
+  }
   // slices per CTA: as many as 48 (the weights are loaded once per CTA), but no fewer than ~3 CTAs per SM in the launch
   int64_t batch = (max_slices_per_ladder * n_ladders + 3 * (int64_t)sm_count() - 1) / (3 * (int64_t)sm_count());
   batch = batch < 4 ? 4 : (batch > BAND_BATCH ? BAND_BATCH : batch);

@@ -736,7 +736,7 @@ def test_implied_vol_two_kernel_form_equals_the_one_launch_form(dev):
     assert (it > 1).sum() > 100, "the tape must exercise the fallback"
 
 
-def _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify):
+def _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify, tensor_path=True):
     """Run ivx_spline_fit_eval_banded on slices (xs[i], ys[i]) presumed to sit on ladders[lad_of[i]]; returns (yq, fallback ids, ok)."""
     import torch
     from iv_interpolation_b200 import device as D
@@ -750,20 +750,23 @@ def _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify):
     lad_slice_off = np.r_[0, np.cumsum(counts)].astype(np.int64)
     max_knots = max(max(lens), max(len(y) for y in ys))
     lu = D.spline_ladder_factor(_t(ladder_off, dev), _t(lx, dev), max_knots=max_knots)
-    band = D.spline_band_build(_t(ladder_off, dev), _t(lx, dev), _t(xq, dev), extrap=extrap)
+    band = D.spline_band_build(_t(ladder_off, dev), _t(lx, dev), _t(xq, dev), extrap=extrap, tensor_path=tensor_path)
     fb = (torch.full((len(ys),), -1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
     yq = D.spline_fit_eval_banded(_t(off, dev), _t(ladder_off[:-1][lad_of], dev), _t(lad_of, dev), _t(order, dev), _t(lad_slice_off, dev),
                                   int(counts.max()), _t(ladder_off, dev), _t(lx, dev), lu, _t(np.concatenate(ys), dev), _t(xq, dev), band,
-                                  max_knots=max_knots, x_own=_t(np.concatenate(xs), dev) if verify else None, fb=fb)
+                                  max_knots=max_knots, x_own=_t(np.concatenate(xs), dev) if verify else None, fb=fb, tensor_path=tensor_path)
     flags = fb[0].cpu().numpy()
     assert set(flags.tolist()) <= {0, 1} and int(fb[1].item()) == int(flags.sum())      # every slice decided, the count agrees
     return yq.cpu().numpy().reshape(len(ys), -1), np.flatnonzero(flags == 1).tolist(), band.ok.cpu().numpy()
 
 
-@pytest.mark.parametrize("n_knots,n_q,extrap", [(2000, 512, 1), (2048, 512, 0), (333, 257, 2), (48, 100, 1), (1001, 512, 1)])
-def test_spline_banded_operator_vs_scipy(dev, n_knots, n_q, extrap):
-    """Slices on tabulated ladders through the banded operators (ivx_spline_band.cu): scipy to 1e-8, the exact scan kernel to
-    1e-10; slices with a missing knot or another length than their ladder are listed and solved by the exact kernel, and only those."""
+@pytest.mark.parametrize("tensor_path", [True, False])
+@pytest.mark.parametrize("n_knots,n_q,extrap", [(2000, 512, 1), (2048, 512, 0), (333, 257, 2), (48, 100, 1), (1001, 512, 1), (2000, 64, 1)])
+def test_spline_banded_operator_vs_scipy(dev, n_knots, n_q, extrap, tensor_path):
+    """Slices on tabulated ladders through the banded operators (ivx_spline_band.cu), as dot products and as the block-banded
+    matrix product on the fp64 tensor path: scipy to 1e-8, the exact scan kernel to 1e-10; slices with a missing knot or another
+    length than their ladder are listed and solved by the exact kernel, and only those.  (2000 knots on 64 points: 31 knots per
+    point, too wide for the fragment registers — the tensor-path call hands those ladders to the dot-product kernel.)"""
     from iv_interpolation_b200 import device as D
     rng = np.random.default_rng(n_knots + n_q)
     n_lad, per = 3, 21
@@ -780,8 +783,10 @@ def test_spline_banded_operator_vs_scipy(dev, n_knots, n_q, extrap):
         xs.append(x); ys.append(y)
     lo, hi = min(l[0] for l in ladders), max(l[-1] for l in ladders)
     xq = np.linspace(lo - 10, hi + 10, n_q)
-    got, fb, ok = _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify=False)
-    assert ok.all() and fb == [4, 7, 11]
+    got, fb, ok = _banded(dev, ladders, lad_of, xs, ys, xq, extrap, verify=False, tensor_path=tensor_path)
+    assert (ok & 1).all() and fb == [4, 7, 11]
+    if tensor_path:
+        assert ((ok & 2) != 0).all() == (n_q != 64), ok        # only the 31-knots-per-point case is too wide for the tensor path
     X, Y = np.concatenate(xs), np.concatenate(ys)
     off = np.r_[0, np.cumsum([len(y) for y in ys])].astype(np.int64)
     gen = D.spline_fit_eval(_t(off, dev), _t(X, dev), _t(Y, dev), _t(xq, dev), max_knots=n_knots, extrap=extrap).cpu().numpy().reshape(len(ys), -1)
@@ -794,7 +799,8 @@ def test_spline_banded_operator_vs_scipy(dev, n_knots, n_q, extrap):
         assert np.abs(got[s][fin] - gen[s][fin]).max() <= 1e-10 * scale, s
 
 
-def test_spline_banded_verify_and_unusable_ladders(dev):
+@pytest.mark.parametrize("tensor_path", [True, False])
+def test_spline_banded_verify_and_unusable_ladders(dev, tensor_path):
     """x_own given: a slice is taken by the band only if its abscissae equal its ladder's bit for bit (one knot off by an ulp ->
     exact solve with its OWN abscissae).  Ladders the band cannot serve — fewer than 48 knots, or spacing so uneven that 22 rows
     do not reach 2e-12 (found by the probe check) — send all their slices to the exact solve; results are right either way."""
@@ -812,8 +818,8 @@ def test_spline_banded_verify_and_unusable_ladders(dev):
             x[100] = np.nextafter(x[100], np.inf)
         xs.append(x); ys.append(np.sin(x / 40.0) + 0.01 * rng.standard_normal(len(x)))
     xq = np.linspace(90.0, good[-1] + 5, 300)
-    got, fb, ok = _banded(dev, ladders, lad_of, xs, ys, xq, 1, verify=True)
-    assert ok[0] == 1 and ok[1] == 0
+    got, fb, ok = _banded(dev, ladders, lad_of, xs, ys, xq, 1, verify=True, tensor_path=tensor_path)
+    assert (ok[0] & 1) == 1 and ok[1] == 0
     expected_fb = sorted([s for s, l in enumerate(lad_of) if l == 1 or (l == 2 and not ok[2])] + [3])
     assert fb == expected_fb, (fb, expected_fb, ok)
     for s in range(len(ys)):
