@@ -437,25 +437,29 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8u(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-// grid: x = 64-point slab, y = batch of MMA_BATCH slices, z = ladder; 256 threads; a staged row holds 32 NIT knots (+4 of padding:
-// rows 4 mod 16 doubles apart keep the fragment loads conflict-free).  Warp w stages row w of every tile (one slice's slab of knots:
+// grid: x = 64-point slab, y = batch of MMA_BATCH slices, z = ladder; 256 threads; a staged row holds 32 NIT knots (+36 of padding:
+// rows 4 mod 16 doubles apart keep the fragment loads conflict-free, and the multiply runs 20 or 24 steps whatever the group
+// needs — the fragments past its last step are zero, and so is the row past its last knot).  NST stages of cp.async.  Warp w stages row w of every tile (one slice's slab of knots:
 // cp.async, 16 bytes at a time where the slice's address allows), checks that row — every y finite, every x equal to the ladder's
 // bit for bit, both as integer operations on the words — votes inside the warp, and multiplies the 8-point group 8 slab + w
 // against all 8 rows.  Knots that no slab touches (the grid may be narrower than the ladder) are dealt evenly to the slabs and
 // checked straight from global memory.
-template <bool VERIFY, int NIT>
+template <bool VERIFY, int NIT, int NST>
 __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
-  constexpr int ROW = 32 * NIT + 4;
+  constexpr int ROW = 32 * NIT + 36;   // 20 steps from a group that starts 48 knots before the end of the slab read 31 knots past it
   extern __shared__ __align__(16) double sm[];
-  double* ybuf = sm;                                         // [2][8][ROW]
-  double* xbuf = ybuf + 2 * 8 * ROW;                         // [2][8][ROW]   (VERIFY)
-  double* ladx = xbuf + (VERIFY ? 2 * 8 * ROW : 0);          // [ROW]         (VERIFY)
+  double* ybuf = sm;                                         // [NST][8][ROW]
+  double* xbuf = ybuf + NST * 8 * ROW;                       // [NST][8][ROW]   (VERIFY)
+  double* ladx = xbuf + (VERIFY ? NST * 8 * ROW : 0);        // [ROW]           (VERIFY)
   __shared__ int s_kb[8], s_ke[8], s_kfirst, s_klast;
-  __shared__ int32_t s_sid[2][8];                            // slice of every row, -1 = no store (no such row, or flagged)
+  __shared__ int32_t s_sid[NST][8];                          // slice of every row, -1 = no store (no such row, or flagged)
   __shared__ int64_t s_base[MMA_BATCH];                      // first knot of every slice of the batch, -1 = another length than the ladder
   __shared__ int32_t s_id[MMA_BATCH];
   const int l = blockIdx.z, slab = blockIdx.x;
@@ -517,47 +521,71 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
   const bool nan0 = st0 && P.band_k0[(int64_t)l * n_q + q0] < 0, nan1 = st1 && P.band_k0[(int64_t)l * n_q + q0 + 1] < 0;
   const bool vec_out = P.vec_ok && st1;                       // 16-byte stores (n_q even, yq aligned)
   // zero both stages once (cp.async never writes past nvalid), ladder abscissae of the slab
-  for (int i = threadIdx.x; i < (VERIFY ? 4 : 2) * 8 * ROW; i += 256) ybuf[i] = 0.0;
+  for (int i = threadIdx.x; i < (VERIFY ? 2 : 1) * NST * 8 * ROW; i += 256) ybuf[i] = 0.0;
   if (VERIFY)
     for (int k = threadIdx.x; k < ROW; k += 256) ladx[k] = k < nvalid ? __ldg(P.x_ladder + P.ladder_off[l] + KB + k) : 0.0;
   __syncthreads();
   const int ntiles = (ns + 7) >> 3;
+  // how many of this lane's 16-byte chunks (knots 2(lane + 32 r), +1) lie wholly inside the row, and whether one 8-byte knot follows
+  const int full16 = nvalid / 2 > lane ? (nvalid / 2 - lane + 31) / 32 : 0;
+  const bool tail8 = (nvalid & 1) && ((nvalid / 2) & 31) == lane;
+  const int tail_k = nvalid - 1;
+  const int full8 = nvalid > lane ? (nvalid - lane + 31) / 32 : 0;
   auto issue = [&](int tile, int buf) {                      // row w of the tile
     const int idx = tile * 8 + w;
     const int64_t ko = idx < ns ? s_base[idx] : (int64_t)-1;
     if (ko >= 0) {
       const double* __restrict__ ysrc = P.y + ko + KB;
-      double* yb = ybuf + (buf * 8 + w) * ROW;
       const double* __restrict__ xsrc = VERIFY ? P.x_own + ko + KB : nullptr;
-      double* xb = xbuf + (buf * 8 + w) * ROW;
+      const uint32_t yb = smem_u32(ybuf + (buf * 8 + w) * ROW), xb = smem_u32(xbuf + (buf * 8 + w) * ROW);
       const bool vec = (((uintptr_t)ysrc | (VERIFY ? (uintptr_t)xsrc : 0)) & 15u) == 0;      // warp-uniform
       if (vec) {
 #pragma unroll
-        for (int r = 0; r < NIT / 2; ++r) {
-          const int k = 2 * (lane + 32 * r);
-          if (k + 1 < nvalid) { cp_async16(yb + k, ysrc + k); if (VERIFY) cp_async16(xb + k, xsrc + k); }
-          else if (k < nvalid) { cp_async8(yb + k, ysrc + k); if (VERIFY) cp_async8(xb + k, xsrc + k); }
-        }
+        for (int r = 0; r < NIT / 2; ++r)
+          if (r < full16) {
+            const int k = 2 * (lane + 32 * r);
+            cp_async16(yb + 8 * k, ysrc + k);
+            if (VERIFY) cp_async16(xb + 8 * k, xsrc + k);
+          }
+        if (tail8) { cp_async8u(yb + 8 * tail_k, ysrc + tail_k); if (VERIFY) cp_async8u(xb + 8 * tail_k, xsrc + tail_k); }
       } else {
 #pragma unroll
-        for (int r = 0; r < NIT; ++r) {
-          const int k = lane + 32 * r;
-          if (k < nvalid) { cp_async8(yb + k, ysrc + k); if (VERIFY) cp_async8(xb + k, xsrc + k); }
-        }
+        for (int r = 0; r < NIT; ++r)
+          if (r < full8) {
+            const int k = lane + 32 * r;
+            cp_async8u(yb + 8 * k, ysrc + k);
+            if (VERIFY) cp_async8u(xb + 8 * k, xsrc + k);
+          }
       }
     }
     cp_async_commit();
   };
-  issue(0, 0);
+#pragma unroll
+  for (int t0 = 0; t0 < NST - 1; ++t0) issue(t0, t0);        // (a tile past the end commits an empty group)
+  // the lane's first knot outside every slab, if it has one: loaded one tile ahead so that the load travels under the multiply
+  const bool has_out = out_lo + lane < out_hi;
+  const int out_k = has_out ? (out_lo + lane < kfirst ? out_lo + lane : klast + (out_lo + lane - kfirst)) : 0;
+  const double out_lx = (VERIFY && has_out) ? __ldg(P.x_ladder + P.ladder_off[l] + out_k) : 0.0;
+  double ey = 0.0, ex = 0.0;
+  auto load_out = [&](int tile) {
+    const int idx = tile * 8 + w;
+    const int64_t ko = idx < ns ? s_base[idx] : (int64_t)-1;
+    if (has_out && ko >= 0) { ey = __ldg(P.y + ko + out_k); if (VERIFY) ex = __ldg(P.x_own + ko + out_k); }
+  };
+  load_out(0);
+  int buf = 0;
   for (int tile = 0; tile < ntiles; ++tile) {
-    const int buf = tile & 1;
     {
       const int idx = tile * 8 + w;
       const int64_t ko = idx < ns ? s_base[idx] : (int64_t)-1;
-      // knots outside every slab: loads first, they travel while the staged row is checked
+      // knots outside every slab: the lane's first one was loaded a tile ago (ey, ex), any further ones are loaded here
       uint32_t bad = 0;
       if (ko >= 0) {
-        for (int i = out_lo + lane; i < out_hi; i += 32) {
+        if (has_out) {
+          bad |= ((uint32_t)__double2hiint(ey) & 0x7ff00000u) == 0x7ff00000u;
+          if (VERIFY) bad |= (uint32_t)((__double2hiint(ex) ^ __double2hiint(out_lx)) | (__double2loint(ex) ^ __double2loint(out_lx)));
+        }
+        for (int i = out_lo + lane + 32; i < out_hi; i += 32) {
           const int k = i < kfirst ? i : klast + (i - kfirst);
           const double yv = __ldg(P.y + ko + k);
           bad |= ((uint32_t)__double2hiint(yv) & 0x7ff00000u) == 0x7ff00000u;
@@ -567,7 +595,7 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
           }
         }
       }
-      cp_async_wait<0>();                                    // the lanes' parts of row w have landed ...
+      cp_async_wait<NST - 2>();                              // the lanes' parts of row w have landed ...
       __syncwarp();                                          // ... and are visible to the whole warp
       if (ko >= 0) {
         const double2* yb = reinterpret_cast<const double2*>(ybuf + (buf * 8 + w) * ROW);
@@ -594,15 +622,26 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
         s_sid[buf][w] = ok ? sl : -1;
       }
     }
-    __syncthreads();                                         // rows and verdicts of this tile visible; the other stage is free
-    if (tile + 1 < ntiles) issue(tile + 1, buf ^ 1); else cp_async_commit();
-    // 8 slices x 8 points: two accumulator chains
+    __syncthreads();                                         // rows and verdicts of this tile visible; the stage of tile - 1 is free
+    {
+      const int nb = buf == 0 ? NST - 1 : buf - 1;           // (tile + NST - 1) mod NST
+      issue(tile + NST - 1, nb);
+      load_out(tile + 1);
+    }
+    // 8 slices x 8 points: two accumulator chains, 20 or 24 steps (zero fragments and zero knots past the group's own)
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    const double* arow = ybuf + (buf * 8 + g) * ROW + (kb - KB) + tig;
+    const double* arow = ybuf + (buf * 8 + g) * ROW + (nks > 0 ? kb - KB : 0) + tig;   // (a group without a point multiplies zeros)
 #pragma unroll
-    for (int ks = 0; ks < MMA_KS; ks += 2) {
-      if (ks < nks) dmma_884(c0, c1, arow[4 * ks], wreg[ks]);
-      if (ks + 1 < nks) dmma_884(d0, d1, arow[4 * ks + 4], wreg[ks + 1]);
+    for (int ks = 0; ks < 20; ks += 2) {
+      dmma_884(c0, c1, arow[4 * ks], wreg[ks]);
+      dmma_884(d0, d1, arow[4 * ks + 4], wreg[ks + 1]);
+    }
+    if (nks > 20) {
+#pragma unroll
+      for (int ks = 20; ks < MMA_KS; ks += 2) {
+        dmma_884(c0, c1, arow[4 * ks], wreg[ks]);
+        dmma_884(d0, d1, arow[4 * ks + 4], wreg[ks + 1]);
+      }
     }
     const int32_t sl = s_sid[buf][g];
     if (sl >= 0) {
@@ -613,6 +652,7 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
       if (vec_out) __stcs(reinterpret_cast<double2*>(dst), make_double2(r0, r1));
       else { if (st0) st_stream(dst, r0); if (st1) st_stream(dst + 1, r1); }
     }
+    buf = buf + 1 == NST ? 0 : buf + 1;
   }
   cp_async_wait<0>();
 }
@@ -690,19 +730,20 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
     // knots one 64-point slab touches: the caller's hint (meta of ivx_spline_band_build) or the most the tables can ask for.
     const int64_t ext = slab_knots_hint > 0 && slab_knots_hint <= MMA_SLAB_MAX ? slab_knots_hint : MMA_SLAB_MAX;
     const int nit = ext <= 320 ? 10 : 16;
-    P.row = 32 * nit + 4;
+    P.row = 32 * nit + 36;
     IVX_CUDA(cudaMemsetAsync(fb_list, 0, (size_t)n_slices * sizeof(int32_t), stream));
     const dim3 mgrid((unsigned)((n_q + 63) / 64), (unsigned)((max_slices_per_ladder + MMA_BATCH - 1) / MMA_BATCH), (unsigned)n_ladders);
     if (mgrid.y > 0 && mgrid.y < 65536) {
-      const size_t smem = (size_t)((x_own ? 33 : 16) * P.row) * sizeof(double);
-#define IVX_MMA_LAUNCH(V, N)                                                                                                          \
+      // stages: as many as let two CTAs share an SM
+#define IVX_MMA_LAUNCH(V, N, S)                                                                                                       \
   {                                                                                                                                   \
+    const size_t smem = (size_t)(((V) ? 2 * (S) * 8 + 1 : (S) * 8) * P.row) * sizeof(double);                                         \
     static DeviceOnce once;                                                                                                           \
-    if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply_mma<V, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
-    k_band_apply_mma<V, N><<<mgrid, 256, smem, stream>>>(P);                                                                          \
+    if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply_mma<V, N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+    k_band_apply_mma<V, N, S><<<mgrid, 256, smem, stream>>>(P);                                                                       \
   }
-      if (x_own) { if (nit == 10) IVX_MMA_LAUNCH(true, 10) else IVX_MMA_LAUNCH(true, 16) }
-      else { if (nit == 10) IVX_MMA_LAUNCH(false, 10) else IVX_MMA_LAUNCH(false, 16) }
+      if (x_own) { if (nit == 10) IVX_MMA_LAUNCH(true, 10, 2) else IVX_MMA_LAUNCH(true, 16, 2) }
+      else { if (nit == 10) IVX_MMA_LAUNCH(false, 10, 4) else IVX_MMA_LAUNCH(false, 16, 3) }
 #undef IVX_MMA_LAUNCH
       IVX_LAUNCH_CHECK("k_band_apply_mma");
     } else {
