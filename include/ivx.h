@@ -162,6 +162,17 @@ int64_t ivx_bs_implied_vol_workspace_bytes(int64_t n);
 int ivx_bs_implied_vol(int64_t n, const double* price, const double* S, const double* K,
                        const double* T, const double* r, const uint8_t* is_call, double* sigma,
                        int32_t* iters, void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+/* The same solve for quotes that form slices on PRESUMED ladders (the per-quote layout of the surface pipeline): quote i = t * period + j,
+ * slice = i / n_strike, and the strike of quote (t, j) is presumed to equal x_ladder[j] (period doubles: typically the first stamp's
+ * strikes).  The solver has every strike in a register anyway, so it compares it with the ladder's bit for bit on the way: a slice with
+ * a differing strike gets slice_flags[slice] = 1 (the array, n_t * period / n_strike int32, and *flag_count are zeroed first;
+ * *flag_count = number of flagged slices).  ivx_spline_fit_eval_banded(..., x_verified = 1) then takes the flags as the verdict and
+ * does not read 8 bytes per knot again.  Two-kernel form only (workspace required), no iteration counts. */
+int64_t ivx_bs_implied_vol_ladder_workspace_bytes(int64_t n_t, int64_t period);
+int ivx_bs_implied_vol_ladder(int64_t n_t, int64_t period, int64_t n_strike, const double* price, const double* S, const double* K,
+                              const double* T, const double* r, const uint8_t* is_call, double* sigma, const double* x_ladder,
+                              int32_t* slice_flags, uint32_t* flag_count, void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+
 /* Chain layout (one underlying, one day): quote (t, e, k) sits at price[(t*n_exp + e)*n_strike + k]; the
  * underlying S_t[n_t] and rate r_t[n_t] are per stamp, the strike K_ek[n_exp*n_strike] per contract, the time to
  * expiry T_te[n_t*n_exp] per (stamp, expiry), call/put per contract or per quote: 8-9 B/quote in, 8 B out
@@ -259,7 +270,11 @@ int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_off, const 
                                const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
                                const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
-                               int32_t slab_knots_hint, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream);
+                               int32_t slab_knots_hint,
+                               int32_t x_verified /* 1: fb_list / fb_count already hold the verdict of an abscissa comparison done elsewhere
+                                                     (ivx_bs_implied_vol_ladder): kept and added to; x_own is then read only by the
+                                                     exact solve of the flagged slices */,
+                               double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream);
 int ivx_spline_strided(int64_t n_systems, int32_t n_knots, const double* x /*n_knots*/,
                        const double* y /*[n_knots][n_systems]*/, int32_t n_q, const double* xq,
                        int32_t extrap, double* yq /*[n_q][n_systems]*/, ivx_stream_t stream);

@@ -606,6 +606,64 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol_retry(uint32_t n, const 
   }
 }
 
+// ---- quotes that form slices on presumed ladders (the per-quote layout of the surface pipeline) -------------------------------
+// Quote i = t * period + j; slice = i / n_strike; the strike of quote (t, j) is PRESUMED to equal x_ladder[j] (the first stamp's
+// strikes).  The strike is in a register here anyway, so it is compared with the ladder's bit for bit on the way: a slice with a
+// strike that differs is flagged (slice_flags[slice] = 1, *flag_count counts slices) and the strike spline, told so
+// (x_verified), does not read 8 bytes per knot again to find out.  grid: x over the quotes of one stamp, y over stamps.
+__global__ void __launch_bounds__(256, 6) k_bs_implied_vol_ladder(uint32_t period, uint32_t n_strike, const double* __restrict__ price,
+                                                               const double* __restrict__ S, const double* __restrict__ K,
+                                                               const double* __restrict__ T, const double* __restrict__ r,
+                                                               const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
+                                                               const double* __restrict__ x_ladder, int32_t* __restrict__ slice_flags,
+                                                               uint32_t* __restrict__ flag_count, uint32_t* __restrict__ list,
+                                                               uint32_t* __restrict__ counter) {
+  const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+  const bool inr = j < period;
+  const uint32_t jj = inr ? j : 0u;
+  const uint32_t i = blockIdx.y * period + jj;       // < 2^31: the wrapper chunks the stamps
+  const double p = ld_stream(price + i), s_ = ld_stream(S + i), k_ = ld_stream(K + i);
+  const double t_ = ld_stream(T + i), r_ = ld_stream(r + i);
+  const bool call = is_call[i] != 0;
+  const double lad = __ldcg(x_ladder + jj);         // L2 only: the 480 KB of ladders must not push the guess table out of L1
+  const double kd = k_ * exp_neg_small(r_ * t_);
+  const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+  double out;
+  int it;
+  const bool deferred = solve_quote<false, true>(ok, p, s_, kd, t_, call, 0.0, out, it);
+  if (inr) {
+    st_stream(sigma + i, out);
+    if (((__double2hiint(k_) ^ __double2hiint(lad)) | (__double2loint(k_) ^ __double2loint(lad))) != 0) {   // rare
+      const uint32_t slice = i / n_strike;
+      if (atomicExch(slice_flags + slice, 1) == 0) atomicAdd(flag_count, 1u);
+    }
+  }
+  record_deferred(deferred && inr, (blockIdx.y * gridDim.x + blockIdx.x) * 8u + (threadIdx.x >> 5), list, counter);
+}
+
+__global__ void __launch_bounds__(256) k_bs_implied_vol_ladder_retry(uint32_t gx, uint32_t period, const double* __restrict__ price,
+                                                                     const double* __restrict__ S, const double* __restrict__ K,
+                                                                     const double* __restrict__ T, const double* __restrict__ r,
+                                                                     const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
+                                                                     const uint32_t* __restrict__ list, const uint32_t* __restrict__ counter) {
+  const uint32_t count = *counter;
+  for (uint32_t e = blockIdx.x * 8u + (threadIdx.x >> 5); e < count; e += gridDim.x * 8u) {
+    const uint32_t w = list[e];
+    const uint32_t blk = w >> 3;                                   // (y * gx + x)
+    const uint32_t j = (blk % gx) * 256u + (w & 7u) * 32u + (threadIdx.x & 31u);
+    const bool inr = j < period;
+    const uint32_t i = (blk / gx) * period + (inr ? j : 0u);
+    const double p = price[i], s_ = S[i], k_ = K[i], t_ = T[i], r_ = r[i];
+    const bool call = is_call[i] != 0;
+    const double kd = k_ * exp_neg_small(r_ * t_);
+    const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+    double out;
+    int it;
+    solve_quote<false, false>(ok, p, s_, kd, t_, call, 0.0, out, it);
+    if (inr) sigma[i] = out;
+  }
+}
+
 // ---- chain layout: quote (t, e, k) = price[(t n_exp + e) n_strike + k]; S per stamp, K per contract, T per (stamp, expiry)
 // terms[0 .. n_t)            ln S[t]
 // terms[n_t .. +n_ek)        ln K[e][k]
@@ -816,6 +874,48 @@ extern "C" int ivx_bs_implied_vol(int64_t n, const double* price, const double* 
       IVX_LAUNCH_CHECK("k_bs_implied_vol");
     }
 #undef IVX_IV_ARGS
+  }
+  return IVX_OK;
+}
+
+// stamps per launch of the ladder form: a 32-bit quote index and a 16-bit grid dimension
+static int64_t ladder_chunk_stamps(int64_t period) {
+  int64_t c = (((int64_t)1 << 31) - 1) / period;
+  return c > 65535 ? 65535 : c;
+}
+
+extern "C" int64_t ivx_bs_implied_vol_ladder_workspace_bytes(int64_t n_t, int64_t period) {
+  if (n_t < 0 || period <= 0 || period >= ((int64_t)1 << 31)) return -1;
+  const int64_t gx = (period + 255) / 256, ch = ladder_chunk_stamps(period), gy = n_t < ch ? n_t : ch;
+  return 256 + 4 * (gx * gy * 8 + 8);
+}
+
+extern "C" int ivx_bs_implied_vol_ladder(int64_t n_t, int64_t period, int64_t n_strike, const double* price, const double* S, const double* K,
+                                         const double* T, const double* r, const uint8_t* is_call, double* sigma, const double* x_ladder,
+                                         int32_t* slice_flags, uint32_t* flag_count, void* workspace, int64_t workspace_bytes, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_t >= 0 && period > 0 && period < ((int64_t)1 << 31) && n_strike > 0 && period % n_strike == 0, IVX_ERR_INVALID_ARG,
+              "ivx_bs_implied_vol_ladder: need n_t >= 0 and a period that is a positive multiple of n_strike");
+  if (n_t == 0) return IVX_OK;
+  IVX_REQUIRE(price && S && K && T && r && is_call && sigma && x_ladder && slice_flags && flag_count && workspace, IVX_ERR_INVALID_ARG,
+              "ivx_bs_implied_vol_ladder: null pointer");
+  IVX_REQUIRE(workspace_bytes >= ivx_bs_implied_vol_ladder_workspace_bytes(n_t, period), IVX_ERR_INVALID_ARG, "ivx_bs_implied_vol_ladder: workspace too small");
+  uint32_t* counter = (uint32_t*)workspace;
+  uint32_t* list = (uint32_t*)((char*)workspace + 256);
+  IVX_CUDA(cudaMemsetAsync(slice_flags, 0, (size_t)(n_t * (period / n_strike)) * sizeof(int32_t), stream));
+  IVX_CUDA(cudaMemsetAsync(flag_count, 0, 4, stream));
+  const unsigned gx = (unsigned)((period + 255) / 256);
+  const int64_t ch = ladder_chunk_stamps(period);
+  for (int64_t t0 = 0; t0 < n_t; t0 += ch) {
+    const unsigned gy = (unsigned)(n_t - t0 < ch ? n_t - t0 : ch);
+    const int64_t o = t0 * period;
+    IVX_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
+    k_bs_implied_vol_ladder<<<dim3(gx, gy), 256, 0, stream>>>((uint32_t)period, (uint32_t)n_strike, price + o, S + o, K + o, T + o, r + o, is_call + o,
+                                                             sigma + o, x_ladder, slice_flags + t0 * (period / n_strike), flag_count, list, counter);
+    IVX_LAUNCH_CHECK("k_bs_implied_vol_ladder");
+    k_bs_implied_vol_ladder_retry<<<(unsigned)(sm_count() * 2), 256, 0, stream>>>(gx, (uint32_t)period, price + o, S + o, K + o, T + o, r + o, is_call + o,
+                                                                                 sigma + o, list, counter);
+    IVX_LAUNCH_CHECK("k_bs_implied_vol_ladder_retry");
   }
   return IVX_OK;
 }

@@ -302,6 +302,7 @@ struct BandParams {
   const int32_t* oct;            // [n_ladders][64][2] first knot and step count of every 8-point group
   int32_t row;                   // doubles per staged slice row (slab extent + padding), = 4 mod 16
   int32_t vec_ok;                // n_q even and yq 16-byte aligned
+  int32_t preflag;               // fb_list already flags slices that must take the exact solve (x verified by the caller): honoured, not cleared
 };
 
 template <bool VERIFY>
@@ -320,8 +321,8 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
   const int t = threadIdx.x;
   if (P.frag && (P.ladder_ok[l] & LADDER_OK_MMA)) return;    // k_band_apply_mma takes this ladder
   if (!P.ladder_ok[l]) {                                     // no usable band for this ladder: everything to the exact solve
-    for (int i = t; i < ns; i += BAND_THREADS) P.fb_list[ord[i]] = 1;
-    if (t == 0) atomicAdd(P.fb_count, (uint32_t)ns);
+    for (int i = t; i < ns; i += BAND_THREADS)
+      if (atomicExch(P.fb_list + ord[i], 1) == 0 || !(P.preflag || P.frag)) atomicAdd(P.fb_count, 1u);
     return;
   }
   const int n = (int)(P.ladder_off[l + 1] - P.ladder_off[l]);      // BAND_W <= n <= BAND_MAXK (k_band_build)
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
     const int32_t s = ord[t];
     const int64_t ko = P.knot_off[s];
     sid[t] = s;
-    sbase[t] = (P.knot_off[s + 1] - ko) == (int64_t)n ? ko : (int64_t)-1;
+    sbase[t] = ((P.knot_off[s + 1] - ko) == (int64_t)n && !(P.preflag && P.fb_list[s] != 0)) ? ko : (int64_t)-1;
   }
   __syncthreads();
   // knots this thread moves: k = t + r * 512, r = 0..3
@@ -419,8 +420,8 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
       if (has_q) obuf[(i & 1) * (BAND_MAXQ + 16) + oq] = nan_q ? qnan() : (a0 + a1) + (a2 + a3);
     }
     if (t == 0) {                                            // a missing knot, off the ladder, another length: flagged for the exact solve
-      P.fb_list[sid[i]] = all_ok ? 0 : 1;
-      if (!all_ok) atomicAdd(P.fb_count, 1u);
+      if (P.preflag || P.frag) { if (!all_ok && atomicExch(P.fb_list + sid[i], 1) == 0) atomicAdd(P.fb_count, 1u); }   // the list was zeroed or pre-set
+      else { P.fb_list[sid[i]] = all_ok ? 0 : 1; if (!all_ok) atomicAdd(P.fb_count, 1u); }
     }
     prev_ok = all_ok;
     buf_next2 = buf;                                         // slice i+3 reuses slice i's buffer
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
     const int32_t sl = ord[threadIdx.x];
     const int64_t ko = P.knot_off[sl];
     s_id[threadIdx.x] = sl;
-    s_base[threadIdx.x] = (P.knot_off[sl + 1] - ko) == (int64_t)n ? ko : (int64_t)-1;
+    s_base[threadIdx.x] = ((P.knot_off[sl + 1] - ko) == (int64_t)n && !(P.preflag && P.fb_list[sl] != 0)) ? ko : (int64_t)-1;
   }
   __syncthreads();
   int KB = INT32_MAX, KE = 0;
@@ -709,7 +710,7 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
                                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                           const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
                                           const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
-                                          int32_t slab_knots_hint, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
+                                          int32_t slab_knots_hint, int32_t x_verified, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_slices >= 0 && n_slices < ((int64_t)1 << 31) && n_ladders >= 0 && n_ladders < 65536 && max_slices_per_ladder >= 0,
               IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: bad sizes");
@@ -719,10 +720,14 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
   IVX_REQUIRE(knot_off && x_off && slice_ladder && order && lad_slice_off && ladder_off && x_ladder && lu_cp && lu_inv && lu_ih && y && xq && band_k0 &&
                   band_w && ladder_ok && band_perm && yq && fb_list && fb_count,
               IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: null pointer");
-  IVX_CUDA(cudaMemsetAsync(fb_count, 0, 4, stream));
+  // x_verified: the caller (ivx_bs_implied_vol_ladder) compared every slice's abscissae with its ladder's already and left the
+  // verdicts in fb_list / fb_count — kept, added to, and x_own is read by the exact solve of the flagged slices only
+  if (!x_verified) IVX_CUDA(cudaMemsetAsync(fb_count, 0, 4, stream));
+  const double* x_check = x_verified ? nullptr : x_own;
   IVX_REQUIRE((band_frag == nullptr) == (band_oct == nullptr) && slab_knots_hint >= 0, IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: band_frag and band_oct go together");
   BandParams P;
-  P.knot_off = knot_off; P.order = order; P.lad_slice_off = lad_slice_off; P.ladder_off = ladder_off; P.x_ladder = x_ladder; P.x_own = x_own;
+  P.knot_off = knot_off; P.order = order; P.lad_slice_off = lad_slice_off; P.ladder_off = ladder_off; P.x_ladder = x_ladder; P.x_own = x_check;
+  P.preflag = x_verified ? 1 : 0;
   P.y = y; P.band_k0 = band_k0; P.band_w = band_w; P.ladder_ok = ladder_ok; P.perm = band_perm; P.yq = yq; P.fb_list = fb_list; P.fb_count = fb_count; P.n_q = (int32_t)n_q;
   P.frag = band_frag; P.oct = band_oct; P.row = 0; P.vec_ok = ((n_q & 1) == 0 && ((uintptr_t)yq & 15u) == 0) ? 1 : 0;
   if (band_frag) {
@@ -731,7 +736,7 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
     const int64_t ext = slab_knots_hint > 0 && slab_knots_hint <= MMA_SLAB_MAX ? slab_knots_hint : MMA_SLAB_MAX;
     const int nit = ext <= 320 ? 10 : 16;
     P.row = 32 * nit + 36;
-    IVX_CUDA(cudaMemsetAsync(fb_list, 0, (size_t)n_slices * sizeof(int32_t), stream));
+    if (!x_verified) IVX_CUDA(cudaMemsetAsync(fb_list, 0, (size_t)n_slices * sizeof(int32_t), stream));
     const dim3 mgrid((unsigned)((n_q + 63) / 64), (unsigned)((max_slices_per_ladder + MMA_BATCH - 1) / MMA_BATCH), (unsigned)n_ladders);
     if (mgrid.y > 0 && mgrid.y < 65536) {
       // stages: as many as let two CTAs share an SM
@@ -742,7 +747,7 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
     if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply_mma<V, N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
     k_band_apply_mma<V, N, S><<<mgrid, 256, smem, stream>>>(P);                                                                       \
   }
-      if (x_own) { if (nit == 10) IVX_MMA_LAUNCH(true, 10, 2) else IVX_MMA_LAUNCH(true, 16, 2) }
+      if (x_check) { if (nit == 10) IVX_MMA_LAUNCH(true, 10, 2) else IVX_MMA_LAUNCH(true, 16, 2) }
       else { if (nit == 10) IVX_MMA_LAUNCH(false, 10, 4) else IVX_MMA_LAUNCH(false, 16, 3) }
 #undef IVX_MMA_LAUNCH
       IVX_LAUNCH_CHECK("k_band_apply_mma");
@@ -756,7 +761,7 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
   P.batch = (int32_t)batch;
   const dim3 grid((unsigned)((max_slices_per_ladder + batch - 1) / batch), (unsigned)n_ladders);
   if (grid.x > 0) {
-    if (x_own) {
+    if (x_check) {
       const size_t smem = (size_t)(2 * BAND_NBUF * BAND_MAXK + 2 * (BAND_MAXQ + 16) + BAND_MAXK) * sizeof(double);
       static DeviceOnce once;
       if (once_per_device(once)) IVX_CUDA(cudaFuncSetAttribute(k_band_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -20,7 +20,7 @@ _LAUNCHES = 0     # kernels of ours enqueued since the last reset (bench.py repo
 # kernels each entry point enqueues (memsets are not kernels of ours and are not counted)
 _KERNELS_PER_CALL = {
     "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
-    "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
+    "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_implied_vol_ladder": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 3, "spline_ladder_factor": 1,
     "spline_band_build": 4, "spline_fit_eval_banded": 2, "spline_fit_eval_banded_mma": 3, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
@@ -333,6 +333,30 @@ def bs_implied_vol(price, S, K, T, r, is_call, *, want_iters: bool = False, out:
     return (sigma, iters) if want_iters else sigma
 
 
+def bs_implied_vol_ladder(price, S, K, T, r, is_call, *, n_t: int, period: int, n_strike: int, x_ladder: torch.Tensor,
+                          flags: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
+                          workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``bs_implied_vol`` for quotes that form slices of ``n_strike`` knots on presumed ladders (quote t * period + j presumed to have
+    the strike ``x_ladder[j]``): the strikes are compared with the ladder's on the way and ``flags`` = (int32[n_t * period / n_strike],
+    int32[1]) receive the slices that differ and their number."""
+    n = price.numel()
+    if n != n_t * period:
+        raise _lib.IvxError("bs_implied_vol_ladder: price must hold n_t * period quotes")
+    for t_, nm in ((price, "price"), (S, "S"), (K, "K"), (T, "T"), (r, "r"), (x_ladder, "x_ladder")):
+        _req(t_, torch.float64, nm)
+    _req(is_call, torch.uint8, "is_call")
+    _req(flags[0], torch.int32, "flags"); _req(flags[1], torch.int32, "flag count")
+    if x_ladder.numel() < period or flags[0].numel() < n_t * (period // n_strike):
+        raise _lib.IvxError("bs_implied_vol_ladder: ladder or flag array too small")
+    sigma = out if out is not None else _empty(n, torch.float64, price)
+    wsb = lib().ivx_bs_implied_vol_ladder_workspace_bytes(n_t, period)
+    ws = workspace if workspace is not None and workspace.numel() >= wsb else torch.empty(max(1, wsb), dtype=torch.uint8, device=price.device)
+    check(lib().ivx_bs_implied_vol_ladder(n_t, period, n_strike, _ptr(price), _ptr(S), _ptr(K), _ptr(T), _ptr(r), _ptr(is_call), _ptr(sigma),
+                                          _ptr(x_ladder), _ptr(flags[0]), _ptr(flags[1]), _ptr(ws), ws.numel(), _stream()), "ivx_bs_implied_vol_ladder")
+    _count("bs_implied_vol_ladder")
+    return sigma
+
+
 def bs_implied_vol_chain(price, is_call, S_t, K_ek, T_te, r_t, *, n_t: int, n_exp: int, n_strike: int,
                          out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
                          want_iters: bool = False):
@@ -496,11 +520,14 @@ def spline_fit_eval_banded(knot_off: torch.Tensor, x_off: torch.Tensor, slice_la
                            lad_slice_off: torch.Tensor, max_slices_per_ladder: int, ladder_off: torch.Tensor, x_ladder: torch.Tensor,
                            lu: Sequence[torch.Tensor], y: torch.Tensor, xq: torch.Tensor, band: SplineBand, *, max_knots: int,
                            x_own: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                           fb: Optional[Sequence[torch.Tensor]] = None, tensor_path: bool = True) -> torch.Tensor:
+                           fb: Optional[Sequence[torch.Tensor]] = None, tensor_path: bool = True, x_verified: bool = False) -> torch.Tensor:
     """Slices on tabulated ladders through the banded operators; whatever cannot be taken that way (a non-finite knot, a slice
     off its ladder when ``x_own`` is given, a ladder without a usable band) goes through the exact scan right behind.
-    ``fb`` = (int32[n_slices] list, uint32[1] count) scratch, allocated when not passed."""
+    ``fb`` = (int32[n_slices] list, uint32[1] count) scratch, allocated when not passed.  ``x_verified``: ``fb`` already holds the
+    verdict of comparing every slice's abscissae with its ladder's (``bs_implied_vol_ladder``); the band then does not read ``x_own``."""
     n_slices, n_q, n_l = knot_off.numel() - 1, xq.numel(), ladder_off.numel() - 1
+    if x_verified and (fb is None or x_own is None):
+        raise _lib.IvxError("spline_fit_eval_banded: x_verified needs the flags of the comparison (fb) and x_own for the flagged slices")
     if band.n_q != n_q:
         raise _lib.IvxError("spline_fit_eval_banded: the band was built for another grid")
     _req(order, torch.int32, "order"); _req(slice_ladder, torch.int32, "slice_ladder")
@@ -517,7 +544,7 @@ def spline_fit_eval_banded(knot_off: torch.Tensor, x_off: torch.Tensor, slice_la
                                            _ptr(x_own) if x_own is not None else None, _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q,
                                            _ptr(xq), int(band.extrap), _ptr(band.k0), _ptr(band.w), _ptr(band.ok), _ptr(band.perm),
                                            _ptr(band.frag) if use_mma else None, _ptr(band.oct) if use_mma else None, int(band.slab_knots),
-                                           _ptr(yq), _ptr(fb[0]), _ptr(fb[1]), _stream()), "ivx_spline_fit_eval_banded")
+                                           1 if x_verified else 0, _ptr(yq), _ptr(fb[0]), _ptr(fb[1]), _stream()), "ivx_spline_fit_eval_banded")
     _count("spline_fit_eval_banded_mma" if use_mma else "spline_fit_eval_banded")
     return yq
 

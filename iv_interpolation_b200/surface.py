@@ -144,6 +144,7 @@ class SurfacePipeline:
         self.banded_auto = banded == "auto"
         self.banded = bool(banded) and spec.n_grid_k <= 512 and 48 <= spec.n_strike <= 2048
         self._band = self._q_band = None
+        self._ivl_ws = None
         self._order = None
         self._fb_host = torch.zeros(1, dtype=torch.int32).pin_memory() if self.banded and self.banded_auto else None
         self._fb_event = None
@@ -204,10 +205,21 @@ class SurfacePipeline:
             D.bs_implied_vol_chain(q.price, q.is_call, q.S_t, q.K_ek, q.T_te, q.r_t, n_t=sp.n_t, n_exp=sp.n_exp,
                                    n_strike=sp.n_strike, out=self.iv, workspace=self._chain_ws)
         else:
-            if self._iv_ws is None:
-                from ._lib import lib
-                self._iv_ws = torch.empty(lib().ivx_bs_implied_vol_workspace_bytes(sp.n_quotes), dtype=torch.uint8, device=self.device)
-            D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv, workspace=self._iv_ws)
+            if self.banded:
+                # the solver has every strike in a register: it compares them with the first stamp's ladders on the way and flags
+                # the slices that differ, so the strike spline below does not read the K column again (x_verified)
+                self._group_slices()
+                if self._ivl_ws is None:
+                    from ._lib import lib
+                    self._ivl_ws = torch.empty(lib().ivx_bs_implied_vol_ladder_workspace_bytes(sp.n_t, sp.n_exp * sp.n_strike), dtype=torch.uint8,
+                                               device=self.device)
+                D.bs_implied_vol_ladder(q.price, q.S, q.K, q.T, q.r, q.is_call, n_t=sp.n_t, period=sp.n_exp * sp.n_strike, n_strike=sp.n_strike,
+                                        x_ladder=q.K, flags=self._fb, out=self.iv, workspace=self._ivl_ws)
+            else:
+                if self._iv_ws is None:
+                    from ._lib import lib
+                    self._iv_ws = torch.empty(lib().ivx_bs_implied_vol_workspace_bytes(sp.n_quotes), dtype=torch.uint8, device=self.device)
+                D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv, workspace=self._iv_ws)
         mark("implied_vol", 1)
         mark("spline_strike", 0)
         # knots of slice (t, e): x = the quoted strikes, read in place from the K column / the expiry's ladder
@@ -251,7 +263,7 @@ class SurfacePipeline:
                 self._group_slices()
                 D.spline_fit_eval_banded(self.knot_off, self._q_x_off, self._q_slice_ladder, self._order, self._lad_slice_off, sp.n_t,
                                          self._q_ladder_off, q.K, self._q_lu, self.iv, q.grid_k, self._q_band, max_knots=sp.n_strike,
-                                         x_own=q.K, out=self.smile, fb=self._fb)
+                                         x_own=q.K, out=self.smile, fb=self._fb, x_verified=True)
             else:
                 D.spline_fit_eval(self.knot_off, q.K, self.iv, q.grid_k, max_knots=sp.n_strike, extrap=sp.extrap, out=self.smile,
                                   x_off=self._q_x_off, lu=self._q_lu, slice_ladder=self._q_slice_ladder, x_own=q.K,
