@@ -45,7 +45,7 @@ __device__ __forceinline__ double norm_pdf(double z) { return INV_SQRT_2PI * exp
 // ---- set-up helpers: cheaper than the general library routines on the ranges the solver feeds them ---------------
 // Polynomial coefficients live in constant memory: as immediates every fp64 coefficient costs two UMOV issue slots
 // next to the DFMA that uses it, and this kernel is bound by instruction issue (profiles/README.md).
-__constant__ double EXP_C[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+__constant__ __align__(16) double EXP_C[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
                                  1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
                                  1.0 / 6.0,          0.5,               1.0,              1.0};
 // Reciprocal and reciprocal square root of a NORMAL a (1e-300 < a < 1e300) without the IEEE special-case tail of the
@@ -139,7 +139,7 @@ __device__ const double2 LOG_TAB[64] = {
     {0.5059288537549407, 0.6813592248079031},
     {0.5019607843137255, 0.689233281238809}};
 // full-mantissa scalars of the fast path, in the constant bank for the same reason (one LDCU instead of two UMOVs each)
-__constant__ double KF[8] = {6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4426950408889634, 0.7071067811865476,
+__constant__ __align__(16) double KF[8] = {6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4426950408889634, 0.7071067811865476,
                              2.5066282746310002, 1e-4, 1e-30, 2.3e-308};
 #define KF_LN2_HI KF[0]
 #define KF_LN2_LO KF[1]
@@ -149,7 +149,7 @@ __constant__ double KF[8] = {6.93147180369123816490e-01, 1.90821492927058770002e
 #define KF_ACCEPT KF[5]
 #define KF_1EM30 KF[6]
 #define KF_MIN_RATIO KF[7]
-__constant__ double LOG1P_C[7] = {-1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5};
+__constant__ __align__(16) double LOG1P_C[7] = {-1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5};
 __device__ __forceinline__ double log_normal(double a) {
   const int hi = __double2hiint(a);
   const int e = (hi >> 20) - 1023;
@@ -192,7 +192,7 @@ __device__ __forceinline__ double exp_neg_core(double z) {
 // folded into the constants (q log2e/2, 2 ln2, coefficients 1/(k! 2^k) to k = 10: 2e-13 at |r| = ln2/2) and 1/sqrt(2 pi) = 1.5958 x 2^-2
 // into the power of two that is assembled from n.  One multiple of ln2, not a hi + lo pair: n <= 1010 and an ulp of 2 ln2 move
 // r by 1.5e-13 at most, the size of the truncation.
-__constant__ double EXPH_C[12] = {2.69114445546737190e-10, 5.38228891093474463e-09, 9.68812003968253967e-08, 1.55009920634920635e-06,
+__constant__ __align__(16) double EXPH_C[12] = {2.69114445546737190e-10, 5.38228891093474463e-09, 9.68812003968253967e-08, 1.55009920634920635e-06,
                                   2.17013888888888897e-05, 2.60416666666666663e-04, 2.60416666666666652e-03, 2.08333333333333322e-02,
                                   0.125,                   0.5,                     0.7213475204444817,      1.3862943611198906};
 __device__ __forceinline__ double exp_half_neg_over_sqrt2pi(double q) {
@@ -298,9 +298,9 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
       A = r2;
     }
     const float fac = f_rcp(fmaf(0.5f * A, newton, 1.0f));
-    float sn = s + ((fac > 0.3f && fac < 3.0f) ? newton * fac : newton);
-    if (!(sn > 0.5f * s && sn < 2.0f * s)) sn = s;   // also catches NaN; no bracket here, the fp64 phase checks the result
-    s = sn;
+    // no bracket and no range guard here: whatever this step produces, the fp64 phase accepts only a converged value and
+    // sends the rest (NaN included) to the bracketed loop
+    s = s + ((fac > 0.3f && fac < 3.0f) ? newton * fac : newton);
   }
   return s;
 }
@@ -313,7 +313,7 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
 // fp64, smooth in q, so the difference of two nearby values keeps that relative accuracy.  The two Horner chains
 // interleave.  (The first version fitted (1 + 2q) erfcx(q) — the same degree for 8e-15, but a second reciprocal 1/(1+2q)
 // per value: ten more fp64 operations per pair.)
-__constant__ double ERFCX_C[21] = {
+__constant__ __align__(16) double ERFCX_C[21] = {
     -8.93653518802207727e-09,
     2.22219577646707465e-09,
     1.08269424077762936e-07,
@@ -337,7 +337,7 @@ __constant__ double ERFCX_C[21] = {
     1.09599566100049106e+00};
 
 // the same coefficients times sqrt(2 pi)/2: the fast path wants E/sqrt(2 pi) (= b') times [sqrt(2 pi)/2 (erfcx - erfcx)]
-__constant__ double ERFCX_CS[21] = {
+__constant__ __align__(16) double ERFCX_CS[21] = {
     -1.12002858897655023e-08,
     2.78510938252897965e-09,
     1.35695599835667513e-07,
@@ -460,27 +460,27 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
   const double target = p - lower_bound;                            // the out-of-the-money twin (p - 0 is p; p - diff is exact near the bound)
   // the upper bound (call: p < S, put: p < Kd) is target < min(S, Kd) for the twin, i.e. beta < e^{x/2}: tested once, below
   ok = ok && (target > 0.0);                                        // false for NaN prices
-  // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max), sqrt(S Kd) = max e^{x/2}, beta = target / sqrt(S Kd).
-  // One reciprocal and one reciprocal square root serve ratio, e^{x/2} and beta.
-  const double rmx = rcp_fast(mx);
-  double ratio = mn * rmx;                                         // (0, 1]
-  if (!pos_normal(ratio)) ok = false;                              // S/Kd beyond 1e308 (or max(S, Kd) above 1e300): an integer test
-  const double rsq = rsqrt_fast(ratio);
-  double x;
-  if (PRE_X) x = -fabs(x_pre);
-  else {                                                           // ratio = 1 gives +-1e-18 from the table: positive results become 0 (sign-bit mask)
-    const double lx = log_normal(ratio);
+  // x = -|ln(S/Kd)| = ln(min/max), e^{x/2} = sqrt(min/max) = min / sqrt(S Kd), beta = target / sqrt(S Kd): ONE reciprocal square root
+  // (of the product S Kd, which must therefore be a normal double itself) serves e^{x/2} and beta, and x/2 = ln e^{x/2} needs no
+  // reciprocal of its own.  hx = x/2 is what the fast path carries (h = -x/s = -hx (2/s), the doubling on the exponent).
+  const double prod = mn * mx;
+  if (!pos_normal(prod)) ok = false;                               // S Kd outside the normal range: an integer test
+  const double rs = rsqrt_fast(prod);
+  double ex2 = mn * rs;                                            // (0, 1]
+  double beta = target * rs;
+  double hx;
+  if (PRE_X) hx = -0.5 * fabs(x_pre);
+  else {                                                           // e^{x/2} = 1 gives +-1e-18 from the table: positive results become 0 (sign-bit mask)
+    const double lx = log_normal(ex2);
     const int keep = __double2hiint(lx) >> 31;
-    x = __hiloint2double(__double2hiint(lx) & keep, __double2loint(lx) & keep);
+    hx = __hiloint2double(__double2hiint(lx) & keep, __double2loint(lx) & keep);
   }
-  double ex2 = ratio * rsq;
-  double beta = (target * rmx) * rsq;
   if (ok && !(beta < ex2)) ok = false;                             // rounding pushed it onto the bound
   // lanes that are not ok: with the bracketed loop in line (DEFER = false) they solve a dummy alongside, since the loop votes
   // and must terminate; the straight-line fast kernel needs nothing of the kind — NaNs flow through (the table index clamps)
-  if (!DEFER && !ok) { x = -0.10536051565782628; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9
+  if (!DEFER && !ok) { hx = -0.05268025782891314; ex2 = 0.9486832980505138; beta = 0.05; }   // ln 0.9 / 2
 
-  const float xf = (float)x;
+  const float xf = 2.0f * (float)hx;
   // ln beta to single precision from the exponent and the leading mantissa bits (beta may be far below FLT_MIN)
   const int bhi = __double2hiint(beta);
   const float lnbeta_f = fmaf((float)(((bhi >> 20) & 0x7ff) - 1023), 0.69314718f,
@@ -504,10 +504,11 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
   {
     // Halley: step = -g / (b' - g b''/(2 b')),  b' = E/sqrt(2 pi) =: Ec,  b''/b' = h^2/s - s/4
     const double inv_s = rcp_fast(s);
-    const double h = -x * inv_s, t = 0.5 * s;        // h >= 0
-    const double hh = h * h;
-    // (1/s)/2 by an exponent decrement (1/40 < 1/s <= 1e30: normal)
+    // (1/s)/2 and 2 (1/s) by an exponent decrement / increment (1/40 < 1/s <= 1e30: normal)
     const double half_inv_s = __hiloint2double(__double2hiint(inv_s) - 0x00100000, __double2loint(inv_s));
+    const double two_inv_s = __hiloint2double(__double2hiint(inv_s) + 0x00100000, __double2loint(inv_s));
+    const double h = -hx * two_inv_s, t = 0.5 * s;   // h = -x/s >= 0
+    const double hh = h * h;
     const double r2h = fma(hh, half_inv_s, -0.125 * s);              // b''/(2 b')
     const double q = fma(t, t, hh);                                  // h^2 + t^2
     const double d = h - t;
@@ -538,7 +539,7 @@ __device__ __forceinline__ bool solve_quote(bool ok, double p, double s_, double
     double inv_beta = 1.0, lnbeta_off = 0.0;
     if (beta < 1e-290) lnbeta_off = log(beta); else inv_beta = 1.0 / beta;
     int it2 = 0;
-    s = polish_f64(x, beta, inv_beta, lnbeta_off, ex2, lower, s, it2);
+    s = polish_f64(hx + hx, beta, inv_beta, lnbeta_off, ex2, lower, s, it2);
     it += it2;
   }
   sigma_out = ok ? s * rsqrt_fast(t_) : qnan();
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(256, 6) k_bs_implied_vol(uint32_t n, const dou
   const bool call = is_call[j] != 0;
   const double kd = k_ * exp_neg_small(r_ * t_);
   // S, K, T and Kd positive, finite and normal (a NaN or infinite r shows in Kd); the price is checked against its bounds
-  const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+  const bool ok = pos_normal(s_) && pos_normal(t_) && pos_normal(kd);   // (Kd normal and positive: so is K, or the quote is outside the domain anyway)
   double out;
   int it;
   const bool deferred = solve_quote<false, DEFER>(ok, p, s_, kd, t_, call, 0.0, out, it);
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol_retry(uint32_t n, const 
     const double p = price[j], s_ = S[j], k_ = K[j], t_ = T[j], r_ = r[j];
     const bool call = is_call[j] != 0;
     const double kd = k_ * exp_neg_small(r_ * t_);
-    const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+    const bool ok = pos_normal(s_) && pos_normal(t_) && pos_normal(kd);   // (Kd normal and positive: so is K, or the quote is outside the domain anyway)
     double out;
     int it;
     solve_quote<false, false>(ok, p, s_, kd, t_, call, 0.0, out, it);
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(256, 6) k_bs_implied_vol_ladder(uint32_t perio
   const bool call = is_call[i] != 0;
   const double lad = __ldcg(x_ladder + jj);         // L2 only: the 480 KB of ladders must not push the guess table out of L1
   const double kd = k_ * exp_neg_small(r_ * t_);
-  const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+  const bool ok = pos_normal(s_) && pos_normal(t_) && pos_normal(kd);   // (Kd normal and positive: so is K, or the quote is outside the domain anyway)
   double out;
   int it;
   const bool deferred = solve_quote<false, true>(ok, p, s_, kd, t_, call, 0.0, out, it);
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol_ladder_retry(uint32_t gx
     const double p = price[i], s_ = S[i], k_ = K[i], t_ = T[i], r_ = r[i];
     const bool call = is_call[i] != 0;
     const double kd = k_ * exp_neg_small(r_ * t_);
-    const bool ok = pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd);
+    const bool ok = pos_normal(s_) && pos_normal(t_) && pos_normal(kd);   // (Kd normal and positive: so is K, or the quote is outside the domain anyway)
     double out;
     int it;
     solve_quote<false, false>(ok, p, s_, kd, t_, call, 0.0, out, it);
@@ -718,7 +719,7 @@ __device__ __forceinline__ bool chain_quote(int32_t j, int64_t t, int32_t n_exp,
     xi = (lnS - lnK) + rt;                                         // ln(S / (K e^{-rT}))
   }
   const double kd = k_ * disc;
-  const bool ok = inr && pos_normal(s_) && pos_normal(k_) && pos_normal(t_) && pos_normal(kd) && isfinite(xi);
+  const bool ok = inr && pos_normal(s_) && pos_normal(t_) && pos_normal(kd) && isfinite(xi);
   double out;
   int it;
   const bool deferred = solve_quote<true, DEFER>(ok, p, s_, kd, t_, call, xi, out, it);
