@@ -353,7 +353,8 @@ def run_gpu(args):
     peak, peak_src = _peaks()
     alg = {
         "implied_vol": n_quotes * BYTES_PER_QUOTE,
-        "spline_strike": n_quotes * 16 + n_t * N_EXP * N_GRID_K * 8,
+        # knots: y only (8 B) when the solver has already compared the strikes with the ladders (banded path, x_verified), else x and y
+        "spline_strike": n_quotes * (8 if pipe.banded else 16) + n_t * N_EXP * N_GRID_K * 8,
         "spline_maturity": n_t * (N_EXP + N_GRID_M) * N_GRID_K * 8,
         "candles": n_t * N_GRID_M * N_GRID_K * 8 + n_buckets * N_GRID_M * N_GRID_K * 32,
     }
@@ -366,24 +367,43 @@ def run_gpu(args):
                       "algorithmic_bytes": alg[s], "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4),
                       "share_of_step": round(stage_ms[s] / ms_step, 4)}
     dom = max(pipe.STAGES, key=lambda s: stage_ms[s])
-    roofline = {"kernel": {"implied_vol": "k_bs_implied_vol", "spline_strike": "k_spline_fit_eval",
+    roofline = {"kernel": {"implied_vol": "k_bs_implied_vol_ladder" if pipe.banded else "k_bs_implied_vol",
+                           "spline_strike": "k_band_apply_mma" if pipe.banded else "k_spline_fit_eval",
                            "spline_maturity": "k_spline_strided", "candles": "k_ohlc_time_major"}[dom],
+                # the figures below are against the HBM roofline (algorithmic bytes / time / measured copy peak); what actually bounds
+                # the dominant kernel is said in `bound` and `limiter`
                 "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac_hbm"],
                 "traffic": None, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes per launch / CUDA-event duration of that launch inside the timed steps"}
 
-    # DRAM traffic of the dominant kernel, from the committed ncu capture (per unit, scaled to this launch)
+    # DRAM traffic and pipe utilisation of the dominant kernel, from the committed ncu capture (per unit, scaled to this launch)
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")) as f:
             tr = json.load(f).get(roofline["kernel"])
         if tr:
             n_units = {"quote": n_quotes, "knot": n_quotes, "grid point": n_t * N_GRID_M * N_GRID_K, "surface row": n_t * N_GRID_M * N_GRID_K}[tr["unit"]]
             roofline["traffic"] = tr["bytes_per_unit"] * n_units
-            roofline["traffic_source"] = f"profiles/ncu_traffic_r1.json: {tr['bytes_per_unit']} DRAM B per {tr['unit']} (ncu --set full) x {n_units}"
+            roofline["traffic_source"] = f"profiles/ncu_traffic_r2.json: {tr['bytes_per_unit']} DRAM B per {tr['unit']} (ncu --set full) x {n_units}"
     except (OSError, ValueError, KeyError):
         pass
-    roofline["limiter"] = ("instruction issue and the fp64 pipe together (ncu, profiles/ncu_r1_final_summary.json: issue slots 78 % busy, "
-                           "fp64 pipe 50 %, DRAM 29 %): 558 instructions per quote, 190 of them fp64 at two issue cycles each") if dom == "implied_vol" else None
+    if dom == "implied_vol":
+        # ncu (profiles/ncu_r2_summary.json): 406 warp instructions per 32 quotes, 133 of them fp64; an fp64 instruction holds the
+        # issue port for two cycles on B200 (16 fp64 lanes per SM sub-partition), and 406 + 133 = 539 of the 560 cycles a warp
+        # of quotes takes per sub-partition: the kernel runs at the issue limit of its own instruction stream
+        roofline["bound"] = "issue/fp64"
+        roofline["hbm_frac"] = roofline["frac"]
+        roofline["limiter"] = ("instruction issue, with fp64 instructions costing two issue cycles each (ncu, profiles/ncu_r2_summary.json: "
+                               "issue slots 77 % busy + the second cycle of the fp64 instructions 24 % = 100 %; fp64 pipe 47 %, DRAM 39 %): "
+                               "406 warp instructions per 32 quotes, 133 of them fp64")
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_r2_summary.json")) as f:
+                for e in json.load(f):
+                    if e["kernel"].startswith(roofline["kernel"]):
+                        roofline["fp64_pipe_frac"] = round(float(e["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"].split()[0]) / 100, 4)
+                        roofline["issue_active_frac"] = round(float(e["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0]) / 100, 4)
+                        break
+        except (OSError, ValueError, KeyError):
+            pass
 
     # ---- the same step in the chain layout (S per stamp, K and call/put per contract, T per (stamp, expiry)) -----
     sc = SF.StructuredChain.from_quotes(chain)

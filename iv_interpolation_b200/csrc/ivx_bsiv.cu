@@ -635,8 +635,12 @@ __global__ void __launch_bounds__(256, 6) k_bs_implied_vol_ladder(uint32_t perio
   if (inr) {
     st_stream(sigma + i, out);
     if (((__double2hiint(k_) ^ __double2hiint(lad)) | (__double2loint(k_) ^ __double2loint(lad))) != 0) {   // rare
+      // one atomic per (warp, slice) at most, none once the slice is flagged: a moved ladder makes all 2000 quotes of a slice differ
       const uint32_t slice = i / n_strike;
-      if (atomicExch(slice_flags + slice, 1) == 0) atomicAdd(flag_count, 1u);
+      const uint32_t peers = __match_any_sync(__activemask(), slice);
+      if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1) && *((volatile int32_t*)(slice_flags + slice)) == 0 &&
+          atomicExch(slice_flags + slice, 1) == 0)
+        atomicAdd(flag_count, 1u);
     }
   }
   record_deferred(deferred && inr, (blockIdx.y * gridDim.x + blockIdx.x) * 8u + (threadIdx.x >> 5), list, counter);

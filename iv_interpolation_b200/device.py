@@ -494,7 +494,7 @@ class SplineBand:
 
 
 def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torch.Tensor, *, extrap: int = 1,
-                      out: Optional[SplineBand] = None, tensor_path: bool = True) -> SplineBand:
+                      out: Optional[SplineBand] = None, tensor_path: bool = True, refresh_hint: bool = False) -> SplineBand:
     """Per (ladder, grid point): the 48 knot weights of "fit the natural spline, evaluate at xq[q]" and their start, checked
     against a full solve of two probe vectors (``ok[l] == 0``: that ladder's slices take the exact solve)."""
     _req(ladder_off, torch.int64, "ladder_off"); _req(x_ladder, torch.float64, "x_ladder"); _req(xq, torch.float64, "xq")
@@ -510,8 +510,10 @@ def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torc
                                       _ptr(out.ok), _ptr(out.perm), _ptr(out.frag) if tensor_path else None,
                                       _ptr(out.oct) if tensor_path else None, _stream()), "ivx_spline_band_build")
     _count("spline_band_build")
-    if tensor_path and n_l > 0:
-        # one read-back per build (a build happens once per version of the ladders): how many knots a slab's rows must hold
+    if tensor_path and n_l > 0 and (out.slab_knots == 0 or refresh_hint):
+        # ONE read-back, at the first build of this set of ladders: how many knots a 64-point slab's staged rows must hold.  Later
+        # builds into the same object (a column rewritten in place, a streaming pipeline's next chunk) keep the figure and stay
+        # asynchronous; should a slab then need more, the kernel sees it and hands the batch to the exact solve — slower, never wrong.
         out.slab_knots = int(out.oct[n_l * 128:].view(n_l, 2)[:, 0].max().item())
     return out
 
