@@ -846,3 +846,58 @@ def test_aggregate_to_5min_merges_buckets_of_unsorted_input_like_groupby(dev):
     assert len(got) == len(want) and (got["timestamp"].to_numpy() == want["time_group"].to_numpy()).all()
     for c in ("open", "high", "low", "close", "volume"):
         assert np.array_equal(got[c].to_numpy(), want[c].to_numpy()), c
+
+
+def test_implied_vol_on_presumed_ladders_flags_exactly_the_slices_that_differ(dev):
+    """ivx_bs_implied_vol_ladder: the same implied vols as the plain solver, bit for bit, and slice_flags / flag_count name exactly
+    the slices in which a strike differs from the ladder's (an ulp is enough; NaN strikes differ too) — whole moved ladders (2000
+    differing quotes per slice: one count per slice) as well as a single quote.  ivx_spline_fit_eval_banded(x_verified) then takes
+    the verdict: flagged slices come from the exact solve with their OWN strikes, the others from the band, none reads x."""
+    import torch
+    from iv_interpolation_b200 import device as D
+    rng = np.random.default_rng(11)
+    n_t, n_exp, n_strike = 37, 3, 160
+    period = n_exp * n_strike
+    lad = np.concatenate([3000.0 + np.cumsum(rng.uniform(3.0, 9.0, n_strike)) for _ in range(n_exp)])
+    K = np.tile(lad, n_t)
+    S = np.repeat(3600.0 * np.exp(rng.normal(0, 0.01, n_t)), period)
+    T = np.tile(np.repeat((np.arange(n_exp) + 1) * 30 / 365.0, n_strike), n_t)
+    r = np.full(n_t * period, 0.03)
+    is_call = (K > S).astype(np.uint8)
+    sigma = 0.2 + 0.3 * np.log(K / S) ** 2
+    moved = {5 * n_exp + 1: "ladder", 20 * n_exp + 2: "ulp", 36 * n_exp + 0: "last"}       # slice -> how it differs
+    for sl, how in moved.items():
+        a = sl * n_strike
+        if how == "ladder":
+            K[a:a + n_strike] += 2.5
+        elif how == "ulp":
+            K[a + 77] = np.nextafter(K[a + 77], np.inf)
+        else:
+            K[a + n_strike - 1] *= 1.001
+    price = O.bs_price(S, K, T, r, sigma, is_call)
+    g = lambda a: _t(a, dev)
+    flags = (torch.full((n_t * n_exp,), 7, dtype=torch.int32, device=dev), torch.full((1,), 9, dtype=torch.int32, device=dev))
+    got = D.bs_implied_vol_ladder(g(price), g(S), g(K), g(T), g(r), g(is_call), n_t=n_t, period=period, n_strike=n_strike,
+                                  x_ladder=g(lad), flags=flags).cpu().numpy()
+    plain = D.bs_implied_vol(g(price), g(S), g(K), g(T), g(r), g(is_call), two_kernels=True).cpu().numpy()
+    assert np.array_equal(got, plain, equal_nan=True)
+    f = flags[0].cpu().numpy()
+    assert sorted(np.flatnonzero(f).tolist()) == sorted(moved) and set(f.tolist()) <= {0, 1} and int(flags[1].item()) == len(moved)
+
+    # the strike spline on the verdict: band for the clean slices, exact solve (own strikes) for the flagged ones
+    xq = np.linspace(lad.min() - 5, lad.max() + 5, 200)
+    knot_off = np.arange(n_t * n_exp + 1, dtype=np.int64) * n_strike
+    ladder_off = np.arange(n_exp + 1, dtype=np.int64) * n_strike
+    slice_ladder = (np.arange(n_t * n_exp) % n_exp).astype(np.int32)
+    order = np.argsort(slice_ladder, kind="stable").astype(np.int32)
+    lad_slice_off = np.arange(n_exp + 1, dtype=np.int64) * n_t
+    lu = D.spline_ladder_factor(g(ladder_off), g(lad), max_knots=n_strike)
+    band = D.spline_band_build(g(ladder_off), g(lad), g(xq), extrap=1)
+    yq = D.spline_fit_eval_banded(g(knot_off), g(ladder_off[:-1][slice_ladder]), g(slice_ladder), g(order), g(lad_slice_off), n_t, g(ladder_off),
+                                  g(lad), lu, g(got), g(xq), band, max_knots=n_strike, x_own=g(K), fb=flags, x_verified=True)
+    yq = yq.cpu().numpy().reshape(n_t * n_exp, -1)
+    assert sorted(np.flatnonzero(flags[0].cpu().numpy()).tolist()) == sorted(moved) and int(flags[1].item()) == len(moved)
+    for sl in list(moved) + [0, 7, 50, n_t * n_exp - 2]:
+        a = sl * n_strike
+        want = O.natural_spline_eval(K[a:a + n_strike], got[a:a + n_strike], xq, 1)
+        assert np.abs(yq[sl] - want).max() <= 1e-8 * max(1.0, np.abs(want).max()), sl
