@@ -47,6 +47,8 @@ struct OhlcvParams {
   int64_t* total;
   unsigned long long* tile_state;  // workspace, zeroed
   unsigned int* tile_counter;      // workspace, zeroed
+  const uint32_t* tile_symhead;    // workspace [n_tiles][16]: bit i of the tile = a symbol starts at its row i (k_ohlcv_tile_plan)
+  const int64_t* tile_sym_end;     // workspace [n_tiles]: end row of the symbol owning the tile's last row
   int32_t n_tiles;
   int32_t use_bulk;
 };
@@ -95,6 +97,28 @@ __device__ __forceinline__ uint32_t row_flags(double o, double h, double l, doub
   return f;
 }
 
+// ---- per-tile plan: where symbols start inside every tile, and where the symbol of the tile's last row ends ---------------------
+// The tiles used to find this out themselves — two 32-ary searches over in_off and a dependent load round, ~8 serialised L2 round
+// trips at the head of every tile's critical path (ncu: 17 % of the kernel's stall samples sat on the first use of that load).
+// One thread per symbol / per tile does it for the whole call in a few microseconds; a tile then reads 16 words and one int64.
+__global__ void __launch_bounds__(256) k_ohlcv_tile_plan(int64_t n_sym, int64_t n_rows, int64_t n_tiles, const int64_t* __restrict__ in_off,
+                                                         uint32_t* __restrict__ tile_symhead, int64_t* __restrict__ tile_sym_end) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_sym) {                                       // symbol i starts at row st (empty symbols mark the next one's start)
+    const int64_t st = __ldg(in_off + i);
+    if (st < n_rows) atomicOr(tile_symhead + (st / TB_ROWS) * 16 + ((st % TB_ROWS) >> 5), 1u << ((st % TB_ROWS) & 31));
+  }
+  if (i < n_tiles) {
+    const int64_t last = min((i + 1) * (int64_t)TB_ROWS, n_rows) - 1;
+    int64_t lo = 0, hi = n_sym;                          // in_off[lo] <= last < in_off[hi]: the LAST such lo (empty symbols before it)
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(in_off + mid) <= last) lo = mid; else hi = mid;
+    }
+    tile_sym_end[i] = __ldg(in_off + lo + 1);
+  }
+}
+
 // running aggregate of one bucket, rows fed in order
 struct Candle {
   double open, high, low, close, sum, comp;
@@ -134,7 +158,7 @@ __global__ void __launch_bounds__(TB_THREADS, 8) k_ohlcv_reduce(const OhlcvParam
     mbar_init(&S.bar, 1);
     fence_mbar_init();
   }
-  if (tid < 32) { S.symhead_mask[tid] = 0; S.kept_mask[tid] = 0; S.head_mask[tid] = 0; }
+  if (tid < 32) { S.kept_mask[tid] = 0; S.head_mask[tid] = 0; }
   if (tid == 0) S.next_bucket = 0;
   __syncthreads();
   const int tile = S.tile_id;
@@ -158,18 +182,10 @@ __global__ void __launch_bounds__(TB_THREADS, 8) k_ohlcv_reduce(const OhlcvParam
   if (P.sym_valid) {
     for (int i = tid; i < rows; i += TB_THREADS) S.valid[i] = P.sym_valid[r0 + i];
   }
-  // symbol starts inside the tile (overlapped with the copy): 32-ary searches by warp 1
+  // symbol starts inside the tile and the end of its last row's symbol: the plan's words, one load round under the copy
   if (warp == 1) {
-    // first symbol whose start is >= r0  =  1 + last s in [0, n_sym] with in_off[s] <= r0 - 1   (in_off[0] = 0)
-    const int64_t s_lo = r0 == 0 ? 0 : warp_upper_le<int64_t>(P.in_off, 0, P.n_sym + 1, r0 - 1, lane) + 1;
-    const int64_t s_last = warp_upper_le<int64_t>(P.in_off, 0, P.n_sym, r0 + rows - 1, lane);   // symbol of the tile's last row
-    if (lane == 0) { S.s_lo = (int32_t)s_lo; S.tile_sym_end = __ldg(P.in_off + s_last + 1); }
-  }
-  __syncthreads();
-  for (int64_t s = (int64_t)S.s_lo + tid; s < P.n_sym; s += TB_THREADS) {
-    int64_t st = __ldg(P.in_off + s);
-    if (st >= r0 + rows) break;
-    atomicOr(&S.symhead_mask[(st - r0) >> 5], 1u << ((st - r0) & 31));
+    S.symhead_mask[lane] = lane < 16 ? __ldg(P.tile_symhead + (int64_t)tile * 16 + lane) : 0u;
+    if (lane == 0) S.tile_sym_end = __ldg(P.tile_sym_end + tile);
   }
   if (bulk_rows > 0) mbar_wait(&S.bar, 0);
   __syncthreads();
@@ -461,7 +477,7 @@ using namespace ivx;
 
 extern "C" int64_t ivx_ohlcv_workspace_bytes(int64_t n_sym, int64_t n_rows) {
   int64_t n_tiles = (n_rows + TB_ROWS - 1) / TB_ROWS;
-  return 256 * 4 + align_up((n_tiles + 1) * 8, 256) + 2 * align_up((n_sym + 1) * 8, 256);
+  return 256 * 4 + align_up((n_tiles + 1) * 8, 256) + 2 * align_up((n_sym + 1) * 8, 256) + align_up(n_tiles * 64, 256) + align_up(n_tiles * 8, 256) + 512;
 }
 
 extern "C" int ivx_ohlcv_reduce(int64_t n_sym, const int64_t* in_off, int64_t n_rows, const int64_t* ts,
@@ -487,6 +503,8 @@ extern "C" int ivx_ohlcv_reduce(int64_t n_sym, const int64_t* in_off, int64_t n_
   unsigned long long* tile_state = cv.take<unsigned long long>(n_tiles + 1);
   int64_t* raw_out = cv.take<int64_t>(n_sym + 1);
   int64_t* raw_grp = cv.take<int64_t>(n_sym + 1);
+  uint32_t* tile_symhead = cv.take<uint32_t>(n_tiles * 16);
+  int64_t* tile_sym_end = cv.take<int64_t>(n_tiles);
 
   // the carved arrays are adjacent (256-byte aligned): one memset for the zeroed pair, one for the -1 pair
   IVX_CUDA(cudaMemsetAsync(counter, 0, (size_t)((char*)(tile_state + n_tiles + 1) - (char*)counter), stream));
@@ -495,6 +513,10 @@ extern "C" int ivx_ohlcv_reduce(int64_t n_sym, const int64_t* in_off, int64_t n_
   if (sym_flags && n_sym) IVX_CUDA(cudaMemsetAsync(sym_flags, 0, n_sym * 4, stream));
 
   if (n_tiles > 0) {
+    IVX_CUDA(cudaMemsetAsync(tile_symhead, 0, (size_t)n_tiles * 64, stream));
+    const int64_t np = n_sym > n_tiles ? n_sym : n_tiles;
+    k_ohlcv_tile_plan<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(n_sym, n_rows, n_tiles, in_off, tile_symhead, tile_sym_end);
+    IVX_LAUNCH_CHECK("k_ohlcv_tile_plan");
     OhlcvParams P;
     P.n_sym = n_sym; P.n_rows = n_rows; P.capacity = capacity;
     P.in_off = in_off; P.ts = ts;
@@ -509,6 +531,7 @@ extern "C" int ivx_ohlcv_reduce(int64_t n_sym, const int64_t* in_off, int64_t n_
     P.raw_out_off = raw_out; P.raw_group_off = raw_grp;
     P.sym_flags = sym_flags; P.total = total;
     P.tile_state = tile_state; P.tile_counter = counter;
+    P.tile_symhead = tile_symhead; P.tile_sym_end = tile_sym_end;
     P.n_tiles = (int32_t)n_tiles;
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
     P.use_bulk = al16(ts) && al16(open) && al16(high) && al16(low) && al16(close) && al16(volume);
