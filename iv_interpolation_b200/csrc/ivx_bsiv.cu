@@ -156,9 +156,9 @@ __device__ __forceinline__ double log_normal(double a) {
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));   // [1, 2)
   const double2 tb = __ldg(&LOG_TAB[(hi >> 14) & 63]);
   const double u = fma(m, tb.x, -1.0);
-  double p = LOG1P_C[0];
+  double p = LOG1P_C[1];                               // series to u^7: the u^8 term is below 2^-59
 #pragma unroll
-  for (int k = 1; k < 7; ++k) p = fma(p, u, LOG1P_C[k]);
+  for (int k = 2; k < 7; ++k) p = fma(p, u, LOG1P_C[k]);
   const double l = fma(u * u, p, u);
   const double ed = (double)e;
   return fma(ed, KF_LN2_HI, tb.y + fma(ed, KF_LN2_LO, l));   // ln2 split hi + lo
@@ -336,28 +336,26 @@ __constant__ __align__(16) double ERFCX_C[21] = {
     -9.76548729080888078e-01,
     1.09599566100049106e+00};
 
-// the same coefficients times sqrt(2 pi)/2: the fast path wants E/sqrt(2 pi) (= b') times [sqrt(2 pi)/2 (erfcx - erfcx)]
-__constant__ __align__(16) double ERFCX_CS[21] = {
-    -1.12002858897655023e-08,
-    2.78510938252897965e-09,
-    1.35695599835667513e-07,
-    -9.91714047967182288e-08,
-    -1.03486704039846220e-06,
-    1.79091139416750533e-06,
-    5.86368235349613527e-06,
-    -2.36432346471893475e-05,
-    -4.54635716508721532e-06,
-    2.21604237121331903e-04,
-    -5.70326893445270472e-04,
-    -3.52130391657651601e-04,
-    7.66032629665477915e-03,
-    -3.30499605309595643e-02,
-    9.57300324116014401e-02,
-    -2.18090367702553301e-01,
-    4.14660972443278708e-01,
-    -6.77859753005568000e-01,
-    9.69073397644359291e-01,
-    -1.22392232793456146e+00,
+// the same fit at degree 18, times sqrt(2 pi)/2: the fast path wants E/sqrt(2 pi) (= b') times [sqrt(2 pi)/2 (erfcx - erfcx)]
+__constant__ __align__(16) double ERFCX_CS[19] = {      // degree 18 (4e-14 as evaluated: the fast path's b needs no more), times sqrt(2 pi)/2
+    8.23961567720295452e-08,
+    -8.59628711319826841e-08,
+    -9.28046551104987971e-07,
+    1.76454135697427688e-06,
+    5.74657144711677158e-06,
+    -2.36144512506849318e-05,
+    -4.47002892624767972e-06,
+    2.21585572078349753e-04,
+    -5.70356973586231652e-04,
+    -3.52123079228094710e-04,
+    7.66033326373934641e-03,
+    -3.30499622129079088e-02,
+    9.57300315369120775e-02,
+    -2.18090367493141701e-01,
+    4.14660972493239299e-01,
+    -6.77859753017408417e-01,
+    9.69073397643521184e-01,
+    -1.22392232793436539e+00,
     1.37362685636836201e+00};
 
 template <bool SCALED = false>
@@ -367,9 +365,10 @@ __device__ __forceinline__ void erfcx_pair_pos(double q1, double q2, double& e1,
   const double r = rcp_fast(a1 * a2);               // q < 1e70: the product is normal
   const double r1 = r * a2, r2 = r * a1;             // 1/(q1+4), 1/(q2+4)
   const double t1 = fma(-8.0, r1, 1.0), t2 = fma(-8.0, r2, 1.0);
+  constexpr int DEG = SCALED ? 18 : 20;
   double p1 = C[0], p2 = C[0];
 #pragma unroll
-  for (int k = 1; k < 21; ++k) { p1 = fma(p1, t1, C[k]); p2 = fma(p2, t2, C[k]); }   // operands straight from the constant bank
+  for (int k = 1; k <= DEG; ++k) { p1 = fma(p1, t1, C[k]); p2 = fma(p2, t2, C[k]); }   // operands straight from the constant bank
   e1 = p1 * r1;
   e2 = p2 * r2;
 }
