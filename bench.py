@@ -806,18 +806,26 @@ def _ct_plan(n_und: int):
     return n_c, n_c.astype(np.float64) * CT_OUT_ROWS
 
 
-def _ct_workload_name(n_und: int, n_contracts: int) -> str:
+def _ct_workload_name(n_und: int, n_contracts: int, args=None) -> str:
+    if args is not None and _ct_is_replay(args):
+        return (f"replay (BASELINE.json configs[4]): {n_und} underlyings x ~1200 contracts ({n_contracts} in all), {args.ct_windows} consecutive "
+                f"20-day windows of hourly rows (~{args.ct_windows * 20} trading days), sparse: {args.ct_nan_frac:.0%} of the IVs NaN and "
+                f"{args.ct_drop_frac:.0%} of the hourly rows missing -> minute rows -> synthetic 1-min candles -> 5-min candles")
     return (f"contracts (BASELINE.json configs[2]): {n_und} underlyings x ~1200 contracts ({n_contracts} in all) x {CT_ROWS} hourly rows "
             f"(20 days) -> {CT_OUT_ROWS} minute rows each -> synthetic 1-min candles -> 5-min candles")
 
 
-def _ct_build_shard(mine, n_c, pin=True):
+def _ct_is_replay(args) -> bool:
+    return args.ct_windows > 1 or args.ct_drop_frac > 0.0 or args.ct_nan_frac != 0.05
+
+
+def _ct_build_shard(mine, n_c, pin=True, nan_frac=0.05, drop_frac=0.0):
     import numpy as np
     from iv_interpolation_b200 import contracts as CT, tapes
     first = np.concatenate([[0], np.cumsum(n_c)])
     parts = []
     for u in mine:
-        tp = tapes.make_underlying_tape(CT_SEED + 1 + int(u), int(n_c[u]), CT_ROWS, underlying=f"u{u}")
+        tp = tapes.make_underlying_tape(CT_SEED + 1 + int(u), int(n_c[u]), CT_ROWS, underlying=f"u{u}", nan_frac=nan_frac, drop_frac=drop_frac)
         parts.append(CT.HostContractShard.from_tape(tp, ids=first[u] + np.arange(n_c[u]), pin=False))
     return CT.HostContractShard.concat(parts, pin=pin)
 
@@ -836,8 +844,9 @@ def bench_contracts(ctx, args, peak):
     shards = SH.lpt_partition(costs, world)
     mine = shards[rank]
     t0 = time.perf_counter()
-    shard = _ct_build_shard(mine, n_c)
+    shard = _ct_build_shard(mine, n_c, nan_frac=args.ct_nan_frac, drop_frac=args.ct_drop_frac)
     t_tape = time.perf_counter() - t0
+    n_win = max(1, args.ct_windows)            # replay: the same contracts over consecutive 20-day windows (timestamps shifted per window)
     stream = CT.HostContractStream(dev, max_rows_per_batch=args.ct_batch_rows, seed=7)
     cuts = stream.batches(shard)
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
@@ -847,10 +856,13 @@ def bench_contracts(ctx, args, peak):
     d_date = shard.date.to(dev)
     d_cols = {c: shard.cols[c].to(dev) for c in CT.SRC_COLS}
     views = []
-    for a, b in cuts:
-        r0, r1 = int(shard.off[a]), int(shard.off[b])
-        views.append(((d_off[a:b + 1] - r0).contiguous(), d_date[r0:r1], [d_cols[c][r0:r1] for c in tapes.INTERP_COLS],
-                      [d_cols[c][r0:r1] for c in tapes.FILL_NUM_COLS], int(shard.ids[a])))
+    win_ticks = (CT_ROWS - 1) * tapes.HOUR_US + tapes.HOUR_US          # one window = 20 days + the hour to the next window's first stamp
+    d_dates = [d_date if wdx == 0 else d_date + wdx * win_ticks for wdx in range(n_win)]
+    for wdx in range(n_win):
+        for a, b in cuts:
+            r0, r1 = int(shard.off[a]), int(shard.off[b])
+            views.append(((d_off[a:b + 1] - r0).contiguous(), d_dates[wdx][r0:r1], [d_cols[c][r0:r1] for c in tapes.INTERP_COLS],
+                          [d_cols[c][r0:r1] for c in tapes.FILL_NUM_COLS], int(shard.ids[a])))
 
     def resident(ev=None):
         rows = minute = candles = 0
@@ -859,7 +871,7 @@ def bench_contracts(ctx, args, peak):
             rows += res.interp.total; minute += res.minute.total; candles += res.candles.total
         return rows, minute, candles
 
-    mk_ev = lambda: [{st: [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for st in CT.STAGES} for _ in cuts]
+    mk_ev = lambda: [{st: [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for st in CT.STAGES} for _ in views]
     for _ in range(warmup):
         resident()
     evs = [mk_ev() for _ in range(steps)]
@@ -876,7 +888,7 @@ def bench_contracts(ctx, args, peak):
     tot = lambda x: int(ctx.sum_over_ranks(float(x)))
     rows_all, minute_all, candles_all = tot(rows), tot(minute), tot(candles)
     stage_ms = {st: sum(ev[st][0].elapsed_time(ev[st][1]) for step in evs for ev in step) / steps for st in CT.STAGES}
-    n_src = int(shard.off[-1])
+    n_src = int(shard.off[-1]) * n_win
     m_e = 0.03 * minute                       # ~3 % of the volumes are NULL in the tape: exponential draws
     alg = {"interp_plan": n_src * 80, "interp_exec": rows * 85, "bridge_plan": rows * 16, "bridge_tapes": (5 * minute + m_e) * 8,
            "bridge_ohlcv": rows * 16 + minute * (40 + 56 + 8) + m_e * 8, "candle_ts": minute * 24,
@@ -890,13 +902,17 @@ def bench_contracts(ctx, args, peak):
         stages[st] = {"ms": round(stage_ms[st], 4), "kernels": kern[st], "algorithmic_bytes": int(alg[st]), "gbs": round(gbs, 1),
                       "frac_hbm": round(gbs / peak, 4), "share_of_step": round(stage_ms[st] / (e0.elapsed_time(e1) / steps), 4)}
     dom = max(CT.STAGES, key=lambda st: stage_ms[st])
-    del views, d_off, d_date, d_cols
+    del views, d_off, d_date, d_dates, d_cols
     torch.cuda.empty_cache()
 
     # ---- e2e: pinned host columns in, candle tables out to pinned host memory, then the gather over NCCL ------------
     def e2e_step(gev=None):
-        out = stream.run(shard)
-        tab = {k: torch.cat([t[k] for t in out["tables"]]) for k in out["tables"][0]} if out["tables"] else {}
+        out = None
+        tabs = []
+        for _w in range(n_win):                # replay: every window is sent again (same bytes; the time shift does not change the work)
+            out = stream.run(shard)
+            tabs.extend(out["tables"])
+        tab = {k: torch.cat([t[k] for t in tabs]) for k in tabs[0]} if tabs else {}
         if gev is not None:
             gev[0].record()
         got = SH.gather_tables(tab, dst=0) if world > 1 and tab else tab
@@ -919,13 +935,14 @@ def bench_contracts(ctx, args, peak):
     wall = (time.perf_counter() - tw) / steps
     ms_e2e = ctx.max_over_ranks(f0.elapsed_time(f1)) / steps
     ms_gather = ctx.max_over_ranks(sum(g[0].elapsed_time(g[1]) for g in gevs) / steps)
-    h2d, d2h = tot(stream.h2d_bytes), tot(stream.d2h_bytes)
+    h2d, d2h = tot(stream.h2d_bytes) * n_win, tot(stream.d2h_bytes) * n_win      # the stream counts one pass over the shard
     if rank == 0 and world > 1 and n_got != candles_all:
         raise SystemExit(f"bench.py: the gather delivered {n_got} candles, the ranks produced {candles_all}")
     per_rank_rows = ctx.gather_floats(float(rows))
     res = {
         "metric": CT_METRIC, "unit": CT_UNIT, "scaling": "strong",
-        "workload": _ct_workload_name(n_und, int(n_c.sum())),
+        "workload": _ct_workload_name(n_und, int(n_c.sum()), args),
+        "windows": n_win, "nan_iv_frac": args.ct_nan_frac, "missing_row_frac": args.ct_drop_frac,
         "value": rows_all / (ms_res / 1e3), "ms_per_step": ms_res, "steps": steps, "warmup": warmup,
         "interp_rows": rows_all, "minute_candles": minute_all, "candles_5min": candles_all,
         "source_rows": tot(n_src), "batches_per_rank": len(cuts),
@@ -1181,6 +1198,9 @@ def main():
     ap.add_argument("--dropin-contracts", type=int, default=DROPIN_CONTRACTS)
     ap.add_argument("--skip-contracts", action="store_true", help="leave the contracts object out of the surface line")
     ap.add_argument("--ct-underlyings", type=int, default=CT_UNDERLYINGS)
+    ap.add_argument("--ct-windows", type=int, default=1, help="contracts workload: consecutive 20-day windows per underlying (12 ~ one trading year: BASELINE configs[4])")
+    ap.add_argument("--ct-nan-frac", type=float, default=0.05, help="contracts workload: share of NaN IVs in the tape")
+    ap.add_argument("--ct-drop-frac", type=float, default=0.0, help="contracts workload: share of hourly rows missing altogether (sparse replay tape)")
     ap.add_argument("--ct-batch-rows", type=int, default=48_000_000, help="minute rows per batch of contracts (HBM working set)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

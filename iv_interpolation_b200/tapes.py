@@ -134,10 +134,11 @@ def make_contract_tape(
 
 def make_underlying_tape(seed: int, n_contracts: int, rows_per_contract: int = 481, spacing_us: int = HOUR_US,
                          nan_frac: float = 0.05, offgrid_frac: float = 0.02, underlying: str = "u0", t0: int = T0_US,
-                         s0: float = 25_000.0) -> ContractTape:
+                         s0: float = 25_000.0, drop_frac: float = 0.0) -> ContractTape:
     """All contracts of ONE underlying over ``rows_per_contract`` hourly stamps (481 = 20 days): the unit BASELINE.json
     configs[2] shards by.  Same distributions as ``make_contract_tape`` (5 % NaN iv incl. leading/trailing ones, 2 % of
-    rows 30 s off the grid, NaN volumes), drawn in whole-underlying arrays so that 100 underlyings take seconds."""
+    rows 30 s off the grid, NaN volumes), drawn in whole-underlying arrays so that 100 underlyings take seconds.
+    ``drop_frac`` > 0: that share of the hourly rows is missing altogether (the sparse replay tape of configs[4])."""
     rng = np.random.default_rng(seed)
     n, m = int(n_contracts), int(rows_per_contract)
     base_t = t0 + np.arange(m, dtype=np.int64) * spacing_us
@@ -170,6 +171,13 @@ def make_underlying_tape(seed: int, n_contracts: int, rows_per_contract: int = 4
         "quote_volume": vol * spot[None, :],
     }
     symbols = [f"{underlying}-{15 + int(e)}mar23-{int(strikes[k])}-{'c' if c else 'p'}" for e, k, c in zip(exp_i, k_i, cp)]
+    if drop_frac > 0.0:
+        # sparse tape (BASELINE.json configs[4]): hourly rows missing at random, never a contract's first or last — ragged CSR
+        keep = rng.random((n, m)) >= drop_frac
+        keep[:, 0] = keep[:, -1] = True
+        off = np.concatenate([[0], np.cumsum(keep.sum(axis=1))]).astype(np.int64)
+        return ContractTape(off, t[keep], {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)[keep]) for k, v in cols.items()},
+                            symbols, cp.astype(np.uint8))
     return ContractTape(np.arange(n + 1, dtype=np.int64) * m, t.reshape(-1),
                         {k: np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for k, v in cols.items()}, symbols,
                         cp.astype(np.uint8))
