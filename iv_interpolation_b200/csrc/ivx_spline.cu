@@ -33,6 +33,7 @@ namespace {
 constexpr int SPL_RMAX = 8;       // rows per thread
 constexpr int STRIDED_MAXK = 64;
 constexpr int STRIDED_SPT = 4;      // systems per thread in the strided kernel
+constexpr int STRIDED_MAXQ = 256;   // grid points whose segment, offset and class are tabulated once per CTA
 
 // 1/a for a normal a (1e-300 < |a| < 1e300): 20-bit hardware seed and two Newton steps, without the special-case tail
 // of the compiler's division (a zero or denormal a gives inf/NaN, like the division it replaces would give inf)
@@ -611,6 +612,13 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
                                                         double* __restrict__ yq) {
   __shared__ double s_x[STRIDED_MAXK], s_cp[STRIDED_MAXK], s_inv[STRIDED_MAXK], s_ih[STRIDED_MAXK];
   __shared__ int s_x_ok;
+  // Every system of the CTA shares the abscissae AND the grid, so which segment a grid point falls in, its offset from the
+  // segment's left knot and whether it lies outside the knots are the same for all 512 systems: tabulated once (ascending
+  // grid, as the walk below has always assumed).  The evaluation loop then has CTA-uniform bounds and no compare per point.
+  __shared__ double s_B[STRIDED_MAXQ];          // xq - x[segment]
+  __shared__ uint8_t s_cls[STRIDED_MAXQ];       // 0 inside, 1 below the first knot, 2 above the last, 3 NaN
+  __shared__ int s_qf[STRIDED_MAXK + 1];        // segment i takes grid points s_qf[i] .. s_qf[i+1]-1
+  const bool tab = n_q <= STRIDED_MAXQ;
   extern __shared__ __align__(16) double s_d[];          // [nk][128]
   x += (int64_t)blockIdx.y * x_batch_stride;
   y += (int64_t)blockIdx.y * nk * n_sys;
@@ -628,6 +636,25 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
       const double inv = 1.0 / (2.0 * (hm + hp) - hm * c_prev);
       c_prev = hp * inv;
       s_cp[i] = c_prev; s_inv[i] = inv;
+    }
+  }
+  if (tab && nk >= 3) {
+    // s_qf[i] = number of grid points below x[i] (i = 1 .. nk-2); segment 0 also takes what lies below x[0], segment nk-2 what lies above
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+      int lo = 0, hi = n_q;                               // first q with !(xq[q] < x[i]); NaN grid points count as "not below"
+      const double xi = s_x[i];
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(xq + mid) < xi) lo = mid + 1; else hi = mid; }
+      s_qf[i] = i == 0 ? 0 : (i == nk - 1 ? n_q : lo);
+    }
+  }
+  __syncthreads();
+  if (tab && nk >= 3) {
+    for (int q = threadIdx.x; q < n_q; q += blockDim.x) {
+      const double xv = __ldg(xq + q);
+      int lo = 0, hi = nk - 1;                            // segment: last i in [0, nk-2] with s_qf[i] <= q
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_qf[mid] <= q) lo = mid; else hi = mid; }
+      s_B[q] = xv - s_x[lo];
+      s_cls[q] = isnan(xv) ? 3 : (xv < s_x[0] ? 1 : (xv > s_x[nk - 1] ? 2 : 0));
     }
   }
   __syncthreads();
@@ -684,6 +711,17 @@ __global__ void __launch_bounds__(128) k_spline_strided(int64_t n_sys, int nk, c
         const double xl = s_x[i], h = s_x[i + 1] - xl, ih = s_ih[i];
         const double a1 = (y_hi - y_lo) * ih - h * (2.0 * M_lo + M_hi) * (1.0 / 6.0);
         const double a2 = 0.5 * M_lo, a3 = (M_hi - M_lo) * ih * (1.0 / 6.0);
+        if (tab) {
+          const int q_lo = s_qf[i], q_hi = s_qf[i + 1];    // CTA-uniform
+          double* op = yq + (int64_t)(q_hi - 1) * n_sys + sys;
+          for (int qq = q_hi - 1; qq >= q_lo; --qq, op -= n_sys) {
+            const double B = s_B[qq];
+            double v = fma(B, fma(B, fma(B, a3, a2), a1), y_lo);
+            const int c = s_cls[qq];
+            if (c) v = (c == 3 || extrap == 0) ? qnan() : (extrap == 2 ? (c == 1 ? y_first : y_last) : v);
+            st_stream(op, v);
+          }
+        } else
         while (q >= 0) {
           const double xv = __ldg(xq + q);
           if (!(i == 0 || xv >= xl || isnan(xv))) break;
