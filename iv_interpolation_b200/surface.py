@@ -174,24 +174,10 @@ class SurfacePipeline:
         self._buckets = (ts.data_ptr(), bucket_ts, bucket_start, nb)
         return self._buckets
 
-    def run(self, q: QuoteChain, events: Optional[Dict[str, List[torch.cuda.Event]]] = None) -> SurfaceResult:
-        """One pass of the hot path.  ``events`` (stage -> [start, end]) are recorded on the current stream."""
+    def _implied_vols(self, q: "QuoteChain", structured: bool):
+        """Stage 1 of ``run``: implied vols of every quote into ``self.iv`` (and, on the banded per-quote path, the slices whose
+        strikes differ from their ladder's into ``self._fb``)."""
         sp = self.spec
-        if self._buckets is None or self._buckets[0] != q.ts.data_ptr():
-            self.plan_buckets(q.ts)
-        _, bucket_ts, bucket_start, nb = self._buckets
-
-        def mark(stage, k):
-            if events is not None:
-                events[stage][k].record()
-
-        structured = isinstance(q, StructuredChain)
-        if self._fb_event is not None:                   # "auto": decided once, after the first run
-            self._fb_event.synchronize()
-            self._fb_event, self.banded_auto = None, False
-            if int(self._fb_host.item()) > 0.25 * sp.n_t * sp.n_exp:
-                self.banded, self.banded_switched_off = False, True
-        mark("implied_vol", 0)
         if structured:
             if self._chain_ws is None:
                 from ._lib import lib
@@ -220,7 +206,32 @@ class SurfacePipeline:
                     from ._lib import lib
                     self._iv_ws = torch.empty(lib().ivx_bs_implied_vol_workspace_bytes(sp.n_quotes), dtype=torch.uint8, device=self.device)
                 D.bs_implied_vol(q.price, q.S, q.K, q.T, q.r, q.is_call, out=self.iv, workspace=self._iv_ws)
-        mark("implied_vol", 1)
+
+    def run(self, q: QuoteChain, events: Optional[Dict[str, List[torch.cuda.Event]]] = None, part: str = "all") -> SurfaceResult:
+        """One pass of the hot path.  ``events`` (stage -> [start, end]) are recorded on the current stream.
+        ``part``: "all", or "iv" (stage 1 only, returns None) / "rest" (stages 2-4 on the IVs of an earlier "iv" call) — the two
+        halves of a chunked day can then run on two streams, the solver of one chunk beside the splines of the chunk before."""
+        sp = self.spec
+        if self._buckets is None or self._buckets[0] != q.ts.data_ptr():
+            self.plan_buckets(q.ts)
+        _, bucket_ts, bucket_start, nb = self._buckets
+
+        def mark(stage, k):
+            if events is not None:
+                events[stage][k].record()
+
+        structured = isinstance(q, StructuredChain)
+        if self._fb_event is not None:                   # "auto": decided once, after the first run
+            self._fb_event.synchronize()
+            self._fb_event, self.banded_auto = None, False
+            if int(self._fb_host.item()) > 0.25 * sp.n_t * sp.n_exp:
+                self.banded, self.banded_switched_off = False, True
+        if part != "rest":
+            mark("implied_vol", 0)
+            self._implied_vols(q, structured)
+            mark("implied_vol", 1)
+        if part == "iv":
+            return None
         mark("spline_strike", 0)
         # knots of slice (t, e): x = the quoted strikes, read in place from the K column / the expiry's ladder
         if structured:
