@@ -367,7 +367,7 @@ def run_gpu(args):
                       "algorithmic_bytes": alg[s], "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4),
                       "share_of_step": round(stage_ms[s] / ms_step, 4)}
     dom = max(pipe.STAGES, key=lambda s: stage_ms[s])
-    roofline = {"kernel": {"implied_vol": "k_bs_implied_vol_ladder" if pipe.banded else "k_bs_implied_vol",
+    roofline = {"kernel": {"implied_vol": "k_bs_implied_vol_ladder2" if pipe.banded else "k_bs_implied_vol",
                            "spline_strike": "k_band_apply_mma" if pipe.banded else "k_spline_fit_eval",
                            "spline_maturity": "k_spline_strided", "candles": "k_ohlc_time_major"}[dom],
                 # the figures below are against the HBM roofline (algorithmic bytes / time / measured copy peak); what actually bounds

@@ -26,6 +26,8 @@
 //      leave the loop (polish_f64).  It takes a quote from anywhere; on realistic tapes it runs for ~0 % of the quotes.
 // Inputs: S, K, T positive NORMAL numbers below 1e300 (subnormal or larger inputs return NaN), any finite r.
 // Loads are structure-of-arrays, one coalesced stream per column.
+#include <stdlib.h>
+
 #include "ivx_common.cuh"
 
 namespace ivx {
@@ -668,6 +670,230 @@ __global__ void __launch_bounds__(256) k_bs_implied_vol_ladder_retry(uint32_t gx
   }
 }
 
+
+// ---- two quotes per thread -------------------------------------------------------------------------------------------
+// The fast kernel is bound by instruction issue (profiles/README.md), and ~65 of its ~400 instructions per quote do nothing
+// quote-specific: 46 constant loads (B200 has no constant operand for fp64: every coefficient comes through LDCU/LDC), the
+// register moves that assemble immediates, the kernel-parameter loads and the index arithmetic.  A thread that solves TWO
+// quotes side by side — D2 below: every fp64 statement of the set-up and of the Halley step written once, executed for both
+// components back to back — pays those once per pair.  The fp32 pre-solve has no constants to share (its coefficients are
+// immediates) and branches per quote: it stays scalar, called twice.
+// Measured (ncu): 370 instead of 406 warp instructions per 32 quotes, 121 instead of 133 of them fp64 — but at 64 registers
+// only 32 warps per SM stay resident and the two dependency chains of a thread do not hide each other's latencies as well as
+// two warps did: issue slots 69-72 % busy instead of 77 %, 19.4 against 19.6 ms per day.  It ships because it is never slower.
+struct D2 { double a, b; };
+using ::fma;                                     // the overloads below must not hide the scalar one
+__device__ __forceinline__ D2 operator+(D2 x, D2 y) { return {x.a + y.a, x.b + y.b}; }
+__device__ __forceinline__ D2 operator-(D2 x, D2 y) { return {x.a - y.a, x.b - y.b}; }
+__device__ __forceinline__ D2 operator*(D2 x, D2 y) { return {x.a * y.a, x.b * y.b}; }
+__device__ __forceinline__ D2 operator+(D2 x, double y) { return {x.a + y, x.b + y}; }
+__device__ __forceinline__ D2 operator*(D2 x, double y) { return {x.a * y, x.b * y}; }
+__device__ __forceinline__ D2 operator*(double x, D2 y) { return {x * y.a, x * y.b}; }
+__device__ __forceinline__ D2 operator-(D2 x) { return {-x.a, -x.b}; }
+__device__ __forceinline__ D2 fma(D2 x, D2 y, D2 z) { return {fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)}; }
+__device__ __forceinline__ D2 fma(D2 x, D2 y, double z) { return {fma(x.a, y.a, z), fma(x.b, y.b, z)}; }
+__device__ __forceinline__ D2 fma(D2 x, double y, D2 z) { return {fma(x.a, y, z.a), fma(x.b, y, z.b)}; }
+__device__ __forceinline__ D2 fma(D2 x, double y, double z) { return {fma(x.a, y, z), fma(x.b, y, z)}; }
+__device__ __forceinline__ D2 fma(double x, D2 y, double z) { return {fma(x, y.a, z), fma(x, y.b, z)}; }
+template <class F> __device__ __forceinline__ D2 map2(D2 x, F f) { return {f(x.a), f(x.b)}; }
+__device__ __forceinline__ D2 add_exp(D2 x, int k) {           // x 2^k on the exponent field (x normal, no overflow: see the callers)
+  return {__hiloint2double(__double2hiint(x.a) + (k << 20), __double2loint(x.a)), __hiloint2double(__double2hiint(x.b) + (k << 20), __double2loint(x.b))};
+}
+__device__ __forceinline__ D2 rcp_fast(D2 a) {
+  const D2 y = map2(a, [](double v) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v)); return r; });
+  const D2 e = fma(-a, y, 1.0);
+  return fma(y, fma(e, e, e), y);
+}
+__device__ __forceinline__ D2 rcp_fast1(D2 a) {
+  const D2 y = map2(a, [](double v) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v)); return r; });
+  return fma(y, fma(-a, y, 1.0), y);
+}
+__device__ __forceinline__ D2 rsqrt_fast(D2 a) {
+  const D2 y = map2(a, [](double v) { double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v)); return r; });
+  const D2 e = fma(-(a * y), y, 1.0);
+  return fma(y, e * fma(e, 0.375, 0.5), y);
+}
+__device__ __forceinline__ D2 log_normal(D2 a) {              // see log_normal(double)
+  const int hia = __double2hiint(a.a), hib = __double2hiint(a.b);
+  const D2 m = {__hiloint2double((hia & 0x000fffff) | 0x3ff00000, __double2loint(a.a)), __hiloint2double((hib & 0x000fffff) | 0x3ff00000, __double2loint(a.b))};
+  const double2 ta = __ldg(&LOG_TAB[(hia >> 14) & 63]), tb = __ldg(&LOG_TAB[(hib >> 14) & 63]);
+  const D2 u = fma(m, D2{ta.x, tb.x}, -1.0);
+  D2 p = {LOG1P_C[1], LOG1P_C[1]};
+#pragma unroll
+  for (int k = 2; k < 7; ++k) p = fma(p, u, LOG1P_C[k]);
+  const D2 l = fma(u * u, p, u);
+  const D2 ed = {(double)((hia >> 20) - 1023), (double)((hib >> 20) - 1023)};
+  return fma(ed, KF_LN2_HI, D2{ta.y, tb.y} + fma(ed, KF_LN2_LO, l));
+}
+__device__ __forceinline__ D2 exp_half_neg_over_sqrt2pi(D2 q) {   // see the scalar version
+  const double MAGIC = 6755399441055744.0;
+  const D2 tn = fma(q, EXPH_C[10], MAGIC);
+  const int na = __double2loint(tn.a), nb = __double2loint(tn.b);
+  const D2 nd = tn + (-MAGIC);
+  const D2 w = fma(nd, EXPH_C[11], -q);
+  D2 p = {EXPH_C[0], EXPH_C[0]};
+#pragma unroll
+  for (int k = 1; k < 10; ++k) p = fma(p, w, EXPH_C[k]);
+  p = fma(p, w, 1.0);
+  return p * D2{__hiloint2double(((1021 - na) << 20) | 0x98845, 0x33d43651), __hiloint2double(((1021 - nb) << 20) | 0x98845, 0x33d43651)};
+}
+// four interleaved Horner chains on one stream of coefficients (the fast path's scaled degree-18 fit)
+__device__ __forceinline__ void erfcx_pair_pos_scaled(D2 q1, D2 q2, D2& e1, D2& e2) {
+  const D2 a1 = q1 + 4.0, a2 = q2 + 4.0;
+  const D2 r = rcp_fast(a1 * a2);
+  const D2 r1 = r * a2, r2 = r * a1;
+  const D2 t1 = fma(r1, -8.0, 1.0), t2 = fma(r2, -8.0, 1.0);
+  D2 p1 = {ERFCX_CS[0], ERFCX_CS[0]}, p2 = p1;
+#pragma unroll
+  for (int k = 1; k <= 18; ++k) { p1 = fma(p1, t1, ERFCX_CS[k]); p2 = fma(p2, t2, ERFCX_CS[k]); }
+  e1 = p1 * r1;
+  e2 = p2 * r2;
+}
+
+struct QuoteIn { double p, s_, k_, t_, r_; bool call; };
+// The fast path of solve_quote<false, true> for two quotes (same arithmetic, statement for statement: results are bit-equal to the
+// one-quote kernel's).  Returns the deferred flags.
+__device__ __forceinline__ void solve_pair(const QuoteIn& A, const QuoteIn& B, double& sigA, double& sigB, bool& defA, bool& defB) {
+  // discount factors: the common range of both by one interleaved polynomial, anything else per quote
+  const D2 z = {A.r_ * A.t_, B.r_ * B.t_};
+  D2 disc;
+  if (((__double2hiint(z.a) & 0x7fffffff) < 0x3FB00000) && ((__double2hiint(z.b) & 0x7fffffff) < 0x3FB00000)) {
+    const D2 w = -z;
+    D2 p = {EXP_C[5], EXP_C[5]};
+#pragma unroll
+    for (int k = 6; k < 14; ++k) p = fma(p, w, EXP_C[k]);
+    disc = p;
+  } else {
+    disc = {exp_neg_small(z.a), exp_neg_small(z.b)};
+  }
+  const D2 kd = D2{A.k_, B.k_} * disc;
+  bool okA = pos_normal(A.s_) && pos_normal(A.t_) && pos_normal(kd.a), okB = pos_normal(B.s_) && pos_normal(B.t_) && pos_normal(kd.b);
+  const bool sgA = A.s_ > kd.a, sgB = B.s_ > kd.b;
+  const D2 mx = {sgA ? A.s_ : kd.a, sgB ? B.s_ : kd.b}, mn = {sgA ? kd.a : A.s_, sgB ? kd.b : B.s_};
+  const D2 diff = mx - mn;
+  const D2 target = D2{A.p, B.p} - D2{(A.call == sgA) ? diff.a : 0.0, (B.call == sgB) ? diff.b : 0.0};
+  okA = okA && (target.a > 0.0); okB = okB && (target.b > 0.0);
+  const D2 prod = mn * mx;
+  okA = okA && pos_normal(prod.a); okB = okB && pos_normal(prod.b);
+  const D2 rs = rsqrt_fast(prod);
+  const D2 ex2 = mn * rs, beta = target * rs;
+  const D2 lx = log_normal(ex2);
+  const int keepA = __double2hiint(lx.a) >> 31, keepB = __double2hiint(lx.b) >> 31;
+  const D2 hx = {__hiloint2double(__double2hiint(lx.a) & keepA, __double2loint(lx.a) & keepA),
+                 __hiloint2double(__double2hiint(lx.b) & keepB, __double2loint(lx.b) & keepB)};
+  if (okA && !(beta.a < ex2.a)) okA = false;
+  if (okB && !(beta.b < ex2.b)) okB = false;
+  // fp32 pre-solve, per quote
+  auto pre = [](double hx_, double beta_, double ex2_) -> float {
+    const float xf = 2.0f * (float)hx_;
+    const int bhi = __double2hiint(beta_);
+    const float lnbeta_f = fmaf((float)(((bhi >> 20) & 0x7ff) - 1023), 0.69314718f,
+                                f_log((float)__hiloint2double((bhi & 0x000fffff) | 0x3ff00000, __double2loint(beta_))));
+    const float s_tab = guess_table(xf, lnbeta_f);
+    const bool lower = s_tab * s_tab < -2.0f * xf;
+    return presolve_f32(xf, (float)beta_, lnbeta_f, (float)ex2_, s_tab, lower);
+  };
+  const float s0A = pre(hx.a, beta.a, ex2.a), s0B = pre(hx.b, beta.b, ex2.b);
+  const bool sokA = s0A >= 1e-30f && s0A < (float)S_MAX, sokB = s0B >= 1e-30f && s0B < (float)S_MAX;
+  const D2 s = {sokA ? (double)s0A : 1.0, sokB ? (double)s0B : 1.0};
+  // fp64 Halley step, both quotes
+  const D2 inv_s = rcp_fast(s);
+  const D2 half_inv_s = add_exp(inv_s, -1), two_inv_s = add_exp(inv_s, 1);
+  const D2 h = -hx * two_inv_s, t = s * 0.5;
+  const D2 hh = h * h;
+  const D2 r2h = fma(hh, half_inv_s, s * -0.125);
+  const D2 q = fma(t, t, hh);
+  const D2 d = h - t;
+  D2 e1, e2;
+  erfcx_pair_pos_scaled(D2{fabs(d.a), fabs(d.b)} * KF_INV_SQRT2, (h + t) * KF_INV_SQRT2, e1, e2);
+  const D2 Ec = exp_half_neg_over_sqrt2pi(q);
+  const int dhiA = __double2hiint(d.a), dhiB = __double2hiint(d.b), amA = dhiA >> 31, amB = dhiB >> 31;
+  const D2 e1s = {__hiloint2double(__double2hiint(e1.a) | (dhiA & (int)0x80000000), __double2loint(e1.a)),
+                  __hiloint2double(__double2hiint(e1.b) | (dhiB & (int)0x80000000), __double2loint(e1.b))};
+  const D2 cst = {__hiloint2double(__double2hiint(ex2.a) & amA, __double2loint(ex2.a) & amA),
+                  __hiloint2double(__double2hiint(ex2.b) & amB, __double2loint(ex2.b) & amB)};
+  const D2 g = fma(Ec, e1s - e2, cst - beta);
+  const D2 den = fma(-g, r2h, Ec);
+  const D2 step = -g * rcp_fast1(den);
+  const D2 sn = s + step;
+  const bool accA = ((unsigned)((__double2hiint(step.a) & 0x7fffffff) + (13 << 20)) < (unsigned)__double2hiint(s.a)) && sokA &&
+                    (__double2hiint(q.a) < 0x4095E000) && (__double2hiint(den.a) > 0);
+  const bool accB = ((unsigned)((__double2hiint(step.b) & 0x7fffffff) + (13 << 20)) < (unsigned)__double2hiint(s.b)) && sokB &&
+                    (__double2hiint(q.b) < 0x4095E000) && (__double2hiint(den.b) > 0);
+  const D2 sf = {accA ? sn.a : s.a, accB ? sn.b : s.b};
+  const D2 sig = sf * rsqrt_fast(D2{A.t_, B.t_});
+  sigA = okA ? sig.a : qnan();
+  sigB = okB ? sig.b : qnan();
+  defA = okA && !accA;
+  defB = okB && !accB;
+}
+
+// the ladder kernel with two quotes per thread: a CTA takes 512 quotes of one stamp, thread t the quotes t and t + 256
+__global__ void __launch_bounds__(256, 4) k_bs_implied_vol_ladder2(uint32_t period, uint32_t n_strike, const double* __restrict__ price,
+                                                                const double* __restrict__ S, const double* __restrict__ K,
+                                                                const double* __restrict__ T, const double* __restrict__ r,
+                                                                const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
+                                                                const double* __restrict__ x_ladder, int32_t* __restrict__ slice_flags,
+                                                                uint32_t* __restrict__ flag_count, uint32_t* __restrict__ list,
+                                                                uint32_t* __restrict__ counter) {
+  const uint32_t j0 = blockIdx.x * 512u + threadIdx.x, j1 = j0 + 256u;
+  const bool in0 = j0 < period, in1 = j1 < period;
+  const uint32_t jj0 = in0 ? j0 : 0u, jj1 = in1 ? j1 : 0u;
+  const uint32_t base = blockIdx.y * period, i0 = base + jj0, i1 = base + jj1;
+  QuoteIn A, B;
+  A.p = ld_stream(price + i0); B.p = ld_stream(price + i1);
+  A.s_ = ld_stream(S + i0); B.s_ = ld_stream(S + i1);
+  A.k_ = ld_stream(K + i0); B.k_ = ld_stream(K + i1);
+  A.t_ = ld_stream(T + i0); B.t_ = ld_stream(T + i1);
+  A.r_ = ld_stream(r + i0); B.r_ = ld_stream(r + i1);
+  A.call = is_call[i0] != 0; B.call = is_call[i1] != 0;
+  const double lad0 = __ldcg(x_ladder + jj0), lad1 = __ldcg(x_ladder + jj1);
+  double sg0, sg1;
+  bool df0, df1;
+  solve_pair(A, B, sg0, sg1, df0, df1);
+  auto finish = [&](bool inr, uint32_t i, double out, double k_, double lad) {
+    if (inr) {
+      st_stream(sigma + i, out);
+      if (((__double2hiint(k_) ^ __double2hiint(lad)) | (__double2loint(k_) ^ __double2loint(lad))) != 0) {   // rare
+        const uint32_t slice = i / n_strike;
+        const uint32_t peers = __match_any_sync(__activemask(), slice);
+        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1) && *((volatile int32_t*)(slice_flags + slice)) == 0 &&
+            atomicExch(slice_flags + slice, 1) == 0)
+          atomicAdd(flag_count, 1u);
+      }
+    }
+  };
+  finish(in0, i0, sg0, A.k_, lad0);
+  finish(in1, i1, sg1, B.k_, lad1);
+  // warp ids of the retry list: ((stamp, 512-block) * 2 + half) * 8 + warp
+  const uint32_t wbase = (blockIdx.y * gridDim.x + blockIdx.x) * 16u + (threadIdx.x >> 5);
+  record_deferred(df0 && in0, wbase, list, counter);
+  record_deferred(df1 && in1, wbase + 8u, list, counter);
+}
+
+__global__ void __launch_bounds__(256) k_bs_implied_vol_ladder2_retry(uint32_t gx, uint32_t period, const double* __restrict__ price,
+                                                                      const double* __restrict__ S, const double* __restrict__ K,
+                                                                      const double* __restrict__ T, const double* __restrict__ r,
+                                                                      const uint8_t* __restrict__ is_call, double* __restrict__ sigma,
+                                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ counter) {
+  const uint32_t count = *counter;
+  for (uint32_t e = blockIdx.x * 8u + (threadIdx.x >> 5); e < count; e += gridDim.x * 8u) {
+    const uint32_t w = list[e];
+    const uint32_t blk = w >> 4;                                   // (y * gx + x)
+    const uint32_t j = (blk % gx) * 512u + ((w >> 3) & 1u) * 256u + (w & 7u) * 32u + (threadIdx.x & 31u);
+    const bool inr = j < period;
+    const uint32_t i = (blk / gx) * period + (inr ? j : 0u);
+    const double p = price[i], s_ = S[i], k_ = K[i], t_ = T[i], r_ = r[i];
+    const bool call = is_call[i] != 0;
+    const double kd = k_ * exp_neg_small(r_ * t_);
+    const bool ok = pos_normal(s_) && pos_normal(t_) && pos_normal(kd);
+    double out;
+    int it;
+    solve_quote<false, false>(ok, p, s_, kd, t_, call, 0.0, out, it);
+    if (inr) sigma[i] = out;
+  }
+}
+
 // ---- chain layout: quote (t, e, k) = price[(t n_exp + e) n_strike + k]; S per stamp, K per contract, T per (stamp, expiry)
 // terms[0 .. n_t)            ln S[t]
 // terms[n_t .. +n_ek)        ln K[e][k]
@@ -891,7 +1117,7 @@ static int64_t ladder_chunk_stamps(int64_t period) {
 extern "C" int64_t ivx_bs_implied_vol_ladder_workspace_bytes(int64_t n_t, int64_t period) {
   if (n_t < 0 || period <= 0 || period >= ((int64_t)1 << 31)) return -1;
   const int64_t gx = (period + 255) / 256, ch = ladder_chunk_stamps(period), gy = n_t < ch ? n_t : ch;
-  return 256 + 4 * (gx * gy * 8 + 8);
+  return 256 + 4 * (gx * gy * 8 + 16 * gy + 8);          // (the two-quote kernel numbers 16 warps per 512-quote block)
 }
 
 extern "C" int ivx_bs_implied_vol_ladder(int64_t n_t, int64_t period, int64_t n_strike, const double* price, const double* S, const double* K,
@@ -908,12 +1134,23 @@ extern "C" int ivx_bs_implied_vol_ladder(int64_t n_t, int64_t period, int64_t n_
   uint32_t* list = (uint32_t*)((char*)workspace + 256);
   IVX_CUDA(cudaMemsetAsync(slice_flags, 0, (size_t)(n_t * (period / n_strike)) * sizeof(int32_t), stream));
   IVX_CUDA(cudaMemsetAsync(flag_count, 0, 4, stream));
-  const unsigned gx = (unsigned)((period + 255) / 256);
+  const unsigned gx = (unsigned)((period + 255) / 256), gx2 = (unsigned)((period + 511) / 512);
   const int64_t ch = ladder_chunk_stamps(period);
+  // IVX_IV_ONE_QUOTE=1 in the environment keeps the one-quote-per-thread kernel (A/B timing of the two forms; read once; same results)
+  static const bool one_quote = [] { const char* e = getenv("IVX_IV_ONE_QUOTE"); return e && e[0] == '1'; }();
   for (int64_t t0 = 0; t0 < n_t; t0 += ch) {
     const unsigned gy = (unsigned)(n_t - t0 < ch ? n_t - t0 : ch);
     const int64_t o = t0 * period;
     IVX_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
+    if (!one_quote) {
+      k_bs_implied_vol_ladder2<<<dim3(gx2, gy), 256, 0, stream>>>((uint32_t)period, (uint32_t)n_strike, price + o, S + o, K + o, T + o, r + o, is_call + o,
+                                                                sigma + o, x_ladder, slice_flags + t0 * (period / n_strike), flag_count, list, counter);
+      IVX_LAUNCH_CHECK("k_bs_implied_vol_ladder2");
+      k_bs_implied_vol_ladder2_retry<<<(unsigned)(sm_count() * 2), 256, 0, stream>>>(gx2, (uint32_t)period, price + o, S + o, K + o, T + o, r + o, is_call + o,
+                                                                                    sigma + o, list, counter);
+      IVX_LAUNCH_CHECK("k_bs_implied_vol_ladder2_retry");
+      continue;
+    }
     k_bs_implied_vol_ladder<<<dim3(gx, gy), 256, 0, stream>>>((uint32_t)period, (uint32_t)n_strike, price + o, S + o, K + o, T + o, r + o, is_call + o,
                                                              sigma + o, x_ladder, slice_flags + t0 * (period / n_strike), flag_count, list, counter);
     IVX_LAUNCH_CHECK("k_bs_implied_vol_ladder");
