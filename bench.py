@@ -387,14 +387,14 @@ def run_gpu(args):
     except (OSError, ValueError, KeyError):
         pass
     if dom == "implied_vol":
-        # ncu (profiles/ncu_r2_summary.json): 406 warp instructions per 32 quotes, 133 of them fp64; an fp64 instruction holds the
-        # issue port for two cycles on B200 (16 fp64 lanes per SM sub-partition), and 406 + 133 = 539 of the 560 cycles a warp
-        # of quotes takes per sub-partition: the kernel runs at the issue limit of its own instruction stream
+        # ncu at the full day (profiles/ncu_r2_fullday_summary.json): 378 warp instructions per 32 quotes, ~121 of them fp64; an fp64
+        # instruction holds the issue port for two cycles on B200 (16 fp64 lanes per SM sub-partition).  The one-quote-per-thread
+        # form runs AT that limit (406 + 133 = 539 of 560 cycles); the two-quote form has fewer instructions and stalls a little more
         roofline["bound"] = "issue/fp64"
         roofline["hbm_frac"] = roofline["frac"]
-        roofline["limiter"] = ("instruction issue, with fp64 instructions costing two issue cycles each (ncu, profiles/ncu_r2_summary.json: "
-                               "issue slots 77 % busy + the second cycle of the fp64 instructions 24 % = 100 %; fp64 pipe 47 %, DRAM 39 %): "
-                               "406 warp instructions per 32 quotes, 133 of them fp64")
+        roofline["limiter"] = ("instruction issue, with fp64 instructions costing two issue cycles each (ncu at the full day, "
+                               "profiles/ncu_r2_fullday_summary.json: issue slots 74 % busy + the second cycle of the fp64 instructions 24 %; "
+                               "fp64 pipe 47 %, DRAM 43 %): 378 warp instructions per 32 quotes, ~121 of them fp64; 49.0 B per quote moved for 49 algorithmic")
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_r2_summary.json")) as f:
                 for e in json.load(f):
