@@ -270,7 +270,9 @@ __device__ __forceinline__ float guess_table(float x, float lnbeta) {
 
 // x <= 0, 0 < beta < e^{x/2}; s = the table guess; `lower`: the root sits below the inflection point sqrt(2|x|) (objective
 // ln b there, b above).  Returns s after one Householder step.
-__device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta, float ex2, float s, bool lower) {
+template <int LOWER>                                 // 1 / 0: the branch is known at compile time (straight-line code); -1: `lower` decides
+__device__ __forceinline__ float presolve_f32_t(float x, float beta, float lnbeta, float ex2, float s, bool lower) {
+  if (LOWER >= 0) lower = LOWER != 0;
   const float kInvSqrt2 = 0.70710678f, kSqrt2Pi = 2.50662827f;
 #pragma unroll
   for (int it = 0; it < PRE_ITERS; ++it) {
@@ -305,6 +307,9 @@ __device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta,
     s = s + ((fac > 0.3f && fac < 3.0f) ? newton * fac : newton);
   }
   return s;
+}
+__device__ __forceinline__ float presolve_f32(float x, float beta, float lnbeta, float ex2, float s, bool lower) {
+  return presolve_f32_t<-1>(x, beta, lnbeta, ex2, s, lower);
 }
 
 // ---- phase 2: double precision ---------------------------------------------------------------------------
@@ -783,17 +788,25 @@ __device__ __forceinline__ void solve_pair(const QuoteIn& A, const QuoteIn& B, d
                  __hiloint2double(__double2hiint(lx.b) & keepB, __double2loint(lx.b) & keepB)};
   if (okA && !(beta.a < ex2.a)) okA = false;
   if (okB && !(beta.b < ex2.b)) okB = false;
-  // fp32 pre-solve, per quote
-  auto pre = [](double hx_, double beta_, double ex2_) -> float {
-    const float xf = 2.0f * (float)hx_;
+  // fp32 pre-solve: the table guesses are straight-line code (the scheduler interleaves the two quotes by itself); the Halley step
+  // branches on the side of the inflection point — when both quotes sit on the same side (neighbours in a smile nearly always do)
+  // the two steps are instantiated for that side back to back in ONE basic block, so that they interleave as well
+  const float xfA = 2.0f * (float)hx.a, xfB = 2.0f * (float)hx.b;
+  auto lnb = [](double beta_) -> float {
     const int bhi = __double2hiint(beta_);
-    const float lnbeta_f = fmaf((float)(((bhi >> 20) & 0x7ff) - 1023), 0.69314718f,
-                                f_log((float)__hiloint2double((bhi & 0x000fffff) | 0x3ff00000, __double2loint(beta_))));
-    const float s_tab = guess_table(xf, lnbeta_f);
-    const bool lower = s_tab * s_tab < -2.0f * xf;
-    return presolve_f32(xf, (float)beta_, lnbeta_f, (float)ex2_, s_tab, lower);
+    return fmaf((float)(((bhi >> 20) & 0x7ff) - 1023), 0.69314718f, f_log((float)__hiloint2double((bhi & 0x000fffff) | 0x3ff00000, __double2loint(beta_))));
   };
-  const float s0A = pre(hx.a, beta.a, ex2.a), s0B = pre(hx.b, beta.b, ex2.b);
+  const float lnbA = lnb(beta.a), lnbB = lnb(beta.b);
+  const float stA = guess_table(xfA, lnbA), stB = guess_table(xfB, lnbB);
+  const bool lowA = stA * stA < -2.0f * xfA, lowB = stB * stB < -2.0f * xfB;
+  float s0A, s0B;
+  if (lowA == lowB) {
+    if (lowA) { s0A = presolve_f32_t<1>(xfA, (float)beta.a, lnbA, (float)ex2.a, stA, true); s0B = presolve_f32_t<1>(xfB, (float)beta.b, lnbB, (float)ex2.b, stB, true); }
+    else { s0A = presolve_f32_t<0>(xfA, (float)beta.a, lnbA, (float)ex2.a, stA, false); s0B = presolve_f32_t<0>(xfB, (float)beta.b, lnbB, (float)ex2.b, stB, false); }
+  } else {
+    s0A = presolve_f32(xfA, (float)beta.a, lnbA, (float)ex2.a, stA, lowA);
+    s0B = presolve_f32(xfB, (float)beta.b, lnbB, (float)ex2.b, stB, lowB);
+  }
   const bool sokA = s0A >= 1e-30f && s0A < (float)S_MAX, sokB = s0B >= 1e-30f && s0B < (float)S_MAX;
   const D2 s = {sokA ? (double)s0A : 1.0, sokB ? (double)s0B : 1.0};
   // fp64 Halley step, both quotes
