@@ -162,3 +162,22 @@ def test_tz_aware_candles_floor_the_local_wall_clock():
     g["date"] = g["date"].dt.tz_localize("Asia/Kolkata")
     g.loc[0, "iv"] = np.nan
     golden_io.assert_frames_match(RL.reference_interpolate(g), OracleIVInterpolator().interpolate_symbol(g))
+
+
+def test_sparse_underlying_tape_is_a_consistent_ragged_csr():
+    """tapes.make_underlying_tape(drop_frac=...): the replay tape of BASELINE configs[4] — hourly rows missing at random, never a
+    contract's first or last; offsets, stamps and columns stay aligned and every contract stays time-sorted."""
+    import numpy as np
+    from iv_interpolation_b200 import tapes
+    full = tapes.make_underlying_tape(7, 40, 121, nan_frac=0.15)
+    tp = tapes.make_underlying_tape(7, 40, 121, nan_frac=0.15, drop_frac=0.25)
+    n = np.diff(tp.off)
+    assert tp.off[0] == 0 and tp.off[-1] == len(tp.date) and (n >= 2).all() and (n <= 121).all() and 0.6 < n.mean() / 121 < 0.9
+    assert all(len(c) == len(tp.date) for c in tp.cols.values()) and len(tp.symbols) == 40
+    for i in range(40):
+        a, b = int(tp.off[i]), int(tp.off[i + 1])
+        fa, fb = int(full.off[i]), int(full.off[i + 1])
+        assert (np.diff(tp.date[a:b]) > 0).all()
+        assert tp.date[a] == full.date[fa] and tp.date[b - 1] == full.date[fb - 1]          # first and last row kept
+        assert np.isin(tp.date[a:b], full.date[fa:fb]).all()
+    assert np.isnan(tp.cols["iv"]).mean() > 0.1
