@@ -17,9 +17,9 @@ from ._lib import check, lib, ptr_array
 
 _LAUNCHES = 0     # kernels of ours enqueued since the last reset (bench.py reports it)
 
-# kernels each entry point enqueues (memsets are not kernels of ours and are not counted)
+# kernels each entry point enqueues (memsets are not kernels of ours and are not counted); ohlcv_reduce: tile plan, reduce, finalize
 _KERNELS_PER_CALL = {
-    "ohlcv_reduce": 2, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
+    "ohlcv_reduce": 3, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_implied_vol_ladder": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 3, "spline_ladder_factor": 1,
     "spline_band_build": 4, "spline_fit_eval_banded": 2, "spline_fit_eval_banded_mma": 3, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
