@@ -208,6 +208,8 @@ int ivx_bs_greeks(int64_t n, const double* S, const double* K, const double* T, 
  * ivx_spline_strided solves many small systems laid out [knot][system] (system index
  * contiguous): used for the maturity direction of the surface.
  * ------------------------------------------------------------------------------------------- */
+/* The solve keeps its whole state in shared memory and registers: no workspace is needed (the query returns a token 256 and the
+ * workspace arguments below are ignored; they stay in the signatures so that callers written against round 1 keep linking). */
 int64_t ivx_spline_workspace_bytes(int64_t n_slices, int64_t n_knots_total);
 int ivx_spline_fit_eval(int64_t n_slices, const int64_t* knot_off, int64_t max_knots,
                         const double* x, const double* y, int64_t n_q, const double* xq,
