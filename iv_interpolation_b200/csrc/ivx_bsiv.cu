@@ -864,24 +864,29 @@ __global__ void __launch_bounds__(256, 4) k_bs_implied_vol_ladder2(uint32_t peri
   double sg0, sg1;
   bool df0, df1;
   solve_pair(A, B, sg0, sg1, df0, df1);
-  auto finish = [&](bool inr, uint32_t i, double out, double k_, double lad) {
-    if (inr) {
-      st_stream(sigma + i, out);
-      if (((__double2hiint(k_) ^ __double2hiint(lad)) | (__double2loint(k_) ^ __double2loint(lad))) != 0) {   // rare
-        const uint32_t slice = i / n_strike;
-        const uint32_t peers = __match_any_sync(__activemask(), slice);
-        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1) && *((volatile int32_t*)(slice_flags + slice)) == 0 &&
-            atomicExch(slice_flags + slice, 1) == 0)
-          atomicAdd(flag_count, 1u);
-      }
-    }
-  };
-  finish(in0, i0, sg0, A.k_, lad0);
-  finish(in1, i1, sg1, B.k_, lad1);
-  // warp ids of the retry list: ((stamp, 512-block) * 2 + half) * 8 + warp
-  const uint32_t wbase = (blockIdx.y * gridDim.x + blockIdx.x) * 16u + (threadIdx.x >> 5);
-  record_deferred(df0 && in0, wbase, list, counter);
-  record_deferred(df1 && in1, wbase + 8u, list, counter);
+  if (in0) st_stream(sigma + i0, sg0);
+  if (in1) st_stream(sigma + i1, sg1);
+  // strikes against the ladder: both quotes in one test, the flagging itself out of the way (rare)
+  const bool mm0 = in0 && ((__double2hiint(A.k_) ^ __double2hiint(lad0)) | (__double2loint(A.k_) ^ __double2loint(lad0))) != 0;
+  const bool mm1 = in1 && ((__double2hiint(B.k_) ^ __double2hiint(lad1)) | (__double2loint(B.k_) ^ __double2loint(lad1))) != 0;
+  if (mm0 | mm1) {
+    auto flag = [&](uint32_t i) {
+      const uint32_t slice = i / n_strike;
+      const uint32_t peers = __match_any_sync(__activemask(), slice);
+      if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1) && *((volatile int32_t*)(slice_flags + slice)) == 0 &&
+          atomicExch(slice_flags + slice, 1) == 0)
+        atomicAdd(flag_count, 1u);
+    };
+    if (mm0) flag(i0);
+    if (mm1) flag(i1);
+  }
+  // warp ids of the retry list: ((stamp, 512-block) * 2 + half) * 8 + warp; one vote for both halves (deferrals are rare)
+  df0 = df0 && in0; df1 = df1 && in1;
+  if (__any_sync(IVX_FULL_MASK, df0 | df1)) {
+    const uint32_t wbase = (blockIdx.y * gridDim.x + blockIdx.x) * 16u + (threadIdx.x >> 5);
+    record_deferred(df0, wbase, list, counter);
+    record_deferred(df1, wbase + 8u, list, counter);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_bs_implied_vol_ladder2_retry(uint32_t gx, uint32_t period, const double* __restrict__ price,
