@@ -848,7 +848,8 @@ def test_aggregate_to_5min_merges_buckets_of_unsorted_input_like_groupby(dev):
         assert np.array_equal(got[c].to_numpy(), want[c].to_numpy()), c
 
 
-def test_implied_vol_on_presumed_ladders_flags_exactly_the_slices_that_differ(dev):
+@pytest.mark.parametrize("n_t,n_exp,n_strike", [(37, 3, 160), (41, 1, 50), (3, 5, 333)])
+def test_implied_vol_on_presumed_ladders_flags_exactly_the_slices_that_differ(dev, n_t, n_exp, n_strike):
     """ivx_bs_implied_vol_ladder: the same implied vols as the plain solver, bit for bit, and slice_flags / flag_count name exactly
     the slices in which a strike differs from the ladder's (an ulp is enough; NaN strikes differ too) — whole moved ladders (2000
     differing quotes per slice: one count per slice) as well as a single quote.  ivx_spline_fit_eval_banded(x_verified) then takes
@@ -856,8 +857,7 @@ def test_implied_vol_on_presumed_ladders_flags_exactly_the_slices_that_differ(de
     import torch
     from iv_interpolation_b200 import device as D
     rng = np.random.default_rng(11)
-    n_t, n_exp, n_strike = 37, 3, 160
-    period = n_exp * n_strike
+    period = n_exp * n_strike            # 480: partial second half of the 512-quote block; 50: no second half at all; 1665: four blocks
     lad = np.concatenate([3000.0 + np.cumsum(rng.uniform(3.0, 9.0, n_strike)) for _ in range(n_exp)])
     K = np.tile(lad, n_t)
     S = np.repeat(3600.0 * np.exp(rng.normal(0, 0.01, n_t)), period)
@@ -865,13 +865,15 @@ def test_implied_vol_on_presumed_ladders_flags_exactly_the_slices_that_differ(de
     r = np.full(n_t * period, 0.03)
     is_call = (K > S).astype(np.uint8)
     sigma = 0.2 + 0.3 * np.log(K / S) ** 2
-    moved = {5 * n_exp + 1: "ladder", 20 * n_exp + 2: "ulp", 36 * n_exp + 0: "last"}       # slice -> how it differs
+    n_sl = n_t * n_exp
+    moved = {min(5 * n_exp + 1, n_sl - 3) % n_sl: "ladder", (n_sl // 2 + n_exp - 1) % n_sl: "ulp", n_sl - n_exp: "last"}   # slice -> how it differs
+    assert len(moved) == 3
     for sl, how in moved.items():
         a = sl * n_strike
         if how == "ladder":
             K[a:a + n_strike] += 2.5
         elif how == "ulp":
-            K[a + 77] = np.nextafter(K[a + 77], np.inf)
+            K[a + n_strike // 2] = np.nextafter(K[a + n_strike // 2], np.inf)
         else:
             K[a + n_strike - 1] *= 1.001
     price = O.bs_price(S, K, T, r, sigma, is_call)
@@ -897,7 +899,7 @@ def test_implied_vol_on_presumed_ladders_flags_exactly_the_slices_that_differ(de
                                   g(lad), lu, g(got), g(xq), band, max_knots=n_strike, x_own=g(K), fb=flags, x_verified=True)
     yq = yq.cpu().numpy().reshape(n_t * n_exp, -1)
     assert sorted(np.flatnonzero(flags[0].cpu().numpy()).tolist()) == sorted(moved) and int(flags[1].item()) == len(moved)
-    for sl in list(moved) + [0, 7, 50, n_t * n_exp - 2]:
+    for sl in list(moved) + [0, 7 % n_sl, 50 % n_sl, n_sl - 2]:
         a = sl * n_strike
         want = O.natural_spline_eval(K[a:a + n_strike], got[a:a + n_strike], xq, 1)
         assert np.abs(yq[sl] - want).max() <= 1e-8 * max(1.0, np.abs(want).max()), sl
