@@ -273,6 +273,8 @@ int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_off, const 
                                const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
                                const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
                                int32_t slab_knots_hint,
+                               int32_t all_tensor_path /* 1: the caller read ladder_ok back and bit 1 is set for every ladder: the dot-product
+                                                          kernel is not launched at all */,
                                int32_t x_verified /* 1: fb_list / fb_count already hold the verdict of an abscissa comparison done elsewhere
                                                      (ivx_bs_implied_vol_ladder): kept and added to; x_own is then read only by the
                                                      exact solve of the flagged slices */,

@@ -44,8 +44,9 @@ int sm_count();          // of the CURRENT device
 struct DeviceOnce { bool done[IVX_MAX_DEVICES] = {}; };
 bool once_per_device(DeviceOnce& o);
 
-// ivx_spline.cu: exact natural-spline solve of the slices flagged in need[0 .. n_slices) (see k_spline_fit_eval_list)
-int spline_fit_eval_list(int64_t n_slices, const int32_t* need, int64_t max_knots, const int64_t* knot_off, const int64_t* x_off,
+// ivx_spline.cu: exact natural-spline solve of the slices flagged in need[0 .. n_slices) (see k_spline_fit_eval_list);
+// n_need (device, may be NULL): how many are flagged — zero lets every CTA leave at once
+int spline_fit_eval_list(int64_t n_slices, const int32_t* need, const uint32_t* n_need, int64_t max_knots, const int64_t* knot_off, const int64_t* x_off,
                          const double* x, const double* lu_cp, const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder,
                          const double* x_own, const int64_t* ladder_off, const double* y, int n_q, const double* xq, int extrap,
                          double* yq, cudaStream_t stream);

@@ -536,7 +536,8 @@ __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k
 // list visits them in a scattered order: every slice in another DRAM page and TLB entry — measured 1.45x slower).
 template <int G, int SPL_R, int MODE>
 __global__ void __launch_bounds__(SplLayout<G, SPL_R>::BT, (G <= 256 ? 4 : 1)) k_spline_fit_eval_list(int64_t n_slices, const int32_t* __restrict__ need,
-                                                                                                  IVX_SPL_PARAMS) {
+                                                                                                  const uint32_t* __restrict__ n_need, IVX_SPL_PARAMS) {
+  if (n_need && *n_need == 0) return;               // nothing was flagged (the usual day): do not walk 700 000 flags to find that out
   constexpr int SPB = SplLayout<G, SPL_R>::SPB;
   constexpr int BT = SplLayout<G, SPL_R>::BT;
   __shared__ int32_t s_need[BT];
@@ -833,7 +834,7 @@ static int spline_dispatch(int64_t n_slices, const int64_t* knot_off, const int6
 }
 
 template <int G, int SPL_R, int MODE>
-static int launch_spline_list_t(int64_t n_slices, const int32_t* need, const int64_t* knot_off, const int64_t* x_off, const double* x,
+static int launch_spline_list_t(int64_t n_slices, const int32_t* need, const uint32_t* n_need, const int64_t* knot_off, const int64_t* x_off, const double* x,
                                 const double* lu_cp, const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder,
                                 const double* x_own, const int64_t* ladder_off, const double* y, int n_q, const double* xq, int extrap,
                                 double* yq, cudaStream_t stream) {
@@ -841,19 +842,19 @@ static int launch_spline_list_t(int64_t n_slices, const int32_t* need, const int
   static DeviceOnce attr_once;
   if (once_per_device(attr_once)) IVX_CUDA(cudaFuncSetAttribute(k_spline_fit_eval_list<G, SPL_R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
   const unsigned blocks = (unsigned)(sm_count() * (G <= 256 ? 4 : 1));
-  k_spline_fit_eval_list<G, SPL_R, MODE><<<blocks, L::BT, L::SMEM, stream>>>(n_slices, need, IVX_SPL_ARGS);
+  k_spline_fit_eval_list<G, SPL_R, MODE><<<blocks, L::BT, L::SMEM, stream>>>(n_slices, need, n_need, IVX_SPL_ARGS);
   IVX_LAUNCH_CHECK("k_spline_fit_eval_list");
   return IVX_OK;
 }
 
 // the exact solve for the slices flagged in need[]: ladder tables where a slice may use them (MODE 1 when the slices are known
 // to sit on their ladders, MODE 2 when that is verified per slice), the general scan otherwise
-int ivx::spline_fit_eval_list(int64_t n_slices, const int32_t* need, int64_t max_knots, const int64_t* knot_off, const int64_t* x_off,
+int ivx::spline_fit_eval_list(int64_t n_slices, const int32_t* need, const uint32_t* n_need, int64_t max_knots, const int64_t* knot_off, const int64_t* x_off,
                               const double* x, const double* lu_cp, const double* lu_inv, const double* lu_ih, const int32_t* slice_ladder,
                               const double* x_own, const int64_t* ladder_off, const double* y, int n_q, const double* xq, int extrap,
                               double* yq, cudaStream_t stream) {
 #define IVX_SPLL(G, R)                                                                                                                   \
-  return x_own ? launch_spline_list_t<G, R, 2>(n_slices, need, IVX_SPL_ARGS, stream) : launch_spline_list_t<G, R, 1>(n_slices, need, IVX_SPL_ARGS, stream)
+  return x_own ? launch_spline_list_t<G, R, 2>(n_slices, need, n_need, IVX_SPL_ARGS, stream) : launch_spline_list_t<G, R, 1>(n_slices, need, n_need, IVX_SPL_ARGS, stream)
   switch (spline_group_width(max_knots)) {
     case 32: IVX_SPLL(32, 8);
     case 64: IVX_SPLL(64, 8);

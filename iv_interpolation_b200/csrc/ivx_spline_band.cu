@@ -710,7 +710,8 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
                                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                           const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
                                           const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
-                                          int32_t slab_knots_hint, int32_t x_verified, double* yq, int32_t* fb_list, uint32_t* fb_count, ivx_stream_t stream_) {
+                                          int32_t slab_knots_hint, int32_t all_tensor_path, int32_t x_verified, double* yq, int32_t* fb_list, uint32_t* fb_count,
+                                          ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_slices >= 0 && n_slices < ((int64_t)1 << 31) && n_ladders >= 0 && n_ladders < 65536 && max_slices_per_ladder >= 0,
               IVX_ERR_INVALID_ARG, "ivx_spline_fit_eval_banded: bad sizes");
@@ -760,7 +761,9 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
   batch = batch < 4 ? 4 : (batch > BAND_BATCH ? BAND_BATCH : batch);
   P.batch = (int32_t)batch;
   const dim3 grid((unsigned)((max_slices_per_ladder + batch - 1) / batch), (unsigned)n_ladders);
-  if (grid.x > 0) {
+  // all_tensor_path: the caller read ladder_ok back after the build and every ladder has its tensor-path tables — the
+  // dot-product kernel would only launch CTAs that leave at once
+  if (grid.x > 0 && !(P.frag && all_tensor_path)) {
     if (x_check) {
       const size_t smem = (size_t)(2 * BAND_NBUF * BAND_MAXK + 2 * (BAND_MAXQ + 16) + BAND_MAXK) * sizeof(double);
       static DeviceOnce once;
@@ -775,6 +778,6 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
     IVX_LAUNCH_CHECK("k_band_apply");
   }
   // whatever the banded kernel listed: the exact solve (ladder tables where a slice may use them), same stream
-  return spline_fit_eval_list(n_slices, fb_list, max_knots, knot_off, x_off, x_ladder, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y,
+  return spline_fit_eval_list(n_slices, fb_list, fb_count, max_knots, knot_off, x_off, x_ladder, lu_cp, lu_inv, lu_ih, slice_ladder, x_own, ladder_off, y,
                               (int)n_q, xq, extrap, yq, stream);
 }

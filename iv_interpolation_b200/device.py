@@ -491,6 +491,7 @@ class SplineBand:
     frag: Optional[torch.Tensor] = None   # float64: the weights as fp64 mma B fragments per group of 8 grid points (tensor-path form)
     oct: Optional[torch.Tensor] = None    # int32: first knot and step count per group, then {largest slab extent, largest step count} per ladder
     slab_knots: int = 0                   # largest number of knots a 64-point slab touches (read back once per build; 0 = unknown)
+    all_tensor_path: bool = False         # every ladder has usable tensor-path tables (read back with slab_knots)
 
 
 def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torch.Tensor, *, extrap: int = 1,
@@ -515,6 +516,7 @@ def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torc
         # builds into the same object (a column rewritten in place, a streaming pipeline's next chunk) keep the figure and stay
         # asynchronous; should a slab then need more, the kernel sees it and hands the batch to the exact solve — slower, never wrong.
         out.slab_knots = int(out.oct[n_l * 128:].view(n_l, 2)[:, 0].max().item())
+        out.all_tensor_path = bool(((out.ok & 2) != 0).all().item())
     return out
 
 
@@ -546,7 +548,7 @@ def spline_fit_eval_banded(knot_off: torch.Tensor, x_off: torch.Tensor, slice_la
                                            _ptr(x_own) if x_own is not None else None, _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q,
                                            _ptr(xq), int(band.extrap), _ptr(band.k0), _ptr(band.w), _ptr(band.ok), _ptr(band.perm),
                                            _ptr(band.frag) if use_mma else None, _ptr(band.oct) if use_mma else None, int(band.slab_knots),
-                                           1 if x_verified else 0, _ptr(yq), _ptr(fb[0]), _ptr(fb[1]), _stream()), "ivx_spline_fit_eval_banded")
+                                           1 if (use_mma and band.all_tensor_path) else 0, 1 if x_verified else 0, _ptr(yq), _ptr(fb[0]), _ptr(fb[1]), _stream()), "ivx_spline_fit_eval_banded")
     _count("spline_fit_eval_banded_mma" if use_mma else "spline_fit_eval_banded")
     return yq
 
