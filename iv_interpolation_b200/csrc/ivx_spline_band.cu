@@ -43,7 +43,7 @@ constexpr int BAND_BATCH = 48;              // slices per CTA at most: the 200 K
 constexpr int MMA_KS = 24;                  // k-steps of 4 knots per 8-point group at most (96 knots): B fragments held in 48 registers
 constexpr int MMA_OCT = BAND_MAXQ / 8;      // 64 groups of 8 grid points
 constexpr int MMA_SLAB_MAX = 512;           // knots a 64-point CTA may touch
-constexpr int MMA_BATCH = 128;              // slices per CTA (16 tiles of 8): the 48 KB of fragments are read once per batch
+constexpr int MMA_BATCH = 256;              // slices per CTA (32 tiles of 8): the 48 KB of fragments are read once per batch
 constexpr int LADDER_OK_BAND = 1, LADDER_OK_MMA = 2;   // bits of ladder_ok
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -521,8 +521,13 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
   const bool st0 = q0 < n_q, st1 = q0 + 1 < n_q;
   const bool nan0 = st0 && P.band_k0[(int64_t)l * n_q + q0] < 0, nan1 = st1 && P.band_k0[(int64_t)l * n_q + q0 + 1] < 0;
   const bool vec_out = P.vec_ok && st1;                       // 16-byte stores (n_q even, yq aligned)
-  // zero both stages once (cp.async never writes past nvalid), ladder abscissae of the slab
-  for (int i = threadIdx.x; i < (VERIFY ? 2 : 1) * NST * 8 * ROW; i += 256) ybuf[i] = 0.0;
+  // zero the tail of every staged row once (cp.async never writes past nvalid, and the multiply reads up to 31 knots past the slab
+  // against zero fragments: those knots must be finite); what lies below nvalid is overwritten by every tile — a row that never
+  // receives a slice keeps whatever it held, feeds only its own outputs and is not stored
+  for (int i = threadIdx.x; i < (VERIFY ? 2 : 1) * NST * 8 * (ROW - (nvalid & ~1)); i += 256) {
+    const int row = i / (ROW - (nvalid & ~1)), k = (nvalid & ~1) + i % (ROW - (nvalid & ~1));
+    ybuf[row * ROW + k] = 0.0;
+  }
   if (VERIFY)
     for (int k = threadIdx.x; k < ROW; k += 256) ladx[k] = k < nvalid ? __ldg(P.x_ladder + P.ladder_off[l] + KB + k) : 0.0;
   __syncthreads();
