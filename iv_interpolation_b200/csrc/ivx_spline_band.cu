@@ -43,7 +43,7 @@ constexpr int BAND_BATCH = 48;              // slices per CTA at most: the 200 K
 constexpr int MMA_KS = 24;                  // k-steps of 4 knots per 8-point group at most (96 knots): B fragments held in 48 registers
 constexpr int MMA_OCT = BAND_MAXQ / 8;      // 64 groups of 8 grid points
 constexpr int MMA_SLAB_MAX = 512;           // knots a 64-point CTA may touch
-constexpr int MMA_BATCH = 256;              // slices per CTA (32 tiles of 8): the 48 KB of fragments are read once per batch
+constexpr int MMA_BATCH = 512;              // slices per CTA (64 tiles of 8): the 48 KB of fragments are read once per batch
 constexpr int LADDER_OK_BAND = 1, LADDER_OK_MMA = 2;   // bits of ladder_ok
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -487,11 +487,11 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
       s_klast = ol >= 0 ? min(n, octl[ol * 2] + 4 * octl[ol * 2 + 1]) : n;
     }
   }
-  if (threadIdx.x < ns) {
-    const int32_t sl = ord[threadIdx.x];
+  for (int i = threadIdx.x; i < ns; i += 256) {
+    const int32_t sl = ord[i];
     const int64_t ko = P.knot_off[sl];
-    s_id[threadIdx.x] = sl;
-    s_base[threadIdx.x] = ((P.knot_off[sl + 1] - ko) == (int64_t)n && !(P.preflag && P.fb_list[sl] != 0)) ? ko : (int64_t)-1;
+    s_id[i] = sl;
+    s_base[i] = ((P.knot_off[sl + 1] - ko) == (int64_t)n && !(P.preflag && P.fb_list[sl] != 0)) ? ko : (int64_t)-1;
   }
   __syncthreads();
   int KB = INT32_MAX, KE = 0;
