@@ -387,14 +387,14 @@ def run_gpu(args):
     except (OSError, ValueError, KeyError):
         pass
     if dom == "implied_vol":
-        # ncu at the full day (profiles/ncu_r2_fullday_summary.json): 378 warp instructions per 32 quotes, ~121 of them fp64; an fp64
+        # ncu at the full day (profiles/ncu_r2_fullday_summary.json): 369 warp instructions per 32 quotes, ~121 of them fp64; an fp64
         # instruction holds the issue port for two cycles on B200 (16 fp64 lanes per SM sub-partition).  The one-quote-per-thread
         # form runs AT that limit (406 + 133 = 539 of 560 cycles); the two-quote form has fewer instructions and stalls a little more
         roofline["bound"] = "issue/fp64"
         roofline["hbm_frac"] = roofline["frac"]
         roofline["limiter"] = ("instruction issue, with fp64 instructions costing two issue cycles each (ncu at the full day, "
-                               "profiles/ncu_r2_fullday_summary.json: issue slots 74 % busy + the second cycle of the fp64 instructions 24 %; "
-                               "fp64 pipe 47 %, DRAM 43 %): 378 warp instructions per 32 quotes, ~121 of them fp64; 49.0 B per quote moved for 49 algorithmic")
+                               "profiles/ncu_r2_fullday_summary.json: issue slots 73 % busy + the second cycle of the fp64 instructions 24 %; "
+                               "fp64 pipe 48 %, DRAM 44 %): 369 warp instructions per 32 quotes, ~121 of them fp64; 49.0 B per quote moved for 49 algorithmic")
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_r2_summary.json")) as f:
                 for e in json.load(f):
