@@ -265,13 +265,23 @@ int64_t ivx_spline_band_oct_len(int64_t n_ladders);    /* int32 of band_oct */
 int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
                           int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok,
                           int16_t* band_perm /* n_ladders*512: which grid point each thread of the evaluation takes */,
-                          double* band_frag, int32_t* band_oct, ivx_stream_t stream);
+                          double* band_frag, int32_t* band_oct,
+                          double* band_fill_w /* ivx_spline_band_fill_len(knots of all ladders) doubles, or NULL */,
+                          int32_t* band_fill_k0 /* one per ladder knot, or NULL */, ivx_stream_t stream);
+/* band_fill_w / band_fill_k0 (both or neither): one more row per interior ladder knot m — the weights of "fit the natural spline
+ * through the ladder WITHOUT knot m and evaluate it at x[m]".  The spline through a slice's quoted knots is also a spline on the
+ * full ladder, so a slice with a MISSING quote (NaN) stays on the banded path: the tensor-path kernel fills the gap with that
+ * 48-term row and goes on.  Rows are checked against the full solve when they are built (ladder_ok bit 2); a slice takes the
+ * exact solve after all when another missing knot lies inside the row's window, the knot is within 24 of an end, or a value is
+ * infinite. */
+int64_t ivx_spline_band_fill_len(int64_t n_ladder_knots);
 int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_off, const int64_t* x_off, const int32_t* slice_ladder,
                                const int32_t* order, const int64_t* lad_slice_off, int64_t n_ladders, int64_t max_slices_per_ladder,
                                const int64_t* ladder_off, int64_t max_knots, const double* x_ladder, const double* x_own /*or NULL*/,
                                const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
                                const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
+                               const double* band_fill_w, const int32_t* band_fill_k0 /* both or NULL */,
                                int32_t slab_knots_hint,
                                int32_t all_tensor_path /* 1: the caller read ladder_ok back and bit 1 is set for every ladder: the dot-product
                                                           kernel is not launched at all */,

@@ -65,9 +65,10 @@ SIGNATURES = {
     "ivx_spline_band_len": (_i64, [_i64, _i64]),
     "ivx_spline_band_frag_len": (_i64, [_i64]),
     "ivx_spline_band_oct_len": (_i64, [_i64]),
-    "ivx_spline_band_build": (C.c_int, [_i64, _p, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "ivx_spline_band_fill_len": (_i64, [_i64]),
+    "ivx_spline_band_build": (C.c_int, [_i64, _p, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ivx_spline_fit_eval_banded": (C.c_int, [_i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _i32, _p, _p, _p,
-                                             _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
+                                             _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "ivx_bs_implied_vol_ladder_workspace_bytes": (_i64, [_i64, _i64]),
     "ivx_bs_implied_vol_ladder": (C.c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_bs_implied_vol_chain_ticks": (C.c_int, [_i64, _i64, _i64, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),

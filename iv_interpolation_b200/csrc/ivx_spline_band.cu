@@ -44,7 +44,9 @@ constexpr int MMA_KS = 24;                  // k-steps of 4 knots per 8-point gr
 constexpr int MMA_OCT = BAND_MAXQ / 8;      // 64 groups of 8 grid points
 constexpr int MMA_SLAB_MAX = 512;           // knots a 64-point CTA may touch
 constexpr int MMA_BATCH = 512;              // slices per CTA (64 tiles of 8): the 48 KB of fragments are read once per batch
-constexpr int LADDER_OK_BAND = 1, LADDER_OK_MMA = 2;   // bits of ladder_ok
+constexpr int LADDER_OK_BAND = 1, LADDER_OK_MMA = 2, LADDER_OK_FILL = 4;   // bits of ladder_ok
+constexpr int FILL_MARGIN = 24;             // knots closer than this to an end of the ladder are not filled (the slice takes the exact solve)
+constexpr int FILL_SAMPLES = 32;            // fill rows per ladder checked against the full solve
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -54,6 +56,56 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- build ---------------------------------------------------------------------------------------------------------
+// The 48 weights (and their first knot k0) of "fit the natural spline through (X(i), y[i]), i < n, and evaluate it at xv", for
+// xv inside [X(0), X(n-1)] or extrapolated along the end cubic: the two local Thomas solves around the bracket of xv.
+// X is an accessor, so that the same code serves a ladder (k_band_build) and a ladder with one knot left out (k_band_fill_build).
+template <class XA>
+__device__ __forceinline__ void band_row(const XA& X, int n, double xv, double* __restrict__ w, int& k0_out) {
+  // bracket: largest i with X(i) <= xv, clamped to a segment
+  int lo_ = 0, hi_ = n;
+  while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (X(mid) <= xv) lo_ = mid + 1; else hi_ = mid; }
+  int i0 = lo_ - 1;
+  i0 = i0 < 0 ? 0 : (i0 > n - 2 ? n - 2 : i0);
+  const int lo = max(1, i0 - BAND_L), hi = min(n - 2, i0 + 1 + BAND_L);   // interior equations kept
+  const int m = hi - lo + 1;                            // <= 2 BAND_L + 2; n >= 48 -> m >= 1
+  double cp[2 * BAND_L + 2], z1[2 * BAND_L + 2], z2[2 * BAND_L + 2];
+  {
+    double cprev = 0.0, d1 = 0.0, d2 = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const int i = lo + j;
+      const double hm = X(i) - X(i - 1), hp = X(i + 1) - X(i);
+      const double inv = 1.0 / (2.0 * (hm + hp) - hm * cprev);
+      cprev = hp * inv;
+      d1 = ((i == i0 ? 1.0 : 0.0) - hm * d1) * inv;
+      d2 = ((i == i0 + 1 ? 1.0 : 0.0) - hm * d2) * inv;
+      cp[j] = cprev; z1[j] = d1; z2[j] = d2;
+    }
+    double m1 = 0.0, m2 = 0.0;
+    for (int j = m - 1; j >= 0; --j) {
+      m1 = z1[j] - cp[j] * m1; m2 = z2[j] - cp[j] * m2;
+      z1[j] = m1; z2[j] = m2;
+    }
+  }
+  const double hseg = X(i0 + 1) - X(i0);
+  const double ta = (X(i0 + 1) - xv) / hseg, tb = (xv - X(i0)) / hseg;
+  const double C = (ta * ta * ta - ta) * hseg * hseg * (1.0 / 6.0), D = (tb * tb * tb - tb) * hseg * hseg * (1.0 / 6.0);
+  int k0 = lo - 1;
+  k0 = k0 < 0 ? 0 : (k0 > n - BAND_W ? n - BAND_W : k0);
+  k0_out = k0;
+  auto zc = [&](int i) -> double { return (i >= lo && i <= hi) ? fma(C, z1[i - lo], D * z2[i - lo]) : 0.0; };   // C z_i0 + D z_{i0+1} at row i
+  for (int k = lo - 1; k <= hi + 1; ++k) {
+    // d/dy[k] of sum_i zc(i) r[i],  r[i] = 6 ((y[i+1]-y[i])/h[i] - (y[i]-y[i-1])/h[i-1]),  h[i] = X(i+1)-X(i)
+    double v = 0.0;
+    if (k >= 1) v += zc(k - 1) / (X(k) - X(k - 1));                                       // row k-1: + y[k]/h[k-1]
+    if (k >= 1 && k <= n - 2) v -= zc(k) * (1.0 / (X(k) - X(k - 1)) + 1.0 / (X(k + 1) - X(k)));
+    if (k <= n - 2) v += zc(k + 1) / (X(k + 1) - X(k));                                   // row k+1: + y[k]/h[k]
+    v *= 6.0;
+    if (k == i0) v += ta;
+    if (k == i0 + 1) v += tb;
+    w[k - k0] = v;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_band_build(int32_t n_ladders, const int64_t* __restrict__ ladder_off, const double* __restrict__ x,
                                                     int32_t n_q, const double* __restrict__ xq, int32_t extrap,
                                                     int32_t* __restrict__ band_k0, double* __restrict__ band_w, uint8_t* __restrict__ ladder_ok) {
@@ -87,49 +139,9 @@ __global__ void __launch_bounds__(128) k_band_build(int32_t n_ladders, const int
     *k0p = k0; w[kk - k0] = 1.0;
     return;
   }
-  // bracket: largest i with X[i] <= xv, clamped to a segment
-  int lo_ = 0, hi_ = n;
-  while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (X[mid] <= xv) lo_ = mid + 1; else hi_ = mid; }
-  int i0 = lo_ - 1;
-  i0 = i0 < 0 ? 0 : (i0 > n - 2 ? n - 2 : i0);
-  const int lo = max(1, i0 - BAND_L), hi = min(n - 2, i0 + 1 + BAND_L);   // interior equations kept
-  const int m = hi - lo + 1;                            // <= 2 BAND_L + 2; n >= 48 -> m >= 1
-  double cp[2 * BAND_L + 2], z1[2 * BAND_L + 2], z2[2 * BAND_L + 2];
-  {
-    double cprev = 0.0, d1 = 0.0, d2 = 0.0;
-    for (int j = 0; j < m; ++j) {
-      const int i = lo + j;
-      const double hm = X[i] - X[i - 1], hp = X[i + 1] - X[i];
-      const double inv = 1.0 / (2.0 * (hm + hp) - hm * cprev);
-      cprev = hp * inv;
-      d1 = ((i == i0 ? 1.0 : 0.0) - hm * d1) * inv;
-      d2 = ((i == i0 + 1 ? 1.0 : 0.0) - hm * d2) * inv;
-      cp[j] = cprev; z1[j] = d1; z2[j] = d2;
-    }
-    double m1 = 0.0, m2 = 0.0;
-    for (int j = m - 1; j >= 0; --j) {
-      m1 = z1[j] - cp[j] * m1; m2 = z2[j] - cp[j] * m2;
-      z1[j] = m1; z2[j] = m2;
-    }
-  }
-  const double hseg = X[i0 + 1] - X[i0];
-  const double ta = (X[i0 + 1] - xv) / hseg, tb = (xv - X[i0]) / hseg;
-  const double C = (ta * ta * ta - ta) * hseg * hseg * (1.0 / 6.0), D = (tb * tb * tb - tb) * hseg * hseg * (1.0 / 6.0);
-  int k0 = lo - 1;
-  k0 = k0 < 0 ? 0 : (k0 > n - BAND_W ? n - BAND_W : k0);
+  int k0;
+  band_row([&](int i) { return X[i]; }, n, xv, w, k0);
   *k0p = k0;
-  auto zc = [&](int i) -> double { return (i >= lo && i <= hi) ? fma(C, z1[i - lo], D * z2[i - lo]) : 0.0; };   // C z_i0 + D z_{i0+1} at row i
-  for (int k = lo - 1; k <= hi + 1; ++k) {
-    // d/dy[k] of sum_i zc(i) r[i],  r[i] = 6 ((y[i+1]-y[i])/h[i] - (y[i]-y[i-1])/h[i-1]),  h[i] = X[i+1]-X[i]
-    double v = 0.0;
-    if (k >= 1) v += zc(k - 1) / (X[k] - X[k - 1]);                                       // row k-1: + y[k]/h[k-1]
-    if (k >= 1 && k <= n - 2) v -= zc(k) * (1.0 / (X[k] - X[k - 1]) + 1.0 / (X[k + 1] - X[k]));
-    if (k <= n - 2) v += zc(k + 1) / (X[k + 1] - X[k]);                                   // row k+1: + y[k]/h[k]
-    v *= 6.0;
-    if (k == i0) v += ta;
-    if (k == i0 + 1) v += tb;
-    w[k - k0] = v;
-  }
 }
 
 // ---- exactness check: two probe vectors per ladder, banded against the full Thomas solve -------------------------------
@@ -196,6 +208,73 @@ __global__ void __launch_bounds__(256) k_band_check(const int64_t* __restrict__ 
   }
   __syncthreads();
   if (threadIdx.x == 0 && bad) ladder_ok[l] = 0;
+}
+
+// ---- missing knots ------------------------------------------------------------------------------------------------------
+// A slice with a missing quote has the natural spline through its OTHER knots.  That spline is also a natural spline on the full
+// ladder (its third derivative simply does not jump at the missing knot), so it equals W y~ with y~ = y at the quoted knots and
+// y~[m] = the value at x[m] of the spline through the others — and THAT is one more row of the same kind: the weights of
+// "fit through the ladder without knot m, evaluate at x[m]" (band_row on an accessor that skips m).  A missing knot is thus
+// FILLED by a 48-term dot product and the slice stays on the banded path.  Exact up to the band's own 1e-12 as long as no other
+// missing knot lies inside the 48-knot window (then the slice is flagged for the exact solve, as before); knots within
+// FILL_MARGIN of an end are not filled either (a missing end knot changes where the spline is extrapolated).
+// fill_k0[a0 + m] = first knot of row m in the indices of the ladder WITHOUT m (-1: no row), fill_w[(a0 + m) * 48 ..] its weights.
+__global__ void __launch_bounds__(128) k_band_fill_build(const int64_t* __restrict__ ladder_off, const double* __restrict__ x,
+                                                         uint8_t* __restrict__ ladder_ok, int32_t* __restrict__ fill_k0, double* __restrict__ fill_w) {
+  const int l = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t a0 = ladder_off[l];
+  const int n = (int)(ladder_off[l + 1] - a0);
+  if (m >= n) return;
+  const double* __restrict__ X = x + a0;
+  double* __restrict__ w = fill_w + (a0 + m) * BAND_W;
+  for (int j = 0; j < BAND_W; ++j) w[j] = 0.0;
+  fill_k0[a0 + m] = -1;
+  const bool usable = (ladder_ok[l] & LADDER_OK_BAND) && n - 1 >= BAND_W;
+  if (m == 0 && usable) ladder_ok[l] |= LADDER_OK_FILL;          // k_band_fill_check may still clear it
+  if (!usable || m < FILL_MARGIN || m > n - 1 - FILL_MARGIN) return;
+  int k0;
+  band_row([&](int i) { return X[i + (i >= m ? 1 : 0)]; }, n - 1, X[m], w, k0);
+  fill_k0[a0 + m] = k0;
+}
+
+// FILL_SAMPLES rows per ladder against the full Thomas solve of the ladder without that knot, two probe vectors each
+__global__ void __launch_bounds__(64) k_band_fill_check(const int64_t* __restrict__ ladder_off, const double* __restrict__ x,
+                                                        const int32_t* __restrict__ fill_k0, const double* __restrict__ fill_w,
+                                                        uint8_t* __restrict__ ladder_ok) {
+  __shared__ double sM[BAND_MAXK], scp[BAND_MAXK];
+  const int l = blockIdx.y;
+  if (!(ladder_ok[l] & LADDER_OK_FILL) || threadIdx.x != 0) return;
+  const int64_t a0 = ladder_off[l];
+  const int n = (int)(ladder_off[l + 1] - a0), nr = n - 1;
+  const int span = n - 1 - 2 * FILL_MARGIN;
+  if (span < 0) return;
+  const int m = FILL_MARGIN + (int)(((int64_t)blockIdx.x * span) / (FILL_SAMPLES - 1));
+  const double* __restrict__ X = x + a0;
+  auto XR = [&](int i) { return X[i + (i >= m ? 1 : 0)]; };
+  const int k0 = fill_k0[a0 + m];
+  bool bad = k0 < 0;
+  for (int which = 0; which < 2 && !bad; ++which) {
+    auto sy = [&](int k) { return probe_value(k, which); };       // values at the knots of the REDUCED ladder
+    double cprev = 0.0, dprev = 0.0;
+    sM[0] = 0.0; sM[nr - 1] = 0.0;
+    for (int i = 1; i <= nr - 2; ++i) {
+      const double hm = XR(i) - XR(i - 1), hp = XR(i + 1) - XR(i);
+      const double inv = 1.0 / (2.0 * (hm + hp) - hm * cprev);
+      cprev = hp * inv;
+      dprev = (6.0 * ((sy(i + 1) - sy(i)) / hp - (sy(i) - sy(i - 1)) / hm) - hm * dprev) * inv;
+      scp[i] = cprev; sM[i] = dprev;
+    }
+    double M = 0.0;
+    for (int i = nr - 2; i >= 1; --i) { M = sM[i] - scp[i] * M; sM[i] = M; }
+    const int i0 = m - 1;                                          // x[m] lies between the reduced knots m-1 and m
+    const double xv = X[m], h = XR(i0 + 1) - XR(i0), A = XR(i0 + 1) - xv, B = xv - XR(i0);
+    const double exact = (sM[i0] * A * A * A + sM[i0 + 1] * B * B * B) / (6.0 * h) + (sy(i0) / h - sM[i0] * h / 6.0) * A + (sy(i0 + 1) / h - sM[i0 + 1] * h / 6.0) * B;
+    double got = 0.0;
+    for (int j = 0; j < BAND_W; ++j) got = fma(fill_w[(a0 + m) * BAND_W + j], sy(k0 + j), got);
+    if (!(fabs(got - exact) <= 2e-12 * (1.0 + fabs(exact)))) bad = true;
+  }
+  if (bad) ladder_ok[l] &= (uint8_t)~LADDER_OK_FILL;             // (several samples may clear the same bit: same value)
 }
 
 // ---- which grid point each thread of k_band_apply takes ------------------------------------------------------------------
@@ -302,6 +381,8 @@ struct BandParams {
   const int32_t* oct;            // [n_ladders][64][2] first knot and step count of every 8-point group
   int32_t row;                   // doubles per staged slice row (slab extent + padding), = 4 mod 16
   int32_t vec_ok;                // n_q even and yq 16-byte aligned
+  const double* fill_w;          // missing-knot rows (k_band_fill_build) or NULL: a slice with a missing knot is flagged
+  const int32_t* fill_k0;
   int32_t preflag;               // fb_list already flags slices that must take the exact solve (x verified by the caller): honoured, not cleared
 };
 
@@ -505,6 +586,8 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
     return;
   }
   const int nvalid = min(klen, n - KB);                      // knots of the slab that exist; the rest of the row stays 0
+  const int64_t lad_a0 = P.ladder_off[l];
+  const bool fill_on = P.fill_w != nullptr && (P.ladder_ok[l] & LADDER_OK_FILL) != 0;
   // this slab's share of the knots no slab stages: [0, kfirst) and [klast, n), dealt evenly
   const int kfirst = s_kfirst, klast = s_klast;
   const int n_out = kfirst + (n - klast), per = (n_out + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -588,13 +671,13 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
       uint32_t bad = 0;
       if (ko >= 0) {
         if (has_out) {
-          bad |= ((uint32_t)__double2hiint(ey) & 0x7ff00000u) == 0x7ff00000u;
+          if (!fill_on) bad |= ((uint32_t)__double2hiint(ey) & 0x7ff00000u) == 0x7ff00000u;   // (no window reaches such a knot: with the fill rows a gap there is nobody's business)
           if (VERIFY) bad |= (uint32_t)((__double2hiint(ex) ^ __double2hiint(out_lx)) | (__double2loint(ex) ^ __double2loint(out_lx)));
         }
         for (int i = out_lo + lane + 32; i < out_hi; i += 32) {
           const int k = i < kfirst ? i : klast + (i - kfirst);
           const double yv = __ldg(P.y + ko + k);
-          bad |= ((uint32_t)__double2hiint(yv) & 0x7ff00000u) == 0x7ff00000u;
+          if (!fill_on) bad |= ((uint32_t)__double2hiint(yv) & 0x7ff00000u) == 0x7ff00000u;
           if (VERIFY) {
             const double xv = __ldg(P.x_own + ko + k), lv = __ldg(P.x_ladder + P.ladder_off[l] + k);
             bad |= (uint32_t)((__double2hiint(xv) ^ __double2hiint(lv)) | (__double2loint(xv) ^ __double2loint(lv)));
@@ -619,7 +702,50 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
                               (__double2hiint(xv.y) ^ __double2hiint(lv.y)) | (__double2loint(xv.y) ^ __double2loint(lv.y)));
           }
         }
-        bad |= emax == 0x7ff00000u;
+        bool nonfin = emax == 0x7ff00000u;
+        if (fill_on && __any_sync(IVX_FULL_MASK, nonfin)) {
+          // a missing quote (NaN) in the staged row: filled by its 48-term row over the slice's other knots (straight from global
+          // memory: the window may reach outside the slab); anything the rows cannot take — an infinity, a knot near an end, another
+          // missing knot inside the window — leaves the slice to the exact solve
+          bool row_bad = false;
+          double* ybw = ybuf + (buf * 8 + w) * ROW;
+          for (int r = 0; r < NIT / 2; ++r) {
+            const int c = lane + 32 * r;
+            const double2 yv = yb[c];
+#pragma unroll
+            for (int comp = 0; comp < 2; ++comp) {
+              const double v = comp ? yv.y : yv.x;
+              uint32_t mask = __ballot_sync(IVX_FULL_MASK, ((uint32_t)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u);
+              while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int k = 2 * (src + 32 * r) + comp, m = KB + k;
+                const double cur = ybw[k];                       // broadcast
+                const int k0f = (k < nvalid && isnan(cur)) ? __ldg(P.fill_k0 + lad_a0 + m) : -1;
+                if (k0f < 0) { row_bad = true; continue; }
+                const double* __restrict__ fw = P.fill_w + (lad_a0 + m) * BAND_W;
+                double acc = 0.0;
+                bool fin = true;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                  const int j = lane + 32 * rr;
+                  if (j < BAND_W) {
+                    const int xi = k0f + j;
+                    const double yy = __ldg(P.y + ko + xi + (xi >= m ? 1 : 0));
+                    fin = fin && (((uint32_t)__double2hiint(yy) & 0x7ff00000u) != 0x7ff00000u);
+                    acc = fma(__ldg(fw + j), yy, acc);
+                  }
+                }
+                if (!__all_sync(IVX_FULL_MASK, fin)) { row_bad = true; continue; }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(IVX_FULL_MASK, acc, d);
+                if (lane == 0) ybw[k] = acc;
+              }
+            }
+          }
+          nonfin = row_bad;
+        }
+        bad |= nonfin;
       }
       const bool ok = (ko >= 0) && __all_sync(IVX_FULL_MASK, bad == 0);
       if (lane == 0) {
@@ -684,9 +810,15 @@ extern "C" int64_t ivx_spline_band_oct_len(int64_t n_ladders) {
   return n_ladders * (MMA_OCT * 2 + 2);
 }
 
+// doubles of band_fill_w for ladders with n_ladder_knots knots in all (band_fill_k0: one int32 per knot)
+extern "C" int64_t ivx_spline_band_fill_len(int64_t n_ladder_knots) {
+  if (n_ladder_knots < 0) return -1;
+  return n_ladder_knots * BAND_W;
+}
+
 extern "C" int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_off, const double* x_ladder, int64_t n_q, const double* xq,
                                      int32_t extrap, int32_t* band_k0, double* band_w, uint8_t* ladder_ok, int16_t* band_perm,
-                                     double* band_frag, int32_t* band_oct, ivx_stream_t stream_) {
+                                     double* band_frag, int32_t* band_oct, double* band_fill_w, int32_t* band_fill_k0, ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_ladders >= 0 && n_ladders < 65536 && n_q >= 0 && n_q < ((int64_t)1 << 30), IVX_ERR_INVALID_ARG, "ivx_spline_band_build: bad sizes");
   IVX_REQUIRE(extrap >= 0 && extrap <= 2, IVX_ERR_INVALID_ARG, "ivx_spline_band_build: extrap must be 0, 1 or 2");
@@ -705,6 +837,13 @@ extern "C" int ivx_spline_band_build(int64_t n_ladders, const int64_t* ladder_of
                                                           band_oct + n_ladders * MMA_OCT * 2);
       IVX_LAUNCH_CHECK("k_band_frag");
     }
+    if (band_fill_w && band_fill_k0) {
+      // ladders hold at most BAND_MAXK knots where the band is usable; longer ones have no band and their threads return at once
+      k_band_fill_build<<<dim3((BAND_MAXK + 127) / 128, (unsigned)n_ladders), 128, 0, stream>>>(ladder_off, x_ladder, ladder_ok, band_fill_k0, band_fill_w);
+      IVX_LAUNCH_CHECK("k_band_fill_build");
+      k_band_fill_check<<<dim3(FILL_SAMPLES, (unsigned)n_ladders), 64, 0, stream>>>(ladder_off, x_ladder, band_fill_k0, band_fill_w, ladder_ok);
+      IVX_LAUNCH_CHECK("k_band_fill_check");
+    }
   }
   return IVX_OK;
 }
@@ -715,7 +854,7 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
                                           const double* lu_cp, const double* lu_inv, const double* lu_ih, const double* y, int64_t n_q,
                                           const double* xq, int32_t extrap, const int32_t* band_k0, const double* band_w,
                                           const uint8_t* ladder_ok, const int16_t* band_perm, const double* band_frag, const int32_t* band_oct,
-                                          int32_t slab_knots_hint, int32_t all_tensor_path, int32_t x_verified, double* yq, int32_t* fb_list, uint32_t* fb_count,
+                                          const double* band_fill_w, const int32_t* band_fill_k0, int32_t slab_knots_hint, int32_t all_tensor_path, int32_t x_verified, double* yq, int32_t* fb_list, uint32_t* fb_count,
                                           ivx_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   IVX_REQUIRE(n_slices >= 0 && n_slices < ((int64_t)1 << 31) && n_ladders >= 0 && n_ladders < 65536 && max_slices_per_ladder >= 0,
@@ -735,6 +874,7 @@ extern "C" int ivx_spline_fit_eval_banded(int64_t n_slices, const int64_t* knot_
   P.knot_off = knot_off; P.order = order; P.lad_slice_off = lad_slice_off; P.ladder_off = ladder_off; P.x_ladder = x_ladder; P.x_own = x_check;
   P.preflag = x_verified ? 1 : 0;
   P.y = y; P.band_k0 = band_k0; P.band_w = band_w; P.ladder_ok = ladder_ok; P.perm = band_perm; P.yq = yq; P.fb_list = fb_list; P.fb_count = fb_count; P.n_q = (int32_t)n_q;
+  P.fill_w = (band_fill_w && band_fill_k0) ? band_fill_w : nullptr; P.fill_k0 = band_fill_k0;
   P.frag = band_frag; P.oct = band_oct; P.row = 0; P.vec_ok = ((n_q & 1) == 0 && ((uintptr_t)yq & 15u) == 0) ? 1 : 0;
   if (band_frag) {
     // tensor-path form for the ladders whose tables allow it (LADDER_OK_MMA); k_band_apply below skips those.  A row holds the

@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 3, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_implied_vol_ladder": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 3, "spline_ladder_factor": 1,
-    "spline_band_build": 4, "spline_fit_eval_banded": 2, "spline_fit_eval_banded_mma": 3, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
+    "spline_band_build": 6, "spline_fit_eval_banded": 2, "spline_fit_eval_banded_mma": 3, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
 
@@ -492,10 +492,13 @@ class SplineBand:
     oct: Optional[torch.Tensor] = None    # int32: first knot and step count per group, then {largest slab extent, largest step count} per ladder
     slab_knots: int = 0                   # largest number of knots a 64-point slab touches (read back once per build; 0 = unknown)
     all_tensor_path: bool = False         # every ladder has usable tensor-path tables (read back with slab_knots)
+    fill_w: Optional[torch.Tensor] = None   # float64: per ladder knot, the 48 weights that fill it when its quote is missing
+    fill_k0: Optional[torch.Tensor] = None  # int32: first knot of that row (-1: the knot is not filled)
 
 
 def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torch.Tensor, *, extrap: int = 1,
-                      out: Optional[SplineBand] = None, tensor_path: bool = True, refresh_hint: bool = False) -> SplineBand:
+                      out: Optional[SplineBand] = None, tensor_path: bool = True, refresh_hint: bool = False,
+                      n_ladder_knots: Optional[int] = None) -> SplineBand:
     """Per (ladder, grid point): the 48 knot weights of "fit the natural spline, evaluate at xq[q]" and their start, checked
     against a full solve of two probe vectors (``ok[l] == 0``: that ladder's slices take the exact solve)."""
     _req(ladder_off, torch.int64, "ladder_off"); _req(x_ladder, torch.float64, "x_ladder"); _req(xq, torch.float64, "xq")
@@ -506,10 +509,14 @@ def spline_band_build(ladder_off: torch.Tensor, x_ladder: torch.Tensor, xq: torc
     if tensor_path and out.frag is None:
         out.frag = _empty(lib().ivx_spline_band_frag_len(n_l), torch.float64, xq)
         out.oct = _empty(lib().ivx_spline_band_oct_len(n_l), torch.int32, xq)
+        n_knots_total = int(n_ladder_knots) if n_ladder_knots is not None else int(ladder_off[-1].item())   # (a read-back, once per band object)
+        out.fill_w = _empty(lib().ivx_spline_band_fill_len(n_knots_total), torch.float64, xq)
+        out.fill_k0 = _empty(max(1, n_knots_total), torch.int32, xq)
     out.extrap = int(extrap)
     check(lib().ivx_spline_band_build(n_l, _ptr(ladder_off), _ptr(x_ladder), n_q, _ptr(xq), int(extrap), _ptr(out.k0), _ptr(out.w),
                                       _ptr(out.ok), _ptr(out.perm), _ptr(out.frag) if tensor_path else None,
-                                      _ptr(out.oct) if tensor_path else None, _stream()), "ivx_spline_band_build")
+                                      _ptr(out.oct) if tensor_path else None, _ptr(out.fill_w) if tensor_path else None,
+                                      _ptr(out.fill_k0) if tensor_path else None, _stream()), "ivx_spline_band_build")
     _count("spline_band_build")
     if tensor_path and n_l > 0 and (out.slab_knots == 0 or refresh_hint):
         # ONE read-back, at the first build of this set of ladders: how many knots a 64-point slab's staged rows must hold.  Later
@@ -524,7 +531,8 @@ def spline_fit_eval_banded(knot_off: torch.Tensor, x_off: torch.Tensor, slice_la
                            lad_slice_off: torch.Tensor, max_slices_per_ladder: int, ladder_off: torch.Tensor, x_ladder: torch.Tensor,
                            lu: Sequence[torch.Tensor], y: torch.Tensor, xq: torch.Tensor, band: SplineBand, *, max_knots: int,
                            x_own: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                           fb: Optional[Sequence[torch.Tensor]] = None, tensor_path: bool = True, x_verified: bool = False) -> torch.Tensor:
+                           fb: Optional[Sequence[torch.Tensor]] = None, tensor_path: bool = True, x_verified: bool = False,
+                           fill_missing: bool = True) -> torch.Tensor:
     """Slices on tabulated ladders through the banded operators; whatever cannot be taken that way (a non-finite knot, a slice
     off its ladder when ``x_own`` is given, a ladder without a usable band) goes through the exact scan right behind.
     ``fb`` = (int32[n_slices] list, uint32[1] count) scratch, allocated when not passed.  ``x_verified``: ``fb`` already holds the
@@ -547,7 +555,9 @@ def spline_fit_eval_banded(knot_off: torch.Tensor, x_off: torch.Tensor, slice_la
                                            int(max_slices_per_ladder), _ptr(ladder_off), int(max_knots), _ptr(x_ladder),
                                            _ptr(x_own) if x_own is not None else None, _ptr(lu[0]), _ptr(lu[1]), _ptr(lu[2]), _ptr(y), n_q,
                                            _ptr(xq), int(band.extrap), _ptr(band.k0), _ptr(band.w), _ptr(band.ok), _ptr(band.perm),
-                                           _ptr(band.frag) if use_mma else None, _ptr(band.oct) if use_mma else None, int(band.slab_knots),
+                                           _ptr(band.frag) if use_mma else None, _ptr(band.oct) if use_mma else None,
+                                           _ptr(band.fill_w) if (use_mma and fill_missing) else None, _ptr(band.fill_k0) if (use_mma and fill_missing) else None,
+                                           int(band.slab_knots),
                                            1 if (use_mma and band.all_tensor_path) else 0, 1 if x_verified else 0, _ptr(yq), _ptr(fb[0]), _ptr(fb[1]), _stream()), "ivx_spline_fit_eval_banded")
     _count("spline_fit_eval_banded_mma" if use_mma else "spline_fit_eval_banded")
     return yq

@@ -240,7 +240,8 @@ class SurfacePipeline:
             key = (q.K_ek.data_ptr(), q.K_ek._version, q.grid_k.data_ptr(), q.grid_k._version)
             if self._lu_key != key:
                 D.spline_ladder_factor(self._ladder_off, q.K_ek, max_knots=sp.n_strike, out=self._lu)
-                self._band = D.spline_band_build(self._ladder_off, q.K_ek, q.grid_k, extrap=sp.extrap, out=self._band) if self.banded else None
+                self._band = D.spline_band_build(self._ladder_off, q.K_ek, q.grid_k, extrap=sp.extrap, out=self._band,
+                                                 n_ladder_knots=sp.n_exp * sp.n_strike) if self.banded else None
                 self._lu_key = key
             if self.banded:
                 # every slice is n_grid_k dot products of 48 terms against its ladder's banded operator; slices with a missing
@@ -266,7 +267,8 @@ class SurfacePipeline:
             key = (q.K.data_ptr(), q.K._version, q.grid_k.data_ptr(), q.grid_k._version)   # tables follow the columns: rebuilt whenever one is written
             if self._q_lu_key != key:
                 D.spline_ladder_factor(self._q_ladder_off, q.K, max_knots=sp.n_strike, out=self._q_lu)
-                self._q_band = D.spline_band_build(self._q_ladder_off, q.K, q.grid_k, extrap=sp.extrap, out=self._q_band) if self.banded else None
+                self._q_band = D.spline_band_build(self._q_ladder_off, q.K, q.grid_k, extrap=sp.extrap, out=self._q_band,
+                                                   n_ladder_knots=sp.n_exp * sp.n_strike) if self.banded else None
                 self._q_lu_key = key
             if self.banded:
                 # the first stamp's ladders as banded operators; a slice is taken that way only if its own strikes equal its
