@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(64) k_band_fill_check(const int64_t* __restric
   const double* __restrict__ X = x + a0;
   auto XR = [&](int i) { return X[i + (i >= m ? 1 : 0)]; };
   const int k0 = fill_k0[a0 + m];
-  bool bad = k0 < 0;
+  bool bad = k0 != m - 24;                                        // (the evaluation kernel relies on where the row starts)
   for (int which = 0; which < 2 && !bad; ++which) {
     auto sy = [&](int k) { return probe_value(k, which); };       // values at the knots of the REDUCED ladder
     double cprev = 0.0, dprev = 0.0;
@@ -721,7 +721,9 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
                 mask &= mask - 1;
                 const int k = 2 * (src + 32 * r) + comp, m = KB + k;
                 const double cur = ybw[k];                       // broadcast
-                const int k0f = (k < nvalid && isnan(cur)) ? __ldg(P.fill_k0 + lad_a0 + m) : -1;
+                // the row of knot m starts 24 knots before it (band_row on the ladder without m: bracket m-1, 22 rows either side,
+                // one more knot): known without loading fill_k0 — one L2 round trip less on a path that is all latency
+                const int k0f = (k < nvalid && isnan(cur) && m >= FILL_MARGIN && m <= n - 1 - FILL_MARGIN) ? m - 24 : -1;
                 if (k0f < 0) { row_bad = true; continue; }
                 const double* __restrict__ fw = P.fill_w + (lad_a0 + m) * BAND_W;
                 double acc = 0.0;
