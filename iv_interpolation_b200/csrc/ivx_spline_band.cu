@@ -655,6 +655,7 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
   const bool has_out = out_lo + lane < out_hi;
   const int out_k = has_out ? (out_lo + lane < kfirst ? out_lo + lane : klast + (out_lo + lane - kfirst)) : 0;
   const double out_lx = (VERIFY && has_out) ? __ldg(P.x_ladder + P.ladder_off[l] + out_k) : 0.0;
+  bool seen_gap = false;                                     // warp-uniform: this warp has filled a gap in this batch
   double ey = 0.0, ex = 0.0;
   auto load_out = [&](int tile) {
     const int idx = tile * 8 + w;
@@ -708,6 +709,7 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
           // memory: the window may reach outside the slab); anything the rows cannot take — an infinity, a knot near an end, another
           // missing knot inside the window — leaves the slice to the exact solve
           bool row_bad = false;
+          seen_gap = true;
           double* ybw = ybuf + (buf * 8 + w) * ROW;
           for (int r = 0; r < NIT / 2; ++r) {
             const int c = lane + 32 * r;
@@ -761,6 +763,37 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
       const int nb = buf == 0 ? NST - 1 : buf - 1;           // (tile + NST - 1) mod NST
       issue(tile + NST - 1, nb);
       load_out(tile + 1);
+    }
+    if (fill_on && seen_gap && NST >= 3 && tile + 1 < ntiles) {
+      // a tape with gaps: look at the NEXT tile's row now (it has landed: NST - 2 newer groups at most are still in flight) and pull
+      // the fill rows and the windows of its gaps into L1, so that the fills of the next check hit there instead of paying an L2
+      // round trip inside the barrier interval.  No state is carried: the next check finds the gaps again by itself.
+      cp_async_wait<NST - 2>();
+      __syncwarp();
+      const int idx1 = (tile + 1) * 8 + w;
+      const int64_t ko1 = idx1 < ns ? s_base[idx1] : (int64_t)-1;
+      if (ko1 >= 0) {
+        const int b1 = buf + 1 == NST ? 0 : buf + 1;
+        const double2* yb1 = reinterpret_cast<const double2*>(ybuf + (b1 * 8 + w) * ROW);
+        for (int r = 0; r < NIT / 2; ++r) {
+          const double2 yv = yb1[lane + 32 * r];
+#pragma unroll
+          for (int comp = 0; comp < 2; ++comp) {
+            const double v = comp ? yv.y : yv.x;
+            uint32_t mask = __ballot_sync(IVX_FULL_MASK, ((uint32_t)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u);
+            while (mask) {
+              const int src = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const int m = KB + 2 * (src + 32 * r) + comp;
+              if (m >= FILL_MARGIN && m <= n - 1 - FILL_MARGIN && lane < 8) {
+                // 48 weights and 49 knots: four 128-byte lines each at most
+                const double* a = lane < 4 ? P.fill_w + (lad_a0 + m) * BAND_W + 16 * lane : P.y + ko1 + (m - 24) + 16 * (lane - 4);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+              }
+            }
+          }
+        }
+      }
     }
     // 8 slices x 8 points: two accumulator chains, 20 or 24 steps (zero fragments and zero knots past the group's own)
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
