@@ -515,6 +515,52 @@ __global__ void __launch_bounds__(BAND_THREADS, 1) k_band_apply(BandParams P) {
 
 
 // ---- apply, tensor path ----------------------------------------------------------------------------------------------
+// The gaps of one staged row, by the warp that owns it: every NaN below nvalid is replaced by its fill row's 48-term dot product over
+// the slice's other knots (weights and knots straight from global memory: the window may reach outside the slab).  Returns false when
+// the rows cannot take the slice — an infinity, a gap near an end of the ladder, another gap inside a window — and the slice is left
+// to the exact solve.  The row of knot m starts 24 knots before it (band_row on the ladder without m; k_band_fill_check holds the table
+// to that), so nothing is looked up on this path, which is all latency.
+__device__ __noinline__ bool fill_row_gaps(double* __restrict__ ybw, int n_chunks, int nvalid, int KB, int n, int64_t ko, int64_t lad_a0,
+                                           const double* __restrict__ y, const double* __restrict__ fill_w) {
+  const int lane = threadIdx.x & 31;
+  const double2* yb = reinterpret_cast<const double2*>(ybw);
+  bool row_ok = true;
+  for (int r = 0; r < n_chunks; ++r) {
+    const double2 yv = yb[lane + 32 * r];
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+      const double v = comp ? yv.y : yv.x;
+      uint32_t mask = __ballot_sync(IVX_FULL_MASK, ((uint32_t)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int k = 2 * (src + 32 * r) + comp, m = KB + k;
+        const double cur = ybw[k];                               // broadcast
+        if (!(k < nvalid && isnan(cur) && m >= FILL_MARGIN && m <= n - 1 - FILL_MARGIN)) { row_ok = false; continue; }
+        const int k0f = m - 24;
+        const double* __restrict__ fw = fill_w + (lad_a0 + m) * BAND_W;
+        double acc = 0.0;
+        bool fin = true;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int j = lane + 32 * rr;
+          if (j < BAND_W) {
+            const int xi = k0f + j;
+            const double yy = __ldg(y + ko + xi + (xi >= m ? 1 : 0));
+            fin = fin && (((uint32_t)__double2hiint(yy) & 0x7ff00000u) != 0x7ff00000u);
+            acc = fma(__ldg(fw + j), yy, acc);
+          }
+        }
+        if (!__all_sync(IVX_FULL_MASK, fin)) { row_ok = false; continue; }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(IVX_FULL_MASK, acc, d);
+        if (lane == 0) ybw[k] = acc;
+      }
+    }
+  }
+  return row_ok;
+}
+
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -655,7 +701,6 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
   const bool has_out = out_lo + lane < out_hi;
   const int out_k = has_out ? (out_lo + lane < kfirst ? out_lo + lane : klast + (out_lo + lane - kfirst)) : 0;
   const double out_lx = (VERIFY && has_out) ? __ldg(P.x_ladder + P.ladder_off[l] + out_k) : 0.0;
-  bool seen_gap = false;                                     // warp-uniform: this warp has filled a gap in this batch
   double ey = 0.0, ex = 0.0;
   auto load_out = [&](int tile) {
     const int idx = tile * 8 + w;
@@ -704,51 +749,8 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
           }
         }
         bool nonfin = emax == 0x7ff00000u;
-        if (fill_on && __any_sync(IVX_FULL_MASK, nonfin)) {
-          // a missing quote (NaN) in the staged row: filled by its 48-term row over the slice's other knots (straight from global
-          // memory: the window may reach outside the slab); anything the rows cannot take — an infinity, a knot near an end, another
-          // missing knot inside the window — leaves the slice to the exact solve
-          bool row_bad = false;
-          seen_gap = true;
-          double* ybw = ybuf + (buf * 8 + w) * ROW;
-          for (int r = 0; r < NIT / 2; ++r) {
-            const int c = lane + 32 * r;
-            const double2 yv = yb[c];
-#pragma unroll
-            for (int comp = 0; comp < 2; ++comp) {
-              const double v = comp ? yv.y : yv.x;
-              uint32_t mask = __ballot_sync(IVX_FULL_MASK, ((uint32_t)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u);
-              while (mask) {
-                const int src = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int k = 2 * (src + 32 * r) + comp, m = KB + k;
-                const double cur = ybw[k];                       // broadcast
-                // the row of knot m starts 24 knots before it (band_row on the ladder without m: bracket m-1, 22 rows either side,
-                // one more knot): known without loading fill_k0 — one L2 round trip less on a path that is all latency
-                const int k0f = (k < nvalid && isnan(cur) && m >= FILL_MARGIN && m <= n - 1 - FILL_MARGIN) ? m - 24 : -1;
-                if (k0f < 0) { row_bad = true; continue; }
-                const double* __restrict__ fw = P.fill_w + (lad_a0 + m) * BAND_W;
-                double acc = 0.0;
-                bool fin = true;
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                  const int j = lane + 32 * rr;
-                  if (j < BAND_W) {
-                    const int xi = k0f + j;
-                    const double yy = __ldg(P.y + ko + xi + (xi >= m ? 1 : 0));
-                    fin = fin && (((uint32_t)__double2hiint(yy) & 0x7ff00000u) != 0x7ff00000u);
-                    acc = fma(__ldg(fw + j), yy, acc);
-                  }
-                }
-                if (!__all_sync(IVX_FULL_MASK, fin)) { row_bad = true; continue; }
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(IVX_FULL_MASK, acc, d);
-                if (lane == 0) ybw[k] = acc;
-              }
-            }
-          }
-          nonfin = row_bad;
-        }
+        // a missing quote (NaN) in the staged row: filled, out of line (the clean day never goes there and its loop keeps its registers)
+        if (fill_on && __any_sync(IVX_FULL_MASK, nonfin)) nonfin = !fill_row_gaps(ybuf + (buf * 8 + w) * ROW, NIT / 2, nvalid, KB, n, ko, lad_a0, P.y, P.fill_w);
         bad |= nonfin;
       }
       const bool ok = (ko >= 0) && __all_sync(IVX_FULL_MASK, bad == 0);
@@ -763,37 +765,6 @@ __global__ void __launch_bounds__(256, 2) k_band_apply_mma(BandParams P) {
       const int nb = buf == 0 ? NST - 1 : buf - 1;           // (tile + NST - 1) mod NST
       issue(tile + NST - 1, nb);
       load_out(tile + 1);
-    }
-    if (fill_on && seen_gap && NST >= 3 && tile + 1 < ntiles) {
-      // a tape with gaps: look at the NEXT tile's row now (it has landed: NST - 2 newer groups at most are still in flight) and pull
-      // the fill rows and the windows of its gaps into L1, so that the fills of the next check hit there instead of paying an L2
-      // round trip inside the barrier interval.  No state is carried: the next check finds the gaps again by itself.
-      cp_async_wait<NST - 2>();
-      __syncwarp();
-      const int idx1 = (tile + 1) * 8 + w;
-      const int64_t ko1 = idx1 < ns ? s_base[idx1] : (int64_t)-1;
-      if (ko1 >= 0) {
-        const int b1 = buf + 1 == NST ? 0 : buf + 1;
-        const double2* yb1 = reinterpret_cast<const double2*>(ybuf + (b1 * 8 + w) * ROW);
-        for (int r = 0; r < NIT / 2; ++r) {
-          const double2 yv = yb1[lane + 32 * r];
-#pragma unroll
-          for (int comp = 0; comp < 2; ++comp) {
-            const double v = comp ? yv.y : yv.x;
-            uint32_t mask = __ballot_sync(IVX_FULL_MASK, ((uint32_t)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u);
-            while (mask) {
-              const int src = __ffs(mask) - 1;
-              mask &= mask - 1;
-              const int m = KB + 2 * (src + 32 * r) + comp;
-              if (m >= FILL_MARGIN && m <= n - 1 - FILL_MARGIN && lane < 8) {
-                // 48 weights and 49 knots: four 128-byte lines each at most
-                const double* a = lane < 4 ? P.fill_w + (lad_a0 + m) * BAND_W + 16 * lane : P.y + ko1 + (m - 24) + 16 * (lane - 4);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-              }
-            }
-          }
-        }
-      }
     }
     // 8 slices x 8 points: two accumulator chains, 20 or 24 steps (zero fragments and zero knots past the group's own)
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
