@@ -166,16 +166,24 @@ __global__ void __launch_bounds__(256) k_band_check(const int64_t* __restrict__ 
   for (int which = 0; which < 2; ++which) {
     auto sy = [&](int k) { return probe_value(k, which); };
     __syncthreads();
+    // the probe vector is staged by the whole CTA (a sine and a hash per value: inside the serial elimination they were 90 % of
+    // a 2.8 ms kernel that a streaming pipeline runs once per chunk); the elimination overwrites it in place behind itself
+    for (int k = threadIdx.x; k < n; k += blockDim.x) sM[k] = sy(k);
+    __syncthreads();
     if (threadIdx.x == 0) {                       // the reference: plain Thomas over the whole ladder
       double cprev = 0.0, dprev = 0.0;
-      sM[0] = 0.0; sM[n - 1] = 0.0;
+      double y_prev = sM[0], y_cur = sM[1];
+      sM[0] = 0.0;
       for (int i = 1; i <= n - 2; ++i) {
+        const double y_next = sM[i + 1];
         const double hm = X[i] - X[i - 1], hp = X[i + 1] - X[i];
         const double inv = 1.0 / (2.0 * (hm + hp) - hm * cprev);
         cprev = hp * inv;
-        dprev = (6.0 * ((sy(i + 1) - sy(i)) / hp - (sy(i) - sy(i - 1)) / hm) - hm * dprev) * inv;
+        dprev = (6.0 * ((y_next - y_cur) / hp - (y_cur - y_prev) / hm) - hm * dprev) * inv;
         scp[i] = cprev; sM[i] = dprev;
+        y_prev = y_cur; y_cur = y_next;
       }
+      sM[n - 1] = 0.0;
       double M = 0.0;
       for (int i = n - 2; i >= 1; --i) { M = sM[i] - scp[i] * M; sM[i] = M; }
     }
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(64) k_band_fill_check(const int64_t* __restric
                                                         uint8_t* __restrict__ ladder_ok) {
   __shared__ double sM[BAND_MAXK], scp[BAND_MAXK];
   const int l = blockIdx.y;
-  if (!(ladder_ok[l] & LADDER_OK_FILL) || threadIdx.x != 0) return;
+  if (!(ladder_ok[l] & LADDER_OK_FILL)) return;
   const int64_t a0 = ladder_off[l];
   const int n = (int)(ladder_off[l + 1] - a0), nr = n - 1;
   const int span = n - 1 - 2 * FILL_MARGIN;
@@ -254,17 +262,25 @@ __global__ void __launch_bounds__(64) k_band_fill_check(const int64_t* __restric
   auto XR = [&](int i) { return X[i + (i >= m ? 1 : 0)]; };
   const int k0 = fill_k0[a0 + m];
   bool bad = k0 != m - 24;                                        // (the evaluation kernel relies on where the row starts)
-  for (int which = 0; which < 2 && !bad; ++which) {
+  for (int which = 0; which < 2; ++which) {
     auto sy = [&](int k) { return probe_value(k, which); };       // values at the knots of the REDUCED ladder
+    __syncthreads();
+    for (int k = threadIdx.x; k < nr; k += blockDim.x) sM[k] = sy(k);   // staged by the CTA, overwritten in place by the elimination
+    __syncthreads();
+    if (threadIdx.x != 0 || bad) continue;
     double cprev = 0.0, dprev = 0.0;
-    sM[0] = 0.0; sM[nr - 1] = 0.0;
+    double y_prev = sM[0], y_cur = sM[1];
+    sM[0] = 0.0;
     for (int i = 1; i <= nr - 2; ++i) {
+      const double y_next = sM[i + 1];
       const double hm = XR(i) - XR(i - 1), hp = XR(i + 1) - XR(i);
       const double inv = 1.0 / (2.0 * (hm + hp) - hm * cprev);
       cprev = hp * inv;
-      dprev = (6.0 * ((sy(i + 1) - sy(i)) / hp - (sy(i) - sy(i - 1)) / hm) - hm * dprev) * inv;
+      dprev = (6.0 * ((y_next - y_cur) / hp - (y_cur - y_prev) / hm) - hm * dprev) * inv;
       scp[i] = cprev; sM[i] = dprev;
+      y_prev = y_cur; y_cur = y_next;
     }
+    sM[nr - 1] = 0.0;
     double M = 0.0;
     for (int i = nr - 2; i >= 1; --i) { M = sM[i] - scp[i] * M; sM[i] = M; }
     const int i0 = m - 1;                                          // x[m] lies between the reduced knots m-1 and m
@@ -274,7 +290,7 @@ __global__ void __launch_bounds__(64) k_band_fill_check(const int64_t* __restric
     for (int j = 0; j < BAND_W; ++j) got = fma(fill_w[(a0 + m) * BAND_W + j], sy(k0 + j), got);
     if (!(fabs(got - exact) <= 2e-12 * (1.0 + fabs(exact)))) bad = true;
   }
-  if (bad) ladder_ok[l] &= (uint8_t)~LADDER_OK_FILL;             // (several samples may clear the same bit: same value)
+  if (threadIdx.x == 0 && bad) ladder_ok[l] &= (uint8_t)~LADDER_OK_FILL;   // (several samples may clear the same bit: same value)
 }
 
 // ---- which grid point each thread of k_band_apply takes ------------------------------------------------------------------
