@@ -49,7 +49,7 @@ __device__ __forceinline__ bool vol_missing(double v) { return isnan(v) || v <= 
 //   close.  Compared bit for bit with Python's round over millions of values in tests/test_gpu_bridge.py.
 //   Large |x| (ulp(x) above one unit of the rounded place: 2^39 for 4 decimals, 2^33 for 6; also inf and NaN) round to
 //   themselves; below that x * 10^d stays under 2^53 and every integer involved is exact.
-template <int D, bool CHECKED = true>
+template <int D>
 __device__ __forceinline__ double round_np(double x) {
   constexpr double s = D == 4 ? 1e4 : 1e6;
   constexpr double rc = D == 4 ? 1e-4 : 1e-6;            // RN(1/s)
@@ -97,7 +97,7 @@ __device__ __forceinline__ BridgeState fresh_state() { return BridgeState{0.0, 0
 
 constexpr int CHAIN_W = 12;                                // warm-up ranks of the parallel close walk: 0.15^12 = 1.3e-10
 struct BridgeSmem {
-  double b[4][32], c[4][32], f[4][32];                     // per warp: base and close offset by rank, final closes by rank
+  double b[4][32], c[4][32], k[4][32], f[4][32];           // per warp: base, close offset and grid step constant by rank; final closes by rank
 };
 
 // Rows [a, b) of ONE symbol, in chunks of 32, continuing from `st`.  o_base / e_base: candles and exponential draws before
@@ -108,7 +108,7 @@ __device__ __forceinline__ void bridge_piece(const BridgeParams& P, const int64_
   const int lane = lane_id();
   const uint32_t lt = (1u << lane) - 1u;
   constexpr int K = STRATEGY == ST_SPREAD ? 5 : STRATEGY == ST_MIDPOINT ? 2 : STRATEGY == ST_PIPELINE ? 4 : STRATEGY == ST_SIMPLE ? 1 : 0;
-  double (*s_b)[32] = sm.b; double (*s_c)[32] = sm.c; double (*s_f)[32] = sm.f;
+  double (*s_b)[32] = sm.b; double (*s_c)[32] = sm.c; double (*s_k)[32] = sm.k; double (*s_f)[32] = sm.f;
   double &pc1 = st.pc1, &pc2 = st.pc2, &pc3 = st.pc3, &pc4 = st.pc4, &pc5 = st.pc5;
   int& n_prev = st.n_prev;
   // base/volume of the next chunk are requested before this chunk's (latency-bound) close walk
@@ -150,25 +150,35 @@ __device__ __forceinline__ void bridge_piece(const BridgeParams& P, const int64_
       const int wi = threadIdx.x >> 5;
       const int rank = __popc(okm & lt), n = __popc(okm);
       __syncwarp();                                        // the previous chunk's readers are done with the staging rows
-      if (ok) { s_b[wi][rank] = bp; s_c[wi][rank] = co; }
+      if (ok) {
+        s_b[wi][rank] = bp; s_c[wi][rank] = co;
+        // the step in units of 1e-4: close[j] * 1e4 ~ rint(k[j] - 0.15 * (close[j-1] * 1e4)); no trend bias on a symbol's first candle
+        s_k[wi][rank] = ((rank == 0 && n_prev == 0) ? bp + co : bp * 1.15 + co) * 1e4;
+      }
       __syncwarp();
+      // Only the LAST step of a lane has to be the reference's arithmetic: the check below proves that the predecessor's
+      // close a lane arrived with IS its neighbour's final close, bit for bit, and the last step then makes the lane's own
+      // close the sequential one (induction from lane 0, which starts from the carried close).  The steps before it only
+      // have to land on the same 1e-4 grid point, so they run on the grid: one fused multiply-add and one rint per rank
+      // instead of the five separately rounded operations and the decimal rounding of the exact step (they differ from
+      // the exact walk by ~1e-10 of a grid step; a lane that does land elsewhere fails the check and the chunk is redone).
+      double a4 = pc1 * 1e4;                               // the predecessor's close in units of 1e-4
       double p = pc1, p_before = pc1;
-      const bool spec = lane > CHAIN_W;
       if (lane < n) {
         int i = lane - CHAIN_W;
-        if (spec) p = s_b[wi][i - 1];                      // the guess: no trend bias at the row before the walk
+        if (lane > CHAIN_W) a4 = s_b[wi][i - 1] * 1e4;     // the guess: no trend bias at the row before the walk
 #pragma unroll
-        for (int t = 0; t <= CHAIN_W; ++t, ++i) {
-          if (i >= 0) {
-            const double b_ = s_b[wi][i], c_ = s_c[wi][i];
-            const double tb_ = (i == 0 && n_prev == 0) ? 0.0 : (b_ - p) * 0.3;      // :219-222
-            p_before = p;
-            p = round_np<4, false>(b_ + (c_ + tb_ * 0.5));                            // :228-229, :256
-          }
+        for (int t = 0; t < CHAIN_W; ++t, ++i)
+          if (i >= 0) a4 = rint(fma(-0.15, a4, s_k[wi][i]));
+        if (lane > 0) {                                    // a4 / 1e4, correctly rounded (see round_np): the close a4 stands for
+          const double q0 = a4 * 1e-4;
+          p_before = fma(fma(-1e4, q0, a4), 1e-4, q0);
         }
+        const double tb_ = (lane == 0 && n_prev == 0) ? 0.0 : (s_b[wi][lane] - p_before) * 0.3;      // :219-222
+        p = round_np<4>(s_b[wi][lane] + (s_c[wi][lane] + tb_ * 0.5));                                  // :228-229, :256
       }
       const double up = __shfl_up_sync(IVX_FULL_MASK, p, 1);
-      const bool bad = (lane < n && spec && !(p_before == up)) || (ok && !(fabs(bp) < 1e290));
+      const bool bad = (lane < n && lane > 0 && !(p_before == up)) || (ok && !(fabs(bp) < 1e290));
       if (!__any_sync(IVX_FULL_MASK, bad)) {
         if (lane < n) s_f[wi][lane] = p;
         __syncwarp();
