@@ -131,6 +131,7 @@ __host__ __device__ __forceinline__ int64_t floor_div(int64_t t, const FloorDiv&
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // streaming loads/stores: data that is touched once should not displace reusable lines
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int64_t ld_stream(const int64_t* p) { return __ldcs((const long long*)p); }
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }

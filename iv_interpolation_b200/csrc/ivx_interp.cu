@@ -17,7 +17,7 @@ namespace {
 
 constexpr int TA_THREADS = 256;
 constexpr int TA_ROWS = 1024;
-constexpr int PLAN_WARPS = 8;
+constexpr int PLAN_WARPS = 4;     // 128 threads, 24 KB of records: five CTAs per SM at 100 registers
 
 // everything exec needs about the interval that starts at one on-grid source row, in ONE record: a row's ~20 parameter
 // loads then fall into two or three cache lines shared by the whole warp, at constant offsets from one address
@@ -93,7 +93,7 @@ __device__ __forceinline__ int lowest_bit_gt(uint32_t m, int lane) {   // lowest
 }
 
 __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParams P) {
-  __shared__ IntervalRec s_rec[PLAN_WARPS * 32];   // 48 KB: one record per lane, copied out coalesced
+  __shared__ IntervalRec s_rec[PLAN_WARPS * 32];   // 24 KB: one record per lane, copied out coalesced
   const int lane = threadIdx.x & 31;
   const int64_t s = blockIdx.x * (int64_t)PLAN_WARPS + (threadIdx.x >> 5);
   if (s >= P.n_sym) return;
@@ -118,14 +118,23 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
   int64_t tmin = INT64_MAX, tmax = INT64_MIN;
   uint32_t flags = 0;
   int64_t prev_last = IVX_NAT;
-  for (int64_t base = a; base < b; base += 32) {
-    int64_t r = base + lane;
-    int64_t t = (r < b) ? P.ts[r] : IVX_NAT;
-    if (t != IVX_NAT) { tmin = min(tmin, t); tmax = max(tmax, t); }
-    int64_t tp = __shfl_up_sync(IVX_FULL_MASK, t, 1);
-    if (lane == 0) tp = prev_last;
-    if (t != IVX_NAT && tp != IVX_NAT && t < tp) flags |= IVX_FLAG_UNSORTED;
-    prev_last = __shfl_sync(IVX_FULL_MASK, t, 31);
+  for (int64_t base = a; base < b; base += 128) {       // four chunks of stamps in flight: the sweep is latency-bound
+    int64_t tt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = base + 32 * u + lane;
+      tt[u] = (r < b) ? __ldg(P.ts + r) : IVX_NAT;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (base + 32 * u >= b) break;
+      const int64_t t = tt[u];
+      if (t != IVX_NAT) { tmin = min(tmin, t); tmax = max(tmax, t); }
+      int64_t tp = __shfl_up_sync(IVX_FULL_MASK, t, 1);
+      if (lane == 0) tp = prev_last;
+      if (t != IVX_NAT && tp != IVX_NAT && t < tp) flags |= IVX_FLAG_UNSORTED;
+      prev_last = __shfl_sync(IVX_FULL_MASK, t, 31);
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -156,7 +165,25 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
   for (int64_t base = a; base < b; base += 32) {
     const int64_t r = base + lane;
     const bool inr = r < b;
-    const int64_t t = inr ? P.ts[r] : IVX_NAT;
+    // every load of the chunk is issued before its first store (one memory latency per chunk, not one per column: the
+    // workspace the sweep writes could alias the columns as far as the compiler knows), and the next chunk's lines are
+    // requested into L2 meanwhile — 2 400 contracts are 16 warps per SM, nothing else hides the latency
+    const int64_t t = inr ? __ldg(P.ts + r) : IVX_NAT;
+    double vc[3], vf[IVX_MAX_FILL_COLS];
+    bool vi[IVX_MAX_IDX_COLS];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vc[c] = inr ? __ldg(P.icol[c] + r) : qnan();
+#pragma unroll
+    for (int kf = 0; kf < IVX_MAX_FILL_COLS; ++kf) vf[kf] = (kf < P.n_fill && inr) ? __ldg(P.fcol[kf] + r) : qnan();
+#pragma unroll
+    for (int ki = 0; ki < IVX_MAX_IDX_COLS; ++ki) vi[ki] = (ki < P.n_idx && inr && P.ivalid[ki]) ? (__ldg(P.ivalid[ki] + r) != 0) : true;
+    if ((lane == 0 || lane == 16 || lane == 31) && r + 32 < b) {      // these three rows touch every line of the next chunk
+      prefetch_l2(P.ts + r + 32);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) prefetch_l2(P.icol[c] + r + 32);
+#pragma unroll
+      for (int kf = 0; kf < IVX_MAX_FILL_COLS; ++kf) if (kf < P.n_fill) prefetch_l2(P.fcol[kf] + r + 32);
+    }
     int64_t k = -2;
     bool on = false;
     if (t != IVX_NAT) {
@@ -179,7 +206,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
 
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const double v = inr ? P.icol[c][r] : qnan();
+      const double v = vc[c];
       const bool valid = on && !isnan(v);
       if (valid && isinf(v)) flags |= IVX_FLAG_NONFINITE;
       const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
@@ -198,7 +225,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
 #pragma unroll
     for (int kf = 0; kf < IVX_MAX_FILL_COLS; ++kf) {
       if (kf < P.n_fill) {
-        const double v = inr ? P.fcol[kf][r] : qnan();
+        const double v = vf[kf];
         const bool valid = on && !isnan(v);
         const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
         const int sl = highest_bit_le(m_v, lane);
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
 #pragma unroll
     for (int ki = 0; ki < IVX_MAX_IDX_COLS; ++ki) {
       if (ki < P.n_idx) {
-        const bool valid = on && (P.ivalid[ki] ? (P.ivalid[ki][r] != 0) : true);
+        const bool valid = on && vi[ki];
         const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
         const int sl = highest_bit_le(m_v, lane);
         int32_t pidx = __shfl_sync(IVX_FULL_MASK, (int32_t)r, sl < 0 ? 0 : sl);
@@ -241,13 +268,25 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
   for (int64_t hi = a + n_on; hi > a; hi -= 32) {
     const int64_t g = hi - 32 + lane;              // chunk [hi-32, hi), may start before a
     const bool ing = g >= a;
+    // the chunk's loads together, ahead of the shuffles (one latency per chunk)
     const int32_t pos = ing ? W.gpos[g] : -1;
+    const int64_t gts = ing ? W.s_gts[g] : 0;
+    const int32_t grow = ing ? W.s_grow[g] : -1;
+    int32_t x0s[3];
+    double y0s[3], fv[IVX_MAX_FILL_COLS];
+    int32_t fi[IVX_MAX_IDX_COLS];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { x0s[c] = ing ? W.s_x0[c][g] : -1; y0s[c] = ing ? W.s_y0[c][g] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) fv[k] = (ing && k < P.n_fill) ? W.s_fval[k][g] : 0.0;
+#pragma unroll
+    for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) fi[k] = (ing && k < P.n_idx) ? W.s_fidx[k][g] : -1;
     IntervalRec& R = s_rec[threadIdx.x];             // this lane's record, assembled in shared memory
-    R.gts = ing ? W.s_gts[g] : 0; R.grow = ing ? W.s_grow[g] : -1; R.pad_ = 0;
+    R.gts = gts; R.grow = grow; R.pad_ = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const int32_t x0 = ing ? W.s_x0[c][g] : -1;
-      const double y0 = ing ? W.s_y0[c][g] : 0.0;
+      const int32_t x0 = x0s[c];
+      const double y0 = y0s[c];
       const bool valid = ing && (x0 == pos);       // the row's own value is a knot
       const uint32_t m_v = __ballot_sync(IVX_FULL_MASK, valid);
       const int sl = lowest_bit_gt(m_v, lane);
@@ -264,9 +303,9 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) k_interp_plan(const PlanParam
       }
     }
 #pragma unroll
-    for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) R.fval[k] = (ing && k < P.n_fill) ? W.s_fval[k][g] : 0.0;
+    for (int k = 0; k < IVX_MAX_FILL_COLS; ++k) R.fval[k] = fv[k];
 #pragma unroll
-    for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) R.fidx[k] = (ing && k < P.n_idx) ? W.s_fidx[k][g] : -1;
+    for (int k = 0; k < IVX_MAX_IDX_COLS; ++k) R.fidx[k] = fi[k];
     __syncwarp();
     // the chunk's records [hi-32, hi) are contiguous in global memory: the warp copies them out 16 bytes per lane at a time
     {
