@@ -52,12 +52,15 @@ class CandleReconstructor:
 
     # -- many symbols in one launch ---------------------------------------------------------------------
     def reconstruct_batch(self, frames: Sequence[pd.DataFrame], presorted: bool = False,
-                          check_len: bool = True, flags_out: Optional[list] = None) -> List[Optional[pd.DataFrame]]:
+                          check_len: bool = True, flags_out: Optional[list] = None, whole_out: Optional[dict] = None,
+                          slices: bool = True) -> List[Optional[pd.DataFrame]]:
         """``[reconstruct_symbol_candles(f) for f in frames]`` with a single kernel launch.
 
         ``presorted=True, check_len=False`` is the contract of the reference's second entry,
         CompleteOptimizedPipeline._aggregate_to_5min (complete_pipeline.py:685-710): rows already
-        ordered by the SQL query, no length early-out.
+        ordered by the SQL query, no length early-out.  ``frames`` may be a ``hostpath.FrameSlices`` (no concat);
+        ``whole_out`` (a dict) receives the one frame the results are slices of, when there is one (``frame``, ``off``, ``ok``,
+        ``slots``), and ``slices=False`` then leaves the per-symbol results to the caller (all ``None``).
         """
         import torch
         from .. import device as D
@@ -71,12 +74,17 @@ class CandleReconstructor:
         if flags_out is not None:           # per frame: IVX_FLAG_* bits of the launch (validate_candle_data of input and output), None = not run
             flags_out[:] = [None] * len(frames)
         from .. import hostpath as H
-        live = [i for i, df in enumerate(frames) if not df.empty]
-        if n >= 1 and len(live) > 1 and H.task2_uniform([frames[i] for i in live]):
-            got = H.reconstruct_uniform([frames[i] for i in live], n, self.target_frequency, datetime.now(),
-                                        presorted=presorted, check_len=check_len)
+        whole = isinstance(frames, H.FrameSlices) and len(frames) > 1 and bool((np.diff(frames.off) > 0).all())
+        live = list(range(len(frames))) if whole else [i for i, df in enumerate(frames) if not df.empty]
+        batch = frames if whole else [frames[i] for i in live]
+        if n >= 1 and len(live) > 1 and H.task2_uniform(batch):
+            wo = {} if whole_out is not None else None
+            got = H.reconstruct_uniform(batch, n, self.target_frequency, datetime.now(), presorted=presorted, check_len=check_len,
+                                        whole_out=wo, slices=slices or whole_out is None)
             from .._lib import FLAG_UNSORTED
             if got is not None and not (presorted and any(f & FLAG_UNSORTED for f in got[1])):
+                if whole_out is not None:
+                    whole_out.update(wo, slots=live)
                 outs, fl = got
                 for k, i in enumerate(live):
                     results[i] = outs[k]

@@ -178,8 +178,14 @@ class InterpolatedToOHLCVConverter:
     def _uniform(self, frames: Sequence[pd.DataFrame], ts_col: str) -> bool:
         """Frames sharing one column layout with a tz-naive datetime64 stamp column, float64 prices/volume and a symbol column:
         they are concatenated once and the result is handed out as slices of one frame (see hostpath.py)."""
-        live = [f for f in frames if not f.empty]
-        if len(live) < 2:
+        from ..hostpath import FrameSlices
+        if isinstance(frames, FrameSlices):                # one frame already (its slices share the layout by construction)
+            live = [frames.big] if len(frames.big) else []
+        else:
+            live = [f for f in frames if not f.empty]
+            if len(live) < 2:
+                return False
+        if not live:
             return False
         first = live[0]
         cols, dtypes = list(first.columns), list(first.dtypes)
@@ -192,24 +198,29 @@ class InterpolatedToOHLCVConverter:
             return False
         return all(list(f.columns) == cols and list(f.dtypes) == dtypes for f in live[1:])
 
-    def _generate_many(self, frames: Sequence[pd.DataFrame], strategy_name: str) -> List[Dict]:
+    def _generate_many(self, frames: Sequence[pd.DataFrame], strategy_name: str, whole_out: Optional[Dict] = None) -> List[Dict]:
+        """``frames``: a list of frames or a ``hostpath.FrameSlices`` (then nothing is concatenated); ``whole_out`` (a dict)
+        receives the one frame the results are slices of, when there is one: ``frame``, ``off``."""
         import torch
 
         from .. import device as D
-        from ..hostpath import d2h_many
+        from ..hostpath import FrameSlices, d2h_many
 
         strategy = canonical_strategy(strategy_name)
         rs = self._rng if self._rng is not None else np.random
         dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         pipeline = strategy == "pipeline"
         ts_col = "date" if pipeline else "timestamp"
-        lens = np.fromiter((len(f) for f in frames), dtype=np.int64, count=len(frames))
-        off = np.zeros(len(frames) + 1, np.int64)
-        np.cumsum(lens, out=off[1:])
+        if isinstance(frames, FrameSlices):
+            lens, off = np.diff(frames.off), frames.off
+        else:
+            lens = np.fromiter((len(f) for f in frames), dtype=np.int64, count=len(frames))
+            off = np.zeros(len(frames) + 1, np.int64)
+            np.cumsum(lens, out=off[1:])
         uniform = self._uniform(frames, ts_col)
         big = None
         if uniform:
-            big = pd.concat([f for f in frames if not f.empty], ignore_index=True)
+            big = frames.big if isinstance(frames, FrameSlices) else pd.concat([f for f in frames if not f.empty], ignore_index=True)
             nz = np.flatnonzero(lens)
             starts = off[:-1][nz]
             if pipeline:                                   # complete_pipeline.py:478: a or b or c on floats (NaN truthy, 0.0 not)
@@ -262,7 +273,7 @@ class InterpolatedToOHLCVConverter:
         out_off, row, quality = host[:3]
         cols = dict(zip(names, host[3:]))
         if uniform:
-            got = self._assemble_uniform(frames, big, ts_col, out_off, row, cols, quality, pipeline, strategy)
+            got = self._assemble_uniform(frames, big, ts_col, out_off, row, cols, quality, pipeline, strategy, whole_out)
             if got is not None:
                 return got
         out: List[Dict] = []
@@ -288,7 +299,7 @@ class InterpolatedToOHLCVConverter:
             out.append({"frame": frame, "quality": self._quality_verdict(int(quality[i]))})
         return out
 
-    def _assemble_uniform(self, frames, big, ts_col, out_off, row, cols, quality, pipeline, strategy):
+    def _assemble_uniform(self, frames, big, ts_col, out_off, row, cols, quality, pipeline, strategy, whole_out=None):
         """All candles as ONE frame, handed out as per-symbol slices.  Returns None (-> per-frame assembly) when the clean-up
         of :404-418 would actually change something: a NaN among the OHLC columns or stamps out of order inside a symbol."""
         nf = len(frames)
@@ -310,6 +321,8 @@ class InterpolatedToOHLCVConverter:
         data["is_synthetic"] = True
         local = np.arange(len(row), dtype=np.int64) - np.repeat(out_off[:-1], n_out)
         frame = pd.DataFrame(data, index=pd.Index(local, copy=False))
+        if whole_out is not None:
+            whole_out.update(frame=frame, off=np.asarray(out_off, dtype=np.int64))
         out: List[Dict] = []
         for i in range(nf):
             a, b_ = int(out_off[i]), int(out_off[i + 1])

@@ -33,6 +33,45 @@ TASK1_COLS = frozenset(("date",) + TASK1_STR + TASK1_NUM)
 TASK2_NUM = ("open", "high", "low", "close", "volume")
 
 
+class FrameSlices:
+    """A batch of per-symbol frames that ARE consecutive row ranges of one frame: ``self[i] == big.iloc[off[i]:off[i+1]]``.
+
+    A stage of ``batch.PipelineBatch`` hands its whole result frame to the next stage in this form, so the next stage skips
+    the per-symbol column selection and the ``pd.concat`` that would rebuild the very frame the slices were cut from
+    (0.5-2 ms of pandas per symbol and stage: at 2 400 contracts that, not the launches, was the cost of the pipeline).
+    Built only by this package from frames it has just produced itself."""
+
+    def __init__(self, big: pd.DataFrame, off: np.ndarray):
+        off = np.asarray(off, dtype=np.int64)
+        if len(off) < 1 or off[0] != 0 or off[-1] != len(big) or (len(off) > 1 and (np.diff(off) < 0).any()):
+            raise ValueError("FrameSlices: offsets do not tile the frame")
+        self.big, self.off = big, off
+
+    def __len__(self) -> int:
+        return len(self.off) - 1
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self.big.iloc[int(self.off[i]):int(self.off[i + 1])]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _batch_of(frames):
+    """(nf, lens, off, big) of a batch: the frame itself for ``FrameSlices``, one ``pd.concat`` for a list of frames."""
+    if isinstance(frames, FrameSlices):
+        return len(frames), np.diff(frames.off), frames.off, frames.big
+    nf = len(frames)
+    lens = np.fromiter((len(f) for f in frames), dtype=np.int64, count=nf)
+    off = np.zeros(nf + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    return nf, lens, off, (frames[0] if nf == 1 else pd.concat(frames, ignore_index=True))
+
+
 def d2h_many(tensors: Sequence[object]) -> List[Optional[np.ndarray]]:
     """Device tensors -> numpy arrays through pinned host memory (torch's caching host allocator: the blocks are reused
     across calls), all copies enqueued before the single synchronisation.  ``None`` entries pass through."""
@@ -72,8 +111,10 @@ def _naive_datetime(dtype) -> Optional[str]:
 def task1_uniform(frames: Sequence[pd.DataFrame]) -> bool:
     """Every frame has exactly the reference's 13 Task-1 columns in one common order, float64 numerics, one tz-naive
     datetime64 unit for ``date`` and non-numeric string columns."""
-    if not frames:
+    if not len(frames):
         return False
+    if isinstance(frames, FrameSlices):
+        frames = [frames.big]
     first = frames[0]
     cols = list(first.columns)
     if len(cols) != len(TASK1_COLS) or set(cols) != TASK1_COLS:
@@ -107,7 +148,8 @@ def _tick(timing: Optional[dict], key: str, t0: float) -> float:
 
 
 def interpolate_uniform(frames: Sequence[pd.DataFrame], min_points: int, launch: Optional[Callable] = None,
-                        device=None, timing: Optional[dict] = None, extra: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
+                        device=None, timing: Optional[dict] = None, extra: Optional[dict] = None,
+                        whole_out: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
     """``[IVInterpolator.interpolate_symbol(f) for f in frames]`` for frames that satisfy ``task1_uniform`` and hold at
     least ``min_points`` rows each (reference core.py:26-28 is the caller's business)."""
     import torch
@@ -117,11 +159,7 @@ def interpolate_uniform(frames: Sequence[pd.DataFrame], min_points: int, launch:
     launch = launch or D.interp_linear_ffill
     dev = device if device is not None else torch.device("cuda")
     tk = time.perf_counter()
-    nf = len(frames)
-    lens = np.fromiter((len(f) for f in frames), dtype=np.int64, count=nf)
-    off = np.zeros(nf + 1, np.int64)
-    np.cumsum(lens, out=off[1:])
-    big = frames[0] if nf == 1 else pd.concat(frames, ignore_index=True)
+    nf, lens, off, big = _batch_of(frames)
     unit = _naive_datetime(big["date"].dtype)
     date = big["date"].to_numpy().view(np.int64)
     order = None
@@ -184,14 +222,18 @@ def interpolate_uniform(frames: Sequence[pd.DataFrame], min_points: int, launch:
         a, b = int(out_off[g]), int(out_off[g + 1])
         if b > a:                                                       # core.py:76-78: empty after dropna -> None
             results[g] = out.iloc[a:b]
+    if whole_out is not None:                                           # the frame the results are slices of (see FrameSlices)
+        whole_out.update(frame=out, off=np.asarray(out_off, dtype=np.int64), ok=np.asarray(status) == SYM_OK)
     _tick(timing, "host_result_frames_s", tk)
     return results
 
 
 def task2_uniform(frames: Sequence[pd.DataFrame]) -> bool:
     """Task-2 frames with one common column order, float64 OHLCV, one tz-naive datetime64 unit and no null symbol."""
-    if not frames:
+    if not len(frames):
         return False
+    if isinstance(frames, FrameSlices):
+        frames = [frames.big]
     first = frames[0]
     cols = list(first.columns)
     if "symbol" not in cols or any(c not in cols for c in F.CANDLE_REQUIRED):
@@ -209,7 +251,8 @@ def task2_uniform(frames: Sequence[pd.DataFrame]) -> bool:
 
 
 def reconstruct_uniform(frames: Sequence[pd.DataFrame], n: int, target_frequency: str, created_at, *, presorted: bool,
-                        check_len: bool, launch: Optional[Callable] = None, device=None):
+                        check_len: bool, launch: Optional[Callable] = None, device=None, whole_out: Optional[dict] = None,
+                        slices: bool = True):
     """``[reconstruct_symbol_candles(f) for f in frames]`` for non-empty ``task2_uniform`` frames; returns (results, flags)
     or ``None`` when a symbol column holds nulls (the per-frame path handles first-non-null semantics)."""
     import torch
@@ -218,11 +261,7 @@ def reconstruct_uniform(frames: Sequence[pd.DataFrame], n: int, target_frequency
 
     launch = launch or D.ohlcv_reduce
     dev = device if device is not None else torch.device("cuda")
-    nf = len(frames)
-    lens = np.fromiter((len(f) for f in frames), dtype=np.int64, count=nf)
-    off = np.zeros(nf + 1, np.int64)
-    np.cumsum(lens, out=off[1:])
-    big = frames[0] if nf == 1 else pd.concat(frames, ignore_index=True)
+    nf, lens, off, big = _batch_of(frames)
     if big["symbol"].isna().any():
         return None
     unit = _naive_datetime(big["timestamp"].dtype)
@@ -255,7 +294,10 @@ def reconstruct_uniform(frames: Sequence[pd.DataFrame], n: int, target_frequency
     out["created_at"] = created_at
     out = out[list(F.CANDLE_OUT_ORDER)]
     results: List[Optional[pd.DataFrame]] = [None] * nf
-    for g in range(nf):
-        if status[g] == SYM_OK:
-            results[g] = out.iloc[int(out_off[g]):int(out_off[g + 1])]
+    if whole_out is not None:                                           # the frame the results are slices of (see FrameSlices)
+        whole_out.update(frame=out, off=np.asarray(out_off, dtype=np.int64), ok=np.asarray(status) == SYM_OK)
+    if slices:
+        for g in range(nf):
+            if status[g] == SYM_OK:
+                results[g] = out.iloc[int(out_off[g]):int(out_off[g + 1])]
     return results, [int(x) for x in flags]

@@ -43,8 +43,10 @@ class IVInterpolator:
 
     # -- many contracts in one launch --------------------------------------------------------------
     def interpolate_batch(self, frames: Sequence[pd.DataFrame], timing: Optional[dict] = None,
-                          extra: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
-        """``[interpolate_symbol(f) for f in frames]`` with one plan + one exec launch for all."""
+                          extra: Optional[dict] = None, whole_out: Optional[dict] = None) -> List[Optional[pd.DataFrame]]:
+        """``[interpolate_symbol(f) for f in frames]`` with one plan + one exec launch for all.  ``whole_out`` (a dict)
+        receives the one frame the results are slices of, when there is one (hostpath.FrameSlices): ``frame``, ``off``, ``ok``
+        and ``slots`` (the positions in ``frames`` the offsets stand for)."""
         import torch
         from .. import device as D
         from .._lib import SYM_OK, IvxError, lib
@@ -61,7 +63,10 @@ class IVInterpolator:
         from .. import hostpath as H
         big_enough = [i for i, df in enumerate(frames) if len(df) >= self.min_points]
         if len(big_enough) > 1 and H.task1_uniform([frames[i] for i in big_enough]):
-            outs = H.interpolate_uniform([frames[i] for i in big_enough], self.min_points, timing=timing, extra=extra)
+            outs = H.interpolate_uniform([frames[i] for i in big_enough], self.min_points, timing=timing, extra=extra,
+                                         whole_out=whole_out)
+            if whole_out is not None:
+                whole_out["slots"] = big_enough
             for i, out in zip(big_enough, outs):
                 if out is None:
                     logger.debug("No valid data after interpolation or guard failed")

@@ -67,3 +67,40 @@ def ohlcv_reduce(in_off, ts, o, h, l, c, v, *, bucket_ticks, min_count, check_le
                         cat(lambda r: np.where(r["sym_row"] >= 0, r["sym_row"] + r["base"], -1), np.int64),
                         cat(lambda r: r["group_index"], np.int64), torch.zeros(n_sym + 1, dtype=torch.int64), int(out_off[-1]))
     return res
+
+
+def bridge_plan(in_off, base, volume):
+    """Stand-in of ``device.bridge_plan``: emitted candles / exponential draws before every symbol (no segment tables)."""
+    from oracle import bridge_oracle as BO
+    off = in_off.numpy()
+    ok = BO.valid_rows(base.numpy())
+    need = ok & BO.needs_volume(volume.numpy())
+    c = np.concatenate([[0], np.cumsum(ok)]).astype(np.int64)
+    ce = np.concatenate([[0], np.cumsum(need)]).astype(np.int64)
+    return D.BridgePlan(torch.from_numpy(c[off]), torch.from_numpy(ce[off]), None, None, int(ok.sum()), int(need.sum()))
+
+
+def bridge_ohlcv(in_off, base, volume, plan, strategy, *, u=None, e=None, z=None, base_spread_percent=0.002,
+                 volatility_factor=1.5, **_):
+    """Stand-in of ``device.bridge_ohlcv``: the reference-pinned row loop of oracle/bridge_oracle.py per symbol, each symbol
+    reading its own stretch of the flat tapes (k uniforms per emitted row, one exponential per drawn volume)."""
+    from iv_interpolation_b200 import _lib
+    from oracle import bridge_oracle as BO
+    off, out_off, e_off = in_off.numpy(), plan.out_off.numpy(), plan.e_off.numpy()
+    k = _lib.BRIDGE_U_PER_ROW[_lib.BRIDGE_STRATEGY[strategy]]
+    un = u.numpy() if u is not None else np.zeros(0)
+    en = e.numpy() if e is not None else np.zeros(0)
+    zn = z.numpy() if z is not None else np.zeros(0)
+    names = ("open", "high", "low", "close", "volume", "source_price")
+    parts, q = [], np.zeros(len(off) - 1, np.int32)
+    for g in range(len(off) - 1):
+        a, b = int(off[g]), int(off[g + 1])
+        r = BO.bridge_ohlcv(strategy, base.numpy()[a:b], volume.numpy()[a:b], un[k * out_off[g]:k * out_off[g + 1]],
+                            en[e_off[g]:e_off[g + 1]], zn[out_off[g]:out_off[g + 1]] if len(zn) else None,
+                            base_spread_percent=base_spread_percent, volatility_factor=volatility_factor)
+        assert len(r["row"]) == out_off[g + 1] - out_off[g]
+        r["row"] = r["row"] + a
+        q[g] = r["quality"]
+        parts.append(r)
+    cat = lambda key, dt: torch.from_numpy(np.concatenate([r[key] for r in parts]).astype(dt) if parts else np.zeros(0, dt))
+    return D.BridgeBatch(plan.out_off, cat("row", np.int64), *(cat(n, np.float64) for n in names), torch.from_numpy(q), plan.total)

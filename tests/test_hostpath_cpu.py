@@ -181,3 +181,53 @@ def test_sparse_underlying_tape_is_a_consistent_ragged_csr():
         assert tp.date[a] == full.date[fa] and tp.date[b - 1] == full.date[fb - 1]          # first and last row kept
         assert np.isin(tp.date[a:b], full.date[fa:fb]).all()
     assert np.isnan(tp.cols["iv"]).mean() > 0.1
+
+
+def test_pipeline_batch_whole_frame_handover_equals_per_symbol_handover(monkeypatch):
+    """PipelineBatch hands each stage's whole result frame to the next stage (hostpath.FrameSlices) instead of per-symbol frames
+    that are cut, column-selected and concatenated again.  Both hand-overs must give the same frames at every stage (values,
+    dtypes, index labels) and the same status dictionaries — with skipped symbols, a symbol below min_points and one whose
+    interpolation fails in the batch."""
+    from iv_interpolation_b200 import _lib, device as D
+    from iv_interpolation_b200.batch import PipelineBatch
+
+    monkeypatch.setattr(D, "interp_linear_ffill", FD.interp_linear_ffill)
+    monkeypatch.setattr(D, "ohlcv_reduce", FD.ohlcv_reduce)
+    monkeypatch.setattr(D, "bridge_plan", FD.bridge_plan)
+    monkeypatch.setattr(D, "bridge_ohlcv", FD.bridge_ohlcv)
+    monkeypatch.setattr(H, "_to_device", lambda a, dev: torch.from_numpy(np.array(a, copy=True)))
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(_lib, "lib", lambda: None)                           # the entries check that libivx.so loads before touching data
+
+    def batch(shape):
+        tp = tapes.make_contract_tape(5, 10, rows_per_contract=12)         # 12 hourly rows -> 661 minute rows each
+        frames = {f"c{i}": tp.frame(i) for i in range(tp.n_sym)}
+        if shape == "ragged":
+            frames["c2"] = frames["c2"].iloc[:0]                             # empty -> skipped at every stage
+            frames["c4"] = frames["c4"].iloc[:2]                             # below min_points
+            f = frames["c6"].copy()
+            f["iv"] = np.nan                                                 # nothing left after dropna -> None
+            frames["c6"] = f
+        return frames
+
+    for shape in ("clean", "ragged"):
+        frames = batch(shape)
+        run = lambda whole: PipelineBatch(rng=np.random.RandomState(2), batch_id=7, whole_frames=whole).run(
+            {k: v for k, v in frames.items()})
+        built = []
+        init = H.FrameSlices.__init__
+        monkeypatch.setattr(H.FrameSlices, "__init__", lambda self, big, off: (built.append(len(off) - 1), init(self, big, off))[1])
+        a = run(True)
+        assert built == [len(a[0]), len(a[1])]                               # both hand-overs went by the whole frame ...
+        b = run(False)
+        assert len(built) == 2                                               # ... and none of them here
+        monkeypatch.setattr(H.FrameSlices, "__init__", init)
+        assert len(a[0]) == (10 if shape == "clean" else 7)
+        for k in range(3):
+            assert list(a[k]) == list(b[k])
+            for s in a[k]:
+                pd.testing.assert_frame_equal(a[k][s], b[k][s], check_exact=True)
+        strip = lambda L: [{k: v for k, v in d.items() if k != "processing_time"} for d in L]
+        for name in a[3]:
+            assert strip(a[3][name][0]) == strip(b[3][name][0])
