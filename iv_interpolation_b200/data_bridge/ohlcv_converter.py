@@ -305,7 +305,8 @@ class InterpolatedToOHLCVConverter:
         nf = len(frames)
         n_out = np.diff(out_off)
         ts_all = big[ts_col].to_numpy()
-        ts = ts_all[row]
+        every = len(row) == len(ts_all)                    # every row emitted a candle: `row` is the identity, nothing to gather
+        ts = ts_all if every else ts_all[row]
         if not pipeline:
             if any(np.isnan(cols[k]).any() for k in ("open", "high", "low", "close")):
                 return None
@@ -313,7 +314,7 @@ class InterpolatedToOHLCVConverter:
                 fid = np.repeat(np.arange(nf), n_out)
                 if ((ts[1:] < ts[:-1]) & (fid[1:] == fid[:-1])).any():
                     return None
-        data = {"symbol": big["symbol"].array.take(row), "timestamp": ts}
+        data = {"symbol": big["symbol"].array if every else big["symbol"].array.take(row), "timestamp": ts}
         for k in ("open", "high", "low", "close", "volume", "source_price"):
             data[k] = cols[k]
         if not pipeline:
