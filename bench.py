@@ -851,7 +851,8 @@ def bench_contracts(ctx, args, peak):
     shard = _ct_build_shard(mine, n_c, nan_frac=args.ct_nan_frac, drop_frac=args.ct_drop_frac)
     t_tape = time.perf_counter() - t0
     n_win = max(1, args.ct_windows)            # replay: the same contracts over consecutive 20-day windows (timestamps shifted per window)
-    stream = CT.HostContractStream(dev, max_rows_per_batch=args.ct_batch_rows, seed=7)
+    pipe_fused = not args.ct_two_step_bridge
+    stream = CT.HostContractStream(dev, max_rows_per_batch=args.ct_batch_rows, seed=7, fused_tapes=pipe_fused, want_row=not pipe_fused)
     cuts = stream.batches(shard)
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
 
@@ -894,11 +895,17 @@ def bench_contracts(ctx, args, peak):
     stage_ms = {st: sum(ev[st][0].elapsed_time(ev[st][1]) for step in evs for ev in step) / steps for st in CT.STAGES}
     n_src = int(shard.off[-1]) * n_win
     m_e = 0.03 * minute                       # ~3 % of the volumes are NULL in the tape: exponential draws
-    alg = {"interp_plan": n_src * 80, "interp_exec": rows * 85, "bridge_plan": rows * 16, "bridge_tapes": (5 * minute + m_e) * 8,
-           "bridge_ohlcv": rows * 16 + minute * (40 + 56 + 8) + m_e * 8, "candle_ts": minute * 24,
+    fused = pipe_fused
+    alg = {"interp_plan": n_src * 80, "interp_exec": rows * 85, "bridge_plan": rows * 16,
+           "bridge_tapes": 0 if fused else (5 * minute + m_e) * 8,
+           # fused: base + volume + stamp read per row, six columns + stamp written per candle (no tape, no row index)
+           "bridge_ohlcv": rows * 24 + minute * (48 + 8) if fused else rows * 16 + minute * (40 + 56 + 8) + m_e * 8,
+           "candle_ts": 0 if fused else minute * 24,
            "ohlcv_reduce": minute * 48 + candles * 52}
     kern = {"interp_plan": "k_interp_plan + k_scan_i64 x2", "interp_exec": "k_interp_exec", "bridge_plan": "k_bridge_count_seg + scans + k_bridge_sym_off",
-            "bridge_tapes": "k_random_tape x2", "bridge_ohlcv": "k_bridge_ohlcv_seg + k_bridge_check", "candle_ts": "k_gather<i64>",
+            "bridge_tapes": "none: the draws are made inside the bridge kernel (Philox)" if fused else "k_random_tape x2",
+            "bridge_ohlcv": "k_bridge_ohlcv_seg<GEN> + k_bridge_check" if fused else "k_bridge_ohlcv_seg + k_bridge_check",
+            "candle_ts": "none: the bridge kernel copies the stamps" if fused else "k_gather<i64>",
             "ohlcv_reduce": "k_ohlcv_reduce + k_ohlcv_finalize"}
     stages = {}
     for st in CT.STAGES:
@@ -970,7 +977,7 @@ def bench_contracts(ctx, args, peak):
                 "api": "iv_interpolation_b200.contracts.HostContractStream.run (pinned host source columns in, 5-min candle tables out to pinned host memory)",
                 "result": "the 5-minute candles (8 columns); the interpolated rows and the synthetic 1-minute candles stay on the device"},
         "gpu_launches": launches * world, "tape_build_s": round(t_tape, 2),
-        "data": "synthetic (tapes.make_underlying_tape, seeds fixed per underlying); bridge random tapes from the device counter generator",
+        "data": "synthetic (tapes.make_underlying_tape, seeds fixed per underlying); bridge random draws from the device counter generator (Philox, " + ("inside the bridge kernel" if pipe_fused else "written as tapes") + ")",
     }
     del out, stream
     torch.cuda.empty_cache()
@@ -1212,6 +1219,8 @@ def main():
     ap.add_argument("--ct-windows", type=int, default=1, help="contracts workload: consecutive 20-day windows per underlying (12 ~ one trading year: BASELINE configs[4])")
     ap.add_argument("--ct-nan-frac", type=float, default=0.05, help="contracts workload: share of NaN IVs in the tape")
     ap.add_argument("--ct-drop-frac", type=float, default=0.0, help="contracts workload: share of hourly rows missing altogether (sparse replay tape)")
+    ap.add_argument("--ct-two-step-bridge", action="store_true",
+                    help="contracts workload: write the bridge's random tapes with k_random_tape, read them in the bridge kernel and gather the stamps behind it (the form before the draws moved into the kernel; same candles)")
     ap.add_argument("--ct-batch-rows", type=int, default=48_000_000, help="minute rows per batch of contracts (HBM working set)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

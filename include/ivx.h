@@ -342,6 +342,20 @@ int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const
                      int64_t* o_row, double* o_open, double* o_high, double* o_low, double* o_close,
                      double* o_volume, double* o_source, uint32_t* sym_quality /*n_sym or NULL*/,
                      void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
+/* The same candles with the tapes GENERATED inside the kernel — the reference's normal, unseeded mode (its draws are part of the
+ * row loop, ohlcv_converter.py:209-263,359-369), where no tape has to exist in memory: element i of the uniform tape is
+ * Philox4x32-10(seed, stream_u, i) and element i of the exponential tape -log1p(-Philox(seed, stream_e, i)), i.e. exactly the
+ * numbers ivx_random_tape(n, seed, stream_u / stream_e, kind) writes — 40 B written and 40 B read per candle less than the
+ * two-step form, same candles bit for bit.  ts / o_ts (both or neither): the candle's stamp is copied from its row's, so no
+ * gather pass has to follow; o_row may then be NULL.  trend_following (normals) is not available here. */
+int ivx_bridge_ohlcv_philox(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
+                            const int64_t* ts /*n_rows or NULL*/, int32_t strategy, double base_spread_percent,
+                            double volatility_factor, uint64_t seed, uint32_t stream_u, uint32_t stream_e,
+                            const int64_t* out_off /*n_sym+1*/, const int64_t* e_off /*n_sym+1*/,
+                            const int64_t* seg_out /*n_seg+1 or NULL*/, const int64_t* seg_e /*n_seg+1 or NULL*/,
+                            int64_t* o_row /*or NULL*/, int64_t* o_ts /*or NULL*/, double* o_open, double* o_high, double* o_low,
+                            double* o_close, double* o_volume, double* o_source, uint32_t* sym_quality /*n_sym or NULL*/,
+                            void* workspace, int64_t workspace_bytes, ivx_stream_t stream);
 /* the same quality bits for candles that already exist (ohlcv_converter.py:371-402 on a frame): *flags = OR over n rows */
 int ivx_bridge_quality(int64_t n, const double* open, const double* high, const double* low, const double* close,
                        const double* source_price, uint32_t* flags /*1*/, ivx_stream_t stream);

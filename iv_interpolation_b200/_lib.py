@@ -80,6 +80,8 @@ SIGNATURES = {
     "ivx_bridge_plan": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_bridge_ohlcv": (C.c_int, [_i64, _i64, _p, _p, _p, _i32, C.c_double, C.c_double, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "ivx_bridge_ohlcv_philox": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _i32, C.c_double, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32,
+                                          _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ivx_exclusive_scan_i64": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_gather_i64": (C.c_int, [_i64, _p, _i64, _p, _p, _p]),
     "ivx_gather_f64": (C.c_int, [_i64, _p, _i64, _p, _p, _p]),

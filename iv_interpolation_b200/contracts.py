@@ -51,7 +51,8 @@ class ContractPipeline:
 
     def __init__(self, device: torch.device, *, strategy: str = "spread_simulation", frequency_minutes: int = 5,
                  seed: int = 0, step: int = TP.MINUTE_US, max_span: int = 30 * TP.DAY_US, min_points: int = 10,
-                 base_spread_percent: float = 0.002, volatility_factor: float = 1.5):
+                 base_spread_percent: float = 0.002, volatility_factor: float = 1.5, fused_tapes: bool = True,
+                 want_row: bool = True):
         if strategy not in BRIDGE_STRATEGY or strategy == "trend_following":
             raise IvxError(f"ContractPipeline: strategy {strategy!r} (trend_following takes normals: use device.bridge_ohlcv)")
         self.device = device
@@ -61,6 +62,8 @@ class ContractPipeline:
         self.step, self.max_span, self.min_points = int(step), int(max_span), int(min_points)
         self.spread = dict(base_spread_percent=base_spread_percent, volatility_factor=volatility_factor) \
             if strategy == "spread_simulation" else {}
+        self.fused_tapes = fused_tapes                   # False: tapes written by random_tape, read by the bridge, stamps gathered (A/B)
+        self.want_row = want_row                         # False: the candles keep their stamps only (minute.row is None)
         self.calls = 0
 
     def run(self, off: torch.Tensor, date: torch.Tensor, icols: Sequence[torch.Tensor], fcols: Sequence[torch.Tensor],
@@ -84,20 +87,32 @@ class ContractPipeline:
         mark("bridge_plan", 0)
         bplan = D.bridge_plan(a.out_off, S, vol)
         mark("bridge_plan", 1)
-        mark("bridge_tapes", 0)
-        if tapes is None:
-            k = BRIDGE_U_PER_ROW[BRIDGE_STRATEGY[self.strategy]]
-            u = D.random_tape(k * bplan.total, self.seed, 2 * first_contract, "uniform", like=S)
-            e = D.random_tape(bplan.total_e, self.seed, 2 * first_contract + 1, "exponential", like=S)
+        if tapes is None and self.fused_tapes:
+            # the reference's normal, unseeded mode: the draws are made inside the bridge kernel (Philox keyed by the seed and the
+            # shard's first contract, the numbers random_tape would have written) and the candle stamps are copied there too —
+            # no tape is written or read and no gather pass follows; the two stages below stay in the table at zero
+            mark("bridge_tapes", 0); mark("bridge_tapes", 1)
+            mark("bridge_ohlcv", 0)
+            m = D.bridge_ohlcv_philox(a.out_off, S, vol, bplan, self.strategy, seed=self.seed, stream_u=2 * first_contract,
+                                      stream_e=2 * first_contract + 1, ts=a.ts, want_row=self.want_row, **self.spread)
+            mark("bridge_ohlcv", 1)
+            mark("candle_ts", 0); mark("candle_ts", 1)
+            mts = m.ts
         else:
-            u, e = tapes
-        mark("bridge_tapes", 1)
-        mark("bridge_ohlcv", 0)
-        m = D.bridge_ohlcv(a.out_off, S, vol, bplan, self.strategy, u=u, e=e, **self.spread)
-        mark("bridge_ohlcv", 1)
-        mark("candle_ts", 0)
-        mts = D.gather(m.row, a.ts)
-        mark("candle_ts", 1)
+            mark("bridge_tapes", 0)
+            if tapes is None:
+                k = BRIDGE_U_PER_ROW[BRIDGE_STRATEGY[self.strategy]]
+                u = D.random_tape(k * bplan.total, self.seed, 2 * first_contract, "uniform", like=S)
+                e = D.random_tape(bplan.total_e, self.seed, 2 * first_contract + 1, "exponential", like=S)
+            else:
+                u, e = tapes
+            mark("bridge_tapes", 1)
+            mark("bridge_ohlcv", 0)
+            m = D.bridge_ohlcv(a.out_off, S, vol, bplan, self.strategy, u=u, e=e, **self.spread)
+            mark("bridge_ohlcv", 1)
+            mark("candle_ts", 0)
+            mts = D.gather(m.row, a.ts)
+            mark("candle_ts", 1)
         mark("ohlcv_reduce", 0)
         c = D.ohlcv_reduce(m.out_off, mts, m.open, m.high, m.low, m.close, m.volume,
                            bucket_ticks=self.n * self.step, min_count=self.n, check_len=True)

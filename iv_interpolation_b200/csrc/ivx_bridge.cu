@@ -83,10 +83,31 @@ struct BridgeParams {
   double base_spread_percent, volatility_factor;
   const double *u, *e, *z;
   const int64_t *out_off, *e_off;
-  int64_t* o_row;
+  int64_t* o_row;                                           // may be null in the generated-tape form (o_ts stands for it)
   double *o_open, *o_high, *o_low, *o_close, *o_volume, *o_source;
   uint32_t* sym_quality;
+  // GEN form (ivx_bridge_ohlcv_philox): no tapes in memory — element i of the uniform / exponential tape is Philox(seed, stream, i),
+  // the very numbers ivx_random_tape would have written (40 B written and 40 B read per candle less), and the candle's stamp
+  // is copied from the row's (no gather pass behind the bridge)
+  uint64_t seed;
+  uint32_t stream_u, stream_e;
+  const int64_t* ts;
+  int64_t* o_ts;
 };
+
+// the K uniforms of candle o: elements o K .. o K + K - 1 of the tape, i.e. (K + 1) / 2 Philox blocks (K odd: the run starts on
+// the second double of its first block for odd o)
+template <int K>
+__device__ __forceinline__ void gen_uniforms(const BridgeParams& P, int64_t o, double (&uu)[K > 0 ? K : 1]) {
+  constexpr int NB = (K + 1) / 2;
+  const uint64_t e0 = (uint64_t)o * (uint64_t)K;
+  double v[2 * NB + 2];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) philox_pair((e0 >> 1) + j, P.stream_u, P.seed, v[2 * j], v[2 * j + 1]);
+  const bool odd = (K & 1) && (e0 & 1);
+#pragma unroll
+  for (int k = 0; k < K; ++k) uu[k] = odd ? v[k + 1] : v[k];
+}
 
 // closes of the candles emitted so far in the current symbol (rounded, newest first) — warp-uniform
 struct BridgeState {
@@ -102,7 +123,7 @@ struct BridgeSmem {
 
 // Rows [a, b) of ONE symbol, in chunks of 32, continuing from `st`.  o_base / e_base: candles and exponential draws before
 // row a.  WRITE = false walks the close chain only (the warm-up of a segment that starts inside a symbol).
-template <int STRATEGY, bool WRITE>
+template <int STRATEGY, bool WRITE, bool GEN = false>
 __device__ __forceinline__ void bridge_piece(const BridgeParams& P, const int64_t a, const int64_t b, int64_t& o_base, int64_t& e_base,
                                              BridgeState& st, uint32_t& qflags, BridgeSmem& sm) {
   const int lane = lane_id();
@@ -128,9 +149,24 @@ __device__ __forceinline__ void bridge_piece(const BridgeParams& P, const int64_
     const uint32_t okm = __ballot_sync(IVX_FULL_MASK, ok), nvm = __ballot_sync(IVX_FULL_MASK, nv);
     const int64_t o = o_base + __popc(okm & lt);
     double uu[K > 0 ? K : 1];
+    double ev = 0.0;
+    int64_t tsv = 0;
+    if (GEN) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) uu[k] = (ok && (WRITE || k == 0 || k == 2)) ? ld_stream(P.u + o * K + k) : 0.0;
-    const double ev = (WRITE && nv) ? ld_stream(P.e + e_base + __popc(nvm & lt)) : 0.0;
+      for (int k = 0; k < K; ++k) uu[k] = 0.0;
+      if (WRITE && ok && P.o_ts) tsv = ld_stream(P.ts + r);
+      if (K > 0 && ok) gen_uniforms<K>(P, o, uu);
+      if (WRITE && nv) {
+        const uint64_t ei = (uint64_t)(e_base + __popc(nvm & lt));
+        double ea, eb;
+        philox_pair(ei >> 1, P.stream_e, P.seed, ea, eb);
+        ev = exp_variate((ei & 1) ? eb : ea);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) uu[k] = (ok && (WRITE || k == 0 || k == 2)) ? ld_stream(P.u + o * K + k) : 0.0;
+      ev = (WRITE && nv) ? ld_stream(P.e + e_base + __popc(nvm & lt)) : 0.0;
+    }
     double op = 0.0, hp = 0.0, lp = 0.0, cp = 0.0;         // unrounded open/high/low, ROUNDED close
     if (STRATEGY == ST_SPREAD) {
       const double vm = uni(0.5, P.volatility_factor, uu[0]);                  // :215
@@ -258,7 +294,8 @@ __device__ __forceinline__ void bridge_piece(const BridgeParams& P, const int64_
       double v = nv ? 50.0 * ev : vin;                                          // :373-376
       v = v > 0.0 ? v : 0.0;                                                    // max(0, volume) :378
       const double ro = round_np<4>(op), rh = round_np<4>(hp), rl = round_np<4>(lp);
-      st_stream(P.o_row + o, r);
+      if (!GEN || P.o_row) st_stream(P.o_row + o, r);
+      if (GEN && P.o_ts) st_stream(P.o_ts + o, tsv);
       st_stream(P.o_open + o, ro); st_stream(P.o_high + o, rh); st_stream(P.o_low + o, rl); st_stream(P.o_close + o, cp);
       st_stream(P.o_volume + o, round_np<6>(v));
       st_stream(P.o_source + o, bp);
@@ -276,7 +313,7 @@ __device__ __forceinline__ void bridge_piece(const BridgeParams& P, const int64_
 
 // ---- one warp per SYMBOL: exact by construction.  Used for trend_following (a five-close memory: its contraction is too
 // slow for the segment warm-up below) and, with `only_if` set, as the stream-ordered fallback of the segmented kernel ----
-template <int STRATEGY>
+template <int STRATEGY, bool GEN = false>
 __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P, const int32_t* __restrict__ only_if) {
   if (only_if && *only_if == 0) return;
   __shared__ BridgeSmem sm;
@@ -285,7 +322,7 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P, cons
   int64_t o_base = P.out_off[s], e_base = P.e_off[s];
   BridgeState st = fresh_state();
   uint32_t qflags = 0;
-  bridge_piece<STRATEGY, true>(P, P.in_off[s], P.in_off[s + 1], o_base, e_base, st, qflags, sm);
+  bridge_piece<STRATEGY, true, GEN>(P, P.in_off[s], P.in_off[s + 1], o_base, e_base, st, qflags, sm);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) qflags |= __shfl_xor_sync(IVX_FULL_MASK, qflags, d);
   if (lane_id() == 0 && P.sym_quality) P.sym_quality[s] = qflags;
@@ -296,13 +333,13 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv(const BridgeParams P, cons
 // candle index of a row is the number of emitting rows before it — symbol boundaries do not enter — so two scans over
 // per-segment counts place every segment in the outputs and in the tapes.
 // A segment that starts INSIDE a symbol needs the carried close of the row before it.  It is obtained by walking the
-// close chain over the WARM rows before the segment from a fresh state: the chain forgets its start at 0.15 per emitted
+// close chain over the WARM_MIN (or, where few of them emit, WARM) rows before the segment from a fresh state: the chain forgets its start at 0.15 per emitted
 // row (see bridge_piece), so after a few dozen emitted rows the walk is ON the true trajectory — and that is CHECKED,
 // not assumed: every segment records the state it entered with and the state it left with, k_bridge_check compares each
 // speculative entry with its predecessor's exit bit for bit (by induction from the segments that start a symbol or
 // whose warm-up reaches the symbol's start, all states are then the sequential ones), and any mismatch raises a flag on
 // which the per-symbol kernel above — enqueued right behind, idle otherwise — recomputes the batch exactly.
-constexpr int SEG = 2048, WARM = 256;
+constexpr int SEG = 2048, WARM = 256, WARM_MIN = 64, WARM_EMIT = 32;
 struct SegArrays {
   int64_t n_seg;
   const int64_t *seg_out, *seg_e;       // [n_seg + 1] candles / exponential draws before each segment
@@ -356,8 +393,11 @@ __global__ void __launch_bounds__(256) k_bridge_sym_off(int64_t n_sym, int64_t n
   if (lane == 0) { out_off[s] = seg_out[g] + c_ok; e_off[s] = seg_e[g] + c_e; }
 }
 
-template <int STRATEGY>
-__global__ void __launch_bounds__(128) k_bridge_ohlcv_seg(const BridgeParams P, const SegArrays A, int64_t n_rows) {
+#ifndef IVX_BRIDGE_GEN_CTAS
+#define IVX_BRIDGE_GEN_CTAS 6                          // 80 registers: 24 warps per SM (99 registers and 20 warps unbounded: 7 % slower)
+#endif
+template <int STRATEGY, bool GEN = false>
+__global__ void __launch_bounds__(128, GEN ? IVX_BRIDGE_GEN_CTAS : 1) k_bridge_ohlcv_seg(const BridgeParams P, const SegArrays A, int64_t n_rows) {
   __shared__ BridgeSmem sm;
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= A.n_seg) return;
@@ -371,14 +411,23 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv_seg(const BridgeParams P, 
   uint32_t dummy_flags = 0;
   int32_t spec = 0;
   if (STRATEGY == ST_SPREAD && r0 > sym_start) {
-    const int64_t ws = max(sym_start, r0 - WARM);
-    spec = ws > sym_start ? 1 : 0;
+    // WARM_MIN rows back when those hold WARM_EMIT emitting rows (the chain forgets its start at 0.15 per EMITTED row:
+    // 0.15^32 = 4e-27 of the first guess's error), WARM rows back on a stretch full of rows that emit nothing
+    int64_t ws = max(sym_start, r0 - WARM_MIN);
     int cnt = 0;                                       // emitting rows in [ws, r0): where the warm-up's uniforms start
     for (int64_t r = ws + lane; r < r0; r += 32) cnt += row_ok(ld_stream(P.base + r)) ? 1 : 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(IVX_FULL_MASK, cnt, d);
+    if (cnt < WARM_EMIT && ws > sym_start) {
+      ws = max(sym_start, r0 - WARM);
+      cnt = 0;
+      for (int64_t r = ws + lane; r < r0; r += 32) cnt += row_ok(ld_stream(P.base + r)) ? 1 : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(IVX_FULL_MASK, cnt, d);
+    }
+    spec = ws > sym_start ? 1 : 0;
     int64_t o_w = o_base - cnt, e_w = 0;
-    bridge_piece<STRATEGY, false>(P, ws, r0, o_w, e_w, st, dummy_flags, sm);
+    bridge_piece<STRATEGY, false, GEN>(P, ws, r0, o_w, e_w, st, dummy_flags, sm);
   }
   if (lane == 0) { A.entry_pc[g] = st.pc1; A.entry_has[g] = st.n_prev > 0; A.spec[g] = spec; }
   // the segment's rows, symbol piece after symbol piece
@@ -387,7 +436,7 @@ __global__ void __launch_bounds__(128) k_bridge_ohlcv_seg(const BridgeParams P, 
     const int64_t b = min(r1, sym_end);
     if (b > a) {
       uint32_t qflags = 0;
-      bridge_piece<STRATEGY, true>(P, a, b, o_base, e_base, st, qflags, sm);
+      bridge_piece<STRATEGY, true, GEN>(P, a, b, o_base, e_base, st, qflags, sm);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) qflags |= __shfl_xor_sync(IVX_FULL_MASK, qflags, d);
       if (lane == 0 && P.sym_quality && qflags) atomicOr(P.sym_quality + sym, qflags);
@@ -467,6 +516,55 @@ extern "C" int ivx_bridge_plan(int64_t n_sym, int64_t n_rows, const int64_t* in_
   return IVX_OK;
 }
 
+// the launches behind ivx_bridge_ohlcv (tapes in memory) and ivx_bridge_ohlcv_philox (GEN: tapes generated in the kernel)
+template <bool GEN>
+static int bridge_launch(const BridgeParams& P, int64_t n_rows, int32_t force_fallback, const int64_t* seg_out, const int64_t* seg_e,
+                         void* workspace, int64_t workspace_bytes, cudaStream_t stream, const char* who) {
+  const int strategy = P.strategy;
+  const int64_t n_sym = P.n_sym;
+  const unsigned blocks = (unsigned)((n_sym + 3) / 4);
+  if (strategy == ST_TREND || workspace == nullptr || seg_out == nullptr || seg_e == nullptr) {   // one warp per symbol
+    switch (strategy) {
+      case ST_SPREAD: k_bridge_ohlcv<ST_SPREAD, GEN><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      case ST_MIDPOINT: k_bridge_ohlcv<ST_MIDPOINT, GEN><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      case ST_TREND: k_bridge_ohlcv<ST_TREND, false><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      case ST_SIMPLE: k_bridge_ohlcv<ST_SIMPLE, GEN><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+      default: k_bridge_ohlcv<ST_PIPELINE, GEN><<<blocks, 128, 0, stream>>>(P, nullptr); break;
+    }
+    IVX_LAUNCH_CHECK("k_bridge_ohlcv");
+    return IVX_OK;
+  }
+  // one warp per segment of SEG rows
+  IVX_REQUIRE(workspace_bytes >= ivx_bridge_workspace_bytes(n_rows), IVX_ERR_INVALID_ARG, "%s: workspace too small", who);
+  const int64_t g = (n_rows + SEG - 1) / SEG;
+  Carver cv(workspace, workspace_bytes);
+  SegArrays A;
+  A.n_seg = g; A.seg_out = seg_out; A.seg_e = seg_e;
+  A.entry_pc = cv.take<double>(g); A.exit_pc = cv.take<double>(g);
+  A.entry_has = cv.take<int32_t>(g); A.exit_has = cv.take<int32_t>(g); A.spec = cv.take<int32_t>(g);
+  A.flag = cv.take<int32_t>(1);
+  IVX_REQUIRE(cv.ok(), IVX_ERR_INVALID_ARG, "%s: workspace too small", who);
+  IVX_CUDA(cudaMemsetAsync(A.flag, 0, sizeof(int32_t), stream));
+  if (P.sym_quality) IVX_CUDA(cudaMemsetAsync(P.sym_quality, 0, (size_t)n_sym * sizeof(uint32_t), stream));
+  const unsigned sblocks = (unsigned)((g + 3) / 4);
+  switch (strategy) {
+    case ST_SPREAD: k_bridge_ohlcv_seg<ST_SPREAD, GEN><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+    case ST_MIDPOINT: k_bridge_ohlcv_seg<ST_MIDPOINT, GEN><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+    case ST_SIMPLE: k_bridge_ohlcv_seg<ST_SIMPLE, GEN><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+    default: k_bridge_ohlcv_seg<ST_PIPELINE, GEN><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
+  }
+  IVX_LAUNCH_CHECK("k_bridge_ohlcv_seg");
+  if (strategy == ST_SPREAD) {
+    // the carried closes the segments assumed are checked against the ones their predecessors produced; on a mismatch
+    // (never seen; ~1e-9 per boundary by the contraction argument) the per-symbol kernel recomputes the batch, stream-ordered
+    k_bridge_check<<<(unsigned)((g + 255) / 256), 256, 0, stream>>>(A, force_fallback);
+    IVX_LAUNCH_CHECK("k_bridge_check");
+    k_bridge_ohlcv<ST_SPREAD, GEN><<<blocks, 128, 0, stream>>>(P, A.flag);
+    IVX_LAUNCH_CHECK("k_bridge_ohlcv(fallback)");
+  }
+  return IVX_OK;
+}
+
 extern "C" int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
                                 int32_t strategy, double base_spread_percent, double volatility_factor, const double* u,
                                 const double* e, const double* z, const int64_t* out_off, const int64_t* e_off,
@@ -487,48 +585,31 @@ extern "C" int ivx_bridge_ohlcv(int64_t n_sym, int64_t n_rows, const int64_t* in
   IVX_REQUIRE(strategy == ST_TREND ? z != nullptr : u != nullptr, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: the strategy's tape is missing");
   IVX_REQUIRE(e != nullptr, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: the exponential tape is missing (pass any valid pointer when it is empty)");
   BridgeParams P{n_sym, in_off, base, volume, strategy, base_spread_percent, volatility_factor, u, e, z, out_off, e_off,
-                 o_row, o_open, o_high, o_low, o_close, o_volume, o_source, sym_quality};
-  const unsigned blocks = (unsigned)((n_sym + 3) / 4);
-  if (strategy == ST_TREND || workspace == nullptr || seg_out == nullptr || seg_e == nullptr) {   // one warp per symbol
-    switch (strategy) {
-      case ST_SPREAD: k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P, nullptr); break;
-      case ST_MIDPOINT: k_bridge_ohlcv<ST_MIDPOINT><<<blocks, 128, 0, stream>>>(P, nullptr); break;
-      case ST_TREND: k_bridge_ohlcv<ST_TREND><<<blocks, 128, 0, stream>>>(P, nullptr); break;
-      case ST_SIMPLE: k_bridge_ohlcv<ST_SIMPLE><<<blocks, 128, 0, stream>>>(P, nullptr); break;
-      default: k_bridge_ohlcv<ST_PIPELINE><<<blocks, 128, 0, stream>>>(P, nullptr); break;
-    }
-    IVX_LAUNCH_CHECK("k_bridge_ohlcv");
-    return IVX_OK;
-  }
-  // one warp per segment of SEG rows
-  IVX_REQUIRE(workspace_bytes >= ivx_bridge_workspace_bytes(n_rows), IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: workspace too small");
-  const int64_t g = (n_rows + SEG - 1) / SEG;
-  Carver cv(workspace, workspace_bytes);
-  SegArrays A;
-  A.n_seg = g; A.seg_out = seg_out; A.seg_e = seg_e;
-  A.entry_pc = cv.take<double>(g); A.exit_pc = cv.take<double>(g);
-  A.entry_has = cv.take<int32_t>(g); A.exit_has = cv.take<int32_t>(g); A.spec = cv.take<int32_t>(g);
-  A.flag = cv.take<int32_t>(1);
-  IVX_REQUIRE(cv.ok(), IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv: workspace too small");
-  IVX_CUDA(cudaMemsetAsync(A.flag, 0, sizeof(int32_t), stream));
-  if (sym_quality) IVX_CUDA(cudaMemsetAsync(sym_quality, 0, (size_t)n_sym * sizeof(uint32_t), stream));
-  const unsigned sblocks = (unsigned)((g + 3) / 4);
-  switch (strategy) {
-    case ST_SPREAD: k_bridge_ohlcv_seg<ST_SPREAD><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
-    case ST_MIDPOINT: k_bridge_ohlcv_seg<ST_MIDPOINT><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
-    case ST_SIMPLE: k_bridge_ohlcv_seg<ST_SIMPLE><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
-    default: k_bridge_ohlcv_seg<ST_PIPELINE><<<sblocks, 128, 0, stream>>>(P, A, n_rows); break;
-  }
-  IVX_LAUNCH_CHECK("k_bridge_ohlcv_seg");
-  if (strategy == ST_SPREAD) {
-    // the carried closes the segments assumed are checked against the ones their predecessors produced; on a mismatch
-    // (never seen; ~1e-9 per boundary by the contraction argument) the per-symbol kernel recomputes the batch, stream-ordered
-    k_bridge_check<<<(unsigned)((g + 255) / 256), 256, 0, stream>>>(A, force_fallback);
-    IVX_LAUNCH_CHECK("k_bridge_check");
-    k_bridge_ohlcv<ST_SPREAD><<<blocks, 128, 0, stream>>>(P, A.flag);
-    IVX_LAUNCH_CHECK("k_bridge_ohlcv(fallback)");
-  }
-  return IVX_OK;
+                 o_row, o_open, o_high, o_low, o_close, o_volume, o_source, sym_quality, 0, 0, 0, nullptr, nullptr};
+  return bridge_launch<false>(P, n_rows, force_fallback, seg_out, seg_e, workspace, workspace_bytes, stream, "ivx_bridge_ohlcv");
+}
+
+extern "C" int ivx_bridge_ohlcv_philox(int64_t n_sym, int64_t n_rows, const int64_t* in_off, const double* base, const double* volume,
+                                       const int64_t* ts, int32_t strategy, double base_spread_percent, double volatility_factor,
+                                       uint64_t seed, uint32_t stream_u, uint32_t stream_e, const int64_t* out_off,
+                                       const int64_t* e_off, const int64_t* seg_out, const int64_t* seg_e, int64_t* o_row,
+                                       int64_t* o_ts, double* o_open, double* o_high, double* o_low, double* o_close,
+                                       double* o_volume, double* o_source, uint32_t* sym_quality, void* workspace,
+                                       int64_t workspace_bytes, ivx_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n_sym >= 0 && n_rows >= 0, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv_philox: negative size");
+  const int32_t force_fallback = (strategy & IVX_BRIDGE_RECOMPUTE) ? 1 : 0;
+  strategy &= ~IVX_BRIDGE_RECOMPUTE;
+  IVX_REQUIRE(strategy >= ST_SPREAD && strategy <= ST_PIPELINE && strategy != ST_TREND, IVX_ERR_INVALID_ARG,
+              "ivx_bridge_ohlcv_philox: strategy %d (trend_following draws normals: pass a tape to ivx_bridge_ohlcv)", strategy);
+  if (n_sym == 0 || n_rows == 0) return IVX_OK;
+  IVX_REQUIRE(in_off && base && volume && out_off && e_off && o_open && o_high && o_low && o_close && o_volume && o_source,
+              IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv_philox: null pointer");
+  IVX_REQUIRE((o_ts == nullptr) || (ts != nullptr), IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv_philox: o_ts without ts");
+  IVX_REQUIRE(o_row || o_ts, IVX_ERR_INVALID_ARG, "ivx_bridge_ohlcv_philox: neither o_row nor o_ts: the candles would have no key");
+  BridgeParams P{n_sym, in_off, base, volume, strategy, base_spread_percent, volatility_factor, nullptr, nullptr, nullptr, out_off, e_off,
+                 o_row, o_open, o_high, o_low, o_close, o_volume, o_source, sym_quality, seed, stream_u, stream_e, ts, o_ts};
+  return bridge_launch<true>(P, n_rows, force_fallback, seg_out, seg_e, workspace, workspace_bytes, stream, "ivx_bridge_ohlcv_philox");
 }
 
 extern "C" int ivx_bridge_quality(int64_t n, const double* open, const double* high, const double* low, const double* close,

@@ -155,6 +155,46 @@ __device__ __forceinline__ int64_t warp_upper_le(const T* __restrict__ key, int6
   return lo;
 }
 
+// ---- counter-based random tapes (Philox4x32-10): element i of a tape is a function of (seed, stream, i) alone, so a tape
+// written by k_random_tape (ivx_util.cu) and the same elements generated inside a consumer (ivx_bridge.cu) are the same numbers
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+  const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+  c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+}
+
+// 128 random bits for counter (idx, stream) under key `seed`
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t idx, uint32_t stream, uint64_t seed) {
+  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = stream, c3 = 0;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// 53-bit uniform in [0, 1) from two words: numpy's random_sample construction, ((a >> 5) 2^26 + (b >> 6)) / 2^53.  The two
+// integers are placed in the mantissas of 2^78 and 2^52 (no int-to-double conversion: those go through the narrow fp64
+// pipe) and scaled by exact fused multiply-adds: hi 2^-27 + lo 2^-53, every step exact, so the value does not depend on how
+// the translation unit contracts multiplies and adds (ivx_bridge.cu is compiled with --fmad=false).
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  const double H = __hiloint2double(0x44D00000, (int)(a >> 5));          // 2^78 + (a >> 5) 2^26
+  const double L = __hiloint2double(0x43300000, (int)(b >> 6));          // 2^52 + (b >> 6)
+  const double s = 1.0 / 9007199254740992.0;                              // 2^-53
+  return fma(H, s, -33554432.0) + fma(L, s, -0.5);                        // (H - 2^78) 2^-53 + (L - 2^52) 2^-53
+}
+
+// standard exponential from a uniform in [0, 1)
+__device__ __forceinline__ double exp_variate(double u) { return -log1p(-u); }
+// element i of the uniform tape (seed, stream): block i >> 1, first or second double of it
+__device__ __forceinline__ void philox_pair(uint64_t block, uint32_t stream, uint64_t seed, double& a, double& b) {
+  const uint4 r = philox4x32_10(block, stream, seed);
+  a = u53(r.x, r.y); b = u53(r.z, r.w);
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

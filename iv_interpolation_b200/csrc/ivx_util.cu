@@ -13,30 +13,6 @@
 namespace ivx {
 namespace {
 
-__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-  const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-  const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-  c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-}
-
-// 128 random bits for counter (idx, stream) under key `seed`
-__device__ __forceinline__ uint4 philox4x32_10(uint64_t idx, uint32_t stream, uint64_t seed) {
-  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = stream, c3 = 0;
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c0, c1, c2, c3, k0, k1);
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-
-// 53-bit uniform in [0, 1) from two words: numpy's random_sample construction, (a >> 5) * 2^26 + (b >> 6)) / 2^53
-__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
-  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
-}
-
 // out[2j], out[2j+1] from one Philox block; kind 0: uniform [0,1); kind 1: standard exponential -log(1-u)
 __global__ void __launch_bounds__(256) k_random_tape(int64_t n, uint64_t seed, uint32_t stream, int32_t kind, double* __restrict__ out) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -44,7 +20,7 @@ __global__ void __launch_bounds__(256) k_random_tape(int64_t n, uint64_t seed, u
   if (i >= n) return;
   const uint4 r = philox4x32_10((uint64_t)j, stream, seed);
   double a = u53(r.x, r.y), b = u53(r.z, r.w);
-  if (kind == 1) { a = -log1p(-a); b = -log1p(-b); }
+  if (kind == 1) { a = exp_variate(a); b = exp_variate(b); }
   if (i + 1 < n && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0)) {
     __stcs(reinterpret_cast<double2*>(out + i), make_double2(a, b));
   } else {

@@ -624,6 +624,7 @@ class BridgeBatch:
     source_price: torch.Tensor
     sym_quality: torch.Tensor      # int32[n_sym] bit flags of _validate_ohlcv_quality
     total: int
+    ts: Optional[torch.Tensor] = None      # int64[m] stamp of each candle (bridge_ohlcv_philox with ts=; `row` may then be None)
 
 
 def bridge_plan(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor) -> BridgePlan:
@@ -681,6 +682,40 @@ def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor,
           "ivx_bridge_ohlcv")
     _count("bridge_ohlcv_seg" if use_seg else "bridge_ohlcv")
     return BridgeBatch(plan.out_off, row, *cols, q, m)
+
+
+def bridge_ohlcv_philox(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor, plan: BridgePlan, strategy: str, *,
+                        seed: int, stream_u: int, stream_e: int, ts: Optional[torch.Tensor] = None, want_row: bool = True,
+                        base_spread_percent: float = 0.002, volatility_factor: float = 1.5, segmented: bool = True,
+                        recompute: bool = False) -> BridgeBatch:
+    """``bridge_ohlcv`` with the tapes generated inside the kernel: the candles are bit-equal to
+    ``bridge_ohlcv(u=random_tape(k m, seed, stream_u), e=random_tape(m_e, seed, stream_e, "exponential"))`` without the tapes ever
+    being written or read.  ``ts`` (int64 per input row): the candles' stamps come back in ``.ts`` (no gather behind the
+    bridge); ``want_row=False`` then leaves ``.row`` out."""
+    code = _lib.BRIDGE_STRATEGY[strategy]
+    if code == 2:
+        raise _lib.IvxError("bridge_ohlcv_philox: trend_following draws normals (pass a tape to bridge_ohlcv)")
+    if ts is None and not want_row:
+        raise _lib.IvxError("bridge_ohlcv_philox: want_row=False needs ts")
+    n_sym, m = in_off.numel() - 1, plan.total
+    cols = [_empty(m, torch.float64, base) for _ in range(6)]
+    row = _empty(m, torch.int64, base) if want_row else None
+    o_ts = _empty(m, torch.int64, base) if ts is not None else None
+    q = torch.zeros(n_sym, dtype=torch.int32, device=base.device)
+    ws, wsb = None, 0
+    if segmented:
+        wsb = lib().ivx_bridge_workspace_bytes(base.numel())
+        ws = torch.empty(wsb, dtype=torch.uint8, device=base.device)
+    check(lib().ivx_bridge_ohlcv_philox(n_sym, base.numel(), _ptr(in_off), _ptr(_req(base, torch.float64, "base")),
+                                        _ptr(_req(volume, torch.float64, "volume")), _ptr(_req(ts, torch.int64, "ts")) if ts is not None else None,
+                                        code | (_lib.BRIDGE_RECOMPUTE if recompute else 0), float(base_spread_percent), float(volatility_factor),
+                                        int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_u) & 0xFFFFFFFF, int(stream_e) & 0xFFFFFFFF,
+                                        _ptr(plan.out_off), _ptr(plan.e_off), _ptr(plan.seg_out) if segmented else None,
+                                        _ptr(plan.seg_e) if segmented else None, _ptr(row), _ptr(o_ts), *(_ptr(c) for c in cols), _ptr(q),
+                                        _ptr(ws), wsb, _stream()),
+          "ivx_bridge_ohlcv_philox")
+    _count("bridge_ohlcv_seg" if segmented else "bridge_ohlcv")
+    return BridgeBatch(plan.out_off, row, *cols, q, m, o_ts)
 
 
 def bridge_quality(o: torch.Tensor, h: torch.Tensor, l: torch.Tensor, c: torch.Tensor, src: torch.Tensor) -> int:

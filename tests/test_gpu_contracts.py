@@ -135,3 +135,57 @@ def test_host_stream_equals_resident_and_counts_its_copies(dev):
     torch.cuda.synchronize()
     m = out["tables"][-1]["timestamp"].numel()
     assert _eq(stream.ring["close"][:m].numpy(), h(out["tables"][-1]["close"]))
+
+
+@pytest.mark.parametrize("strategy", ["spread_simulation", "pipeline", "simple_spread", "price_as_midpoint"])
+def test_bridge_with_generated_tapes_equals_the_bridge_on_written_tapes(dev, strategy):
+    """ivx_bridge_ohlcv_philox draws inside the kernel what ivx_random_tape would have written: the candles (and the quality bits)
+    are bit-equal to the two-step form, per segment and per symbol, with rows that emit nothing, NULL volumes (exponential
+    draws) and symbols shorter and longer than a 2048-row segment; the stamps it copies are the gathered ones."""
+    import torch
+    from iv_interpolation_b200 import _lib, device as D
+    rng = np.random.default_rng(8)
+    lens = np.array([5, 0, 3000, 1, 2047, 2049, 700, 4500, 33], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    n = int(off[-1])
+    base = 100.0 + np.cumsum(rng.normal(0, 0.05, n))
+    base[rng.random(n) < 0.03] = np.nan
+    base[rng.random(n) < 0.01] = -1.0
+    vol = rng.exponential(5.0, n)
+    vol[rng.random(n) < 0.2] = np.nan
+    vol[rng.random(n) < 0.05] = 0.0
+    ts = (np.arange(n, dtype=np.int64) * 60_000_000 + 1_700_000_000_000_000)
+    d_off, d_base, d_vol, d_ts = _t(off, dev), _t(base, dev), _t(vol, dev), _t(ts, dev)
+    plan = D.bridge_plan(d_off, d_base, d_vol)
+    assert 0 < plan.total_e < plan.total < n
+    k = _lib.BRIDGE_U_PER_ROW[_lib.BRIDGE_STRATEGY[strategy]]
+    u = D.random_tape(k * plan.total, 1234, 6, "uniform", like=d_base)
+    e = D.random_tape(plan.total_e, 1234, 7, "exponential", like=d_base)
+    want = D.bridge_ohlcv(d_off, d_base, d_vol, plan, strategy, u=u, e=e)
+    cols = ("open", "high", "low", "close", "volume", "source_price")
+    for seg in (True, False):
+        got = D.bridge_ohlcv_philox(d_off, d_base, d_vol, plan, strategy, seed=1234, stream_u=6, stream_e=7, ts=d_ts, segmented=seg)
+        assert torch.equal(got.row, want.row) and torch.equal(got.sym_quality, want.sym_quality)
+        assert torch.equal(got.ts, d_ts[want.row])
+        for c in cols:
+            assert torch.equal(getattr(got, c).view(torch.int64), getattr(want, c).view(torch.int64)), (strategy, seg, c)
+    bare = D.bridge_ohlcv_philox(d_off, d_base, d_vol, plan, strategy, seed=1234, stream_u=6, stream_e=7, ts=d_ts, want_row=False)
+    assert bare.row is None and torch.equal(bare.ts, d_ts[want.row]) and torch.equal(bare.close, want.close)
+    other = D.bridge_ohlcv_philox(d_off, d_base, d_vol, plan, strategy, seed=1235, stream_u=6, stream_e=7)
+    assert other.ts is None and not torch.equal(other.close, want.close)
+    with pytest.raises(_lib.IvxError):
+        D.bridge_ohlcv_philox(d_off, d_base, d_vol, plan, "trend_following", seed=1, stream_u=0, stream_e=1)
+
+
+def test_contract_pipeline_fused_tapes_equal_the_two_step_form(dev):
+    from iv_interpolation_b200 import contracts as CT, tapes
+    import torch
+    tp = tapes.make_underlying_tape(5, 30, rows_per_contract=97)
+    args = (_t(tp.off, dev), _t(tp.date, dev), [_t(tp.cols[c], dev) for c in tapes.INTERP_COLS], [_t(tp.cols[c], dev) for c in tapes.FILL_NUM_COLS])
+    a = CT.ContractPipeline(dev, seed=3, fused_tapes=True).run(*args, first_contract=40)
+    b = CT.ContractPipeline(dev, seed=3, fused_tapes=False).run(*args, first_contract=40)
+    assert a.candles.total == b.candles.total > 0 and torch.equal(a.minute_ts, b.minute_ts) and torch.equal(a.minute.row, b.minute.row)
+    for c in ("open", "high", "low", "close", "volume"):
+        assert torch.equal(getattr(a.minute, c).view(torch.int64), getattr(b.minute, c).view(torch.int64)), c
+        assert torch.equal(getattr(a.candles, c).view(torch.int64), getattr(b.candles, c).view(torch.int64)), c
+    assert torch.equal(a.candles.ts, b.candles.ts)
