@@ -968,8 +968,13 @@ def bench_contracts(ctx, args, peak):
                      "imbalance_max_over_mean": round(SH.imbalance(costs, shards), 4), "underlyings_per_rank": [len(x) for x in shards],
                      "minute_rows_per_rank": [int(x) for x in per_rank_rows]},
         "stages": stages,
-        "roofline": {"kernel": kern[dom], "stage": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": stages[dom]["frac_hbm"], "traffic": None},
+        "roofline": {"kernel": kern[dom], "stage": dom, "bound": "issue" if (dom == "bridge_ohlcv" and pipe_fused) else "hbm",
+                     "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac_hbm"], "traffic": None,
+                     **({"hbm_frac": stages[dom]["frac_hbm"], "issue_active_frac": 0.72, "fp64_pipe_frac": 0.31,
+                         "limiter": "instruction issue: with the random draws made inside the kernel 26 % of its instructions are Philox and the "
+                                    "53-bit assembly (profiles/ncu_r2e_bridge_philox_summary.json, srcprof_r2e_bridge_philox.txt); `achieved`/`frac` stay "
+                                    "the algorithmic bytes (24 B read per row, 56 B written per candle) over the stage time against the HBM copy peak"}
+                        if (dom == "bridge_ohlcv" and pipe_fused) else {})},
         "e2e": {"value": rows_all / (ms_e2e / 1e3), "unit": CT_UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "wall_ms_per_step": wall * 1e3, "gather_ms": ms_gather,
                 "gather": ("sharding.gather_tables over NCCL: the 5-min candle tables of all ranks land on rank 0 (point to point, "

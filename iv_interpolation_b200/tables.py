@@ -234,18 +234,15 @@ def pipeline_table(table: pa.Table, *, min_points: int = 10, strategy: str = "sp
     back: "interpolated", "minute", "candles".  The bridge's random numbers come from the device's counter generator keyed
     by ``seed`` (the reference draws from an unseeded generator; seeded parity runs go through the DataFrame classes)."""
     from . import device as D
-    from ._lib import BRIDGE_STRATEGY, BRIDGE_U_PER_ROW
     n = parse_frequency(target_frequency)
     g, num_names, str_names, a = _task1_device(table, min_points)
     if "volume" not in num_names:
         raise KeyError("volume")
     S, vol = a.interp[1], a.fill[num_names.index("volume")]
     bplan = D.bridge_plan(a.out_off, S, vol)
-    k = BRIDGE_U_PER_ROW[BRIDGE_STRATEGY[strategy]]
-    u = D.random_tape(k * bplan.total, seed, 0, "uniform", like=S)
-    e = D.random_tape(bplan.total_e, seed, 1, "exponential", like=S)
-    m = D.bridge_ohlcv(a.out_off, S, vol, bplan, strategy, u=u, e=e)
-    mts = D.gather(m.row, a.ts)
+    # the draws are made inside the bridge kernel (the elements random_tape(seed, stream 0 / 1) would hold) and the stamps copied there
+    m = D.bridge_ohlcv_philox(a.out_off, S, vol, bplan, strategy, seed=seed, stream_u=0, stream_e=1, ts=a.ts, want_row=False)
+    mts = m.ts
     step = 60 * F.ticks_per_second(g.unit)
     c = D.ohlcv_reduce(m.out_off, mts, m.open, m.high, m.low, m.close, m.volume, bucket_ticks=n * step, min_count=n, check_len=True)
     out: Dict[str, object] = {"symbols": g.symbols}
@@ -276,7 +273,6 @@ def pipeline_table(table: pa.Table, *, min_points: int = 10, strategy: str = "sp
 def bridge_table(table: pa.Table, strategy: str = "spread_simulation", seed: int = 0) -> pa.Table:
     """Interpolated rows (``symbol, date|timestamp, underlying_price, volume``) -> synthetic 1-minute candles, device tapes."""
     from . import device as D
-    from ._lib import BRIDGE_STRATEGY, BRIDGE_U_PER_ROW
     tcol = "timestamp" if "timestamp" in table.column_names else "date"
     g = group_by_symbol(table, tcol)
     dev = _dev()
@@ -287,9 +283,7 @@ def bridge_table(table: pa.Table, strategy: str = "spread_simulation", seed: int
     vol = _t(_ordered(_f64(table["volume"]), g), dev) if "volume" in table.column_names else S.new_zeros(S.numel())
     off, ts = _t(g.off, dev), _t(g.ticks, dev)
     bplan = D.bridge_plan(off, S, vol)
-    k = BRIDGE_U_PER_ROW[BRIDGE_STRATEGY[strategy]]
-    m = D.bridge_ohlcv(off, S, vol, bplan, strategy, u=D.random_tape(k * bplan.total, seed, 0, "uniform", like=S),
-                       e=D.random_tape(bplan.total_e, seed, 1, "exponential", like=S))
-    h = d2h_many([m.out_off, D.gather(m.row, ts), m.open, m.high, m.low, m.close, m.volume, m.source_price])
+    m = D.bridge_ohlcv_philox(off, S, vol, bplan, strategy, seed=seed, stream_u=0, stream_e=1, ts=ts, want_row=False)
+    h = d2h_many([m.out_off, m.ts, m.open, m.high, m.low, m.close, m.volume, m.source_price])
     return pa.table({"symbol": _symbol_column(g, h[0]), "timestamp": _stamps(h[1], g), "open": pa.array(h[2]), "high": pa.array(h[3]),
                      "low": pa.array(h[4]), "close": pa.array(h[5]), "volume": pa.array(h[6]), "source_price": pa.array(h[7])})
