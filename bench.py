@@ -1099,10 +1099,15 @@ def bench_dropin(args):
         return min(ts), r
 
     itp = IVInterpolator()
-    timing = {}
-    t_a, res_a = best(lambda: itp.interpolate_batch(frames, timing=timing))
+    splits = []
+
+    def timed_interp():
+        splits.append({})
+        return itp.interpolate_batch(frames, timing=splits[-1])
+    t_a, res_a = best(timed_interp)
     rows = sum(len(r) for r in res_a if r is not None)
-    reps_done = 4
+    timing = min(splits[1:], key=lambda d: sum(d.values()))             # the split of the fastest timed call (the warm-up call left out)
+    reps_done = 1
     out["interpolate_batch"] = {"api": "IVInterpolator.interpolate_batch(frames)", "rows_out": rows, "seconds": round(t_a, 4), "rate": rows / t_a,
                                 "rate_unit": "minute-rows/s", "frames_ok": sum(r is not None for r in res_a),
                                 "split_s": {k: round(v / reps_done, 4) for k, v in timing.items()}}
