@@ -375,6 +375,11 @@ int ivx_gather_f64(int64_t n, const int64_t* idx, int64_t n_src, const double* s
  * kind 1: standard exponential.  This is the reference's normal mode — np.random unseeded (ohlcv_converter.py:213-263,
  * 359-369) — without the host drawing 5 numbers per row; parity runs pass host-drawn numpy tapes instead. */
 int ivx_random_tape(int64_t n, uint64_t seed, uint32_t stream_id, int32_t kind, double* out, ivx_stream_t stream);
+/* n <= 16 int64 values (output sizes of a plan) from device memory to out_host, a plain host array, without the copy engine: a
+ * one-warp kernel stores them into mapped pinned host memory (128 bytes per device, allocated on first use) and the call waits
+ * on an event behind it.  An 8-byte cudaMemcpy would queue behind every bulk device-to-host copy in flight on other streams.
+ * Blocks until the stream has reached this point, like the cudaMemcpy it replaces. */
+int ivx_read_back_i64(int32_t n, const int64_t* src, int64_t* out_host, ivx_stream_t stream);
 int ivx_probe_copy(int64_t n_f64, const double* src, double* dst, ivx_stream_t stream);
 int ivx_probe_fp64_fma(int64_t n_threads, int32_t iters, double* sink, ivx_stream_t stream);
 /* kernel A's store pattern alone (11 fp64 + one int32 + one uint8 stream of n_rows, arrays stride_f64 doubles apart):

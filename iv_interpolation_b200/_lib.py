@@ -85,6 +85,7 @@ SIGNATURES = {
     "ivx_exclusive_scan_i64": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_gather_i64": (C.c_int, [_i64, _p, _i64, _p, _p, _p]),
     "ivx_gather_f64": (C.c_int, [_i64, _p, _i64, _p, _p, _p]),
+    "ivx_read_back_i64": (C.c_int, [_i32, _p, C.POINTER(C.c_int64), _p]),
     "ivx_random_tape": (C.c_int, [_i64, C.c_uint64, C.c_uint32, _i32, _p, _p]),
     "ivx_probe_copy": (C.c_int, [_i64, _p, _p, _p]),
     "ivx_probe_fp64_fma": (C.c_int, [_i64, _i32, _p, _p]),

@@ -40,8 +40,11 @@ class ContractResult:
         """The 5-minute candles as flat columns + the (shard-local) contract each belongs to (for the final gather)."""
         c = self.candles
         n_sym = c.out_off.numel() - 1
+        # output_size: without it torch reads the total back with a cudaMemcpy, which queues behind every bulk device-to-host copy
+        # in flight (HostContractStream calls this right after it has enqueued the batch's drain: the host then waited for the
+        # whole drain, and compute and drain stopped overlapping)
         sym = torch.repeat_interleave(torch.arange(first_contract, first_contract + n_sym, dtype=torch.int32, device=c.ts.device),
-                                      (c.out_off[1:] - c.out_off[:-1]))
+                                      (c.out_off[1:] - c.out_off[:-1]), output_size=int(c.total))
         return {"contract": sym, "timestamp": c.ts, "open": c.open, "high": c.high, "low": c.low, "close": c.close,
                 "volume": c.volume, "count": c.count}
 

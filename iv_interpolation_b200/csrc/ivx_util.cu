@@ -38,10 +38,47 @@ __global__ void __launch_bounds__(256) k_gather(int64_t n, const int64_t* __rest
   out[i] = (k >= 0 && k < n_src) ? __ldg(src + k) : fill;
 }
 
+__global__ void k_store_i64(int n, const int64_t* __restrict__ src, volatile int64_t* dst) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+
 }  // namespace
 }  // namespace ivx
 
 using namespace ivx;
+
+// A few sizes from the device to the host WITHOUT the copy engine: a one-warp kernel stores them into mapped pinned host memory
+// and the host waits on an event.  A cudaMemcpy of 8 bytes queues behind every bulk device-to-host copy already submitted on
+// other streams (the copy queue is first in, first out): in a streaming pipeline the size read-back of batch k+1 then waits for
+// the whole drain of batch k, and compute and drain stop overlapping.
+#include <mutex>
+extern "C" int ivx_read_back_i64(int32_t n, const int64_t* src, int64_t* out_host, ivx_stream_t stream_) {
+  constexpr int CAP = 16;
+  static std::mutex mu;
+  static int64_t* mapped[IVX_MAX_DEVICES] = {};
+  static cudaEvent_t done[IVX_MAX_DEVICES] = {};
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IVX_REQUIRE(n >= 0 && n <= CAP, IVX_ERR_INVALID_ARG, "ivx_read_back_i64: 0 <= n <= %d", CAP);
+  if (n == 0) return IVX_OK;
+  IVX_REQUIRE(src && out_host, IVX_ERR_INVALID_ARG, "ivx_read_back_i64: null pointer");
+  int dev = 0;
+  IVX_CUDA(cudaGetDevice(&dev));
+  IVX_REQUIRE(dev >= 0 && dev < IVX_MAX_DEVICES, IVX_ERR_INVALID_ARG, "ivx_read_back_i64: device %d beyond the table", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!mapped[dev]) {                                     // 128 bytes of mapped pinned memory and one event per device, once
+    IVX_CUDA(cudaHostAlloc((void**)&mapped[dev], CAP * sizeof(int64_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    IVX_CUDA(cudaEventCreateWithFlags(&done[dev], cudaEventDisableTiming));
+  }
+  int64_t* dptr = nullptr;
+  IVX_CUDA(cudaHostGetDevicePointer((void**)&dptr, mapped[dev], 0));
+  k_store_i64<<<1, 32, 0, stream>>>(n, src, dptr);
+  IVX_LAUNCH_CHECK("k_store_i64");
+  IVX_CUDA(cudaEventRecord(done[dev], stream));
+  IVX_CUDA(cudaEventSynchronize(done[dev]));
+  for (int i = 0; i < n; ++i) out_host[i] = mapped[dev][i];
+  return IVX_OK;
+}
 
 extern "C" int ivx_random_tape(int64_t n, uint64_t seed, uint32_t stream_id, int32_t kind, double* out, ivx_stream_t stream) {
   IVX_REQUIRE(n >= 0 && (kind == 0 || kind == 1), IVX_ERR_INVALID_ARG, "ivx_random_tape: n >= 0 and kind in {0 uniform, 1 exponential}");

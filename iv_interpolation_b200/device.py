@@ -54,6 +54,19 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+def read_back(vals: torch.Tensor) -> List[int]:
+    """A few int64 sizes from the device to the host without the copy engine (``ivx_read_back_i64``): an 8-byte ``.item()`` is a
+    cudaMemcpy and queues behind every bulk device-to-host copy in flight on other streams — in a streaming pipeline the plan
+    of batch k+1 then waits for the whole drain of batch k.  Blocks until the current stream has produced ``vals``."""
+    import ctypes
+    n = vals.numel()
+    if vals.dtype != torch.int64 or not vals.is_contiguous():
+        vals = vals.to(torch.int64).contiguous()
+    out = (ctypes.c_int64 * max(1, n))()
+    check(lib().ivx_read_back_i64(n, _ptr(vals), out, _stream()), "ivx_read_back_i64")
+    return [int(out[i]) for i in range(n)]
+
+
 def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
     if t.dtype != dtype:
         raise _lib.IvxError(f"{name}: expected {dtype}, got {t.dtype}")
@@ -128,7 +141,7 @@ def ohlcv_reduce(in_off: torch.Tensor, ts: torch.Tensor, o: torch.Tensor, h: tor
                       sym_group_off)
     res._total_dev = total
     if trim:
-        m = int(total.item())
+        m = read_back(total)[0]
         if m > capacity:
             raise _lib.IvxError(f"ohlcv_reduce: {m} candles exceed the capacity {capacity}")
         res.total = m
@@ -223,7 +236,7 @@ class InterpPlan:
     def total(self) -> int:
         """Rows the batch will emit (reads 8 bytes back from the device the first time)."""
         if self._total is None:
-            self._total = int(self.out_off[-1].item())
+            self._total = read_back(self.out_off[-1:])[0]
         return self._total
 
 
@@ -641,8 +654,8 @@ def bridge_plan(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor) 
                                 _ptr(_req(volume, torch.float64, "volume")), _ptr(seg_out), _ptr(seg_e), _ptr(out_off), _ptr(e_off),
                                 _ptr(ws), wsb, _stream()), "ivx_bridge_plan")
     _count("bridge_plan")
-    totals = torch.stack([out_off[-1], e_off[-1]]).cpu()          # 16 bytes: sizes of the outputs and of the tapes
-    return BridgePlan(out_off, e_off, seg_out, seg_e, int(totals[0]), int(totals[1]))
+    total, total_e = read_back(out_off[-1:])[0], read_back(e_off[-1:])[0]          # sizes of the outputs and of the tapes
+    return BridgePlan(out_off, e_off, seg_out, seg_e, total, total_e)
 
 
 def bridge_ohlcv(in_off: torch.Tensor, base: torch.Tensor, volume: torch.Tensor, plan: BridgePlan, strategy: str, *,

@@ -102,5 +102,5 @@ def gather_tables(local: Dict[str, torch.Tensor], dst: int = 0, group=None) -> O
     if rank != dst:
         return None
     out["_rank"] = torch.repeat_interleave(torch.arange(world, dtype=torch.int32, device=dev),
-                                           torch.tensor(counts, dtype=torch.int64, device=dev))
+                                           torch.tensor(counts, dtype=torch.int64, device=dev), output_size=int(sum(counts)))
     return out
