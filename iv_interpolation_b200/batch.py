@@ -241,13 +241,16 @@ class PipelineBatch:
             err = None
         except Exception as e:
             res, err = [], str(e)
-        if w3 and "frame" in w3 and w3["slots"] == list(range(len(todo))):             # one frame for all: :693-704, :669-671 once
+        if w3 and "frame" in w3:                                                       # one frame for all: :693-704, :669-671 once
             bigc = w3["frame"][["timestamp", "open", "high", "low", "close", "volume", "symbol"]].copy()
             bigc["frequency"] = "5min"
             bigc["source_candles"] = 5
             bigc["batch_id"] = self.batch_id
             c_off, c_ok = w3["off"], w3["ok"]
-            res = [bigc.iloc[int(c_off[k]):int(c_off[k + 1])] if c_ok[k] else None for k in range(len(todo))]
+            res = [None] * len(todo)
+            for k, i in enumerate(w3["slots"]):                                        # slots: the positions in `todo` the offsets stand for
+                if c_ok[k]:
+                    res[i] = bigc.iloc[int(c_off[k]):int(c_off[k + 1])]
             prepared = True
         else:
             prepared = False
