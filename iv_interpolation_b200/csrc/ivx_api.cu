@@ -58,7 +58,7 @@ extern "C" const char* ivx_build_info(void) {
          "k_ohlc_time_major,k_bs_implied_vol,k_bs_implied_vol_ladder,k_bs_implied_vol_chain,k_bs_implied_vol_retry,k_chain_terms,"
          "k_bs_price,k_bs_greeks,k_spline_fit_eval,k_spline_fit_eval_list,k_spline_ladder_factor,k_spline_strided,"
          "k_band_build,k_band_check,k_band_perm,k_band_frag,k_band_apply,k_band_apply_mma,"
-         "k_bridge_count_seg,k_bridge_sym_off,k_bridge_ohlcv_seg,k_bridge_check,k_bridge_ohlcv,k_bridge_quality,k_random_tape,k_gather,k_probe_copy,k_probe_fp64";
+         "k_bridge_count_seg,k_bridge_sym_off,k_bridge_ohlcv_seg,k_bridge_check,k_bridge_ohlcv,k_bridge_quality,k_random_tape,k_gather,k_store_i64,k_probe_copy,k_probe_fp64";
 }
 
 // host-side check of the multiply-high floor division used by the bucket kernels (tests call this)
