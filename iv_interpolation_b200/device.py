@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "ohlcv_reduce": 3, "time_buckets": 1, "ohlc_time_major": 1, "interp_plan": 3, "interp_exec": 1,
     "bs_implied_vol": 1, "bs_implied_vol_2k": 2, "bs_implied_vol_ladder": 2, "bs_price": 1, "bs_greeks": 1, "spline_fit_eval": 1, "spline_strided": 1,
     "spline_strided_batched": 1, "scan": 1, "probe": 1, "bs_implied_vol_chain": 3, "spline_ladder_factor": 1,
-    "spline_band_build": 6, "spline_fit_eval_banded": 2, "spline_fit_eval_banded_mma": 3, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
+    "spline_band_build": 6, "spline_fit_eval_banded": 2, "spline_fit_eval_banded_mma": 3, "bridge_quality": 1, "gather": 1, "random_tape": 1, "bridge_plan": 4, "bridge_ohlcv": 1, "bridge_ohlcv_seg": 3, "read_back": 1,   # plan: count, 2 scans, offsets; segments, check, (idle) fallback
 }
 
 
@@ -64,6 +64,7 @@ def read_back(vals: torch.Tensor) -> List[int]:
         vals = vals.to(torch.int64).contiguous()
     out = (ctypes.c_int64 * max(1, n))()
     check(lib().ivx_read_back_i64(n, _ptr(vals), out, _stream()), "ivx_read_back_i64")
+    _count("read_back")
     return [int(out[i]) for i in range(n)]
 
 
